@@ -1,0 +1,243 @@
+"""ctypes bindings for the TEST-ONLY checkers under oracle/.
+
+  * ``Oracle``  -> oracle/liboracle.so      (plain-C restatement, nvb_oracle.c)
+  * ``Ref``     -> oracle/_ref/libnvbio_ref.so (the unmodified reference templates, ref_shim.cpp)
+
+Both expose the same numpy-level API so tests can pin one against the other.
+This module is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs may import it.  The product never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+GLOBAL, LOCAL, SEMI_GLOBAL = 0, 1, 2   # nvbio/alignment/alignment_base.h:54
+
+
+def _p(a, ty=None):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def seq_words(n):
+    """BWT words, rounded up to whole 64-symbol blocks (4 words) as the loader requires
+    (nvbio/io/fmindex/fmindex_impl.cu:289-303)."""
+    return ((n + 63) // 64) * 4
+
+
+class _Index(dict):
+    __getattr__ = dict.__getitem__
+
+
+class _Base:
+    def _interleave(self, n, bwt, occ, cnt):
+        sw = seq_words(n)
+        bwt_occ = np.zeros(2 * sw, dtype=np.uint32)
+        b = bwt_occ.reshape(-1, 8)
+        b[:, 0:4] = bwt.reshape(-1, 4)
+        b[:, 4:8] = occ.reshape(-1, 4)
+        L2 = np.zeros(5, dtype=np.uint32)
+        L2[1:] = np.cumsum(cnt.astype(np.uint64)).astype(np.uint32)
+        return bwt_occ, L2
+
+
+class Oracle(_Base):
+    kind = "port"
+
+    def __init__(self):
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+        self.lib = C.CDLL(path)
+        self.lib.orc_match.restype = C.c_uint64
+        self.lib.orc_locate.restype = C.c_uint64
+        self.lib.orc_bwt_from_sa.restype = C.c_uint32
+        self.lib.orc_dict_rank.restype = C.c_uint32
+
+    def build_index(self, text):
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        n = len(text)
+        sa = np.zeros(n + 1, dtype=np.int32)
+        self.lib.orc_suffix_array(C.c_uint32(n), _p(text), _p(sa))
+        return self.index_from_sa(text, sa)
+
+    def index_from_sa(self, text, sa):
+        n = len(text)
+        sw = seq_words(n)
+        bwt = np.zeros(sw, dtype=np.uint32)
+        primary = self.lib.orc_bwt_from_sa(C.c_uint32(n), _p(text), _p(sa), _p(bwt), C.c_uint32(sw))
+        occ = np.zeros(sw, dtype=np.uint32)
+        cnt = np.zeros(4, dtype=np.uint32)
+        self.lib.orc_build_occ(C.c_uint32(n), _p(bwt), _p(occ), _p(cnt))
+        bwt_occ = np.zeros(2 * sw, dtype=np.uint32)
+        L2 = np.zeros(5, dtype=np.uint32)
+        self.lib.orc_interleave(C.c_uint32(sw), _p(bwt), _p(occ), _p(cnt), _p(bwt_occ), _p(L2))
+        ssa = np.zeros((n + 16) // 16, dtype=np.uint32)
+        self.lib.orc_build_ssa(C.c_uint32(n), _p(sa), _p(ssa))
+        return _Index(n=n, primary=int(primary), sa=sa, bwt=bwt, occ=occ, bwt_occ=bwt_occ, L2=L2, ssa=ssa)
+
+    def count_table(self):
+        t = np.zeros(256, dtype=np.uint32)
+        self.lib.orc_count_table(_p(t))
+        return t
+
+    def rank(self, idx, k, c):
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        out = np.zeros(len(k), dtype=np.uint32)
+        self.lib.orc_rank(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(idx.n), C.c_uint32(idx.primary),
+                          _p(k), _p(c), C.c_uint32(len(k)), _p(out))
+        return out
+
+    def dict_rank(self, idx, i, c):
+        return np.array([self.lib.orc_dict_rank(_p(idx.bwt_occ), C.c_uint32(int(a)), C.c_uint32(int(b)))
+                         for a, b in zip(i, c)], dtype=np.uint32)
+
+    def match(self, idx, q, off, ln):
+        """returns (ranges[nq,2] inclusive, total 32-byte blocks touched)"""
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        ln = np.ascontiguousarray(ln, dtype=np.uint32)
+        out = np.zeros((len(off), 2), dtype=np.uint32)
+        blocks = self.lib.orc_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(idx.n), C.c_uint32(idx.primary),
+                                    _p(q), _p(off), _p(ln), C.c_uint32(len(off)), _p(out))
+        return out, int(blocks)
+
+    def locate(self, idx, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.zeros(len(rows), dtype=np.uint32)
+        steps = self.lib.orc_locate(_p(idx.bwt_occ), _p(idx.ssa), _p(idx.L2), C.c_uint32(idx.n),
+                                    C.c_uint32(idx.primary), _p(rows), C.c_uint32(len(rows)), _p(out))
+        self.last_locate_steps = int(steps)
+        return out
+
+    def banded_gotoh(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
+        """scheme = (match, mismatch, gap_open, gap_ext) or a 6-tuple
+        (match, mismatch, pattern_gap_open, pattern_gap_ext, text_gap_open, text_gap_ext)."""
+        if len(scheme) == 4:
+            scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+        s = np.array(scheme, dtype=np.int32)
+        pat = np.ascontiguousarray(pat, dtype=np.uint8)
+        txt = np.ascontiguousarray(txt, dtype=np.uint8)
+        p_off = np.ascontiguousarray(p_off, dtype=np.uint32)
+        p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+        t_off = np.ascontiguousarray(t_off, dtype=np.uint32)
+        t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+        n = len(p_off)
+        score = np.zeros(n, dtype=np.int32)
+        sx = np.zeros(n, dtype=np.uint32)
+        sy = np.zeros(n, dtype=np.uint32)
+        ok = np.zeros(n, dtype=np.uint8)
+        if qual is not None:
+            qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        if qtab is not None:
+            qtab = np.ascontiguousarray(qtab, dtype=np.int32)
+        self.lib.orc_banded_gotoh(C.c_int(band), C.c_int(typ), _p(s), _p(qtab),
+                                  _p(pat), _p(qual), _p(p_off), _p(p_len),
+                                  _p(txt), _p(t_off), _p(t_len), C.c_uint32(n),
+                                  _p(score), _p(sx), _p(sy), _p(ok))
+        return score, sx, sy, ok
+
+
+class Ref(_Base):
+    """The reference's own templates (only where oracle/_ref/libnvbio_ref.so exists)."""
+    kind = "reference"
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libnvbio_ref.so"))
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libnvbio_ref.so"))
+        self.lib.ref_build_bwt.restype = C.c_uint32
+        self.lib.ref_num_threads.restype = C.c_int
+
+    def num_threads(self):
+        return int(self.lib.ref_num_threads())
+
+    def set_num_threads(self, t):
+        self.lib.ref_set_num_threads(C.c_int(t))
+
+    def build_index(self, text):
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        n = len(text)
+        sw = seq_words(n)
+        sa = np.zeros(n + 1, dtype=np.int32)
+        bwt = np.zeros(sw, dtype=np.uint32)
+        primary = self.lib.ref_build_bwt(C.c_uint32(n), _p(text), _p(sa), _p(bwt), C.c_uint32(sw))
+        occ = np.zeros(sw, dtype=np.uint32)
+        cnt = np.zeros(4, dtype=np.uint32)
+        self.lib.ref_build_occ(C.c_uint32(n), _p(bwt), _p(occ), _p(cnt))
+        bwt_occ, L2 = self._interleave(n, bwt, occ, cnt)
+        ssa = np.zeros((n + 16) // 16, dtype=np.uint32)
+        self.lib.ref_build_ssa(C.c_uint32(n), _p(sa), _p(ssa))
+        return _Index(n=n, primary=int(primary), sa=sa, bwt=bwt, occ=occ, bwt_occ=bwt_occ, L2=L2, ssa=ssa)
+
+    def count_table(self):
+        t = np.zeros(256, dtype=np.uint32)
+        self.lib.ref_count_table(_p(t))
+        return t
+
+    def rank(self, idx, k, c):
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        out = np.zeros(len(k), dtype=np.uint32)
+        self.lib.ref_rank(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(idx.n), C.c_uint32(idx.primary),
+                          _p(k), _p(c), C.c_uint32(len(k)), _p(out))
+        return out
+
+    def dict_rank(self, idx, i, c):
+        i = np.ascontiguousarray(i, dtype=np.uint32)
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        out = np.zeros(len(i), dtype=np.uint32)
+        self.lib.ref_dict_rank(_p(idx.bwt_occ), _p(i), _p(c), C.c_uint32(len(i)), _p(out))
+        return out
+
+    def match(self, idx, q, off, ln):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        ln = np.ascontiguousarray(ln, dtype=np.uint32)
+        out = np.zeros((len(off), 2), dtype=np.uint32)
+        self.lib.ref_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(idx.n), C.c_uint32(idx.primary),
+                           _p(q), _p(off), _p(ln), C.c_uint32(len(off)), _p(out))
+        return out, None
+
+    def locate(self, idx, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.zeros(len(rows), dtype=np.uint32)
+        self.lib.ref_locate(_p(idx.bwt_occ), _p(idx.ssa), _p(idx.L2), C.c_uint32(idx.n),
+                            C.c_uint32(idx.primary), _p(rows), C.c_uint32(len(rows)), _p(out))
+        return out
+
+    def banded_gotoh(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
+        assert qual is None and qtab is None and len(scheme) == 4, "ref shim instantiates SimpleGotohScheme only"
+        pat = np.ascontiguousarray(pat, dtype=np.uint8)
+        txt = np.ascontiguousarray(txt, dtype=np.uint8)
+        p_off = np.ascontiguousarray(p_off, dtype=np.uint32)
+        p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+        t_off = np.ascontiguousarray(t_off, dtype=np.uint32)
+        t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+        n = len(p_off)
+        score = np.zeros(n, dtype=np.int32)
+        sx = np.zeros(n, dtype=np.uint32)
+        sy = np.zeros(n, dtype=np.uint32)
+        ok = np.zeros(n, dtype=np.uint8)
+        r = self.lib.ref_banded_gotoh(C.c_int(band), C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]),
+                                      C.c_int(scheme[2]), C.c_int(scheme[3]),
+                                      _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len),
+                                      C.c_uint32(n), _p(score), _p(sx), _p(sy), _p(ok))
+        assert r == 0
+        return score, sx, sy, ok
+
+
+def dna(s):
+    """ASCII ACGT(N) -> symbols 0..3 (4)"""
+    lut = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate("ACGT"):
+        lut[ord(ch)] = i
+    return lut[np.frombuffer(s.encode(), dtype=np.uint8)]

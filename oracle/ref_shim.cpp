@@ -1,0 +1,202 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin extern "C" wrappers that instantiate the UNMODIFIED reference templates of
+// NVlabs/nvbio (header-only, found under /root/reference at build time) on the host, so that
+// tests and the CPU baseline can call the reference's own implementation of the two hot paths.
+// Nothing from the reference is copied here: this file only *includes* the reference headers
+// where they lie and calls their public entry points:
+//
+//   nvbio::gen_sa / gen_bwt_from_sa            nvbio/fmindex/bwt.h:38-63
+//   nvbio::build_occurrence_table<2,64>        nvbio/fmindex/rank_dictionary_inl.h:42-77
+//   nvbio::rank / match / locate               nvbio/fmindex/fmindex_inl.h:36-99, 280-341, 471-499
+//   nvbio::SSA_index_multiple<16>              nvbio/fmindex/ssa_inl.h:262-277
+//   nvbio::aln::banded_alignment_score<B>      nvbio/alignment/banded_inl.h:50-73
+//                                              -> gotoh/gotoh_banded_inl.h:406-658
+//
+// Built by oracle/Makefile into oracle/_ref/libnvbio_ref.so (git-ignored; travels to the GPU box).
+// Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it.
+
+#include <nvbio/basic/types.h>
+#include <nvbio/basic/numbers.h>
+#include <nvbio/basic/packedstream.h>
+#include <nvbio/basic/deinterleaved_iterator.h>
+#include <nvbio/basic/vector_view.h>
+#include <nvbio/fmindex/bwt.h>
+#include <nvbio/fmindex/ssa.h>
+#include <nvbio/fmindex/fmindex.h>
+#include <nvbio/alignment/alignment.h>
+#include <nvbio/alignment/utils.h>
+#include <vector>
+#include <climits>
+#include <cstring>
+#include <omp.h>
+
+using namespace nvbio;
+
+namespace {
+
+// production index layout (nvbio/io/fmindex/fmindex.h:302-319) with plain host pointers
+typedef const uint4*                                               bwt_occ_ptr;
+typedef deinterleaved_iterator<2,0,bwt_occ_ptr>                    bwt_iter;
+typedef deinterleaved_iterator<2,1,bwt_occ_ptr>                    occ_iter;
+typedef PackedStream<bwt_iter,uint8,2u,true>                       bwt_stream;
+typedef rank_dictionary<2u,64u,bwt_stream,occ_iter,const uint32*>  rank_dict_t;
+typedef SSA_index_multiple_context<16u,const uint32*>              ssa_ctx_t;
+typedef fm_index<rank_dict_t,ssa_ctx_t>                            fm_index_t;
+
+fm_index_t make_index(const uint32* bwt_occ, const uint32* ssa, const uint32* L2,
+                      const uint32* count_table, uint32 n, uint32 primary)
+{
+    const bwt_occ_ptr p = (const uint4*)bwt_occ;
+    return fm_index_t( n, primary, L2,
+        rank_dict_t( bwt_stream( bwt_iter(p) ), occ_iter(p), count_table ),
+        ssa_ctx_t( ssa ) );
+}
+
+typedef vector_view<const uint8*> str_view;
+
+template <uint32 BAND, aln::AlignmentType TYPE>
+void run_banded(const aln::SimpleGotohScheme scheme,
+                const uint8* pat, const uint32* p_off, const uint32* p_len,
+                const uint8* txt, const uint32* t_off, const uint32* t_len,
+                uint32 n, int32* score, uint32* sink_x, uint32* sink_y, uint8* ok)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        aln::BestSink<int32> sink;
+        const bool r = aln::banded_alignment_score<BAND>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),
+            str_view( p_len[i], pat + p_off[i] ),
+            str_view( t_len[i], txt + t_off[i] ),
+            INT_MIN,
+            sink );
+        score[i]  = sink.score;
+        sink_x[i] = sink.sink.x;
+        sink_y[i] = sink.sink.y;
+        if (ok) ok[i] = r ? 1 : 0;
+    }
+}
+
+template <uint32 BAND>
+int run_banded_type(int type, const aln::SimpleGotohScheme s,
+                const uint8* pat, const uint32* p_off, const uint32* p_len,
+                const uint8* txt, const uint32* t_off, const uint32* t_len,
+                uint32 n, int32* score, uint32* sink_x, uint32* sink_y, uint8* ok)
+{
+    switch (type)
+    {
+    case 0: run_banded<BAND,aln::GLOBAL>     ( s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok ); return 0;
+    case 1: run_banded<BAND,aln::LOCAL>      ( s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok ); return 0;
+    case 2: run_banded<BAND,aln::SEMI_GLOBAL>( s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok ); return 0;
+    }
+    return -1;
+}
+
+} // anonymous namespace
+
+extern "C" {
+
+int ref_num_threads() { return omp_get_max_threads(); }
+void ref_set_num_threads(int t) { omp_set_num_threads(t); }
+
+// text: n unpacked symbols in {0..3}.  Outputs: sa[n+1] (sa[0]=n), bwt words (2-bit big-endian,
+// `bwt_words` uint32 words, caller-zeroed), returns primary.
+uint32 ref_build_bwt(uint32 n, const uint8* text, int32* sa, uint32* bwt, uint32 bwt_words)
+{
+    std::vector<uint32> twords( (n + 15)/16 + 4, 0u );
+    typedef PackedStream<uint32*,uint8,2u,true> stream_t;
+    stream_t T( &twords[0] );
+    for (uint32 i = 0; i < n; ++i) T[i] = text[i];
+
+    gen_sa( n, T, sa );
+    std::memset( bwt, 0, sizeof(uint32)*bwt_words );
+    stream_t B( bwt );
+    return gen_bwt_from_sa( n, T, sa, B );
+}
+
+// occ: ceil(n/64)*4 words; cnt: 4 words
+void ref_build_occ(uint32 n, const uint32* bwt, uint32* occ, uint32* cnt)
+{
+    typedef PackedStream<const uint32*,uint8,2u,true> stream_t;
+    stream_t B( bwt );
+    build_occurrence_table<2u,64u>( B, B + n, occ, cnt );
+}
+
+void ref_count_table(uint32* table) { gen_bwt_count_table( table ); }
+
+// ssa[(n+16)/16] from a full SA (sa[0] = n), then ssa[0] = -1 as the loader does
+// (nvbio/io/fmindex/fmindex_impl.cu:244)
+void ref_build_ssa(uint32 n, const int32* sa, uint32* ssa)
+{
+    SSA_index_multiple<16u> s( n, (const uint32*)sa );
+    const uint32 n_items = (n + 16u)/16u;
+    for (uint32 i = 0; i < n_items; ++i) ssa[i] = s.m_ssa[i];
+    ssa[0] = uint32(-1);
+}
+
+// rank(fmi, k, c) for many (k,c)
+void ref_rank(const uint32* bwt_occ, const uint32* L2, uint32 n, uint32 primary,
+              const uint32* k, const uint8* c, uint32 nq, uint32* out)
+{
+    uint32 ct[256]; gen_bwt_count_table( ct );
+    const fm_index_t fmi = make_index( bwt_occ, NULL, L2, ct, n, primary );
+    for (uint32 i = 0; i < nq; ++i) out[i] = rank( fmi, k[i], c[i] );
+}
+
+// dictionary-level rank over the interleaved layout (no $ correction): rank(dict, i, c)
+void ref_dict_rank(const uint32* bwt_occ, const uint32* idx, const uint8* c, uint32 nq, uint32* out)
+{
+    uint32 ct[256]; gen_bwt_count_table( ct );
+    const bwt_occ_ptr p = (const uint4*)bwt_occ;
+    const rank_dict_t dict( bwt_stream( bwt_iter(p) ), occ_iter(p), ct );
+    for (uint32 i = 0; i < nq; ++i) out[i] = rank( dict, idx[i], uint32(c[i]) );
+}
+
+// match(): queries are unpacked symbols, query i = q[off[i] .. off[i]+len[i]); out = inclusive (x,y)
+void ref_match(const uint32* bwt_occ, const uint32* L2, uint32 n, uint32 primary,
+               const uint8* q, const uint32* off, const uint32* len, uint32 nq, uint32* out_xy)
+{
+    uint32 ct[256]; gen_bwt_count_table( ct );
+    const fm_index_t fmi = make_index( bwt_occ, NULL, L2, ct, n, primary );
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(nq); ++i)
+    {
+        const uint2 r = match( fmi, q + off[i], len[i] );
+        out_xy[2*i+0] = r.x;
+        out_xy[2*i+1] = r.y;
+    }
+}
+
+// locate(): SA rows -> text positions
+void ref_locate(const uint32* bwt_occ, const uint32* ssa, const uint32* L2, uint32 n, uint32 primary,
+                const uint32* rows, uint32 nq, uint32* out)
+{
+    uint32 ct[256]; gen_bwt_count_table( ct );
+    const fm_index_t fmi = make_index( bwt_occ, ssa, L2, ct, n, primary );
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(nq); ++i)
+        out[i] = locate( fmi, rows[i] );
+}
+
+// banded Gotoh score with SimpleGotohScheme(match, mismatch, gap_open, gap_ext).
+// type: 0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL (nvbio/alignment/alignment_base.h:54)
+int ref_banded_gotoh(int band, int type, int match, int mismatch, int gap_open, int gap_ext,
+                     const uint8* pat, const uint32* p_off, const uint32* p_len,
+                     const uint8* txt, const uint32* t_off, const uint32* t_len,
+                     uint32 n, int32* score, uint32* sink_x, uint32* sink_y, uint8* ok)
+{
+    const aln::SimpleGotohScheme s( match, mismatch, gap_open, gap_ext );
+    switch (band)
+    {
+    case  3: return run_banded_type< 3>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
+    case  5: return run_banded_type< 5>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
+    case  7: return run_banded_type< 7>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
+    case 15: return run_banded_type<15>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
+    case 31: return run_banded_type<31>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
+    case 63: return run_banded_type<63>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
+    }
+    return -1;
+}
+
+} // extern "C"

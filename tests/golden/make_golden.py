@@ -1,0 +1,141 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (oracle/_ref/libnvbio_ref.so, i.e. the
+unmodified nvbio templates compiled by oracle/Makefile from /root/reference).
+
+Run in the dev container only (needs /root/reference to have built oracle/_ref):
+    python tests/golden/make_golden.py
+
+The fixtures pin (a) the two banded-Gotoh problems asserted by the reference's own test
+(nvbio-test/alignment_test.cu:761-825), (b) seeded random banded problems for every BAND/TYPE the
+reference instantiates, incl. text symbols > 3 and ragged lengths, (c) a small FM-index
+(SA, BWT, occ, SSA, match ranges, locate results) incl. a repetitive text.
+"""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import orc  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+G1_P = "ACAACTA"
+G1_T = "AAACACCCTAACACACTAAA"
+G2_P = ("TTATGTAGGTGGTCTGGTTTTTGCCTTTTAAGCTTCTGCAAAAAACAACAACAAACTTGTGGTATTACACTGACTCTACAGATCAATTTGGGGACAACTTCC"
+        "ATGTGTTCCACCACCAATACTGAATCTTTCAATCGACTGACGTGGTAT")
+G2_T = ("ATCGGATTCTTTCTTACTTGTAGGTGGTCTGGTTTTTGCCTTTTAAGCTTCTGCAAAAAACAACAACAAACTTGTGGTATTACACTGACTCTACAGATCAA"
+        "TTTGGGGACAACTTCCATGTGTTCCACCACCAATACTGAATCTTTCAATCGACTGACGTGGTATCTCTCTCTCCATCTAT")
+
+
+def random_problems(rng, n, band, max_m, alphabet_text=4, ragged=True):
+    """patterns sampled from their own windows with mutations, so that alignments are non-trivial"""
+    pats, txts, p_off, p_len, t_off, t_len = [], [], [], [], [], []
+    po = to = 0
+    for _ in range(n):
+        m = int(rng.integers(1, max_m + 1)) if ragged else max_m
+        extra = int(rng.integers(0, band + 8))
+        extra = max(extra, band - 1 - m)                       # the reference reads text[0..B-2] unchecked
+        N = m + extra
+        t = rng.integers(0, alphabet_text, size=N).astype(np.uint8)
+        start = int(rng.integers(0, min(extra, band // 2) + 1))
+        p = []
+        j = start
+        while len(p) < m:
+            r = rng.random()
+            if r < 0.05 or j >= N:
+                p.append(int(rng.integers(0, 4)))           # substitution / insertion
+                if r < 0.03:
+                    j += 1
+            elif r < 0.08:
+                j += 1                                         # deletion
+            else:
+                p.append(int(t[j]) & 3)
+                j += 1
+        p = np.array(p[:m], dtype=np.uint8)
+        if alphabet_text > 4 and rng.random() < 0.3:
+            p[int(rng.integers(0, m))] = 4                     # an N in the read
+        pats.append(p); txts.append(t)
+        p_off.append(po); p_len.append(m); po += m
+        t_off.append(to); t_len.append(N); to += N
+    return (np.concatenate(pats), np.array(p_off, np.uint32), np.array(p_len, np.uint32),
+            np.concatenate(txts), np.array(t_off, np.uint32), np.array(t_len, np.uint32))
+
+
+def main():
+    assert orc.Ref.available(), "build oracle/_ref first: make -C oracle"
+    ref = orc.Ref()
+    rng = np.random.default_rng(20240917)
+    out = {}
+
+    # (a) the reference's own asserted problems
+    for name, P, T, scheme, band in (("g1", G1_P, G1_T, (2, -1, -1, -1), 7),
+                                     ("g2", G2_P, G2_T, (0, -5, -8, -3), 31)):
+        p, t = orc.dna(P), orc.dna(T)
+        for typ in (0, 1, 2):
+            s, x, y, ok = ref.banded_gotoh(band, typ, scheme, p, [0], [len(p)], t, [0], [len(t)])
+            out[f"{name}_t{typ}"] = np.array([s[0], x[0], y[0], ok[0]], dtype=np.int64)
+    # (b) random problems
+    cases = []
+    cid = 0
+    for band in (3, 5, 7, 15, 31, 63):
+        for typ in (0, 1, 2):
+            for scheme in ((2, -2, -5, -3), (2, -1, -1, -1), (0, -5, -8, -3), (1, -3, -2, -4)):
+                alpha = 4 if cid % 3 else 6          # every third case has text symbols 4,5 (N-like)
+                pr = random_problems(rng, 24, band, 40 if band < 31 else 160, alphabet_text=alpha)
+                s, x, y, ok = ref.banded_gotoh(band, typ, scheme, *pr)
+                for k, v in zip(("pat", "p_off", "p_len", "txt", "t_off", "t_len"), pr):
+                    out[f"r{cid}_{k}"] = v
+                out[f"r{cid}_res"] = np.stack([s.astype(np.int64), x.astype(np.int64), y.astype(np.int64),
+                                               ok.astype(np.int64)])
+                cases.append((cid, band, typ) + scheme)
+                cid += 1
+    out["cases"] = np.array(cases, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "banded_gotoh.npz"), **out)
+
+    # (c) FM-index fixtures
+    fm = {}
+    texts = {
+        "rand": rng.integers(0, 4, size=5000).astype(np.uint8),
+        "rep": np.tile(np.array([0, 1, 0, 1, 2, 3, 0, 0], np.uint8), 200)[:1531],
+        "allA": np.zeros(257, np.uint8),
+        "tiny": orc.dna("ACGTTGCA"),
+    }
+    for name, text in texts.items():
+        idx = ref.build_index(text)
+        n = len(text)
+        nq = 300
+        lens = rng.integers(1, 24, size=nq).astype(np.uint32)
+        offs = np.zeros(nq, np.uint32)
+        qs = []
+        o = 0
+        for i in range(nq):
+            L = int(lens[i])
+            if i % 4 != 3 and n > L:
+                st = int(rng.integers(0, n - L + 1))
+                q = text[st:st + L].copy()
+            else:
+                q = rng.integers(0, 4, size=L).astype(np.uint8)
+            # NOTE: no N's here: nvbio::match() tests `c > 4` (fmindex_inl.h:329), so a symbol 4 indexes
+            # occ/L2 out of bounds (it segfaults); the N -> (1,0) rule is nvBowtie's match_range
+            # (mapping_inl.h:90) and is pinned by the oracle tests instead.
+            qs.append(q); offs[i] = o; o += L
+        q = np.concatenate(qs)
+        ranges, _ = ref.match(idx, q, offs, lens)
+        rows = rng.integers(0, n + 1, size=400).astype(np.uint32)
+        rows[:3] = (0, idx.primary, n)
+        pos = ref.locate(idx, rows)
+        k = rng.integers(0, n + 1, size=500).astype(np.uint32)
+        k[:3] = (0xFFFFFFFF, n, idx.primary)
+        c = rng.integers(0, 4, size=500).astype(np.uint8)
+        rk = ref.rank(idx, k, c)
+        for key, v in dict(text=text, sa=idx.sa, bwt_occ=idx.bwt_occ, L2=idx.L2, ssa=idx.ssa,
+                           primary=np.array([idx.primary], np.uint32), q=q, q_off=offs, q_len=lens,
+                           ranges=ranges, rows=rows, pos=pos, rank_k=k, rank_c=c, rank_out=rk).items():
+            fm[f"{name}_{key}"] = v
+    fm["count_table"] = ref.count_table()
+    np.savez_compressed(os.path.join(OUT, "fmindex.npz"), **fm)
+    print("wrote", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    main()

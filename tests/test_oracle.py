@@ -1,0 +1,160 @@
+"""Pins the plain-C oracle (oracle/nvb_oracle.c) against
+  (1) golden vectors produced by running the reference itself (tests/golden/make_golden.py),
+  (2) the reference's own templates (oracle/_ref/libnvbio_ref.so) on fresh seeded inputs, when that
+      library is present (dev container, and the GPU box via the travelling prebuilt .so).
+CPU only."""
+import os
+import numpy as np
+import pytest
+from oracle import orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+from tests.golden.make_golden import G1_P, G1_T, G2_P, G2_T, random_problems  # noqa: E402
+
+
+def mask_pad(bwt_occ, n):
+    """zero the BWT symbols at positions >= n (the reference's gen_bwt_from_sa leaves a stale copy of
+    the last symbol at position n, nvbio/fmindex/bwt.h:61; padding never influences rank())"""
+    b = bwt_occ.copy().reshape(-1, 8)
+    w = b[:, :4].reshape(-1).copy()
+    full, rem = n // 16, n % 16
+    if rem:
+        w[full] &= np.uint32((0xFFFFFFFF << (32 - 2 * rem)) & 0xFFFFFFFF)
+        full += 1
+    w[full:] = 0
+    b[:, :4] = w.reshape(-1, 4)
+    return b.reshape(-1)
+
+
+@pytest.fixture(scope="module")
+def O():
+    return orc.Oracle()
+
+
+@pytest.fixture(scope="module")
+def R():
+    if not orc.Ref.available():
+        pytest.skip("oracle/_ref not built")
+    return orc.Ref()
+
+
+def test_reference_asserted_problems(O):
+    """nvbio-test/alignment_test.cu:761-825 (scores/sinks measured by running the reference)"""
+    g = np.load(os.path.join(GOLD, "banded_gotoh.npz"))
+    # the survey's re-derived values
+    assert tuple(g["g1_t2"][:3]) == (10, 10, 7)
+    assert tuple(g["g2_t2"][:3]) == (-11, 165, 150)
+    assert tuple(g["g1_t0"][:3]) == (5, 13, 7)
+    for name, P, T, scheme, band in (("g1", G1_P, G1_T, (2, -1, -1, -1), 7),
+                                     ("g2", G2_P, G2_T, (0, -5, -8, -3), 31)):
+        p, t = orc.dna(P), orc.dna(T)
+        for typ in (0, 1, 2):
+            s, x, y, ok = O.banded_gotoh(band, typ, scheme, p, [0], [len(p)], t, [0], [len(t)])
+            assert (int(s[0]), int(x[0]), int(y[0]), int(ok[0])) == tuple(int(v) for v in g[f"{name}_t{typ}"])
+
+
+def test_banded_golden_random(O):
+    g = np.load(os.path.join(GOLD, "banded_gotoh.npz"))
+    for cid, band, typ, m, mm, go, ge in g["cases"]:
+        pr = [g[f"r{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        s, x, y, ok = O.banded_gotoh(int(band), int(typ), (int(m), int(mm), int(go), int(ge)), *pr)
+        res = g[f"r{cid}_res"]
+        assert np.array_equal(s.astype(np.int64), res[0]), (cid, band, typ)
+        assert np.array_equal(x.astype(np.int64), res[1]), (cid, band, typ)
+        assert np.array_equal(y.astype(np.int64), res[2]), (cid, band, typ)
+        assert np.array_equal(ok.astype(np.int64), res[3])
+
+
+def test_fm_golden(O):
+    g = np.load(os.path.join(GOLD, "fmindex.npz"))
+    assert np.array_equal(O.count_table(), g["count_table"])
+    assert g["count_table"][0b00100001] == 0x00010102          # nvbio/fmindex/bwt.h:83
+    for name in ("rand", "rep", "allA", "tiny"):
+        text = g[f"{name}_text"]
+        idx = O.build_index(text)
+        assert np.array_equal(idx.sa, g[f"{name}_sa"]), name
+        assert idx.primary == int(g[f"{name}_primary"][0])
+        assert np.array_equal(mask_pad(idx.bwt_occ, idx.n), mask_pad(g[f"{name}_bwt_occ"], idx.n))
+        assert np.array_equal(idx.L2, g[f"{name}_L2"])
+        assert np.array_equal(idx.ssa, g[f"{name}_ssa"])
+        r, blocks = O.match(idx, g[f"{name}_q"], g[f"{name}_q_off"], g[f"{name}_q_len"])
+        assert np.array_equal(r, g[f"{name}_ranges"]), name
+        assert np.array_equal(O.locate(idx, g[f"{name}_rows"]), g[f"{name}_pos"])
+        assert np.array_equal(O.rank(idx, g[f"{name}_rank_k"], g[f"{name}_rank_c"]), g[f"{name}_rank_out"])
+
+
+def test_match_N_rule(O):
+    """nvBowtie's match_range: any symbol > 3 -> empty range (1,0) (mapping_inl.h:90)"""
+    text = np.random.default_rng(1).integers(0, 4, 300).astype(np.uint8)
+    idx = O.build_index(text)
+    q = np.array([0, 1, 4, 2], np.uint8)
+    r, _ = O.match(idx, q, [0], [4])
+    assert tuple(r[0]) == (1, 0)
+
+
+def test_rank_property(O):
+    """rank_test.cu:55-86: rank(dict,i,c) == running count, every (i,c)"""
+    rng = np.random.default_rng(7)
+    text = rng.integers(0, 4, 1000).astype(np.uint8)
+    idx = O.build_index(text)
+    # unpack the BWT back from the interleaved blocks
+    blk = idx.bwt_occ.reshape(-1, 8)[:, :4].reshape(-1)
+    bwt = np.array([(int(blk[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(idx.n)])
+    for c in range(4):
+        run = np.cumsum(bwt == c)
+        got = O.dict_rank(idx, np.arange(idx.n), np.full(idx.n, c))
+        assert np.array_equal(got, run)
+
+
+def test_locate_property(O):
+    """fmindex_test.cu:611-664: text[locate(match(p))..] == p"""
+    rng = np.random.default_rng(11)
+    text = rng.integers(0, 4, 3000).astype(np.uint8)
+    idx = O.build_index(text)
+    for _ in range(50):
+        L = int(rng.integers(4, 12)); st = int(rng.integers(0, 3000 - L))
+        p = text[st:st + L]
+        r, _ = O.match(idx, p, [0], [L])
+        x, y = int(r[0, 0]), int(r[0, 1])
+        assert x <= y
+        pos = O.locate(idx, np.arange(x, y + 1))
+        assert st in pos
+        for q in pos:
+            assert np.array_equal(text[q:q + L], p)
+        assert np.array_equal(np.sort(pos), np.sort(idx.sa[x:y + 1]).astype(np.uint32))
+
+
+def test_oracle_vs_reference_fresh(O, R):
+    rng = np.random.default_rng(99)
+    for n in (1, 2, 63, 64, 65, 1000, 20000):
+        text = rng.integers(0, 4, n).astype(np.uint8)
+        a, b = O.build_index(text), R.build_index(text)
+        for k in ("sa", "L2", "ssa"):
+            assert np.array_equal(a[k], b[k]), (n, k)
+        assert np.array_equal(mask_pad(a.bwt_occ, n), mask_pad(b.bwt_occ, n)), n
+        assert a.primary == b.primary
+        nq = 500
+        lens = rng.integers(1, 26, nq).astype(np.uint32)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+        q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
+        for i in range(0, nq, 2):                      # half of them sampled from the text
+            L = int(lens[i])
+            if n > L:
+                st = int(rng.integers(0, n - L + 1)); q[offs[i]:offs[i] + L] = text[st:st + L]
+        ra, _ = O.match(a, q, offs, lens)
+        rb, _ = R.match(b, q, offs, lens)
+        assert np.array_equal(ra, rb), n
+        rows = rng.integers(0, n + 1, 300).astype(np.uint32)
+        assert np.array_equal(O.locate(a, rows), R.locate(b, rows))
+
+
+def test_banded_vs_reference_fresh(O, R):
+    rng = np.random.default_rng(5)
+    for band in (3, 7, 15, 31):
+        for typ in (0, 1, 2):
+            scheme = tuple(int(v) for v in (rng.integers(0, 4), -rng.integers(1, 7), -rng.integers(1, 9), -rng.integers(1, 5)))
+            pr = random_problems(rng, 64, band, 150, alphabet_text=5)
+            a = O.banded_gotoh(band, typ, scheme, *pr)
+            b = R.banded_gotoh(band, typ, scheme, *pr)
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v), (band, typ, scheme)
