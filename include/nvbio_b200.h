@@ -1,0 +1,205 @@
+/* nvbio_b200.h -- C ABI of the B200-native replacement for nvbio's two data-parallel hot paths.
+ *
+ * Plain C: pointers, sizes, PODs.  No torch / thrust / nvbio types in any signature.
+ * All `d_` pointers are DEVICE memory owned by the caller; all calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream) unless stated otherwise.
+ * Return value: 0 on success, a positive cudaError_t value, or a negative NVB_E_* code.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the nvbio tree).
+ * INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef NVBIO_B200_H
+#define NVBIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVB_VERSION 100
+
+/* error codes (negative; positive values are cudaError_t) */
+#define NVB_OK              0
+#define NVB_E_INVALID      -1   /* bad argument (unsupported band length, bits, NULL pointer, ...) */
+#define NVB_E_TEMP_SIZE    -2   /* temp buffer too small: *temp_bytes holds the required size */
+#define NVB_E_CAPACITY     -3   /* an output buffer capacity would be exceeded */
+#define NVB_E_UNSUPPORTED  -4   /* valid request that this build does not implement */
+
+typedef struct nvb_uint2 { uint32_t x, y; } nvb_uint2;
+
+/* ---------------------------------------------------------------------------------------------
+ * Data views
+ * ------------------------------------------------------------------------------------------- */
+
+/* FM-index in the reference's production layout (nvbio/io/fmindex/fmindex.h:302-319,
+ * nvbio/io/fmindex/fmindex_impl.cu:308-322): block k = 32 bytes at byte offset 32k =
+ * { uint4 bwt = 64 symbols, 2-bit big-endian ; uint4 occ = #A,#C,#G,#T in bwt[0,64k) }.
+ * Mirrors nvbio::fm_index<rank_dictionary<2,64,...>, SSA_index_multiple_context<16>>
+ * (nvbio/fmindex/fmindex.h:341-387): {m_length, m_primary, m_L2, m_rank_dict, m_sa}. */
+typedef struct nvb_fm_index {
+    const void*     d_bwt_occ;   /* ceil(length/64) blocks of 32 bytes, 32-byte aligned            */
+    const uint32_t* d_ssa;       /* (length+16)/16 words: SA[r] for r%16==0, ssa[0]=0xFFFFFFFF; may
+                                    be NULL when only rank/match are used                          */
+    uint32_t        length;      /* text length n (number of BWT symbols)                          */
+    uint32_t        primary;     /* row of the `$` suffix                                          */
+    uint32_t        L2[5];       /* exclusive prefix sums of the symbol counts                     */
+} nvb_fm_index;
+
+/* A set of strings stored in one packed symbol stream (nvbio PackedStream semantics,
+ * nvbio/basic/packedstream_inl.h:336-372): `bits` per symbol in {2,4,8}; big_endian = symbol 0 of a
+ * word sits in its TOP bits (nvbio's BIG_ENDIAN_T).  String i spans symbols
+ * [off_i, off_i+len_i) of the stream, with
+ *     off_i = d_offsets ? d_offsets[i] : i * stride,   len_i = d_lengths ? d_lengths[i] : length.
+ * This covers ConcatenatedStringSet / SparseStringSet / fixed-stride sets over a packed stream
+ * (nvbio/strings/string_set.h) and the infix sets built by extract_seeds (nvbio/strings/seeds.h). */
+typedef struct nvb_string_set {
+    const uint32_t* d_words;
+    uint32_t        bits;
+    uint32_t        big_endian;
+    const uint32_t* d_offsets;
+    const uint32_t* d_lengths;
+    uint32_t        stride;
+    uint32_t        length;
+} nvb_string_set;
+
+/* alignment type, values of nvbio::aln::AlignmentType (nvbio/alignment/alignment_base.h:54) */
+#define NVB_GLOBAL      0
+#define NVB_LOCAL       1
+#define NVB_SEMI_GLOBAL 2
+
+/* Gotoh scoring scheme.  With d_qual_table == NULL this is aln::SimpleGotohScheme
+ * (nvbio/alignment/utils.h:114-135: substitution = r==q ? match : mismatch).  With a table it is
+ * nvBowtie's SmithWatermanScoringScheme<QualCost,ConstantCost>::substitution
+ * (nvBowtie/bowtie2/cuda/scoring.h:281): r==q ? table[2*qual] : table[2*qual+1]; the caller evaluates
+ * the reference's float expression (scoring.h:96-100) on the host into the 256x2 int32 table so that
+ * fast-math differences cannot leak in.  All gap costs are negative. */
+typedef struct nvb_gotoh_scheme {
+    int32_t        match, mismatch;
+    int32_t        pattern_gap_open, pattern_gap_ext;
+    int32_t        text_gap_open, text_gap_ext;
+    const int32_t* d_qual_table;     /* device, 512 int32, or NULL */
+} nvb_gotoh_scheme;
+
+int         nvb_version(void);
+const char* nvb_error_string(int err);
+
+/* ---------------------------------------------------------------------------------------------
+ * HP-A  FM-index
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[i] = rank(fmi, k[i], c[i]) : occurrences of c in bwt rows [0,k], `$`-aware.
+ * Replaces nvbio::rank(fm_index,k,c)  (nvbio/fmindex/fmindex_inl.h:36-57 ->
+ * rank_dictionary_inl.h:500-511 dispatch_rank<2,64,...,uint4,uint4>::run). */
+int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c, uint32_t n,
+                uint32_t* d_out, void* stream);
+
+#define NVB_MATCH_FORWARD_ORDER 1u  /* consume the query left-to-right instead of right-to-left   */
+#define NVB_MATCH_COMPLEMENT    2u  /* complement each symbol (c<4 ? 3-c : c) before ranking      */
+/* FORWARD_ORDER|COMPLEMENT is how nvBowtie searches the reverse-complement strand of a seed over the
+ * forward index (nvBowtie/bowtie2/cuda/mapping_inl.h:292-309). */
+
+/* Exact backward search of n queries: d_ranges[i] = inclusive SA range (x,y), empty iff x>y;
+ * a query symbol > 3 yields (1,0).
+ * Replaces nvbio::match(fm_index,pattern,len) (nvbio/fmindex/fmindex_inl.h:280-341), nvBowtie's
+ * match_range (nvBowtie/bowtie2/cuda/mapping_inl.h:83-97) and the thrust::transform(rank_functor) of
+ * FMIndexFilter::rank (nvbio/fmindex/filter_inl.h:283-287). */
+int nvb_fm_match(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
+                 nvb_uint2* d_ranges, void* stream);
+
+/* d_pos[i] = text position of SA row d_rows[i]  (row 0 -> 0xFFFFFFFF as in the reference).
+ * Replaces nvbio::locate(fm_index,i) (nvbio/fmindex/fmindex_inl.h:471-499) with
+ * SSA_index_multiple_context<16>::fetch (nvbio/fmindex/ssa_inl.h:487-504). */
+int nvb_fm_locate(const nvb_fm_index* fmi, const uint32_t* d_rows, uint32_t n, uint32_t* d_pos, void* stream);
+
+/* FMIndexFilter<device_tag>::rank (nvbio/fmindex/filter_inl.h:268-300): match every query, then
+ * d_slots = inclusive scan of the range sizes (uint64).  The total hit count is d_slots[n-1]; if
+ * h_n_hits != NULL the call synchronises the stream and stores it there (the reference returns it). */
+int nvb_fm_filter_rank(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
+                       nvb_uint2* d_ranges, uint64_t* d_slots, uint64_t* h_n_hits,
+                       void* d_temp, size_t* temp_bytes, void* stream);
+
+/* FMIndexFilter<device_tag>::locate(begin,end,hits) (nvbio/fmindex/filter_inl.h:306-402):
+ * for global hit index h in [begin,end): d_hits[h-begin] = (text position, query id). */
+int nvb_fm_filter_locate(const nvb_fm_index* fmi, const nvb_uint2* d_ranges, const uint64_t* d_slots,
+                         uint32_t n_queries, uint64_t begin, uint64_t end, nvb_uint2* d_hits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HP-B  batched banded Gotoh score
+ * ------------------------------------------------------------------------------------------- */
+
+/* For i < n: banded DP of patterns[i] (rows) against texts[i] (band anchored at text offset 0),
+ * d_score[i] / d_sink[i] = BestSink<int32>{score, sink=(text_end, pattern_end)}; an alignment with
+ * text_len < pattern_len leaves the sink at its defaults (INT_MIN, (-1,-1)).
+ * band_len in {3,5,7,15,31,63}.  d_quals (one byte per pattern symbol, indexed like the pattern
+ * stream) may be NULL (trivial_quality_string).
+ * Replaces aln::BatchedBandedAlignmentScore<BAND_LEN,stream,DeviceThreadScheduler>::enact and
+ * aln::batch_banded_alignment_score<BAND_LEN> with GotohAligner (nvbio/alignment/batched_banded_inl.h:
+ * 78-162, nvbio/alignment/batched_inl.h:1067-1101 -> gotoh/gotoh_banded_inl.h:406-658).
+ * Temp storage follows the reference's min_temp_storage/enact(temp_size,temp) convention
+ * (nvbio/alignment/batched.h:333-353): call with d_temp==NULL to query *temp_bytes. */
+int nvb_banded_gotoh_score(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                           const nvb_string_set* patterns, const uint8_t* d_quals,
+                           const nvb_string_set* texts, uint32_t n,
+                           int32_t* d_score, nvb_uint2* d_sink,
+                           void* d_temp, size_t* temp_bytes, void* stream);
+
+/* same, reading the number of alignments from device memory (*d_n <= n_max): lets a pipeline chain
+ * locate -> extend without a host round trip. */
+int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                           const nvb_string_set* patterns, const uint8_t* d_quals,
+                           const nvb_string_set* texts, const uint32_t* d_n, uint32_t n_max,
+                           int32_t* d_score, nvb_uint2* d_sink,
+                           void* d_temp, size_t* temp_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index construction on the device (needed to run any of the above on synthetic data)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Build occ + interleave: d_bwt holds n 2-bit big-endian BWT symbols (ceil(n/64)*4 words, padding
+ * ignored); writes ceil(n/64) 32-byte blocks to d_bwt_occ and the L2 table to h_L2 (synchronises).
+ * Replaces nvbio::build_occurrence_table<2,64> + the interleave loop
+ * (nvbio/fmindex/rank_dictionary_inl.h:42-77, nvbio/io/fmindex/fmindex_impl.cu:263-331). */
+int nvb_fm_build_occ(const uint32_t* d_bwt, uint32_t n, void* d_bwt_occ, uint32_t h_L2[5],
+                     void* d_temp, size_t* temp_bytes, void* stream);
+
+/* Suffix-sort a 2-bit big-endian packed text of n symbols on the device and emit the BWT (nvbio
+ * convention: `$` row removed, nvbio/fmindex/bwt.h:51-63), the primary row, the sampled SA
+ * (every 16th row, ssa[0]=0xFFFFFFFF) and optionally the full SA (n+1 entries, d_sa may be NULL).
+ * d_bwt must hold ceil(n/64)*4 words, d_ssa (n+16)/16 words.  Synchronises. */
+int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n, uint32_t* d_bwt, uint32_t* h_primary,
+                     uint32_t* d_ssa, uint32_t* d_sa, void* d_temp, size_t* temp_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Seed + extend composition (the fmmap / nvBowtie hot loop: seeds -> match -> locate -> window ->
+ * banded Gotoh -> best score per read; nvbio examples/fmmap/fmmap.cu:255-400)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nvb_seed_extend_params {
+    uint32_t seed_len;        /* 20 (nvBowtie local) / 22 (fmmap)                                    */
+    uint32_t seed_interval;   /* 10 for 150 bp: int(1 + 0.75*sqrtf(150)) evaluated on the host        */
+    uint32_t band_len;        /* 31 */
+    uint32_t type;            /* NVB_LOCAL */
+    uint32_t both_strands;    /* 1: also seed/extend the reverse complement of every read           */
+    uint32_t max_seed_hits;   /* ranges wider than this contribute only their first max_seed_hits rows */
+    nvb_gotoh_scheme scheme;
+} nvb_seed_extend_params;
+
+/* reads: n_reads strings (2- or 4-bit).  genome: 2-bit big-endian packed text of fmi->length symbols.
+ * Outputs: d_best_score[n_reads] (INT_MIN when a read has no hit), d_best_pos[n_reads] = genome
+ * coordinate of the best alignment's end (window begin + sink.x; 0xFFFFFFFF when none).
+ * Optional per-hit outputs (may be NULL) of capacity hit_capacity: d_hit_read, d_hit_window (begin,end),
+ * d_hit_score, d_hit_sink; *d_n_hits receives the number of hits (device counter).
+ * Returns NVB_E_TEMP_SIZE with the needed size when d_temp is NULL/too small. */
+int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_reads,
+                    const nvb_seed_extend_params* params, uint32_t hit_capacity,
+                    int32_t* d_best_score, uint32_t* d_best_pos,
+                    uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
+                    int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    void* d_temp, size_t* temp_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVBIO_B200_H */

@@ -1,0 +1,63 @@
+"""ctypes loader for the in-tree CUDA library.  There is NO fallback: if the library is missing or
+does not load, every entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnvbio_b200.so")
+
+EXPORTS = [
+    "nvb_version", "nvb_error_string",
+    "nvb_fm_rank", "nvb_fm_match", "nvb_fm_locate", "nvb_fm_filter_rank", "nvb_fm_filter_locate",
+    "nvb_banded_gotoh_score", "nvb_banded_gotoh_score_indirect",
+    "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_seed_extend",
+]
+
+
+class NvbError(RuntimeError):
+    pass
+
+
+class FmIndexStruct(C.Structure):          # nvb_fm_index
+    _fields_ = [("d_bwt_occ", C.c_void_p), ("d_ssa", C.c_void_p), ("length", C.c_uint32),
+                ("primary", C.c_uint32), ("L2", C.c_uint32 * 5)]
+
+
+class StringSetStruct(C.Structure):        # nvb_string_set
+    _fields_ = [("d_words", C.c_void_p), ("bits", C.c_uint32), ("big_endian", C.c_uint32),
+                ("d_offsets", C.c_void_p), ("d_lengths", C.c_void_p), ("stride", C.c_uint32),
+                ("length", C.c_uint32)]
+
+
+class GotohSchemeStruct(C.Structure):      # nvb_gotoh_scheme
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("pattern_gap_open", C.c_int32),
+                ("pattern_gap_ext", C.c_int32), ("text_gap_open", C.c_int32), ("text_gap_ext", C.c_int32),
+                ("d_qual_table", C.c_void_p)]
+
+
+class SeedExtendParamsStruct(C.Structure):  # nvb_seed_extend_params
+    _fields_ = [("seed_len", C.c_uint32), ("seed_interval", C.c_uint32), ("band_len", C.c_uint32),
+                ("type", C.c_uint32), ("both_strands", C.c_uint32), ("max_seed_hits", C.c_uint32),
+                ("scheme", GotohSchemeStruct)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NvbError("nvbio_b200: %s is missing -- run `python -m nvbio_b200.build` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.nvb_error_string.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(_lib, name)            # raises AttributeError if a symbol is not exported
+    return _lib
+
+
+def check(err, what=""):
+    if err != 0:
+        msg = lib().nvb_error_string(C.c_int(err)).decode()
+        raise NvbError("%s failed: %s (%d)" % (what or "nvbio_b200 call", msg, err))

@@ -1,0 +1,112 @@
+"""Host-side mirror of nvbio::aln for the banded Gotoh scoring path (nvbio/alignment/alignment_base.h,
+utils.h, batched.h) over the C ABI."""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+import numpy as np
+import torch
+from ._lib import lib, check, GotohSchemeStruct
+from .strings import PackedStringSet
+
+GLOBAL, LOCAL, SEMI_GLOBAL = 0, 1, 2        # aln::AlignmentType (alignment_base.h:54)
+
+
+@dataclass
+class SimpleGotohScheme:
+    """aln::SimpleGotohScheme(match, mismatch, gap_open, gap_ext) (nvbio/alignment/utils.h:114-135)"""
+    match: int
+    mismatch: int
+    gap_open: int
+    gap_ext: int
+
+    def struct(self) -> GotohSchemeStruct:
+        s = GotohSchemeStruct()
+        s.match, s.mismatch = self.match, self.mismatch
+        s.pattern_gap_open = s.text_gap_open = self.gap_open
+        s.pattern_gap_ext = s.text_gap_ext = self.gap_ext
+        s.d_qual_table = None
+        return s
+
+
+class QualityGotohScheme:
+    """nvBowtie's SmithWatermanScoringScheme<QualCost,ConstantCost> seen through the Gotoh interface
+    (nvBowtie/bowtie2/cuda/scoring.h:203-317): substitution = r==q ? match(q) : -mmp(q).  The float
+    expression of QualCost (scoring.h:96-100) is evaluated HERE, on the host, in float32 exactly as
+    written, and shipped as a 256x2 int32 table."""
+
+    def __init__(self, match_bonus: int, mm_min: int, mm_max: int, read_gap_const: int, read_gap_coeff: int,
+                 ref_gap_const: int, ref_gap_coeff: int, device="cuda"):
+        q = np.arange(256)
+        frac = (np.minimum(q, 40).astype(np.float32) / np.float32(40.0)).astype(np.float32)
+        mmp = mm_min + (frac * np.float32(mm_max - mm_min)).astype(np.int32)
+        tab = np.stack([np.full(256, match_bonus, dtype=np.int32), (-mmp).astype(np.int32)], axis=1)
+        self.table_host = np.ascontiguousarray(tab)
+        self.table = torch.from_numpy(self.table_host).to(device)
+        self.pgo, self.pge = -read_gap_const - read_gap_coeff, -read_gap_coeff
+        self.tgo, self.tge = -ref_gap_const - ref_gap_coeff, -ref_gap_coeff
+        self.match_bonus = match_bonus
+
+    def struct(self) -> GotohSchemeStruct:
+        s = GotohSchemeStruct()
+        s.match, s.mismatch = self.match_bonus, int(self.table_host[0, 1])
+        s.pattern_gap_open, s.pattern_gap_ext = self.pgo, self.pge
+        s.text_gap_open, s.text_gap_ext = self.tgo, self.tge
+        s.d_qual_table = self.table.data_ptr()
+        return s
+
+
+@dataclass
+class GotohAligner:
+    """aln::GotohAligner<TYPE, scheme> / make_gotoh_aligner<TYPE>(scheme) (alignment_base.h:255-298)"""
+    type: int
+    scheme: object
+
+
+def make_gotoh_aligner(type: int, scheme) -> GotohAligner:
+    return GotohAligner(type, scheme)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def batch_banded_alignment_score(band_len: int, aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet,
+                                 quals: Optional[torch.Tensor] = None,
+                                 out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                                 temp: Optional[torch.Tensor] = None):
+    """aln::batch_banded_alignment_score<BAND_LEN>(aligner, patterns, texts, sinks, DeviceThreadScheduler(), ...)
+    (nvbio/alignment/batched_inl.h:1067-1101).  Returns (scores int32[n], sinks int32[n,2]) = BestSink<int32>."""
+    L = lib()
+    n = patterns.count
+    assert texts.count == n
+    dev = patterns.words.device
+    if out is None:
+        out = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.int32, device=dev))
+    score, sink = out
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    qp = C.c_void_p(quals.data_ptr()) if quals is not None else None
+    tb = C.c_size_t(0 if temp is None else temp.numel())
+    if temp is None:
+        r = L.nvb_banded_gotoh_score(C.c_int(band_len), C.c_int(aligner.type), C.byref(sch), C.byref(p), qp, C.byref(t),
+                                     C.c_uint32(n), C.c_void_p(score.data_ptr()), C.c_void_p(sink.data_ptr()),
+                                     None, C.byref(tb), _stream())
+        if r != -2:
+            check(r, "nvb_banded_gotoh_score(size query)")
+        temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
+    check(L.nvb_banded_gotoh_score(C.c_int(band_len), C.c_int(aligner.type), C.byref(sch), C.byref(p), qp, C.byref(t),
+                                   C.c_uint32(n), C.c_void_p(score.data_ptr()), C.c_void_p(sink.data_ptr()),
+                                   C.c_void_p(temp.data_ptr()), C.byref(tb), _stream()), "nvb_banded_gotoh_score")
+    return score, sink
+
+
+def banded_temp_bytes(band_len, aligner, patterns, texts) -> int:
+    L = lib()
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    tb = C.c_size_t(0)
+    r = L.nvb_banded_gotoh_score(C.c_int(band_len), C.c_int(aligner.type), C.byref(sch), C.byref(p), None, C.byref(t),
+                                 C.c_uint32(patterns.count), None, None, None, C.byref(tb), _stream())
+    if r not in (0, -2):
+        check(r, "nvb_banded_gotoh_score(size query)")
+    return int(tb.value)

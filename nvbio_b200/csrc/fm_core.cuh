@@ -1,0 +1,187 @@
+// fm_core.cuh -- per-thread FM-index primitives over the interleaved {bwt,occ} 32-byte blocks.
+//
+// Behaviour follows nvbio (paths relative to the reference tree):
+//   rank_dictionary_inl.h:424-538   dispatch_rank<2,64,PackedStream<...,2,true>,...,uint4,uint4>
+//   popcount_inl.h:239-247,327-350  popc_2bit / truncated popc_2bit
+//   fmindex_inl.h:36-99             `$`-aware rank(fmi,k,c) / rank(fmi,range,c)
+//   fmindex_inl.h:307-341           match();   mapping_inl.h:83-97 match_range (N -> (1,0))
+//   fmindex_inl.h:471-499           locate();  ssa_inl.h:487-504 SSA_index_multiple_context<16>
+// The code is a fresh formulation: one 256-bit load per block (LDG.E.ENL2.256 on sm_100a), a
+// branch-free prefix popcount over the four BWT words, and a uniform treatment of the reference's
+// special cases (k==-1, k==length, primary shift), which are all pure functions of (k,c).
+#pragma once
+#include "common.cuh"
+
+namespace nvb {
+
+struct __align__(32) FmBlock {
+    uint32_t bwt[4];   // 64 symbols, 2-bit big-endian: symbol s of word q at bits [31-2s, 30-2s]
+    uint32_t occ[4];   // #A,#C,#G,#T in bwt[0, 64k)
+};
+
+struct FmIndex {
+    const FmBlock*  blocks;
+    const uint32_t* ssa;
+    uint32_t n, primary;
+    uint32_t L2[5];
+    // constant-index selects keep the struct in the kernel-parameter constant bank (a dynamic L2[c]
+    // would force a local-memory copy of the whole struct)
+    __host__ __device__ __forceinline__ uint32_t l2(uint32_t c) const {
+        return (c == 0) ? L2[0] : (c == 1) ? L2[1] : (c == 2) ? L2[2] : L2[3];
+    }
+    __host__ __device__ __forceinline__ uint32_t count(uint32_t c) const {
+        return (c == 0) ? L2[1] - L2[0] : (c == 1) ? L2[2] - L2[1] : (c == 2) ? L2[3] - L2[2] : L2[4] - L2[3];
+    }
+};
+
+static inline FmIndex make_fmindex(const nvb_fm_index* f) {
+    FmIndex r;
+    r.blocks = (const FmBlock*)f->d_bwt_occ; r.ssa = f->d_ssa; r.n = f->length; r.primary = f->primary;
+    for (int i = 0; i < 5; ++i) r.L2[i] = f->L2[i];
+    return r;
+}
+
+__host__ __device__ __forceinline__ uint32_t nvb_popc(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+__host__ __device__ __forceinline__ FmBlock load_block(const FmBlock* __restrict__ blocks, uint32_t k) {
+#ifdef __CUDA_ARCH__
+    // one 256-bit read-only load (SASS: LDG.E.ENL2.256.CONSTANT); volatile keeps paired loads adjacent
+    FmBlock b;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(b.bwt[0]), "=r"(b.bwt[1]), "=r"(b.bwt[2]), "=r"(b.bwt[3]),
+                   "=r"(b.occ[0]), "=r"(b.occ[1]), "=r"(b.occ[2]), "=r"(b.occ[3])
+                 : "l"(blocks + k));
+    return b;
+#else
+    return blocks[k];
+#endif
+}
+// b = blocks[k] if pred (else b is left untouched); issued right behind a preceding load_block so that
+// both gathers of an LF step are in flight together
+__host__ __device__ __forceinline__ void load_block_if(FmBlock& b, const FmBlock* __restrict__ blocks, uint32_t k, bool pred) {
+#ifdef __CUDA_ARCH__
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
+                 "@p ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 : "+r"(b.bwt[0]), "+r"(b.bwt[1]), "+r"(b.bwt[2]), "+r"(b.bwt[3]),
+                   "+r"(b.occ[0]), "+r"(b.occ[1]), "+r"(b.occ[2]), "+r"(b.occ[3])
+                 : "l"(blocks + k), "r"((uint32_t)pred));
+#else
+    if (pred) b = blocks[k];
+#endif
+}
+
+// one-hot flags (at bit 30-2s) of the symbols of w equal to c
+__host__ __device__ __forceinline__ uint32_t eq_flags(uint32_t w, uint32_t pat) {
+    const uint32_t d = w ^ pat;
+    return ~(d | (d >> 1)) & 0x55555555u;
+}
+
+// occurrences of c among symbols [0, r] (r in 0..63) of the block, plus the block's base counter:
+// = rank(dict, 64k + r, c)
+__host__ __device__ __forceinline__ uint32_t block_rank(const FmBlock& b, uint32_t r, uint32_t c) {
+    const uint32_t pat = c * 0x55555555u;
+    const uint32_t nsym = r + 1;                              // 1..64 symbols to keep
+    uint32_t cnt = (c == 0) ? b.occ[0] : (c == 1) ? b.occ[1] : (c == 2) ? b.occ[2] : b.occ[3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        // symbols of word q to keep: clamp(nsym - 16q, 0, 16), counted from the top of the word
+        const int keep = (int)nsym - 16 * q;
+        const uint32_t k = keep < 0 ? 0u : (keep > 16 ? 16u : (uint32_t)keep);
+        const uint32_t mask = (uint32_t)(0xFFFFFFFF00000000ull >> (2 * k));
+        cnt += nvb_popc(eq_flags(b.bwt[q], pat) & mask);
+    }
+    return cnt;
+}
+
+__host__ __device__ __forceinline__ uint32_t block_symbol(const FmBlock& b, uint32_t r) {
+    const uint32_t q = r >> 4;
+    const uint32_t w = (q == 0) ? b.bwt[0] : (q == 1) ? b.bwt[1] : (q == 2) ? b.bwt[2] : b.bwt[3];
+    return (w >> (30u - 2u * (r & 15u))) & 3u;
+}
+
+// rank(fmi, k, c)  (fmindex_inl.h:36-57)
+__host__ __device__ __forceinline__ uint32_t fm_rank1(const FmIndex& f, uint32_t k, uint32_t c) {
+    if (k == 0xFFFFFFFFu) return 0u;
+    if (k == f.n) return f.count(c);
+    if (k >= f.primary) --k;
+    const FmBlock b = load_block(f.blocks, k >> 6);
+    return block_rank(b, k & 63u, c);
+}
+
+// rank(fmi, (kx,ky), c)  (fmindex_inl.h:66-99 -> rank_dictionary_inl.h:512-538).  All of the
+// reference's case splits reduce to "each end is rank1 of that end"; the only thing worth keeping
+// is the shared block load when both ends fall in one 64-symbol block.
+__host__ __device__ __forceinline__ void fm_rank2(const FmIndex& f, uint32_t kx, uint32_t ky, uint32_t c,
+                                                  uint32_t& rx, uint32_t& ry) {
+    const bool need_x = (kx != 0xFFFFFFFFu) && (kx != f.n);
+    const bool need_y = (ky != 0xFFFFFFFFu) && (ky != f.n);
+    const uint32_t cnt = f.count(c);
+    rx = (kx == f.n) ? cnt : 0u;
+    ry = (ky == f.n) ? cnt : 0u;
+    const uint32_t ax = kx - (kx >= f.primary ? 1u : 0u);
+    const uint32_t ay = ky - (ky >= f.primary ? 1u : 0u);
+    if (need_x || need_y) {
+        const uint32_t bx = ax >> 6, by = ay >> 6;
+        FmBlock b0 = load_block(f.blocks, need_x ? bx : by);
+        FmBlock b1 = b0;
+        load_block_if(b1, f.blocks, by, need_x && need_y && bx != by);
+        const uint32_t tx = block_rank(b0, ax & 63u, c);
+        const uint32_t ty = block_rank(b1, ay & 63u, c);
+        if (need_x) rx = tx;
+        if (need_y) ry = ty;
+    }
+}
+
+// one backward-search step; returns false when the range became empty
+__host__ __device__ __forceinline__ void fm_step(const FmIndex& f, uint32_t c, uint32_t& x, uint32_t& y) {
+    uint32_t rx, ry;
+    fm_rank2(f, x - 1u, y, c, rx, ry);
+    const uint32_t base = f.l2(c);
+    x = base + rx + 1u;
+    y = base + ry;
+}
+
+// match() of one query read through a SymReader; FORWARD consumes left-to-right, COMPLEMENT maps
+// c<4 -> 3-c (nvBowtie's reverse-complement seed search over the forward index).
+template <int BITS, bool BE>
+__host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const uint32_t* __restrict__ words,
+                                                      uint32_t off, uint32_t len, uint32_t flags,
+                                                      uint32_t& ox, uint32_t& oy) {
+    SymReader<BITS, BE> rd(words);
+    uint32_t x = 0, y = f.n;
+    const bool fwd = (flags & NVB_MATCH_FORWARD_ORDER) != 0;
+    const bool comp = (flags & NVB_MATCH_COMPLEMENT) != 0;
+    for (uint32_t s = 0; s < len && x <= y; ++s) {
+        const uint32_t i = fwd ? s : (len - 1u - s);
+        uint32_t c = rd.get(off + i);
+        if (c > 3u) { x = 1u; y = 0u; break; }
+        if (comp) c = 3u - c;
+        fm_step(f, c, x, y);
+    }
+    ox = x; oy = y;
+}
+
+// locate(fmi, row)
+__host__ __device__ __forceinline__ uint32_t fm_locate_one(const FmIndex& f, uint32_t row) {
+    uint32_t j = row, t = 0;
+    while ((j & 15u) != 0u) {
+        if (j != f.primary) {
+            const uint32_t k = j < f.primary ? j : j - 1u;
+            const FmBlock b = load_block(f.blocks, k >> 6);
+            const uint32_t c = block_symbol(b, k & 63u);
+            j = f.l2(c) + block_rank(b, k & 63u, c);
+        } else {
+            j = 0u;
+        }
+        ++t;
+    }
+    return f.ssa[j >> 4] + t;
+}
+
+} // namespace nvb

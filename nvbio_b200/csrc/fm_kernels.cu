@@ -1,0 +1,242 @@
+// fm_kernels.cu -- HP-A: FM-index rank / match / locate / FMIndexFilter and the occ-table builder.
+//
+// One query per thread, a whole SM's worth of independent 32-byte gathers in flight (the path is
+// bound by random-sector HBM/L2 throughput): each LF step issues one 256-bit load per
+// distinct block (two when the range ends straddle blocks) and ~40 integer ops.
+#include "fm_core.cuh"
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+namespace nvb {
+
+constexpr int FM_BLOCKDIM = 256;
+
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_rank_kernel(const FmIndex f, const uint32_t* __restrict__ k, const uint8_t* __restrict__ c, uint32_t n,
+               uint32_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fm_rank1(f, k[i], c[i] & 3u);
+}
+
+template <int BITS, bool BE>
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_match_kernel(const FmIndex f, const StrSet q, uint32_t n, uint32_t flags, uint2* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x, y;
+    fm_match_one<BITS, BE>(f, q.words, str_off(q, i), str_len(q, i), flags, x, y);
+    out[i] = make_uint2(x, y);
+}
+
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_locate_kernel(const FmIndex f, const uint32_t* __restrict__ rows, uint32_t n, uint32_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fm_locate_one(f, rows[i]);
+}
+
+// range sizes as uint64 (filter_inl.h:36-42: 1 + y - x in uint32 arithmetic, widened)
+struct RangeSize {
+    __host__ __device__ __forceinline__ uint64_t operator()(const uint2& r) const { return (uint64_t)(uint32_t)(1u + r.y - r.x); }
+};
+
+// upper_bound over the inclusive slots (filter_inl.h:99-118)
+__device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t* __restrict__ a, uint32_t n, uint64_t v)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_filter_locate_kernel(const FmIndex f, const uint2* __restrict__ ranges, const uint64_t* __restrict__ slots,
+                        uint32_t n_queries, uint64_t begin, uint64_t count, uint2* __restrict__ hits)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (t >= count) return;
+    const uint64_t h = begin + t;
+    const uint32_t slot = upper_bound_u64(slots, n_queries, h);
+    const uint64_t base = slot ? slots[slot - 1] : 0ull;
+    const uint32_t row = ranges[slot].x + (uint32_t)(h - base);
+    hits[t] = make_uint2(fm_locate_one(f, row), slot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// occ-table build + interleave on the device (the reference does this serially on the host,
+// rank_dictionary_inl.h:42-77 + fmindex_impl.cu:263-331, and carries a TODO for a CUDA version)
+// ---------------------------------------------------------------------------------------------
+struct U4Add { __host__ __device__ __forceinline__ uint4 operator()(const uint4& a, const uint4& b) const {
+    return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); } };
+
+__global__ void __launch_bounds__(256)
+occ_block_counts_kernel(const uint32_t* __restrict__ bwt, uint32_t n, uint32_t n_blocks, uint4* __restrict__ counts)
+{
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n_blocks) return;
+    const uint4 w = reinterpret_cast<const uint4*>(bwt)[k];
+    const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+    const uint32_t valid = (n - k * 64u) < 64u ? (n - k * 64u) : 64u;     // symbols of this block that exist
+    uint32_t cnt[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int keep = (int)valid - 16 * q;
+        const uint32_t kk = keep < 0 ? 0u : (keep > 16 ? 16u : (uint32_t)keep);
+        const uint32_t mask = (uint32_t)(0xFFFFFFFF00000000ull >> (2 * kk));
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) cnt[c] += __popc(eq_flags(ws[q], c * 0x55555555u) & mask);
+    }
+    counts[k] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+}
+
+__global__ void __launch_bounds__(256)
+occ_interleave_kernel(const uint32_t* __restrict__ bwt, const uint4* __restrict__ occ_excl, uint32_t n, uint32_t n_blocks,
+                      FmBlock* __restrict__ out)
+{
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n_blocks) return;
+    uint4 w = reinterpret_cast<const uint4*>(bwt)[k];
+    // zero the padding symbols (positions >= n) so that the emitted index is deterministic
+    const uint32_t valid = (n - k * 64u) < 64u ? (n - k * 64u) : 64u;
+    uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int keep = (int)valid - 16 * q;
+        const uint32_t kk = keep < 0 ? 0u : (keep > 16 ? 16u : (uint32_t)keep);
+        ws[q] &= (uint32_t)(0xFFFFFFFF00000000ull >> (2 * kk));
+    }
+    const uint4 o = occ_excl[k];
+    FmBlock b;
+    b.bwt[0] = ws[0]; b.bwt[1] = ws[1]; b.bwt[2] = ws[2]; b.bwt[3] = ws[3];
+    b.occ[0] = o.x; b.occ[1] = o.y; b.occ[2] = o.z; b.occ[3] = o.w;
+    out[k] = b;
+}
+
+} // namespace nvb
+
+using namespace nvb;
+
+extern "C" {
+
+int nvb_version(void) { return NVB_VERSION; }
+
+const char* nvb_error_string(int err)
+{
+    switch (err) {
+    case NVB_OK:            return "success";
+    case NVB_E_INVALID:     return "nvbio_b200: invalid argument";
+    case NVB_E_TEMP_SIZE:   return "nvbio_b200: temp storage missing or too small";
+    case NVB_E_CAPACITY:    return "nvbio_b200: output capacity exceeded";
+    case NVB_E_UNSUPPORTED: return "nvbio_b200: unsupported configuration";
+    }
+    return err > 0 ? cudaGetErrorString((cudaError_t)err) : "nvbio_b200: unknown error";
+}
+
+int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c, uint32_t n,
+                uint32_t* d_out, void* stream)
+{
+    if (!fmi || !fmi->d_bwt_occ || (n && (!d_k || !d_c || !d_out))) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    fm_rank_kernel<<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), d_k, d_c, n, d_out);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_match(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
+                 nvb_uint2* d_ranges, void* stream)
+{
+    if (!fmi || !fmi->d_bwt_occ || !valid_strset(queries) || (n && !d_ranges)) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    const FmIndex f = make_fmindex(fmi);
+    const StrSet q = make_strset(queries);
+    const uint32_t grid = (n + FM_BLOCKDIM - 1) / FM_BLOCKDIM;
+#define CALL(B, E) fm_match_kernel<B, E><<<grid, FM_BLOCKDIM, 0, as_stream(stream)>>>(f, q, n, flags, (uint2*)d_ranges)
+    NVB_DISPATCH_STREAM(q.bits, q.big_endian, CALL);
+#undef CALL
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_locate(const nvb_fm_index* fmi, const uint32_t* d_rows, uint32_t n, uint32_t* d_pos, void* stream)
+{
+    if (!fmi || !fmi->d_bwt_occ || !fmi->d_ssa || (n && (!d_rows || !d_pos))) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    fm_locate_kernel<<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), d_rows, n, d_pos);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_filter_rank(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
+                       nvb_uint2* d_ranges, uint64_t* d_slots, uint64_t* h_n_hits,
+                       void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!temp_bytes || (n && (!d_ranges || !d_slots))) return NVB_E_INVALID;
+    if (h_n_hits) *h_n_hits = 0;
+    if (n == 0) { *temp_bytes = 0; return NVB_OK; }
+    cub::TransformInputIterator<uint64_t, RangeSize, const uint2*> sizes((const uint2*)d_ranges, RangeSize());
+    size_t need = 0;
+    NVB_CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, need, sizes, d_slots, (int)n, as_stream(stream)));
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    const int r = nvb_fm_match(fmi, queries, n, flags, d_ranges, stream);
+    if (r != NVB_OK) return r;
+    NVB_CUDA_TRY(cub::DeviceScan::InclusiveSum(d_temp, need, sizes, d_slots, (int)n, as_stream(stream)));
+    if (h_n_hits) {
+        NVB_CUDA_TRY(cudaMemcpyAsync(h_n_hits, d_slots + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+        NVB_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
+    }
+    return NVB_OK;
+}
+
+int nvb_fm_filter_locate(const nvb_fm_index* fmi, const nvb_uint2* d_ranges, const uint64_t* d_slots,
+                         uint32_t n_queries, uint64_t begin, uint64_t end, nvb_uint2* d_hits, void* stream)
+{
+    if (!fmi || !fmi->d_bwt_occ || !fmi->d_ssa || !d_ranges || !d_slots || end < begin) return NVB_E_INVALID;
+    const uint64_t count = end - begin;
+    if (count == 0) return NVB_OK;
+    if (!d_hits || count > 0x7FFFFFFFull * FM_BLOCKDIM) return NVB_E_INVALID;
+    const uint32_t grid = (uint32_t)((count + FM_BLOCKDIM - 1) / FM_BLOCKDIM);
+    fm_filter_locate_kernel<<<grid, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), (const uint2*)d_ranges, d_slots,
+                                                                        n_queries, begin, count, (uint2*)d_hits);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_build_occ(const uint32_t* d_bwt, uint32_t n, void* d_bwt_occ, uint32_t h_L2[5],
+                     void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!temp_bytes || !h_L2 || (n && (!d_bwt || !d_bwt_occ))) return NVB_E_INVALID;
+    const uint32_t n_blocks = (n + 63u) / 64u;
+    TempCarver tc(d_temp);
+    uint4* counts = tc.take<uint4>(n_blocks + 1);
+    uint4* excl   = tc.take<uint4>(n_blocks + 1);
+    size_t scan_bytes = 0;
+    NVB_CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, scan_bytes, counts, excl, U4Add(), make_uint4(0, 0, 0, 0), (int)(n_blocks + 1), as_stream(stream)));
+    char* scan_tmp = tc.take<char>(scan_bytes);
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    cudaStream_t s = as_stream(stream);
+    // counts[n_blocks] = 0 so that excl[n_blocks] = totals
+    NVB_CUDA_TRY(cudaMemsetAsync(counts + n_blocks, 0, sizeof(uint4), s));
+    if (n_blocks) {
+        occ_block_counts_kernel<<<(n_blocks + 255) / 256, 256, 0, s>>>(d_bwt, n, n_blocks, counts);
+        NVB_LAUNCH_CHECK();
+    }
+    NVB_CUDA_TRY(cub::DeviceScan::ExclusiveScan(scan_tmp, scan_bytes, counts, excl, U4Add(), make_uint4(0, 0, 0, 0), (int)(n_blocks + 1), s));
+    if (n_blocks) {
+        occ_interleave_kernel<<<(n_blocks + 255) / 256, 256, 0, s>>>(d_bwt, excl, n, n_blocks, (FmBlock*)d_bwt_occ);
+        NVB_LAUNCH_CHECK();
+    }
+    uint4 tot;
+    NVB_CUDA_TRY(cudaMemcpyAsync(&tot, excl + n_blocks, sizeof(uint4), cudaMemcpyDeviceToHost, s));
+    NVB_CUDA_TRY(cudaStreamSynchronize(s));
+    h_L2[0] = 0; h_L2[1] = tot.x; h_L2[2] = tot.x + tot.y; h_L2[3] = tot.x + tot.y + tot.z; h_L2[4] = tot.x + tot.y + tot.z + tot.w;
+    return NVB_OK;
+}
+
+} // extern "C"

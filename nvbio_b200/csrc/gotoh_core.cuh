@@ -1,0 +1,301 @@
+// gotoh_core.cuh -- per-thread banded Gotoh scoring (HP-B).
+//
+// Semantics follow nvbio's priv::banded::gotoh_alignment_score_dispatch<BAND_LEN,TYPE>::run
+// (nvbio/alignment/gotoh/gotoh_banded_inl.h:406-658), the row-0 initialisation (:46-77), BestSink's
+// `<=` tie-break (nvbio/alignment/sink_inl.h:57-65) and the 2-bit sliding text cache used for every
+// BAND_LEN outside {3,5,7,15} (nvbio/alignment/alignment_base_inl.h:75-99).  Band cell j of row i is
+// DP cell (pattern i, text i+j);   F[j] <- max(F[j+1]+Ge, H[j+1]+Go)   (previous row's H[j+1]),
+// H[j] <- max(F[j], E, H[j]+S(text[i+j],pattern[i]))  (LOCAL: clamped at 0, every cell reported),
+// E <- max(H[j]+Go, E+Ge) chained left to right.  E and F both use the PATTERN gap costs.
+//
+// Two formulations, both new:
+//   * gotoh_generic<B,TYPE>  one alignment per thread, int32, any symbol width / quality table;
+//   * gotoh_pair<B,TYPE>     TWO alignments per thread packed as s16x2 halves, driven by Blackwell's
+//                            DPX instructions (VIADDMNMX.S16x2[.RELU], VIMNMX[3].S16x2, VIADD.16x2):
+//                            5 DPX ops + 1 PRMT (substitution lookup) per cell PAIR, the LOCAL sink
+//                            tracked with one IMAD + half a VIMNMX3.U16x2 per cell pair.
+#pragma once
+#include "common.cuh"
+#include <limits.h>
+
+namespace nvb {
+
+struct GotohScheme {
+    int32_t match, mismatch, pgo, pge, tgo, tge;
+    const int32_t* qtab;       // device (or host in host tests): [256][2] = {match(q), mismatch(q)} or NULL
+};
+static inline GotohScheme make_scheme(const nvb_gotoh_scheme* s) {
+    GotohScheme r; r.match = s->match; r.mismatch = s->mismatch; r.pgo = s->pattern_gap_open; r.pge = s->pattern_gap_ext;
+    r.tgo = s->text_gap_open; r.tge = s->text_gap_ext; r.qtab = s->d_qual_table; return r;
+}
+
+__host__ __device__ __forceinline__ int32_t imax2(int32_t a, int32_t b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ uint32_t umin2(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+__host__ __device__ __forceinline__ int32_t gotoh_infimum(const GotohScheme& S) {
+    return SHRT_MIN - imax2(imax2(S.pgo, S.pge), imax2(S.tgo, S.tge));
+}
+__host__ __device__ __forceinline__ constexpr bool packed_text_cache(int B) { return !(B == 3 || B == 5 || B == 7 || B == 15); }
+
+// runtime-format sequential symbol reader (bits in {2,4,8})
+struct SymReaderRT {
+    const uint32_t* words; uint32_t bits, be, log_spw, cur_idx, cur_word;
+    __host__ __device__ __forceinline__ SymReaderRT(const uint32_t* w, uint32_t b, uint32_t e)
+        : words(w), bits(b), be(e), log_spw(b == 2 ? 4 : (b == 4 ? 3 : 2)), cur_idx(0xFFFFFFFFu), cur_word(0) {}
+    __host__ __device__ __forceinline__ uint32_t get(uint32_t p) {
+        const uint32_t wi = p >> log_spw;
+        if (wi != cur_idx) { cur_idx = wi; cur_word = words[wi]; }
+        const uint32_t r = p & ((1u << log_spw) - 1u);
+        const uint32_t sh = (bits == 8) ? 8u * r : (be ? 32u - bits - bits * r : bits * r);
+        return (cur_word >> sh) & ((1u << bits) - 1u);
+    }
+};
+
+struct SinkResult { int32_t score; uint32_t x, y; };
+
+// ---------------------------------------------------------------------------------------------
+// generic: one alignment, int32
+// ---------------------------------------------------------------------------------------------
+template <int B, int TYPE>
+__host__ __device__ inline SinkResult gotoh_generic(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
+        const uint8_t* __restrict__ quals,
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N)
+{
+    SinkResult res; res.score = INT_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
+    if (N < M) return res;
+
+    constexpr bool PACKED = packed_text_cache(B);
+    const int32_t Go = S.pgo, Ge = S.pge;
+    const int32_t INF = gotoh_infimum(S);
+
+    int32_t H[B], F[B];
+    uint32_t cache[B];        // cache[j] = (quirk-adjusted) text symbol of band cell j, j < B-1
+    H[0] = 0;
+#pragma unroll
+    for (int j = 1; j < B; ++j) H[j] = (TYPE == NVB_GLOBAL) ? S.tgo + (j - 1) * S.tge : 0;
+#pragma unroll
+    for (int j = 0; j < B; ++j) F[j] = INF;
+
+    SymReaderRT tr(twords, tbits, tbe), pr(pwords, pbits, pbe);
+#pragma unroll
+    for (int j = 0; j < B - 1; ++j) {
+        // the reference reads text[j], j < B-1, without a bound check (undefined beyond N); we define 255
+        const uint32_t g = ((uint32_t)j < N) ? tr.get(toff + j) : 255u;
+        cache[j] = PACKED ? (g & 3u) : g;
+    }
+
+    int32_t best = INT_MIN; uint32_t bpos = 0;     // bpos = (i << 6) | j of the last maximal LOCAL cell
+    for (uint32_t i = 0; i < M; ++i) {
+        const uint32_t q = pr.get(poff + i);
+        const uint32_t qq = quals ? quals[poff + i] : 0u;
+        const int32_t s_eq = S.qtab ? S.qtab[2 * qq]     : S.match;
+        const int32_t s_ne = S.qtab ? S.qtab[2 * qq + 1] : S.mismatch;
+        const uint32_t g_new = (i + (uint32_t)B - 1u < N) ? tr.get(toff + i + B - 1) : 255u;
+        int32_t E = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const uint32_t g = (j < B - 1) ? cache[j] : g_new;          // cell B-1 sees the unmasked symbol
+            if (j >= 1 && j < B - 1) cache[j - 1] = g;
+            if (j < B - 1) F[j] = imax2(F[j + 1] + Ge, H[j + 1] + Go); else F[j] = INF;
+            int32_t h = H[j] + ((g == q) ? s_eq : s_ne);
+            if (j < B - 1) h = imax2(h, F[j]);
+            if (j > 0)     h = imax2(h, E);
+            if (TYPE == NVB_LOCAL) {
+                h = imax2(h, 0);
+                if (best <= h) { best = h; bpos = (i << 6) | (uint32_t)j; }
+            }
+            H[j] = h;
+            E = (j == 0) ? h + Go : imax2(h + Go, E + Ge);
+        }
+        cache[B - 2] = PACKED ? (g_new & 3u) : g_new;
+    }
+    if (TYPE == NVB_LOCAL) {
+        if (M > 0) { res.score = best; res.x = (bpos >> 6) + (bpos & 63u) + 1u; res.y = (bpos >> 6) + 1u; }
+    } else if (TYPE == NVB_GLOBAL) {
+        res.score = H[B - 1]; res.x = M + (uint32_t)B - 1u; res.y = M;
+    } else {
+        const uint32_t m = umin2(M + (uint32_t)B - 1u, N) - (M - 1u);
+        res.score = H[0]; res.x = M; res.y = M;
+#pragma unroll
+        for (int j = 1; j < B; ++j)
+            if ((uint32_t)j < m && res.score <= H[j]) { res.score = H[j]; res.x = M + (uint32_t)j; }
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed pair: two alignments per thread in s16x2 halves
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__host__ __device__ __forceinline__ int32_t half_lo(uint32_t v) { return (int32_t)(int16_t)(v & 0xFFFFu); }
+__host__ __device__ __forceinline__ int32_t half_hi(uint32_t v) { return (int32_t)(int16_t)(v >> 16); }
+
+// prmt.b32 generic mode incl. the sign-replicate bit of each selector nibble
+__host__ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d;
+#else
+    const uint64_t ab = ((uint64_t)b << 32) | a;
+    uint32_t d = 0;
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t nib = (sel >> (4 * k)) & 0xFu;
+        uint32_t byte = (uint32_t)(ab >> (8 * (nib & 7u))) & 0xFFu;
+        if (nib & 8u) byte = (byte & 0x80u) ? 0xFFu : 0x00u;
+        d |= byte << (8 * k);
+    }
+    return d;
+#endif
+}
+
+// selector for a pair of 2-bit text symbols (g0 -> low half from profile a, g1 -> high half from b):
+// nibbles {g0, 8|g0, 4|g1, 0xC|g1}: byte, its sign extension, byte, its sign extension
+__host__ __device__ __forceinline__ uint32_t pair_selector(uint32_t g0, uint32_t g1) { return 0xC480u + g0 * 0x11u + g1 * 0x1100u; }
+
+// 4-byte substitution profile of one pattern symbol: byte c = (c == q) ? s_eq : s_ne  (int8 each)
+__host__ __device__ __forceinline__ uint32_t sub_profile(uint32_t q, int32_t s_eq, int32_t s_ne) {
+    const uint32_t base = ((uint32_t)s_ne & 0xFFu) * 0x01010101u;
+    const uint32_t flip = (uint32_t)(s_eq ^ s_ne) & 0xFFu;
+    return (q < 4u) ? (base ^ (flip << (8u * q))) : base;
+}
+
+// host-side admissibility of the packed path for a batch (max pattern length max_m)
+static inline bool pair_path_ok(int B, int type, const nvb_gotoh_scheme* s, uint32_t max_m) {
+    if (!(B == 7 || B == 15 || B == 31)) return false;
+    if (s->d_qual_table) return false;                      // quality tables go through the generic path
+    const int64_t Go = s->pattern_gap_open, Ge = s->pattern_gap_ext;
+    if (Go >= 0 || Ge >= 0 || s->text_gap_open >= 0 || s->text_gap_ext >= 0) return false;
+    const int64_t a_m = s->match < 0 ? -(int64_t)s->match : s->match, a_x = s->mismatch < 0 ? -(int64_t)s->mismatch : s->mismatch;
+    const int64_t max_s = a_m > a_x ? a_m : a_x;
+    int64_t max_g = -Go; if (-Ge > max_g) max_g = -Ge; if (-(int64_t)s->text_gap_open > max_g) max_g = -(int64_t)s->text_gap_open;
+    if (-(int64_t)s->text_gap_ext > max_g) max_g = -(int64_t)s->text_gap_ext;
+    const int64_t bound = (int64_t)max_m * max_s + (int64_t)(B + 2) * max_g + max_g;
+    if (bound > 30000) return false;
+    // substitution bytes (S - Go) must fit int8
+    const int64_t c_eq = (int64_t)s->match - Go, c_ne = (int64_t)s->mismatch - Go;
+    if (c_eq < -128 || c_eq > 127 || c_ne < -128 || c_ne > 127) return false;
+    if (type == NVB_LOCAL) {
+        // LOCAL cells are packed as (h << 5) | j in 16 bits
+        const int64_t top = (int64_t)max_m * (s->match > 0 ? s->match : 0);
+        if (top >= 2048) return false;
+    }
+    return true;
+}
+
+// DPX / SIMD-in-word wrappers.  On sm_100a each is ONE instruction (VIADDMNMX.S16x2[.RELU],
+// VIMNMX.S16x2[.RELU], VIADD.16x2, VIMNMX[3].U16x2); the host versions exist only so that tests can run
+// the very same per-thread routine on the CPU.
+#define NVB_VIADDMAX(a, b, c)      __viaddmax_s16x2((a), (b), (c))
+#define NVB_VIADDMAX_RELU(a, b, c) __viaddmax_s16x2_relu((a), (b), (c))
+#define NVB_VIMAX_RELU(a, b)       __vimax_s16x2_relu((a), (b))
+#ifdef __CUDA_ARCH__
+#define NVB_VIMAX(a, b)            __vmaxs2((a), (b))
+#define NVB_VIADD(a, b)            __vadd2((a), (b))
+#define NVB_VIMAX_U(a, b)          __vmaxu2((a), (b))
+#else
+static inline uint32_t nvb_host_vmaxs2(uint32_t a, uint32_t b) {
+    const int32_t l = imax2(half_lo(a), half_lo(b)), h = imax2(half_hi(a), half_hi(b)); return pack16(l, h); }
+static inline uint32_t nvb_host_vadd2(uint32_t a, uint32_t b) {
+    return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
+static inline uint32_t nvb_host_vmaxu2(uint32_t a, uint32_t b) {
+    const uint32_t l = (a & 0xFFFFu) > (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
+    const uint32_t h = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16); return l | (h << 16); }
+#define NVB_VIMAX(a, b)            nvb_host_vmaxs2((a), (b))
+#define NVB_VIADD(a, b)            nvb_host_vadd2((a), (b))
+#define NVB_VIMAX_U(a, b)          nvb_host_vmaxu2((a), (b))
+#endif
+
+// Preconditions (checked by the caller, else the generic path is used):
+//   M0,M1 >= 1; N_k >= M_k + B - 1 (no pad symbol is ever read inside an alignment's own rows);
+//   text is 2-bit; TYPE != LOCAL => M0 == M1; scheme admitted by pair_path_ok().
+// sel: selectors of text columns t = 0 .. max(M0,M1)+B-2, element t at sel[t*sel_stride]
+// (shared memory on the device: conflict-free u16 column per thread).
+template <int B, int TYPE>
+__host__ __device__ inline void gotoh_pair(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe,
+        uint32_t poff0, uint32_t M0, uint32_t poff1, uint32_t M1,
+        uint32_t N0, uint32_t N1,
+        const uint16_t* sel, uint32_t sel_stride,
+        SinkResult& r0, SinkResult& r1)
+{
+    const int32_t Go = S.pgo, Ge = S.pge;
+    const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
+    // F "minus infinity", raised just enough that INF+Ge cannot wrap below -32768 (identical maxima:
+    // every H+Go it competes with is representable and therefore >= -32768)
+    int32_t INF = gotoh_infimum(S);
+    if (INF + Ge < -32768) INF = -32768 - Ge;
+    const uint32_t INF2 = pack16(INF, INF);
+    const int32_t c_eq = S.match - Go, c_ne = S.mismatch - Go;       // substitution minus Go (G = H + Go is stored)
+
+    uint32_t G[B], F[B - 1];
+    {
+        G[0] = pack16(0 + Go, 0 + Go);
+#pragma unroll
+        for (int j = 1; j < B; ++j) {
+            const int32_t h = (TYPE == NVB_GLOBAL) ? S.tgo + (j - 1) * S.tge : 0;
+            G[j] = pack16(h + Go, h + Go);
+        }
+#pragma unroll
+        for (int j = 0; j < B - 1; ++j) F[j] = INF2;
+    }
+
+    SymReaderRT pr0(pwords, pbits, pbe), pr1(pwords, pbits, pbe);
+    const uint32_t Mmax = M0 > M1 ? M0 : M1;
+    int32_t best0 = -1, best1 = -1; uint32_t bi0 = 0, bj0 = 0, bi1 = 0, bj1 = 0;
+
+    for (uint32_t i = 0; i < Mmax; ++i) {
+        const uint32_t q0 = (i < M0) ? pr0.get(poff0 + i) : 255u;
+        const uint32_t q1 = (i < M1) ? pr1.get(poff1 + i) : 255u;
+        const uint32_t P0 = sub_profile(q0, c_eq, c_ne);
+        const uint32_t P1 = sub_profile(q1, c_eq, c_ne);
+        const uint16_t* srow = sel + (size_t)i * sel_stride;
+        uint32_t E = 0, rowkey = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
+            uint32_t h;
+            if (j == 0) {
+                F[0] = NVB_VIADDMAX(F[1], Ge2, G[1]);
+                h = (TYPE == NVB_LOCAL) ? NVB_VIADDMAX_RELU(G[0], s, F[0]) : NVB_VIADDMAX(G[0], s, F[0]);
+            } else if (j < B - 1) {
+                F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INF2, Ge2, G[j + 1]);
+                const uint32_t t = NVB_VIADDMAX(G[j], s, F[j]);
+                h = (TYPE == NVB_LOCAL) ? NVB_VIMAX_RELU(t, E) : NVB_VIMAX(t, E);
+            } else {
+                h = (TYPE == NVB_LOCAL) ? NVB_VIADDMAX_RELU(G[j], s, E) : NVB_VIADDMAX(G[j], s, E);
+            }
+            if (TYPE == NVB_LOCAL) {
+                const uint32_t key = h * 32u + (uint32_t)(j | (j << 16));        // (h << 5) | j per half, h < 2048
+                rowkey = NVB_VIMAX_U(rowkey, key);
+            }
+            G[j] = NVB_VIADD(h, Go2);
+            E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
+        }
+        if (TYPE == NVB_LOCAL) {
+            const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
+            if (i < M0 && (k0 >> 5) >= best0) { best0 = k0 >> 5; bi0 = i; bj0 = (uint32_t)k0 & 31u; }
+            if (i < M1 && (k1 >> 5) >= best1) { best1 = k1 >> 5; bi1 = i; bj1 = (uint32_t)k1 & 31u; }
+        }
+    }
+
+    if (TYPE == NVB_LOCAL) {
+        r0.score = best0; r0.x = bi0 + bj0 + 1u; r0.y = bi0 + 1u;
+        r1.score = best1; r1.x = bi1 + bj1 + 1u; r1.y = bi1 + 1u;
+    } else if (TYPE == NVB_GLOBAL) {
+        r0.score = half_lo(G[B - 1]) - Go; r0.x = M0 + (uint32_t)B - 1u; r0.y = M0;
+        r1.score = half_hi(G[B - 1]) - Go; r1.x = M1 + (uint32_t)B - 1u; r1.y = M1;
+    } else {
+        const uint32_t m0 = umin2(M0 + (uint32_t)B - 1u, N0) - (M0 - 1u);
+        const uint32_t m1 = umin2(M1 + (uint32_t)B - 1u, N1) - (M1 - 1u);
+        r0.score = half_lo(G[0]) - Go; r0.x = M0; r0.y = M0;
+        r1.score = half_hi(G[0]) - Go; r1.x = M1; r1.y = M1;
+#pragma unroll
+        for (int j = 1; j < B; ++j) {
+            const int32_t h0 = half_lo(G[j]) - Go, h1 = half_hi(G[j]) - Go;
+            if ((uint32_t)j < m0 && r0.score <= h0) { r0.score = h0; r0.x = M0 + (uint32_t)j; }
+            if ((uint32_t)j < m1 && r1.score <= h1) { r1.score = h1; r1.x = M1 + (uint32_t)j; }
+        }
+    }
+}
+
+} // namespace nvb

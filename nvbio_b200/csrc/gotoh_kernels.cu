@@ -1,0 +1,231 @@
+// gotoh_kernels.cu -- HP-B: batched banded Gotoh scoring kernels and their C ABI.
+//
+//   gotoh_pair_kernel<B,TYPE>     two alignments per thread in s16x2 halves (DPX), text selectors staged
+//                                 in shared memory (one conflict-free u16 column per thread); pairs that
+//                                 violate the packed path's preconditions are appended to a todo list
+//   gotoh_generic_kernel<B,TYPE>  one alignment per thread, int32, every symbol width / quality table;
+//                                 runs over the whole batch or over the todo list
+//
+// The path is bound by integer issue rate, not memory: ~0.1 KB moved per 4,650 cell updates (B=31, M=150).
+#include "gotoh_core.cuh"
+
+namespace nvb {
+
+constexpr int PAIR_BLOCKDIM    = 128;
+constexpr int GENERIC_BLOCKDIM = 128;
+
+struct GotohBatch {
+    StrSet   pat, txt;
+    const uint8_t* quals;
+    const uint32_t* d_n;       // optional device-side count
+    uint32_t n_max;
+    int32_t* score;
+    uint2*   sink;
+};
+
+__device__ __forceinline__ uint32_t batch_count(const GotohBatch& b) {
+    if (!b.d_n) return b.n_max;
+    const uint32_t n = *b.d_n;
+    return n < b.n_max ? n : b.n_max;
+}
+
+template <int B, int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_generic_kernel(const GotohScheme S, const GotohBatch b, const uint32_t* __restrict__ todo, const uint32_t* __restrict__ todo_count)
+{
+    const uint32_t n = todo ? *todo_count : batch_count(b);
+    for (uint32_t t = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x; t < n; t += gridDim.x * GENERIC_BLOCKDIM) {
+        const uint32_t a = todo ? todo[t] : t;
+        const SinkResult r = gotoh_generic<B, TYPE>(S,
+            b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a), b.quals,
+            b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a));
+        b.score[a] = r.score;
+        b.sink[a]  = make_uint2(r.x, r.y);
+    }
+}
+
+template <int B, int TYPE>
+__global__ void __launch_bounds__(PAIR_BLOCKDIM)
+gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
+{
+    extern __shared__ uint16_t sel_smem[];            // [sel_rows][PAIR_BLOCKDIM]
+    const uint32_t n = batch_count(b);
+    const uint32_t pair = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x;
+    const uint32_t a0 = 2u * pair;
+    if (a0 >= n) return;
+    const bool has1 = (a0 + 1u < n);
+    const uint32_t a1 = has1 ? a0 + 1u : a0;          // an odd tail computes the same alignment in both halves
+
+    const uint32_t M0 = str_len(b.pat, a0), M1 = str_len(b.pat, a1);
+    const uint32_t N0 = str_len(b.txt, a0), N1 = str_len(b.txt, a1);
+    const uint32_t Mmax = M0 > M1 ? M0 : M1;
+    const uint32_t L = Mmax + (uint32_t)B - 1u;       // text columns touched
+
+    const bool ok = (M0 >= 1u) && (M1 >= 1u) && (N0 >= M0 + (uint32_t)B - 1u) && (N1 >= M1 + (uint32_t)B - 1u) &&
+                    (L <= sel_rows) && (TYPE == NVB_LOCAL || M0 == M1);
+    if (!ok) {
+        const uint32_t cnt = has1 ? 2u : 1u;
+        const uint32_t slot = atomicAdd(todo_count, cnt);
+        todo[slot] = a0;
+        if (has1) todo[slot + 1u] = a1;
+        return;
+    }
+
+    // stage the PRMT selectors of this thread's two text windows
+    uint16_t* my_sel = sel_smem + threadIdx.x;
+    {
+        const uint32_t t0 = str_off(b.txt, a0), t1 = str_off(b.txt, a1);
+        if (b.txt.big_endian) {
+            SymReader<2, true> r0(b.txt.words), r1(b.txt.words);
+            for (uint32_t t = 0; t < L; ++t) {
+                const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
+                const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
+                my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+            }
+        } else {
+            SymReader<2, false> r0(b.txt.words), r1(b.txt.words);
+            for (uint32_t t = 0; t < L; ++t) {
+                const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
+                const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
+                my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+            }
+        }
+    }
+    // each thread reads back only its own column: no barrier needed
+
+    SinkResult r0, r1;
+    gotoh_pair<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
+                        str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
+                        my_sel, PAIR_BLOCKDIM, r0, r1);
+    b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
+    if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
+}
+
+template <int B, int TYPE>
+static int launch_generic(const GotohScheme& S, const GotohBatch& b, const uint32_t* todo, const uint32_t* todo_count, uint32_t n_hint, cudaStream_t s)
+{
+    // grid-stride: the count may live on the device
+    uint32_t grid = (n_hint + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
+    const uint32_t cap = 148u * 32u;
+    if (todo) grid = grid < cap ? grid : cap;
+    if (grid == 0) grid = 1;
+    gotoh_generic_kernel<B, TYPE><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, todo, todo_count);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+template <int B, int TYPE>
+static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
+{
+    const size_t smem = (size_t)sel_rows * PAIR_BLOCKDIM * sizeof(uint16_t);
+    static bool attr_done = false;      // per instantiation
+    if (!attr_done) {
+        NVB_CUDA_TRY(cudaFuncSetAttribute(gotoh_pair_kernel<B, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    const uint32_t pairs = (b.n_max + 1u) / 2u;
+    const uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
+    gotoh_pair_kernel<B, TYPE><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+#define NVB_TYPE_SWITCH(BAND, FN, ...)                                            \
+    switch (type) {                                                               \
+    case NVB_GLOBAL:      return FN<BAND, NVB_GLOBAL>(__VA_ARGS__);               \
+    case NVB_LOCAL:       return FN<BAND, NVB_LOCAL>(__VA_ARGS__);                \
+    case NVB_SEMI_GLOBAL: return FN<BAND, NVB_SEMI_GLOBAL>(__VA_ARGS__);          \
+    default:              return NVB_E_INVALID; }
+
+static int dispatch_generic(int band, int type, const GotohScheme& S, const GotohBatch& b, const uint32_t* todo, const uint32_t* todo_count, uint32_t n_hint, cudaStream_t s)
+{
+    switch (band) {
+    case 3:  NVB_TYPE_SWITCH(3,  launch_generic, S, b, todo, todo_count, n_hint, s)
+    case 5:  NVB_TYPE_SWITCH(5,  launch_generic, S, b, todo, todo_count, n_hint, s)
+    case 7:  NVB_TYPE_SWITCH(7,  launch_generic, S, b, todo, todo_count, n_hint, s)
+    case 15: NVB_TYPE_SWITCH(15, launch_generic, S, b, todo, todo_count, n_hint, s)
+    case 31: NVB_TYPE_SWITCH(31, launch_generic, S, b, todo, todo_count, n_hint, s)
+    case 63: NVB_TYPE_SWITCH(63, launch_generic, S, b, todo, todo_count, n_hint, s)
+    }
+    return NVB_E_INVALID;
+}
+static int dispatch_pair(int band, int type, const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
+{
+    switch (band) {
+    case 7:  NVB_TYPE_SWITCH(7,  launch_pair, S, b, sel_rows, todo, todo_count, s)
+    case 15: NVB_TYPE_SWITCH(15, launch_pair, S, b, sel_rows, todo, todo_count, s)
+    case 31: NVB_TYPE_SWITCH(31, launch_pair, S, b, sel_rows, todo, todo_count, s)
+    }
+    return NVB_E_INVALID;
+}
+
+// force_path: 0 auto, 1 generic only (used by tests to exercise both paths on the same inputs)
+static int g_force_path = 0;
+
+static int banded_impl(int band, int type, const nvb_gotoh_scheme* scheme,
+                       const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts,
+                       const uint32_t* d_n, uint32_t n_max, int32_t* d_score, nvb_uint2* d_sink,
+                       void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
+    if (!(band == 3 || band == 5 || band == 7 || band == 15 || band == 31 || band == 63)) return NVB_E_INVALID;
+    if (type < 0 || type > 2) return NVB_E_INVALID;
+    if (n_max && (!d_score || !d_sink)) return NVB_E_INVALID;
+
+    TempCarver tc(d_temp);
+    uint32_t* todo_count = tc.take<uint32_t>(4);
+    uint32_t* todo       = tc.take<uint32_t>((size_t)n_max + 2);
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    if (n_max == 0) return NVB_OK;
+
+    cudaStream_t s = as_stream(stream);
+    GotohBatch b;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
+    b.d_n = d_n; b.n_max = n_max; b.score = d_score; b.sink = (uint2*)d_sink;
+    const GotohScheme S = make_scheme(scheme);
+
+    // `length` is the maximum pattern length (the reference's batch API takes max_pattern_length too,
+    // nvbio/alignment/batched_inl.h:1067-1101)
+    const uint32_t max_m = patterns->length;
+    const uint32_t sel_rows = max_m + (uint32_t)band - 1u;
+    const size_t smem = (size_t)sel_rows * PAIR_BLOCKDIM * sizeof(uint16_t);
+    const bool fast = (g_force_path != 1) && texts->bits == 2 && max_m >= 1 && smem <= 200u * 1024u &&
+                      pair_path_ok(band, type, scheme, max_m);
+    if (!fast) return dispatch_generic(band, type, S, b, nullptr, nullptr, n_max, s);
+
+    NVB_CUDA_TRY(cudaMemsetAsync(todo_count, 0, sizeof(uint32_t), s));
+    int r = dispatch_pair(band, type, S, b, sel_rows, todo, todo_count, s);
+    if (r != NVB_OK) return r;
+    return dispatch_generic(band, type, S, b, todo, todo_count, n_max, s);
+}
+
+} // namespace nvb
+
+using namespace nvb;
+
+extern "C" {
+
+int nvb_banded_gotoh_score(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                           const nvb_string_set* patterns, const uint8_t* d_quals,
+                           const nvb_string_set* texts, uint32_t n,
+                           int32_t* d_score, nvb_uint2* d_sink,
+                           void* d_temp, size_t* temp_bytes, void* stream)
+{
+    return banded_impl(band_len, type, scheme, patterns, d_quals, texts, nullptr, n, d_score, d_sink, d_temp, temp_bytes, stream);
+}
+
+int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                           const nvb_string_set* patterns, const uint8_t* d_quals,
+                           const nvb_string_set* texts, const uint32_t* d_n, uint32_t n_max,
+                           int32_t* d_score, nvb_uint2* d_sink,
+                           void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!d_n) return NVB_E_INVALID;
+    return banded_impl(band_len, type, scheme, patterns, d_quals, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
+}
+
+// test hook (declared in tests only): 0 = auto, 1 = generic int32 kernel for everything
+void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
+
+} // extern "C"

@@ -1,0 +1,278 @@
+// pipeline.cu -- seed + extend composition of the two hot paths (the loop nvbio's examples/fmmap/fmmap.cu:255-400
+// and nvBowtie's best_approx run per read batch):
+//
+//   reads -> [fw, rc] strings -> seeds every `seed_interval` -> FM-index match (SA ranges)
+//         -> locate every hit row -> diagonal -> genome window [diag - B/2, + read_len + B)
+//         -> banded Gotoh score of the read (or its reverse complement) against the window
+//         -> best score per read.
+//
+// Everything stays on the device between stages; the hit count never visits the host (the extension
+// kernels read it from device memory).  Window rule: fmmap.cu:190-208 (genome_infixes); best-per-read
+// reduction: fmmap.cu:365-385.
+#include "fm_core.cuh"
+#include "gotoh_core.cuh"
+#include <cub/device/device_scan.cuh>
+
+namespace nvb {
+
+struct PipeGeom {
+    uint32_t n_reads;        // input reads
+    uint32_t n_strings;      // n_reads * (both_strands ? 2 : 1)
+    uint32_t strands;        // 1 or 2
+    uint32_t stride;         // symbols per string slot in the [fw,rc] stream (multiple of 32/bits)
+    uint32_t bits;           // symbol width of the [fw,rc] stream (= input width)
+    uint32_t seeds_per_string;
+    uint32_t seed_len, seed_interval;
+    uint32_t band;
+    uint32_t max_seed_hits;
+    uint32_t genome_len;
+    uint32_t hit_capacity;
+};
+
+// string s = 2*read + strand (strands==2) or read: copy / reverse-complement into an aligned slot.
+// One thread per output word.
+template <int BITS>
+__global__ void __launch_bounds__(256)
+pipe_make_strings_kernel(const StrSet reads, const PipeGeom g, uint32_t* __restrict__ out_words, uint32_t* __restrict__ out_len)
+{
+    constexpr uint32_t SPW = 32 / BITS;
+    const uint32_t words_per_string = g.stride / SPW;
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (uint64_t)g.n_strings * words_per_string) return;
+    const uint32_t s = (uint32_t)(t / words_per_string), w = (uint32_t)(t % words_per_string);
+    const uint32_t read = s / g.strands, strand = s % g.strands;
+    const uint32_t off = str_off(reads, read), len = str_len(reads, read);
+    if (w == 0) out_len[s] = len;
+    uint32_t word = 0;
+    for (uint32_t k = 0; k < SPW; ++k) {
+        const uint32_t p = w * SPW + k;
+        uint32_t c = 0;
+        if (p < len) {
+            if (strand == 0) c = sym_at_rt(reads.words, reads.bits, reads.big_endian, off + p);
+            else { c = sym_at_rt(reads.words, reads.bits, reads.big_endian, off + (len - 1u - p)); c = (c < 4u) ? 3u - c : c; }
+        }
+        word |= c << (32u - BITS - BITS * k);              // big-endian packing
+    }
+    out_words[t] = word;
+}
+
+// one thread per (string, seed slot): SA range of the seed, and its clamped size
+template <int BITS>
+__global__ void __launch_bounds__(256)
+pipe_seed_match_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __restrict__ words, const uint32_t* __restrict__ slen,
+                       uint2* __restrict__ ranges, uint32_t* __restrict__ sizes)
+{
+    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= g.n_strings * g.seeds_per_string) return;
+    const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
+    const uint32_t len = slen[s];
+    const uint32_t pos = k * g.seed_interval;
+    uint32_t x = 1, y = 0;
+    if (pos + g.seed_len <= len)
+        fm_match_one<BITS, true>(f, words, s * g.stride + pos, g.seed_len, 0u, x, y);
+    ranges[q] = make_uint2(x, y);
+    const uint32_t sz = (x <= y) ? (y - x + 1u) : 0u;
+    sizes[q] = sz < g.max_seed_hits ? sz : g.max_seed_hits;
+}
+
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t v)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// counts[0] = min(total, capacity), counts[1] = total
+__global__ void pipe_count_kernel(const uint32_t* __restrict__ excl, const uint32_t* __restrict__ sizes, uint32_t n_queries, uint32_t capacity,
+                                  uint32_t* __restrict__ counts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const uint32_t total = n_queries ? excl[n_queries - 1] + sizes[n_queries - 1] : 0u;
+        counts[1] = total;
+        counts[0] = total < capacity ? total : capacity;
+    }
+}
+
+// one thread per hit: locate the SA row, derive the genome window and the alignment job
+__global__ void __launch_bounds__(256)
+pipe_expand_hits_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict__ ranges, const uint32_t* __restrict__ excl,
+                        const uint32_t* __restrict__ slen, const uint32_t* __restrict__ counts,
+                        uint32_t* __restrict__ hit_string, uint32_t* __restrict__ p_off, uint32_t* __restrict__ p_len,
+                        uint32_t* __restrict__ t_off, uint32_t* __restrict__ t_len)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    if (h >= counts[0]) return;
+    const uint32_t nq = g.n_strings * g.seeds_per_string;
+    const uint32_t q = upper_bound_u32(excl, nq, h) - 1u;          // last query whose exclusive offset <= h
+    const uint32_t local = h - excl[q];
+    const uint32_t row = ranges[q].x + local;
+    const uint32_t pos = fm_locate_one(f, row);
+    const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
+    const uint32_t seed_begin = k * g.seed_interval;
+    const uint32_t len = slen[s];
+    const uint32_t diag = pos > seed_begin ? pos - seed_begin : 0u;               // text position of read offset 0
+    const uint32_t gb = diag > g.band / 2u ? diag - g.band / 2u : 0u;             // fmmap.cu:198-199
+    const uint64_t ge64 = (uint64_t)gb + len + g.band;
+    const uint32_t ge = ge64 < g.genome_len ? (uint32_t)ge64 : g.genome_len;
+    hit_string[h] = s;
+    p_off[h] = s * g.stride; p_len[h] = len;
+    t_off[h] = gb;           t_len[h] = ge - gb;
+}
+
+// best hit per read: max score, ties -> smallest hit index (deterministic)
+__global__ void __launch_bounds__(256)
+pipe_reduce_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ hit_string,
+                   const int32_t* __restrict__ score, unsigned long long* __restrict__ best_key)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    if (h >= counts[0]) return;
+    const uint32_t read = hit_string[h] / g.strands;
+    const unsigned long long key = ((unsigned long long)((uint32_t)score[h] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - h);
+    atomicMax(best_key + read, key);
+}
+
+__global__ void __launch_bounds__(256)
+pipe_finalize_kernel(const PipeGeom g, const unsigned long long* __restrict__ best_key, const uint32_t* __restrict__ t_off,
+                     const uint2* __restrict__ sink, int32_t* __restrict__ best_score, uint32_t* __restrict__ best_pos)
+{
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= g.n_reads) return;
+    const unsigned long long key = best_key[r];
+    if (key == 0ull) { best_score[r] = INT_MIN; best_pos[r] = 0xFFFFFFFFu; return; }
+    const uint32_t h = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    best_score[r] = (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u);
+    best_pos[r] = t_off[h] + sink[h].x;
+}
+
+__global__ void __launch_bounds__(256)
+pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ hit_string,
+                        const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
+                        uint32_t* __restrict__ out_read, uint2* __restrict__ out_window)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    if (h >= counts[0]) return;
+    if (out_read)   out_read[h] = hit_string[h];              // string id = read*strands + strand
+    if (out_window) out_window[h] = make_uint2(t_off[h], t_off[h] + t_len[h]);
+}
+
+} // namespace nvb
+
+using namespace nvb;
+
+extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_reads,
+                    const nvb_seed_extend_params* P, uint32_t hit_capacity,
+                    int32_t* d_best_score, uint32_t* d_best_pos,
+                    uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
+                    int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!fmi || !fmi->d_bwt_occ || !fmi->d_ssa || !d_genome || !valid_strset(reads) || !P || !temp_bytes) return NVB_E_INVALID;
+    if (reads->bits == 8) return NVB_E_UNSUPPORTED;
+    if (P->seed_len == 0 || P->seed_interval == 0 || P->max_seed_hits == 0) return NVB_E_INVALID;
+    if (n_reads && (!d_best_score || !d_best_pos)) return NVB_E_INVALID;
+    const uint32_t max_len = reads->length;                 // maximum read length (== length for fixed-length sets)
+    if (max_len < P->seed_len) return NVB_E_INVALID;
+
+    PipeGeom g;
+    g.n_reads = n_reads; g.strands = P->both_strands ? 2u : 1u; g.n_strings = n_reads * g.strands;
+    g.bits = reads->bits;
+    const uint32_t spw = 32u / g.bits;
+    g.stride = (max_len + spw - 1u) / spw * spw;
+    g.seeds_per_string = (max_len - P->seed_len) / P->seed_interval + 1u;
+    g.seed_len = P->seed_len; g.seed_interval = P->seed_interval; g.band = P->band_len;
+    g.max_seed_hits = P->max_seed_hits; g.genome_len = fmi->length; g.hit_capacity = hit_capacity;
+    if ((uint64_t)g.n_strings * g.stride > 0xFFFFFFFFull) return NVB_E_UNSUPPORTED;
+    const uint64_t nq64 = (uint64_t)g.n_strings * g.seeds_per_string;
+    if (nq64 > 0x7FFFFFFFull) return NVB_E_UNSUPPORTED;
+    const uint32_t nq = (uint32_t)nq64;
+
+    // the extension's own temp requirement
+    nvb_string_set pats, txts;
+    pats.bits = g.bits; pats.big_endian = 1; pats.stride = 0; pats.length = max_len;
+    txts.bits = 2; txts.big_endian = 1; txts.stride = 0; txts.length = max_len + P->band_len;
+    pats.d_words = (const uint32_t*)16; txts.d_words = d_genome;     // placeholders for the size query
+    pats.d_offsets = pats.d_lengths = txts.d_offsets = txts.d_lengths = nullptr;
+    size_t gotoh_bytes = 0;
+    {
+        const int r = nvb_banded_gotoh_score(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, hit_capacity,
+                                             (int32_t*)16, (nvb_uint2*)16, nullptr, &gotoh_bytes, stream);
+        if (r != NVB_E_TEMP_SIZE && r != NVB_OK) return r;
+    }
+
+    TempCarver tc(d_temp);
+    uint32_t* str_words  = tc.take<uint32_t>((size_t)g.n_strings * (g.stride / spw) + 4);
+    uint32_t* str_len_   = tc.take<uint32_t>(g.n_strings);
+    uint2*    ranges     = tc.take<uint2>(nq);
+    uint32_t* sizes      = tc.take<uint32_t>(nq);
+    uint32_t* excl       = tc.take<uint32_t>(nq);
+    uint32_t* counts     = tc.take<uint32_t>(4);
+    uint32_t* hit_string = tc.take<uint32_t>(hit_capacity);
+    uint32_t* p_off      = tc.take<uint32_t>(hit_capacity);
+    uint32_t* p_len      = tc.take<uint32_t>(hit_capacity);
+    uint32_t* t_off      = tc.take<uint32_t>(hit_capacity);
+    uint32_t* t_len      = tc.take<uint32_t>(hit_capacity);
+    int32_t*  h_score    = d_hit_score ? d_hit_score : tc.take<int32_t>(hit_capacity);
+    uint2*    h_sink     = d_hit_sink ? (uint2*)d_hit_sink : tc.take<uint2>(hit_capacity);
+    unsigned long long* best_key = tc.take<unsigned long long>(n_reads);
+    size_t scan_bytes = 0;
+    NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, sizes, excl, (int)nq, as_stream(stream)));
+    char* scan_tmp  = tc.take<char>(scan_bytes);
+    char* gotoh_tmp = tc.take<char>(gotoh_bytes);
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    if (n_reads == 0) return NVB_OK;
+
+    cudaStream_t s = as_stream(stream);
+    const FmIndex f = make_fmindex(fmi);
+    const StrSet rd = make_strset(reads);
+
+    // 1. [fw, rc] strings
+    {
+        const uint64_t total_words = (uint64_t)g.n_strings * (g.stride / spw);
+        const uint32_t grid = (uint32_t)((total_words + 255) / 256);
+        if (g.bits == 2) pipe_make_strings_kernel<2><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
+        else             pipe_make_strings_kernel<4><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
+        NVB_LAUNCH_CHECK();
+    }
+    // 2. seed ranges
+    {
+        const uint32_t grid = (nq + 255) / 256;
+        if (g.bits == 2) pipe_seed_match_kernel<2><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, ranges, sizes);
+        else             pipe_seed_match_kernel<4><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, ranges, sizes);
+        NVB_LAUNCH_CHECK();
+    }
+    // 3. hit slots
+    NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, sizes, excl, (int)nq, s));
+    pipe_count_kernel<<<1, 32, 0, s>>>(excl, sizes, nq, hit_capacity, counts);
+    NVB_LAUNCH_CHECK();
+    // 4. locate + windows
+    const uint32_t hgrid = (hit_capacity + 255) / 256;
+    if (hit_capacity) {
+        pipe_expand_hits_kernel<<<hgrid, 256, 0, s>>>(f, g, ranges, excl, str_len_, counts, hit_string, p_off, p_len, t_off, t_len);
+        NVB_LAUNCH_CHECK();
+    }
+    // 5. extension
+    pats.d_words = str_words; pats.d_offsets = p_off; pats.d_lengths = p_len;
+    txts.d_words = d_genome;  txts.d_offsets = t_off; txts.d_lengths = t_len;
+    if (hit_capacity) {
+        size_t gb = gotoh_bytes;
+        const int r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts, hit_capacity,
+                                                      h_score, (nvb_uint2*)h_sink, gotoh_tmp, &gb, stream);
+        if (r != NVB_OK) return r;
+    }
+    // 6. best per read
+    NVB_CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * n_reads, s));
+    if (hit_capacity) {
+        pipe_reduce_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, h_score, best_key);
+        NVB_LAUNCH_CHECK();
+    }
+    pipe_finalize_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(g, best_key, t_off, h_sink, d_best_score, d_best_pos);
+    NVB_LAUNCH_CHECK();
+    if (hit_capacity && (d_hit_read || d_hit_window)) {
+        pipe_export_hits_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, t_off, t_len, d_hit_read, (uint2*)d_hit_window);
+        NVB_LAUNCH_CHECK();
+    }
+    if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    return NVB_OK;
+}

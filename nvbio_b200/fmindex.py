@@ -1,0 +1,185 @@
+"""Host-side mirror of nvbio's FM-index interface for the hot path (nvbio/fmindex/fmindex.h,
+nvbio/fmindex/filter.h, nvbio/io/fmindex/fmindex.h) over the C ABI.  torch = device memory + streams."""
+import ctypes as C
+from typing import Optional
+import numpy as np
+import torch
+from ._lib import lib, check, FmIndexStruct, NvbError
+from .strings import PackedStringSet
+
+MATCH_FORWARD_ORDER = 1
+MATCH_COMPLEMENT = 2
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _np_u32(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+def _dev_u32(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32)).to(device)
+
+
+class FMIndexDevice:
+    """Device-resident FM-index in the reference's production layout: interleaved 32-byte
+    {bwt,occ} blocks + SA sampled every 16 rows (io::FMIndexDataDevice, nvbio/io/fmindex/fmindex.h:294-352)."""
+
+    def __init__(self, bwt_occ: torch.Tensor, ssa: Optional[torch.Tensor], L2, length: int, primary: int):
+        assert bwt_occ.is_cuda and bwt_occ.data_ptr() % 32 == 0
+        self.bwt_occ, self.ssa = bwt_occ, ssa
+        self.L2 = [int(v) for v in L2]
+        self.length, self.primary = int(length), int(primary)
+
+    # -- views ------------------------------------------------------------------------------
+    def struct(self) -> FmIndexStruct:
+        s = FmIndexStruct()
+        s.d_bwt_occ = self.bwt_occ.data_ptr()
+        s.d_ssa = self.ssa.data_ptr() if self.ssa is not None else None
+        s.length, s.primary = self.length, self.primary
+        for i in range(5):
+            s.L2[i] = self.L2[i]
+        return s
+
+    @property
+    def device(self):
+        return self.bwt_occ.device
+
+    def nbytes(self):
+        return self.bwt_occ.numel() * 4 + (self.ssa.numel() * 4 if self.ssa is not None else 0)
+
+    # -- construction -----------------------------------------------------------------------
+    @staticmethod
+    def from_host(bwt_occ: np.ndarray, ssa: Optional[np.ndarray], L2, length, primary, device="cuda"):
+        """upload host arrays laid out as the reference's loader produces them
+        (nvbio/io/fmindex/fmindex_impl.cu:263-331)"""
+        return FMIndexDevice(_dev_u32(bwt_occ, device), None if ssa is None else _dev_u32(ssa, device), L2, length, primary)
+
+    @staticmethod
+    def from_bwt(bwt_words: torch.Tensor, n: int, primary: int, ssa: Optional[torch.Tensor]):
+        """occ table + interleave on the device (replaces build_occurrence_table + the interleave loop)"""
+        L = lib()
+        n_blocks = (n + 63) // 64
+        bwt_occ = torch.empty(n_blocks * 8, dtype=torch.int32, device=bwt_words.device)
+        L2 = (C.c_uint32 * 5)()
+        tb = C.c_size_t(0)
+        r = L.nvb_fm_build_occ(C.c_void_p(bwt_words.data_ptr()), C.c_uint32(n), C.c_void_p(bwt_occ.data_ptr()), L2,
+                               None, C.byref(tb), _stream())
+        if r != -2:
+            check(r, "nvb_fm_build_occ(size query)")
+        temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=bwt_words.device)
+        check(L.nvb_fm_build_occ(C.c_void_p(bwt_words.data_ptr()), C.c_uint32(n), C.c_void_p(bwt_occ.data_ptr()), L2,
+                                 C.c_void_p(temp.data_ptr()), C.byref(tb), _stream()), "nvb_fm_build_occ")
+        return FMIndexDevice(bwt_occ, ssa, list(L2), n, primary)
+
+    @staticmethod
+    def from_text(text_words: torch.Tensor, n: int, want_sa: bool = False):
+        """suffix-sort a 2-bit big-endian packed text on the device and build the whole index.
+        text_words must be readable 2 words past ceil(n/16).  Returns (index, sa or None)."""
+        L = lib()
+        dev = text_words.device
+        bwt = torch.empty(((n + 63) // 64) * 4, dtype=torch.int32, device=dev)
+        ssa = torch.empty((n + 16) // 16, dtype=torch.int32, device=dev)
+        sa = torch.empty(n + 1, dtype=torch.int32, device=dev) if want_sa else None
+        primary = C.c_uint32(0)
+        tb = C.c_size_t(0)
+        args = (C.c_void_p(text_words.data_ptr()), C.c_uint32(n), C.c_void_p(bwt.data_ptr()), C.byref(primary),
+                C.c_void_p(ssa.data_ptr()), C.c_void_p(sa.data_ptr()) if sa is not None else None)
+        r = L.nvb_fm_build_bwt(*args, None, C.byref(tb), _stream())
+        if r != -2:
+            check(r, "nvb_fm_build_bwt(size query)")
+        temp = torch.empty(tb.value, dtype=torch.uint8, device=dev)
+        check(L.nvb_fm_build_bwt(*args, C.c_void_p(temp.data_ptr()), C.byref(tb), _stream()), "nvb_fm_build_bwt")
+        del temp
+        idx = FMIndexDevice.from_bwt(bwt, n, int(primary.value), ssa)
+        return idx, sa
+
+    def to_host(self):
+        return dict(bwt_occ=_np_u32(self.bwt_occ), ssa=None if self.ssa is None else _np_u32(self.ssa),
+                    L2=np.array(self.L2, dtype=np.uint32), n=self.length, primary=self.primary)
+
+
+def rank(fmi: FMIndexDevice, k: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """nvbio::rank(fm_index, k, c) for arrays of (k, c); k int32 (uint32 bit pattern), c uint8"""
+    n = k.numel()
+    out = torch.empty(n, dtype=torch.int32, device=k.device)
+    s = fmi.struct()
+    check(lib().nvb_fm_rank(C.byref(s), C.c_void_p(k.data_ptr()), C.c_void_p(c.data_ptr()), C.c_uint32(n),
+                            C.c_void_p(out.data_ptr()), _stream()), "nvb_fm_rank")
+    return out
+
+
+def match(fmi: FMIndexDevice, queries: PackedStringSet, flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nvbio::match(fm_index, pattern, len) for a string set -> int32 [n,2] inclusive SA ranges (uint32 bits)"""
+    n = queries.count
+    if out is None:
+        out = torch.empty((n, 2), dtype=torch.int32, device=fmi.device)
+    s, q = fmi.struct(), queries.struct()
+    check(lib().nvb_fm_match(C.byref(s), C.byref(q), C.c_uint32(n), C.c_uint32(flags),
+                             C.c_void_p(out.data_ptr()), _stream()), "nvb_fm_match")
+    return out
+
+
+def locate(fmi: FMIndexDevice, rows: torch.Tensor) -> torch.Tensor:
+    """nvbio::locate(fm_index, row) for an array of SA rows"""
+    n = rows.numel()
+    out = torch.empty(n, dtype=torch.int32, device=rows.device)
+    s = fmi.struct()
+    check(lib().nvb_fm_locate(C.byref(s), C.c_void_p(rows.data_ptr()), C.c_uint32(n), C.c_void_p(out.data_ptr()), _stream()),
+          "nvb_fm_locate")
+    return out
+
+
+class FMIndexFilterDevice:
+    """nvbio::FMIndexFilter<device_tag, fm_index_type> (nvbio/fmindex/filter.h:145-214):
+    rank() -> n_hits, then ranges()/slots()/n_hits() and locate(begin, end) -> (text pos, query id) hits."""
+
+    def __init__(self):
+        self._fmi = None
+        self._ranges = None
+        self._slots = None
+        self._n_hits = 0
+        self._n_queries = 0
+
+    def rank(self, fm_index: FMIndexDevice, string_set: PackedStringSet, flags: int = 0) -> int:
+        L = lib()
+        n = string_set.count
+        dev = fm_index.device
+        self._fmi, self._n_queries = fm_index, n
+        self._ranges = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        self._slots = torch.empty(n, dtype=torch.int64, device=dev)
+        n_hits = C.c_uint64(0)
+        tb = C.c_size_t(0)
+        s, q = fm_index.struct(), string_set.struct()
+        r = L.nvb_fm_filter_rank(C.byref(s), C.byref(q), C.c_uint32(n), C.c_uint32(flags), C.c_void_p(self._ranges.data_ptr()),
+                                 C.c_void_p(self._slots.data_ptr()), C.byref(n_hits), None, C.byref(tb), _stream())
+        if r != -2:
+            check(r, "nvb_fm_filter_rank(size query)")
+        temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
+        check(L.nvb_fm_filter_rank(C.byref(s), C.byref(q), C.c_uint32(n), C.c_uint32(flags), C.c_void_p(self._ranges.data_ptr()),
+                                   C.c_void_p(self._slots.data_ptr()), C.byref(n_hits), C.c_void_p(temp.data_ptr()),
+                                   C.byref(tb), _stream()), "nvb_fm_filter_rank")
+        self._n_hits = int(n_hits.value)
+        return self._n_hits
+
+    def n_hits(self):
+        return self._n_hits
+
+    def ranges(self):
+        return self._ranges
+
+    def slots(self):
+        return self._slots
+
+    def locate(self, begin: int, end: int, hits: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._fmi is None:
+            raise NvbError("FMIndexFilterDevice.locate() before rank()")
+        if hits is None:
+            hits = torch.empty((end - begin, 2), dtype=torch.int32, device=self._fmi.device)
+        s = self._fmi.struct()
+        check(lib().nvb_fm_filter_locate(C.byref(s), C.c_void_p(self._ranges.data_ptr()), C.c_void_p(self._slots.data_ptr()),
+                                         C.c_uint32(self._n_queries), C.c_uint64(begin), C.c_uint64(end),
+                                         C.c_void_p(hits.data_ptr()), _stream()), "nvb_fm_filter_locate")
+        return hits

@@ -1,0 +1,127 @@
+// tests/host/host_harness.cu -- TEST INFRASTRUCTURE.
+// Runs the product's per-thread __host__ __device__ routines (fm_core.cuh, gotoh_core.cuh) serially on the
+// CPU so that their logic can be checked against the oracle in the GPU-less dev container.  The kernels
+// proper (thread mapping, shared-memory staging, todo lists) are covered by the -m gpu tests.
+#include "../../nvbio_b200/csrc/fm_core.cuh"
+#include "../../nvbio_b200/csrc/gotoh_core.cuh"
+#include <vector>
+
+using namespace nvb;
+
+static FmIndex mk(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary) {
+    FmIndex f; f.blocks = (const FmBlock*)bwt_occ; f.ssa = ssa; f.n = n; f.primary = primary;
+    for (int i = 0; i < 5; ++i) f.L2[i] = L2[i];
+    return f;
+}
+
+extern "C" {
+
+void hh_fm_rank(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary,
+                const uint32_t* k, const uint8_t* c, uint32_t nq, uint32_t* out) {
+    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary);
+    for (uint32_t i = 0; i < nq; ++i) out[i] = fm_rank1(f, k[i], c[i] & 3u);
+}
+
+void hh_fm_match(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary,
+                 const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len, uint32_t nq,
+                 uint32_t flags, uint32_t* out_xy) {
+    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary);
+    for (uint32_t i = 0; i < nq; ++i) {
+        uint32_t x, y;
+#define CALL(B, E) fm_match_one<B, E>(f, words, off[i], len[i], flags, x, y)
+        NVB_DISPATCH_STREAM(bits, be, CALL);
+#undef CALL
+        out_xy[2 * i] = x; out_xy[2 * i + 1] = y;
+    }
+}
+
+void hh_fm_locate(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
+                  const uint32_t* rows, uint32_t nq, uint32_t* out) {
+    const FmIndex f = mk(bwt_occ, ssa, L2, n, primary);
+    for (uint32_t i = 0; i < nq; ++i) out[i] = fm_locate_one(f, rows[i]);
+}
+
+} // extern "C"
+
+template <int B, int TYPE>
+static void run_generic(const GotohScheme& S, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                        const uint8_t* quals, const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
+                        uint32_t n, int32_t* score, uint32_t* sx, uint32_t* sy) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const SinkResult r = gotoh_generic<B, TYPE>(S, pw, pbits, pbe, poff[i], plen[i], quals, tw, tbits, tbe, toff[i], tlen[i]);
+        score[i] = r.score; sx[i] = r.x; sy[i] = r.y;
+    }
+}
+
+// mirrors gotoh_pair_kernel: precondition check -> packed pair routine, else generic
+template <int B, int TYPE>
+static void run_pair(const GotohScheme& S, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                     const uint32_t* tw, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
+                     uint32_t n, uint32_t sel_rows, int32_t* score, uint32_t* sx, uint32_t* sy, uint32_t* n_fallback) {
+    std::vector<uint16_t> sel(sel_rows + 1);
+    for (uint32_t a0 = 0; a0 < n; a0 += 2) {
+        const bool has1 = a0 + 1 < n;
+        const uint32_t a1 = has1 ? a0 + 1 : a0;
+        const uint32_t M0 = plen[a0], M1 = plen[a1], N0 = tlen[a0], N1 = tlen[a1];
+        const uint32_t Mmax = M0 > M1 ? M0 : M1, L = Mmax + B - 1;
+        const bool ok = M0 >= 1 && M1 >= 1 && N0 >= M0 + B - 1 && N1 >= M1 + B - 1 && L <= sel_rows && (TYPE == NVB_LOCAL || M0 == M1);
+        if (!ok) {
+            for (uint32_t a = a0; a <= a1; ++a) {
+                const SinkResult r = gotoh_generic<B, TYPE>(S, pw, pbits, pbe, poff[a], plen[a], nullptr, tw, 2, tbe, toff[a], tlen[a]);
+                score[a] = r.score; sx[a] = r.x; sy[a] = r.y; ++*n_fallback;
+            }
+            continue;
+        }
+        SymReaderRT r0(tw, 2, tbe), r1(tw, 2, tbe);
+        for (uint32_t t = 0; t < L; ++t) {
+            const uint32_t g0 = t < N0 ? r0.get(toff[a0] + t) : 0u, g1 = t < N1 ? r1.get(toff[a1] + t) : 0u;
+            sel[t] = (uint16_t)pair_selector(g0, g1);
+        }
+        SinkResult q0, q1;
+        gotoh_pair<B, TYPE>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1);
+        score[a0] = q0.score; sx[a0] = q0.x; sy[a0] = q0.y;
+        if (has1) { score[a1] = q1.score; sx[a1] = q1.x; sy[a1] = q1.y; }
+    }
+}
+
+extern "C" {
+
+#define TYPE_SWITCH(BAND, FN, ...) \
+    switch (type) { case 0: FN<BAND, 0>(__VA_ARGS__); return 0; case 1: FN<BAND, 1>(__VA_ARGS__); return 0; case 2: FN<BAND, 2>(__VA_ARGS__); return 0; } return -1;
+
+int hh_gotoh_generic(int band, int type, const int32_t* scheme6, const int32_t* qtab,
+                     const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen, const uint8_t* quals,
+                     const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
+                     uint32_t n, int32_t* score, uint32_t* sx, uint32_t* sy) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab;
+    switch (band) {
+    case 3:  TYPE_SWITCH(3,  run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    case 5:  TYPE_SWITCH(5,  run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    case 7:  TYPE_SWITCH(7,  run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    case 15: TYPE_SWITCH(15, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    case 31: TYPE_SWITCH(31, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    case 63: TYPE_SWITCH(63, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    }
+    return -1;
+}
+
+// returns -2 when the scheme is not admissible for the packed path
+int hh_gotoh_pair(int band, int type, const int32_t* scheme6, uint32_t max_m,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
+                  uint32_t n, int32_t* score, uint32_t* sx, uint32_t* sy, uint32_t* n_fallback) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr;
+    nvb_gotoh_scheme cs; cs.match = S.match; cs.mismatch = S.mismatch; cs.pattern_gap_open = S.pgo; cs.pattern_gap_ext = S.pge;
+    cs.text_gap_open = S.tgo; cs.text_gap_ext = S.tge; cs.d_qual_table = nullptr;
+    if (!pair_path_ok(band, type, &cs, max_m)) return -2;
+    const uint32_t sel_rows = max_m + band - 1;
+    *n_fallback = 0;
+    switch (band) {
+    case 7:  TYPE_SWITCH(7,  run_pair, S, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
+    case 15: TYPE_SWITCH(15, run_pair, S, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
+    case 31: TYPE_SWITCH(31, run_pair, S, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
+    }
+    return -1;
+}
+
+} // extern "C"

@@ -1,0 +1,217 @@
+"""CPU checks of the PRODUCT's per-thread routines (nvbio_b200/csrc/fm_core.cuh, gotoh_core.cuh), compiled
+for the host by tests/host/host_harness.cu, against the oracle.  This is the pre-GPU gate: the same
+functions are what the CUDA kernels call per thread."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+from oracle import orc
+from nvbio_b200.strings import pack_symbols
+from tests.golden.make_golden import random_problems
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "host", "libhost_harness.so")
+SRC = os.path.join(HERE, "host", "host_harness.cu")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def H():
+    deps = [SRC] + [os.path.join(HERE, "..", "nvbio_b200", "csrc", f) for f in ("fm_core.cuh", "gotoh_core.cuh", "common.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+                               "-Wno-deprecated-declarations", "-Xcompiler", "-fPIC", "-shared", "-o", SO, SRC])
+    return C.CDLL(SO)
+
+
+@pytest.fixture(scope="module")
+def O():
+    return orc.Oracle()
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 4097])
+def test_fm_core(H, O, n):
+    rng = np.random.default_rng(n)
+    text = rng.integers(0, 4, n).astype(np.uint8)
+    idx = O.build_index(text)
+    # rank
+    k = rng.integers(0, n + 1, 400).astype(np.uint32); k[:3] = (0xFFFFFFFF, n, idx.primary)
+    c = rng.integers(0, 4, 400).astype(np.uint8)
+    out = np.zeros(400, np.uint32)
+    H.hh_fm_rank(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(k), _p(c), C.c_uint32(400), _p(out))
+    assert np.array_equal(out, O.rank(idx, k, c))
+    # match, every stream format
+    nq = 300
+    lens = rng.integers(1, 26, nq).astype(np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
+    for i in range(0, nq, 2):
+        L = int(lens[i])
+        if n > L:
+            st = int(rng.integers(0, n - L + 1)); q[offs[i]:offs[i] + L] = text[st:st + L]
+    want, _ = O.match(idx, q, offs, lens)
+    for bits, be in ((2, 1), (2, 0), (4, 1), (4, 0), (8, 0)):
+        words = pack_symbols(q, bits, bool(be))
+        got = np.zeros((nq, 2), np.uint32)
+        H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(bits), C.c_uint32(be),
+                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got))
+        assert np.array_equal(got, want), (bits, be)
+    # N rule on a 4-bit stream
+    qn = q.copy(); qn[offs[5] + lens[5] - 1] = 4          # last symbol = first one consumed
+    want_n, _ = O.match(idx, qn, offs, lens)
+    got = np.zeros((nq, 2), np.uint32)
+    words = pack_symbols(qn, 4, True)
+    H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(4), C.c_uint32(1),
+                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got))
+    assert np.array_equal(got, want_n) and tuple(got[5]) == (1, 0)
+    # forward-order + complement == backward search of the reverse complement
+    rc = np.concatenate([(3 - q[o:o + l])[::-1] for o, l in zip(offs, lens)]).astype(np.uint8)
+    want_rc, _ = O.match(idx, rc, offs, lens)
+    words = pack_symbols(q, 2, True)
+    H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
+                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(3), _p(got))
+    assert np.array_equal(got, want_rc)
+    # locate
+    rows = rng.integers(0, n + 1, 300).astype(np.uint32); rows[:3] = (0, idx.primary, n)
+    out = np.zeros(300, np.uint32)
+    H.hh_fm_locate(_p(idx.bwt_occ), _p(idx.ssa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(rows), C.c_uint32(300), _p(out))
+    assert np.array_equal(out, O.locate(idx, rows))
+
+
+def _gotoh_generic(H, band, typ, scheme6, pr, pbits, pbe, tbits, tbe, qual=None, qtab=None):
+    pat, p_off, p_len, txt, t_off, t_len = pr
+    pw, tw = pack_symbols(pat, pbits, bool(pbe)), pack_symbols(txt, tbits, bool(tbe))
+    n = len(p_off)
+    score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+    s6 = np.array(scheme6, np.int32)
+    r = H.hh_gotoh_generic(C.c_int(band), C.c_int(typ), _p(s6), _p(qtab), _p(pw), C.c_uint32(pbits), C.c_uint32(pbe), _p(u32(p_off)), _p(u32(p_len)),
+                           _p(qual), _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(u32(t_off)), _p(u32(t_len)), C.c_uint32(n),
+                           _p(score), _p(sx), _p(sy))
+    assert r == 0
+    return score, sx, sy
+
+
+@pytest.mark.parametrize("band", [3, 5, 7, 15, 31, 63])
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_generic(H, O, band, typ):
+    rng = np.random.default_rng(band * 10 + typ)
+    for scheme in ((2, -2, -5, -3), (1, -3, -2, -4), (0, -5, -8, -3)):
+        pr = random_problems(rng, 40, band, 120, alphabet_text=6)      # text symbols up to 5, read N's
+        want = O.banded_gotoh(band, typ, scheme, *pr)
+        s6 = scheme + (scheme[2], scheme[3])
+        got = _gotoh_generic(H, band, typ, s6, pr, 4, 1, 8, 0)
+        for a, b in zip(got, want[:3]):
+            assert np.array_equal(a, b), (band, typ, scheme)
+    # 2-bit inputs, both endiannesses
+    pr = random_problems(rng, 40, band, 120, alphabet_text=4)
+    want = O.banded_gotoh(band, typ, (2, -2, -5, -3), *pr)
+    for pbe, tbe in ((1, 1), (0, 0), (1, 0)):
+        got = _gotoh_generic(H, band, typ, (2, -2, -5, -3, -5, -3), pr, 2, pbe, 2, tbe)
+        for a, b in zip(got, want[:3]):
+            assert np.array_equal(a, b)
+
+
+def test_gotoh_generic_quality_table(H, O):
+    rng = np.random.default_rng(3)
+    pr = random_problems(rng, 60, 31, 150, alphabet_text=5)
+    qual = rng.integers(0, 60, len(pr[0])).astype(np.uint8)
+    q = np.arange(256)
+    frac = (np.minimum(q, 40).astype(np.float32) / np.float32(40.0))
+    mmp = 2 + (frac * np.float32(6 - 2)).astype(np.int32)
+    qtab = np.ascontiguousarray(np.stack([np.full(256, 2, np.int32), -mmp.astype(np.int32)], axis=1))
+    s6 = (2, -6, -8, -3, -8, -3)
+    for typ in (1, 2):
+        want = O.banded_gotoh(31, typ, s6, *pr, qual=qual, qtab=qtab)
+        got = _gotoh_generic(H, 31, typ, s6, pr, 4, 1, 2 if False else 8, 0, qual=qual, qtab=qtab)
+        for a, b in zip(got, want[:3]):
+            assert np.array_equal(a, b)
+
+
+def fixed_problems(rng, n, band, m, extra_text=0, ragged=False):
+    """nvBowtie-shaped jobs: window = read_len + band (+extra), read sampled near the band centre"""
+    pats, txts, p_off, p_len, t_off, t_len = [], [], [], [], [], []
+    po = to = 0
+    for _ in range(n):
+        mm = int(rng.integers(max(1, m - 40), m + 1)) if ragged else m
+        N = mm + band + extra_text
+        t = rng.integers(0, 4, N).astype(np.uint8)
+        j = int(rng.integers(0, band))
+        p = []
+        while len(p) < mm:
+            r = rng.random()
+            if r < 0.04 or j >= N:
+                p.append(int(rng.integers(0, 4))); j += 1 if r < 0.03 else 0
+            elif r < 0.06:
+                j += 1
+            else:
+                p.append(int(t[j])); j += 1
+        pats.append(np.array(p[:mm], np.uint8)); txts.append(t)
+        p_off.append(po); p_len.append(mm); po += mm
+        t_off.append(to); t_len.append(N); to += N
+    return (np.concatenate(pats), np.array(p_off, np.uint32), np.array(p_len, np.uint32),
+            np.concatenate(txts), np.array(t_off, np.uint32), np.array(t_len, np.uint32))
+
+
+def _gotoh_pair(H, band, typ, scheme6, pr, max_m, pbits=2, pbe=1, tbe=1):
+    pat, p_off, p_len, txt, t_off, t_len = pr
+    pw, tw = pack_symbols(pat, pbits, bool(pbe)), pack_symbols(txt, 2, bool(tbe))
+    n = len(p_off)
+    score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+    nf = C.c_uint32(0)
+    s6 = np.array(scheme6, np.int32)
+    r = H.hh_gotoh_pair(C.c_int(band), C.c_int(typ), _p(s6), C.c_uint32(max_m), _p(pw), C.c_uint32(pbits), C.c_uint32(pbe), _p(u32(p_off)), _p(u32(p_len)),
+                        _p(tw), C.c_uint32(tbe), _p(u32(t_off)), _p(u32(t_len)), C.c_uint32(n), _p(score), _p(sx), _p(sy), C.byref(nf))
+    return r, (score, sx, sy), nf.value
+
+
+@pytest.mark.parametrize("band", [7, 15, 31])
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_pair(H, O, band, typ):
+    rng = np.random.default_rng(100 + band + typ)
+    for scheme in ((2, -2, -5, -3), (2, -1, -1, -1), (0, -5, -8, -3), (1, -3, -2, -4), (2, -6, -8, -3)):
+        s6 = scheme + (scheme[2], scheme[3])
+        for ragged in (False, True):
+            pr = fixed_problems(rng, 51, band, 150, extra_text=int(rng.integers(0, 3)), ragged=ragged)   # odd count: tail pair
+            want = O.banded_gotoh(band, typ, scheme, *pr)
+            r, got, nf = _gotoh_pair(H, band, typ, s6, pr, 150)
+            assert r == 0
+            for a, b in zip(got, want[:3]):
+                assert np.array_equal(a, b), (band, typ, scheme, ragged)
+            if not ragged:
+                assert nf == 0                       # everything went through the packed path
+    # 4-bit patterns with N's, little-endian text
+    pr = list(fixed_problems(rng, 40, band, 100))
+    pr[0] = pr[0].copy(); pr[0][rng.integers(0, len(pr[0]), 30)] = 4
+    want = O.banded_gotoh(band, typ, (2, -2, -5, -3), *pr)
+    r, got, nf = _gotoh_pair(H, band, typ, (2, -2, -5, -3, -5, -3), pr, 100, pbits=4, pbe=1, tbe=0)
+    assert r == 0 and nf == 0
+    for a, b in zip(got, want[:3]):
+        assert np.array_equal(a, b)
+
+
+def test_gotoh_pair_mixed_fallback(H, O):
+    """short windows / empty patterns in a batch go through the generic routine, pairwise"""
+    rng = np.random.default_rng(9)
+    pr = random_problems(rng, 80, 31, 150, alphabet_text=4)
+    want = O.banded_gotoh(31, 1, (2, -2, -5, -3), *pr)
+    r, got, nf = _gotoh_pair(H, 31, 1, (2, -2, -5, -3, -5, -3), pr, 160)
+    assert r == 0 and nf > 0
+    for a, b in zip(got, want[:3]):
+        assert np.array_equal(a, b)
+
+
+def test_pair_path_admission(H):
+    # scores that do not fit the 16-bit budget must be refused (-2), not computed wrongly
+    pr = fixed_problems(np.random.default_rng(1), 4, 31, 50)
+    r, _, _ = _gotoh_pair(H, 31, 1, (40, -2, -5, -3, -5, -3), pr, 150)        # 150*40 >= 2048
+    assert r == -2
+    r, _, _ = _gotoh_pair(H, 31, 2, (2, -2, -200, -3, -200, -3), pr, 150)      # S - Go does not fit int8
+    assert r == -2
