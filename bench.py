@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for nvbio_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--genome-mbp 3000] [--reads 1000000] [--workload seed_extend|fm_match|banded_gotoh]
+
+Default workload = BASELINE.json configs[2] "nvBowtie seed-and-extend: 1M x 150bp single-end, 20bp seeds,
+band=31, synthetic 3Gbp index" -- the configuration the headline metric (Mreads/s, 150 bp, seed+extend) is
+quoted on; it fits one B200.  One step = one pass of the seed+extend hot path (seeds -> FM-index match ->
+locate -> windows -> banded Gotoh LOCAL -> best per read) over one batch of synthetic reads.
+value      : whole-job Mreads/s with the reads already resident in HBM (device events, max over ranks)
+e2e        : the same through the public API with HOST buffers (pinned H2D of the packed reads + D2H of the
+             per-read results inside the timed region)
+roofline   : the FM-index seed-match kernel (HBM-bound random 32-byte gathers), algorithmic bytes / live
+             CUDA-event kernel time vs MEASURED_PEAKS.json
+cpu_baseline: the reference's own templates (oracle/_ref, OpenMP, all host cores) on a bounded read sample
+--impl reference : the reference CPU path alone, same metric/config (rank 0 only)
+Multi-GPU: one process per GPU (torchrun), rank 0 builds the index and NCCL-broadcasts it once; reads are
+sharded (weak scaling: every rank processes its own --reads batch); no collective in the steady state.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCHEME = (2, -2, -5, -3)      # SimpleGotohScheme(2,-2,-5,-3), LOCAL (fmmap.cu:358 precedent)
+SEED_LEN, SEED_INTERVAL, BAND, READ_LEN = 20, 10, 31, 150
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="seed_extend", choices=["seed_extend", "fm_match", "banded_gotoh"])
+    ap.add_argument("--genome-mbp", type=float, default=3000.0)
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def setup_dist(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+        local = 0
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def build_index(args, rank, world, device):
+    """rank 0 builds (genome, FM-index) on its GPU; the others receive replicas over NCCL"""
+    import nvbio_b200 as nb
+    from nvbio_b200 import synth, dist as nd
+    n = int(args.genome_mbp * 1e6)
+    t_build = t_bcast = 0.0
+    fmi = genome = None
+    if rank == 0:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        genome = synth.random_genome_words(n, device=device)
+        fmi, _ = nb.FMIndexDevice.from_text(genome, n)
+        torch.cuda.synchronize(); t_build = time.perf_counter() - t0
+        torch.cuda.empty_cache()
+    if world > 1:
+        barrier(world); t0 = time.perf_counter()
+        fmi, genome = nd.broadcast_index(fmi, genome, device, src=0)
+        barrier(world); t_bcast = time.perf_counter() - t0
+    return n, genome, fmi, t_build, t_bcast
+
+
+def make_reads(genome, n, n_reads, rank, device):
+    from nvbio_b200 import synth
+    rw, pos, strand = synth.sample_reads(genome, n, n_reads, READ_LEN, sub_rate=0.01, indel_rate=0.001, device=device,
+                                         seed=synth.SEED_QUERIES + 7919 * rank, mut_seed=synth.SEED_MUT + 104729 * rank)
+    return rw.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
+    """the reference's CPU path (oracle/_ref if present, else the C port) on a bounded sample per step"""
+    from oracle import orc
+    from oracle.cpu_pipeline import cpu_seed_extend
+    from nvbio_b200 import synth
+    E = orc.Ref() if orc.Ref.available() else orc.Oracle()
+    cores = E.num_threads() if E.kind == "reference" else 1
+    host = fmi.to_host()
+    idx = orc._Index(n=host["n"], primary=host["primary"], bwt_occ=host["bwt_occ"], ssa=host["ssa"], L2=host["L2"])
+    gw = genome.cpu().numpy().view(np.uint32)
+    nsample = args.cpu_sample
+    times, res = [], None
+    O = orc.Oracle() if want_blocks else None
+    for it in range(warmup + steps):
+        rw = make_reads(genome, n, nsample, 1000 + it, genome.device)
+        words = rw.cpu().numpy().view(np.uint32)
+        sym = _unpack_rows(words, READ_LEN)
+        res = cpu_seed_extend(E, idx, gw, sym, SEED_LEN, SEED_INTERVAL, BAND, 1, SCHEME, True, 100,
+                              count_blocks_with=(O if (want_blocks and it == 0) else None))
+        if it == 0 and want_blocks:
+            blocks_per_seed = res["blocks"] / res["n_seeds"]
+        if it >= warmup:
+            times.append(res["t_total"])
+    t = float(np.mean(times)) if times else float("nan")
+    out = dict(kind=E.kind, cores=cores, sample="%d reads x %d bp per step (%d seeds, %d extensions), C calls only" %
+               (nsample, READ_LEN, res["n_seeds"], res["n_hits"]), value=nsample / t / 1e6, unit="Mreads/s",
+               ms_per_step=t * 1e3, t_match_ms=res["t_match"] * 1e3, t_locate_ms=res["t_locate"] * 1e3, t_dp_ms=res["t_dp"] * 1e3,
+               gcups=res["cells"] / res["t_dp"] / 1e9 if res["t_dp"] > 0 else None,
+               mseeds_per_s=res["n_seeds"] / res["t_match"] / 1e6 if res["t_match"] > 0 else None)
+    if want_blocks:
+        out["blocks_per_seed"] = blocks_per_seed
+    return out
+
+
+def _unpack_rows(words, L):
+    i = np.arange(L)
+    sh = (30 - 2 * (i & 15)).astype(np.uint32)
+    return ((words[:, i >> 4] >> sh) & 3).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    # under torchrun only rank 0 works; the other ranks exit 0 at once (no process group is needed)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    # the index is built on the device as untimed set-up (a 3 Gbp suffix sort on the host takes ~1 h); the
+    # timed path is the reference's CPU code only
+    n, genome, fmi, t_build, _ = build_index(args, 0, 1, device)
+    r = cpu_reference_leg(args, n, genome, fmi, args.steps, args.warmup, want_blocks=False)
+    line = {
+        "impl": "reference", "metric": "Mreads/s (150bp) seed+extend", "value": r["value"], "unit": "Mreads/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, n, args.cpu_sample, world=1),
+        "cpu_baseline": {"value": r["value"], "unit": "Mreads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "fm_match_Mseeds_s": r["mseeds_per_s"], "banded_gotoh_GCUPS": r["gcups"]},
+        "e2e": {"value": r["value"], "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "index_build": "device suffix sort (set-up, untimed): %.1f s" % t_build,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n, reads_per_gpu, world):
+    return {"workload": "nvBowtie seed-and-extend: %d x %dbp single-end reads per GPU, %dbp seeds every %dbp on both strands, "
+                        "band=%d Gotoh LOCAL (2,-2,-5,-3), synthetic %.0f Mbp 2-bit genome / FM-index (occ every 64, SA every 16)"
+                        % (reads_per_gpu, READ_LEN, SEED_LEN, SEED_INTERVAL, BAND, n / 1e6),
+            "reads_per_gpu_per_step": reads_per_gpu, "genome_bp": n, "parallelism": "dp%d (index replicated by one NCCL broadcast)" % world,
+            "l2": "index (%.2f GB) and SSA exceed L2; a 512 MiB buffer is overwritten between timed steps" % (n / 64 * 32 / 1e9)}
+
+
+def run_ours(args):
+    import nvbio_b200 as nb
+    from nvbio_b200 import aln
+    from nvbio_b200.strings import PackedStringSet
+    from nvbio_b200.pipeline import SeedExtendWorkspace, last_stage_ms
+    from nvbio_b200 import dist as nd
+
+    rank, local, world = setup_dist(args)
+    device = torch.device("cuda", local)
+    nb.lib()                                            # fail loudly if the CUDA library is missing
+    n, genome, fmi, t_build, t_bcast = build_index(args, rank, world, device)
+    n_reads = args.reads
+    params = nb.SeedExtendParams(seed_len=SEED_LEN, seed_interval=SEED_INTERVAL, band_len=BAND, type=aln.LOCAL,
+                                 both_strands=True, max_seed_hits=100, scheme=aln.SimpleGotohScheme(*SCHEME))
+    batches = [make_reads(genome, n, n_reads, rank * 16 + b, device) for b in range(2)]
+    wpr = batches[0].shape[1]
+
+    def as_set(words):
+        return PackedStringSet.fixed(words.reshape(-1), n_reads, READ_LEN, stride=wpr * 16)
+    hit_capacity = 24 * n_reads
+    ws = SeedExtendWorkspace(fmi, genome, as_set(batches[0]), params, hit_capacity, keep_hits=False)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step(words):
+        nb.seed_extend(fmi, genome, as_set(words), params, workspace=ws)
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for i in range(args.warmup):
+        flush.zero_(); step(batches[i % 2])
+    barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    total_ms, stage_acc, hits = 0.0, None, 0
+    for i in range(args.steps):
+        flush.zero_()
+        ev0.record(); step(batches[i % 2]); ev1.record()
+        torch.cuda.synchronize()
+        total_ms += ev0.elapsed_time(ev1)
+        st = last_stage_ms()
+        stage_acc = st if stage_acc is None else {k: stage_acc[k] + st[k] for k in st}
+        kept, hits = [int(v) for v in ws.n_hits.cpu()]
+        if kept != hits:
+            raise SystemExit("bench: hit capacity %d exceeded (%d hits): results would be truncated" % (hit_capacity, hits))
+    barrier(world)
+    clocks = sampler.stop()
+    total_ms = nd.max_over_ranks(total_ms, device)
+    ms_per_step = total_ms / args.steps
+    value = world * n_reads / (ms_per_step * 1e-3) / 1e6
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    found = float((ws.best_score > READ_LEN).float().mean())
+
+    # ---- end to end through the public API with host buffers -----------------------------------
+    host_reads = [b.cpu().pin_memory() for b in batches]
+    dev_in = torch.empty_like(batches[0])
+    host_score = torch.empty(n_reads, dtype=torch.int32).pin_memory()
+    host_pos = torch.empty(n_reads, dtype=torch.int32).pin_memory()
+
+    def e2e_step(i):
+        dev_in.copy_(host_reads[i % 2], non_blocking=True)
+        step(dev_in)
+        host_score.copy_(ws.best_score, non_blocking=True)
+        host_pos.copy_(ws.best_pos, non_blocking=True)
+    for i in range(args.warmup):
+        flush.zero_(); e2e_step(i)
+    barrier(world)
+    e2e_ms = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        ev0.record(); e2e_step(i); ev1.record()
+        torch.cuda.synchronize()
+        e2e_ms += ev0.elapsed_time(ev1)
+    barrier(world)
+    e2e_ms = nd.max_over_ranks(e2e_ms, device) / args.steps
+    e2e_value = world * n_reads / (e2e_ms * 1e-3) / 1e6
+    h2d = batches[0].numel() * 4
+    d2h = n_reads * 8
+
+    if rank != 0:
+        return
+    # ---- CPU baseline + algorithmic bytes (rank 0, N=1 only) ----------------------------------
+    cpu = None
+    n_seeds = 2 * n_reads * ((READ_LEN - SEED_LEN) // SEED_INTERVAL + 1)
+    blocks_per_seed = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_leg(args, n, genome, fmi, steps=1, warmup=1, want_blocks=True)
+        blocks_per_seed = r["blocks_per_seed"]
+        cpu = {"value": r["value"], "unit": "Mreads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "fm_match_Mseeds_s": r["mseeds_per_s"], "banded_gotoh_GCUPS": r["gcups"]}
+    if blocks_per_seed is None:
+        # (L-1) + log4(n/64) blocks per seed: the closed form SURVEY.md 8d fits to the exact counts
+        blocks_per_seed = (SEED_LEN - 1) + float(np.log(max(n / 64.0, 1.0)) / np.log(4.0))
+    peak, peak_src = measured_peaks()
+    bytes_per_seed = 32.0 * blocks_per_seed + SEED_LEN * 2 / 8.0 + 8.0
+    fm_ms = stage_ms["seed_match"]
+    achieved = n_seeds * bytes_per_seed / (fm_ms * 1e-3) / 1e9
+    cells = hits * READ_LEN * BAND
+    line = {
+        "metric": "Mreads/s (150bp) seed+extend", "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": workload_config(args, n, n_reads, world),
+        "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": 8 * args.steps,
+        "clocks": clocks,
+        "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "ms_per_launch": fm_ms,
+                     "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": blocks_per_seed,
+                     "note": "32 B x distinct {bwt,occ} blocks per LF step (oracle count on the CPU sample) + query + 8 B out"},
+        "stage_ms": stage_ms,
+        "fm_match_Mseeds_s": n_seeds / (fm_ms * 1e-3) / 1e6,
+        "banded_gotoh": {"alignments_per_step": hits, "GCUPS": cells / (stage_ms["extend"] * 1e-3) / 1e9, "band": BAND,
+                         "note": "integer-issue bound (DPX s16x2), not HBM"},
+        "reads_found_frac": found,
+        "index": {"build_s": t_build, "broadcast_s": t_bcast, "bytes": fmi.nbytes() + genome.numel() * 4},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nvbio_b200 has no CPU fallback")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -188,8 +188,9 @@ typedef struct nvb_seed_extend_params {
 /* reads: n_reads strings (2- or 4-bit).  genome: 2-bit big-endian packed text of fmi->length symbols.
  * Outputs: d_best_score[n_reads] (INT_MIN when a read has no hit), d_best_pos[n_reads] = genome
  * coordinate of the best alignment's end (window begin + sink.x; 0xFFFFFFFF when none).
- * Optional per-hit outputs (may be NULL) of capacity hit_capacity: d_hit_read, d_hit_window (begin,end),
- * d_hit_score, d_hit_sink; *d_n_hits receives the number of hits (device counter).
+ * Optional per-hit outputs (may be NULL) of capacity hit_capacity: d_hit_read (string id = read*strands
+ * + strand), d_hit_window (begin,end), d_hit_score, d_hit_sink; d_n_hits[0] receives the number of hits
+ * kept (<= hit_capacity) and d_n_hits[1] the number found (device counters, no host round trip).
  * Returns NVB_E_TEMP_SIZE with the needed size when d_temp is NULL/too small. */
 int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,
@@ -198,6 +199,12 @@ int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
                     int32_t* d_hit_score, nvb_uint2* d_hit_sink,
                     void* d_temp, size_t* temp_bytes, void* stream);
+
+/* Profiling aid (the reference wraps every stage in cuda::Timer, nvBowtie/bowtie2/cuda/aligner_best_approx.h:
+ * 219-241): device time in ms of the six stages of the most recent nvb_seed_extend call -- [fw,rc] strings,
+ * seed match (FM-index), hit slots, locate + windows, banded extension, best-per-read.  Synchronises on the
+ * call's last event. */
+int nvb_seed_extend_stage_ms(float ms[6]);
 
 #ifdef __cplusplus
 }

@@ -159,6 +159,21 @@ pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, c
 
 using namespace nvb;
 
+// stage boundaries of the most recent nvb_seed_extend call (events are recorded on the caller's stream; they
+// cost no synchronisation).  [0]=start, then after: strings, seed match, slots, locate+windows, extension, reduce
+static cudaEvent_t g_stage_ev[7];
+static bool g_stage_ev_ready = false;
+static bool g_stage_ev_valid = false;
+#define NVB_STAGE(i) do { if (g_stage_ev_ready) NVB_CUDA_TRY(cudaEventRecord(g_stage_ev[i], s)); } while (0)
+
+extern "C" int nvb_seed_extend_stage_ms(float ms[6])
+{
+    if (!ms || !g_stage_ev_valid) return NVB_E_INVALID;
+    NVB_CUDA_TRY(cudaEventSynchronize(g_stage_ev[6]));
+    for (int i = 0; i < 6; ++i) NVB_CUDA_TRY(cudaEventElapsedTime(&ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
+    return NVB_OK;
+}
+
 extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,
                     const nvb_seed_extend_params* P, uint32_t hit_capacity,
@@ -226,6 +241,11 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     cudaStream_t s = as_stream(stream);
     const FmIndex f = make_fmindex(fmi);
     const StrSet rd = make_strset(reads);
+    if (!g_stage_ev_ready) {
+        for (int i = 0; i < 7; ++i) NVB_CUDA_TRY(cudaEventCreate(&g_stage_ev[i]));
+        g_stage_ev_ready = true;
+    }
+    NVB_STAGE(0);
 
     // 1. [fw, rc] strings
     {
@@ -235,6 +255,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
         else             pipe_make_strings_kernel<4><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
         NVB_LAUNCH_CHECK();
     }
+    NVB_STAGE(1);
     // 2. seed ranges
     {
         const uint32_t grid = (nq + 255) / 256;
@@ -242,16 +263,19 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
         else             pipe_seed_match_kernel<4><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, ranges, sizes);
         NVB_LAUNCH_CHECK();
     }
+    NVB_STAGE(2);
     // 3. hit slots
     NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, sizes, excl, (int)nq, s));
     pipe_count_kernel<<<1, 32, 0, s>>>(excl, sizes, nq, hit_capacity, counts);
     NVB_LAUNCH_CHECK();
+    NVB_STAGE(3);
     // 4. locate + windows
     const uint32_t hgrid = (hit_capacity + 255) / 256;
     if (hit_capacity) {
         pipe_expand_hits_kernel<<<hgrid, 256, 0, s>>>(f, g, ranges, excl, str_len_, counts, hit_string, p_off, p_len, t_off, t_len);
         NVB_LAUNCH_CHECK();
     }
+    NVB_STAGE(4);
     // 5. extension
     pats.d_words = str_words; pats.d_offsets = p_off; pats.d_lengths = p_len;
     txts.d_words = d_genome;  txts.d_offsets = t_off; txts.d_lengths = t_len;
@@ -261,6 +285,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
                                                       h_score, (nvb_uint2*)h_sink, gotoh_tmp, &gb, stream);
         if (r != NVB_OK) return r;
     }
+    NVB_STAGE(5);
     // 6. best per read
     NVB_CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * n_reads, s));
     if (hit_capacity) {
@@ -274,5 +299,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
         NVB_LAUNCH_CHECK();
     }
     if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    NVB_STAGE(6);
+    g_stage_ev_valid = true;
     return NVB_OK;
 }

@@ -75,3 +75,13 @@ def seed_extend(fmi: FMIndexDevice, genome: torch.Tensor, reads: PackedStringSet
     tb = C.c_size_t(workspace.temp_bytes)
     check(_call(fmi, genome, reads, params, workspace, workspace.temp, tb), "nvb_seed_extend")
     return workspace
+
+
+STAGES = ("strings", "seed_match", "hit_slots", "locate_windows", "extend", "reduce")
+
+
+def last_stage_ms():
+    """device time (ms) of the stages of the most recent seed_extend call"""
+    ms = (C.c_float * 6)()
+    check(lib().nvb_seed_extend_stage_ms(ms), "nvb_seed_extend_stage_ms")
+    return dict(zip(STAGES, [float(v) for v in ms]))

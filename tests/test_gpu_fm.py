@@ -1,0 +1,182 @@
+"""-m gpu: FM-index parity through the C ABI (nvbio_b200 python mirror -> libnvbio_b200.so) against
+the golden fixtures produced by the reference and against the oracle on fresh seeded inputs."""
+import os
+import numpy as np
+import pytest
+import torch
+from oracle import orc
+import nvbio_b200 as nb
+from nvbio_b200.strings import pack_symbols, PackedStringSet
+from tests.gpu_util import require_gpu, dev_u32, host_u32, mask_pad
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def O():
+    require_gpu()
+    return orc.Oracle()
+
+
+def upload(idx):
+    return nb.FMIndexDevice.from_host(idx["bwt_occ"] if isinstance(idx, dict) else idx.bwt_occ,
+                                      idx["ssa"] if isinstance(idx, dict) else idx.ssa,
+                                      idx["L2"] if isinstance(idx, dict) else idx.L2,
+                                      idx["n"] if isinstance(idx, dict) else idx.n,
+                                      idx["primary"] if isinstance(idx, dict) else idx.primary)
+
+
+def test_golden_fixtures(O):
+    g = np.load(os.path.join(GOLD, "fmindex.npz"))
+    for name in ("rand", "rep", "allA", "tiny"):
+        text = g[f"{name}_text"]
+        n = len(text)
+        fmi = nb.FMIndexDevice.from_host(g[f"{name}_bwt_occ"], g[f"{name}_ssa"], g[f"{name}_L2"], n, int(g[f"{name}_primary"][0]))
+        q = PackedStringSet.from_symbols(g[f"{name}_q"], g[f"{name}_q_off"], g[f"{name}_q_len"], bits=2)
+        assert np.array_equal(host_u32(nb.match(fmi, q)), g[f"{name}_ranges"]), name
+        assert np.array_equal(host_u32(nb.locate(fmi, dev_u32(g[f"{name}_rows"]))), g[f"{name}_pos"]), name
+        k, c = dev_u32(g[f"{name}_rank_k"]), torch.from_numpy(g[f"{name}_rank_c"]).cuda()
+        assert np.array_equal(host_u32(nb.rank(fmi, k, c)), g[f"{name}_rank_out"]), name
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 1000, 50021, 300000])
+def test_device_index_build_matches_oracle(O, n):
+    rng = np.random.default_rng(n)
+    text = rng.integers(0, 4, n).astype(np.uint8)
+    ref = O.build_index(text)
+    words = dev_u32(pack_symbols(text, 2, True))
+    fmi, sa = nb.FMIndexDevice.from_text(words, n, want_sa=True)
+    assert np.array_equal(host_u32(sa).astype(np.int64), ref.sa.astype(np.int64))
+    assert fmi.primary == ref.primary
+    assert np.array_equal(np.array(fmi.L2, np.uint32), ref.L2)
+    assert np.array_equal(mask_pad(host_u32(fmi.bwt_occ), n), mask_pad(ref.bwt_occ, n))
+    assert np.array_equal(host_u32(fmi.ssa), ref.ssa)
+
+
+@pytest.mark.parametrize("kind", ["allA", "period2", "period7", "blocks", "long_repeat"])
+def test_device_suffix_sort_repetitive(O, kind):
+    """ties far beyond the 32-symbol radix key: exercises the prefix-doubling rounds"""
+    rng = np.random.default_rng(5)
+    if kind == "allA":
+        text = np.zeros(5000, np.uint8)
+    elif kind == "period2":
+        text = np.tile(np.array([1, 2], np.uint8), 3000)[:5999]
+    elif kind == "period7":
+        text = np.tile(rng.integers(0, 4, 7).astype(np.uint8), 1200)
+    elif kind == "blocks":
+        blk = rng.integers(0, 4, 300).astype(np.uint8)
+        text = np.concatenate([blk, blk, rng.integers(0, 4, 50).astype(np.uint8), blk, blk[:200]])
+    else:
+        a = rng.integers(0, 4, 20000).astype(np.uint8)
+        text = np.concatenate([a, rng.integers(0, 4, 13).astype(np.uint8), a[:15000]])
+    n = len(text)
+    ref = O.build_index(text)
+    fmi, sa = nb.FMIndexDevice.from_text(dev_u32(pack_symbols(text, 2, True)), n, want_sa=True)
+    assert np.array_equal(host_u32(sa).astype(np.int64), ref.sa.astype(np.int64)), kind
+    assert fmi.primary == ref.primary
+    assert np.array_equal(mask_pad(host_u32(fmi.bwt_occ), n), mask_pad(ref.bwt_occ, n))
+
+
+def _queries(rng, text, nq, lo=1, hi=30, n_frac=0.0):
+    n = len(text)
+    lens = rng.integers(lo, hi + 1, nq).astype(np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
+    for i in range(0, nq, 2):
+        L = int(lens[i])
+        if n > L:
+            st = int(rng.integers(0, n - L + 1)); q[offs[i]:offs[i] + L] = text[st:st + L]
+    if n_frac:
+        for i in rng.integers(0, nq, int(nq * n_frac)):
+            q[offs[i] + rng.integers(0, lens[i])] = 4
+    return q, offs, lens
+
+
+@pytest.mark.parametrize("bits,be", [(2, True), (2, False), (4, True), (4, False), (8, False)])
+def test_match_all_stream_formats(O, bits, be):
+    rng = np.random.default_rng(bits * 2 + be)
+    text = rng.integers(0, 4, 70001).astype(np.uint8)
+    idx = O.build_index(text)
+    fmi = upload(idx)
+    q, offs, lens = _queries(rng, text, 20000, n_frac=0.02 if bits > 2 else 0.0)
+    want, _ = O.match(idx, q, offs, lens)
+    got = host_u32(nb.match(fmi, PackedStringSet.from_symbols(q, offs, lens, bits=bits, big_endian=be)))
+    assert np.array_equal(got, want)
+    # nvBowtie's reverse-complement seed search: forward order + complement on the forward index
+    if bits == 2:
+        rc = np.concatenate([(3 - q[o:o + l])[::-1] for o, l in zip(offs, lens)]).astype(np.uint8)
+        want_rc, _ = O.match(idx, rc, offs, lens)
+        got_rc = host_u32(nb.match(fmi, PackedStringSet.from_symbols(q, offs, lens, bits=2, big_endian=be),
+                                   flags=nb.MATCH_FORWARD_ORDER | nb.MATCH_COMPLEMENT))
+        assert np.array_equal(got_rc, want_rc)
+
+
+def test_empty_and_degenerate(O):
+    text = np.random.default_rng(2).integers(0, 4, 1000).astype(np.uint8)
+    idx = O.build_index(text)
+    fmi = upload(idx)
+    # zero queries
+    q = PackedStringSet.from_symbols(np.zeros(4, np.uint8), np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    assert nb.match(fmi, q).shape[0] == 0
+    # zero-length query -> the whole range (0, n) as in the reference
+    q = PackedStringSet.from_symbols(np.zeros(4, np.uint8), [0, 1], [0, 1])
+    r = host_u32(nb.match(fmi, q))
+    assert tuple(r[0]) == (0, 1000)
+    # fixed-stride set == offsets set
+    sym = np.random.default_rng(3).integers(0, 4, 22 * 64).astype(np.uint8)
+    a = PackedStringSet.from_symbols(sym, np.arange(64) * 22, np.full(64, 22))
+    b = PackedStringSet.fixed(a.words, 64, 22)
+    assert torch.equal(nb.match(fmi, a), nb.match(fmi, b))
+
+
+def test_filter_rank_locate(O):
+    """FMIndexFilter semantics (filter_inl.h:268-402): ranges, uint64 slots, hits = (text pos, query id)"""
+    rng = np.random.default_rng(17)
+    text = np.tile(rng.integers(0, 4, 4000).astype(np.uint8), 3)     # every seed occurs >= 3 times
+    idx = O.build_index(text)
+    fmi = upload(idx)
+    q, offs, lens = _queries(rng, text, 3000, lo=6, hi=14)
+    want, _ = O.match(idx, q, offs, lens)
+    flt = nb.FMIndexFilterDevice()
+    n_hits = flt.rank(fmi, PackedStringSet.from_symbols(q, offs, lens))
+    assert np.array_equal(host_u32(flt.ranges()), want)
+    sizes = np.where(want[:, 0] <= want[:, 1], want[:, 1].astype(np.int64) - want[:, 0] + 1, 0)
+    slots = np.cumsum(sizes)
+    assert n_hits == int(slots[-1])
+    assert np.array_equal(flt.slots().cpu().numpy(), slots)
+    # expected hits in slot order
+    rows = np.concatenate([np.arange(x, x + s, dtype=np.uint32) for (x, _), s in zip(want, sizes)])
+    qid = np.repeat(np.arange(len(sizes), dtype=np.uint32), sizes)
+    pos = O.locate(idx, rows)
+    for b, e in ((0, n_hits), (17, min(n_hits, 5000)), (n_hits - 1, n_hits)):
+        hits = host_u32(flt.locate(b, e))
+        assert np.array_equal(hits[:, 0], pos[b:e]) and np.array_equal(hits[:, 1], qid[b:e])
+    # located text really carries the query (fmindex_test.cu:611-664)
+    hits = host_u32(flt.locate(0, min(n_hits, 2000)))
+    for p, i in hits[::97]:
+        L = int(lens[i]); assert np.array_equal(text[p:p + L], q[offs[i]:offs[i] + L])
+
+
+def test_large_index_properties():
+    """size-independent properties on a 20 Mbp device-built index: every sampled seed hits its own
+    position; ranges are stable under query permutation; forward+complement == reverse complement."""
+    require_gpu()
+    from nvbio_b200 import synth
+    n = 20_000_000
+    words = synth.random_genome_words(n)
+    fmi, _ = nb.FMIndexDevice.from_text(words, n)
+    assert sum(fmi.L2[i + 1] - fmi.L2[i] for i in range(4)) == n
+    sw, pos = synth.sample_seeds(words, n, 200_000, 22)
+    q = PackedStringSet.fixed(sw.reshape(-1), 200_000, 22, stride=32)
+    r = nb.match(fmi, q)
+    x = r[:, 0].to(torch.int64) & 0xFFFFFFFF
+    y = r[:, 1].to(torch.int64) & 0xFFFFFFFF
+    assert bool((x <= y).all())
+    one = (x == y)
+    assert one.float().mean() > 0.99
+    located = nb.locate(fmi, r[:, 0][one].contiguous()).to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(located, pos[one])
+    perm = torch.randperm(200_000, device="cuda")
+    q2 = PackedStringSet.fixed(sw[perm].contiguous().reshape(-1), 200_000, 22, stride=32)
+    assert torch.equal(nb.match(fmi, q2), r[perm])

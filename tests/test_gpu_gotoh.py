@@ -1,0 +1,158 @@
+"""-m gpu: banded Gotoh parity through the C ABI against the reference-generated golden fixtures and the
+oracle; the packed DPX path and the generic int32 path are both exercised and compared with each other."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+import torch
+from oracle import orc
+import nvbio_b200 as nb
+from nvbio_b200 import aln
+from nvbio_b200.strings import PackedStringSet
+from tests.gpu_util import require_gpu, host_u32
+from tests.golden.make_golden import G1_P, G1_T, G2_P, G2_T, random_problems
+from tests.test_host_core import fixed_problems
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def O():
+    require_gpu()
+    return orc.Oracle()
+
+
+def force_path(p):
+    nb.lib().nvb_debug_force_gotoh_path(C.c_int(p))
+
+
+def run(band, typ, scheme, pr, pbits=4, tbits=8, pbe=True, tbe=False, quals=None, max_m=None):
+    pat, p_off, p_len, txt, t_off, t_len = pr
+    P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=pbits, big_endian=pbe)
+    T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=tbits, big_endian=tbe)
+    if max_m is not None:
+        P.length = max_m
+    sch = scheme if not isinstance(scheme, tuple) else aln.SimpleGotohScheme(*scheme)
+    q = torch.from_numpy(quals).cuda() if quals is not None else None
+    s, k = aln.batch_banded_alignment_score(band, aln.make_gotoh_aligner(typ, sch), P, T, quals=q)
+    torch.cuda.synchronize()
+    k = host_u32(k)
+    return s.cpu().numpy(), k[:, 0], k[:, 1]
+
+
+def same(got, want):
+    return all(np.array_equal(a, b) for a, b in zip(got, want[:3]))
+
+
+def test_reference_asserted_problems(O):
+    g = np.load(os.path.join(GOLD, "banded_gotoh.npz"))
+    for name, P, T, scheme, band in (("g1", G1_P, G1_T, (2, -1, -1, -1), 7), ("g2", G2_P, G2_T, (0, -5, -8, -3), 31)):
+        p, t = orc.dna(P), orc.dna(T)
+        for typ in (0, 1, 2):
+            for tbits in (2, 8):            # 2-bit text -> packed DPX path (when admissible), 8-bit -> generic
+                s, x, y = run(band, typ, scheme, (p, [0], [len(p)], t, [0], [len(t)]), pbits=2, tbits=tbits, tbe=True)
+                assert (int(s[0]), int(x[0]), int(y[0])) == tuple(int(v) for v in g[f"{name}_t{typ}"][:3]), (name, typ, tbits)
+
+
+def test_golden_random(O):
+    g = np.load(os.path.join(GOLD, "banded_gotoh.npz"))
+    for cid, band, typ, m, mm, go, ge in g["cases"]:
+        pr = [g[f"r{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        res = g[f"r{cid}_res"]
+        s, x, y = run(int(band), int(typ), (int(m), int(mm), int(go), int(ge)), pr)
+        assert np.array_equal(s.astype(np.int64), res[0]), (cid, band, typ)
+        assert np.array_equal(x.astype(np.int64), res[1]) and np.array_equal(y.astype(np.int64), res[2]), (cid, band, typ)
+
+
+@pytest.mark.parametrize("band", [7, 15, 31])
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_packed_path_vs_oracle(O, band, typ):
+    rng = np.random.default_rng(band * 7 + typ)
+    for scheme in ((2, -2, -5, -3), (2, -1, -1, -1), (0, -5, -8, -3), (1, -3, -2, -4), (2, -6, -8, -3)):
+        for ragged in (False, True):
+            pr = fixed_problems(rng, 1037, band, 150, extra_text=int(rng.integers(0, 3)), ragged=ragged)
+            want = O.banded_gotoh(band, typ, scheme, *pr)
+            for pbits, tbe in ((2, True), (4, False)):
+                force_path(0)
+                assert same(run(band, typ, scheme, pr, pbits=pbits, tbits=2, tbe=tbe, max_m=150), want), (band, typ, scheme, ragged)
+            force_path(1)
+            try:
+                assert same(run(band, typ, scheme, pr, pbits=2, tbits=2, tbe=True, max_m=150), want)
+            finally:
+                force_path(0)
+
+
+def test_mixed_batch_fallback_list(O):
+    """batches mixing admissible pairs with short windows / N's / empty patterns"""
+    rng = np.random.default_rng(1)
+    pr = random_problems(rng, 3001, 31, 150, alphabet_text=4)
+    want = O.banded_gotoh(31, 1, (2, -2, -5, -3), *pr)
+    assert same(run(31, 1, (2, -2, -5, -3), pr, pbits=4, tbits=2, tbe=True, max_m=160), want)
+    # empty batch and a single alignment
+    e = (np.zeros(4, np.uint8), np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(4, np.uint8), np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    s, x, y = run(31, 1, (2, -2, -5, -3), e, pbits=2, tbits=2, tbe=True)
+    assert len(s) == 0
+    one = fixed_problems(rng, 1, 31, 150)
+    assert same(run(31, 1, (2, -2, -5, -3), one, pbits=2, tbits=2, tbe=True), O.banded_gotoh(31, 1, (2, -2, -5, -3), *one))
+    # text shorter than the pattern -> BestSink defaults
+    short = (np.zeros(10, np.uint8), np.array([0], np.uint32), np.array([10], np.uint32), np.zeros(8, np.uint8), np.array([0], np.uint32), np.array([5], np.uint32))
+    s, x, y = run(31, 1, (2, -2, -5, -3), short, pbits=2, tbits=2, tbe=True)
+    assert int(s[0]) == -2**31 and int(x[0]) == 0xFFFFFFFF and int(y[0]) == 0xFFFFFFFF
+
+
+def test_quality_table_scheme(O):
+    """nvBowtie's quality-dependent substitution (scoring.h:86-105,281) through the table interface"""
+    rng = np.random.default_rng(4)
+    pr = random_problems(rng, 2000, 31, 150, alphabet_text=5)
+    qual = rng.integers(0, 60, len(pr[0])).astype(np.uint8)
+    sch = aln.QualityGotohScheme(match_bonus=2, mm_min=2, mm_max=6, read_gap_const=5, read_gap_coeff=3, ref_gap_const=5, ref_gap_coeff=3)
+    assert sch.pgo == -8 and sch.pge == -3
+    # the padded per-string quality layout: quals are indexed like the pattern stream
+    for typ in (1, 2):
+        want = O.banded_gotoh(31, typ, (2, int(sch.table_host[0, 1]), sch.pgo, sch.pge, sch.tgo, sch.tge), *pr, qual=qual, qtab=sch.table_host)
+        assert same(run(31, typ, sch, pr, pbits=4, tbits=8, quals=qual), want)
+
+
+def test_scores_out_of_int16_budget_use_int32(O):
+    """a scheme the packed path must refuse is still scored exactly (generic int32 kernel)"""
+    rng = np.random.default_rng(8)
+    pr = fixed_problems(rng, 500, 31, 150)
+    for scheme in ((300, -200, -500, -300), (40, -2, -5, -3)):
+        want = O.banded_gotoh(31, 1, scheme, *pr)
+        assert same(run(31, 1, scheme, pr, pbits=2, tbits=2, tbe=True), want)
+
+
+def test_full_size_properties():
+    """C4-shaped batch (1M x 151 bp vs 300 bp windows): packed path == generic path bit for bit, scores of
+    exact substrings equal 2*len, and results are invariant under batch permutation."""
+    require_gpu()
+    from nvbio_b200 import synth
+    n_g, n, L, W = 4_000_000, 1_000_000, 151, 300
+    gw = synth.random_genome_words(n_g)
+    rw, pos, strand = synth.sample_reads(gw, n_g, n, L, rc_half=False)
+    begin = synth.windows_for_reads(n_g, pos, L, W)
+    P = PackedStringSet.fixed(rw.reshape(-1), n, L, stride=rw.shape[1] * 16)
+    T = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=begin.to(torch.int32), lengths=None, stride=0, length=W, count=n)
+    al = aln.make_gotoh_aligner(aln.LOCAL, aln.SimpleGotohScheme(2, -2, -5, -3))
+    for band in (15, 31):
+        force_path(0)
+        s0, k0 = aln.batch_banded_alignment_score(band, al, P, T)
+        force_path(1)
+        try:
+            s1, k1 = aln.batch_banded_alignment_score(band, al, P, T)
+        finally:
+            force_path(0)
+        assert torch.equal(s0, s1) and torch.equal(k0, k1)
+        assert int(s0.max()) <= 2 * L and int(s0.min()) >= 0
+    # reads that are exact substrings score 2*L when the window offset is inside the band
+    rw2, pos2, _ = synth.sample_reads(gw, n_g, 10000, L, sub_rate=0.0, indel_rate=0.0, rc_half=False)
+    P2 = PackedStringSet.fixed(rw2.reshape(-1), 10000, L, stride=rw2.shape[1] * 16)
+    T2 = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=(pos2 - 7).clamp_(0).to(torch.int32), lengths=None, stride=0, length=W, count=10000)
+    s2, k2 = aln.batch_banded_alignment_score(31, al, P2, T2)
+    assert bool((s2 == 2 * L).all())
+    perm = torch.randperm(10000, device="cuda")
+    T3 = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=T2.offsets[perm].contiguous(), lengths=None, stride=0, length=W, count=10000)
+    P3 = PackedStringSet(words=P2.words, bits=2, big_endian=True, offsets=(perm * P2.stride).to(torch.int32), lengths=None, stride=0, length=L, count=10000)
+    s3, k3 = aln.batch_banded_alignment_score(31, al, P3, T3)
+    assert torch.equal(s3, s2[perm]) and torch.equal(k3, k2[perm])

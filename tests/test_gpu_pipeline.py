@@ -1,0 +1,91 @@
+"""-m gpu: the seed+extend composition (seeds -> match -> locate -> window -> banded Gotoh -> best per read)
+against the oracle composition, hit by hit."""
+import numpy as np
+import pytest
+import torch
+from oracle import orc
+import nvbio_b200 as nb
+from nvbio_b200 import aln, synth
+from nvbio_b200.strings import PackedStringSet, pack_symbols, unpack_symbols
+from tests.gpu_util import require_gpu, dev_u32, host_u32
+from tests.pipeline_oracle import seed_extend_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("both,read_len,ragged", [(True, 150, False), (False, 100, False), (True, 120, True)])
+def test_seed_extend_vs_oracle(both, read_len, ragged):
+    require_gpu()
+    O = orc.Oracle()
+    n = 200_000
+    gw = synth.random_genome_words(n, seed=77)
+    gsym = unpack_symbols(host_u32(gw), n)
+    idx = O.build_index(gsym)
+    fmi = nb.FMIndexDevice.from_host(idx.bwt_occ, idx.ssa, idx.L2, idx.n, idx.primary)
+    n_reads = 600
+    rw, pos, strand = synth.sample_reads(gw, n, n_reads, read_len, sub_rate=0.02, indel_rate=0.004, seed=5, mut_seed=6)
+    wpr = rw.shape[1]
+    reads_sym = [unpack_symbols(host_u32(rw[i]), read_len) for i in range(n_reads)]
+    if ragged:
+        rng = np.random.default_rng(3)
+        lens = rng.integers(read_len - 50, read_len + 1, n_reads).astype(np.uint32)
+        reads_sym = [r[:l] for r, l in zip(reads_sym, lens)]
+        rs = PackedStringSet(words=rw.reshape(-1), bits=2, big_endian=True,
+                             offsets=(torch.arange(n_reads, device="cuda", dtype=torch.int32) * (wpr * 16)),
+                             lengths=dev_u32(lens), stride=0, length=read_len, count=n_reads)
+    else:
+        rs = PackedStringSet.fixed(rw.reshape(-1), n_reads, read_len, stride=wpr * 16)
+    params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=both,
+                                 max_seed_hits=50, scheme=aln.SimpleGotohScheme(2, -2, -5, -3))
+    ws = nb.seed_extend(fmi, gw, rs, params, hit_capacity=64 * n_reads, keep_hits=True)
+    torch.cuda.synchronize()
+    want = seed_extend_oracle(O, idx, gsym, reads_sym, params)
+    kept, total = [int(v) for v in ws.n_hits.cpu()]
+    assert kept == total == want["n_hits"]
+    assert np.array_equal(ws.hit_read.cpu().numpy()[:kept].astype(np.int64), want["hit_string"])
+    assert np.array_equal(host_u32(ws.hit_window)[:kept].astype(np.int64), want["hit_window"])
+    assert np.array_equal(ws.hit_score.cpu().numpy()[:kept].astype(np.int64), want["hit_score"])
+    assert np.array_equal(host_u32(ws.hit_sink)[:kept].astype(np.int64), want["hit_sink"])
+    assert np.array_equal(ws.best_score.cpu().numpy().astype(np.int64), want["best_score"])
+    assert np.array_equal(host_u32(ws.best_pos).astype(np.int64), want["best_pos"])
+    # most reads are found at their true locus
+    found = (ws.best_score.cpu().numpy() > read_len)   # > half of the perfect score 2*len
+    assert found.mean() > 0.9
+
+
+def test_seed_extend_4bit_reads_with_N():
+    require_gpu()
+    O = orc.Oracle()
+    n = 50_000
+    gw = synth.random_genome_words(n, seed=9)
+    gsym = unpack_symbols(host_u32(gw), n)
+    idx = O.build_index(gsym)
+    fmi = nb.FMIndexDevice.from_host(idx.bwt_occ, idx.ssa, idx.L2, idx.n, idx.primary)
+    rng = np.random.default_rng(0)
+    reads = []
+    for i in range(200):
+        p = int(rng.integers(0, n - 100)); r = gsym[p:p + 100].copy()
+        r[rng.integers(0, 100, 3)] = 4
+        reads.append(r)
+    sym = np.concatenate(reads)
+    rs = PackedStringSet.from_symbols(sym, np.arange(200) * 100, np.full(200, 100), bits=4, big_endian=True)
+    params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, both_strands=True, max_seed_hits=10)
+    ws = nb.seed_extend(fmi, gw, rs, params, hit_capacity=20000, keep_hits=True)
+    torch.cuda.synchronize()
+    want = seed_extend_oracle(O, idx, gsym, reads, params)
+    kept = int(ws.n_hits[0])
+    assert kept == want["n_hits"]
+    assert np.array_equal(ws.hit_score.cpu().numpy()[:kept].astype(np.int64), want["hit_score"])
+    assert np.array_equal(ws.best_score.cpu().numpy().astype(np.int64), want["best_score"])
+
+
+def test_hit_capacity_is_respected():
+    require_gpu()
+    n = 100_000
+    gw = synth.random_genome_words(n, seed=1)
+    fmi, _ = nb.FMIndexDevice.from_text(gw, n)
+    rw, pos, strand = synth.sample_reads(gw, n, 500, 150, sub_rate=0.0, indel_rate=0.0)
+    rs = PackedStringSet.fixed(rw.reshape(-1), 500, 150, stride=rw.shape[1] * 16)
+    ws = nb.seed_extend(fmi, gw, rs, nb.SeedExtendParams(), hit_capacity=1000, keep_hits=True)
+    kept, total = [int(v) for v in ws.n_hits.cpu()]
+    assert kept == 1000 and total > 1000
