@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--genome-mbp", type=float, default=3000.0)
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
+    ap.add_argument("--ktab-k", type=int, default=12, help="k of the k-mer range table (0 = none)")
+    ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -136,13 +139,17 @@ def build_index(args, rank, world, device):
     if rank == 0:
         torch.cuda.synchronize(); t0 = time.perf_counter()
         genome = synth.random_genome_words(n, device=device)
-        fmi, _ = nb.FMIndexDevice.from_text(genome, n)
+        fmi, _ = nb.FMIndexDevice.from_text(genome, n, sa_interval=args.sa_interval)
         torch.cuda.synchronize(); t_build = time.perf_counter() - t0
         torch.cuda.empty_cache()
     if world > 1:
         barrier(world); t0 = time.perf_counter()
         fmi, genome = nd.broadcast_index(fmi, genome, device, src=0)
         barrier(world); t_bcast = time.perf_counter() - t0
+    if args.ktab_k > 0 and args.impl == "ours":
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        fmi.build_ktab(args.ktab_k)                      # every rank derives the table from its replica
+        torch.cuda.synchronize(); t_build += time.perf_counter() - t0
     return n, genome, fmi, t_build, t_bcast
 
 
@@ -162,7 +169,9 @@ def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
     E = orc.Ref() if orc.Ref.available() else orc.Oracle()
     cores = E.num_threads() if E.kind == "reference" else 1
     host = fmi.to_host()
-    idx = orc._Index(n=host["n"], primary=host["primary"], bwt_occ=host["bwt_occ"], ssa=host["ssa"], L2=host["L2"])
+    # the reference's index format samples the SA every 16 rows (SA_INT): slice the device index's denser array
+    ssa16 = np.ascontiguousarray(host["ssa"][::16 // host["sa_interval"]])
+    idx = orc._Index(n=host["n"], primary=host["primary"], bwt_occ=host["bwt_occ"], ssa=ssa16, L2=host["L2"])
     gw = genome.cpu().numpy().view(np.uint32)
     nsample = args.cpu_sample
     times, res = [], None
@@ -172,9 +181,10 @@ def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
         words = rw.cpu().numpy().view(np.uint32)
         sym = _unpack_rows(words, READ_LEN)
         res = cpu_seed_extend(E, idx, gw, sym, SEED_LEN, SEED_INTERVAL, BAND, 1, SCHEME, True, 100,
-                              count_blocks_with=(O if (want_blocks and it == 0) else None))
+                              count_blocks_with=(O if (want_blocks and it == 0) else None), blocks_from_step=args.ktab_k)
         if it == 0 and want_blocks:
             blocks_per_seed = res["blocks"] / res["n_seeds"]
+            tail_blocks_per_seed = (res["blocks_tail"] / res["n_seeds"]) if res["blocks_tail"] is not None else blocks_per_seed
         if it >= warmup:
             times.append(res["t_total"])
     t = float(np.mean(times)) if times else float("nan")
@@ -185,6 +195,7 @@ def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
                mseeds_per_s=res["n_seeds"] / res["t_match"] / 1e6 if res["t_match"] > 0 else None)
     if want_blocks:
         out["blocks_per_seed"] = blocks_per_seed
+        out["tail_blocks_per_seed"] = tail_blocks_per_seed
     return out
 
 
@@ -240,7 +251,8 @@ def run_ours(args):
     n, genome, fmi, t_build, t_bcast = build_index(args, rank, world, device)
     n_reads = args.reads
     params = nb.SeedExtendParams(seed_len=SEED_LEN, seed_interval=SEED_INTERVAL, band_len=BAND, type=aln.LOCAL,
-                                 both_strands=True, max_seed_hits=100, scheme=aln.SimpleGotohScheme(*SCHEME))
+                                 both_strands=True, max_seed_hits=100, dedup_jobs=not args.no_dedup,
+                                 scheme=aln.SimpleGotohScheme(*SCHEME))
     batches = [make_reads(genome, n, n_reads, rank * 16 + b, device) for b in range(2)]
     wpr = batches[0].shape[1]
 
@@ -267,7 +279,7 @@ def run_ours(args):
         total_ms += ev0.elapsed_time(ev1)
         st = last_stage_ms()
         stage_acc = st if stage_acc is None else {k: stage_acc[k] + st[k] for k in st}
-        kept, hits = [int(v) for v in ws.n_hits.cpu()]
+        kept, hits, jobs = [int(v) for v in ws.n_hits.cpu()]
         if kept != hits:
             raise SystemExit("bench: hit capacity %d exceeded (%d hits): results would be truncated" % (hit_capacity, hits))
     barrier(world)
@@ -309,38 +321,47 @@ def run_ours(args):
     # ---- CPU baseline + algorithmic bytes (rank 0, N=1 only) ----------------------------------
     cpu = None
     n_seeds = 2 * n_reads * ((READ_LEN - SEED_LEN) // SEED_INTERVAL + 1)
-    blocks_per_seed = None
+    blocks_per_seed = tail_blocks = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_leg(args, n, genome, fmi, steps=1, warmup=1, want_blocks=True)
-        blocks_per_seed = r["blocks_per_seed"]
+        blocks_per_seed, tail_blocks = r["blocks_per_seed"], r["tail_blocks_per_seed"]
         cpu = {"value": r["value"], "unit": "Mreads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "fm_match_Mseeds_s": r["mseeds_per_s"], "banded_gotoh_GCUPS": r["gcups"]}
     if blocks_per_seed is None:
         # (L-1) + log4(n/64) blocks per seed: the closed form SURVEY.md 8d fits to the exact counts
         blocks_per_seed = (SEED_LEN - 1) + float(np.log(max(n / 64.0, 1.0)) / np.log(4.0))
+        tail_blocks = max(blocks_per_seed - 2.0 * args.ktab_k + 1.0, 1.0) if args.ktab_k else blocks_per_seed
     peak, peak_src = measured_peaks()
-    bytes_per_seed = 32.0 * blocks_per_seed + SEED_LEN * 2 / 8.0 + 8.0
+    # reference algorithm: every LF step fetches its distinct 32-byte blocks.  This kernel replaces the first
+    # k steps by one 8-byte table entry (one 32-byte sector), so ITS necessary traffic is the tail blocks + that sector.
+    ref_bytes_per_seed = 32.0 * blocks_per_seed + SEED_LEN * 2 / 8.0 + 8.0
+    bytes_per_seed = 32.0 * tail_blocks + (32.0 if args.ktab_k else 0.0) + SEED_LEN * 2 / 8.0 + 8.0
     fm_ms = stage_ms["seed_match"]
     achieved = n_seeds * bytes_per_seed / (fm_ms * 1e-3) / 1e9
-    cells = hits * READ_LEN * BAND
+    cells = jobs * READ_LEN * BAND
     line = {
         "metric": "Mreads/s (150bp) seed+extend", "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": workload_config(args, n, n_reads, world),
         "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-        "gpu_launches": 8 * args.steps,
+        "gpu_launches": (12 if params.dedup_jobs else 8) * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "ms_per_launch": fm_ms,
-                     "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": blocks_per_seed,
-                     "note": "32 B x distinct {bwt,occ} blocks per LF step (oracle count on the CPU sample) + query + 8 B out"},
+                     "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": tail_blocks,
+                     "reference_algorithm_bytes_per_seed": ref_bytes_per_seed, "reference_algorithm_blocks_per_seed": blocks_per_seed,
+                     "reference_algorithm_equiv_GBs": n_seeds * ref_bytes_per_seed / (fm_ms * 1e-3) / 1e9,
+                     "note": "32 B x distinct {bwt,occ} blocks per LF step after the %d-mer table look-up (oracle count on the CPU "
+                             "sample) + one 32 B table sector + query + 8 B out; the reference algorithm (no table) needs "
+                             "reference_algorithm_bytes_per_seed" % args.ktab_k},
         "stage_ms": stage_ms,
         "fm_match_Mseeds_s": n_seeds / (fm_ms * 1e-3) / 1e6,
-        "banded_gotoh": {"alignments_per_step": hits, "GCUPS": cells / (stage_ms["extend"] * 1e-3) / 1e9, "band": BAND,
-                         "note": "integer-issue bound (DPX s16x2), not HBM"},
+        "banded_gotoh": {"alignments_per_step": hits, "distinct_jobs_scored": jobs, "GCUPS": cells / (stage_ms["extend"] * 1e-3) / 1e9,
+                         "band": BAND, "note": "cells = distinct jobs x 150 x 31; integer-issue bound (DPX s16x2), not HBM"},
         "reads_found_frac": found,
-        "index": {"build_s": t_build, "broadcast_s": t_bcast, "bytes": fmi.nbytes() + genome.numel() * 4},
+        "index": {"build_s": t_build, "broadcast_s": t_bcast, "bytes": fmi.nbytes() + genome.numel() * 4,
+                  "sa_interval": fmi.sa_interval, "ktab_k": fmi.ktab_k},
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -40,11 +40,19 @@ typedef struct nvb_uint2 { uint32_t x, y; } nvb_uint2;
  * (nvbio/fmindex/fmindex.h:341-387): {m_length, m_primary, m_L2, m_rank_dict, m_sa}. */
 typedef struct nvb_fm_index {
     const void*     d_bwt_occ;   /* ceil(length/64) blocks of 32 bytes, 32-byte aligned            */
-    const uint32_t* d_ssa;       /* (length+16)/16 words: SA[r] for r%16==0, ssa[0]=0xFFFFFFFF; may
-                                    be NULL when only rank/match are used                          */
+    const uint32_t* d_ssa;       /* (length+I)/I words: SA[r] for r%I==0, ssa[0]=0xFFFFFFFF; may be
+                                    NULL when only rank/match are used                             */
     uint32_t        length;      /* text length n (number of BWT symbols)                          */
     uint32_t        primary;     /* row of the `$` suffix                                          */
     uint32_t        L2[5];       /* exclusive prefix sums of the symbol counts                     */
+    /* ---- optional B200 extensions; zero-initialise for an index in the reference's format ---- */
+    uint32_t        sa_interval; /* I: 0 or 16 = the reference's SA_INT (FMIndexDataCore::SA_INT);
+                                    any power of two down to 1 (= the full suffix array, 4 bytes per
+                                    base: 12 GB at 3 Gbp, nothing on a 180 GB part) shortens locate  */
+    const nvb_uint2* d_ktab;     /* 4^ktab_k inclusive SA ranges of every k-mer (index = the k symbols
+                                    as a 2k-bit number, first symbol most significant), built by
+                                    nvb_fm_build_ktab; replaces the first k LF steps of match()     */
+    uint32_t        ktab_k;      /* 0 = no table */
 } nvb_fm_index;
 
 /* A set of strings stored in one packed symbol stream (nvbio PackedStream semantics,
@@ -166,10 +174,16 @@ int nvb_fm_build_occ(const uint32_t* d_bwt, uint32_t n, void* d_bwt_occ, uint32_
 
 /* Suffix-sort a 2-bit big-endian packed text of n symbols on the device and emit the BWT (nvbio
  * convention: `$` row removed, nvbio/fmindex/bwt.h:51-63), the primary row, the sampled SA
- * (every 16th row, ssa[0]=0xFFFFFFFF) and optionally the full SA (n+1 entries, d_sa may be NULL).
- * d_bwt must hold ceil(n/64)*4 words, d_ssa (n+16)/16 words.  Synchronises. */
+ * (every sa_interval-th row, ssa[0]=0xFFFFFFFF; sa_interval 0 means 16) and optionally the full SA with
+ * the `$` row (n+1 entries, d_sa may be NULL).
+ * d_bwt must hold ceil(n/64)*4 words, d_ssa (n+I)/I words.  Synchronises. */
 int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n, uint32_t* d_bwt, uint32_t* h_primary,
-                     uint32_t* d_ssa, uint32_t* d_sa, void* d_temp, size_t* temp_bytes, void* stream);
+                     uint32_t* d_ssa, uint32_t sa_interval, uint32_t* d_sa,
+                     void* d_temp, size_t* temp_bytes, void* stream);
+
+/* Fill d_ktab[4^k] with match() of every k-mer (level by level: 4^k * 4/3 LF steps in total).
+ * k in [1,14].  fmi->d_ktab / ktab_k are ignored on input. */
+int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Seed + extend composition (the fmmap / nvBowtie hot loop: seeds -> match -> locate -> window ->
@@ -182,6 +196,8 @@ typedef struct nvb_seed_extend_params {
     uint32_t type;            /* NVB_LOCAL */
     uint32_t both_strands;    /* 1: also seed/extend the reverse complement of every read           */
     uint32_t max_seed_hits;   /* ranges wider than this contribute only their first max_seed_hits rows */
+    uint32_t dedup_jobs;      /* 1: hits of a read that define the same (strand, window) alignment are scored once and
+                                 the result copied to each of them (bit-identical per-hit outputs, fewer cells)       */
     nvb_gotoh_scheme scheme;
 } nvb_seed_extend_params;
 
@@ -190,7 +206,8 @@ typedef struct nvb_seed_extend_params {
  * coordinate of the best alignment's end (window begin + sink.x; 0xFFFFFFFF when none).
  * Optional per-hit outputs (may be NULL) of capacity hit_capacity: d_hit_read (string id = read*strands
  * + strand), d_hit_window (begin,end), d_hit_score, d_hit_sink; d_n_hits[0] receives the number of hits
- * kept (<= hit_capacity) and d_n_hits[1] the number found (device counters, no host round trip).
+ * kept (<= hit_capacity), d_n_hits[1] the number found and d_n_hits[2] the number of distinct alignment jobs
+ * actually scored (device counters, no host round trip).
  * Returns NVB_E_TEMP_SIZE with the needed size when d_temp is NULL/too small. */
 int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,
@@ -201,10 +218,10 @@ int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     void* d_temp, size_t* temp_bytes, void* stream);
 
 /* Profiling aid (the reference wraps every stage in cuda::Timer, nvBowtie/bowtie2/cuda/aligner_best_approx.h:
- * 219-241): device time in ms of the six stages of the most recent nvb_seed_extend call -- [fw,rc] strings,
- * seed match (FM-index), hit slots, locate + windows, banded extension, best-per-read.  Synchronises on the
- * call's last event. */
-int nvb_seed_extend_stage_ms(float ms[6]);
+ * 219-241): device time in ms of the seven stages of the most recent nvb_seed_extend call -- [fw,rc] strings,
+ * seed match (FM-index), hit slots, locate + windows, job de-duplication, banded extension, best-per-read.
+ * Synchronises on the call's last event. */
+int nvb_seed_extend_stage_ms(float ms[7]);
 
 #ifdef __cplusplus
 }

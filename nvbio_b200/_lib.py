@@ -10,7 +10,7 @@ EXPORTS = [
     "nvb_version", "nvb_error_string",
     "nvb_fm_rank", "nvb_fm_match", "nvb_fm_locate", "nvb_fm_filter_rank", "nvb_fm_filter_locate",
     "nvb_banded_gotoh_score", "nvb_banded_gotoh_score_indirect",
-    "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_seed_extend", "nvb_seed_extend_stage_ms",
+    "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_fm_build_ktab", "nvb_seed_extend", "nvb_seed_extend_stage_ms",
 ]
 
 
@@ -20,7 +20,8 @@ class NvbError(RuntimeError):
 
 class FmIndexStruct(C.Structure):          # nvb_fm_index
     _fields_ = [("d_bwt_occ", C.c_void_p), ("d_ssa", C.c_void_p), ("length", C.c_uint32),
-                ("primary", C.c_uint32), ("L2", C.c_uint32 * 5)]
+                ("primary", C.c_uint32), ("L2", C.c_uint32 * 5), ("sa_interval", C.c_uint32),
+                ("d_ktab", C.c_void_p), ("ktab_k", C.c_uint32)]
 
 
 class StringSetStruct(C.Structure):        # nvb_string_set
@@ -38,7 +39,7 @@ class GotohSchemeStruct(C.Structure):      # nvb_gotoh_scheme
 class SeedExtendParamsStruct(C.Structure):  # nvb_seed_extend_params
     _fields_ = [("seed_len", C.c_uint32), ("seed_interval", C.c_uint32), ("band_len", C.c_uint32),
                 ("type", C.c_uint32), ("both_strands", C.c_uint32), ("max_seed_hits", C.c_uint32),
-                ("scheme", GotohSchemeStruct)]
+                ("dedup_jobs", C.c_uint32), ("scheme", GotohSchemeStruct)]
 
 
 _lib = None

@@ -22,8 +22,11 @@ struct __align__(32) FmBlock {
 struct FmIndex {
     const FmBlock*  blocks;
     const uint32_t* ssa;
+    const uint2*    ktab;          // optional k-mer range table (NULL = none)
     uint32_t n, primary;
     uint32_t L2[5];
+    uint32_t sa_mask, sa_shift;    // sampled-SA interval I = 1 << sa_shift, mask = I - 1
+    uint32_t ktab_k;
     // constant-index selects keep the struct in the kernel-parameter constant bank (a dynamic L2[c]
     // would force a local-memory copy of the whole struct)
     __host__ __device__ __forceinline__ uint32_t l2(uint32_t c) const {
@@ -34,10 +37,21 @@ struct FmIndex {
     }
 };
 
+static inline bool valid_fmindex(const nvb_fm_index* f) {
+    if (!f || !f->d_bwt_occ) return false;
+    const uint32_t I = f->sa_interval;
+    if (I != 0 && (I & (I - 1)) != 0) return false;           // power of two
+    if (f->d_ktab && (f->ktab_k < 1 || f->ktab_k > 14)) return false;
+    return true;
+}
 static inline FmIndex make_fmindex(const nvb_fm_index* f) {
     FmIndex r;
     r.blocks = (const FmBlock*)f->d_bwt_occ; r.ssa = f->d_ssa; r.n = f->length; r.primary = f->primary;
     for (int i = 0; i < 5; ++i) r.L2[i] = f->L2[i];
+    const uint32_t I = f->sa_interval ? f->sa_interval : 16u;
+    r.sa_shift = 0; while ((1u << r.sa_shift) < I) ++r.sa_shift;
+    r.sa_mask = (1u << r.sa_shift) - 1u;
+    r.ktab = (const uint2*)f->d_ktab; r.ktab_k = f->d_ktab ? f->ktab_k : 0u;
     return r;
 }
 
@@ -157,7 +171,24 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
     uint32_t x = 0, y = f.n;
     const bool fwd = (flags & NVB_MATCH_FORWARD_ORDER) != 0;
     const bool comp = (flags & NVB_MATCH_COMPLEMENT) != 0;
-    for (uint32_t s = 0; s < len && x <= y; ++s) {
+    uint32_t s = 0;
+    if (f.ktab_k && len >= f.ktab_k) {
+        // the first k symbols consumed are the LAST k symbols of the effective pattern: look their range up.
+        // ktab[u] is match() of that k-mer, which also reproduces the reference's early exit on an empty range.
+        uint32_t u = 0; bool has_n = false;
+        for (uint32_t j = 0; j < f.ktab_k; ++j) {
+            const uint32_t i = fwd ? j : (len - 1u - j);
+            uint32_t c = rd.get(off + i);
+            has_n |= (c > 3u);
+            if (comp) c = 3u - c;
+            u |= (c & 3u) << (2u * j);
+        }
+        if (!has_n) {                                   // an N among them: take the step-by-step path below
+            const uint2 r = f.ktab[u];
+            x = r.x; y = r.y; s = f.ktab_k;
+        }
+    }
+    for (; s < len && x <= y; ++s) {
         const uint32_t i = fwd ? s : (len - 1u - s);
         uint32_t c = rd.get(off + i);
         if (c > 3u) { x = 1u; y = 0u; break; }
@@ -170,7 +201,7 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
 // locate(fmi, row)
 __host__ __device__ __forceinline__ uint32_t fm_locate_one(const FmIndex& f, uint32_t row) {
     uint32_t j = row, t = 0;
-    while ((j & 15u) != 0u) {
+    while ((j & f.sa_mask) != 0u) {
         if (j != f.primary) {
             const uint32_t k = j < f.primary ? j : j - 1u;
             const FmBlock b = load_block(f.blocks, k >> 6);
@@ -181,7 +212,7 @@ __host__ __device__ __forceinline__ uint32_t fm_locate_one(const FmIndex& f, uin
         }
         ++t;
     }
-    return f.ssa[j >> 4] + t;
+    return f.ssa[j >> f.sa_shift] + t;
 }
 
 } // namespace nvb

@@ -39,6 +39,22 @@ fm_locate_kernel(const FmIndex f, const uint32_t* __restrict__ rows, uint32_t n,
     out[i] = fm_locate_one(f, rows[i]);
 }
 
+// one level of the k-mer table: entry v of level t-1 (the range of a (t-1)-mer w) fans out to the four
+// t-mers c.w (c prepended = consumed next by the backward search).  The c=0 child overwrites its own parent.
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_ktab_level_kernel(const FmIndex f, uint2* __restrict__ tab, uint32_t prev_entries)
+{
+    const uint32_t v = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (v >= prev_entries) return;
+    const uint2 r = tab[v];
+#pragma unroll
+    for (int c = 3; c >= 0; --c) {
+        uint32_t x = r.x, y = r.y;
+        if (x <= y) fm_step(f, (uint32_t)c, x, y);        // an empty range stays as it is (match() stops there)
+        tab[(uint32_t)c * prev_entries + v] = make_uint2(x, y);
+    }
+}
+
 // range sizes as uint64 (filter_inl.h:36-42: 1 + y - x in uint32 arithmetic, widened)
 struct RangeSize {
     __host__ __device__ __forceinline__ uint64_t operator()(const uint2& r) const { return (uint64_t)(uint32_t)(1u + r.y - r.x); }
@@ -138,10 +154,27 @@ const char* nvb_error_string(int err)
     return err > 0 ? cudaGetErrorString((cudaError_t)err) : "nvbio_b200: unknown error";
 }
 
+int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream)
+{
+    if (!valid_fmindex(fmi) || k < 1 || k > 14 || !d_ktab) return NVB_E_INVALID;
+    nvb_fm_index plain = *fmi; plain.d_ktab = nullptr; plain.ktab_k = 0;
+    const FmIndex f = make_fmindex(&plain);
+    cudaStream_t s = as_stream(stream);
+    const uint2 root = make_uint2(0u, fmi->length);
+    NVB_CUDA_TRY(cudaMemcpyAsync(d_ktab, &root, sizeof(uint2), cudaMemcpyHostToDevice, s));
+    NVB_CUDA_TRY(cudaStreamSynchronize(s));              // `root` lives on this stack frame
+    uint32_t prev = 1;
+    for (uint32_t t = 1; t <= k; ++t, prev *= 4u) {
+        fm_ktab_level_kernel<<<(prev + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, s>>>(f, (uint2*)d_ktab, prev);
+        NVB_LAUNCH_CHECK();
+    }
+    return NVB_OK;
+}
+
 int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c, uint32_t n,
                 uint32_t* d_out, void* stream)
 {
-    if (!fmi || !fmi->d_bwt_occ || (n && (!d_k || !d_c || !d_out))) return NVB_E_INVALID;
+    if (!valid_fmindex(fmi) || (n && (!d_k || !d_c || !d_out))) return NVB_E_INVALID;
     if (n == 0) return NVB_OK;
     fm_rank_kernel<<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), d_k, d_c, n, d_out);
     NVB_LAUNCH_CHECK();
@@ -151,7 +184,7 @@ int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c
 int nvb_fm_match(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
                  nvb_uint2* d_ranges, void* stream)
 {
-    if (!fmi || !fmi->d_bwt_occ || !valid_strset(queries) || (n && !d_ranges)) return NVB_E_INVALID;
+    if (!valid_fmindex(fmi) || !valid_strset(queries) || (n && !d_ranges)) return NVB_E_INVALID;
     if (n == 0) return NVB_OK;
     const FmIndex f = make_fmindex(fmi);
     const StrSet q = make_strset(queries);
@@ -165,7 +198,7 @@ int nvb_fm_match(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_
 
 int nvb_fm_locate(const nvb_fm_index* fmi, const uint32_t* d_rows, uint32_t n, uint32_t* d_pos, void* stream)
 {
-    if (!fmi || !fmi->d_bwt_occ || !fmi->d_ssa || (n && (!d_rows || !d_pos))) return NVB_E_INVALID;
+    if (!valid_fmindex(fmi) || !fmi->d_ssa || (n && (!d_rows || !d_pos))) return NVB_E_INVALID;
     if (n == 0) return NVB_OK;
     fm_locate_kernel<<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), d_rows, n, d_pos);
     NVB_LAUNCH_CHECK();
@@ -196,7 +229,7 @@ int nvb_fm_filter_rank(const nvb_fm_index* fmi, const nvb_string_set* queries, u
 int nvb_fm_filter_locate(const nvb_fm_index* fmi, const nvb_uint2* d_ranges, const uint64_t* d_slots,
                          uint32_t n_queries, uint64_t begin, uint64_t end, nvb_uint2* d_hits, void* stream)
 {
-    if (!fmi || !fmi->d_bwt_occ || !fmi->d_ssa || !d_ranges || !d_slots || end < begin) return NVB_E_INVALID;
+    if (!valid_fmindex(fmi) || !fmi->d_ssa || !d_ranges || !d_slots || end < begin) return NVB_E_INVALID;
     const uint64_t count = end - begin;
     if (count == 0) return NVB_OK;
     if (!d_hits || count > 0x7FFFFFFFull * FM_BLOCKDIM) return NVB_E_INVALID;

@@ -23,10 +23,13 @@ namespace nvb {
 struct GotohScheme {
     int32_t match, mismatch, pgo, pge, tgo, tge;
     const int32_t* qtab;       // device (or host in host tests): [256][2] = {match(q), mismatch(q)} or NULL
+    // multipliers that are 1 and 32 at run time but opaque to the compiler (kernel-parameter constants), so that
+    // "x*one + y" and "x*keymul + y" stay IMADs on the FMA pipe instead of IADD3/LEA on the saturated ALU pipe
+    uint32_t one, keymul;
 };
 static inline GotohScheme make_scheme(const nvb_gotoh_scheme* s) {
     GotohScheme r; r.match = s->match; r.mismatch = s->mismatch; r.pgo = s->pattern_gap_open; r.pge = s->pattern_gap_ext;
-    r.tgo = s->text_gap_open; r.tge = s->text_gap_ext; r.qtab = s->d_qual_table; return r;
+    r.tgo = s->text_gap_open; r.tge = s->text_gap_ext; r.qtab = s->d_qual_table; r.one = 1u; r.keymul = 32u; return r;
 }
 
 __host__ __device__ __forceinline__ int32_t imax2(int32_t a, int32_t b) { return a > b ? a : b; }
@@ -188,6 +191,7 @@ static inline bool pair_path_ok(int B, int type, const nvb_gotoh_scheme* s, uint
 #define NVB_VIADDMAX(a, b, c)      __viaddmax_s16x2((a), (b), (c))
 #define NVB_VIADDMAX_RELU(a, b, c) __viaddmax_s16x2_relu((a), (b), (c))
 #define NVB_VIMAX_RELU(a, b)       __vimax_s16x2_relu((a), (b))
+#define NVB_VIMAX3(a, b, c)        __vimax3_s16x2((a), (b), (c))
 #ifdef __CUDA_ARCH__
 #define NVB_VIMAX(a, b)            __vmaxs2((a), (b))
 #define NVB_VIADD(a, b)            __vadd2((a), (b))
@@ -243,38 +247,72 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
     const uint32_t Mmax = M0 > M1 ? M0 : M1;
     int32_t best0 = -1, best1 = -1; uint32_t bi0 = 0, bj0 = 0, bi1 = 0, bj1 = 0;
 
-    for (uint32_t i = 0; i < Mmax; ++i) {
-        const uint32_t q0 = (i < M0) ? pr0.get(poff0 + i) : 255u;
-        const uint32_t q1 = (i < M1) ? pr1.get(poff1 + i) : 255u;
-        const uint32_t P0 = sub_profile(q0, c_eq, c_ne);
-        const uint32_t P1 = sub_profile(q1, c_eq, c_ne);
-        const uint16_t* srow = sel + (size_t)i * sel_stride;
-        uint32_t E = 0, rowkey = 0;
+    if (TYPE == NVB_LOCAL) {
+        // LOCAL formulation, biased by beta = -Go so that the one plain add per cell (h + Go) is carry-free and can be
+        // an IMAD on the FMA pipe:  G[] holds H itself (>= 0), F[] and E hold F+beta / E+beta, h' = h+beta >= beta.
+        //   F'[j] = max(F'[j+1]+Ge, H[j+1]);  t' = max(H[j] + (S-Go), F'[j]);  h' = max(t', E', beta);
+        //   H[j] = h' + Go  (IMAD: both halves stay >= 0);  E' = max(E'+Ge, H[j])
+        const int32_t beta = -Go;
+        const uint32_t beta2 = pack16(beta, beta);
+        const uint32_t GoX = (uint32_t)(Go * 65537);                  // Go in both halves, as ONE 32-bit addend
+        const uint32_t INFb2 = pack16(INF + beta, INF + beta);
 #pragma unroll
-        for (int j = 0; j < B; ++j) {
-            const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
-            uint32_t h;
-            if (j == 0) {
-                F[0] = NVB_VIADDMAX(F[1], Ge2, G[1]);
-                h = (TYPE == NVB_LOCAL) ? NVB_VIADDMAX_RELU(G[0], s, F[0]) : NVB_VIADDMAX(G[0], s, F[0]);
-            } else if (j < B - 1) {
-                F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INF2, Ge2, G[j + 1]);
-                const uint32_t t = NVB_VIADDMAX(G[j], s, F[j]);
-                h = (TYPE == NVB_LOCAL) ? NVB_VIMAX_RELU(t, E) : NVB_VIMAX(t, E);
-            } else {
-                h = (TYPE == NVB_LOCAL) ? NVB_VIADDMAX_RELU(G[j], s, E) : NVB_VIADDMAX(G[j], s, E);
-            }
-            if (TYPE == NVB_LOCAL) {
-                const uint32_t key = h * 32u + (uint32_t)(j | (j << 16));        // (h << 5) | j per half, h < 2048
+        for (int j = 0; j < B; ++j) G[j] = 0u;
+#pragma unroll
+        for (int j = 0; j < B - 1; ++j) F[j] = INFb2;
+        for (uint32_t i = 0; i < Mmax; ++i) {
+            const uint32_t q0 = (i < M0) ? pr0.get(poff0 + i) : 255u;
+            const uint32_t q1 = (i < M1) ? pr1.get(poff1 + i) : 255u;
+            const uint32_t P0 = sub_profile(q0, c_eq, c_ne);
+            const uint32_t P1 = sub_profile(q1, c_eq, c_ne);
+            const uint16_t* srow = sel + (size_t)i * sel_stride;
+            uint32_t E = 0, rowkey = 0;
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
+                uint32_t hb;
+                if (j == 0) {
+                    F[0] = NVB_VIADDMAX(F[1], Ge2, G[1]);
+                    hb = NVB_VIMAX(NVB_VIADDMAX(G[0], s, F[0]), beta2);
+                } else if (j < B - 1) {
+                    F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INFb2, Ge2, G[j + 1]);
+                    hb = NVB_VIMAX3(NVB_VIADDMAX(G[j], s, F[j]), E, beta2);
+                } else {
+                    hb = NVB_VIMAX(NVB_VIADDMAX(G[j], s, E), beta2);
+                }
+                G[j] = hb * S.one + GoX;                                       // IMAD: H = h' + Go per half
+                const uint32_t key = G[j] * S.keymul + (uint32_t)(j | (j << 16));   // IMAD: (H << 5) | j per half, H < 2048
                 rowkey = NVB_VIMAX_U(rowkey, key);
+                E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
             }
-            G[j] = NVB_VIADD(h, Go2);
-            E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
-        }
-        if (TYPE == NVB_LOCAL) {
             const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
             if (i < M0 && (k0 >> 5) >= best0) { best0 = k0 >> 5; bi0 = i; bj0 = (uint32_t)k0 & 31u; }
             if (i < M1 && (k1 >> 5) >= best1) { best1 = k1 >> 5; bi1 = i; bj1 = (uint32_t)k1 & 31u; }
+        }
+    } else {
+        for (uint32_t i = 0; i < Mmax; ++i) {
+            const uint32_t q0 = (i < M0) ? pr0.get(poff0 + i) : 255u;
+            const uint32_t q1 = (i < M1) ? pr1.get(poff1 + i) : 255u;
+            const uint32_t P0 = sub_profile(q0, c_eq, c_ne);
+            const uint32_t P1 = sub_profile(q1, c_eq, c_ne);
+            const uint16_t* srow = sel + (size_t)i * sel_stride;
+            uint32_t E = 0;
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
+                uint32_t h;
+                if (j == 0) {
+                    F[0] = NVB_VIADDMAX(F[1], Ge2, G[1]);
+                    h = NVB_VIADDMAX(G[0], s, F[0]);
+                } else if (j < B - 1) {
+                    F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INF2, Ge2, G[j + 1]);
+                    h = NVB_VIMAX(NVB_VIADDMAX(G[j], s, F[j]), E);
+                } else {
+                    h = NVB_VIADDMAX(G[j], s, E);
+                }
+                G[j] = NVB_VIADD(h, Go2);
+                E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
+            }
         }
     }
 

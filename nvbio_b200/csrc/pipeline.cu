@@ -119,6 +119,61 @@ pipe_expand_hits_kernel(const FmIndex f, const PipeGeom g, const uint2* __restri
     t_off[h] = gb;           t_len[h] = ge - gb;
 }
 
+// Hits of one string are contiguous (queries are ordered by string, then seed).  Several seeds of a read usually
+// vote for the same diagonal, i.e. the very same (string, window) alignment job: score it once.
+// leader[h] = the smallest h' <= h of the same string with the same window; flag[h] = (leader[h] == h).
+// A missed duplicate (beyond the look-back) only costs a redundant alignment, never a different result.
+__global__ void __launch_bounds__(256)
+pipe_find_leaders_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ hit_string,
+                         const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
+                         uint32_t* __restrict__ leader, uint32_t* __restrict__ flag)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    if (h >= counts[0]) return;
+    const uint32_t s = hit_string[h], o = t_off[h], l = t_len[h];
+    uint32_t lead = h;
+    for (uint32_t back = 1; back <= 64u && back <= h; ++back) {
+        const uint32_t g = h - back;
+        if (hit_string[g] != s) break;
+        if (t_off[g] == o && t_len[g] == l) lead = g;
+    }
+    leader[h] = lead;
+    flag[h] = (lead == h) ? 1u : 0u;
+}
+
+// counts[2] = number of unique jobs
+__global__ void pipe_job_count_kernel(const uint32_t* __restrict__ job_idx, const uint32_t* __restrict__ flag, uint32_t* __restrict__ counts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const uint32_t n = counts[0];
+        counts[2] = n ? job_idx[n - 1] + flag[n - 1] : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pipe_compact_jobs_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ job_idx,
+                         const uint32_t* __restrict__ p_off, const uint32_t* __restrict__ p_len,
+                         const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
+                         uint32_t* __restrict__ jp_off, uint32_t* __restrict__ jp_len, uint32_t* __restrict__ jt_off, uint32_t* __restrict__ jt_len)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    if (h >= counts[0] || !flag[h]) return;
+    const uint32_t j = job_idx[h];
+    jp_off[j] = p_off[h]; jp_len[j] = p_len[h]; jt_off[j] = t_off[h]; jt_len[j] = t_len[h];
+}
+
+__global__ void __launch_bounds__(256)
+pipe_scatter_scores_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ leader, const uint32_t* __restrict__ job_idx,
+                           const int32_t* __restrict__ job_score, const uint2* __restrict__ job_sink,
+                           int32_t* __restrict__ score, uint2* __restrict__ sink)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    if (h >= counts[0]) return;
+    const uint32_t j = job_idx[leader[h]];
+    score[h] = job_score[j];
+    sink[h]  = job_sink[j];
+}
+
 // best hit per read: max score, ties -> smallest hit index (deterministic)
 __global__ void __launch_bounds__(256)
 pipe_reduce_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ hit_string,
@@ -160,17 +215,17 @@ pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, c
 using namespace nvb;
 
 // stage boundaries of the most recent nvb_seed_extend call (events are recorded on the caller's stream; they
-// cost no synchronisation).  [0]=start, then after: strings, seed match, slots, locate+windows, extension, reduce
-static cudaEvent_t g_stage_ev[7];
+// cost no synchronisation).  [0]=start, then after: strings, seed match, slots, locate+windows, job dedup, extension, reduce
+static cudaEvent_t g_stage_ev[8];
 static bool g_stage_ev_ready = false;
 static bool g_stage_ev_valid = false;
 #define NVB_STAGE(i) do { if (g_stage_ev_ready) NVB_CUDA_TRY(cudaEventRecord(g_stage_ev[i], s)); } while (0)
 
-extern "C" int nvb_seed_extend_stage_ms(float ms[6])
+extern "C" int nvb_seed_extend_stage_ms(float ms[7])
 {
     if (!ms || !g_stage_ev_valid) return NVB_E_INVALID;
-    NVB_CUDA_TRY(cudaEventSynchronize(g_stage_ev[6]));
-    for (int i = 0; i < 6; ++i) NVB_CUDA_TRY(cudaEventElapsedTime(&ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
+    NVB_CUDA_TRY(cudaEventSynchronize(g_stage_ev[7]));
+    for (int i = 0; i < 7; ++i) NVB_CUDA_TRY(cudaEventElapsedTime(&ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
     return NVB_OK;
 }
 
@@ -182,7 +237,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
                     int32_t* d_hit_score, nvb_uint2* d_hit_sink,
                     void* d_temp, size_t* temp_bytes, void* stream)
 {
-    if (!fmi || !fmi->d_bwt_occ || !fmi->d_ssa || !d_genome || !valid_strset(reads) || !P || !temp_bytes) return NVB_E_INVALID;
+    if (!valid_fmindex(fmi) || !fmi->d_ssa || !d_genome || !valid_strset(reads) || !P || !temp_bytes) return NVB_E_INVALID;
     if (reads->bits == 8) return NVB_E_UNSUPPORTED;
     if (P->seed_len == 0 || P->seed_interval == 0 || P->max_seed_hits == 0) return NVB_E_INVALID;
     if (n_reads && (!d_best_score || !d_best_pos)) return NVB_E_INVALID;
@@ -221,7 +276,17 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     uint2*    ranges     = tc.take<uint2>(nq);
     uint32_t* sizes      = tc.take<uint32_t>(nq);
     uint32_t* excl       = tc.take<uint32_t>(nq);
-    uint32_t* counts     = tc.take<uint32_t>(4);
+    uint32_t* counts     = tc.take<uint32_t>(4);          // [0] hits kept, [1] hits found, [2] unique alignment jobs
+    const bool dedup = P->dedup_jobs != 0;
+    uint32_t* leader  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* flag    = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* job_idx = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* jp_off  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* jp_len  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* jt_off  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* jt_len  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    int32_t*  job_score = dedup ? tc.take<int32_t>(hit_capacity) : nullptr;
+    uint2*    job_sink  = dedup ? tc.take<uint2>(hit_capacity) : nullptr;
     uint32_t* hit_string = tc.take<uint32_t>(hit_capacity);
     uint32_t* p_off      = tc.take<uint32_t>(hit_capacity);
     uint32_t* p_len      = tc.take<uint32_t>(hit_capacity);
@@ -230,8 +295,12 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     int32_t*  h_score    = d_hit_score ? d_hit_score : tc.take<int32_t>(hit_capacity);
     uint2*    h_sink     = d_hit_sink ? (uint2*)d_hit_sink : tc.take<uint2>(hit_capacity);
     unsigned long long* best_key = tc.take<unsigned long long>(n_reads);
-    size_t scan_bytes = 0;
+    size_t scan_bytes = 0, scan2_bytes = 0;
     NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, sizes, excl, (int)nq, as_stream(stream)));
+    if (dedup && hit_capacity) {
+        NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan2_bytes, flag, job_idx, (int)hit_capacity, as_stream(stream)));
+        if (scan2_bytes > scan_bytes) scan_bytes = scan2_bytes;
+    }
     char* scan_tmp  = tc.take<char>(scan_bytes);
     char* gotoh_tmp = tc.take<char>(gotoh_bytes);
     const size_t need = tc.total();
@@ -242,7 +311,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     const FmIndex f = make_fmindex(fmi);
     const StrSet rd = make_strset(reads);
     if (!g_stage_ev_ready) {
-        for (int i = 0; i < 7; ++i) NVB_CUDA_TRY(cudaEventCreate(&g_stage_ev[i]));
+        for (int i = 0; i < 8; ++i) NVB_CUDA_TRY(cudaEventCreate(&g_stage_ev[i]));
         g_stage_ev_ready = true;
     }
     NVB_STAGE(0);
@@ -276,16 +345,41 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(4);
-    // 5. extension
-    pats.d_words = str_words; pats.d_offsets = p_off; pats.d_lengths = p_len;
-    txts.d_words = d_genome;  txts.d_offsets = t_off; txts.d_lengths = t_len;
-    if (hit_capacity) {
-        size_t gb = gotoh_bytes;
-        const int r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts, hit_capacity,
-                                                      h_score, (nvb_uint2*)h_sink, gotoh_tmp, &gb, stream);
-        if (r != NVB_OK) return r;
+    // 4b. collapse identical (string, window) jobs
+    if (dedup && hit_capacity) {
+        pipe_find_leaders_kernel<<<hgrid, 256, 0, s>>>(counts, hit_string, t_off, t_len, leader, flag);
+        NVB_LAUNCH_CHECK();
+        // the scan runs over the whole capacity; job_idx[h] depends only on flag[0..h), so the (unwritten) entries
+        // past counts[0] cannot influence any index that is read back
+        size_t sb = scan_bytes;
+        NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, sb, flag, job_idx, (int)hit_capacity, s));
+        pipe_job_count_kernel<<<1, 32, 0, s>>>(job_idx, flag, counts);
+        NVB_LAUNCH_CHECK();
+        pipe_compact_jobs_kernel<<<hgrid, 256, 0, s>>>(counts, flag, job_idx, p_off, p_len, t_off, t_len, jp_off, jp_len, jt_off, jt_len);
+        NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(5);
+    // 5. extension
+    if (hit_capacity) {
+        size_t gb = gotoh_bytes;
+        int r;
+        if (dedup) {
+            pats.d_words = str_words; pats.d_offsets = jp_off; pats.d_lengths = jp_len;
+            txts.d_words = d_genome;  txts.d_offsets = jt_off; txts.d_lengths = jt_len;
+            r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts + 2, hit_capacity,
+                                                job_score, (nvb_uint2*)job_sink, gotoh_tmp, &gb, stream);
+            if (r != NVB_OK) return r;
+            pipe_scatter_scores_kernel<<<hgrid, 256, 0, s>>>(counts, leader, job_idx, job_score, job_sink, h_score, h_sink);
+            NVB_LAUNCH_CHECK();
+        } else {
+            pats.d_words = str_words; pats.d_offsets = p_off; pats.d_lengths = p_len;
+            txts.d_words = d_genome;  txts.d_offsets = t_off; txts.d_lengths = t_len;
+            r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts, hit_capacity,
+                                                h_score, (nvb_uint2*)h_sink, gotoh_tmp, &gb, stream);
+            if (r != NVB_OK) return r;
+        }
+    }
+    NVB_STAGE(6);
     // 6. best per read
     NVB_CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * n_reads, s));
     if (hit_capacity) {
@@ -298,8 +392,9 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
         pipe_export_hits_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, t_off, t_len, d_hit_read, (uint2*)d_hit_window);
         NVB_LAUNCH_CHECK();
     }
-    if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    NVB_STAGE(6);
+    if (!dedup) NVB_CUDA_TRY(cudaMemcpyAsync(counts + 2, counts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    NVB_STAGE(7);
     g_stage_ev_valid = true;
     return NVB_OK;
 }

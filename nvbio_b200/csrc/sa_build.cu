@@ -153,11 +153,11 @@ sa_emit_bwt_kernel(const uint32_t* __restrict__ text, const uint32_t* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-sa_emit_ssa_kernel(const uint32_t* __restrict__ vals, uint64_t n, uint32_t n_items, uint32_t* __restrict__ ssa)
+sa_emit_ssa_kernel(const uint32_t* __restrict__ vals, uint64_t n, uint64_t n_items, uint32_t interval, uint32_t* __restrict__ ssa)
 {
-    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= n_items) return;
-    ssa[t] = (t == 0) ? 0xFFFFFFFFu : vals[(uint64_t)t * 16 - 1];
+    ssa[t] = (t == 0) ? 0xFFFFFFFFu : vals[t * interval - 1];
 }
 
 __global__ void __launch_bounds__(256)
@@ -175,9 +175,12 @@ static inline uint32_t grid_for(uint64_t n) { return (uint32_t)((n + 255) / 256)
 using namespace nvb;
 
 extern "C" int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n32, uint32_t* d_bwt, uint32_t* h_primary,
-                                uint32_t* d_ssa, uint32_t* d_sa, void* d_temp, size_t* temp_bytes, void* stream)
+                                uint32_t* d_ssa, uint32_t sa_interval, uint32_t* d_sa,
+                                void* d_temp, size_t* temp_bytes, void* stream)
 {
     if (!temp_bytes || !h_primary || n32 == 0 || !d_text) return NVB_E_INVALID;
+    if (sa_interval == 0) sa_interval = 16;
+    if (sa_interval & (sa_interval - 1)) return NVB_E_INVALID;
     const uint64_t n = n32;
     const uint64_t n_words = (n + 15) / 16;
     cudaStream_t s = as_stream(stream);
@@ -265,8 +268,8 @@ extern "C" int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n32, uint32_t* 
     sa_emit_bwt_kernel<<<grid_for(n_out_words), 256, 0, s>>>(d_text, vals, n, d_scalars, n_out_words, d_bwt);
     NVB_LAUNCH_CHECK();
     if (d_ssa) {
-        const uint32_t n_items = (uint32_t)((n + 16) / 16);
-        sa_emit_ssa_kernel<<<grid_for(n_items), 256, 0, s>>>(vals, n, n_items, d_ssa);
+        const uint64_t n_items = (n + sa_interval) / sa_interval;
+        sa_emit_ssa_kernel<<<grid_for(n_items), 256, 0, s>>>(vals, n, n_items, sa_interval, d_ssa);
         NVB_LAUNCH_CHECK();
     }
     if (d_sa) {

@@ -29,11 +29,11 @@ def broadcast_index(index_or_none, genome_or_none, device, src: int = 0):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return index_or_none, genome_or_none
     rank = dist.get_rank()
-    meta = torch.zeros(10, dtype=torch.int64, device=device)
+    meta = torch.zeros(11, dtype=torch.int64, device=device)
     if rank == src:
         f = index_or_none
-        meta[:10] = torch.tensor([f.length, f.primary] + list(f.L2) + [f.bwt_occ.numel(), f.ssa.numel(), genome_or_none.numel()],
-                                 dtype=torch.int64, device=device)
+        meta[:11] = torch.tensor([f.length, f.primary] + list(f.L2) + [f.bwt_occ.numel(), f.ssa.numel(), genome_or_none.numel(),
+                                  getattr(f, "sa_interval", 16)], dtype=torch.int64, device=device)
     dist.broadcast(meta, src=src)
     m = [int(v) for v in meta.cpu()]
     if rank == src:
@@ -46,7 +46,7 @@ def broadcast_index(index_or_none, genome_or_none, device, src: int = 0):
         dist.broadcast(t, src=src)
     if rank == src:
         return index_or_none, genome_or_none
-    return FMIndexDevice(bwt_occ, ssa, m[2:7], m[0], m[1]), genome
+    return FMIndexDevice(bwt_occ, ssa, m[2:7], m[0], m[1], sa_interval=m[10]), genome
 
 
 def max_over_ranks(value: float, device) -> float:

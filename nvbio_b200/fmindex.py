@@ -27,11 +27,14 @@ class FMIndexDevice:
     """Device-resident FM-index in the reference's production layout: interleaved 32-byte
     {bwt,occ} blocks + SA sampled every 16 rows (io::FMIndexDataDevice, nvbio/io/fmindex/fmindex.h:294-352)."""
 
-    def __init__(self, bwt_occ: torch.Tensor, ssa: Optional[torch.Tensor], L2, length: int, primary: int):
+    def __init__(self, bwt_occ: torch.Tensor, ssa: Optional[torch.Tensor], L2, length: int, primary: int,
+                 sa_interval: int = 16, ktab: Optional[torch.Tensor] = None, ktab_k: int = 0):
         assert bwt_occ.is_cuda and bwt_occ.data_ptr() % 32 == 0
         self.bwt_occ, self.ssa = bwt_occ, ssa
         self.L2 = [int(v) for v in L2]
         self.length, self.primary = int(length), int(primary)
+        self.sa_interval = int(sa_interval)        # 16 = the reference's SA_INT; 1 = full suffix array
+        self.ktab, self.ktab_k = ktab, int(ktab_k)  # optional k-mer range table (B200 extension)
 
     # -- views ------------------------------------------------------------------------------
     def struct(self) -> FmIndexStruct:
@@ -41,6 +44,9 @@ class FMIndexDevice:
         s.length, s.primary = self.length, self.primary
         for i in range(5):
             s.L2[i] = self.L2[i]
+        s.sa_interval = self.sa_interval
+        s.d_ktab = self.ktab.data_ptr() if self.ktab is not None else None
+        s.ktab_k = self.ktab_k if self.ktab is not None else 0
         return s
 
     @property
@@ -48,17 +54,27 @@ class FMIndexDevice:
         return self.bwt_occ.device
 
     def nbytes(self):
-        return self.bwt_occ.numel() * 4 + (self.ssa.numel() * 4 if self.ssa is not None else 0)
+        return (self.bwt_occ.numel() * 4 + (self.ssa.numel() * 4 if self.ssa is not None else 0) +
+                (self.ktab.numel() * 4 if self.ktab is not None else 0))
+
+    def build_ktab(self, k: int = 12):
+        """k-mer range table (4^k x uint2): replaces the first k LF steps of every match()"""
+        tab = torch.empty((4 ** k, 2), dtype=torch.int32, device=self.device)
+        s = self.struct()
+        check(lib().nvb_fm_build_ktab(C.byref(s), C.c_uint32(k), C.c_void_p(tab.data_ptr()), _stream()), "nvb_fm_build_ktab")
+        self.ktab, self.ktab_k = tab, k
+        return self
 
     # -- construction -----------------------------------------------------------------------
     @staticmethod
-    def from_host(bwt_occ: np.ndarray, ssa: Optional[np.ndarray], L2, length, primary, device="cuda"):
+    def from_host(bwt_occ: np.ndarray, ssa: Optional[np.ndarray], L2, length, primary, device="cuda", sa_interval=16):
         """upload host arrays laid out as the reference's loader produces them
         (nvbio/io/fmindex/fmindex_impl.cu:263-331)"""
-        return FMIndexDevice(_dev_u32(bwt_occ, device), None if ssa is None else _dev_u32(ssa, device), L2, length, primary)
+        return FMIndexDevice(_dev_u32(bwt_occ, device), None if ssa is None else _dev_u32(ssa, device), L2, length, primary,
+                             sa_interval=sa_interval)
 
     @staticmethod
-    def from_bwt(bwt_words: torch.Tensor, n: int, primary: int, ssa: Optional[torch.Tensor]):
+    def from_bwt(bwt_words: torch.Tensor, n: int, primary: int, ssa: Optional[torch.Tensor], sa_interval: int = 16):
         """occ table + interleave on the device (replaces build_occurrence_table + the interleave loop)"""
         L = lib()
         n_blocks = (n + 63) // 64
@@ -72,33 +88,34 @@ class FMIndexDevice:
         temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=bwt_words.device)
         check(L.nvb_fm_build_occ(C.c_void_p(bwt_words.data_ptr()), C.c_uint32(n), C.c_void_p(bwt_occ.data_ptr()), L2,
                                  C.c_void_p(temp.data_ptr()), C.byref(tb), _stream()), "nvb_fm_build_occ")
-        return FMIndexDevice(bwt_occ, ssa, list(L2), n, primary)
+        return FMIndexDevice(bwt_occ, ssa, list(L2), n, primary, sa_interval=sa_interval)
 
     @staticmethod
-    def from_text(text_words: torch.Tensor, n: int, want_sa: bool = False):
+    def from_text(text_words: torch.Tensor, n: int, want_sa: bool = False, sa_interval: int = 16):
         """suffix-sort a 2-bit big-endian packed text on the device and build the whole index.
-        text_words must be readable 2 words past ceil(n/16).  Returns (index, sa or None)."""
+        text_words must be readable 2 words past ceil(n/16).  Returns (index, sa or None).
+        sa_interval: 16 = the reference's format; smaller powers of two (down to 1) trade HBM for locate steps."""
         L = lib()
         dev = text_words.device
         bwt = torch.empty(((n + 63) // 64) * 4, dtype=torch.int32, device=dev)
-        ssa = torch.empty((n + 16) // 16, dtype=torch.int32, device=dev)
+        ssa = torch.empty((n + sa_interval) // sa_interval, dtype=torch.int32, device=dev)
         sa = torch.empty(n + 1, dtype=torch.int32, device=dev) if want_sa else None
         primary = C.c_uint32(0)
         tb = C.c_size_t(0)
         args = (C.c_void_p(text_words.data_ptr()), C.c_uint32(n), C.c_void_p(bwt.data_ptr()), C.byref(primary),
-                C.c_void_p(ssa.data_ptr()), C.c_void_p(sa.data_ptr()) if sa is not None else None)
+                C.c_void_p(ssa.data_ptr()), C.c_uint32(sa_interval), C.c_void_p(sa.data_ptr()) if sa is not None else None)
         r = L.nvb_fm_build_bwt(*args, None, C.byref(tb), _stream())
         if r != -2:
             check(r, "nvb_fm_build_bwt(size query)")
         temp = torch.empty(tb.value, dtype=torch.uint8, device=dev)
         check(L.nvb_fm_build_bwt(*args, C.c_void_p(temp.data_ptr()), C.byref(tb), _stream()), "nvb_fm_build_bwt")
         del temp
-        idx = FMIndexDevice.from_bwt(bwt, n, int(primary.value), ssa)
+        idx = FMIndexDevice.from_bwt(bwt, n, int(primary.value), ssa, sa_interval=sa_interval)
         return idx, sa
 
     def to_host(self):
         return dict(bwt_occ=_np_u32(self.bwt_occ), ssa=None if self.ssa is None else _np_u32(self.ssa),
-                    L2=np.array(self.L2, dtype=np.uint32), n=self.length, primary=self.primary)
+                    L2=np.array(self.L2, dtype=np.uint32), n=self.length, primary=self.primary, sa_interval=self.sa_interval)
 
 
 def rank(fmi: FMIndexDevice, k: torch.Tensor, c: torch.Tensor) -> torch.Tensor:

@@ -17,6 +17,7 @@ class SeedExtendParams:
     type: int = aln.LOCAL
     both_strands: bool = True
     max_seed_hits: int = 100         # nvBowtie max_hits
+    dedup_jobs: bool = True          # score identical (strand, window) jobs of a read once
     scheme: object = field(default_factory=lambda: aln.SimpleGotohScheme(2, -2, -5, -3))
 
     def struct(self) -> SeedExtendParamsStruct:
@@ -24,6 +25,7 @@ class SeedExtendParams:
         p.seed_len, p.seed_interval, p.band_len, p.type = self.seed_len, self.seed_interval, self.band_len, self.type
         p.both_strands = 1 if self.both_strands else 0
         p.max_seed_hits = self.max_seed_hits
+        p.dedup_jobs = 1 if self.dedup_jobs else 0
         p.scheme = self.scheme.struct()
         return p
 
@@ -37,7 +39,7 @@ class SeedExtendWorkspace:
         n = reads.count
         self.best_score = torch.empty(n, dtype=torch.int32, device=dev)
         self.best_pos = torch.empty(n, dtype=torch.int32, device=dev)
-        self.n_hits = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.n_hits = torch.zeros(3, dtype=torch.int32, device=dev)      # kept, found, distinct alignment jobs
         self.hit_capacity = hit_capacity
         self.hit_read = self.hit_window = self.hit_score = self.hit_sink = None
         if keep_hits:
@@ -77,11 +79,11 @@ def seed_extend(fmi: FMIndexDevice, genome: torch.Tensor, reads: PackedStringSet
     return workspace
 
 
-STAGES = ("strings", "seed_match", "hit_slots", "locate_windows", "extend", "reduce")
+STAGES = ("strings", "seed_match", "hit_slots", "locate_windows", "dedup", "extend", "reduce")
 
 
 def last_stage_ms():
     """device time (ms) of the stages of the most recent seed_extend call"""
-    ms = (C.c_float * 6)()
+    ms = (C.c_float * 7)()
     check(lib().nvb_seed_extend_stage_ms(ms), "nvb_seed_extend_stage_ms")
     return dict(zip(STAGES, [float(v) for v in ms]))

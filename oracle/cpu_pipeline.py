@@ -15,7 +15,7 @@ def gather_2bit(words_u32: np.ndarray, pos: np.ndarray) -> np.ndarray:
 
 
 def cpu_seed_extend(E, idx, genome_words_u32, reads_sym, seed_len=20, seed_interval=10, band=31, typ=1,
-                    scheme=(2, -2, -5, -3), both_strands=True, max_seed_hits=100, count_blocks_with=None):
+                    scheme=(2, -2, -5, -3), both_strands=True, max_seed_hits=100, count_blocks_with=None, blocks_from_step=0):
     """reads_sym: uint8 [n, L] (fixed length).  Returns dict with best_score[n], timings and counts."""
     n, L = reads_sym.shape
     glen = idx.n
@@ -38,9 +38,11 @@ def cpu_seed_extend(E, idx, genome_words_u32, reads_sym, seed_len=20, seed_inter
     t0 = time.perf_counter()
     ranges, _ = E.match(idx, q, off, ln)
     t_match = time.perf_counter() - t0
-    blocks = None
+    blocks = blocks_tail = None
     if count_blocks_with is not None:
         _, blocks = count_blocks_with.match(idx, q, off, ln)
+        if blocks_from_step:
+            _, blocks_tail = count_blocks_with.match(idx, q, off, ln, blocks_from_step=blocks_from_step)
 
     x = ranges[:, 0].astype(np.int64); y = ranges[:, 1].astype(np.int64)
     sizes = np.where(x <= y, np.minimum(y - x + 1, max_seed_hits), 0)
@@ -84,5 +86,5 @@ def cpu_seed_extend(E, idx, genome_words_u32, reads_sym, seed_len=20, seed_inter
     if total:
         np.maximum.at(best, s_id // strands, score.astype(np.int64))
     return dict(best_score=best, n_seeds=nq, n_hits=total, t_match=t_match, t_locate=t_locate, t_dp=t_dp,
-                t_total=t_match + t_locate + t_dp, blocks=blocks, hit_score=score, hit_read=s_id // strands,
+                t_total=t_match + t_locate + t_dp, blocks=blocks, blocks_tail=blocks_tail, hit_score=score, hit_read=s_id // strands,
                 cells=int(total) * L * band)

@@ -218,27 +218,35 @@ void orc_rank(const u32* bwt_occ, const u32* L2, u32 n, u32 primary, const u32* 
 /* backward search, nvBowtie's form: a symbol > 3 aborts with the empty range (1,0)
  * (nvbio/fmindex/fmindex_inl.h:307-341; nvBowtie/bowtie2/cuda/mapping_inl.h:83-97).
  * Queries are unpacked symbols.  Returns the total number of 32-byte blocks touched. */
-u64 orc_match(const u32* bwt_occ, const u32* L2, u32 n, u32 primary,
-              const u8* q, const u32* off, const u32* len, u32 nq, u32* out_xy)
+/* blocks_from_step: LF steps with index < blocks_from_step are not counted in the returned block total
+ * (used to size the traffic of a search whose first k steps are replaced by a k-mer table look-up) */
+u64 orc_match_from(const u32* bwt_occ, const u32* L2, u32 n, u32 primary,
+              const u8* q, const u32* off, const u32* len, u32 nq, u32* out_xy, u32 blocks_from_step)
 {
     orc_index f = { bwt_occ, NULL, n, primary, { L2[0], L2[1], L2[2], L2[3], L2[4] } };
-    u64 blocks = 0;
+    u64 blocks = 0, skipped = 0;
     for (u32 s = 0; s < nq; ++s)
     {
         u32 x = 0, y = n;
         const u8* p = q + off[s];
-        for (i32 i = (i32)len[s] - 1; i >= 0 && x <= y; --i)
+        u32 step = 0;
+        for (i32 i = (i32)len[s] - 1; i >= 0 && x <= y; --i, ++step)
         {
             const u32 c = p[i];
             if (c > 3) { x = 1; y = 0; break; }
             u32 rx, ry;
-            fm_rank2(&f, x - 1u, y, c, &rx, &ry, &blocks);
+            fm_rank2(&f, x - 1u, y, c, &rx, &ry, step >= blocks_from_step ? &blocks : &skipped);
             x = f.L2[c] + rx + 1u;
             y = f.L2[c] + ry;
         }
         out_xy[2 * s] = x; out_xy[2 * s + 1] = y;
     }
     return blocks;
+}
+u64 orc_match(const u32* bwt_occ, const u32* L2, u32 n, u32 primary,
+              const u8* q, const u32* off, const u32* len, u32 nq, u32* out_xy)
+{
+    return orc_match_from(bwt_occ, L2, n, primary, q, off, len, nq, out_xy, 0);
 }
 
 /* locate: LF-walk to the next sampled row (rows that are multiples of 16), then ssa + steps

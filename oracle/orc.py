@@ -55,6 +55,7 @@ class Oracle(_Base):
             subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
         self.lib = C.CDLL(path)
         self.lib.orc_match.restype = C.c_uint64
+        self.lib.orc_match_from.restype = C.c_uint64
         self.lib.orc_locate.restype = C.c_uint64
         self.lib.orc_bwt_from_sa.restype = C.c_uint32
         self.lib.orc_dict_rank.restype = C.c_uint32
@@ -98,14 +99,14 @@ class Oracle(_Base):
         return np.array([self.lib.orc_dict_rank(_p(idx.bwt_occ), C.c_uint32(int(a)), C.c_uint32(int(b)))
                          for a, b in zip(i, c)], dtype=np.uint32)
 
-    def match(self, idx, q, off, ln):
-        """returns (ranges[nq,2] inclusive, total 32-byte blocks touched)"""
+    def match(self, idx, q, off, ln, blocks_from_step=0):
+        """returns (ranges[nq,2] inclusive, total 32-byte blocks touched by LF steps >= blocks_from_step)"""
         q = np.ascontiguousarray(q, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         ln = np.ascontiguousarray(ln, dtype=np.uint32)
         out = np.zeros((len(off), 2), dtype=np.uint32)
-        blocks = self.lib.orc_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(idx.n), C.c_uint32(idx.primary),
-                                    _p(q), _p(off), _p(ln), C.c_uint32(len(off)), _p(out))
+        blocks = self.lib.orc_match_from(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(idx.n), C.c_uint32(idx.primary),
+                                         _p(q), _p(off), _p(ln), C.c_uint32(len(off)), _p(out), C.c_uint32(blocks_from_step))
         return out, int(blocks)
 
     def locate(self, idx, rows):

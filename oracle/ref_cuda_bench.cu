@@ -1,0 +1,186 @@
+// oracle/ref_cuda_bench.cu -- BASELINE INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// The reference's own CUDA path (its sm_35-era kernels, header templates included from /root/reference where
+// they lie) recompiled for sm_100a, driven through the reference's public batch APIs:
+//   banded : aln::batch_banded_alignment_score<31>( make_gotoh_aligner<LOCAL>(SimpleGotohScheme), patterns, texts,
+//            sinks, DeviceThreadScheduler(), ... )      nvbio/alignment/batched_inl.h:1067-1101
+//            -> batched_banded_alignment_score_kernel     nvbio/alignment/batched_banded_inl.h:78-162
+//   fm     : FMIndexFilterDevice<fm_index_type>::rank + locate   nvbio/fmindex/filter_inl.h:268-402
+// Inputs are the arrays bench.py / the tests dump (same workload as the B200-native kernels); outputs are
+// written back so that the results can be compared bit for bit.
+//
+// Build (oracle/Makefile, only where /root/reference exists):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -use_fast_math -Xcompiler -fopenmp \
+//        -I/root/reference -I/root/reference/contrib oracle/ref_cuda_bench.cu -o oracle/_ref/ref_cuda_bench
+#include <nvbio/basic/types.h>
+#include <nvbio/basic/packedstream.h>
+#include <nvbio/basic/deinterleaved_iterator.h>
+#include <nvbio/basic/cuda/ldg.h>
+#include <nvbio/strings/string_set.h>
+#include <nvbio/fmindex/bwt.h>
+#include <nvbio/fmindex/fmindex.h>
+#include <nvbio/fmindex/ssa.h>
+#include <nvbio/fmindex/filter.h>
+#include <nvbio/alignment/alignment.h>
+#include <nvbio/alignment/batched.h>
+#include <thrust/device_vector.h>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+using namespace nvbio;
+
+template <typename T>
+static std::vector<T> read_file(const std::string& path)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+    fseek(f, 0, SEEK_END); const long bytes = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<T> v(bytes / sizeof(T));
+    if (fread(v.data(), 1, bytes, f) != (size_t)bytes) { fprintf(stderr, "short read %s\n", path.c_str()); exit(2); }
+    fclose(f);
+    return v;
+}
+template <typename T>
+static void write_file(const std::string& path, const T* p, size_t n)
+{
+    FILE* f = fopen(path.c_str(), "wb"); fwrite(p, sizeof(T), n, f); fclose(f);
+}
+
+// --------------------------------------------------------------------------------------------------
+// banded Gotoh: n patterns of M symbols (2-bit big-endian, pattern i at symbols [i*Mstride, +M)) against
+// genome windows [begin,end)
+// --------------------------------------------------------------------------------------------------
+static int run_banded(const std::string& dir)
+{
+    const std::vector<uint32> meta = read_file<uint32>(dir + "/meta.bin");    // n, M, Mstride, match, mismatch(neg as int), go, ge, reps
+    const uint32 n = meta[0], M = meta[1], Mstride = meta[2];
+    const int32 s_match = (int32)meta[3], s_mm = (int32)meta[4], s_go = (int32)meta[5], s_ge = (int32)meta[6];
+    const uint32 reps = meta[7];
+    const std::vector<uint32> h_pat = read_file<uint32>(dir + "/pat_words.bin");
+    const std::vector<uint32> h_gen = read_file<uint32>(dir + "/genome_words.bin");
+    const std::vector<uint2>  h_win = read_file<uint2>(dir + "/windows.bin");
+
+    thrust::device_vector<uint32> d_pat(h_pat), d_gen(h_gen);
+    thrust::device_vector<uint2>  d_win(h_win);
+    std::vector<uint2> h_prange(n);
+    for (uint32 i = 0; i < n; ++i) h_prange[i] = make_uint2(i * Mstride, i * Mstride + M);
+    thrust::device_vector<uint2> d_prange(h_prange);
+    thrust::device_vector< aln::BestSink<int32> > d_sinks(n);
+
+    typedef nvbio::cuda::ldg_pointer<uint32>                    storage_it;
+    typedef PackedStream<storage_it, uint8, 2u, true>           stream_t;
+    typedef SparseStringSet<stream_t, const uint2*>             set_t;
+
+    const stream_t pat_stream( storage_it( thrust::raw_pointer_cast(d_pat.data()) ) );
+    const stream_t gen_stream( storage_it( thrust::raw_pointer_cast(d_gen.data()) ) );
+    const set_t patterns( n, pat_stream, thrust::raw_pointer_cast(d_prange.data()) );
+    const set_t texts   ( n, gen_stream, thrust::raw_pointer_cast(d_win.data()) );
+
+    const aln::SimpleGotohScheme scheme( s_match, s_mm, s_go, s_ge );
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best_ms = 1e30f;
+    for (uint32 r = 0; r < reps + 1; ++r)
+    {
+        cudaEventRecord(e0);
+        aln::batch_banded_alignment_score<31u>(
+            aln::make_gotoh_aligner<aln::LOCAL>( scheme ),
+            patterns, texts,
+            thrust::raw_pointer_cast(d_sinks.data()),
+            aln::DeviceThreadScheduler(),
+            M, M + 31u + 8u );
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best_ms) best_ms = ms;              // first run is the warm-up
+    }
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+    std::vector< aln::BestSink<int32> > h_sinks(n);
+    cudaMemcpy(h_sinks.data(), thrust::raw_pointer_cast(d_sinks.data()), sizeof(aln::BestSink<int32>) * n, cudaMemcpyDeviceToHost);
+    std::vector<int32> score(n); std::vector<uint2> sink(n);
+    for (uint32 i = 0; i < n; ++i) { score[i] = h_sinks[i].score; sink[i] = h_sinks[i].sink; }
+    write_file(dir + "/ref_scores.bin", score.data(), n);
+    write_file(dir + "/ref_sinks.bin", sink.data(), n);
+    printf("{\"what\": \"reference CUDA batched_banded_alignment_score_kernel<128,1,31> (LOCAL Gotoh), sm_100a\", \"n\": %u, \"M\": %u, "
+           "\"ms\": %.4f, \"gcups\": %.2f}\n", n, M, best_ms, double(n) * M * 31.0 / (best_ms * 1e-3) / 1e9);
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// FM-index: nq seeds of L symbols (2-bit big-endian, seed i at [i*Lstride, +L))
+// --------------------------------------------------------------------------------------------------
+static int run_fm(const std::string& dir)
+{
+    const std::vector<uint32> meta = read_file<uint32>(dir + "/meta.bin");    // length, primary, L2[5], nq, L, Lstride, reps
+    const uint32 length = meta[0], primary = meta[1], nq = meta[7], L = meta[8], Lstride = meta[9], reps = meta[10];
+    const std::vector<uint32> h_bwt_occ = read_file<uint32>(dir + "/bwt_occ.bin");
+    const std::vector<uint32> h_ssa     = read_file<uint32>(dir + "/ssa.bin");
+    const std::vector<uint32> h_seeds   = read_file<uint32>(dir + "/seed_words.bin");
+    thrust::device_vector<uint32> d_bwt_occ(h_bwt_occ), d_ssa(h_ssa), d_seeds(h_seeds), d_L2(meta.begin() + 2, meta.begin() + 7);
+    std::vector<uint32> h_ct(256); gen_bwt_count_table(h_ct.data());
+    thrust::device_vector<uint32> d_ct(h_ct);
+    std::vector<uint2> h_range(nq);
+    for (uint32 i = 0; i < nq; ++i) h_range[i] = make_uint2(i * Lstride, i * Lstride + L);
+    thrust::device_vector<uint2> d_range(h_range);
+
+    // the production device index types (nvbio/io/fmindex/fmindex.h:302-319)
+    typedef nvbio::cuda::ldg_pointer<uint4>                              bwt_occ_type;
+    typedef deinterleaved_iterator<2,0,bwt_occ_type>                     bwt_type;
+    typedef deinterleaved_iterator<2,1,bwt_occ_type>                     occ_type;
+    typedef nvbio::cuda::ldg_pointer<uint32>                             u32_ldg;
+    typedef PackedStream<bwt_type,uint8,2u,true>                         bwt_stream_type;
+    typedef SSA_index_multiple_context<16u,u32_ldg>                      ssa_type;
+    typedef rank_dictionary<2u,64u,bwt_stream_type,occ_type,u32_ldg>     rank_dict_type;
+    typedef fm_index<rank_dict_type,ssa_type>                            fm_index_type;
+
+    const bwt_occ_type p( (const uint4*)thrust::raw_pointer_cast(d_bwt_occ.data()) );
+    const fm_index_type fmi( length, primary, thrust::raw_pointer_cast(d_L2.data()),
+        rank_dict_type( bwt_stream_type( bwt_type(p) ), occ_type(p), u32_ldg( thrust::raw_pointer_cast(d_ct.data()) ) ),
+        ssa_type( u32_ldg( thrust::raw_pointer_cast(d_ssa.data()) ) ) );
+
+    typedef PackedStream<u32_ldg, uint8, 2u, true>          stream_t;
+    typedef SparseStringSet<stream_t, const uint2*>         set_t;
+    const set_t seeds( nq, stream_t( u32_ldg( thrust::raw_pointer_cast(d_seeds.data()) ) ), thrust::raw_pointer_cast(d_range.data()) );
+
+    FMIndexFilterDevice<fm_index_type> filter;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float rank_ms = 1e30f, locate_ms = 1e30f; uint64 n_hits = 0;
+    thrust::device_vector<uint2> d_hits;
+    for (uint32 r = 0; r < reps + 1; ++r)
+    {
+        cudaEventRecord(e0);
+        n_hits = filter.rank( fmi, seeds );
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < rank_ms) rank_ms = ms;
+        const uint64 n_loc = n_hits < (uint64(1) << 26) ? n_hits : (uint64(1) << 26);
+        d_hits.resize(n_loc);
+        cudaEventRecord(e0);
+        filter.locate( 0, n_loc, d_hits.begin() );
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < locate_ms) locate_ms = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+    std::vector<uint2> h_ranges(nq);
+    cudaMemcpy(h_ranges.data(), filter.ranges(), sizeof(uint2) * nq, cudaMemcpyDeviceToHost);
+    write_file(dir + "/ref_ranges.bin", h_ranges.data(), nq);
+    std::vector<uint2> h_hits(d_hits.size());
+    cudaMemcpy(h_hits.data(), thrust::raw_pointer_cast(d_hits.data()), sizeof(uint2) * d_hits.size(), cudaMemcpyDeviceToHost);
+    write_file(dir + "/ref_hits.bin", h_hits.data(), h_hits.size());
+    printf("{\"what\": \"reference CUDA FMIndexFilterDevice::rank/locate (thrust::transform of match()/locate), sm_100a\", \"nq\": %u, \"L\": %u, "
+           "\"n_hits\": %llu, \"rank_ms\": %.4f, \"mseeds_per_s\": %.2f, \"locate_ms\": %.4f}\n",
+           nq, L, (unsigned long long)n_hits, rank_ms, double(nq) / (rank_ms * 1e-3) / 1e6, locate_ms);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: ref_cuda_bench banded|fm <dir>\n"); return 1; }
+    const std::string mode = argv[1], dir = argv[2];
+    if (mode == "banded") return run_banded(dir);
+    if (mode == "fm")     return run_fm(dir);
+    return 1;
+}

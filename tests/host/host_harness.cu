@@ -8,10 +8,12 @@
 
 using namespace nvb;
 
-static FmIndex mk(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary) {
-    FmIndex f; f.blocks = (const FmBlock*)bwt_occ; f.ssa = ssa; f.n = n; f.primary = primary;
-    for (int i = 0; i < 5; ++i) f.L2[i] = L2[i];
-    return f;
+static FmIndex mk(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
+                  uint32_t sa_interval = 16, const uint32_t* ktab = nullptr, uint32_t ktab_k = 0) {
+    nvb_fm_index c; c.d_bwt_occ = bwt_occ; c.d_ssa = ssa; c.length = n; c.primary = primary;
+    for (int i = 0; i < 5; ++i) c.L2[i] = L2[i];
+    c.sa_interval = sa_interval; c.d_ktab = (const nvb_uint2*)ktab; c.ktab_k = ktab_k;
+    return make_fmindex(&c);
 }
 
 extern "C" {
@@ -22,10 +24,27 @@ void hh_fm_rank(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_
     for (uint32_t i = 0; i < nq; ++i) out[i] = fm_rank1(f, k[i], c[i] & 3u);
 }
 
+// mirrors fm_ktab_level_kernel level by level
+void hh_fm_build_ktab(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary, uint32_t k, uint32_t* ktab) {
+    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary);
+    uint2* tab = (uint2*)ktab;
+    tab[0] = make_uint2(0u, n);
+    uint32_t prev = 1;
+    for (uint32_t t = 1; t <= k; ++t, prev *= 4u)
+        for (uint32_t v = 0; v < prev; ++v) {
+            const uint2 r = tab[v];
+            for (int c = 3; c >= 0; --c) {
+                uint32_t x = r.x, y = r.y;
+                if (x <= y) fm_step(f, (uint32_t)c, x, y);
+                tab[(uint32_t)c * prev + v] = make_uint2(x, y);
+            }
+        }
+}
+
 void hh_fm_match(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary,
                  const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len, uint32_t nq,
-                 uint32_t flags, uint32_t* out_xy) {
-    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary);
+                 uint32_t flags, uint32_t* out_xy, const uint32_t* ktab, uint32_t ktab_k) {
+    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary, 16, ktab, ktab_k);
     for (uint32_t i = 0; i < nq; ++i) {
         uint32_t x, y;
 #define CALL(B, E) fm_match_one<B, E>(f, words, off[i], len[i], flags, x, y)
@@ -36,8 +55,8 @@ void hh_fm_match(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32
 }
 
 void hh_fm_locate(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
-                  const uint32_t* rows, uint32_t nq, uint32_t* out) {
-    const FmIndex f = mk(bwt_occ, ssa, L2, n, primary);
+                  const uint32_t* rows, uint32_t nq, uint32_t* out, uint32_t sa_interval) {
+    const FmIndex f = mk(bwt_occ, ssa, L2, n, primary, sa_interval);
     for (uint32_t i = 0; i < nq; ++i) out[i] = fm_locate_one(f, rows[i]);
 }
 
@@ -93,7 +112,7 @@ int hh_gotoh_generic(int band, int type, const int32_t* scheme6, const int32_t* 
                      const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen, const uint8_t* quals,
                      const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
                      uint32_t n, int32_t* score, uint32_t* sx, uint32_t* sy) {
-    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab;
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab; S.one = 1u; S.keymul = 32u;
     switch (band) {
     case 3:  TYPE_SWITCH(3,  run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
     case 5:  TYPE_SWITCH(5,  run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
@@ -110,7 +129,7 @@ int hh_gotoh_pair(int band, int type, const int32_t* scheme6, uint32_t max_m,
                   const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                   const uint32_t* tw, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
                   uint32_t n, int32_t* score, uint32_t* sx, uint32_t* sy, uint32_t* n_fallback) {
-    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr;
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr; S.one = 1u; S.keymul = 32u;
     nvb_gotoh_scheme cs; cs.match = S.match; cs.mismatch = S.mismatch; cs.pattern_gap_open = S.pgo; cs.pattern_gap_ext = S.pge;
     cs.text_gap_open = S.tgo; cs.text_gap_ext = S.tge; cs.d_qual_table = nullptr;
     if (!pair_path_ok(band, type, &cs, max_m)) return -2;

@@ -33,7 +33,7 @@ def _worker(rank, world, port, q):
     dev = torch.device("cpu")
     if rank == 0:
         f = FakeIndex()
-        f.length, f.primary, f.L2 = 1000, 17, [0, 250, 500, 760, 1000]
+        f.length, f.primary, f.L2, f.sa_interval = 1000, 17, [0, 250, 500, 760, 1000], 4
         f.bwt_occ = torch.arange(16 * 8, dtype=torch.int32)
         f.ssa = torch.arange(63, dtype=torch.int32)
         genome = torch.arange(70, dtype=torch.int32)
@@ -42,12 +42,13 @@ def _worker(rank, world, port, q):
     # patch the constructor check so that the CPU tensors are accepted in this gloo test
     orig = FMIndexDevice.__init__
 
-    def init(self, bwt_occ, ssa, L2, length, primary):
+    def init(self, bwt_occ, ssa, L2, length, primary, sa_interval=16):
         self.bwt_occ, self.ssa, self.L2, self.length, self.primary = bwt_occ, ssa, [int(v) for v in L2], int(length), int(primary)
+        self.sa_interval = sa_interval
     FMIndexDevice.__init__ = init
     g, gen = nd.broadcast_index(f, genome, dev, src=0)
     FMIndexDevice.__init__ = orig
-    ok = (g.length == 1000 and g.primary == 17 and list(g.L2) == [0, 250, 500, 760, 1000] and
+    ok = (g.length == 1000 and g.primary == 17 and g.sa_interval == 4 and list(g.L2) == [0, 250, 500, 760, 1000] and
           torch.equal(g.bwt_occ, torch.arange(16 * 8, dtype=torch.int32)) and torch.equal(g.ssa, torch.arange(63, dtype=torch.int32)) and
           torch.equal(gen, torch.arange(70, dtype=torch.int32)))
     t = nd.max_over_ranks(1.0 + rank, dev)

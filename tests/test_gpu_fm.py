@@ -180,3 +180,43 @@ def test_large_index_properties():
     perm = torch.randperm(200_000, device="cuda")
     q2 = PackedStringSet.fixed(sw[perm].contiguous().reshape(-1), 200_000, 22, stride=32)
     assert torch.equal(nb.match(fmi, q2), r[perm])
+
+
+@pytest.mark.parametrize("k", [1, 5, 9])
+def test_ktab_gives_identical_ranges(O, k):
+    """the k-mer range table (B200 extension) only replaces the first k LF steps: ranges stay bit-identical,
+    including empty ranges (the reference's early exit), N's and queries shorter than k"""
+    rng = np.random.default_rng(k)
+    text = rng.integers(0, 4, 90001).astype(np.uint8)
+    idx = O.build_index(text)
+    plain = upload(idx)
+    tab = upload(idx).build_ktab(k)
+    assert tab.ktab.shape[0] == 4 ** k
+    # table entries themselves == match() of every k-mer
+    kmers = np.array([[(u >> (2 * (k - 1 - j))) & 3 for j in range(k)] for u in range(min(4 ** k, 4096))], np.uint8)
+    want_tab, _ = O.match(idx, kmers.reshape(-1), np.arange(len(kmers)) * k, np.full(len(kmers), k))
+    assert np.array_equal(host_u32(tab.ktab)[:len(kmers)], want_tab)
+    q, offs, lens = _queries(rng, text, 30000, lo=1, hi=28, n_frac=0.03)
+    want, _ = O.match(idx, q, offs, lens)
+    for bits, be in ((4, True), (8, False)):
+        qs = PackedStringSet.from_symbols(q, offs, lens, bits=bits, big_endian=be)
+        assert np.array_equal(host_u32(nb.match(tab, qs)), want)
+    q2 = np.where(q > 3, 0, q).astype(np.uint8)
+    qs = PackedStringSet.from_symbols(q2, offs, lens, bits=2)
+    for flags in (0, nb.MATCH_FORWARD_ORDER | nb.MATCH_COMPLEMENT, nb.MATCH_FORWARD_ORDER, nb.MATCH_COMPLEMENT):
+        assert torch.equal(nb.match(tab, qs, flags=flags), nb.match(plain, qs, flags=flags)), flags
+
+
+@pytest.mark.parametrize("interval", [1, 2, 4, 16, 32])
+def test_sampled_sa_interval(O, interval):
+    """denser (or sparser) SA sampling than the reference's SA_INT=16 locates the same positions"""
+    rng = np.random.default_rng(interval)
+    n = 40007
+    text = rng.integers(0, 4, n).astype(np.uint8)
+    ref = O.build_index(text)
+    fmi, _ = nb.FMIndexDevice.from_text(dev_u32(pack_symbols(text, 2, True)), n, sa_interval=interval)
+    assert fmi.ssa.numel() == (n + interval) // interval
+    want_ssa = ref.sa[::interval].astype(np.uint32).copy(); want_ssa[0] = 0xFFFFFFFF
+    assert np.array_equal(host_u32(fmi.ssa), want_ssa)
+    rows = rng.integers(0, n + 1, 5000).astype(np.uint32); rows[:3] = (0, ref.primary, n)
+    assert np.array_equal(host_u32(nb.locate(fmi, dev_u32(rows))), O.locate(ref, rows))

@@ -40,17 +40,29 @@ def test_seed_extend_vs_oracle(both, read_len, ragged):
     ws = nb.seed_extend(fmi, gw, rs, params, hit_capacity=64 * n_reads, keep_hits=True)
     torch.cuda.synchronize()
     want = seed_extend_oracle(O, idx, gsym, reads_sym, params)
-    kept, total = [int(v) for v in ws.n_hits.cpu()]
+    kept, total, jobs = [int(v) for v in ws.n_hits.cpu()]
     assert kept == total == want["n_hits"]
+    uniq = len(set(zip(want["hit_string"].tolist(), want["hit_window"][:, 0].tolist(), want["hit_window"][:, 1].tolist())))
+    assert jobs == uniq < kept              # identical (strand, window) jobs are scored once
     assert np.array_equal(ws.hit_read.cpu().numpy()[:kept].astype(np.int64), want["hit_string"])
     assert np.array_equal(host_u32(ws.hit_window)[:kept].astype(np.int64), want["hit_window"])
     assert np.array_equal(ws.hit_score.cpu().numpy()[:kept].astype(np.int64), want["hit_score"])
     assert np.array_equal(host_u32(ws.hit_sink)[:kept].astype(np.int64), want["hit_sink"])
     assert np.array_equal(ws.best_score.cpu().numpy().astype(np.int64), want["best_score"])
     assert np.array_equal(host_u32(ws.best_pos).astype(np.int64), want["best_pos"])
-    # most reads are found at their true locus
+    # without job de-duplication: same outputs, every hit scored separately
+    params.dedup_jobs = False
+    ws2 = nb.seed_extend(fmi, gw, rs, params, hit_capacity=64 * n_reads, keep_hits=True)
+    torch.cuda.synchronize()
+    assert int(ws2.n_hits[2]) == kept
+    assert torch.equal(ws2.hit_score[:kept], ws.hit_score[:kept]) and torch.equal(ws2.hit_sink[:kept], ws.hit_sink[:kept])
+    assert torch.equal(ws2.best_score, ws.best_score) and torch.equal(ws2.best_pos, ws.best_pos)
+    # most reads are found at their true locus (every other read is reverse-complemented: single-strand
+    # runs can only find the forward half)
     found = (ws.best_score.cpu().numpy() > read_len)   # > half of the perfect score 2*len
-    assert found.mean() > 0.9
+    if ragged:
+        found = (ws.best_score.cpu().numpy() > np.array([len(r) for r in reads_sym]))
+    assert found.mean() > (0.9 if both else 0.45)
 
 
 def test_seed_extend_4bit_reads_with_N():
@@ -87,5 +99,5 @@ def test_hit_capacity_is_respected():
     rw, pos, strand = synth.sample_reads(gw, n, 500, 150, sub_rate=0.0, indel_rate=0.0)
     rs = PackedStringSet.fixed(rw.reshape(-1), 500, 150, stride=rw.shape[1] * 16)
     ws = nb.seed_extend(fmi, gw, rs, nb.SeedExtendParams(), hit_capacity=1000, keep_hits=True)
-    kept, total = [int(v) for v in ws.n_hits.cpu()]
-    assert kept == 1000 and total > 1000
+    kept, total, jobs = [int(v) for v in ws.n_hits.cpu()]
+    assert kept == 1000 and total > 1000 and jobs <= kept

@@ -62,7 +62,7 @@ def test_fm_core(H, O, n):
         words = pack_symbols(q, bits, bool(be))
         got = np.zeros((nq, 2), np.uint32)
         H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(bits), C.c_uint32(be),
-                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got))
+                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), None, C.c_uint32(0))
         assert np.array_equal(got, want), (bits, be)
     # N rule on a 4-bit stream
     qn = q.copy(); qn[offs[5] + lens[5] - 1] = 4          # last symbol = first one consumed
@@ -70,20 +70,38 @@ def test_fm_core(H, O, n):
     got = np.zeros((nq, 2), np.uint32)
     words = pack_symbols(qn, 4, True)
     H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(4), C.c_uint32(1),
-                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got))
+                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), None, C.c_uint32(0))
     assert np.array_equal(got, want_n) and tuple(got[5]) == (1, 0)
     # forward-order + complement == backward search of the reverse complement
     rc = np.concatenate([(3 - q[o:o + l])[::-1] for o, l in zip(offs, lens)]).astype(np.uint8)
     want_rc, _ = O.match(idx, rc, offs, lens)
     words = pack_symbols(q, 2, True)
     H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
-                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(3), _p(got))
+                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(3), _p(got), None, C.c_uint32(0))
     assert np.array_equal(got, want_rc)
+    # k-mer table: identical ranges with the first k steps looked up (incl. empty ranges, N's, short queries)
+    for k in (1, 3, 6):
+        ktab = np.zeros(2 * 4 ** k, np.uint32)
+        H.hh_fm_build_ktab(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), C.c_uint32(k), _p(ktab))
+        for flags, w in ((0, want), (3, want_rc)):
+            H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
+                          _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(flags), _p(got), _p(ktab), C.c_uint32(k))
+            assert np.array_equal(got, w), (k, flags)
+        wn = pack_symbols(qn, 4, True)
+        H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(wn), C.c_uint32(4), C.c_uint32(1),
+                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), _p(ktab), C.c_uint32(k))
+        assert np.array_equal(got, want_n), k
     # locate
     rows = rng.integers(0, n + 1, 300).astype(np.uint32); rows[:3] = (0, idx.primary, n)
     out = np.zeros(300, np.uint32)
-    H.hh_fm_locate(_p(idx.bwt_occ), _p(idx.ssa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(rows), C.c_uint32(300), _p(out))
-    assert np.array_equal(out, O.locate(idx, rows))
+    H.hh_fm_locate(_p(idx.bwt_occ), _p(idx.ssa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(rows), C.c_uint32(300), _p(out), C.c_uint32(16))
+    want_pos = O.locate(idx, rows)
+    assert np.array_equal(out, want_pos)
+    # denser sampled SA (B200 extension): same positions with fewer LF steps; interval 1 = the full SA
+    for I in (1, 2, 8):
+        ssa = idx.sa[::I].astype(np.uint32).copy(); ssa[0] = 0xFFFFFFFF
+        H.hh_fm_locate(_p(idx.bwt_occ), _p(ssa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(rows), C.c_uint32(300), _p(out), C.c_uint32(I))
+        assert np.array_equal(out, want_pos), I
 
 
 def _gotoh_generic(H, band, typ, scheme6, pr, pbits, pbe, tbits, tbe, qual=None, qtab=None):

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""BASELINE TOOL (not product): run the reference's own CUDA kernels recompiled for sm_100a
+(oracle/_ref/ref_cuda_bench, built by oracle/Makefile from /root/reference) and the nvbio_b200 kernels on the
+SAME inputs, compare the results bit for bit, and print both throughputs.
+
+    python tools/compare_ref_cuda.py [--n 1000000] [--genome-mbp 100] [--seeds 1000000]
+
+Outputs one JSON line per path (banded Gotoh LOCAL band 31 on n x 150 bp vs 181 bp windows; FM-index exact
+match + locate of 22-mers)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nvbio_b200 as nb                      # noqa: E402
+from nvbio_b200 import aln, synth            # noqa: E402
+from nvbio_b200.strings import PackedStringSet  # noqa: E402
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_cuda_bench")
+
+
+def time_ms(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    best = 1e30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(reps):
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--genome-mbp", type=float, default=100.0)
+    ap.add_argument("--seeds", type=int, default=1_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    args = ap.parse_args()
+    if not os.path.exists(BIN):
+        print(json.dumps({"unavailable": "oracle/_ref/ref_cuda_bench not built"})); return
+    n_g = int(args.genome_mbp * 1e6)
+    gw = synth.random_genome_words(n_g)
+    fmi, _ = nb.FMIndexDevice.from_text(gw, n_g)
+    M, n = args.read_len, args.n
+
+    # ---------------- banded Gotoh ----------------
+    rw, pos, _ = synth.sample_reads(gw, n_g, n, M, rc_half=False)
+    begin = (pos - 15).clamp_(0)
+    end = (begin + M + 31).clamp_(max=n_g)
+    wpr = rw.shape[1]
+    P = PackedStringSet.fixed(rw.reshape(-1), n, M, stride=wpr * 16)
+    T = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=begin.to(torch.int32), lengths=(end - begin).to(torch.int32),
+                        stride=0, length=M + 31, count=n)
+    al = aln.make_gotoh_aligner(aln.LOCAL, aln.SimpleGotohScheme(2, -2, -5, -3))
+    out = (torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty((n, 2), dtype=torch.int32, device="cuda"))
+    temp = torch.empty(aln.banded_temp_bytes(31, al, P, T) + 256, dtype=torch.uint8, device="cuda")
+    ours_ms = time_ms(lambda: aln.batch_banded_alignment_score(31, al, P, T, out=out, temp=temp))
+    with tempfile.TemporaryDirectory() as d:
+        np.array([n, M, wpr * 16, 2, -2 & 0xFFFFFFFF, -5 & 0xFFFFFFFF, -3 & 0xFFFFFFFF, 3], dtype=np.uint32).tofile(d + "/meta.bin")
+        rw.cpu().numpy().tofile(d + "/pat_words.bin")
+        gw.cpu().numpy().tofile(d + "/genome_words.bin")
+        torch.stack([begin, end], dim=1).to(torch.int32).cpu().numpy().tofile(d + "/windows.bin")
+        r = subprocess.run([BIN, "banded", d], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(json.dumps({"error": r.stderr[-400:]})); return
+        ref = json.loads(r.stdout.strip().splitlines()[-1])
+        ref_scores = np.fromfile(d + "/ref_scores.bin", dtype=np.int32)
+        ref_sinks = np.fromfile(d + "/ref_sinks.bin", dtype=np.uint32).reshape(-1, 2)
+    same = bool(np.array_equal(out[0].cpu().numpy(), ref_scores) and np.array_equal(out[1].cpu().numpy().view(np.uint32), ref_sinks))
+    gcups = n * M * 31 / (ours_ms * 1e-3) / 1e9
+    print(json.dumps({"path": "banded Gotoh LOCAL band 31, %d x %d bp, (2,-2,-5,-3)" % (n, M), "nvbio_b200_ms": ours_ms, "nvbio_b200_gcups": gcups,
+                      "reference_cuda_sm100a_ms": ref["ms"], "reference_cuda_sm100a_gcups": ref["gcups"], "speedup": ref["ms"] / ours_ms,
+                      "bit_identical_scores_and_sinks": same}), flush=True)
+
+    # ---------------- FM-index ----------------
+    nq, L = args.seeds, 22
+    sw, spos = synth.sample_seeds(gw, n_g, nq, L)
+    q = PackedStringSet.fixed(sw.reshape(-1), nq, L, stride=32)
+    ranges = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+    ours_ms = time_ms(lambda: nb.match(fmi, q, out=ranges))
+    flt = nb.FMIndexFilterDevice()
+    n_hits = flt.rank(fmi, q)
+    hits = torch.empty((n_hits, 2), dtype=torch.int32, device="cuda")
+    loc_ms = time_ms(lambda: flt.locate(0, n_hits, hits))
+    with tempfile.TemporaryDirectory() as d:
+        meta = [fmi.length, fmi.primary] + list(fmi.L2) + [nq, L, 32, 3]
+        np.array(meta, dtype=np.uint32).tofile(d + "/meta.bin")
+        fmi.bwt_occ.cpu().numpy().tofile(d + "/bwt_occ.bin")
+        fmi.ssa.cpu().numpy().tofile(d + "/ssa.bin")
+        sw.cpu().numpy().tofile(d + "/seed_words.bin")
+        r = subprocess.run([BIN, "fm", d], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(json.dumps({"error": r.stderr[-400:]})); return
+        ref = json.loads(r.stdout.strip().splitlines()[-1])
+        ref_ranges = np.fromfile(d + "/ref_ranges.bin", dtype=np.uint32).reshape(-1, 2)
+        ref_hits = np.fromfile(d + "/ref_hits.bin", dtype=np.uint32).reshape(-1, 2)
+    same_r = bool(np.array_equal(ranges.cpu().numpy().view(np.uint32), ref_ranges))
+    same_h = bool(np.array_equal(hits.cpu().numpy().view(np.uint32)[:len(ref_hits)], ref_hits))
+    print(json.dumps({"path": "FM-index exact match, %d x %d bp seeds, %.0f Mbp genome" % (nq, L, n_g / 1e6), "nvbio_b200_match_ms": ours_ms,
+                      "nvbio_b200_mseeds_s": nq / (ours_ms * 1e-3) / 1e6, "reference_cuda_sm100a_rank_ms": ref["rank_ms"],
+                      "reference_cuda_sm100a_mseeds_s": ref["mseeds_per_s"], "speedup_match": ref["rank_ms"] / ours_ms,
+                      "nvbio_b200_locate_ms": loc_ms, "reference_cuda_sm100a_locate_ms": ref["locate_ms"], "n_hits": n_hits,
+                      "bit_identical_ranges": same_r, "bit_identical_hits": same_h}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
