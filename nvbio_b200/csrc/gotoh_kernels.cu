@@ -50,55 +50,57 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
 {
     extern __shared__ uint16_t sel_smem[];            // [sel_rows][PAIR_BLOCKDIM]
     const uint32_t n = batch_count(b);
-    const uint32_t pair = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x;
-    const uint32_t a0 = 2u * pair;
-    if (a0 >= n) return;
-    const bool has1 = (a0 + 1u < n);
-    const uint32_t a1 = has1 ? a0 + 1u : a0;          // an odd tail computes the same alignment in both halves
-
-    const uint32_t M0 = str_len(b.pat, a0), M1 = str_len(b.pat, a1);
-    const uint32_t N0 = str_len(b.txt, a0), N1 = str_len(b.txt, a1);
-    const uint32_t Mmax = M0 > M1 ? M0 : M1;
-    const uint32_t L = Mmax + (uint32_t)B - 1u;       // text columns touched
-
-    const bool ok = (M0 >= 1u) && (M1 >= 1u) && (N0 >= M0 + (uint32_t)B - 1u) && (N1 >= M1 + (uint32_t)B - 1u) &&
-                    (L <= sel_rows) && (TYPE == NVB_LOCAL || M0 == M1);
-    if (!ok) {
-        const uint32_t cnt = has1 ? 2u : 1u;
-        const uint32_t slot = atomicAdd(todo_count, cnt);
-        todo[slot] = a0;
-        if (has1) todo[slot + 1u] = a1;
-        return;
-    }
-
-    // stage the PRMT selectors of this thread's two text windows
+    const uint32_t n_pairs = (n + 1u) / 2u;
     uint16_t* my_sel = sel_smem + threadIdx.x;
-    {
-        const uint32_t t0 = str_off(b.txt, a0), t1 = str_off(b.txt, a1);
-        if (b.txt.big_endian) {
-            SymReader<2, true> r0(b.txt.words), r1(b.txt.words);
-            for (uint32_t t = 0; t < L; ++t) {
-                const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
-                const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
-                my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
-            }
-        } else {
-            SymReader<2, false> r0(b.txt.words), r1(b.txt.words);
-            for (uint32_t t = 0; t < L; ++t) {
-                const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
-                const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
-                my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+    // grid-stride over pairs: the batch size may only be known on the device, and a fixed resident grid avoids
+    // launching tens of thousands of empty CTAs when it is far below the capacity
+    for (uint32_t pair = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x; pair < n_pairs; pair += gridDim.x * PAIR_BLOCKDIM) {
+        const uint32_t a0 = 2u * pair;
+        const bool has1 = (a0 + 1u < n);
+        const uint32_t a1 = has1 ? a0 + 1u : a0;          // an odd tail computes the same alignment in both halves
+
+        const uint32_t M0 = str_len(b.pat, a0), M1 = str_len(b.pat, a1);
+        const uint32_t N0 = str_len(b.txt, a0), N1 = str_len(b.txt, a1);
+        const uint32_t Mmax = M0 > M1 ? M0 : M1;
+        const uint32_t L = Mmax + (uint32_t)B - 1u;       // text columns touched
+
+        const bool ok = (M0 >= 1u) && (M1 >= 1u) && (N0 >= M0 + (uint32_t)B - 1u) && (N1 >= M1 + (uint32_t)B - 1u) &&
+                        (L <= sel_rows) && (TYPE == NVB_LOCAL || M0 == M1);
+        if (!ok) {
+            const uint32_t cnt = has1 ? 2u : 1u;
+            const uint32_t slot = atomicAdd(todo_count, cnt);
+            todo[slot] = a0;
+            if (has1) todo[slot + 1u] = a1;
+            continue;
+        }
+
+        // stage the PRMT selectors of this thread's two text windows (own shared-memory column: no barrier needed)
+        {
+            const uint32_t t0 = str_off(b.txt, a0), t1 = str_off(b.txt, a1);
+            if (b.txt.big_endian) {
+                SymReader<2, true> r0(b.txt.words), r1(b.txt.words);
+                for (uint32_t t = 0; t < L; ++t) {
+                    const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
+                    const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
+                    my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+                }
+            } else {
+                SymReader<2, false> r0(b.txt.words), r1(b.txt.words);
+                for (uint32_t t = 0; t < L; ++t) {
+                    const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
+                    const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
+                    my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+                }
             }
         }
-    }
-    // each thread reads back only its own column: no barrier needed
 
-    SinkResult r0, r1;
-    gotoh_pair<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
-                        str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
-                        my_sel, PAIR_BLOCKDIM, r0, r1);
-    b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
-    if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
+        SinkResult r0, r1;
+        gotoh_pair<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
+                            str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
+                            my_sel, PAIR_BLOCKDIM, r0, r1);
+        b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
+        if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
+    }
 }
 
 template <int B, int TYPE>
@@ -124,7 +126,9 @@ static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_r
         attr_done = true;
     }
     const uint32_t pairs = (b.n_max + 1u) / 2u;
-    const uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
+    uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
+    const uint32_t resident = 148u * 4u * 16u;          // 16 waves of the 4 CTAs an SM holds: balanced tail, no empty CTAs
+    if (grid > resident) grid = resident;
     gotoh_pair_kernel<B, TYPE><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
@@ -170,7 +174,6 @@ static int banded_impl(int band, int type, const nvb_gotoh_scheme* scheme,
     if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
     if (!(band == 3 || band == 5 || band == 7 || band == 15 || band == 31 || band == 63)) return NVB_E_INVALID;
     if (type < 0 || type > 2) return NVB_E_INVALID;
-    if (n_max && (!d_score || !d_sink)) return NVB_E_INVALID;
 
     TempCarver tc(d_temp);
     uint32_t* todo_count = tc.take<uint32_t>(4);
@@ -178,6 +181,7 @@ static int banded_impl(int band, int type, const nvb_gotoh_scheme* scheme,
     const size_t need = tc.total();
     if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
     if (n_max == 0) return NVB_OK;
+    if (!d_score || !d_sink) return NVB_E_INVALID;
 
     cudaStream_t s = as_stream(stream);
     GotohBatch b;
