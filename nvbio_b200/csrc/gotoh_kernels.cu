@@ -52,9 +52,11 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
     const uint32_t n = batch_count(b);
     const uint32_t n_pairs = (n + 1u) / 2u;
     uint16_t* my_sel = sel_smem + threadIdx.x;
-    // grid-stride over pairs: the batch size may only be known on the device, and a fixed resident grid avoids
-    // launching tens of thousands of empty CTAs when it is far below the capacity
-    for (uint32_t pair = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x; pair < n_pairs; pair += gridDim.x * PAIR_BLOCKDIM) {
+    // one pair per thread (a grid-stride loop over a resident grid measured 5% slower: 108 vs 118 registers cost
+    // more than the empty CTAs of a device-side count save)
+    {
+        const uint32_t pair = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x;
+        if (pair >= n_pairs) return;
         const uint32_t a0 = 2u * pair;
         const bool has1 = (a0 + 1u < n);
         const uint32_t a1 = has1 ? a0 + 1u : a0;          // an odd tail computes the same alignment in both halves
@@ -71,7 +73,7 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
             const uint32_t slot = atomicAdd(todo_count, cnt);
             todo[slot] = a0;
             if (has1) todo[slot + 1u] = a1;
-            continue;
+            return;
         }
 
         // stage the PRMT selectors of this thread's two text windows (own shared-memory column: no barrier needed)
@@ -126,9 +128,7 @@ static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_r
         attr_done = true;
     }
     const uint32_t pairs = (b.n_max + 1u) / 2u;
-    uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
-    const uint32_t resident = 148u * 4u * 16u;          // 16 waves of the 4 CTAs an SM holds: balanced tail, no empty CTAs
-    if (grid > resident) grid = resident;
+    const uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
     gotoh_pair_kernel<B, TYPE><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
     NVB_LAUNCH_CHECK();
     return NVB_OK;

@@ -56,6 +56,50 @@ pipe_make_strings_kernel(const StrSet reads, const PipeGeom g, uint32_t* __restr
     out_words[t] = word;
 }
 
+// 2-bit fast path of the above: whole words at a time.  16 consecutive symbols starting at any symbol offset are a
+// funnel shift of two words; the reverse complement of a word is ~brev(word) with the two bits of every symbol
+// swapped back.
+__device__ __forceinline__ uint32_t load16_2bit_be(const uint32_t* __restrict__ words, uint32_t p /* symbol offset */, uint32_t cnt /* symbols needed */)
+{
+    const uint32_t w = p >> 4, sh = 2u * (p & 15u);
+    const uint32_t a = words[w];
+    if (sh == 0) return a;
+    const uint32_t b = ((p & 15u) + cnt > 16u) ? words[w + 1] : 0u;     // never touch a word the string does not reach
+    return (a << sh) | (b >> (32u - sh));
+}
+__device__ __forceinline__ uint32_t revcomp16_2bit(uint32_t x)
+{
+    uint32_t y = __brev(~x);                                  // symbols reversed, bits inside each symbol swapped
+    return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+__global__ void __launch_bounds__(256)
+pipe_make_strings_2bit_be_kernel(const StrSet reads, const PipeGeom g, uint32_t* __restrict__ out_words, uint32_t* __restrict__ out_len)
+{
+    const uint32_t words_per_string = g.stride / 16u;
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (uint64_t)g.n_strings * words_per_string) return;
+    const uint32_t s = (uint32_t)(t / words_per_string), w = (uint32_t)(t % words_per_string);
+    const uint32_t read = s / g.strands, strand = s % g.strands;
+    const uint32_t off = str_off(reads, read), len = str_len(reads, read);
+    if (w == 0) out_len[s] = len;
+    const uint32_t first = w * 16u;                           // first output symbol of this word
+    uint32_t word = 0;
+    if (first < len) {
+        const uint32_t cnt = (len - first) < 16u ? (len - first) : 16u;
+        if (strand == 0) {
+            word = load16_2bit_be(reads.words, off + first, cnt);
+        } else {
+            // output symbols first..first+cnt-1 are the complements of input symbols len-1-first .. len-first-cnt (descending)
+            const uint32_t lo = len - first - cnt;            // lowest input symbol needed
+            uint32_t x = load16_2bit_be(reads.words, off + lo, cnt);   // symbols lo .. lo+15 (only the first cnt matter)
+            x = revcomp16_2bit(x);                             // now symbol (lo+15-j) sits at position j
+            word = x << (2u * (16u - cnt));                    // drop the 16-cnt leading junk symbols
+        }
+        if (cnt < 16u) word &= ~(0xFFFFFFFFu >> (2u * cnt));   // zero the padding
+    }
+    out_words[t] = word;
+}
+
 // one thread per (string, seed slot): SA range of the seed, and its clamped size
 template <int BITS>
 __global__ void __launch_bounds__(256)
@@ -320,8 +364,9 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     {
         const uint64_t total_words = (uint64_t)g.n_strings * (g.stride / spw);
         const uint32_t grid = (uint32_t)((total_words + 255) / 256);
-        if (g.bits == 2) pipe_make_strings_kernel<2><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
-        else             pipe_make_strings_kernel<4><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
+        if (g.bits == 2 && rd.big_endian) pipe_make_strings_2bit_be_kernel<<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
+        else if (g.bits == 2)             pipe_make_strings_kernel<2><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
+        else                              pipe_make_strings_kernel<4><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(1);

@@ -87,3 +87,64 @@ def last_stage_ms():
     ms = (C.c_float * 7)()
     check(lib().nvb_seed_extend_stage_ms(ms), "nvb_seed_extend_stage_ms")
     return dict(zip(STAGES, [float(v) for v in ms]))
+
+
+class StreamingSeedExtend:
+    """Host-to-host batches: the production entry point (nvBowtie's input thread -> compute thread hand-off,
+    nvBowtie/bowtie2/cuda/compute_thread.cu:213-243, without the per-stage cudaDeviceSynchronize).
+
+    `submit(host_words)` enqueues H2D copy -> seed_extend -> D2H copy of (best_score, best_pos) on three streams
+    and returns a ticket; `result(ticket)` waits for that batch only.  With depth >= 2 the copies of one batch
+    overlap the kernels of its neighbours.  host_words must be a pinned int32 tensor [n_reads, words_per_read]."""
+
+    def __init__(self, fmi: FMIndexDevice, genome: torch.Tensor, params: SeedExtendParams, n_reads: int, read_len: int,
+                 words_per_read: int, hit_capacity: Optional[int] = None, depth: int = 2, bits: int = 2):
+        self.fmi, self.genome, self.params = fmi, genome, params
+        self.n_reads, self.read_len, self.wpr, self.bits = n_reads, read_len, words_per_read, bits
+        dev = fmi.device
+        self.h2d, self.compute, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        if hit_capacity is None:
+            hit_capacity = 32 * n_reads + 1024
+        self.slots = []
+        for _ in range(depth):
+            dev_in = torch.empty((n_reads, words_per_read), dtype=torch.int32, device=dev)
+            rs = self._as_set(dev_in)
+            ws = SeedExtendWorkspace(fmi, genome, rs, params, hit_capacity, keep_hits=False)
+            self.slots.append(dict(dev_in=dev_in, rs=rs, ws=ws,
+                                   host_score=torch.empty(n_reads, dtype=torch.int32).pin_memory(),
+                                   host_pos=torch.empty(n_reads, dtype=torch.int32).pin_memory(),
+                                   host_nhits=torch.empty(3, dtype=torch.int32).pin_memory(),
+                                   ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False))
+        self._next = 0
+
+    def _as_set(self, words):
+        spw = 32 // self.bits
+        return PackedStringSet.fixed(words.reshape(-1), self.n_reads, self.read_len, stride=self.wpr * spw, bits=self.bits)
+
+    def submit(self, host_words: torch.Tensor) -> int:
+        k = self._next % len(self.slots)
+        self._next += 1
+        s = self.slots[k]
+        if s["busy"]:
+            s["ev_out"].synchronize()           # the slot's previous results must have left the device
+        with torch.cuda.stream(self.h2d):
+            s["dev_in"].copy_(host_words, non_blocking=True)
+            s["ev_in"].record(self.h2d)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(s["ev_in"])
+            seed_extend(self.fmi, self.genome, s["rs"], self.params, workspace=s["ws"])
+            s["ev_done"].record(self.compute)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(s["ev_done"])
+            s["host_score"].copy_(s["ws"].best_score, non_blocking=True)
+            s["host_pos"].copy_(s["ws"].best_pos, non_blocking=True)
+            s["host_nhits"].copy_(s["ws"].n_hits, non_blocking=True)
+            s["ev_out"].record(self.d2h)
+        s["busy"] = True
+        return k
+
+    def result(self, ticket: int):
+        s = self.slots[ticket]
+        s["ev_out"].synchronize()
+        s["busy"] = False
+        return s["host_score"], s["host_pos"], s["host_nhits"]

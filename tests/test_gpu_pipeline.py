@@ -101,3 +101,45 @@ def test_hit_capacity_is_respected():
     ws = nb.seed_extend(fmi, gw, rs, nb.SeedExtendParams(), hit_capacity=1000, keep_hits=True)
     kept, total, jobs = [int(v) for v in ws.n_hits.cpu()]
     assert kept == 1000 and total > 1000 and jobs <= kept
+
+
+def test_unaligned_2bit_reads_and_streaming_api():
+    """2-bit reads of odd lengths packed back to back (offsets not word aligned) through the word-wise [fw,rc]
+    materialisation, and the host-to-host StreamingSeedExtend API against the plain call."""
+    require_gpu()
+    O = orc.Oracle()
+    n = 120_000
+    gw = synth.random_genome_words(n, seed=31)
+    gsym = unpack_symbols(host_u32(gw), n)
+    idx = O.build_index(gsym)
+    fmi = nb.FMIndexDevice.from_host(idx.bwt_occ, idx.ssa, idx.L2, idx.n, idx.primary)
+    rng = np.random.default_rng(12)
+    reads, offs, lens, o = [], [], [], 0
+    for i in range(400):
+        L = int(rng.integers(61, 151)); p = int(rng.integers(0, n - L))
+        r = gsym[p:p + L].copy()
+        if i & 1:
+            r = (3 - r)[::-1].copy()
+        reads.append(r); offs.append(o); lens.append(L); o += L
+    rs = PackedStringSet.from_symbols(np.concatenate(reads), offs, lens, bits=2, big_endian=True)
+    rs.length = 150
+    params = nb.SeedExtendParams(max_seed_hits=20)
+    ws = nb.seed_extend(fmi, gw, rs, params, hit_capacity=40000, keep_hits=True)
+    torch.cuda.synchronize()
+    want = seed_extend_oracle(O, idx, gsym, reads, params)
+    kept = int(ws.n_hits[0])
+    assert kept == want["n_hits"]
+    assert np.array_equal(ws.hit_score.cpu().numpy()[:kept].astype(np.int64), want["hit_score"])
+    assert np.array_equal(host_u32(ws.hit_window)[:kept].astype(np.int64), want["hit_window"])
+    assert np.array_equal(ws.best_score.cpu().numpy().astype(np.int64), want["best_score"])
+    # streaming API on fixed-length batches
+    rw, pos, strand = synth.sample_reads(gw, n, 1000, 150, seed=3, mut_seed=4)
+    plain = nb.seed_extend(fmi, gw, PackedStringSet.fixed(rw.reshape(-1), 1000, 150, stride=rw.shape[1] * 16), nb.SeedExtendParams(), hit_capacity=64000)
+    torch.cuda.synchronize()
+    st = nb.StreamingSeedExtend(fmi, gw, nb.SeedExtendParams(), 1000, 150, rw.shape[1], hit_capacity=64000, depth=2)
+    host = rw.cpu().pin_memory()
+    tickets = [st.submit(host) for _ in range(2)]
+    for t in tickets + [st.submit(host)]:
+        sc, ps, nh = st.result(t)
+        assert torch.equal(sc, plain.best_score.cpu()) and torch.equal(ps, plain.best_pos.cpu())
+        assert torch.equal(nh, plain.n_hits.cpu())
