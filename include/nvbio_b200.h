@@ -103,6 +103,11 @@ const char* nvb_error_string(int err);
 int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c, uint32_t n,
                 uint32_t* d_out, void* stream);
 
+/* d_out4[4*i + c] = rank(fmi, k[i], c) for c = A,C,G,T at once (16-byte aligned output).
+ * Replaces nvbio::rank4(fm_index,k) / rank_all (nvbio/fmindex/fmindex_inl.h:107-133,194-222 ->
+ * rank_dictionary_inl.h:539-573, the count-table popc_2bit_all path used by nvBowtie's 1-mismatch mapper). */
+int nvb_fm_rank4(const nvb_fm_index* fmi, const uint32_t* d_k, uint32_t n, uint32_t* d_out4, void* stream);
+
 #define NVB_MATCH_FORWARD_ORDER 1u  /* consume the query left-to-right instead of right-to-left   */
 #define NVB_MATCH_COMPLEMENT    2u  /* complement each symbol (c<4 ? 3-c : c) before ranking      */
 /* FORWARD_ORDER|COMPLEMENT is how nvBowtie searches the reverse-complement strand of a seed over the

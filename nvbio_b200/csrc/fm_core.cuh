@@ -128,6 +128,17 @@ __host__ __device__ __forceinline__ uint32_t fm_rank1(const FmIndex& f, uint32_t
     return block_rank(b, k & 63u, c);
 }
 
+// rank4(fmi, k): occurrences of all four symbols in rows [0,k]  (fmindex_inl.h:107-133 ->
+// rank_dictionary_inl.h:539-550 run4 with the count table; here four masked popcounts of the same block)
+__host__ __device__ __forceinline__ uint4 fm_rank4(const FmIndex& f, uint32_t k) {
+    if (k == 0xFFFFFFFFu) return make_uint4(0u, 0u, 0u, 0u);
+    if (k == f.n) return make_uint4(f.count(0), f.count(1), f.count(2), f.count(3));
+    if (k >= f.primary) --k;
+    const FmBlock b = load_block(f.blocks, k >> 6);
+    const uint32_t r = k & 63u;
+    return make_uint4(block_rank(b, r, 0), block_rank(b, r, 1), block_rank(b, r, 2), block_rank(b, r, 3));
+}
+
 // rank(fmi, (kx,ky), c)  (fmindex_inl.h:66-99 -> rank_dictionary_inl.h:512-538).  All of the
 // reference's case splits reduce to "each end is rank1 of that end"; the only thing worth keeping
 // is the shared block load when both ends fall in one 64-symbol block.

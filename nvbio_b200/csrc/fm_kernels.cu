@@ -20,6 +20,14 @@ fm_rank_kernel(const FmIndex f, const uint32_t* __restrict__ k, const uint8_t* _
     out[i] = fm_rank1(f, k[i], c[i] & 3u);
 }
 
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_rank4_kernel(const FmIndex f, const uint32_t* __restrict__ k, uint32_t n, uint4* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fm_rank4(f, k[i]);
+}
+
 template <int BITS, bool BE>
 __global__ void __launch_bounds__(FM_BLOCKDIM)
 fm_match_kernel(const FmIndex f, const StrSet q, uint32_t n, uint32_t flags, uint2* __restrict__ out)
@@ -177,6 +185,15 @@ int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c
     if (!valid_fmindex(fmi) || (n && (!d_k || !d_c || !d_out))) return NVB_E_INVALID;
     if (n == 0) return NVB_OK;
     fm_rank_kernel<<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), d_k, d_c, n, d_out);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_rank4(const nvb_fm_index* fmi, const uint32_t* d_k, uint32_t n, uint32_t* d_out4, void* stream)
+{
+    if (!valid_fmindex(fmi) || (n && (!d_k || !d_out4))) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    fm_rank4_kernel<<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, as_stream(stream)>>>(make_fmindex(fmi), d_k, n, (uint4*)d_out4);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
 }

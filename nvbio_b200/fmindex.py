@@ -128,6 +128,15 @@ def rank(fmi: FMIndexDevice, k: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rank4(fmi: FMIndexDevice, k: torch.Tensor) -> torch.Tensor:
+    """nvbio::rank4(fm_index, k): int32 [n,4] = occurrences of A,C,G,T in rows [0,k]"""
+    n = k.numel()
+    out = torch.empty((n, 4), dtype=torch.int32, device=k.device)
+    s = fmi.struct()
+    check(lib().nvb_fm_rank4(C.byref(s), C.c_void_p(k.data_ptr()), C.c_uint32(n), C.c_void_p(out.data_ptr()), _stream()), "nvb_fm_rank4")
+    return out
+
+
 def match(fmi: FMIndexDevice, queries: PackedStringSet, flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nvbio::match(fm_index, pattern, len) for a string set -> int32 [n,2] inclusive SA ranges (uint32 bits)"""
     n = queries.count

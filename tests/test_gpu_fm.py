@@ -38,6 +38,11 @@ def test_golden_fixtures(O):
         assert np.array_equal(host_u32(nb.locate(fmi, dev_u32(g[f"{name}_rows"]))), g[f"{name}_pos"]), name
         k, c = dev_u32(g[f"{name}_rank_k"]), torch.from_numpy(g[f"{name}_rank_c"]).cuda()
         assert np.array_equal(host_u32(nb.rank(fmi, k, c)), g[f"{name}_rank_out"]), name
+        # rank4 == the four single-symbol ranks (rank_test.cu:55-86 checks rank_all against running counts)
+        r4 = host_u32(nb.rank4(fmi, k))
+        for cc in range(4):
+            want4 = host_u32(nb.rank(fmi, k, torch.full_like(c, cc)))
+            assert np.array_equal(r4[:, cc], want4), (name, cc)
 
 
 @pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 1000, 50021, 300000])
