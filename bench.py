@@ -98,6 +98,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel, **cfg):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` captures (profiles/traffic.json), when
+    one exists for exactly this configuration; else None"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for e in json.load(open(p)):
+            if e["kernel"] == kernel and all(e.get(k) == v for k, v in cfg.items()):
+                return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -168,6 +181,13 @@ def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
     from oracle.cpu_pipeline import cpu_seed_extend
     from nvbio_b200 import synth
     E = orc.Ref() if orc.Ref.available() else orc.Oracle()
+    if E.kind == "reference":
+        # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
+        try:
+            n_thr = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n_thr = os.cpu_count() or 1
+        E.set_num_threads(n_thr)
     cores = E.num_threads() if E.kind == "reference" else 1
     host = fmi.to_host()
     # the reference's index format samples the SA every 16 rows (SA_INT): slice the device index's denser array
@@ -423,7 +443,8 @@ def run_ours(args):
         "gpu_launches": (12 if params.dedup_jobs else 8) * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
-                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": measured_traffic("pipe_seed_match_kernel", ktab_k=args.ktab_k, genome_bp=n, reads=n_reads),
                      "peak_source": peak_src, "ms_per_launch": fm_ms,
                      "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": tail_blocks,
                      "reference_algorithm_bytes_per_seed": ref_bytes_per_seed, "reference_algorithm_blocks_per_seed": blocks_per_seed,

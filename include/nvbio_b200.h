@@ -88,6 +88,8 @@ typedef struct nvb_gotoh_scheme {
     int32_t        pattern_gap_open, pattern_gap_ext;
     int32_t        text_gap_open, text_gap_ext;
     const int32_t* d_qual_table;     /* device, 512 int32, or NULL */
+    int32_t        qual_table_min;   /* bounds of the table's values (host knowledge of device data): they admit the */
+    int32_t        qual_table_max;   /* packed 16-bit DPX path; 0,0 = unknown -> the int32 kernel scores the batch   */
 } nvb_gotoh_scheme;
 
 int         nvb_version(void);

@@ -74,7 +74,7 @@ enum AlignmentType { GLOBAL = NVB_GLOBAL, LOCAL = NVB_LOCAL, SEMI_GLOBAL = NVB_S
 struct SimpleGotohScheme {
     SimpleGotohScheme(int32_t match, int32_t mm, int32_t gap_open, int32_t gap_ext) : m_match(match), m_mismatch(mm), m_gap_open(gap_open), m_gap_ext(gap_ext) {}
     int32_t m_match, m_mismatch, m_gap_open, m_gap_ext;
-    nvb_gotoh_scheme abi() const { nvb_gotoh_scheme s = { m_match, m_mismatch, m_gap_open, m_gap_ext, m_gap_open, m_gap_ext, nullptr }; return s; }
+    nvb_gotoh_scheme abi() const { nvb_gotoh_scheme s = { m_match, m_mismatch, m_gap_open, m_gap_ext, m_gap_open, m_gap_ext, nullptr, 0, 0 }; return s; }
 };
 template <AlignmentType TYPE, typename scheme_type> struct GotohAligner { scheme_type scheme; };
 template <AlignmentType TYPE, typename scheme_type>

@@ -33,7 +33,7 @@ class StringSetStruct(C.Structure):        # nvb_string_set
 class GotohSchemeStruct(C.Structure):      # nvb_gotoh_scheme
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("pattern_gap_open", C.c_int32),
                 ("pattern_gap_ext", C.c_int32), ("text_gap_open", C.c_int32), ("text_gap_ext", C.c_int32),
-                ("d_qual_table", C.c_void_p)]
+                ("d_qual_table", C.c_void_p), ("qual_table_min", C.c_int32), ("qual_table_max", C.c_int32)]
 
 
 class SeedExtendParamsStruct(C.Structure):  # nvb_seed_extend_params

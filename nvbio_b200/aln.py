@@ -25,6 +25,7 @@ class SimpleGotohScheme:
         s.pattern_gap_open = s.text_gap_open = self.gap_open
         s.pattern_gap_ext = s.text_gap_ext = self.gap_ext
         s.d_qual_table = None
+        s.qual_table_min = s.qual_table_max = 0
         return s
 
 
@@ -52,6 +53,7 @@ class QualityGotohScheme:
         s.pattern_gap_open, s.pattern_gap_ext = self.pgo, self.pge
         s.text_gap_open, s.text_gap_ext = self.tgo, self.tge
         s.d_qual_table = self.table.data_ptr()
+        s.qual_table_min, s.qual_table_max = int(self.table_host.min()), int(self.table_host.max())
         return s
 
 

@@ -165,21 +165,25 @@ __host__ __device__ __forceinline__ uint32_t sub_profile(uint32_t q, int32_t s_e
 // host-side admissibility of the packed path for a batch (max pattern length max_m)
 static inline bool pair_path_ok(int B, int type, const nvb_gotoh_scheme* s, uint32_t max_m) {
     if (!(B == 7 || B == 15 || B == 31)) return false;
-    if (s->d_qual_table) return false;                      // quality tables go through the generic path
     const int64_t Go = s->pattern_gap_open, Ge = s->pattern_gap_ext;
     if (Go >= 0 || Ge >= 0 || s->text_gap_open >= 0 || s->text_gap_ext >= 0) return false;
-    const int64_t a_m = s->match < 0 ? -(int64_t)s->match : s->match, a_x = s->mismatch < 0 ? -(int64_t)s->mismatch : s->mismatch;
+    // value range of the substitution scores: the two constants, or the caller's bounds on the quality table
+    int64_t s_lo = s->match < s->mismatch ? s->match : s->mismatch, s_hi = s->match > s->mismatch ? s->match : s->mismatch;
+    if (s->d_qual_table) {
+        if (s->qual_table_min == 0 && s->qual_table_max == 0) return false;   // bounds unknown: generic path
+        s_lo = s->qual_table_min; s_hi = s->qual_table_max;
+    }
+    const int64_t a_m = s_lo < 0 ? -s_lo : s_lo, a_x = s_hi < 0 ? -s_hi : s_hi;
     const int64_t max_s = a_m > a_x ? a_m : a_x;
     int64_t max_g = -Go; if (-Ge > max_g) max_g = -Ge; if (-(int64_t)s->text_gap_open > max_g) max_g = -(int64_t)s->text_gap_open;
     if (-(int64_t)s->text_gap_ext > max_g) max_g = -(int64_t)s->text_gap_ext;
     const int64_t bound = (int64_t)max_m * max_s + (int64_t)(B + 2) * max_g + max_g;
     if (bound > 30000) return false;
     // substitution bytes (S - Go) must fit int8
-    const int64_t c_eq = (int64_t)s->match - Go, c_ne = (int64_t)s->mismatch - Go;
-    if (c_eq < -128 || c_eq > 127 || c_ne < -128 || c_ne > 127) return false;
+    if (s_lo - Go < -128 || s_hi - Go > 127) return false;
     if (type == NVB_LOCAL) {
         // LOCAL cells are packed as (h << 5) | j in 16 bits
-        const int64_t top = (int64_t)max_m * (s->match > 0 ? s->match : 0);
+        const int64_t top = (int64_t)max_m * (s_hi > 0 ? s_hi : 0);
         if (top >= 2048) return false;
     }
     return true;
@@ -220,7 +224,8 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         uint32_t poff0, uint32_t M0, uint32_t poff1, uint32_t M1,
         uint32_t N0, uint32_t N1,
         const uint16_t* sel, uint32_t sel_stride,
-        SinkResult& r0, SinkResult& r1)
+        SinkResult& r0, SinkResult& r1,
+        const uint8_t* __restrict__ quals = nullptr)
 {
     const int32_t Go = S.pgo, Ge = S.pge;
     const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
@@ -230,6 +235,20 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
     if (INF + Ge < -32768) INF = -32768 - Ge;
     const uint32_t INF2 = pack16(INF, INF);
     const int32_t c_eq = S.match - Go, c_ne = S.mismatch - Go;       // substitution minus Go (G = H + Go is stored)
+    // per-row substitution profile of both alignments; with a quality table the two scores of a row come from
+    // table[2*qual], table[2*qual+1] (nvBowtie's SmithWatermanScoringScheme::substitution)
+#define NVB_ROW_PROFILES(i)                                                                                   \
+    const uint32_t q0 = ((i) < M0) ? pr0.get(poff0 + (i)) : 255u;                                             \
+    const uint32_t q1 = ((i) < M1) ? pr1.get(poff1 + (i)) : 255u;                                             \
+    int32_t e0 = c_eq, n0 = c_ne, e1 = c_eq, n1 = c_ne;                                                        \
+    if (S.qtab) {                                                                                             \
+        const uint32_t qq0 = (quals && (i) < M0) ? quals[poff0 + (i)] : 0u;                                   \
+        const uint32_t qq1 = (quals && (i) < M1) ? quals[poff1 + (i)] : 0u;                                   \
+        e0 = S.qtab[2 * qq0] - Go; n0 = S.qtab[2 * qq0 + 1] - Go;                                             \
+        e1 = S.qtab[2 * qq1] - Go; n1 = S.qtab[2 * qq1 + 1] - Go;                                             \
+    }                                                                                                         \
+    const uint32_t P0 = sub_profile(q0, e0, n0);                                                              \
+    const uint32_t P1 = sub_profile(q1, e1, n1);
 
     uint32_t G[B], F[B - 1];
     {
@@ -261,10 +280,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
 #pragma unroll
         for (int j = 0; j < B - 1; ++j) F[j] = INFb2;
         for (uint32_t i = 0; i < Mmax; ++i) {
-            const uint32_t q0 = (i < M0) ? pr0.get(poff0 + i) : 255u;
-            const uint32_t q1 = (i < M1) ? pr1.get(poff1 + i) : 255u;
-            const uint32_t P0 = sub_profile(q0, c_eq, c_ne);
-            const uint32_t P1 = sub_profile(q1, c_eq, c_ne);
+            NVB_ROW_PROFILES(i)
             const uint16_t* srow = sel + (size_t)i * sel_stride;
             uint32_t E = 0, rowkey = 0;
 #pragma unroll
@@ -291,10 +307,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         }
     } else {
         for (uint32_t i = 0; i < Mmax; ++i) {
-            const uint32_t q0 = (i < M0) ? pr0.get(poff0 + i) : 255u;
-            const uint32_t q1 = (i < M1) ? pr1.get(poff1 + i) : 255u;
-            const uint32_t P0 = sub_profile(q0, c_eq, c_ne);
-            const uint32_t P1 = sub_profile(q1, c_eq, c_ne);
+            NVB_ROW_PROFILES(i)
             const uint16_t* srow = sel + (size_t)i * sel_stride;
             uint32_t E = 0;
 #pragma unroll
@@ -316,6 +329,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         }
     }
 
+#undef NVB_ROW_PROFILES
     if (TYPE == NVB_LOCAL) {
         r0.score = best0; r0.x = bi0 + bj0 + 1u; r0.y = bi0 + 1u;
         r1.score = best1; r1.x = bi1 + bj1 + 1u; r1.y = bi1 + 1u;

@@ -99,7 +99,7 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
         SinkResult r0, r1;
         gotoh_pair<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
                             str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
-                            my_sel, PAIR_BLOCKDIM, r0, r1);
+                            my_sel, PAIR_BLOCKDIM, r0, r1, b.quals);
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
         if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
     }

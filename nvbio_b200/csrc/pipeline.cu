@@ -137,30 +137,35 @@ __global__ void pipe_count_kernel(const uint32_t* __restrict__ excl, const uint3
     }
 }
 
-// one thread per hit: locate the SA row, derive the genome window and the alignment job
+// one thread per QUERY (most seeds have 0 or 1 hits): locate each of its SA rows, derive the genome window and the
+// alignment job.  Hit h = excl[q] + j keeps the reference's slot order (filter_inl.h:99-118) without a binary search.
 __global__ void __launch_bounds__(256)
-pipe_expand_hits_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict__ ranges, const uint32_t* __restrict__ excl,
-                        const uint32_t* __restrict__ slen, const uint32_t* __restrict__ counts,
+pipe_expand_hits_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict__ ranges, const uint32_t* __restrict__ sizes,
+                        const uint32_t* __restrict__ excl, const uint32_t* __restrict__ slen, const uint32_t* __restrict__ counts,
                         uint32_t* __restrict__ hit_string, uint32_t* __restrict__ p_off, uint32_t* __restrict__ p_len,
                         uint32_t* __restrict__ t_off, uint32_t* __restrict__ t_len)
 {
-    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
-    if (h >= counts[0]) return;
-    const uint32_t nq = g.n_strings * g.seeds_per_string;
-    const uint32_t q = upper_bound_u32(excl, nq, h) - 1u;          // last query whose exclusive offset <= h
-    const uint32_t local = h - excl[q];
-    const uint32_t row = ranges[q].x + local;
-    const uint32_t pos = fm_locate_one(f, row);
+    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= g.n_strings * g.seeds_per_string) return;
+    const uint32_t sz = sizes[q];
+    if (sz == 0) return;
+    const uint32_t base = excl[q], kept = counts[0];
+    const uint32_t x = ranges[q].x;
     const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
     const uint32_t seed_begin = k * g.seed_interval;
     const uint32_t len = slen[s];
-    const uint32_t diag = pos > seed_begin ? pos - seed_begin : 0u;               // text position of read offset 0
-    const uint32_t gb = diag > g.band / 2u ? diag - g.band / 2u : 0u;             // fmmap.cu:198-199
-    const uint64_t ge64 = (uint64_t)gb + len + g.band;
-    const uint32_t ge = ge64 < g.genome_len ? (uint32_t)ge64 : g.genome_len;
-    hit_string[h] = s;
-    p_off[h] = s * g.stride; p_len[h] = len;
-    t_off[h] = gb;           t_len[h] = ge - gb;
+    for (uint32_t j = 0; j < sz; ++j) {
+        const uint32_t h = base + j;
+        if (h >= kept) break;                                                      // beyond the caller's capacity
+        const uint32_t pos = fm_locate_one(f, x + j);
+        const uint32_t diag = pos > seed_begin ? pos - seed_begin : 0u;               // text position of read offset 0
+        const uint32_t gb = diag > g.band / 2u ? diag - g.band / 2u : 0u;             // fmmap.cu:198-199
+        const uint64_t ge64 = (uint64_t)gb + len + g.band;
+        const uint32_t ge = ge64 < g.genome_len ? (uint32_t)ge64 : g.genome_len;
+        hit_string[h] = s;
+        p_off[h] = s * g.stride; p_len[h] = len;
+        t_off[h] = gb;           t_len[h] = ge - gb;
+    }
 }
 
 // Hits of one string are contiguous (queries are ordered by string, then seed).  Several seeds of a read usually
@@ -386,7 +391,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     // 4. locate + windows
     const uint32_t hgrid = (hit_capacity + 255) / 256;
     if (hit_capacity) {
-        pipe_expand_hits_kernel<<<hgrid, 256, 0, s>>>(f, g, ranges, excl, str_len_, counts, hit_string, p_off, p_len, t_off, t_len);
+        pipe_expand_hits_kernel<<<(nq + 255) / 256, 256, 0, s>>>(f, g, ranges, sizes, excl, str_len_, counts, hit_string, p_off, p_len, t_off, t_len);
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(4);

@@ -74,7 +74,7 @@ static void run_generic(const GotohScheme& S, const uint32_t* pw, uint32_t pbits
 
 // mirrors gotoh_pair_kernel: precondition check -> packed pair routine, else generic
 template <int B, int TYPE>
-static void run_pair(const GotohScheme& S, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+static void run_pair(const GotohScheme& S, const uint8_t* quals, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                      const uint32_t* tw, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
                      uint32_t n, uint32_t sel_rows, int32_t* score, uint32_t* sx, uint32_t* sy, uint32_t* n_fallback) {
     std::vector<uint16_t> sel(sel_rows + 1);
@@ -86,7 +86,7 @@ static void run_pair(const GotohScheme& S, const uint32_t* pw, uint32_t pbits, u
         const bool ok = M0 >= 1 && M1 >= 1 && N0 >= M0 + B - 1 && N1 >= M1 + B - 1 && L <= sel_rows && (TYPE == NVB_LOCAL || M0 == M1);
         if (!ok) {
             for (uint32_t a = a0; a <= a1; ++a) {
-                const SinkResult r = gotoh_generic<B, TYPE>(S, pw, pbits, pbe, poff[a], plen[a], nullptr, tw, 2, tbe, toff[a], tlen[a]);
+                const SinkResult r = gotoh_generic<B, TYPE>(S, pw, pbits, pbe, poff[a], plen[a], quals, tw, 2, tbe, toff[a], tlen[a]);
                 score[a] = r.score; sx[a] = r.x; sy[a] = r.y; ++*n_fallback;
             }
             continue;
@@ -97,7 +97,7 @@ static void run_pair(const GotohScheme& S, const uint32_t* pw, uint32_t pbits, u
             sel[t] = (uint16_t)pair_selector(g0, g1);
         }
         SinkResult q0, q1;
-        gotoh_pair<B, TYPE>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1);
+        gotoh_pair<B, TYPE>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
         score[a0] = q0.score; sx[a0] = q0.x; sy[a0] = q0.y;
         if (has1) { score[a1] = q1.score; sx[a1] = q1.x; sy[a1] = q1.y; }
     }
@@ -125,20 +125,22 @@ int hh_gotoh_generic(int band, int type, const int32_t* scheme6, const int32_t* 
 }
 
 // returns -2 when the scheme is not admissible for the packed path
-int hh_gotoh_pair(int band, int type, const int32_t* scheme6, uint32_t max_m,
+int hh_gotoh_pair(int band, int type, const int32_t* scheme6, const int32_t* qtab, const uint8_t* quals, uint32_t max_m,
                   const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                   const uint32_t* tw, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
                   uint32_t n, int32_t* score, uint32_t* sx, uint32_t* sy, uint32_t* n_fallback) {
-    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr; S.one = 1u; S.keymul = 32u;
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab; S.one = 1u; S.keymul = 32u;
     nvb_gotoh_scheme cs; cs.match = S.match; cs.mismatch = S.mismatch; cs.pattern_gap_open = S.pgo; cs.pattern_gap_ext = S.pge;
-    cs.text_gap_open = S.tgo; cs.text_gap_ext = S.tge; cs.d_qual_table = nullptr;
+    cs.text_gap_open = S.tgo; cs.text_gap_ext = S.tge; cs.d_qual_table = qtab; cs.qual_table_min = cs.qual_table_max = 0;
+    if (qtab) { int32_t lo = qtab[0], hi = qtab[0]; for (int i = 0; i < 512; ++i) { lo = qtab[i] < lo ? qtab[i] : lo; hi = qtab[i] > hi ? qtab[i] : hi; }
+                cs.qual_table_min = lo; cs.qual_table_max = hi; }
     if (!pair_path_ok(band, type, &cs, max_m)) return -2;
     const uint32_t sel_rows = max_m + band - 1;
     *n_fallback = 0;
     switch (band) {
-    case 7:  TYPE_SWITCH(7,  run_pair, S, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
-    case 15: TYPE_SWITCH(15, run_pair, S, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
-    case 31: TYPE_SWITCH(31, run_pair, S, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
+    case 7:  TYPE_SWITCH(7,  run_pair, S, quals, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
+    case 15: TYPE_SWITCH(15, run_pair, S, quals, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
+    case 31: TYPE_SWITCH(31, run_pair, S, quals, pw, pbits, pbe, poff, plen, tw, tbe, toff, tlen, n, sel_rows, score, sx, sy, n_fallback)
     }
     return -1;
 }

@@ -112,6 +112,48 @@ def test_quality_table_scheme(O):
     for typ in (1, 2):
         want = O.banded_gotoh(31, typ, (2, int(sch.table_host[0, 1]), sch.pgo, sch.pge, sch.tgo, sch.tge), *pr, qual=qual, qtab=sch.table_host)
         assert same(run(31, typ, sch, pr, pbits=4, tbits=8, quals=qual), want)
+    # nvBowtie-shaped jobs (2-bit genome windows, 4-bit reads): the packed DPX path builds its per-row profiles from the table
+    for band in (15, 31):
+        for typ in (1, 2):
+            pr2 = fixed_problems(rng, 2001, band, 150, ragged=(typ == 1))
+            qual2 = rng.integers(0, 60, len(pr2[0])).astype(np.uint8)
+            want = O.banded_gotoh(band, typ, (2, int(sch.table_host[0, 1]), sch.pgo, sch.pge, sch.tgo, sch.tge), *pr2, qual=qual2, qtab=sch.table_host)
+            force_path(0)
+            assert same(run(band, typ, sch, pr2, pbits=4, tbits=2, tbe=True, quals=qual2, max_m=150), want), (band, typ)
+            force_path(1)
+            try:
+                assert same(run(band, typ, sch, pr2, pbits=4, tbits=2, tbe=True, quals=qual2, max_m=150), want)
+            finally:
+                force_path(0)
+
+
+def test_c1_sw_benchmark_banded(O):
+    """BASELINE.json configs[0], banded variant: 10K x 100 bp patterns sampled from a 1 Kbp reference
+    with 2% substitutions + 0.5% indels, BAND_LEN 15, GLOBAL, SimpleGotohScheme(2,-1,-2,-1) (sw-benchmark.cu:594-598),
+    each against its 114 bp true window"""
+    rng = np.random.default_rng(2024)
+    ref = rng.integers(0, 4, 1000).astype(np.uint8)
+    pats, p_off, p_len, t_off, t_len = [], [], [], [], []
+    po = 0
+    for _ in range(10000):
+        st = int(rng.integers(0, 1000 - 114))
+        j, p = st, []
+        while len(p) < 100:
+            r = rng.random()
+            if r < 0.0025:
+                p.append(int(rng.integers(0, 4)))            # insertion
+            elif r < 0.005:
+                j += 1                                        # deletion
+            elif r < 0.025:
+                p.append(int((ref[min(j, 999)] + 1 + rng.integers(0, 3)) % 4)); j += 1
+            else:
+                p.append(int(ref[min(j, 999)])); j += 1
+        pats.append(np.array(p, np.uint8)); p_off.append(po); p_len.append(100); po += 100
+        t_off.append(st); t_len.append(114)
+    pr = (np.concatenate(pats), np.array(p_off, np.uint32), np.array(p_len, np.uint32), ref, np.array(t_off, np.uint32), np.array(t_len, np.uint32))
+    for typ in (0, 2, 1):
+        want = O.banded_gotoh(15, typ, (2, -1, -2, -1), *pr)
+        assert same(run(15, typ, (2, -1, -2, -1), pr, pbits=4, tbits=2, tbe=False, max_m=100), want), typ
 
 
 def test_scores_out_of_int16_budget_use_int32(O):

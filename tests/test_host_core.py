@@ -178,14 +178,14 @@ def fixed_problems(rng, n, band, m, extra_text=0, ragged=False):
             np.concatenate(txts), np.array(t_off, np.uint32), np.array(t_len, np.uint32))
 
 
-def _gotoh_pair(H, band, typ, scheme6, pr, max_m, pbits=2, pbe=1, tbe=1):
+def _gotoh_pair(H, band, typ, scheme6, pr, max_m, pbits=2, pbe=1, tbe=1, qtab=None, qual=None):
     pat, p_off, p_len, txt, t_off, t_len = pr
     pw, tw = pack_symbols(pat, pbits, bool(pbe)), pack_symbols(txt, 2, bool(tbe))
     n = len(p_off)
     score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
     nf = C.c_uint32(0)
     s6 = np.array(scheme6, np.int32)
-    r = H.hh_gotoh_pair(C.c_int(band), C.c_int(typ), _p(s6), C.c_uint32(max_m), _p(pw), C.c_uint32(pbits), C.c_uint32(pbe), _p(u32(p_off)), _p(u32(p_len)),
+    r = H.hh_gotoh_pair(C.c_int(band), C.c_int(typ), _p(s6), _p(qtab), _p(qual), C.c_uint32(max_m), _p(pw), C.c_uint32(pbits), C.c_uint32(pbe), _p(u32(p_off)), _p(u32(p_len)),
                         _p(tw), C.c_uint32(tbe), _p(u32(t_off)), _p(u32(t_len)), C.c_uint32(n), _p(score), _p(sx), _p(sy), C.byref(nf))
     return r, (score, sx, sy), nf.value
 
@@ -233,3 +233,23 @@ def test_pair_path_admission(H):
     assert r == -2
     r, _, _ = _gotoh_pair(H, 31, 2, (2, -2, -200, -3, -200, -3), pr, 150)      # S - Go does not fit int8
     assert r == -2
+
+
+def test_gotoh_pair_quality_table(H, O):
+    """nvBowtie's quality-dependent substitution through the packed path (per-row profiles from the table)"""
+    rng = np.random.default_rng(21)
+    q = np.arange(256)
+    frac = (np.minimum(q, 40).astype(np.float32) / np.float32(40.0))
+    mmp = 2 + (frac * np.float32(6 - 2)).astype(np.int32)
+    qtab = np.ascontiguousarray(np.stack([np.full(256, 2, np.int32), -mmp.astype(np.int32)], axis=1))
+    s6 = (2, -6, -8, -3, -8, -3)
+    for band in (15, 31):
+        for typ in (1, 2):
+            for ragged in (False, True):
+                pr = fixed_problems(rng, 41, band, 150, ragged=ragged)
+                qual = rng.integers(0, 60, len(pr[0])).astype(np.uint8)
+                want = O.banded_gotoh(band, typ, s6, *pr, qual=qual, qtab=qtab)
+                r, got, nf = _gotoh_pair(H, band, typ, s6, pr, 150, pbits=4, qtab=qtab, qual=qual)
+                assert r == 0 and (ragged or nf == 0)
+                for a, b in zip(got, want[:3]):
+                    assert np.array_equal(a, b), (band, typ, ragged)
