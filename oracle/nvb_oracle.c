@@ -382,3 +382,124 @@ void orc_banded_gotoh(int B, int type, const orc_scheme* S, const i32* qtab,
         if (ok) ok[i] = (u8)r;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * banded Gotoh traceback (nvbio/alignment/banded_inl.h:352-489 driver; direction vectors as produced by
+ * gotoh_banded_inl.h:463-620 and stored by GotohSubmatrixContext::new_cell :325-337; state machine
+ * gotoh_banded_inl.h:893-958).  The reference recomputes 32-row windows between checkpoints; walking one
+ * full M x B direction matrix visits the same cells with the same bits.
+ * ops: the backtracer's pushes in END -> START order (0 SUBSTITUTION 'M', 1 INSERTION 'I', 2 DELETION 'D');
+ * clips = (M - sink.y, source.y).  Returns the number of ops (may exceed max_ops: then truncated).
+ * ---------------------------------------------------------------------------------------------- */
+enum { D_SUB = 0, D_INS = 1, D_DEL = 2, D_SINK = 3, D_INS_EXT = 4, D_DEL_EXT = 8 };
+
+u32 orc_banded_traceback_one(int B, int type, const orc_scheme* S,
+                             const u8* P, u32 M, const u8* T, u32 N,
+                             i32* out_score, u32* sink_xy, u32* source_xy, u8* ops, u32 max_ops, u32* clips)
+{
+    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    *out_score = best; sink_xy[0] = sink_xy[1] = source_xy[0] = source_xy[1] = 0xFFFFFFFFu; clips[0] = clips[1] = 0;
+    if (N < M) return 0;
+    const int packed_cache = !(B == 3 || B == 5 || B == 7 || B == 15);
+    const i32 Go = S->pattern_gap_open, Ge = S->pattern_gap_ext;
+    const i32 INF = SHRT_MIN - imax(imax(Go, Ge), imax(S->text_gap_open, S->text_gap_ext));
+    i32 H[ORC_MAX_BAND], F[ORC_MAX_BAND]; u32 cache[ORC_MAX_BAND];
+    u8* dir = (u8*)malloc((size_t)(M ? M : 1) * (size_t)B);
+    H[0] = 0;
+    for (int j = 1; j < B; ++j) H[j] = (type == 0) ? S->text_gap_open + (j - 1) * S->text_gap_ext : 0;
+    for (int j = 0; j < B; ++j) F[j] = INF;
+    for (int j = 0; j < B - 1; ++j) { const u32 g = ((u32)j < N) ? T[j] : 255u; cache[j] = packed_cache ? (g & 3u) : g; }
+#define SUB(g, q) (((u8)(g) == (q)) ? S->match : S->mismatch)
+    for (u32 i = 0; i < M; ++i)
+    {
+        const u8 q = P[i];
+        u8 edir = D_SUB;
+        {   /* j = 0 */
+            const i32 ftop = F[1] + Ge, htop = H[1] + Go;
+            F[0] = imax(ftop, htop);
+            const u8 fdir = ftop > htop ? D_DEL_EXT : D_SUB;
+            const i32 diagonal = H[0] + SUB(cache[0], q), top = F[0];
+            i32 hi = imax(top, diagonal);
+            u8 hdir = top > diagonal ? D_INS : D_SUB;
+            if (type == 1) { hi = imax(hi, 0); if (hi == 0) hdir = D_SINK; sink_report(&best, &bx, &by, hi, i + 1, i + 1); }
+            H[0] = hi;
+            dir[(size_t)i * B] = (u8)(hdir | D_SUB | fdir);
+        }
+        i32 E = H[0] + Go;
+        for (int j = 1; j < B - 1; ++j)
+        {
+            const i32 ftop = F[j + 1] + Ge, htop = H[j + 1] + Go;
+            F[j] = imax(ftop, htop);
+            const u8 fdir = ftop > htop ? D_DEL_EXT : D_SUB;
+            const u32 g = cache[j]; cache[j - 1] = g;
+            const i32 diagonal = H[j] + SUB(g, q), top = F[j], left = E;
+            i32 hi = imax(imax(top, left), diagonal);
+            u8 hdir = top > left ? (top > diagonal ? D_INS : D_SUB) : (left > diagonal ? D_DEL : D_SUB);
+            if (type == 1) { hi = imax(hi, 0); if (hi == 0) hdir = D_SINK; sink_report(&best, &bx, &by, hi, i + (u32)j + 1, i + 1); }
+            H[j] = hi;
+            dir[(size_t)i * B + j] = (u8)(hdir | edir | fdir);
+            const i32 eleft = E + Ge, ediagonal = hi + Go;
+            edir = eleft > ediagonal ? D_INS_EXT : D_SUB;
+            E = imax(ediagonal, eleft);
+        }
+        const u8 g = (i + (u32)B - 1 < N) ? T[i + B - 1] : 255u;
+        cache[B - 2] = packed_cache ? (g & 3u) : g;
+        {   /* j = B-1 */
+            F[B - 1] = INF;
+            const i32 diagonal = H[B - 1] + SUB(g, q), left = E;
+            i32 hi = imax(left, diagonal);
+            u8 hdir = left > diagonal ? D_DEL : D_SUB;
+            if (type == 1) { hi = imax(hi, 0); if (hi == 0) hdir = D_SINK; sink_report(&best, &bx, &by, hi, i + (u32)B, i + 1); }
+            H[B - 1] = hi;
+            dir[(size_t)i * B + B - 1] = (u8)(hdir | edir | D_SUB);
+        }
+    }
+#undef SUB
+    if (type == 0) sink_report(&best, &bx, &by, H[B - 1], M + (u32)B - 1, M);
+    else if (type == 2)
+    {
+        const u32 lim = (M + (u32)B - 1 < N ? M + (u32)B - 1 : N) - (M - 1);
+        sink_report(&best, &bx, &by, H[0], M, M);
+        for (int j = 1; j < B; ++j) if ((u32)j < lim) sink_report(&best, &bx, &by, H[j], M + (u32)j, M);
+    }
+    *out_score = best;
+    u32 n_ops = 0;
+    if (bx != 0xFFFFFFFFu && by != 0xFFFFFFFFu)
+    {
+        sink_xy[0] = bx; sink_xy[1] = by;
+        clips[0] = M - by;
+        i32 entry = (i32)(bx - by), row = (i32)by - 1;
+        int state = 0;                                /* HSTATE 0, ESTATE 1, FSTATE 2 */
+        int found = 0;
+        u32 sx = 0, sy = 0;
+        while (row >= 0)
+        {
+            const u8 op = dir[(size_t)row * B + entry];
+            const u8 h_op = op & 3u;
+            if (type == 1 && state == 0 && h_op == D_SINK) { sy = (u32)row + 1u; sx = (u32)entry + sy; found = 1; break; }
+            if (state == 1)      { if ((op & D_INS_EXT) == 0) state = 0; --entry;        if (n_ops < max_ops) ops[n_ops] = D_DEL; ++n_ops; }
+            else if (state == 2) { if ((op & D_DEL_EXT) == 0) state = 0; ++entry; --row; if (n_ops < max_ops) ops[n_ops] = D_INS; ++n_ops; }
+            else
+            {
+                if (h_op == D_DEL) state = 1;
+                else if (h_op == D_INS) state = 2;
+                else { --row; if (n_ops < max_ops) ops[n_ops] = D_SUB; ++n_ops; }
+            }
+        }
+        if (!found) { sy = 0; sx = (u32)entry; }
+        source_xy[0] = sx; source_xy[1] = sy;
+        clips[1] = sy;
+    }
+    free(dir);
+    return n_ops;
+}
+
+void orc_banded_traceback(int B, int type, const orc_scheme* S,
+                          const u8* pat, const u32* p_off, const u32* p_len,
+                          const u8* txt, const u32* t_off, const u32* t_len, u32 n, u32 max_ops,
+                          i32* score, u32* sink_xy, u32* source_xy, u8* ops, u32* n_ops, u32* clips)
+{
+    for (u32 i = 0; i < n; ++i)
+        n_ops[i] = orc_banded_traceback_one(B, type, S, pat + p_off[i], p_len[i], txt + t_off[i], t_len[i],
+                                            &score[i], &sink_xy[2 * i], &source_xy[2 * i], ops + (size_t)i * max_ops, max_ops, &clips[2 * i]);
+}

@@ -145,6 +145,28 @@ class Oracle(_Base):
         return score, sx, sy, ok
 
 
+def _oracle_traceback(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=512):
+    """Oracle.banded_traceback: ops in END->START push order (0 M, 1 I, 2 D), clips = (M - sink.y, source.y)"""
+    pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
+    if len(scheme) == 4:
+        scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+    s = np.array(scheme, dtype=np.int32)
+    self.lib.orc_banded_traceback(C.c_int(band), C.c_int(typ), _p(s), _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len),
+                                  C.c_uint32(n), C.c_uint32(max_ops), _p(o["score"]), _p(o["sink"]), _p(o["source"]), _p(o["ops"]),
+                                  _p(o["n_ops"]), _p(o["clips"]))
+    return o
+
+
+def _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops):
+    pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+    p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+    t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+    n = len(p_off)
+    out = dict(score=np.zeros(n, np.int32), sink=np.zeros((n, 2), np.uint32), source=np.zeros((n, 2), np.uint32),
+               ops=np.zeros((n, max_ops), np.uint8), n_ops=np.zeros(n, np.uint32), clips=np.zeros((n, 2), np.uint32))
+    return pat, p_off, p_len, txt, t_off, t_len, n, out
+
+
 class Ref(_Base):
     """The reference's own templates (only where oracle/_ref/libnvbio_ref.so exists)."""
     kind = "reference"
@@ -215,6 +237,15 @@ class Ref(_Base):
                             C.c_uint32(idx.primary), _p(rows), C.c_uint32(len(rows)), _p(out))
         return out
 
+    def banded_traceback(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=512):
+        """aln::banded_alignment_traceback: ops in END->START push order (0 M, 1 I, 2 D)"""
+        pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
+        r = self.lib.ref_banded_traceback(C.c_int(band), C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]), C.c_int(scheme[2]), C.c_int(scheme[3]),
+                                          _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n), C.c_uint32(max_ops),
+                                          _p(o["score"]), _p(o["sink"]), _p(o["source"]), _p(o["ops"]), _p(o["n_ops"]), _p(o["clips"]))
+        assert r == 0
+        return o
+
     def banded_gotoh(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
         assert qual is None and qtab is None and len(scheme) == 4, "ref shim instantiates SimpleGotohScheme only"
         pat = np.ascontiguousarray(pat, dtype=np.uint8)
@@ -236,9 +267,27 @@ class Ref(_Base):
         return score, sx, sy, ok
 
 
+def rle(ops):
+    """run-length string of an op array in the given order, letters as TestBacktracker: 0 M, 1 I, 2 D"""
+    out, prev, cnt = [], None, 0
+    for o in ops:
+        if o == prev:
+            cnt += 1
+        else:
+            if prev is not None:
+                out.append("%d%s" % (cnt, "MID"[prev]))
+            prev, cnt = int(o), 1
+    if prev is not None:
+        out.append("%d%s" % (cnt, "MID"[prev]))
+    return "".join(out)
+
+
 def dna(s):
     """ASCII ACGT(N) -> symbols 0..3 (4)"""
     lut = np.full(256, 4, dtype=np.uint8)
     for i, ch in enumerate("ACGT"):
         lut[ord(ch)] = i
     return lut[np.frombuffer(s.encode(), dtype=np.uint8)]
+
+
+Oracle.banded_traceback = _oracle_traceback

@@ -93,9 +93,80 @@ int run_banded_type(int type, const aln::SimpleGotohScheme s,
     return -1;
 }
 
+// a Backtracer (nvbio/alignment/alignment.h "Backtracer" concept) that records the pushed ops (end -> start order, as
+// TestBacktracker does, nvbio-test/alignment_test_utils.h:628-643) and the two clip lengths
+struct RecordingBacktracer
+{
+    uint8* ops; uint32 n, cap; uint32 clips[2]; uint32 n_clips;
+    void clip(const uint32 len) { if (n_clips < 2) clips[n_clips] = len; ++n_clips; }
+    void push(const uint8 op)   { if (n < cap) ops[n] = op; ++n; }
+};
+
+template <uint32 BAND, aln::AlignmentType TYPE>
+void run_traceback(const aln::SimpleGotohScheme scheme,
+                   const uint8* pat, const uint32* p_off, const uint32* p_len,
+                   const uint8* txt, const uint32* t_off, const uint32* t_len,
+                   uint32 n, uint32 max_ops, int32* score, uint32* sink_xy, uint32* source_xy,
+                   uint8* ops, uint32* n_ops, uint32* clips)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        RecordingBacktracer bt; bt.ops = ops + uint64(i)*max_ops; bt.n = 0; bt.cap = max_ops; bt.n_clips = 0; bt.clips[0] = bt.clips[1] = 0;
+        const aln::Alignment<int32> a = aln::banded_alignment_traceback<BAND,1024u,32u>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),
+            str_view( p_len[i], pat + p_off[i] ),
+            aln::trivial_quality_string(),
+            str_view( t_len[i], txt + t_off[i] ),
+            INT_MIN,
+            bt );
+        score[i] = a.score;
+        sink_xy[2*i] = a.sink.x;     sink_xy[2*i+1] = a.sink.y;
+        source_xy[2*i] = a.source.x; source_xy[2*i+1] = a.source.y;
+        n_ops[i] = bt.n;
+        clips[2*i] = bt.clips[0]; clips[2*i+1] = bt.clips[1];
+    }
+}
+
+template <uint32 BAND>
+int run_traceback_type(int type, const aln::SimpleGotohScheme s,
+                   const uint8* pat, const uint32* p_off, const uint32* p_len,
+                   const uint8* txt, const uint32* t_off, const uint32* t_len,
+                   uint32 n, uint32 max_ops, int32* score, uint32* sink_xy, uint32* source_xy,
+                   uint8* ops, uint32* n_ops, uint32* clips)
+{
+    switch (type)
+    {
+    case 0: run_traceback<BAND,aln::GLOBAL>     ( s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips ); return 0;
+    case 1: run_traceback<BAND,aln::LOCAL>      ( s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips ); return 0;
+    case 2: run_traceback<BAND,aln::SEMI_GLOBAL>( s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips ); return 0;
+    }
+    return -1;
+}
+
 } // anonymous namespace
 
 extern "C" {
+
+// banded Gotoh traceback (aln::banded_alignment_traceback<BAND,1024,32>, nvbio/alignment/banded_inl.h:352-489):
+// ops are the backtracer's pushes in END -> START order (0 = SUBSTITUTION 'M', 1 = INSERTION 'I', 2 = DELETION 'D'),
+// clips = (pattern_len - sink.y, source.y)
+int ref_banded_traceback(int band, int type, int match, int mismatch, int gap_open, int gap_ext,
+                     const uint8* pat, const uint32* p_off, const uint32* p_len,
+                     const uint8* txt, const uint32* t_off, const uint32* t_len,
+                     uint32 n, uint32 max_ops, int32* score, uint32* sink_xy, uint32* source_xy,
+                     uint8* ops, uint32* n_ops, uint32* clips)
+{
+    const aln::SimpleGotohScheme s( match, mismatch, gap_open, gap_ext );
+    switch (band)
+    {
+    case  7: return run_traceback_type< 7>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips );
+    case 15: return run_traceback_type<15>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips );
+    case 31: return run_traceback_type<31>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips );
+    }
+    return -1;
+}
+
 
 int ref_num_threads() { return omp_get_max_threads(); }
 void ref_set_num_threads(int t) { omp_set_num_threads(t); }
