@@ -168,6 +168,22 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
                            int32_t* d_score, nvb_uint2* d_sink,
                            void* d_temp, size_t* temp_bytes, void* stream);
 
+/* Banded Gotoh traceback.  For i < n: score, sink (end cells) as nvb_banded_gotoh_score, plus the
+ * source (start cells) and the alignment as the backtracer's pushes in END -> START order, one byte per op
+ * (0 = SUBSTITUTION 'M', 1 = INSERTION 'I', 2 = DELETION 'D'; nvbio::aln::DirectionVector) at d_ops[i*max_ops ..];
+ * d_n_ops[i] = number of ops (ops beyond max_ops are counted, not stored; max_ops >= pattern length + band_len always
+ * suffices).  The soft clips the reference passes to Backtracer::clip are (pattern_len - sink.y) and source.y.
+ * `patterns->length` must bound the pattern lengths (it sizes the per-alignment direction matrix in d_temp).
+ * Replaces aln::banded_alignment_traceback<BAND_LEN,MAX_PATTERN_LEN,CHECKPOINTS> and
+ * BatchedBandedAlignmentTraceback (nvbio/alignment/banded_inl.h:352-489, gotoh/gotoh_banded_inl.h:763-962,
+ * batched_banded_inl.h:248-451): instead of 32-row checkpoints + window recomputation the whole 4-bit direction
+ * matrix of every alignment is kept in HBM and walked once. */
+int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                               const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
+                               int32_t* d_score, nvb_uint2* d_sink, nvb_uint2* d_source,
+                               uint8_t* d_ops, uint32_t max_ops, uint32_t* d_n_ops,
+                               void* d_temp, size_t* temp_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Index construction on the device (needed to run any of the above on synthetic data)
  * ------------------------------------------------------------------------------------------- */

@@ -112,3 +112,50 @@ def banded_temp_bytes(band_len, aligner, patterns, texts) -> int:
     if r not in (0, -2):
         check(r, "nvb_banded_gotoh_score(size query)")
     return int(tb.value)
+
+
+def batch_banded_alignment_traceback(band_len: int, aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet,
+                                     quals: Optional[torch.Tensor] = None, max_ops: Optional[int] = None):
+    """aln::banded_alignment_traceback<BAND_LEN,...> for a batch (nvbio/alignment/banded_inl.h:352-489).
+    Returns dict(score[n], sink[n,2], source[n,2], ops[n,max_ops] uint8 in END->START push order (0 M, 1 I, 2 D), n_ops[n])."""
+    L = lib()
+    n = patterns.count
+    dev = patterns.words.device
+    if max_ops is None:
+        max_ops = patterns.length + band_len + 1
+    out = dict(score=torch.empty(n, dtype=torch.int32, device=dev), sink=torch.empty((n, 2), dtype=torch.int32, device=dev),
+               source=torch.empty((n, 2), dtype=torch.int32, device=dev), ops=torch.zeros((n, max_ops), dtype=torch.uint8, device=dev),
+               n_ops=torch.empty(n, dtype=torch.int32, device=dev))
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    qp = C.c_void_p(quals.data_ptr()) if quals is not None else None
+    tb = C.c_size_t(0)
+
+    def call(temp_ptr):
+        return L.nvb_banded_gotoh_traceback(C.c_int(band_len), C.c_int(aligner.type), C.byref(sch), C.byref(p), qp, C.byref(t), C.c_uint32(n),
+                                            C.c_void_p(out["score"].data_ptr()), C.c_void_p(out["sink"].data_ptr()),
+                                            C.c_void_p(out["source"].data_ptr()), C.c_void_p(out["ops"].data_ptr()), C.c_uint32(max_ops),
+                                            C.c_void_p(out["n_ops"].data_ptr()), temp_ptr, C.byref(tb), _stream())
+    r = call(None)
+    if r != -2:
+        check(r, "nvb_banded_gotoh_traceback(size query)")
+    temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
+    check(call(C.c_void_p(temp.data_ptr())), "nvb_banded_gotoh_traceback")
+    return out
+
+
+def cigar(ops_row, n_ops: int) -> str:
+    """run-length CIGAR in START->END order from one row of END->START ops"""
+    letters = "MID"
+    seq = [int(v) for v in ops_row[:n_ops]][::-1]
+    out, prev, cnt = [], None, 0
+    for o in seq:
+        if o == prev:
+            cnt += 1
+        else:
+            if prev is not None:
+                out.append("%d%s" % (cnt, letters[prev]))
+            prev, cnt = o, 1
+    if prev is not None:
+        out.append("%d%s" % (cnt, letters[prev]))
+    return "".join(out)

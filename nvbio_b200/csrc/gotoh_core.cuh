@@ -59,16 +59,24 @@ struct SinkResult { int32_t score; uint32_t x, y; };
 // ---------------------------------------------------------------------------------------------
 // generic: one alignment, int32
 // ---------------------------------------------------------------------------------------------
-template <int B, int TYPE>
-__host__ __device__ inline SinkResult gotoh_generic(const GotohScheme& S,
+// direction vectors of the traceback (nvbio::aln::DirectionVector, nvbio/alignment/alignment_base.h:139-150)
+enum { DIR_SUB = 0, DIR_INS = 1, DIR_DEL = 2, DIR_SINK = 3, DIR_INS_EXT = 4, DIR_DEL_EXT = 8 };
+template <int B> struct DirWords { static constexpr int N = (B * 4 + 31) / 32; };     // 4 bits per band cell
+
+// DIRS: also emit, per row, the packed 4-bit direction vectors (H | E | F flow) of every band cell to
+// dirs[row * DirWords<B>::N ..] -- exactly the bits GotohSubmatrixContext::new_cell stores (gotoh_banded_inl.h:325-337)
+template <int B, int TYPE, bool DIRS>
+__host__ __device__ inline SinkResult gotoh_generic_impl(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
         const uint8_t* __restrict__ quals,
-        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N)
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
+        uint32_t* __restrict__ dirs)
 {
     SinkResult res; res.score = INT_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
     if (N < M) return res;
 
     constexpr bool PACKED = packed_text_cache(B);
+    constexpr int  NW = DirWords<B>::N;
     const int32_t Go = S.pgo, Ge = S.pge;
     const int32_t INF = gotoh_infimum(S);
 
@@ -96,22 +104,52 @@ __host__ __device__ inline SinkResult gotoh_generic(const GotohScheme& S,
         const int32_t s_ne = S.qtab ? S.qtab[2 * qq + 1] : S.mismatch;
         const uint32_t g_new = (i + (uint32_t)B - 1u < N) ? tr.get(toff + i + B - 1) : 255u;
         int32_t E = 0;
+        uint32_t edir = DIR_SUB;
+        uint32_t dw[NW];
+        if (DIRS) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) dw[w] = 0u;
+        }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const uint32_t g = (j < B - 1) ? cache[j] : g_new;          // cell B-1 sees the unmasked symbol
             if (j >= 1 && j < B - 1) cache[j - 1] = g;
-            if (j < B - 1) F[j] = imax2(F[j + 1] + Ge, H[j + 1] + Go); else F[j] = INF;
-            int32_t h = H[j] + ((g == q) ? s_eq : s_ne);
-            if (j < B - 1) h = imax2(h, F[j]);
-            if (j > 0)     h = imax2(h, E);
+            uint32_t fdir = DIR_SUB;
+            if (j < B - 1) {
+                const int32_t ftop = F[j + 1] + Ge, htop = H[j + 1] + Go;
+                F[j] = imax2(ftop, htop);
+                if (DIRS) fdir = ftop > htop ? DIR_DEL_EXT : DIR_SUB;
+            } else F[j] = INF;
+            const int32_t diagonal = H[j] + ((g == q) ? s_eq : s_ne);
+            const int32_t top = F[j], left = E;
+            int32_t h = diagonal;
+            if (j < B - 1) h = imax2(h, top);
+            if (j > 0)     h = imax2(h, left);
+            uint32_t hdir = DIR_SUB;
+            if (DIRS) {
+                if (j == 0)          hdir = top > diagonal ? DIR_INS : DIR_SUB;
+                else if (j < B - 1)  hdir = top > left ? (top > diagonal ? DIR_INS : DIR_SUB) : (left > diagonal ? DIR_DEL : DIR_SUB);
+                else                 hdir = left > diagonal ? DIR_DEL : DIR_SUB;
+            }
             if (TYPE == NVB_LOCAL) {
                 h = imax2(h, 0);
+                if (DIRS && h == 0) hdir = DIR_SINK;
                 if (best <= h) { best = h; bpos = (i << 6) | (uint32_t)j; }
             }
             H[j] = h;
-            E = (j == 0) ? h + Go : imax2(h + Go, E + Ge);
+            if (DIRS) dw[j >> 3] |= (hdir | edir | fdir) << (4 * (j & 7));
+            if (j == 0) { E = h + Go; edir = DIR_SUB; }
+            else {
+                const int32_t eleft = E + Ge, ediagonal = h + Go;
+                if (DIRS) edir = eleft > ediagonal ? DIR_INS_EXT : DIR_SUB;
+                E = imax2(ediagonal, eleft);
+            }
         }
         cache[B - 2] = PACKED ? (g_new & 3u) : g_new;
+        if (DIRS) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) dirs[(size_t)i * NW + w] = dw[w];
+        }
     }
     if (TYPE == NVB_LOCAL) {
         if (M > 0) { res.score = best; res.x = (bpos >> 6) + (bpos & 63u) + 1u; res.y = (bpos >> 6) + 1u; }
@@ -125,6 +163,45 @@ __host__ __device__ inline SinkResult gotoh_generic(const GotohScheme& S,
             if ((uint32_t)j < m && res.score <= H[j]) { res.score = H[j]; res.x = M + (uint32_t)j; }
     }
     return res;
+}
+
+template <int B, int TYPE>
+__host__ __device__ inline SinkResult gotoh_generic(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
+        const uint8_t* __restrict__ quals,
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N)
+{
+    return gotoh_generic_impl<B, TYPE, false>(S, pwords, pbits, pbe, poff, M, quals, twords, tbits, tbe, toff, N, nullptr);
+}
+
+// Backtrack through the direction matrix from the sink (the H/E/F state machine of
+// priv::banded_alignment_traceback, gotoh_banded_inl.h:893-958, walked over the whole matrix instead of one
+// 32-row checkpoint window at a time).  Pushes ops in END -> START order (0 SUBSTITUTION 'M', 1 INSERTION 'I',
+// 2 DELETION 'D'); returns their number (ops beyond max_ops are counted but not stored) and the source cell.
+template <int B, int TYPE>
+__host__ __device__ inline uint32_t gotoh_walk(const uint32_t* __restrict__ dirs, const SinkResult& sink,
+                                               uint8_t* __restrict__ ops, uint32_t max_ops, uint32_t& src_x, uint32_t& src_y)
+{
+    constexpr int NW = DirWords<B>::N;
+    int32_t entry = (int32_t)(sink.x - sink.y), row = (int32_t)sink.y - 1;
+    uint32_t n_ops = 0, state = 0;                  // HSTATE 0, ESTATE 1, FSTATE 2
+    while (row >= 0) {
+        const uint32_t op = (dirs[(size_t)row * NW + (entry >> 3)] >> (4 * (entry & 7))) & 15u;
+        const uint32_t h_op = op & 3u;
+        if (TYPE == NVB_LOCAL && state == 0 && h_op == DIR_SINK) {
+            src_y = (uint32_t)row + 1u; src_x = (uint32_t)entry + src_y;
+            return n_ops;
+        }
+        if (state == 1)      { if ((op & DIR_INS_EXT) == 0) state = 0; --entry;        if (n_ops < max_ops) ops[n_ops] = DIR_DEL; ++n_ops; }
+        else if (state == 2) { if ((op & DIR_DEL_EXT) == 0) state = 0; ++entry; --row; if (n_ops < max_ops) ops[n_ops] = DIR_INS; ++n_ops; }
+        else {
+            if (h_op == DIR_DEL) state = 1;
+            else if (h_op == DIR_INS) state = 2;
+            else { --row; if (n_ops < max_ops) ops[n_ops] = DIR_SUB; ++n_ops; }
+        }
+    }
+    src_y = 0u; src_x = (uint32_t)entry;
+    return n_ops;
 }
 
 // ---------------------------------------------------------------------------------------------

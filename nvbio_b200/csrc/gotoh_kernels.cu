@@ -105,6 +105,45 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
     }
 }
 
+// traceback: one alignment per thread; DP with direction vectors into a per-alignment global scratch matrix
+// (M rows x DirWords<B>::N words -- no checkpoints / recomputation: 2.4 KB per 150 x 31 alignment is nothing in 180 GB),
+// then the H/E/F state-machine walk from the sink.
+struct TracebackOut {
+    uint2* source; uint8_t* ops; uint32_t* n_ops; uint32_t max_ops; uint32_t* dirs; uint32_t dir_rows;
+};
+
+template <int B, int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_traceback_kernel(const GotohScheme S, const GotohBatch b, const TracebackOut o)
+{
+    constexpr int NW = DirWords<B>::N;
+    const uint32_t n = batch_count(b);
+    const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
+    if (a >= n) return;
+    uint32_t* dirs = o.dirs + (size_t)a * o.dir_rows * NW;
+    const uint32_t M = str_len(b.pat, a);
+    SinkResult r; r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu;
+    if (M <= o.dir_rows)
+        r = gotoh_generic_impl<B, TYPE, true>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), M, b.quals,
+                                              b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a), dirs);
+    b.score[a] = r.score;
+    b.sink[a]  = make_uint2(r.x, r.y);
+    uint32_t sx = 0xFFFFFFFFu, sy = 0xFFFFFFFFu, cnt = 0;
+    if (r.x != 0xFFFFFFFFu && r.y != 0xFFFFFFFFu)
+        cnt = gotoh_walk<B, TYPE>(dirs, r, o.ops + (size_t)a * o.max_ops, o.max_ops, sx, sy);
+    o.source[a] = make_uint2(sx, sy);
+    o.n_ops[a]  = cnt;
+}
+
+template <int B, int TYPE>
+static int launch_traceback(const GotohScheme& S, const GotohBatch& b, const TracebackOut& o, cudaStream_t s)
+{
+    const uint32_t grid = (b.n_max + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
+    gotoh_traceback_kernel<B, TYPE><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, o);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
 template <int B, int TYPE>
 static int launch_generic(const GotohScheme& S, const GotohBatch& b, const uint32_t* todo, const uint32_t* todo_count, uint32_t n_hint, cudaStream_t s)
 {
@@ -162,6 +201,19 @@ static int dispatch_pair(int band, int type, const GotohScheme& S, const GotohBa
     }
     return NVB_E_INVALID;
 }
+
+static int dispatch_traceback(int band, int type, const GotohScheme& S, const GotohBatch& b, const TracebackOut& o, cudaStream_t s)
+{
+    switch (band) {
+    case 3:  NVB_TYPE_SWITCH(3,  launch_traceback, S, b, o, s)
+    case 5:  NVB_TYPE_SWITCH(5,  launch_traceback, S, b, o, s)
+    case 7:  NVB_TYPE_SWITCH(7,  launch_traceback, S, b, o, s)
+    case 15: NVB_TYPE_SWITCH(15, launch_traceback, S, b, o, s)
+    case 31: NVB_TYPE_SWITCH(31, launch_traceback, S, b, o, s)
+    }
+    return NVB_E_INVALID;
+}
+static inline int dir_words(int band) { return (band * 4 + 31) / 32; }
 
 // force_path: 0 auto, 1 generic only (used by tests to exercise both paths on the same inputs)
 static int g_force_path = 0;
@@ -227,6 +279,30 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
 {
     if (!d_n) return NVB_E_INVALID;
     return banded_impl(band_len, type, scheme, patterns, d_quals, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
+}
+
+int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                               const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
+                               int32_t* d_score, nvb_uint2* d_sink, nvb_uint2* d_source,
+                               uint8_t* d_ops, uint32_t max_ops, uint32_t* d_n_ops,
+                               void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
+    if (!(band_len == 3 || band_len == 5 || band_len == 7 || band_len == 15 || band_len == 31)) return NVB_E_INVALID;
+    if (type < 0 || type > 2) return NVB_E_INVALID;
+    const uint32_t max_m = patterns->length ? patterns->length : 1u;
+    TempCarver tc(d_temp);
+    uint32_t* dirs = tc.take<uint32_t>((size_t)n * max_m * dir_words(band_len));
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    if (n == 0) return NVB_OK;
+    if (!d_score || !d_sink || !d_source || !d_ops || !d_n_ops || max_ops == 0) return NVB_E_INVALID;
+    GotohBatch b;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
+    b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
+    TracebackOut o;
+    o.source = (uint2*)d_source; o.ops = d_ops; o.n_ops = d_n_ops; o.max_ops = max_ops; o.dirs = dirs; o.dir_rows = max_m;
+    return dispatch_traceback(band_len, type, make_scheme(scheme), b, o, as_stream(stream));
 }
 
 // test hook (declared in tests only): 0 = auto, 1 = generic int32 kernel for everything

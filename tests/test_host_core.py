@@ -253,3 +253,26 @@ def test_gotoh_pair_quality_table(H, O):
                 assert r == 0 and (ragged or nf == 0)
                 for a, b in zip(got, want[:3]):
                     assert np.array_equal(a, b), (band, typ, ragged)
+
+
+@pytest.mark.parametrize("band", [7, 15, 31])
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_traceback(H, O, band, typ):
+    """direction-matrix traceback of the product's per-thread routine == the oracle's (== the reference's checkpointed
+    aln::banded_alignment_traceback, pinned in tests/test_oracle.py)"""
+    rng = np.random.default_rng(300 + band + typ)
+    for scheme in ((2, -2, -5, -3), (2, -1, -1, -1), (0, -5, -8, -3)):
+        pr = fixed_problems(rng, 60, band, 150, extra_text=int(rng.integers(0, 3)), ragged=True)
+        want = O.banded_traceback(band, typ, scheme, *pr)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 2, True)
+        n, max_ops = len(p_off), 512
+        score = np.zeros(n, np.int32); sink = np.zeros((n, 2), np.uint32); source = np.zeros((n, 2), np.uint32)
+        ops = np.zeros((n, max_ops), np.uint8); n_ops = np.zeros(n, np.uint32)
+        s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+        r = H.hh_gotoh_traceback(C.c_int(band), C.c_int(typ), _p(s6), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(u32(p_off)), _p(u32(p_len)),
+                                 _p(tw), C.c_uint32(2), C.c_uint32(1), _p(u32(t_off)), _p(u32(t_len)), C.c_uint32(n), C.c_uint32(max_ops),
+                                 _p(score), _p(sink), _p(source), _p(ops), _p(n_ops))
+        assert r == 0
+        assert np.array_equal(score, want["score"]) and np.array_equal(sink, want["sink"]) and np.array_equal(source, want["source"])
+        assert np.array_equal(n_ops, want["n_ops"]) and np.array_equal(ops, want["ops"]), (band, typ, scheme)

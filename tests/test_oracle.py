@@ -158,3 +158,23 @@ def test_banded_vs_reference_fresh(O, R):
             b = R.banded_gotoh(band, typ, scheme, *pr)
             for u, v in zip(a, b):
                 assert np.array_equal(u, v), (band, typ, scheme)
+
+
+def test_traceback_reference_cigars(O):
+    """the CIGARs the reference's own test asserts (nvbio-test/alignment_test.cu:793,825), in its END->START order"""
+    for P, T, scheme, band, want in ((G1_P, G1_T, (2, -1, -1, -1), 7, "4M1D3M"), (G2_P, G2_T, (0, -5, -8, -3), 31, "147M2D3M")):
+        p, t = orc.dna(P), orc.dna(T)
+        o = O.banded_traceback(band, 2, scheme, p, [0], [len(p)], t, [0], [len(t)])
+        assert orc.rle(o["ops"][0][:o["n_ops"][0]]) == want
+
+
+def test_traceback_vs_reference_fresh(O, R):
+    from tests.test_host_core import fixed_problems
+    rng = np.random.default_rng(77)
+    for band in (7, 15, 31):
+        for typ in (0, 1, 2):
+            scheme = tuple(int(v) for v in (rng.integers(0, 4), -rng.integers(1, 7), -rng.integers(1, 9), -rng.integers(1, 5)))
+            pr = fixed_problems(rng, 120, band, 150, extra_text=int(rng.integers(0, 3)), ragged=True)
+            a, b = O.banded_traceback(band, typ, scheme, *pr), R.banded_traceback(band, typ, scheme, *pr)
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (band, typ, scheme, k)
