@@ -55,7 +55,9 @@ def test_traceback_vs_oracle(O, band, typ):
         for a in range(0, 777, 37):
             ops = got["ops"][a][:got["n_ops"][a]][::-1]
             i, j = int(got["source"][a][1]), int(got["source"][a][0])
-            s, prev = 0, -1
+            # GLOBAL starts from row 0 of the band, whose cell j carries the text-gap cost of skipping j symbols
+            # (init_row_zero, gotoh_banded_inl.h:57-59)
+            s, prev = ((go + (j - 1) * ge) if (typ == 0 and j > 0) else 0), -1
             for op in ops:
                 if op == 0:
                     s += m if pat[p_off[a] + i] == txt[t_off[a] + j] else x; i += 1; j += 1
