@@ -123,6 +123,20 @@ int nvb_fm_rank4(const nvb_fm_index* fmi, const uint32_t* d_k, uint32_t n, uint3
 int nvb_fm_match(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
                  nvb_uint2* d_ranges, void* stream);
 
+/* One-mismatch seed search: nvBowtie's map<find_exact>(query, len1, len2, index, ...) as a batch primitive
+ * (nvBowtie/bowtie2/cuda/mapping_inl.h:128-220, the rank4-based core of the APPROX / CASE_PRUNING seed mappers,
+ * :318-429).  For query i: every SA range of the query with exactly one substitution among its consumed symbols
+ * [exact_len, len) (none in the first exact_len), in the reference's push order (position ascending, substituted
+ * symbol ascending), followed by the perfect match when find_exact; an N inside the exact region or a second N yields
+ * nothing, a single later N ends exact matching there.  "Consumed symbols" are the stream's symbols in order with
+ * NVB_MATCH_FORWARD_ORDER (nvBowtie's forward reader over its reversed reads), reversed without it.
+ * d_ranges[i*max_out + k] = k-th inclusive range (k < min(count, max_out)); d_counts[i] = pushes; d_range_sums[i]
+ * (optional) = sum of the range sizes (the reference's range_sum; range_count = count).
+ * The bounded priority deque the reference feeds (seed_hit_deque_array.h) stays with the caller. */
+int nvb_fm_match_approx(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
+                        uint32_t exact_len, int find_exact, uint32_t max_out,
+                        nvb_uint2* d_ranges, uint32_t* d_counts, uint32_t* d_range_sums, void* stream);
+
 /* d_pos[i] = text position of SA row d_rows[i]  (row 0 -> 0xFFFFFFFF as in the reference).
  * Replaces nvbio::locate(fm_index,i) (nvbio/fmindex/fmindex_inl.h:471-499) with
  * SSA_index_multiple_context<16>::fetch (nvbio/fmindex/ssa_inl.h:487-504). */
@@ -238,6 +252,29 @@ int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     int32_t* d_best_score, uint32_t* d_best_pos,
                     uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
                     int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    void* d_temp, size_t* temp_bytes, void* stream);
+
+/* Optional alignment of every read's best hit (what nvBowtie's banded_traceback_best produces for SAM output,
+ * aligner_best_approx.h:300-500): the banded traceback of the best (strand, window) job of each read.
+ *   d_ops[r*max_ops ..]  ops in END -> START order (0 M, 1 I, 2 D), d_n_ops[r] their number (0 when the read has no hit)
+ *   d_begin[r]           = (genome coordinate of the alignment's first text symbol, first aligned read symbol)
+ *   d_strand[r]          = 0 forward, 1 reverse complement (the read symbols are those of that strand's string)
+ * Call with the same arguments as nvb_seed_extend plus this struct; temp size grows by the direction matrices. */
+typedef struct nvb_best_alignment_out {
+    uint8_t*   d_ops;
+    uint32_t   max_ops;
+    uint32_t*  d_n_ops;
+    nvb_uint2* d_begin;
+    uint8_t*   d_strand;
+} nvb_best_alignment_out;
+
+int nvb_seed_extend_traceback(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_reads,
+                    const nvb_seed_extend_params* params, uint32_t hit_capacity,
+                    int32_t* d_best_score, uint32_t* d_best_pos,
+                    uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
+                    int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    const nvb_best_alignment_out* best_alignment,
                     void* d_temp, size_t* temp_bytes, void* stream);
 
 /* Profiling aid (the reference wraps every stage in cuda::Timer, nvBowtie/bowtie2/cuda/aligner_best_approx.h:

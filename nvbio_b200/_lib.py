@@ -8,9 +8,9 @@ LIB_PATH = os.path.join(_HERE, "libnvbio_b200.so")
 
 EXPORTS = [
     "nvb_version", "nvb_error_string",
-    "nvb_fm_rank", "nvb_fm_rank4", "nvb_fm_match", "nvb_fm_locate", "nvb_fm_filter_rank", "nvb_fm_filter_locate",
+    "nvb_fm_rank", "nvb_fm_rank4", "nvb_fm_match", "nvb_fm_match_approx", "nvb_fm_locate", "nvb_fm_filter_rank", "nvb_fm_filter_locate",
     "nvb_banded_gotoh_score", "nvb_banded_gotoh_score_indirect", "nvb_banded_gotoh_traceback",
-    "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_fm_build_ktab", "nvb_seed_extend", "nvb_seed_extend_stage_ms",
+    "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_fm_build_ktab", "nvb_seed_extend", "nvb_seed_extend_traceback", "nvb_seed_extend_stage_ms",
 ]
 
 
@@ -40,6 +40,11 @@ class SeedExtendParamsStruct(C.Structure):  # nvb_seed_extend_params
     _fields_ = [("seed_len", C.c_uint32), ("seed_interval", C.c_uint32), ("band_len", C.c_uint32),
                 ("type", C.c_uint32), ("both_strands", C.c_uint32), ("max_seed_hits", C.c_uint32),
                 ("dedup_jobs", C.c_uint32), ("scheme", GotohSchemeStruct)]
+
+
+class BestAlignmentOutStruct(C.Structure):   # nvb_best_alignment_out
+    _fields_ = [("d_ops", C.c_void_p), ("max_ops", C.c_uint32), ("d_n_ops", C.c_void_p), ("d_begin", C.c_void_p),
+                ("d_strand", C.c_void_p)]
 
 
 _lib = None

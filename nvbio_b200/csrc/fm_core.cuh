@@ -209,6 +209,69 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
     ox = x; oy = y;
 }
 
+// nvBowtie's map<find_exact>(query, len1, len2, ...) (nvBowtie/bowtie2/cuda/mapping_inl.h:128-220): hits that match
+// exactly over the first len1 consumed symbols and carry exactly one substitution among symbols [len1, len2), plus the
+// perfect match when find_exact.  Symbols are taken in CONSUMPTION order (query[i] of the reference's reader): stream
+// order with NVB_MATCH_FORWARD_ORDER, reversed without; complemented with NVB_MATCH_COMPLEMENT.
+// Ranges are written in the reference's push order (position ascending, substituted symbol ascending, exact last) to
+// out[0..max_out); the return value counts every push (it may exceed max_out) and range_sum adds their sizes.
+template <int BITS, bool BE>
+__host__ __device__ inline uint32_t fm_map_approx_one(const FmIndex& f, const uint32_t* __restrict__ words,
+                                                      uint32_t off, uint32_t len2, uint32_t len1, uint32_t flags, bool find_exact,
+                                                      uint2* __restrict__ out, uint32_t max_out, uint32_t& range_sum)
+{
+    const bool fwd = (flags & NVB_MATCH_FORWARD_ORDER) != 0;
+    const bool comp = (flags & NVB_MATCH_COMPLEMENT) != 0;
+    SymReader<BITS, BE> rd(words);
+    auto sym = [&](uint32_t i) -> uint32_t {
+        const uint32_t c = rd.get(off + (fwd ? i : (len2 - 1u - i)));
+        return (comp && c < 4u) ? 3u - c : c;
+    };
+    range_sum = 0;
+    uint32_t n_out = 0;
+    if (len1 > len2) len1 = len2;
+    // an N inside the exact region, or a second N, rules the seed out; a single N later stops exact matching there
+    uint32_t n_pos = 0, n_cnt = 0;
+    for (uint32_t i = 0; i < len2; ++i) {
+        if (sym(i) > 3u) {
+            if (i < len1 || n_cnt) return 0u;
+            n_pos = i; ++n_cnt;
+        }
+    }
+    if (n_cnt) len1 = n_pos;
+
+    uint32_t bx = 0, by = f.n;
+    for (uint32_t i = 0; i < len1 && bx <= by; ++i) fm_step(f, sym(i), bx, by);
+
+    for (uint32_t i = len1; i < len2 && bx <= by; ++i) {
+        const uint32_t c = sym(i);
+        const uint4 lo = fm_rank4(f, bx - 1u), hi = fm_rank4(f, by);
+        const uint32_t los[4] = { lo.x, lo.y, lo.z, lo.w }, his[4] = { hi.x, hi.y, hi.z, hi.w };
+#pragma unroll
+        for (uint32_t sub = 0; sub < 4; ++sub) {
+            if (sub != c && his[sub] > los[sub]) {
+                uint32_t x = f.l2(sub) + los[sub] + 1u, y = f.l2(sub) + his[sub];
+                for (uint32_t k = i + 1u; k < len2 && x <= y; ++k) {
+                    const uint32_t ck = sym(k);
+                    if (ck > 3u) { x = 1u; y = 0u; break; }
+                    fm_step(f, ck, x, y);
+                }
+                if (x <= y) {
+                    if (n_out < max_out) out[n_out] = make_uint2(x, y);
+                    ++n_out; range_sum += y - x + 1u;
+                }
+            }
+        }
+        if (c < 4u) { bx = f.l2(c) + los[c] + 1u; by = f.l2(c) + his[c]; }
+        else { bx = 1u; by = 0u; break; }
+    }
+    if (find_exact && bx <= by) {
+        if (n_out < max_out) out[n_out] = make_uint2(bx, by);
+        ++n_out; range_sum += by - bx + 1u;
+    }
+    return n_out;
+}
+
 // locate(fmi, row)
 __host__ __device__ __forceinline__ uint32_t fm_locate_one(const FmIndex& f, uint32_t row) {
     uint32_t j = row, t = 0;

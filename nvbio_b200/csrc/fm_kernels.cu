@@ -39,6 +39,20 @@ fm_match_kernel(const FmIndex f, const StrSet q, uint32_t n, uint32_t flags, uin
     out[i] = make_uint2(x, y);
 }
 
+template <int BITS, bool BE>
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_match_approx_kernel(const FmIndex f, const StrSet q, uint32_t n, uint32_t flags, uint32_t exact_len, bool find_exact, uint32_t max_out,
+                       uint2* __restrict__ out, uint32_t* __restrict__ counts, uint32_t* __restrict__ sums)
+{
+    const uint32_t i = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (i >= n) return;
+    uint32_t sum = 0;
+    const uint32_t cnt = fm_map_approx_one<BITS, BE>(f, q.words, str_off(q, i), str_len(q, i), exact_len, flags, find_exact,
+                                                     out + (size_t)i * max_out, max_out, sum);
+    counts[i] = cnt;
+    if (sums) sums[i] = sum;
+}
+
 __global__ void __launch_bounds__(FM_BLOCKDIM)
 fm_locate_kernel(const FmIndex f, const uint32_t* __restrict__ rows, uint32_t n, uint32_t* __restrict__ out)
 {
@@ -207,6 +221,24 @@ int nvb_fm_match(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_
     const StrSet q = make_strset(queries);
     const uint32_t grid = (n + FM_BLOCKDIM - 1) / FM_BLOCKDIM;
 #define CALL(B, E) fm_match_kernel<B, E><<<grid, FM_BLOCKDIM, 0, as_stream(stream)>>>(f, q, n, flags, (uint2*)d_ranges)
+    NVB_DISPATCH_STREAM(q.bits, q.big_endian, CALL);
+#undef CALL
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_match_approx(const nvb_fm_index* fmi, const nvb_string_set* queries, uint32_t n, uint32_t flags,
+                        uint32_t exact_len, int find_exact, uint32_t max_out,
+                        nvb_uint2* d_ranges, uint32_t* d_counts, uint32_t* d_range_sums, void* stream)
+{
+    if (!valid_fmindex(fmi) || !valid_strset(queries) || max_out == 0 || (n && (!d_ranges || !d_counts))) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    nvb_fm_index plain = *fmi; plain.d_ktab = nullptr; plain.ktab_k = 0;      // ranges start mid-seed: no table look-up here
+    const FmIndex f = make_fmindex(&plain);
+    const StrSet q = make_strset(queries);
+    const uint32_t grid = (n + FM_BLOCKDIM - 1) / FM_BLOCKDIM;
+#define CALL(B, E) fm_match_approx_kernel<B, E><<<grid, FM_BLOCKDIM, 0, as_stream(stream)>>>(f, q, n, flags, exact_len, find_exact != 0, max_out, \
+                                                                                           (uint2*)d_ranges, d_counts, d_range_sums)
     NVB_DISPATCH_STREAM(q.bits, q.big_endian, CALL);
 #undef CALL
     NVB_LAUNCH_CHECK();

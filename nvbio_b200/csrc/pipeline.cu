@@ -248,6 +248,35 @@ pipe_finalize_kernel(const PipeGeom g, const unsigned long long* __restrict__ be
     best_pos[r] = t_off[h] + sink[h].x;
 }
 
+// the best hit of every read as an alignment job for the traceback (reads without a hit get an empty job)
+__global__ void __launch_bounds__(256)
+pipe_best_jobs_kernel(const PipeGeom g, const unsigned long long* __restrict__ best_key, const uint32_t* __restrict__ hit_string,
+                      const uint32_t* __restrict__ p_off, const uint32_t* __restrict__ p_len,
+                      const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
+                      uint32_t* __restrict__ bp_off, uint32_t* __restrict__ bp_len, uint32_t* __restrict__ bt_off, uint32_t* __restrict__ bt_len,
+                      uint8_t* __restrict__ strand)
+{
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= g.n_reads) return;
+    const unsigned long long key = best_key[r];
+    if (key == 0ull) { bp_off[r] = 0; bp_len[r] = 0; bt_off[r] = 0; bt_len[r] = 0; if (strand) strand[r] = 0; return; }
+    const uint32_t h = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    bp_off[r] = p_off[h]; bp_len[r] = p_len[h]; bt_off[r] = t_off[h]; bt_len[r] = t_len[h];
+    if (strand) strand[r] = (uint8_t)(hit_string[h] % g.strands);
+}
+
+// source cell (window-relative text start, read start) -> (genome coordinate, read start); reads without a hit: n_ops 0
+__global__ void __launch_bounds__(256)
+pipe_best_begin_kernel(const PipeGeom g, const unsigned long long* __restrict__ best_key, const uint32_t* __restrict__ bt_off,
+                       const uint2* __restrict__ source, uint32_t* __restrict__ n_ops, uint2* __restrict__ begin)
+{
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= g.n_reads) return;
+    if (best_key[r] == 0ull) { n_ops[r] = 0; begin[r] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); return; }
+    const uint2 sc = source[r];
+    begin[r] = make_uint2(bt_off[r] + sc.x, sc.y);
+}
+
 __global__ void __launch_bounds__(256)
 pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ hit_string,
                         const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
@@ -278,14 +307,16 @@ extern "C" int nvb_seed_extend_stage_ms(float ms[7])
     return NVB_OK;
 }
 
-extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
+static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,
                     const nvb_seed_extend_params* P, uint32_t hit_capacity,
                     int32_t* d_best_score, uint32_t* d_best_pos,
                     uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
                     int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    const nvb_best_alignment_out* BA,
                     void* d_temp, size_t* temp_bytes, void* stream)
 {
+    if (BA && (!BA->d_ops || !BA->d_n_ops || !BA->d_begin || BA->max_ops == 0)) return NVB_E_INVALID;
     if (!valid_fmindex(fmi) || !fmi->d_ssa || !d_genome || !valid_strset(reads) || !P || !temp_bytes) return NVB_E_INVALID;
     if (reads->bits == 8) return NVB_E_UNSUPPORTED;
     if (P->seed_len == 0 || P->seed_interval == 0 || P->max_seed_hits == 0) return NVB_E_INVALID;
@@ -352,6 +383,18 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
     }
     char* scan_tmp  = tc.take<char>(scan_bytes);
     char* gotoh_tmp = tc.take<char>(gotoh_bytes);
+    // best-alignment traceback: per-read job arrays + the traceback's own temp (direction matrices)
+    uint32_t *bp_off = nullptr, *bp_len = nullptr, *bt_off = nullptr, *bt_len = nullptr; int32_t* b_score = nullptr;
+    uint2 *b_sink = nullptr, *b_source = nullptr; char* tb_tmp = nullptr; size_t tb_bytes = 0;
+    if (BA) {
+        bp_off = tc.take<uint32_t>(n_reads); bp_len = tc.take<uint32_t>(n_reads);
+        bt_off = tc.take<uint32_t>(n_reads); bt_len = tc.take<uint32_t>(n_reads);
+        b_score = tc.take<int32_t>(n_reads); b_sink = tc.take<uint2>(n_reads); b_source = tc.take<uint2>(n_reads);
+        const int r = nvb_banded_gotoh_traceback(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, n_reads,
+                                                 nullptr, nullptr, nullptr, nullptr, BA->max_ops, nullptr, nullptr, &tb_bytes, stream);
+        if (r != NVB_E_TEMP_SIZE && r != NVB_OK) return r;
+        tb_tmp = tc.take<char>(tb_bytes);
+    }
     const size_t need = tc.total();
     if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
     if (n_reads == 0) return NVB_OK;
@@ -442,9 +485,49 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
         pipe_export_hits_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, t_off, t_len, d_hit_read, (uint2*)d_hit_window);
         NVB_LAUNCH_CHECK();
     }
+    if (BA) {
+        const uint32_t rgrid = (n_reads + 255) / 256;
+        pipe_best_jobs_kernel<<<rgrid, 256, 0, s>>>(g, best_key, hit_string, p_off, p_len, t_off, t_len, bp_off, bp_len, bt_off, bt_len, BA->d_strand);
+        NVB_LAUNCH_CHECK();
+        pats.d_words = str_words; pats.d_offsets = bp_off; pats.d_lengths = bp_len;
+        txts.d_words = d_genome;  txts.d_offsets = bt_off; txts.d_lengths = bt_len;
+        size_t tbb = tb_bytes;
+        const int r = nvb_banded_gotoh_traceback(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, n_reads,
+                                                 b_score, (nvb_uint2*)b_sink, (nvb_uint2*)b_source, BA->d_ops, BA->max_ops, BA->d_n_ops,
+                                                 tb_tmp, &tbb, stream);
+        if (r != NVB_OK) return r;
+        pipe_best_begin_kernel<<<rgrid, 256, 0, s>>>(g, best_key, bt_off, b_source, BA->d_n_ops, (uint2*)BA->d_begin);
+        NVB_LAUNCH_CHECK();
+    }
     if (!dedup) NVB_CUDA_TRY(cudaMemcpyAsync(counts + 2, counts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     NVB_STAGE(7);
     g_stage_ev_valid = true;
     return NVB_OK;
+}
+
+extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_reads,
+                    const nvb_seed_extend_params* P, uint32_t hit_capacity,
+                    int32_t* d_best_score, uint32_t* d_best_pos,
+                    uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
+                    int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    void* d_temp, size_t* temp_bytes, void* stream)
+{
+    return seed_extend_impl(fmi, d_genome, reads, n_reads, P, hit_capacity, d_best_score, d_best_pos, d_n_hits, d_hit_read, d_hit_window,
+                            d_hit_score, d_hit_sink, nullptr, d_temp, temp_bytes, stream);
+}
+
+extern "C" int nvb_seed_extend_traceback(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_reads,
+                    const nvb_seed_extend_params* P, uint32_t hit_capacity,
+                    int32_t* d_best_score, uint32_t* d_best_pos,
+                    uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
+                    int32_t* d_hit_score, nvb_uint2* d_hit_sink,
+                    const nvb_best_alignment_out* best_alignment,
+                    void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!best_alignment) return NVB_E_INVALID;
+    return seed_extend_impl(fmi, d_genome, reads, n_reads, P, hit_capacity, d_best_score, d_best_pos, d_n_hits, d_hit_read, d_hit_window,
+                            d_hit_score, d_hit_sink, best_alignment, d_temp, temp_bytes, stream);
 }

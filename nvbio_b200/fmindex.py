@@ -148,6 +148,21 @@ def match(fmi: FMIndexDevice, queries: PackedStringSet, flags: int = 0, out: Opt
     return out
 
 
+def match_approx(fmi: FMIndexDevice, queries: PackedStringSet, exact_len: int, find_exact: bool = True, max_out: int = 64, flags: int = 0):
+    """nvBowtie's map<find_exact> (one substitution after the first exact_len consumed symbols) for a string set.
+    Returns (ranges int32[n,max_out,2], counts int32[n], range_sums int32[n])."""
+    n = queries.count
+    dev = fmi.device
+    ranges = torch.zeros((n, max_out, 2), dtype=torch.int32, device=dev)
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    sums = torch.empty(n, dtype=torch.int32, device=dev)
+    s, q = fmi.struct(), queries.struct()
+    check(lib().nvb_fm_match_approx(C.byref(s), C.byref(q), C.c_uint32(n), C.c_uint32(flags), C.c_uint32(exact_len),
+                                    C.c_int(1 if find_exact else 0), C.c_uint32(max_out), C.c_void_p(ranges.data_ptr()),
+                                    C.c_void_p(counts.data_ptr()), C.c_void_p(sums.data_ptr()), _stream()), "nvb_fm_match_approx")
+    return ranges, counts, sums
+
+
 def locate(fmi: FMIndexDevice, rows: torch.Tensor) -> torch.Tensor:
     """nvbio::locate(fm_index, row) for an array of SA rows"""
     n = rows.numel()

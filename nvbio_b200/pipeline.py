@@ -3,7 +3,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import Optional
 import torch
-from ._lib import lib, check, SeedExtendParamsStruct
+from ._lib import lib, check, SeedExtendParamsStruct, BestAlignmentOutStruct
 from .strings import PackedStringSet
 from .fmindex import FMIndexDevice
 from . import aln
@@ -34,7 +34,7 @@ class SeedExtendWorkspace:
     """pre-allocated outputs + temp storage for repeated calls on equally-shaped batches"""
 
     def __init__(self, fmi: FMIndexDevice, genome: torch.Tensor, reads: PackedStringSet, params: SeedExtendParams,
-                 hit_capacity: int, keep_hits: bool = False):
+                 hit_capacity: int, keep_hits: bool = False, traceback: bool = False):
         dev = fmi.device
         n = reads.count
         self.best_score = torch.empty(n, dtype=torch.int32, device=dev)
@@ -47,6 +47,14 @@ class SeedExtendWorkspace:
             self.hit_window = torch.empty((hit_capacity, 2), dtype=torch.int32, device=dev)
             self.hit_score = torch.empty(hit_capacity, dtype=torch.int32, device=dev)
             self.hit_sink = torch.empty((hit_capacity, 2), dtype=torch.int32, device=dev)
+        # optional alignment (CIGAR ops, begin, strand) of every read's best hit
+        self.best_ops = self.best_n_ops = self.best_begin = self.best_strand = None
+        self.max_ops = reads.length + params.band_len + 1
+        if traceback:
+            self.best_ops = torch.zeros((n, self.max_ops), dtype=torch.uint8, device=dev)
+            self.best_n_ops = torch.zeros(n, dtype=torch.int32, device=dev)
+            self.best_begin = torch.empty((n, 2), dtype=torch.int32, device=dev)
+            self.best_strand = torch.empty(n, dtype=torch.uint8, device=dev)
         tb = C.c_size_t(0)
         r = _call(fmi, genome, reads, params, self, None, tb)
         if r != -2:
@@ -61,6 +69,14 @@ def _p(t):
 
 def _call(fmi, genome, reads, params, ws, temp, tb):
     s, rd, ps = fmi.struct(), reads.struct(), params.struct()
+    if ws.best_ops is not None:
+        ba = BestAlignmentOutStruct()
+        ba.d_ops, ba.max_ops, ba.d_n_ops = ws.best_ops.data_ptr(), ws.max_ops, ws.best_n_ops.data_ptr()
+        ba.d_begin, ba.d_strand = ws.best_begin.data_ptr(), ws.best_strand.data_ptr()
+        return lib().nvb_seed_extend_traceback(C.byref(s), _p(genome), C.byref(rd), C.c_uint32(reads.count), C.byref(ps),
+                                               C.c_uint32(ws.hit_capacity), _p(ws.best_score), _p(ws.best_pos), _p(ws.n_hits),
+                                               _p(ws.hit_read), _p(ws.hit_window), _p(ws.hit_score), _p(ws.hit_sink), C.byref(ba),
+                                               _p(temp), C.byref(tb), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     return lib().nvb_seed_extend(C.byref(s), _p(genome), C.byref(rd), C.c_uint32(reads.count), C.byref(ps),
                                  C.c_uint32(ws.hit_capacity), _p(ws.best_score), _p(ws.best_pos), _p(ws.n_hits),
                                  _p(ws.hit_read), _p(ws.hit_window), _p(ws.hit_score), _p(ws.hit_sink),
@@ -68,12 +84,15 @@ def _call(fmi, genome, reads, params, ws, temp, tb):
 
 
 def seed_extend(fmi: FMIndexDevice, genome: torch.Tensor, reads: PackedStringSet, params: SeedExtendParams,
-                workspace: Optional[SeedExtendWorkspace] = None, hit_capacity: Optional[int] = None, keep_hits: bool = False):
-    """returns the workspace: .best_score[n], .best_pos[n], .n_hits[2] = (kept, total), optional per-hit arrays"""
+                workspace: Optional[SeedExtendWorkspace] = None, hit_capacity: Optional[int] = None, keep_hits: bool = False,
+                traceback: bool = False):
+    """returns the workspace: .best_score[n], .best_pos[n], .n_hits[3] = (kept, total, distinct jobs), optional per-hit
+    arrays, and with traceback=True the alignment of every read's best hit (.best_ops END->START, .best_n_ops,
+    .best_begin = (genome start, read start), .best_strand)"""
     if workspace is None:
         if hit_capacity is None:
             hit_capacity = 32 * reads.count + 1024
-        workspace = SeedExtendWorkspace(fmi, genome, reads, params, hit_capacity, keep_hits)
+        workspace = SeedExtendWorkspace(fmi, genome, reads, params, hit_capacity, keep_hits, traceback)
     tb = C.c_size_t(workspace.temp_bytes)
     check(_call(fmi, genome, reads, params, workspace, workspace.temp, tb), "nvb_seed_extend")
     return workspace

@@ -54,6 +54,19 @@ void hh_fm_match(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32
     }
 }
 
+void hh_fm_match_approx(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary,
+                        const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len, uint32_t nq,
+                        uint32_t flags, uint32_t exact_len, int find_exact, uint32_t max_out, uint32_t* out_xy, uint32_t* counts, uint32_t* sums) {
+    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary);
+    for (uint32_t i = 0; i < nq; ++i) {
+        uint32_t sum = 0, cnt = 0;
+#define CALL(B, E) cnt = fm_map_approx_one<B, E>(f, words, off[i], len[i], exact_len, flags, find_exact != 0, (uint2*)out_xy + (size_t)i * max_out, max_out, sum)
+        NVB_DISPATCH_STREAM(bits, be, CALL);
+#undef CALL
+        counts[i] = cnt; sums[i] = sum;
+    }
+}
+
 void hh_fm_locate(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
                   const uint32_t* rows, uint32_t nq, uint32_t* out, uint32_t sa_interval) {
     const FmIndex f = mk(bwt_occ, ssa, L2, n, primary, sa_interval);

@@ -225,3 +225,35 @@ def test_sampled_sa_interval(O, interval):
     assert np.array_equal(host_u32(fmi.ssa), want_ssa)
     rows = rng.integers(0, n + 1, 5000).astype(np.uint32); rows[:3] = (0, ref.primary, n)
     assert np.array_equal(host_u32(nb.locate(fmi, dev_u32(rows))), O.locate(ref, rows))
+
+
+def test_match_approx_one_mismatch(O):
+    """nvBowtie's map<find_exact> core (rank4-based one-substitution search) against its characterisation through the pinned
+    exact match(): every single-substitution variant in push order, then the exact match"""
+    from tests.test_host_core import approx_expected
+    rng = np.random.default_rng(31)
+    n = 60000
+    text = rng.integers(0, 4, n).astype(np.uint8)
+    idx = O.build_index(text)
+    fmi = upload(idx)
+    nq = 1500
+    lens = rng.integers(10, 23, nq).astype(np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
+    for i in range(nq):
+        L = int(lens[i]); st = int(rng.integers(0, n - L))
+        cons = text[st:st + L][::-1].copy()             # consumed order = reversed text order
+        if i % 3:
+            cons[int(rng.integers(L // 2, L))] ^= 2
+        if i % 23 == 0:
+            cons[int(rng.integers(0, L))] = 4
+        q[offs[i]:offs[i] + L] = cons
+    qs = PackedStringSet.from_symbols(q, offs, lens, bits=4, big_endian=True)
+    for exact_len, find_exact in ((10, True), (0, False)):
+        want = approx_expected(O, idx, q, offs, lens, exact_len, find_exact, True, False)
+        ranges, counts, sums = nb.match_approx(fmi, qs, exact_len, find_exact, max_out=80, flags=nb.MATCH_FORWARD_ORDER)
+        r, c, s = host_u32(ranges), host_u32(counts), host_u32(sums)
+        for i in range(nq):
+            got = [tuple(x) for x in r[i, :c[i]]]
+            assert got == want[i], (i, exact_len)
+            assert s[i] == sum(y - x + 1 for x, y in want[i])

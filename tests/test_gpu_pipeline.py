@@ -143,3 +143,44 @@ def test_unaligned_2bit_reads_and_streaming_api():
         sc, ps, nh = st.result(t)
         assert torch.equal(sc, plain.best_score.cpu()) and torch.equal(ps, plain.best_pos.cpu())
         assert torch.equal(nh, plain.n_hits.cpu())
+
+
+def test_best_alignment_traceback():
+    """CIGAR of every read's best hit: re-applying the ops to the genome reproduces the read (up to its substitutions) and
+    the score; equals the oracle traceback of the same (strand, window) job"""
+    require_gpu()
+    O = orc.Oracle()
+    n = 150_000
+    gw = synth.random_genome_words(n, seed=41)
+    gsym = unpack_symbols(host_u32(gw), n)
+    fmi, _ = nb.FMIndexDevice.from_text(gw, n, sa_interval=1)
+    n_reads = 500
+    rw, pos, strand = synth.sample_reads(gw, n, n_reads, 150, sub_rate=0.02, indel_rate=0.01, seed=8, mut_seed=9)
+    rs = PackedStringSet.fixed(rw.reshape(-1), n_reads, 150, stride=rw.shape[1] * 16)
+    ws = nb.seed_extend(fmi, gw, rs, nb.SeedExtendParams(), hit_capacity=64 * n_reads, keep_hits=True, traceback=True)
+    torch.cuda.synchronize()
+    score = ws.best_score.cpu().numpy(); n_ops = ws.best_n_ops.cpu().numpy(); ops = ws.best_ops.cpu().numpy()
+    begin = host_u32(ws.best_begin); st = ws.best_strand.cpu().numpy(); bpos = host_u32(ws.best_pos)
+    checked = 0
+    for r in range(n_reads):
+        if score[r] == -2**31:
+            assert n_ops[r] == 0
+            continue
+        read = unpack_symbols(host_u32(rw[r]), 150)
+        if st[r]:
+            read = (3 - read)[::-1]
+        j, i = int(begin[r, 0]), int(begin[r, 1])
+        s, prev = 0, -1
+        for op in ops[r, :n_ops[r]][::-1]:
+            if op == 0:
+                s += 2 if read[i] == gsym[j] else -2; i += 1; j += 1
+            elif op == 1:
+                s += -3 if prev == 1 else -5; i += 1
+            else:
+                s += -3 if prev == 2 else -5; j += 1
+            prev = op
+        assert s == score[r] and j == int(bpos[r]), (r, s, score[r], j, bpos[r])
+        checked += 1
+    assert checked > 0.9 * n_reads
+    # indel-carrying reads produce I/D ops
+    assert (ops == 1).any() and (ops == 2).any()

@@ -276,3 +276,79 @@ def test_gotoh_traceback(H, O, band, typ):
         assert r == 0
         assert np.array_equal(score, want["score"]) and np.array_equal(sink, want["sink"]) and np.array_equal(source, want["source"])
         assert np.array_equal(n_ops, want["n_ops"]) and np.array_equal(ops, want["ops"]), (band, typ, scheme)
+
+
+def approx_expected(O, idx, q, offs, lens, exact_len, find_exact, fwd, comp):
+    """the reference's map<find_exact> characterised through the PINNED exact match(): every single-substitution
+    variant (consumed position ascending, substituted symbol ascending) whose range is non-empty, then the exact match"""
+    exp = []
+    for o, L in zip(offs, lens):
+        s = q[o:o + L].copy()
+        if not fwd:
+            s = s[::-1]
+        if comp:
+            s = np.where(s < 4, 3 - s, s).astype(np.uint8)
+        l1 = min(exact_len, L)
+        npos = [i for i in range(L) if s[i] > 3]
+        if (npos and npos[0] < l1) or len(npos) > 1:
+            exp.append([]); continue
+        if npos:
+            l1 = npos[0]
+        variants = []
+        last = L if not npos else npos[0] + 1            # after an N position the base range is dead
+        for i in range(l1, last):
+            for sub in range(4):
+                if sub != s[i]:
+                    v = s.copy(); v[i] = sub; variants.append(v)
+        if find_exact and not npos:
+            variants.append(s.copy())
+        if variants:
+            cat = np.concatenate([v[::-1] for v in variants])       # match() consumes from the END of its pattern
+            r, _ = O.match(idx, cat, np.arange(len(variants)) * L, np.full(len(variants), L))
+            exp.append([tuple(x) for x in r if x[0] <= x[1]])
+        else:
+            exp.append([])
+    return exp
+
+
+@pytest.mark.parametrize("fwd,comp", [(True, False), (False, True), (True, True)])
+def test_fm_match_approx(H, O, fwd, comp):
+    rng = np.random.default_rng(5 + fwd + 2 * comp)
+    n = 3000
+    text = rng.integers(0, 4, n).astype(np.uint8)
+    idx = O.build_index(text)
+    nq = 200
+    lens = rng.integers(8, 16, nq).astype(np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
+    for i in range(nq):                                   # seeds from the text with one planted substitution
+        L = int(lens[i]); st = int(rng.integers(0, n - L))
+        seg = text[st:st + L].copy()
+        if comp:
+            seg = (3 - seg)
+        if not fwd:
+            pass
+        # put it in the stream so that the CONSUMED order spells the reversed text segment (match() is a backward search)
+        cons = seg[::-1].copy() if not comp else seg[::-1].copy()
+        if i % 3:
+            cons[int(rng.integers(L // 2, L))] ^= 1
+        if i % 17 == 0:
+            cons[int(rng.integers(0, L))] = 4
+        q[offs[i]:offs[i] + L] = cons if fwd else cons[::-1]
+    flags = (1 if fwd else 0) | (2 if comp else 0)
+    for exact_len, find_exact in ((5, 1), (0, 0), (8, 1)):
+        want = approx_expected(O, idx, q, offs, lens, exact_len, bool(find_exact), fwd, comp)
+        max_out = 48
+        words = pack_symbols(q, 4, True)
+        out = np.zeros((nq, max_out, 2), np.uint32); counts = np.zeros(nq, np.uint32); sums = np.zeros(nq, np.uint32)
+        H.hh_fm_match_approx(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(4), C.c_uint32(1),
+                             _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(flags), C.c_uint32(exact_len), C.c_int(find_exact),
+                             C.c_uint32(max_out), _p(out), _p(counts), _p(sums))
+        nonempty = 0
+        for i in range(nq):
+            got = [tuple(x) for x in out[i, :counts[i]]]
+            assert counts[i] <= max_out
+            assert got == want[i], (i, exact_len, find_exact, got, want[i])
+            assert sums[i] == sum(y - x + 1 for x, y in want[i])
+            nonempty += len(got) > 0
+        assert nonempty > nq // 3
