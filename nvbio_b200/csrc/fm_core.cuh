@@ -63,11 +63,16 @@ __host__ __device__ __forceinline__ uint32_t nvb_popc(uint32_t x) {
 #endif
 }
 
+// L2 fetch granularity of the block gathers: the default 256-bit load pulls the whole 128-byte line from DRAM (4 sectors
+// per gather, measured: profiles/r01_ubench_gather_variants.txt); ".L2::64B" halves the DRAM bytes at unchanged speed.
+#ifndef NVB_FM_LD_QUAL
+#define NVB_FM_LD_QUAL ".L2::64B"
+#endif
 __host__ __device__ __forceinline__ FmBlock load_block(const FmBlock* __restrict__ blocks, uint32_t k) {
 #ifdef __CUDA_ARCH__
     // one 256-bit read-only load (SASS: LDG.E.ENL2.256.CONSTANT); volatile keeps paired loads adjacent
     FmBlock b;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" NVB_FM_LD_QUAL ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(b.bwt[0]), "=r"(b.bwt[1]), "=r"(b.bwt[2]), "=r"(b.bwt[3]),
                    "=r"(b.occ[0]), "=r"(b.occ[1]), "=r"(b.occ[2]), "=r"(b.occ[3])
                  : "l"(blocks + k));
@@ -81,7 +86,7 @@ __host__ __device__ __forceinline__ FmBlock load_block(const FmBlock* __restrict
 __host__ __device__ __forceinline__ void load_block_if(FmBlock& b, const FmBlock* __restrict__ blocks, uint32_t k, bool pred) {
 #ifdef __CUDA_ARCH__
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
-                 "@p ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 "@p ld.global.nc" NVB_FM_LD_QUAL ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
                  : "+r"(b.bwt[0]), "+r"(b.bwt[1]), "+r"(b.bwt[2]), "+r"(b.bwt[3]),
                    "+r"(b.occ[0]), "+r"(b.occ[1]), "+r"(b.occ[2]), "+r"(b.occ[3])
                  : "l"(blocks + k), "r"((uint32_t)pred));
