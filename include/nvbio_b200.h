@@ -219,7 +219,7 @@ int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n, uint32_t* d_bwt, uint32
                      void* d_temp, size_t* temp_bytes, void* stream);
 
 /* Fill d_ktab[4^k] with match() of every k-mer (level by level: 4^k * 4/3 LF steps in total).
- * k in [1,14].  fmi->d_ktab / ktab_k are ignored on input. */
+ * k in [1,15].  fmi->d_ktab / ktab_k are ignored on input. */
 int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

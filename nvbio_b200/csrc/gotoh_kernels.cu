@@ -76,22 +76,42 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
             return;
         }
 
-        // stage the PRMT selectors of this thread's two text windows (own shared-memory column: no barrier needed)
+        // stage the PRMT selectors of this thread's two text windows (own shared-memory column: no barrier needed).
+        // Word-wise: the 16 symbols starting at any offset are a funnel shift of two consecutive words, and the loads
+        // of successive words are independent, so they overlap instead of forming a chain of dependent round trips.
         {
             const uint32_t t0 = str_off(b.txt, a0), t1 = str_off(b.txt, a1);
-            if (b.txt.big_endian) {
-                SymReader<2, true> r0(b.txt.words), r1(b.txt.words);
-                for (uint32_t t = 0; t < L; ++t) {
-                    const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
-                    const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
-                    my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+            const uint32_t* __restrict__ w = b.txt.words;
+            const bool be = b.txt.big_endian != 0;
+            const uint32_t w0 = t0 >> 4, w1 = t1 >> 4;                         // first stream word of each window
+            const uint32_t sh0 = 2u * (t0 & 15u), sh1 = 2u * (t1 & 15u);
+            const uint32_t last0 = (t0 + N0 - 1u) >> 4, last1 = (t1 + N1 - 1u) >> 4;   // last word holding a window symbol
+            const uint32_t nw = (L + 15u) >> 4;
+            uint32_t p0 = w[w0], p1 = w[w1];
+#pragma unroll 2
+            for (uint32_t k = 0; k < nw; ++k) {
+                // never touch a word beyond the window's last one (symbols past N are defined as 0 below anyway)
+                const uint32_t n0 = (w0 + k + 1u <= last0) ? w[w0 + k + 1u] : 0u;
+                const uint32_t n1 = (w1 + k + 1u <= last1) ? w[w1 + k + 1u] : 0u;
+                uint32_t c0, c1;
+                if (be) {
+                    c0 = sh0 ? ((p0 << sh0) | (n0 >> (32u - sh0))) : p0;
+                    c1 = sh1 ? ((p1 << sh1) | (n1 >> (32u - sh1))) : p1;
+                } else {
+                    c0 = sh0 ? ((p0 >> sh0) | (n0 << (32u - sh0))) : p0;
+                    c1 = sh1 ? ((p1 >> sh1) | (n1 << (32u - sh1))) : p1;
                 }
-            } else {
-                SymReader<2, false> r0(b.txt.words), r1(b.txt.words);
-                for (uint32_t t = 0; t < L; ++t) {
-                    const uint32_t g0 = (t < N0) ? r0.get(t0 + t) : 0u;
-                    const uint32_t g1 = (t < N1) ? r1.get(t1 + t) : 0u;
-                    my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+                p0 = n0; p1 = n1;
+                const uint32_t first = k << 4;
+#pragma unroll
+                for (uint32_t s16 = 0; s16 < 16u; ++s16) {
+                    const uint32_t t = first + s16;
+                    if (t < L) {
+                        const uint32_t shf = be ? (30u - 2u * s16) : (2u * s16);
+                        const uint32_t g0 = (t < N0) ? ((c0 >> shf) & 3u) : 0u;
+                        const uint32_t g1 = (t < N1) ? ((c1 >> shf) & 3u) : 0u;
+                        my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+                    }
                 }
             }
         }
