@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
-    ap.add_argument("--ktab-k", type=int, default=14, help="k of the k-mer range table (0 = none)")
+    ap.add_argument("--ktab-k", type=int, default=15, help="k of the k-mer range table (0 = none)")
     ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 kernel-level measurements")

@@ -503,3 +503,59 @@ void orc_banded_traceback(int B, int type, const orc_scheme* S,
         n_ops[i] = orc_banded_traceback_one(B, type, S, pat + p_off[i], p_len[i], txt + t_off[i], t_len[i],
                                             &score[i], &sink_xy[2 * i], &source_xy[2 * i], ops + (size_t)i * max_ops, max_ops, &clips[2 * i]);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * full-matrix Gotoh score: aln::alignment_score with GotohAligner<TYPE,scheme,PatternBlockingTag>
+ * (nvbio/alignment/gotoh/gotoh_inl.h:459-960; first column :75-89, top row :688-696, infimum :665).
+ * Rows r = 1..N follow the TEXT, columns c = 1..M the PATTERN; E runs along the pattern, F along the text, both with
+ * the PATTERN gap costs; the first column uses the TEXT gap costs (GLOBAL only).  sink = (text end, pattern end).
+ * LOCAL reports every cell stripe by stripe (stripes of 8 pattern columns, gotoh_bandlen_selector :1491-1495), inside
+ * a stripe row by row, so ties resolve to the last maximal cell in (stripe, row, column) order; SEMI_GLOBAL reports
+ * H[r][M] for every row; GLOBAL reports H[N][M].  Requires M >= 1, N >= 1.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_gotoh_full_one(int type, const orc_scheme* S, const u8* P, u32 M, const u8* T, u32 N,
+                        i32* out_score, u32* out_x, u32* out_y)
+{
+    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    const i32 Go = S->pattern_gap_open, Ge = S->pattern_gap_ext;
+    const i32 INF = SHRT_MIN - (Go < Ge ? Go : Ge);
+    const size_t W = (size_t)M + 1;
+    i32* H = (i32*)malloc(sizeof(i32) * (N + 1) * W);
+    i32* E = (i32*)malloc(sizeof(i32) * (N + 1) * W);
+    i32* F = (i32*)malloc(sizeof(i32) * (N + 1) * W);
+    for (u32 c = 0; c <= M; ++c) { H[c] = (type != 1) ? (c > 0 ? Go + Ge * (i32)(c - 1) : 0) : 0; F[c] = INF; E[c] = INF; }
+    for (u32 r = 1; r <= N; ++r)
+    {
+        H[r * W] = (type == 0) ? S->text_gap_open + S->text_gap_ext * (i32)(r - 1) : 0;
+        E[r * W] = (type == 1) ? 0 : INF;
+        F[r * W] = INF;
+        for (u32 c = 1; c <= M; ++c)
+        {
+            const i32 f = imax(F[(r - 1) * W + c] + Ge, H[(r - 1) * W + c] + Go);
+            const i32 e = imax(E[r * W + c - 1] + Ge, H[r * W + c - 1] + Go);
+            const i32 d = H[(r - 1) * W + c - 1] + ((T[r - 1] == P[c - 1]) ? S->match : S->mismatch);
+            i32 h = imax(imax(e, f), d);
+            if (type == 1) h = imax(h, 0);
+            F[r * W + c] = f; E[r * W + c] = e; H[r * W + c] = h;
+        }
+    }
+    if (type == 1)
+    {
+        for (u32 b = 0; b < M; b += 8)
+            for (u32 r = 1; r <= N; ++r)
+                for (u32 c = b + 1; c <= b + 8 && c <= M; ++c)
+                    sink_report(&best, &bx, &by, H[r * W + c], r, c);
+    }
+    else if (type == 2) { for (u32 r = 1; r <= N; ++r) sink_report(&best, &bx, &by, H[r * W + M], r, M); }
+    else sink_report(&best, &bx, &by, H[N * W + M], N, M);
+    free(H); free(E); free(F);
+    *out_score = best; *out_x = bx; *out_y = by;
+}
+
+void orc_gotoh_full(int type, const orc_scheme* S,
+                    const u8* pat, const u32* p_off, const u32* p_len,
+                    const u8* txt, const u32* t_off, const u32* t_len, u32 n, i32* score, u32* sink_x, u32* sink_y)
+{
+    for (u32 i = 0; i < n; ++i)
+        orc_gotoh_full_one(type, S, pat + p_off[i], p_len[i], txt + t_off[i], t_len[i], &score[i], &sink_x[i], &sink_y[i]);
+}

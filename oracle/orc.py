@@ -291,3 +291,34 @@ def dna(s):
 
 
 Oracle.banded_traceback = _oracle_traceback
+
+
+def _full_args(pat, p_off, p_len, txt, t_off, t_len):
+    pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+    p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+    t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+    n = len(p_off)
+    return pat, p_off, p_len, txt, t_off, t_len, n, np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+
+
+def _oracle_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len):
+    """full-matrix Gotoh: (score, sink_x = text end, sink_y = pattern end)"""
+    pat, p_off, p_len, txt, t_off, t_len, n, score, sx, sy = _full_args(pat, p_off, p_len, txt, t_off, t_len)
+    if len(scheme) == 4:
+        scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+    s = np.array(scheme, dtype=np.int32)
+    self.lib.orc_gotoh_full(C.c_int(typ), _p(s), _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n),
+                            _p(score), _p(sx), _p(sy))
+    return score, sx, sy
+
+
+def _ref_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len):
+    pat, p_off, p_len, txt, t_off, t_len, n, score, sx, sy = _full_args(pat, p_off, p_len, txt, t_off, t_len)
+    r = self.lib.ref_gotoh_full(C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]), C.c_int(scheme[2]), C.c_int(scheme[3]),
+                                _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+    assert r == 0
+    return score, sx, sy
+
+
+Oracle.gotoh_full = _oracle_full
+Ref.gotoh_full = _ref_full

@@ -144,9 +144,49 @@ int run_traceback_type(int type, const aln::SimpleGotohScheme s,
     return -1;
 }
 
+template <aln::AlignmentType TYPE>
+void run_full(const aln::SimpleGotohScheme scheme,
+              const uint8* pat, const uint32* p_off, const uint32* p_len,
+              const uint8* txt, const uint32* t_off, const uint32* t_len,
+              uint32 n, int32* score, uint32* sink_x, uint32* sink_y)
+{
+    #pragma omp parallel for schedule(dynamic,16)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        aln::BestSink<int32> sink;
+        aln::alignment_score<4096u>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),           // default algorithm tag = PatternBlockingTag
+            str_view( p_len[i], pat + p_off[i] ),
+            aln::trivial_quality_string(),
+            str_view( t_len[i], txt + t_off[i] ),
+            INT_MIN,
+            sink );
+        score[i]  = sink.score;
+        sink_x[i] = sink.sink.x;
+        sink_y[i] = sink.sink.y;
+    }
+}
+
 } // anonymous namespace
 
 extern "C" {
+
+// full-matrix Gotoh score: aln::alignment_score<MAX_TEXT_LEN>(GotohAligner<TYPE,SimpleGotohScheme>, ...)
+// (nvbio/alignment/alignment_inl.h:95-125 -> gotoh/gotoh_inl.h:459-960, PatternBlockingTag); texts up to 4096 symbols
+int ref_gotoh_full(int type, int match, int mismatch, int gap_open, int gap_ext,
+                   const uint8* pat, const uint32* p_off, const uint32* p_len,
+                   const uint8* txt, const uint32* t_off, const uint32* t_len,
+                   uint32 n, int32* score, uint32* sink_x, uint32* sink_y)
+{
+    const aln::SimpleGotohScheme s( match, mismatch, gap_open, gap_ext );
+    switch (type)
+    {
+    case 0: run_full<aln::GLOBAL>     ( s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y ); return 0;
+    case 1: run_full<aln::LOCAL>      ( s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y ); return 0;
+    case 2: run_full<aln::SEMI_GLOBAL>( s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y ); return 0;
+    }
+    return -1;
+}
 
 // banded Gotoh traceback (aln::banded_alignment_traceback<BAND,1024,32>, nvbio/alignment/banded_inl.h:352-489):
 // ops are the backtracer's pushes in END -> START order (0 = SUBSTITUTION 'M', 1 = INSERTION 'I', 2 = DELETION 'D'),

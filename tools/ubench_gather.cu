@@ -83,5 +83,15 @@ int main() {
     run<4, 4>(tab, big_blocks - 1, out, "DRAM  2 x v4 no_allocate, granularity 32");
     run<0, 8>(tab, small_blocks - 1, out, "L2    v8 (LDG.256), 64 MiB table");
     run<2, 8>(tab, small_blocks - 1, out, "L2    2 x v4, 64 MiB table");
+    // table-size sweep (.L2::64B loads): where does the rate fall off -- L2 capacity (126 MB) or TLB reach?
+    cudaFree(tab);
+    Blk* big; const uint32_t sweep_blocks = 1u << 29;         // 16 GiB
+    if (cudaMalloc(&big, (size_t)sweep_blocks * sizeof(Blk)) == cudaSuccess) {
+        cudaMemset(big, 1, (size_t)sweep_blocks * sizeof(Blk));
+        for (uint32_t lg = 21; lg <= 29; ++lg) {
+            char what[64]; snprintf(what, sizeof(what), "sweep .L2::64B, %6u MiB table", (1u << lg) / 32768u);
+            run<1, 4>(big, (1u << lg) - 1, out, what);
+        }
+    }
     return 0;
 }
