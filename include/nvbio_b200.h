@@ -182,6 +182,16 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
                            int32_t* d_score, nvb_uint2* d_sink,
                            void* d_temp, size_t* temp_bytes, void* stream);
 
+/* Full-matrix (un-banded) Gotoh score: every pattern against the WHOLE of its text.
+ * d_score / d_sink = BestSink<int32>{score, (text end, pattern end)}; pattern and text lengths must be >= 1 and
+ * `patterns->length` / `texts->length` must bound them (<= 65535; the text bound sizes the boundary-column scratch).
+ * Replaces aln::alignment_score / aln::BatchedAlignmentScore<stream,DeviceThreadScheduler> with
+ * GotohAligner<TYPE,SimpleGotohScheme> (default PatternBlockingTag; nvbio/alignment/alignment_inl.h:95-125,
+ * gotoh/gotoh_inl.h:459-960, batched_inl.h:236-605) -- the DP sw-benchmark times (sw-benchmark.cu:592-641) and nvBowtie's
+ * opposite-mate scoring.  LOCAL ties resolve in the reference's (8-column stripe, row, column) order. */
+int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+                    int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream);
+
 /* Banded Gotoh traceback.  For i < n: score, sink (end cells) as nvb_banded_gotoh_score, plus the
  * source (start cells) and the alignment as the backtracer's pushes in END -> START order, one byte per op
  * (0 = SUBSTITUTION 'M', 1 = INSERTION 'I', 2 = DELETION 'D'; nvbio::aln::DirectionVector) at d_ops[i*max_ops ..];

@@ -159,3 +159,27 @@ def cigar(ops_row, n_ops: int) -> str:
     if prev is not None:
         out.append("%d%s" % (cnt, letters[prev]))
     return "".join(out)
+
+
+def batch_alignment_score(aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet):
+    """aln::batch_alignment_score(aligner, patterns, texts, sinks, DeviceThreadScheduler(), ...) with a Gotoh aligner: the
+    full-matrix DP of every pattern against its whole text (nvbio/alignment/batched_inl.h:984-1040).
+    Returns (scores int32[n], sinks int32[n,2] = (text end, pattern end))."""
+    L = lib()
+    n = patterns.count
+    dev = patterns.words.device
+    score = torch.empty(n, dtype=torch.int32, device=dev)
+    sink = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    tb = C.c_size_t(0)
+
+    def call(temp_ptr):
+        return L.nvb_gotoh_score(C.c_int(aligner.type), C.byref(sch), C.byref(p), C.byref(t), C.c_uint32(n),
+                                 C.c_void_p(score.data_ptr()), C.c_void_p(sink.data_ptr()), temp_ptr, C.byref(tb), _stream())
+    r = call(None)
+    if r != -2:
+        check(r, "nvb_gotoh_score(size query)")
+    temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
+    check(call(C.c_void_p(temp.data_ptr())), "nvb_gotoh_score")
+    return score, sink

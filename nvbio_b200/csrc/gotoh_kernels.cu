@@ -8,6 +8,7 @@
 //
 // The path is bound by integer issue rate, not memory: ~0.1 KB moved per 4,650 cell updates (B=31, M=150).
 #include "gotoh_core.cuh"
+#include "gotoh_full_core.cuh"
 
 namespace nvb {
 
@@ -123,6 +124,22 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
         if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
     }
+}
+
+// full-matrix Gotoh: one alignment per thread, 32-column register stripes, boundary column in HBM scratch laid out
+// [text row][alignment] so that a warp's accesses to one row are contiguous
+template <int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_full_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ col)
+{
+    const uint32_t n = batch_count(b);
+    const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
+    if (a >= n) return;
+    const SinkResult r = gotoh_full<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a),
+                                          b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a),
+                                          col + a, (size_t)b.n_max);
+    b.score[a] = r.score;
+    b.sink[a]  = make_uint2(r.x, r.y);
 }
 
 // traceback: one alignment per thread; DP with direction vectors into a per-alignment global scratch matrix
@@ -299,6 +316,35 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
 {
     if (!d_n) return NVB_E_INVALID;
     return banded_impl(band_len, type, scheme, patterns, d_quals, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
+}
+
+int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+                    int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
+    if (type < 0 || type > 2) return NVB_E_INVALID;
+    if (scheme->d_qual_table) return NVB_E_UNSUPPORTED;                 // quality tables: banded path only (for now)
+    if (texts->length > 65535u || patterns->length > 65535u) return NVB_E_UNSUPPORTED;
+    TempCarver tc(d_temp);
+    const bool need_col = patterns->length > (uint32_t)FULL_W;          // a single stripe needs no boundary column
+    int2* col = need_col ? tc.take<int2>((size_t)n * (texts->length ? texts->length : 1u)) : tc.take<int2>(1);
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    if (n == 0) return NVB_OK;
+    if (!d_score || !d_sink) return NVB_E_INVALID;
+    GotohBatch b;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = nullptr;
+    b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
+    const GotohScheme S = make_scheme(scheme);
+    const uint32_t grid = (n + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
+    cudaStream_t s = as_stream(stream);
+    switch (type) {
+    case NVB_GLOBAL:      gotoh_full_kernel<NVB_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+    case NVB_LOCAL:       gotoh_full_kernel<NVB_LOCAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+    default:              gotoh_full_kernel<NVB_SEMI_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+    }
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
 }
 
 int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* scheme,

@@ -49,6 +49,61 @@ static void write_file(const std::string& path, const T* p, size_t n)
 }
 
 // --------------------------------------------------------------------------------------------------
+// full-matrix Gotoh (the DP sw-benchmark times): n patterns of M symbols against n texts of N symbols (2-bit big-endian,
+// string i at symbols [i*stride, +len)), LOCAL, aln::batch_alignment_score with the DeviceThreadScheduler
+// --------------------------------------------------------------------------------------------------
+static int run_full(const std::string& dir)
+{
+    const std::vector<uint32> meta = read_file<uint32>(dir + "/meta.bin");    // n, M, Mstride, N, Nstride, match, mismatch, go, ge, reps
+    const uint32 n = meta[0], M = meta[1], Mstride = meta[2], N = meta[3], Nstride = meta[4];
+    const int32 s_match = (int32)meta[5], s_mm = (int32)meta[6], s_go = (int32)meta[7], s_ge = (int32)meta[8];
+    const uint32 reps = meta[9];
+    const std::vector<uint32> h_pat = read_file<uint32>(dir + "/pat_words.bin");
+    const std::vector<uint32> h_txt = read_file<uint32>(dir + "/txt_words.bin");
+    thrust::device_vector<uint32> d_pat(h_pat), d_txt(h_txt);
+    std::vector<uint2> h_pr(n), h_tr(n);
+    for (uint32 i = 0; i < n; ++i) { h_pr[i] = make_uint2(i * Mstride, i * Mstride + M); h_tr[i] = make_uint2(i * Nstride, i * Nstride + N); }
+    thrust::device_vector<uint2> d_pr(h_pr), d_tr(h_tr);
+    thrust::device_vector< aln::BestSink<int32> > d_sinks(n);
+
+    typedef nvbio::cuda::ldg_pointer<uint32>                    storage_it;
+    typedef PackedStream<storage_it, uint8, 2u, true>           stream_t;
+    typedef SparseStringSet<stream_t, const uint2*>             set_t;
+    const stream_t pat_stream( storage_it( thrust::raw_pointer_cast(d_pat.data()) ) );
+    const stream_t txt_stream( storage_it( thrust::raw_pointer_cast(d_txt.data()) ) );
+    const set_t patterns( n, pat_stream, thrust::raw_pointer_cast(d_pr.data()) );
+    const set_t texts   ( n, txt_stream, thrust::raw_pointer_cast(d_tr.data()) );
+
+    const aln::SimpleGotohScheme scheme( s_match, s_mm, s_go, s_ge );
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best_ms = 1e30f;
+    for (uint32 r = 0; r < reps + 1; ++r)
+    {
+        cudaEventRecord(e0);
+        aln::batch_alignment_score(
+            aln::make_gotoh_aligner<aln::LOCAL>( scheme ),
+            patterns, texts,
+            thrust::raw_pointer_cast(d_sinks.data()),
+            aln::DeviceThreadScheduler(),
+            M, N );
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+    std::vector< aln::BestSink<int32> > h_sinks(n);
+    cudaMemcpy(h_sinks.data(), thrust::raw_pointer_cast(d_sinks.data()), sizeof(aln::BestSink<int32>) * n, cudaMemcpyDeviceToHost);
+    std::vector<int32> score(n); std::vector<uint2> sink(n);
+    for (uint32 i = 0; i < n; ++i) { score[i] = h_sinks[i].score; sink[i] = h_sinks[i].sink; }
+    write_file(dir + "/ref_scores.bin", score.data(), n);
+    write_file(dir + "/ref_sinks.bin", sink.data(), n);
+    printf("{\"what\": \"reference CUDA batched_alignment_score_kernel (full-matrix LOCAL Gotoh, DeviceThreadScheduler), sm_100a\", \"n\": %u, \"M\": %u, \"N\": %u, "
+           "\"ms\": %.4f, \"gcups\": %.2f}\n", n, M, N, best_ms, double(n) * M * N / (best_ms * 1e-3) / 1e9);
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
 // banded Gotoh: n patterns of M symbols (2-bit big-endian, pattern i at symbols [i*Mstride, +M)) against
 // genome windows [begin,end)
 // --------------------------------------------------------------------------------------------------
@@ -182,5 +237,6 @@ int main(int argc, char** argv)
     const std::string mode = argv[1], dir = argv[2];
     if (mode == "banded") return run_banded(dir);
     if (mode == "fm")     return run_fm(dir);
+    if (mode == "full")   return run_full(dir);
     return 1;
 }

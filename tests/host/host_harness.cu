@@ -4,6 +4,7 @@
 // proper (thread mapping, shared-memory staging, todo lists) are covered by the -m gpu tests.
 #include "../../nvbio_b200/csrc/fm_core.cuh"
 #include "../../nvbio_b200/csrc/gotoh_core.cuh"
+#include "../../nvbio_b200/csrc/gotoh_full_core.cuh"
 #include <vector>
 
 using namespace nvb;
@@ -151,6 +152,22 @@ int hh_gotoh_generic(int band, int type, const int32_t* scheme6, const int32_t* 
     case 63: TYPE_SWITCH(63, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
     }
     return -1;
+}
+
+int hh_gotoh_full(int type, const int32_t* scheme6,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,
+                  int32_t* score, uint32_t* sx, uint32_t* sy) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr; S.one = 1u; S.keymul = 32u;
+    for (uint32_t a = 0; a < n; ++a) {
+        std::vector<int2> col(tlen[a] + 1);
+        SinkResult r;
+        if (type == 0)      r = gotoh_full<0>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1);
+        else if (type == 1) r = gotoh_full<1>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1);
+        else                r = gotoh_full<2>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1);
+        score[a] = r.score; sx[a] = r.x; sy[a] = r.y;
+    }
+    return 0;
 }
 
 int hh_gotoh_traceback(int band, int type, const int32_t* scheme6,

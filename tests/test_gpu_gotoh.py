@@ -198,3 +198,32 @@ def test_full_size_properties():
     P3 = PackedStringSet(words=P2.words, bits=2, big_endian=True, offsets=(perm * P2.stride).to(torch.int32), lengths=None, stride=0, length=L, count=10000)
     s3, k3 = aln.batch_banded_alignment_score(31, al, P3, T3)
     assert torch.equal(s3, s2[perm]) and torch.equal(k3, k2[perm])
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_full_matrix_score_vs_oracle(O, typ):
+    """nvb_gotoh_score (full DP, SURVEY 8f-3) == the oracle (pinned against aln::alignment_score): scores, sinks, LOCAL tie order;
+    ragged lengths from 1 symbol to several 32-column stripes, 2/4/8-bit packings"""
+    from tests.test_host_core import full_problems
+    rng = np.random.default_rng(900 + typ)
+    for scheme in ((2, -1, -2, -1), (2, -2, -5, -3), (0, -5, -8, -3)):
+        pr = full_problems(rng, 700, max_m=200, max_n=500)
+        want = O.gotoh_full(typ, scheme, *pr)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        for pbits, tbits, tbe in ((4, 2, True), (2, 8, False)):
+            P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=pbits, big_endian=True)
+            T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=tbits, big_endian=tbe)
+            s, k = aln.batch_alignment_score(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme)), P, T)
+            torch.cuda.synchronize()
+            k = host_u32(k)
+            assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, scheme, pbits, tbits)
+
+
+def test_full_matrix_reference_strings(O):
+    p, t = orc.dna(G1_P), orc.dna(G1_T)
+    for typ, want in ((0, (1, 20, 7)), (1, (13, 18, 7)), (2, (13, 18, 7))):
+        P = PackedStringSet.from_symbols(p, [0], [len(p)], bits=2, big_endian=True)
+        T = PackedStringSet.from_symbols(t, [0], [len(t)], bits=2, big_endian=True)
+        s, k = aln.batch_alignment_score(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -1, -1, -1)), P, T)
+        k = host_u32(k)
+        assert (int(s[0]), int(k[0, 0]), int(k[0, 1])) == want

@@ -352,3 +352,38 @@ def test_fm_match_approx(H, O, fwd, comp):
             assert sums[i] == sum(y - x + 1 for x, y in want[i])
             nonempty += len(got) > 0
         assert nonempty > nq // 3
+
+
+def full_problems(rng, n, max_m=130, max_n=400):
+    pats, txts, po, pl, to, tl = [], [], [], [], [], []
+    a = b = 0
+    for _ in range(n):
+        M = int(rng.integers(1, max_m + 1)); N = int(rng.integers(1, max_n + 1))
+        t = rng.integers(0, 4, N).astype(np.uint8)
+        if N > M and rng.random() < 0.7:
+            st = int(rng.integers(0, N - M + 1)); p = t[st:st + M].copy()
+            for _k in range(int(rng.integers(0, 5))):
+                p[int(rng.integers(0, M))] = rng.integers(0, 4)
+        else:
+            p = rng.integers(0, 4, M).astype(np.uint8)
+        pats.append(p); txts.append(t); po.append(a); pl.append(M); a += M; to.append(b); tl.append(N); b += N
+    return (np.concatenate(pats), np.array(po, np.uint32), np.array(pl, np.uint32), np.concatenate(txts), np.array(to, np.uint32), np.array(tl, np.uint32))
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_full(H, O, typ):
+    """full-matrix Gotoh per-thread routine (32-column stripes, four 8-column LOCAL trackers) == the oracle (== the reference's
+    aln::alignment_score, pinned in tests/test_oracle.py), scores and sinks incl. LOCAL tie order"""
+    rng = np.random.default_rng(500 + typ)
+    for scheme in ((2, -1, -2, -1), (2, -2, -5, -3), (0, -5, -8, -3), (2, -1, -1, -1)):
+        pr = full_problems(rng, 120)
+        want = O.gotoh_full(typ, scheme, *pr)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        for pbits, tbits, tbe in ((4, 2, 0), (2, 2, 1)):
+            pw, tw = pack_symbols(pat, pbits, True), pack_symbols(txt, tbits, bool(tbe))
+            n = len(p_off)
+            score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+            s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+            H.hh_gotoh_full(C.c_int(typ), _p(s6), _p(pw), C.c_uint32(pbits), C.c_uint32(1), _p(p_off), _p(p_len),
+                            _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+            assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, scheme)

@@ -178,3 +178,20 @@ def test_traceback_vs_reference_fresh(O, R):
             a, b = O.banded_traceback(band, typ, scheme, *pr), R.banded_traceback(band, typ, scheme, *pr)
             for k in a:
                 assert np.array_equal(a[k], b[k]), (band, typ, scheme, k)
+
+
+def test_full_matrix_gotoh_vs_reference(O, R):
+    """aln::alignment_score (full DP, PatternBlockingTag) == the C restatement: scores and sinks, every type; plus the values
+    of the reference's 7 x 20 test strings (alignment_test.cu:761-793)"""
+    from tests.test_host_core import full_problems
+    p, t = orc.dna(G1_P), orc.dna(G1_T)
+    for typ, want in ((0, (1, 20, 7)), (1, (13, 18, 7)), (2, (13, 18, 7))):
+        s, x, y = O.gotoh_full(typ, (2, -1, -1, -1), p, [0], [len(p)], t, [0], [len(t)])
+        assert (int(s[0]), int(x[0]), int(y[0])) == want
+    rng = np.random.default_rng(13)
+    for typ in (0, 1, 2):
+        for scheme in ((2, -1, -2, -1), (2, -2, -5, -3), (1, -3, -2, -4)):
+            pr = full_problems(rng, 100)
+            a, b = O.gotoh_full(typ, scheme, *pr), R.gotoh_full(typ, scheme, *pr)
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v), (typ, scheme)

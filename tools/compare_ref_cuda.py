@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--genome-mbp", type=float, default=100.0)
     ap.add_argument("--seeds", type=int, default=1_000_000)
     ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--full-n", type=int, default=200_000)
     args = ap.parse_args()
     if not os.path.exists(BIN):
         print(json.dumps({"unavailable": "oracle/_ref/ref_cuda_bench not built"})); return
@@ -78,6 +79,45 @@ def main():
     print(json.dumps({"path": "banded Gotoh LOCAL band 31, %d x %d bp, (2,-2,-5,-3)" % (n, M), "nvbio_b200_ms": ours_ms, "nvbio_b200_gcups": gcups,
                       "reference_cuda_sm100a_ms": ref["ms"], "reference_cuda_sm100a_gcups": ref["gcups"], "speedup": ref["ms"] / ours_ms,
                       "bit_identical_scores_and_sinks": same}), flush=True)
+
+    # ---------------- full-matrix Gotoh (sw-benchmark shape: 150 bp patterns vs 500 bp texts) ----------------
+    nf, Mf, Nf = args.full_n, 150, 500
+    if nf:
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        tsw = (Nf + 15) // 16
+        tw = torch.randint(-2**31, 2**31, (nf, tsw), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+        # patterns = a window of the text with a few substitutions: copy symbol by symbol on the host for simplicity
+        from nvbio_b200.strings import unpack_symbols, pack_symbols
+        tsym = unpack_symbols(tw.cpu().numpy().reshape(-1).view(np.uint32), 2, True, nf * tsw * 16).reshape(nf, tsw * 16)
+        rng = np.random.default_rng(3)
+        st = rng.integers(0, Nf - Mf, nf)
+        psym = np.stack([tsym[i, st[i]:st[i] + Mf] for i in range(nf)])
+        mut = rng.random(psym.shape) < 0.03
+        psym = np.where(mut, rng.integers(0, 4, psym.shape), psym).astype(np.uint8)
+        psw = (Mf + 15) // 16
+        pfull = np.zeros((nf, psw * 16), np.uint8); pfull[:, :Mf] = psym
+        pw = torch.from_numpy(pack_symbols(pfull.reshape(-1), 2, True).view(np.int32)).cuda()
+        Pf = PackedStringSet.fixed(pw, nf, Mf, stride=psw * 16)
+        Tf = PackedStringSet.fixed(tw.reshape(-1), nf, Nf, stride=tsw * 16)
+        al = aln.make_gotoh_aligner(aln.LOCAL, aln.SimpleGotohScheme(2, -2, -5, -3))
+        res = [None]
+        def go():
+            res[0] = aln.batch_alignment_score(al, Pf, Tf)
+        ours_ms = time_ms(go, reps=3)
+        with tempfile.TemporaryDirectory() as d:
+            np.array([nf, Mf, psw * 16, Nf, tsw * 16, 2, -2 & 0xFFFFFFFF, -5 & 0xFFFFFFFF, -3 & 0xFFFFFFFF, 2], dtype=np.uint32).tofile(d + "/meta.bin")
+            pw.cpu().numpy().tofile(d + "/pat_words.bin")
+            tw.cpu().numpy().tofile(d + "/txt_words.bin")
+            r = subprocess.run([BIN, "full", d], capture_output=True, text=True)
+            if r.returncode != 0:
+                print(json.dumps({"error": r.stderr[-400:]})); return
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            ref_scores = np.fromfile(d + "/ref_scores.bin", dtype=np.int32)
+            ref_sinks = np.fromfile(d + "/ref_sinks.bin", dtype=np.uint32).reshape(-1, 2)
+        same = bool(np.array_equal(res[0][0].cpu().numpy(), ref_scores) and np.array_equal(res[0][1].cpu().numpy().view(np.uint32), ref_sinks))
+        print(json.dumps({"path": "full-matrix Gotoh LOCAL, %d x (%d bp vs %d bp), (2,-2,-5,-3)" % (nf, Mf, Nf), "nvbio_b200_ms": ours_ms,
+                          "nvbio_b200_gcups": nf * Mf * Nf / (ours_ms * 1e-3) / 1e9, "reference_cuda_sm100a_ms": ref["ms"],
+                          "reference_cuda_sm100a_gcups": ref["gcups"], "speedup": ref["ms"] / ours_ms, "bit_identical_scores_and_sinks": same}), flush=True)
 
     # ---------------- FM-index ----------------
     nq, L = args.seeds, 22
