@@ -92,6 +92,33 @@ def test_c4_slice_1M_alignments(R, genome100):
         assert np.array_equal(kk[:, 0], wx) and np.array_equal(kk[:, 1], wy)
 
 
+def test_c1_sw_benchmark_10k(R):
+    """configs[0] (sw-benchmark's CPU-runnable case): 10K x 100 bp reads vs 1 Kbp references, Gotoh GLOBAL (2,-1,-2,-1) as
+    sw-benchmark sets it (sw-benchmark.cu:592-641) -- the full-matrix DP of every read against its whole reference and the
+    band-15 DP, each (score, sink) bit-identical to the reference's own templates run on the host; LOCAL and SEMI_GLOBAL too"""
+    rng = np.random.default_rng(77)
+    n_al, M, N = 10_000, 100, 1000
+    txt = rng.integers(0, 4, (n_al, N)).astype(np.uint8)
+    st = rng.integers(0, N - M, n_al)
+    pat = np.stack([txt[i, st[i]:st[i] + M] for i in range(n_al)])
+    pat = np.where(rng.random(pat.shape) < 0.04, rng.integers(0, 4, pat.shape), pat).astype(np.uint8)
+    p_off = np.arange(n_al, dtype=np.uint32) * M; p_len = np.full(n_al, M, np.uint32)
+    t_off = np.arange(n_al, dtype=np.uint32) * N; t_len = np.full(n_al, N, np.uint32)
+    P = PackedStringSet.from_symbols(pat.reshape(-1), p_off, p_len, bits=2, big_endian=True)
+    T = PackedStringSet.from_symbols(txt.reshape(-1), t_off, t_len, bits=2, big_endian=True)
+    scheme = (2, -1, -2, -1)
+    for typ in (0, 1, 2):
+        s, k = aln.batch_alignment_score(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme)), P, T)
+        ws, wx, wy = R.gotoh_full(typ, scheme, pat.reshape(-1), p_off, p_len, txt.reshape(-1), t_off, t_len)
+        kk = host_u32(k)
+        assert np.array_equal(s.cpu().numpy(), ws), typ
+        assert np.array_equal(kk[:, 0], wx) and np.array_equal(kk[:, 1], wy), typ
+    s, k = aln.batch_banded_alignment_score(15, aln.make_gotoh_aligner(aln.GLOBAL, aln.SimpleGotohScheme(*scheme)), P, T)
+    ws, wx, wy, _ = R.banded_gotoh(15, 0, scheme, pat.reshape(-1), p_off, p_len, txt.reshape(-1), t_off, t_len)
+    kk = host_u32(k)
+    assert np.array_equal(s.cpu().numpy(), ws) and np.array_equal(kk[:, 0], wx) and np.array_equal(kk[:, 1], wy)
+
+
 def test_c3_100k_reads_pipeline(R, genome100):
     """configs[2] shape (150 bp reads, 20 bp seeds every 10 bp, both strands, band 31 LOCAL) on 100K reads: best score per
     read and the number of hits identical to the reference composition (match -> locate -> banded score -> max)"""

@@ -88,7 +88,7 @@ def main():
         tw = torch.randint(-2**31, 2**31, (nf, tsw), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
         # patterns = a window of the text with a few substitutions: copy symbol by symbol on the host for simplicity
         from nvbio_b200.strings import unpack_symbols, pack_symbols
-        tsym = unpack_symbols(tw.cpu().numpy().reshape(-1).view(np.uint32), 2, True, nf * tsw * 16).reshape(nf, tsw * 16)
+        tsym = unpack_symbols(tw.cpu().numpy().reshape(-1).view(np.uint32), nf * tsw * 16, 2, True).reshape(nf, tsw * 16)
         rng = np.random.default_rng(3)
         st = rng.integers(0, Nf - Mf, nf)
         psym = np.stack([tsym[i, st[i]:st[i] + Mf] for i in range(nf)])

@@ -44,6 +44,37 @@ __global__ void gather(const Blk* __restrict__ tab, uint32_t n_blocks_mask, uint
     out[t] = acc;
 }
 
+// address-ordered variant: thread t gathers from a window of 2^win_lg blocks whose position grows with t (what a batch of
+// queries SORTED by SA row would do); win_lg = table size -> fully random
+template <int PER_THREAD>
+__global__ void gather_windowed(const Blk* __restrict__ tab, uint32_t n_blocks_lg, uint32_t win_lg, uint32_t* out, uint32_t seed) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;        // 2^25 threads
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const uint32_t h = hash32(t * PER_THREAD + k + seed);
+        const uint32_t base = n_blocks_lg >= 25 ? (t << (n_blocks_lg - 25)) : (t >> (25 - n_blocks_lg));
+        const uint32_t idx = ((base >> win_lg) << win_lg) | (h & ((1u << win_lg) - 1u));
+        const Blk b = load<1>(tab + idx);
+        acc += b.w[0] ^ b.w[3] ^ b.w[7];
+    }
+    out[t] = acc;
+}
+void run_windowed(const Blk* tab, uint32_t n_blocks_lg, uint32_t win_lg, uint32_t* out) {
+    const uint32_t threads = 1u << 25;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    gather_windowed<4><<<threads / 256, 256>>>(tab, n_blocks_lg, win_lg, out, 1u);
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0);
+        gather_windowed<4><<<threads / 256, 256>>>(tab, n_blocks_lg, win_lg, out, 77u + r);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    printf("ordered .L2::64B 16 GiB table, window %8.3f MiB  %7.3f ms  %7.1f G gathers/s\n", (double)(1ull << win_lg) * 32 / 1048576.0, best,
+           (double)threads * 4 / (best * 1e-3) / 1e9);
+}
+
 template <int VARIANT, int PER_THREAD>
 void run(const Blk* tab, uint32_t mask, uint32_t* out, const char* what) {
     const uint32_t threads = 1u << 25;                    // 33.5 M threads
@@ -92,6 +123,8 @@ int main() {
             char what[64]; snprintf(what, sizeof(what), "sweep .L2::64B, %6u MiB table", (1u << lg) / 32768u);
             run<1, 4>(big, (1u << lg) - 1, out, what);
         }
+        // the same 134 M gathers over the 16 GiB table, but address-ordered at decreasing window sizes
+        for (uint32_t w = 29; w >= 5; w -= 3) run_windowed(big, 29, w, out);
     }
     return 0;
 }
