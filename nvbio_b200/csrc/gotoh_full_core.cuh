@@ -91,4 +91,183 @@ __host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
     return res;
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed pair: TWO full-matrix alignments per thread in s16x2 halves (DPX), same formulation as gotoh_pair (gotoh_core.cuh)
+// transposed: the per-ROW substitution profile comes from the two text symbols, the per-COLUMN selector from the two
+// pattern symbols (constant over a stripe sweep; staged by the thread itself in `sel`, element j at sel[j*sel_stride] --
+// shared memory on the device: one conflict-free u16 column per thread, read back with one LDS.U16 per cell).
+//
+// Preconditions (the caller routes everything else to gotoh_full): M0 == M1 >= 1, N0 == N1 >= 1, every pattern symbol < 4
+// (returns false otherwise, before touching any output), scheme admitted by full_pair_path_ok().
+// LOCAL keeps H itself (>= 0, < 2048) and F,E biased by beta = -Go; per row the maximum of the 16-bit keys
+// (H << 5) | (column within the stripe) is taken, and since the column index is (8-column sub-stripe << 3) | column, comparing
+// keys >> 3 across rows and whole keys inside a row reproduces the reference's (sub-stripe, row, column) report order.
+// ---------------------------------------------------------------------------------------------
+static inline bool full_pair_path_ok(int type, const nvb_gotoh_scheme* s, uint32_t max_m, uint32_t max_n) {
+    const int64_t Go = s->pattern_gap_open, Ge = s->pattern_gap_ext;
+    if (s->d_qual_table) return false;
+    if (Go >= 0 || Ge >= 0 || s->text_gap_open >= 0 || s->text_gap_ext >= 0) return false;
+    const int64_t s_lo = s->match < s->mismatch ? s->match : s->mismatch, s_hi = s->match > s->mismatch ? s->match : s->mismatch;
+    int64_t mx = s_lo < 0 ? -s_lo : s_lo; if (s_hi > mx) mx = s_hi; if (-s_hi > mx) mx = -s_hi;
+    if (-Go > mx) mx = -Go; if (-Ge > mx) mx = -Ge;
+    if (-(int64_t)s->text_gap_open > mx) mx = -(int64_t)s->text_gap_open;
+    if (-(int64_t)s->text_gap_ext > mx) mx = -(int64_t)s->text_gap_ext;
+    if (((int64_t)max_m + (int64_t)max_n + 4) * mx > 30000) return false;          // every intermediate fits 16 bits
+    if (s_lo - Go < -128 || s_hi - Go > 127) return false;                          // (S - Go) is looked up as an int8
+    if (type == NVB_LOCAL) {
+        const uint32_t mn = max_m < max_n ? max_m : max_n;
+        if ((int64_t)mn * (s_hi > 0 ? s_hi : 0) >= 2048) return false;              // key = (H << 5) | column in 16 bits
+    }
+    return true;
+}
+
+// sequential symbol reader over a packed string (one shift per symbol, one load per word)
+struct SymSeq {
+    const uint32_t* wp; uint32_t w, left, bits, be, spw;
+    __host__ __device__ __forceinline__ SymSeq(const uint32_t* words, uint32_t b, uint32_t e, uint32_t off)
+        : bits(b), be(b == 8 ? 0u : e), spw(32u / b) {
+        const uint32_t lg = (b == 2 ? 4u : (b == 4 ? 3u : 2u));
+        const uint32_t r = off & (spw - 1u);
+        wp = words + (off >> lg);
+        w = *wp++;
+        if (r) w = be ? (w << (bits * r)) : (w >> (bits * r));
+        left = spw - r;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+        if (left == 0u) { w = *wp++; left = spw; }
+        const uint32_t s = be ? (w >> (32u - bits)) : (w & ((1u << bits) - 1u));
+        w = be ? (w << bits) : (w >> bits);
+        --left;
+        return s;
+    }
+};
+
+struct FullPairTrack { int32_t k0, k1; uint32_t r0, r1; int32_t s0, s1; uint32_t x0, x1; };   // LOCAL: best key/row; SEMI: best score/row
+
+template <int TYPE, bool PARTIAL>
+__host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, const bool first, const bool last, const uint32_t b,
+        const uint32_t ncols, const uint32_t N, SymSeq t0, SymSeq t1, const uint16_t* sel, const uint32_t sel_stride,
+        uint2* __restrict__ col, const size_t col_stride, FullPairTrack& trk, uint32_t& g_last)
+{
+    const int32_t Go = S.pgo, Ge = S.pge;
+    const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
+    int32_t INF = SHRT_MIN - (Go < Ge ? Go : Ge);
+    if (INF + Ge < -32768) INF = -32768 - Ge;
+    const int32_t c_eq = S.match - Go, c_ne = S.mismatch - Go;
+    const int32_t beta = -Go;
+    const uint32_t beta2 = pack16(beta, beta);
+    const uint32_t GoX = (uint32_t)(Go * 65537);
+    const uint32_t INFx = (TYPE == NVB_LOCAL) ? pack16(INF + beta, INF + beta) : pack16(INF, INF);
+
+    // arrays of the PREVIOUS row: V[j] = H (LOCAL) or H + Go (otherwise) of column b + j; F[j] likewise biased for LOCAL
+    uint32_t V[FULL_W + 1], F[FULL_W + 1];
+#pragma unroll
+    for (int j = 0; j <= FULL_W; ++j) {
+        int32_t h = 0;
+        if (TYPE != NVB_LOCAL) h = ((b + j > 0) ? Go + Ge * (int32_t)(b + j - 1) : 0) + Go;
+        V[j] = pack16(h, h);
+        F[j] = INFx;
+    }
+    uint32_t diag_next = V[0];
+    uint32_t left_h = (TYPE == NVB_LOCAL) ? 0u : pack16(((TYPE == NVB_GLOBAL) ? S.tgo : 0) + Go, ((TYPE == NVB_GLOBAL) ? S.tgo : 0) + Go);
+    const uint32_t left_step = (TYPE == NVB_GLOBAL) ? pack16(S.tge, S.tge) : 0u;
+    const uint32_t left_e = (TYPE == NVB_LOCAL) ? beta2 : INFx;
+    uint2 nxt = make_uint2(0u, 0u);
+    if (!first) nxt = col[0];
+    for (uint32_t r = 0; r < N; ++r) {
+        const uint32_t P0 = sub_profile(t0.next(), c_eq, c_ne);
+        const uint32_t P1 = sub_profile(t1.next(), c_eq, c_ne);
+        uint32_t Vl, E;
+        if (first) { Vl = left_h; E = left_e; left_h = NVB_VIADD(left_h, left_step); }
+        else       { Vl = nxt.x; E = nxt.y; if (r + 1u < N) nxt = col[(size_t)(r + 1u) * col_stride]; }
+        uint32_t Vd = diag_next;
+        diag_next = Vl;
+        V[0] = Vl;
+        uint32_t rowkey = 0u, vM = 0u;
+#pragma unroll
+        for (int j = 1; j <= FULL_W; ++j) {
+            const uint32_t s = prmt(P0, P1, (uint32_t)sel[(size_t)(j - 1) * sel_stride]);
+            F[j] = NVB_VIADDMAX(F[j], Ge2, V[j]);
+            E    = NVB_VIADDMAX(E, Ge2, V[j - 1]);
+            const uint32_t old = V[j];
+            if (TYPE == NVB_LOCAL) {
+                const uint32_t hb = NVB_VIMAX3(NVB_VIADDMAX(Vd, s, F[j]), E, beta2);
+                V[j] = hb * S.one + GoX;                                              // IMAD: H = h' + Go per half (carry-free)
+                const uint32_t key = V[j] * S.keymul + (uint32_t)((j - 1) | ((j - 1) << 16));
+                if (!PARTIAL || (uint32_t)j <= ncols) rowkey = NVB_VIMAX_U(rowkey, key);
+            } else {
+                const uint32_t h = NVB_VIMAX(NVB_VIADDMAX(Vd, s, F[j]), E);
+                V[j] = NVB_VIADD(h, Go2);
+                if (TYPE == NVB_SEMI_GLOBAL && PARTIAL && (uint32_t)j == ncols) vM = V[j];
+            }
+            Vd = old;
+        }
+        if (!last) col[(size_t)r * col_stride] = make_uint2(V[FULL_W], E);
+        if (TYPE == NVB_LOCAL) {
+            const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
+            if ((k0 >> 3) >= (trk.k0 >> 3)) { trk.k0 = k0; trk.r0 = r; }
+            if ((k1 >> 3) >= (trk.k1 >> 3)) { trk.k1 = k1; trk.r1 = r; }
+        }
+        if (TYPE == NVB_SEMI_GLOBAL && last) {
+            if (!PARTIAL) vM = V[FULL_W];
+            const int32_t h0 = half_lo(vM) - Go, h1 = half_hi(vM) - Go;
+            if (trk.s0 <= h0) { trk.s0 = h0; trk.x0 = r + 1u; }
+            if (trk.s1 <= h1) { trk.s1 = h1; trk.x1 = r + 1u; }
+        }
+    }
+    if (TYPE == NVB_GLOBAL && last) {
+        uint32_t v = V[FULL_W];
+        if (PARTIAL) {
+#pragma unroll
+            for (int j = 1; j <= FULL_W; ++j) if ((uint32_t)j == ncols) v = V[j];
+        }
+        g_last = v;
+    }
+}
+
+template <int TYPE>
+__host__ __device__ inline bool gotoh_full_pair(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff0, uint32_t poff1, uint32_t M,
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff0, uint32_t toff1, uint32_t N,
+        uint2* __restrict__ col, size_t col_stride, uint16_t* sel, uint32_t sel_stride, SinkResult& r0, SinkResult& r1)
+{
+    const int32_t Go = S.pgo;
+    r0.score = INT_MIN; r0.x = r0.y = 0xFFFFFFFFu; r1 = r0;
+    FullPairTrack trk; trk.s0 = trk.s1 = INT_MIN; trk.x0 = trk.x1 = 0u;
+    for (uint32_t b = 0; b < M; b += FULL_W) {
+        const bool first = (b == 0), last = (b + FULL_W >= M);
+        const uint32_t ncols = last ? M - b : (uint32_t)FULL_W;
+        {
+            SymSeq p0(pwords, pbits, pbe, poff0 + b), p1(pwords, pbits, pbe, poff1 + b);
+            uint32_t bad = 0u;
+#pragma unroll
+            for (int j = 0; j < FULL_W; ++j) {
+                uint32_t q0 = 0u, q1 = 0u;
+                if ((uint32_t)j < ncols) { q0 = p0.next(); q1 = p1.next(); }
+                bad |= (q0 | q1) >> 2;
+                sel[(size_t)j * sel_stride] = (uint16_t)pair_selector(q0 & 3u, q1 & 3u);
+            }
+            if (bad) return false;            // a pattern symbol >= 4 (N): not expressible as a 2-bit selector
+        }
+        trk.k0 = trk.k1 = -1; trk.r0 = trk.r1 = 0u;
+        uint32_t g_last = 0u;
+        const SymSeq t0(twords, tbits, tbe, toff0), t1(twords, tbits, tbe, toff1);
+        if (ncols == (uint32_t)FULL_W) full_pair_stripe<TYPE, false>(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last);
+        else                           full_pair_stripe<TYPE, true >(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last);
+        if (TYPE == NVB_LOCAL) {
+            if (r0.score <= (trk.k0 >> 5)) { r0.score = trk.k0 >> 5; r0.x = trk.r0 + 1u; r0.y = b + ((uint32_t)trk.k0 & 31u) + 1u; }
+            if (r1.score <= (trk.k1 >> 5)) { r1.score = trk.k1 >> 5; r1.x = trk.r1 + 1u; r1.y = b + ((uint32_t)trk.k1 & 31u) + 1u; }
+        }
+        if (TYPE == NVB_GLOBAL && last) {
+            r0.score = half_lo(g_last) - Go; r0.x = N; r0.y = M;
+            r1.score = half_hi(g_last) - Go; r1.x = N; r1.y = M;
+        }
+    }
+    if (TYPE == NVB_SEMI_GLOBAL) {
+        r0.score = trk.s0; r0.x = trk.x0; r0.y = M;
+        r1.score = trk.s1; r1.x = trk.x1; r1.y = M;
+    }
+    return true;
+}
+
 } // namespace nvb

@@ -142,6 +142,52 @@ gotoh_full_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ co
     b.sink[a]  = make_uint2(r.x, r.y);
 }
 
+// full-matrix Gotoh, packed: one PAIR of alignments per thread (a, a+1); pairs that break a precondition of the packed
+// path go to the todo list and are scored by gotoh_full_todo_kernel (int32)
+template <int TYPE, int MINB>
+__global__ void __launch_bounds__(PAIR_BLOCKDIM, MINB)
+gotoh_full_pair_kernel(const GotohScheme S, const GotohBatch b, uint2* __restrict__ col, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
+{
+    const uint32_t n = batch_count(b);
+    const uint32_t n_pairs = (n + 1u) >> 1;
+    const uint32_t p = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint32_t a0 = 2u * p, a1 = a0 + 1u;
+    const bool has1 = a1 < n;
+    const uint32_t M0 = str_len(b.pat, a0), N0 = str_len(b.txt, a0);
+    const uint32_t M1 = has1 ? str_len(b.pat, a1) : M0, N1 = has1 ? str_len(b.txt, a1) : N0;
+    bool ok = (M0 == M1) && (N0 == N1) && M0 >= 1u && N0 >= 1u;
+    SinkResult r0, r1;
+    __shared__ uint16_t sel[FULL_W * PAIR_BLOCKDIM];
+    if (ok) ok = gotoh_full_pair<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a0), str_off(b.pat, has1 ? a1 : a0), M0,
+                                       b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a0), str_off(b.txt, has1 ? a1 : a0), N0,
+                                       col + p, (size_t)((b.n_max + 1u) >> 1), sel + threadIdx.x, PAIR_BLOCKDIM, r0, r1);
+    if (ok) {
+        b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
+        if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
+    } else {
+        const uint32_t cnt = has1 ? 2u : 1u;
+        const uint32_t slot = atomicAdd(todo_count, cnt);
+        todo[slot] = a0;
+        if (has1) todo[slot + 1u] = a1;
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_full_todo_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ col, const uint32_t* __restrict__ todo, const uint32_t* __restrict__ todo_count)
+{
+    const uint32_t n = *todo_count;
+    for (uint32_t t = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x; t < n; t += gridDim.x * GENERIC_BLOCKDIM) {
+        const uint32_t a = todo[t];
+        const SinkResult r = gotoh_full<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a),
+                                              b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a),
+                                              col + a, (size_t)b.n_max);
+        b.score[a] = r.score;
+        b.sink[a]  = make_uint2(r.x, r.y);
+    }
+}
+
 // traceback: one alignment per thread; DP with direction vectors into a per-alignment global scratch matrix
 // (M rows x DirWords<B>::N words -- no checkpoints / recomputation: 2.4 KB per 150 x 31 alignment is nothing in 180 GB),
 // then the H/E/F state-machine walk from the sink.
@@ -254,6 +300,7 @@ static inline int dir_words(int band) { return (band * 4 + 31) / 32; }
 
 // force_path: 0 auto, 1 generic only (used by tests to exercise both paths on the same inputs)
 static int g_force_path = 0;
+static int g_full_minb = 0;          // 0 = per-type default; tuning knob of gotoh_full_pair_kernel's occupancy (nvb_debug_full_minb)
 
 static int banded_impl(int band, int type, const nvb_gotoh_scheme* scheme,
                        const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts,
@@ -327,7 +374,9 @@ int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_s
     if (texts->length > 65535u || patterns->length > 65535u) return NVB_E_UNSUPPORTED;
     TempCarver tc(d_temp);
     const bool need_col = patterns->length > (uint32_t)FULL_W;          // a single stripe needs no boundary column
-    int2* col = need_col ? tc.take<int2>((size_t)n * (texts->length ? texts->length : 1u)) : tc.take<int2>(1);
+    int2* col = need_col ? tc.take<int2>((size_t)(n + 1u) * (texts->length ? texts->length : 1u)) : tc.take<int2>(1);
+    uint32_t* todo_count = tc.take<uint32_t>(4);
+    uint32_t* todo       = tc.take<uint32_t>((size_t)n + 2);
     const size_t need = tc.total();
     if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
     if (n == 0) return NVB_OK;
@@ -338,11 +387,34 @@ int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_s
     const GotohScheme S = make_scheme(scheme);
     const uint32_t grid = (n + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
     cudaStream_t s = as_stream(stream);
-    switch (type) {
-    case NVB_GLOBAL:      gotoh_full_kernel<NVB_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
-    case NVB_LOCAL:       gotoh_full_kernel<NVB_LOCAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
-    default:              gotoh_full_kernel<NVB_SEMI_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+    const bool packed = g_force_path != 1 && full_pair_path_ok(type, scheme, patterns->length, texts->length);
+    if (!packed) {
+        switch (type) {
+        case NVB_GLOBAL:      gotoh_full_kernel<NVB_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+        case NVB_LOCAL:       gotoh_full_kernel<NVB_LOCAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+        default:              gotoh_full_kernel<NVB_SEMI_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col); break;
+        }
+        NVB_LAUNCH_CHECK();
+        return NVB_OK;
     }
+    // packed pairs first (the boundary columns of pair p live in the first half of `col`), then whatever they rejected
+    NVB_CUDA_TRY(cudaMemsetAsync(todo_count, 0, sizeof(uint32_t), s));
+    const uint32_t n_pairs = (n + 1u) >> 1;
+    const uint32_t pgrid = (n_pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
+    uint32_t tgrid = grid < 148u * 8u ? grid : 148u * 8u;
+    // occupancy per type as measured (tools/bench_full.py): LOCAL and SEMI_GLOBAL run fastest spill-free at 2 CTAs/SM, GLOBAL at 3
+    const int minb = g_full_minb ? g_full_minb : (type == NVB_GLOBAL ? 3 : 2);
+#define NVB_FULL_PAIR(T)                                                                                               \
+    if (minb == 2)      gotoh_full_pair_kernel<T, 2><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
+    else if (minb == 4)        gotoh_full_pair_kernel<T, 4><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
+    else                       gotoh_full_pair_kernel<T, 3><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
+    gotoh_full_todo_kernel<T><<<tgrid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, todo, todo_count);
+    switch (type) {
+    case NVB_GLOBAL: NVB_FULL_PAIR(NVB_GLOBAL) break;
+    case NVB_LOCAL:  NVB_FULL_PAIR(NVB_LOCAL) break;
+    default:         NVB_FULL_PAIR(NVB_SEMI_GLOBAL) break;
+    }
+#undef NVB_FULL_PAIR
     NVB_LAUNCH_CHECK();
     return NVB_OK;
 }
@@ -373,5 +445,6 @@ int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* s
 
 // test hook (declared in tests only): 0 = auto, 1 = generic int32 kernel for everything
 void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
+void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
 
 } // extern "C"

@@ -170,6 +170,36 @@ int hh_gotoh_full(int type, const int32_t* scheme6,
     return 0;
 }
 
+// packed pair version; alignments (2p, 2p+1) are paired when their lengths agree, else scored singly with gotoh_full
+// returns the number of alignments that took the packed path
+int hh_gotoh_full_pair(int type, const int32_t* scheme6,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,
+                  int32_t* score, uint32_t* sx, uint32_t* sy) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr; S.one = 1u; S.keymul = 32u;
+    int packed = 0;
+    for (uint32_t a = 0; a < n; a += 2) {
+        const uint32_t a1 = (a + 1 < n) ? a + 1 : a;
+        std::vector<uint2> col(tlen[a] + 1);
+        uint16_t sel[FULL_W];
+        SinkResult r0, r1;
+        bool ok = plen[a] == plen[a1] && tlen[a] == tlen[a1] && plen[a] >= 1 && tlen[a] >= 1;
+        if (ok) {
+            if (type == 0)      ok = gotoh_full_pair<0>(S, pw, pbits, pbe, poff[a], poff[a1], plen[a], tw, tbits, tbe, toff[a], toff[a1], tlen[a], col.data(), 1, sel, 1, r0, r1);
+            else if (type == 1) ok = gotoh_full_pair<1>(S, pw, pbits, pbe, poff[a], poff[a1], plen[a], tw, tbits, tbe, toff[a], toff[a1], tlen[a], col.data(), 1, sel, 1, r0, r1);
+            else                ok = gotoh_full_pair<2>(S, pw, pbits, pbe, poff[a], poff[a1], plen[a], tw, tbits, tbe, toff[a], toff[a1], tlen[a], col.data(), 1, sel, 1, r0, r1);
+        }
+        if (ok) {
+            packed += (a1 != a) ? 2 : 1;
+            score[a] = r0.score; sx[a] = r0.x; sy[a] = r0.y;
+            if (a1 != a) { score[a1] = r1.score; sx[a1] = r1.x; sy[a1] = r1.y; }
+        } else {
+            hh_gotoh_full(type, scheme6, pw, pbits, pbe, poff + a, plen + a, tw, tbits, tbe, toff + a, tlen + a, (a1 != a) ? 2 : 1, score + a, sx + a, sy + a);
+        }
+    }
+    return packed;
+}
+
 int hh_gotoh_traceback(int band, int type, const int32_t* scheme6,
                        const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                        const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n, uint32_t max_ops,

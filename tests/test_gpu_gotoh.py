@@ -227,3 +227,32 @@ def test_full_matrix_reference_strings(O):
         s, k = aln.batch_alignment_score(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -1, -1, -1)), P, T)
         k = host_u32(k)
         assert (int(s[0]), int(k[0, 0]), int(k[0, 1])) == want
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_full_matrix_packed_path(O, typ):
+    """gotoh_full_pair_kernel (two alignments per thread, s16x2): consecutive alignments of equal shape take the packed path, the
+    rest (ragged neighbours, N in the pattern) its int32 fallback; all == oracle; forcing the int32 kernel gives the same"""
+    from tests.test_host_core import paired_full_problems
+    rng = np.random.default_rng(950 + typ)
+    for scheme in ((2, -1, -2, -1), (2, -2, -5, -3)):
+        for n_frac in (0.0, 0.1):
+            pr = paired_full_problems(rng, 600, max_m=200, max_n=400, n_frac=n_frac)
+            want = O.gotoh_full(typ, scheme, *pr)
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+            T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2, big_endian=True)
+            al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme))
+            for minb in (2, 3, 4):
+                nb.lib().nvb_debug_full_minb(C.c_int(minb))
+                s, k = aln.batch_alignment_score(al, P, T)
+                k = host_u32(k)
+                assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, scheme, n_frac, minb)
+            nb.lib().nvb_debug_full_minb(C.c_int(0))
+            force_path(1)
+            try:
+                s, k = aln.batch_alignment_score(al, P, T)
+            finally:
+                force_path(0)
+            k = host_u32(k)
+            assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, scheme, "int32")

@@ -387,3 +387,46 @@ def test_gotoh_full(H, O, typ):
             H.hh_gotoh_full(C.c_int(typ), _p(s6), _p(pw), C.c_uint32(pbits), C.c_uint32(1), _p(p_off), _p(p_len),
                             _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
             assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, scheme)
+
+
+def paired_full_problems(rng, n_pairs, max_m=130, max_n=300, n_frac=0.0):
+    """consecutive alignments share (M, N) so that the packed pair path admits them"""
+    pats, txts, po, pl, to, tl = [], [], [], [], [], []
+    a = b = 0
+    for _ in range(n_pairs):
+        M = int(rng.integers(1, max_m + 1)); N = int(rng.integers(1, max_n + 1))
+        for _k in range(2):
+            t = rng.integers(0, 4, N).astype(np.uint8)
+            if N > M and rng.random() < 0.7:
+                st = int(rng.integers(0, N - M + 1)); p = t[st:st + M].copy()
+                for _j in range(int(rng.integers(0, 5))):
+                    p[int(rng.integers(0, M))] = rng.integers(0, 4)
+            else:
+                p = rng.integers(0, 4, M).astype(np.uint8)
+            if n_frac and rng.random() < n_frac:
+                p[int(rng.integers(0, M))] = 4
+            pats.append(p); txts.append(t); po.append(a); pl.append(M); a += M; to.append(b); tl.append(N); b += N
+    return (np.concatenate(pats), np.array(po, np.uint32), np.array(pl, np.uint32), np.concatenate(txts), np.array(to, np.uint32), np.array(tl, np.uint32))
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_full_pair(H, O, typ):
+    """packed s16x2 full-matrix routine (two alignments per thread) == the oracle: scores, sinks, LOCAL tie order; lengths that
+    are and are not multiples of the 32-column stripe; N's in the pattern fall back to the int32 routine"""
+    rng = np.random.default_rng(600 + typ)
+    for scheme in ((2, -1, -2, -1), (2, -2, -5, -3), (0, -5, -8, -3), (2, -1, -1, -1)):
+        for n_frac in (0.0, 0.2):
+            pr = paired_full_problems(rng, 70, n_frac=n_frac)
+            want = O.gotoh_full(typ, scheme, *pr)
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            for pbits, tbits, tbe in ((4, 2, 1), (4, 4, 1), (2, 8, 0)):
+                if pbits == 2 and n_frac:
+                    continue
+                pw, tw = pack_symbols(pat, pbits, True), pack_symbols(txt, tbits, bool(tbe))
+                n = len(p_off)
+                score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+                s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+                packed = H.hh_gotoh_full_pair(C.c_int(typ), _p(s6), _p(pw), C.c_uint32(pbits), C.c_uint32(1), _p(p_off), _p(p_len),
+                                              _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+                assert packed > 0 and (n_frac or packed == n)
+                assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, scheme, pbits, tbits)
