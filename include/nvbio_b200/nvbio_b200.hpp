@@ -5,6 +5,7 @@
 //   nvbio::aln::SimpleGotohScheme, make_gotoh_aligner<TYPE>, BestSink<int32>         (nvbio/alignment/utils.h:114-135,
 //                                                                                     alignment_base.h:255-298, sink.h:69-93)
 //   nvbio::aln::batch_banded_alignment_score<BAND_LEN>                               (nvbio/alignment/batched_inl.h:1067-1101)
+//   nvbio::aln::batch_alignment_score (full DP)                                      (nvbio/alignment/batched_inl.h:984-1040)
 // Errors are thrown as std::runtime_error carrying nvb_error_string(), the analogue of the reference's
 // cuda::check_error exceptions.
 #pragma once
@@ -91,6 +92,19 @@ void batch_banded_alignment_score(const GotohAligner<TYPE, scheme_type> aligner,
     if (r != NVB_E_TEMP_SIZE) check(r, "nvb_banded_gotoh_score");
     temp.resize(tb ? tb : 1);
     check(nvb_banded_gotoh_score(BAND_LEN, TYPE, &s, &patterns, nullptr, &texts, n, d_scores, d_sinks, temp.ptr, &tb, stream), "nvb_banded_gotoh_score");
+}
+
+/// batch_alignment_score(aligner, patterns, texts, scores, sinks): the full-matrix DP (nvbio/alignment/batched_inl.h:984-1040)
+template <AlignmentType TYPE, typename scheme_type>
+void batch_alignment_score(const GotohAligner<TYPE, scheme_type> aligner, const nvb_string_set& patterns, const nvb_string_set& texts,
+                           uint32_t n, int32_t* d_scores, nvb_uint2* d_sinks, device_buffer<char>& temp, cudaStream_t stream = 0)
+{
+    const nvb_gotoh_scheme s = aligner.scheme.abi();
+    size_t tb = 0;
+    int r = nvb_gotoh_score(TYPE, &s, &patterns, &texts, n, d_scores, d_sinks, nullptr, &tb, stream);
+    if (r != NVB_E_TEMP_SIZE) check(r, "nvb_gotoh_score");
+    temp.resize(tb ? tb : 1);
+    check(nvb_gotoh_score(TYPE, &s, &patterns, &texts, n, d_scores, d_sinks, temp.ptr, &tb, stream), "nvb_gotoh_score");
 }
 
 } // namespace aln

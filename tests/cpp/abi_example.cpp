@@ -26,5 +26,15 @@ int main() {
     cudaDeviceSynchronize();
     const int32_t s = score.download(1)[0]; const nvb_uint2 k = sink.download(1)[0];
     printf("score %d sink (%u,%u)\n", s, k.x, k.y);
-    return (s == -11 && k.x == 165 && k.y == 150) ? 0 : 1;      // values of the reference on this problem
+    if (!(s == -11 && k.x == 165 && k.y == 150)) return 1;      // values of the reference on this problem
+    // full-matrix DP of the reference's 7 x 20 strings (alignment_test.cu:761-793), LOCAL: score 13 ending at (18,7)
+    const char* P2 = "ACAACTA"; const char* T2 = "AAACACCCTAACACACTAAA";
+    device_buffer<uint32_t> dp2, dt2; dp2.upload(pack2(P2)); dt2.upload(pack2(T2));
+    nvb_string_set ps2 = { dp2.ptr, 2, 1, nullptr, nullptr, 0, (uint32_t)strlen(P2) };
+    nvb_string_set ts2 = { dt2.ptr, 2, 1, nullptr, nullptr, 0, (uint32_t)strlen(T2) };
+    aln::batch_alignment_score(aln::make_gotoh_aligner<aln::LOCAL>(aln::SimpleGotohScheme(2, -1, -1, -1)), ps2, ts2, 1u, score.ptr, sink.ptr, temp);
+    cudaDeviceSynchronize();
+    const int32_t s2 = score.download(1)[0]; const nvb_uint2 k2 = sink.download(1)[0];
+    printf("full score %d sink (%u,%u)\n", s2, k2.x, k2.y);
+    return (s2 == 13 && k2.x == 18 && k2.y == 7) ? 0 : 1;
 }
