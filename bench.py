@@ -48,10 +48,11 @@ def parse():
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
-    ap.add_argument("--ktab-k", type=int, default=15, help="k of the k-mer range table (0 = none)")
+    ap.add_argument("--ktab-k", type=int, default=16, help="k of the k-mer range table (0 = none)")
     ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 kernel-level measurements")
+    ap.add_argument("--pairs", type=int, default=500_000, help="read pairs per GPU per step of the paired-end (C5-shaped) measurement; 0 = skip")
     return ap.parse_args()
 
 
@@ -333,6 +334,55 @@ def other_configs(device):
     return out
 
 
+def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
+    """BASELINE configs[4] shape at per-GPU scale: `--pairs` FR pairs of 2 x 150 bp per GPU per step through
+    nvb_seed_extend_paired (both mates seeded + extended, concordance check, opposite-mate full-matrix Gotoh rescue).
+    Device-resident timing, L2 flushed between steps, max over ranks."""
+    from nvbio_b200.pipeline import PairedWorkspace
+    from nvbio_b200.strings import PackedStringSet
+    from nvbio_b200 import synth
+    n_pairs = args.pairs
+    rank = int(os.environ.get("RANK", "0"))
+    words, left, frag = synth.sample_pairs(genome, n, n_pairs, READ_LEN, frag_mean=350.0, frag_sd=30.0, sub_rate=0.01, hard_frac=0.05,
+                                           hard_sub_rate=0.2, device=device, seed=0x51ED + rank, mut_seed=0xC0FFEE + rank)
+    wpr = words.shape[1]
+    rs = PackedStringSet.fixed(words.reshape(-1), 2 * n_pairs, READ_LEN, stride=wpr * 16)
+    pair = nb.PairParams(min_frag=0, max_frag=500, min_mate_score=80, rescue_capacity=max(n_pairs // 4, 1024))
+    ws = PairedWorkspace(fmi, genome, rs, params, pair, 24 * 2 * n_pairs)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        flush.zero_(); nb.seed_extend_paired(fmi, genome, rs, params, pair, workspace=ws)
+    barrier(world)
+    total, k = 0.0, 5
+    for _ in range(k):
+        flush.zero_()
+        ev0.record(); nb.seed_extend_paired(fmi, genome, rs, params, pair, workspace=ws); ev1.record()
+        torch.cuda.synchronize()
+        total += ev0.elapsed_time(ev1)
+    barrier(world)
+    ms = nd.max_over_ranks(total, device) / k
+    flags = ws.pair_flags.cpu().numpy()
+    run, wanted = [int(v) for v in ws.n_rescue.cpu()]
+    kept, hits, _ = [int(v) for v in ws.n_hits.cpu()]
+    # placement check against the generator's truth: the forward mate must end at left + 150, the reverse one at left + frag
+    pos = ws.mate_pos.cpu().numpy().view(np.uint32).astype(np.int64)
+    strand = ws.mate_strand.cpu().numpy()
+    l, f = left.cpu().numpy(), frag.cpu().numpy()
+    truth = np.where(strand == 0, l[None, :] + READ_LEN, (l + f)[None, :])
+    placed = np.abs(pos - truth) <= 8
+    paired = flags != 0
+    return {"workload": "%d FR pairs (2 x %d bp) per GPU per step, fragments ~N(350,30), 1%% substitutions, 5%% of the second mates with 20%% "
+                        "substitutions; both mates seeded+extended (band %d LOCAL), opposite-mate rescue by full-matrix Gotoh LOCAL in the "
+                        "500 bp fragment window" % (n_pairs, READ_LEN, BAND),
+            "Mreads_per_s": world * 2 * n_pairs / (ms * 1e-3) / 1e6, "Mpairs_per_s": world * n_pairs / (ms * 1e-3) / 1e6, "ms_per_step": ms, "n_gpus": world,
+            "pairs_concordant_frac": float((flags == 1).mean()), "pairs_rescued_frac": float(((flags == 2) | (flags == 4)).mean()),
+            "pairs_unpaired_frac": float((flags == 0).mean()), "rescue_jobs_run": run, "rescue_jobs_wanted": wanted,
+            "rescue_cells": run * READ_LEN * 500, "hits_truncated": bool(kept != hits),
+            "paired_and_both_mates_at_true_locus_frac": float((paired & placed[0] & placed[1]).mean()),
+            "rank0_counts_only": True}
+
+
 def run_ours(args):
     import nvbio_b200 as nb
     from nvbio_b200 import aln
@@ -424,6 +474,17 @@ def run_ours(args):
     d2h = n_reads * 8 + 12
     found = float((stream.slots[0]["host_score"] > READ_LEN).float().mean())
 
+    # ---- paired-end composition (C5 shape), every world size --------------------------------------
+    paired = None
+    if args.pairs > 0:
+        try:
+            paired = paired_end_config(args, nb, fmi, genome, n, params, device, world, nd)
+        except SystemExit:
+            raise
+        except Exception as e:
+            if world > 1:
+                raise                                    # a rank that skips the collectives would hang the others
+            paired = {"error": repr(e)[:300]}
     if rank != 0:
         return
     # ---- CPU baseline + algorithmic bytes (rank 0, N=1 only) ----------------------------------
@@ -475,6 +536,8 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if paired is not None:
+        line["paired_end"] = paired
     if world == 1 and not args.no_other_configs:
         del stream, batches, flush
         torch.cuda.empty_cache()

@@ -192,6 +192,12 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
 int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
                     int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream);
 
+/* Same, with the number of alignments read from device memory (*d_n, clamped to n_max): lets a producer kernel decide
+ * the batch size without a host round trip (the opposite-mate stage of nvb_seed_extend_paired). */
+int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts,
+                             const uint32_t* d_n, uint32_t n_max,
+                             int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream);
+
 /* Banded Gotoh traceback.  For i < n: score, sink (end cells) as nvb_banded_gotoh_score, plus the
  * source (start cells) and the alignment as the backtracer's pushes in END -> START order, one byte per op
  * (0 = SUBSTITUTION 'M', 1 = INSERTION 'I', 2 = DELETION 'D'; nvbio::aln::DirectionVector) at d_ops[i*max_ops ..];
@@ -229,7 +235,7 @@ int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n, uint32_t* d_bwt, uint32
                      void* d_temp, size_t* temp_bytes, void* stream);
 
 /* Fill d_ktab[4^k] with match() of every k-mer (level by level: 4^k * 4/3 LF steps in total).
- * k in [1,15].  fmi->d_ktab / ktab_k are ignored on input. */
+ * k in [1,16] (8.6 GB at k=15, 34 GB at k=16).  fmi->d_ktab / ktab_k are ignored on input. */
 int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -286,6 +292,49 @@ int nvb_seed_extend_traceback(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     int32_t* d_hit_score, nvb_uint2* d_hit_sink,
                     const nvb_best_alignment_out* best_alignment,
                     void* d_temp, size_t* temp_bytes, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Paired-end composition (BASELINE configs[4] shape; nvBowtie best_approx paired: anchor scoring + opposite-mate full DP,
+ * nvBowtie/bowtie2/cuda/aligner_best_approx_paired.h, score_opposite_inl.h:90-266, alignment_utils.h:62-95 PE_POLICY_FR).
+ *
+ * reads = 2*n_pairs strings: mate 1 of pair p at index p, mate 2 at index n_pairs + p.  Every mate is seeded and extended
+ * on its own (nvb_seed_extend with both_strands = 1, which is required).  Per pair:
+ *   - if both mates have a best alignment, on opposite strands, the forward one starting at or before the reverse one,
+ *     ending at or before it, and the fragment [begin of the forward mate, end of the reverse mate) has a length in
+ *     [min_frag, max_frag]: the pair is CONCORDANT as it stands (alignment begin := end - read length, clamped at 0);
+ *   - otherwise every mate that has an alignment (score >= min_mate_score) acts as anchor and the OTHER mate is searched
+ *     with the full-matrix Gotoh DP (nvb_gotoh_score, same type and scheme) where the FR policy puts it: anchor forward at
+ *     [b, e) -> the reverse complement of the other mate in [b, min(b + max_frag, genome length)); anchor reverse ->
+ *     the other mate forward in [max(e - max_frag, 0), e)  (score_opposite_inl.h:177-191 with pe_overlap).  A rescue whose
+ *     score reaches min_mate_score yields a candidate pair; the candidate with the larger score sum wins (tie: mate 1 as
+ *     anchor).  No candidate: the pair is UNPAIRED and each mate keeps its own best alignment.
+ * At most rescue_capacity full-DP jobs are run per call (in pair order; d_n_rescue[1] reports how many were wanted).
+ * Outputs (mate m of pair p at index m*n_pairs + p): d_pair_score (sum of the two mates' scores, INT_MIN when unpaired),
+ * d_pair_flags (NVB_PAIR_*), d_mate_score (INT_MIN = unaligned), d_mate_pos (genome coordinate one past the last aligned
+ * base, 0xFFFFFFFF = unaligned), d_mate_strand (0 forward, 1 reverse complement). */
+typedef struct nvb_pair_params {
+    uint32_t min_frag, max_frag;
+    int32_t  min_mate_score;
+    uint32_t rescue_capacity;
+} nvb_pair_params;
+typedef struct nvb_pair_out {
+    int32_t*  d_pair_score;     /* [n_pairs]   */
+    uint32_t* d_pair_flags;     /* [n_pairs]   */
+    int32_t*  d_mate_score;     /* [2*n_pairs] */
+    uint32_t* d_mate_pos;       /* [2*n_pairs] */
+    uint8_t*  d_mate_strand;    /* [2*n_pairs] */
+    uint32_t* d_n_rescue;       /* [2] full-DP jobs run, wanted (may be NULL) */
+} nvb_pair_out;
+#define NVB_PAIR_UNPAIRED       0u
+#define NVB_PAIR_CONCORDANT     1u    /* the mates' independent best alignments form a proper FR pair */
+#define NVB_PAIR_RESCUED_MATE1  2u    /* mate 1 was placed by the opposite-mate DP next to mate 2's alignment */
+#define NVB_PAIR_RESCUED_MATE2  4u
+
+int nvb_seed_extend_paired(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_pairs,
+                    const nvb_seed_extend_params* params, uint32_t hit_capacity,
+                    const nvb_pair_params* pair_params, const nvb_pair_out* out,
+                    uint32_t* d_n_hits, void* d_temp, size_t* temp_bytes, void* stream);
 
 /* Profiling aid (the reference wraps every stage in cuda::Timer, nvBowtie/bowtie2/cuda/aligner_best_approx.h:
  * 219-241): device time in ms of the seven stages of the most recent nvb_seed_extend call -- [fw,rc] strings,

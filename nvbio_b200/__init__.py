@@ -7,4 +7,4 @@ from .strings import PackedStringSet, pack_symbols, unpack_symbols              
 from .fmindex import (FMIndexDevice, FMIndexFilterDevice, rank, rank4, match, match_approx, locate,   # noqa: F401
                       MATCH_FORWARD_ORDER, MATCH_COMPLEMENT)
 from . import aln                                                                # noqa: F401
-from .pipeline import SeedExtendParams, seed_extend, StreamingSeedExtend                              # noqa: F401
+from .pipeline import SeedExtendParams, seed_extend, StreamingSeedExtend, PairParams, seed_extend_paired     # noqa: F401

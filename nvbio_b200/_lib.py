@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libnvbio_b200.so")
 EXPORTS = [
     "nvb_version", "nvb_error_string",
     "nvb_fm_rank", "nvb_fm_rank4", "nvb_fm_match", "nvb_fm_match_approx", "nvb_fm_locate", "nvb_fm_filter_rank", "nvb_fm_filter_locate",
-    "nvb_banded_gotoh_score", "nvb_banded_gotoh_score_indirect", "nvb_banded_gotoh_traceback", "nvb_gotoh_score",
+    "nvb_banded_gotoh_score", "nvb_banded_gotoh_score_indirect", "nvb_banded_gotoh_traceback", "nvb_gotoh_score", "nvb_gotoh_score_indirect", "nvb_seed_extend_paired",
     "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_fm_build_ktab", "nvb_seed_extend", "nvb_seed_extend_traceback", "nvb_seed_extend_stage_ms",
 ]
 
@@ -45,6 +45,15 @@ class SeedExtendParamsStruct(C.Structure):  # nvb_seed_extend_params
 class BestAlignmentOutStruct(C.Structure):   # nvb_best_alignment_out
     _fields_ = [("d_ops", C.c_void_p), ("max_ops", C.c_uint32), ("d_n_ops", C.c_void_p), ("d_begin", C.c_void_p),
                 ("d_strand", C.c_void_p)]
+
+
+class PairParamsStruct(C.Structure):        # nvb_pair_params
+    _fields_ = [("min_frag", C.c_uint32), ("max_frag", C.c_uint32), ("min_mate_score", C.c_int32), ("rescue_capacity", C.c_uint32)]
+
+
+class PairOutStruct(C.Structure):           # nvb_pair_out
+    _fields_ = [("d_pair_score", C.c_void_p), ("d_pair_flags", C.c_void_p), ("d_mate_score", C.c_void_p), ("d_mate_pos", C.c_void_p),
+                ("d_mate_strand", C.c_void_p), ("d_n_rescue", C.c_void_p)]
 
 
 _lib = None

@@ -41,7 +41,7 @@ static inline bool valid_fmindex(const nvb_fm_index* f) {
     if (!f || !f->d_bwt_occ) return false;
     const uint32_t I = f->sa_interval;
     if (I != 0 && (I & (I - 1)) != 0) return false;           // power of two
-    if (f->d_ktab && (f->ktab_k < 1 || f->ktab_k > 15)) return false;
+    if (f->d_ktab && (f->ktab_k < 1 || f->ktab_k > 16)) return false;
     return true;
 }
 static inline FmIndex make_fmindex(const nvb_fm_index* f) {

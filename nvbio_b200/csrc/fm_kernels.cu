@@ -178,7 +178,7 @@ const char* nvb_error_string(int err)
 
 int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream)
 {
-    if (!valid_fmindex(fmi) || k < 1 || k > 15 || !d_ktab) return NVB_E_INVALID;
+    if (!valid_fmindex(fmi) || k < 1 || k > 16 || !d_ktab) return NVB_E_INVALID;
     nvb_fm_index plain = *fmi; plain.d_ktab = nullptr; plain.ktab_k = 0;
     const FmIndex f = make_fmindex(&plain);
     cudaStream_t s = as_stream(stream);

@@ -365,8 +365,9 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
     return banded_impl(band_len, type, scheme, patterns, d_quals, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
 }
 
-int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
-                    int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
+static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts,
+                           const uint32_t* d_n, uint32_t n,
+                           int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
 {
     if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
     if (type < 0 || type > 2) return NVB_E_INVALID;
@@ -383,7 +384,7 @@ int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_s
     if (!d_score || !d_sink) return NVB_E_INVALID;
     GotohBatch b;
     b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = nullptr;
-    b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
+    b.d_n = d_n; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
     const GotohScheme S = make_scheme(scheme);
     const uint32_t grid = (n + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
     cudaStream_t s = as_stream(stream);
@@ -417,6 +418,20 @@ int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_s
 #undef NVB_FULL_PAIR
     NVB_LAUNCH_CHECK();
     return NVB_OK;
+}
+
+int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+                    int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
+{
+    return gotoh_full_impl(type, scheme, patterns, texts, nullptr, n, d_score, d_sink, d_temp, temp_bytes, stream);
+}
+
+int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts,
+                             const uint32_t* d_n, uint32_t n_max,
+                             int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!d_n) return NVB_E_INVALID;
+    return gotoh_full_impl(type, scheme, patterns, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
 }
 
 int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* scheme,

@@ -288,6 +288,123 @@ pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, c
     if (out_window) out_window[h] = make_uint2(t_off[h], t_off[h] + t_len[h]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// paired-end stage (see nvb_seed_extend_paired in the header for the rules)
+// ---------------------------------------------------------------------------------------------
+struct MateBest { bool has; int32_t score; uint32_t strand, beg, end, len; };
+
+__device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, const unsigned long long* __restrict__ best_key,
+                                              const uint32_t* __restrict__ hit_string, const uint32_t* __restrict__ t_off,
+                                              const uint2* __restrict__ sink, const uint32_t* __restrict__ str_len)
+{
+    MateBest m; m.has = false; m.score = INT_MIN; m.strand = 0; m.beg = m.end = 0xFFFFFFFFu; m.len = 0;
+    const unsigned long long key = best_key[r];
+    if (key == 0ull) return m;
+    const uint32_t h = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    m.has = true;
+    m.score = (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u);
+    m.strand = hit_string[h] % g.strands;
+    m.len = str_len[hit_string[h]];
+    m.end = t_off[h] + sink[h].x;
+    m.beg = m.end > m.len ? m.end - m.len : 0u;
+    return m;
+}
+
+// one thread per pair: concordance of the independent best alignments, else up to two opposite-mate jobs (slot 2p + anchor)
+__global__ void __launch_bounds__(256)
+pair_classify_kernel(const PipeGeom g, const uint32_t n_pairs, const nvb_pair_params pp,
+                     const unsigned long long* __restrict__ best_key, const uint32_t* __restrict__ hit_string,
+                     const uint32_t* __restrict__ t_off, const uint2* __restrict__ sink, const uint32_t* __restrict__ str_len,
+                     uint32_t* __restrict__ want, uint32_t* __restrict__ w_pstr, uint32_t* __restrict__ w_toff, uint32_t* __restrict__ w_tlen,
+                     int32_t* __restrict__ pair_score, uint32_t* __restrict__ pair_flags,
+                     int32_t* __restrict__ mate_score, uint32_t* __restrict__ mate_pos, uint8_t* __restrict__ mate_strand)
+{
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n_pairs) return;
+    MateBest m[2];
+    m[0] = mate_best(g, p, best_key, hit_string, t_off, sink, str_len);
+    m[1] = mate_best(g, n_pairs + p, best_key, hit_string, t_off, sink, str_len);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        mate_score[k * n_pairs + p] = m[k].score; mate_pos[k * n_pairs + p] = m[k].end; mate_strand[k * n_pairs + p] = (uint8_t)m[k].strand;
+    }
+    bool conc = m[0].has && m[1].has && (m[0].strand != m[1].strand);
+    if (conc) {
+        const MateBest& f = m[0].strand == 0 ? m[0] : m[1];
+        const MateBest& r = m[0].strand == 0 ? m[1] : m[0];
+        conc = f.beg <= r.beg && f.end <= r.end && r.end > f.beg && (r.end - f.beg) >= pp.min_frag && (r.end - f.beg) <= pp.max_frag;
+    }
+    if (conc) {
+        pair_score[p] = m[0].score + m[1].score; pair_flags[p] = NVB_PAIR_CONCORDANT;
+        want[2 * p] = want[2 * p + 1] = 0u;
+        return;
+    }
+    pair_score[p] = INT_MIN; pair_flags[p] = NVB_PAIR_UNPAIRED;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {                               // a = anchor mate, 1 - a = the mate to place
+        uint32_t w = 0u, ps = 0u, to = 0u, tl = 0u;
+        if (m[a].has && m[a].score >= pp.min_mate_score) {
+            const uint32_t o_read = (uint32_t)(1 - a) * n_pairs + p;
+            if (m[a].strand == 0u) { to = m[a].beg; const uint32_t e = (g.genome_len - to) < pp.max_frag ? g.genome_len : to + pp.max_frag; tl = e - to; ps = 2u * o_read + 1u; }
+            else                   { to = m[a].end > pp.max_frag ? m[a].end - pp.max_frag : 0u; tl = m[a].end - to; ps = 2u * o_read; }
+            w = (tl >= 1u && str_len[ps] >= 1u) ? 1u : 0u;
+        }
+        want[2 * p + a] = w; w_pstr[2 * p + a] = ps; w_toff[2 * p + a] = to; w_tlen[2 * p + a] = tl;
+    }
+}
+
+// counts[0] = jobs run (<= capacity), counts[1] = jobs wanted
+__global__ void pair_job_count_kernel(const uint32_t* __restrict__ job_idx, const uint32_t* __restrict__ want, uint32_t n_slots, uint32_t capacity,
+                                      uint32_t* __restrict__ counts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const uint32_t total = n_slots ? job_idx[n_slots - 1] + want[n_slots - 1] : 0u;
+        counts[0] = total < capacity ? total : capacity; counts[1] = total;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pair_compact_kernel(const PipeGeom g, const uint32_t n_slots, const uint32_t capacity, const uint32_t* __restrict__ want, const uint32_t* __restrict__ job_idx,
+                    const uint32_t* __restrict__ w_pstr, const uint32_t* __restrict__ w_toff, const uint32_t* __restrict__ w_tlen,
+                    const uint32_t* __restrict__ str_len,
+                    uint32_t* __restrict__ jp_off, uint32_t* __restrict__ jp_len, uint32_t* __restrict__ jt_off, uint32_t* __restrict__ jt_len)
+{
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_slots || !want[i]) return;
+    const uint32_t j = job_idx[i];
+    if (j >= capacity) return;
+    jp_off[j] = w_pstr[i] * g.stride; jp_len[j] = str_len[w_pstr[i]]; jt_off[j] = w_toff[i]; jt_len[j] = w_tlen[i];
+}
+
+__global__ void __launch_bounds__(256)
+pair_finalize_kernel(const uint32_t n_pairs, const nvb_pair_params pp, const uint32_t* __restrict__ want, const uint32_t* __restrict__ job_idx,
+                     const uint32_t* __restrict__ w_toff, const int32_t* __restrict__ rs_score, const uint2* __restrict__ rs_sink,
+                     int32_t* __restrict__ pair_score, uint32_t* __restrict__ pair_flags,
+                     int32_t* __restrict__ mate_score, uint32_t* __restrict__ mate_pos, uint8_t* __restrict__ mate_strand)
+{
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n_pairs || pair_flags[p] == NVB_PAIR_CONCORDANT) return;
+    int best_a = -1; int32_t best_sum = INT_MIN, best_rs = 0; uint32_t best_pos = 0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const uint32_t i = 2 * p + a;
+        if (!want[i]) continue;
+        const uint32_t j = job_idx[i];
+        if (j >= pp.rescue_capacity) continue;
+        const int32_t rs = rs_score[j];
+        if (rs < pp.min_mate_score) continue;
+        const int32_t sum = mate_score[a * n_pairs + p] + rs;
+        if (sum > best_sum) { best_sum = sum; best_a = a; best_rs = rs; best_pos = w_toff[i] + rs_sink[j].x; }
+    }
+    if (best_a < 0) return;
+    const int o = 1 - best_a;
+    pair_score[p] = best_sum;
+    pair_flags[p] = o == 0 ? NVB_PAIR_RESCUED_MATE1 : NVB_PAIR_RESCUED_MATE2;
+    mate_score[o * n_pairs + p] = best_rs;
+    mate_pos[o * n_pairs + p] = best_pos;
+    mate_strand[o * n_pairs + p] = (uint8_t)(1u - mate_strand[best_a * n_pairs + p]);
+}
+
 } // namespace nvb
 
 using namespace nvb;
@@ -314,8 +431,13 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     uint32_t* d_n_hits, uint32_t* d_hit_read, nvb_uint2* d_hit_window,
                     int32_t* d_hit_score, nvb_uint2* d_hit_sink,
                     const nvb_best_alignment_out* BA,
+                    const nvb_pair_params* PP, const nvb_pair_out* PO,
                     void* d_temp, size_t* temp_bytes, void* stream)
 {
+    if (PP) {
+        if (!PO || !PO->d_pair_score || !PO->d_pair_flags || !PO->d_mate_score || !PO->d_mate_pos || !PO->d_mate_strand) return NVB_E_INVALID;
+        if (!P || !P->both_strands || (n_reads & 1u) || PP->max_frag == 0 || PP->min_frag > PP->max_frag) return NVB_E_INVALID;
+    }
     if (BA && (!BA->d_ops || !BA->d_n_ops || !BA->d_begin || BA->max_ops == 0)) return NVB_E_INVALID;
     if (!valid_fmindex(fmi) || !fmi->d_ssa || !d_genome || !valid_strset(reads) || !P || !temp_bytes) return NVB_E_INVALID;
     if (reads->bits == 8) return NVB_E_UNSUPPORTED;
@@ -394,6 +516,25 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
                                                  nullptr, nullptr, nullptr, nullptr, BA->max_ops, nullptr, nullptr, &tb_bytes, stream);
         if (r != NVB_E_TEMP_SIZE && r != NVB_OK) return r;
         tb_tmp = tc.take<char>(tb_bytes);
+    }
+    // paired-end stage: job slots (2 per pair), compacted full-DP jobs and the DP's own temp
+    uint32_t *pw_want = nullptr, *pw_idx = nullptr, *pw_pstr = nullptr, *pw_toff = nullptr, *pw_tlen = nullptr, *pcounts = nullptr;
+    uint32_t *rp_off = nullptr, *rp_len = nullptr, *rt_off = nullptr, *rt_len = nullptr; int32_t* rs_score = nullptr; uint2* rs_sink = nullptr;
+    char *pscan_tmp = nullptr, *full_tmp = nullptr; size_t pscan_bytes = 0, full_bytes = 0;
+    nvb_string_set rpats = pats, rtxts = txts;
+    if (PP) {
+        const uint32_t cap = PP->rescue_capacity;
+        pw_want = tc.take<uint32_t>(n_reads); pw_idx = tc.take<uint32_t>(n_reads); pw_pstr = tc.take<uint32_t>(n_reads);
+        pw_toff = tc.take<uint32_t>(n_reads); pw_tlen = tc.take<uint32_t>(n_reads); pcounts = tc.take<uint32_t>(4);
+        rp_off = tc.take<uint32_t>(cap); rp_len = tc.take<uint32_t>(cap); rt_off = tc.take<uint32_t>(cap); rt_len = tc.take<uint32_t>(cap);
+        rs_score = tc.take<int32_t>(cap); rs_sink = tc.take<uint2>(cap);
+        NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, pscan_bytes, pw_want, pw_idx, (int)n_reads, as_stream(stream)));
+        pscan_tmp = tc.take<char>(pscan_bytes);
+        rtxts.length = PP->max_frag;
+        const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, &rtxts, (const uint32_t*)16, cap, (int32_t*)16, (nvb_uint2*)16,
+                                               nullptr, &full_bytes, stream);
+        if (r != NVB_E_TEMP_SIZE && r != NVB_OK) return r;
+        full_tmp = tc.take<char>(full_bytes);
     }
     const size_t need = tc.total();
     if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
@@ -499,6 +640,31 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         pipe_best_begin_kernel<<<rgrid, 256, 0, s>>>(g, best_key, bt_off, b_source, BA->d_n_ops, (uint2*)BA->d_begin);
         NVB_LAUNCH_CHECK();
     }
+    if (PP) {
+        const uint32_t n_pairs = n_reads / 2u, cap = PP->rescue_capacity;
+        const uint32_t pgrid = (n_pairs + 255) / 256, sgrid = (n_reads + 255) / 256;
+        pair_classify_kernel<<<pgrid, 256, 0, s>>>(g, n_pairs, *PP, best_key, hit_string, t_off, h_sink, str_len_,
+                                                    pw_want, pw_pstr, pw_toff, pw_tlen, PO->d_pair_score, PO->d_pair_flags,
+                                                    PO->d_mate_score, PO->d_mate_pos, PO->d_mate_strand);
+        NVB_LAUNCH_CHECK();
+        size_t sb = pscan_bytes;
+        NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(pscan_tmp, sb, pw_want, pw_idx, (int)n_reads, s));
+        pair_job_count_kernel<<<1, 32, 0, s>>>(pw_idx, pw_want, n_reads, cap, pcounts);
+        NVB_LAUNCH_CHECK();
+        if (cap) {
+            pair_compact_kernel<<<sgrid, 256, 0, s>>>(g, n_reads, cap, pw_want, pw_idx, pw_pstr, pw_toff, pw_tlen, str_len_, rp_off, rp_len, rt_off, rt_len);
+            NVB_LAUNCH_CHECK();
+            rpats.d_words = str_words; rpats.d_offsets = rp_off; rpats.d_lengths = rp_len;
+            rtxts.d_words = d_genome;  rtxts.d_offsets = rt_off; rtxts.d_lengths = rt_len;
+            size_t fb = full_bytes;
+            const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, &rtxts, pcounts, cap, rs_score, (nvb_uint2*)rs_sink, full_tmp, &fb, stream);
+            if (r != NVB_OK) return r;
+        }
+        pair_finalize_kernel<<<pgrid, 256, 0, s>>>(n_pairs, *PP, pw_want, pw_idx, pw_toff, rs_score, rs_sink, PO->d_pair_score, PO->d_pair_flags,
+                                                    PO->d_mate_score, PO->d_mate_pos, PO->d_mate_strand);
+        NVB_LAUNCH_CHECK();
+        if (PO->d_n_rescue) NVB_CUDA_TRY(cudaMemcpyAsync(PO->d_n_rescue, pcounts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
     if (!dedup) NVB_CUDA_TRY(cudaMemcpyAsync(counts + 2, counts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     NVB_STAGE(7);
@@ -515,7 +681,7 @@ extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome
                     void* d_temp, size_t* temp_bytes, void* stream)
 {
     return seed_extend_impl(fmi, d_genome, reads, n_reads, P, hit_capacity, d_best_score, d_best_pos, d_n_hits, d_hit_read, d_hit_window,
-                            d_hit_score, d_hit_sink, nullptr, d_temp, temp_bytes, stream);
+                            d_hit_score, d_hit_sink, nullptr, nullptr, nullptr, d_temp, temp_bytes, stream);
 }
 
 extern "C" int nvb_seed_extend_traceback(const nvb_fm_index* fmi, const uint32_t* d_genome,
@@ -529,5 +695,17 @@ extern "C" int nvb_seed_extend_traceback(const nvb_fm_index* fmi, const uint32_t
 {
     if (!best_alignment) return NVB_E_INVALID;
     return seed_extend_impl(fmi, d_genome, reads, n_reads, P, hit_capacity, d_best_score, d_best_pos, d_n_hits, d_hit_read, d_hit_window,
-                            d_hit_score, d_hit_sink, best_alignment, d_temp, temp_bytes, stream);
+                            d_hit_score, d_hit_sink, best_alignment, nullptr, nullptr, d_temp, temp_bytes, stream);
+}
+
+extern "C" int nvb_seed_extend_paired(const nvb_fm_index* fmi, const uint32_t* d_genome,
+                    const nvb_string_set* reads, uint32_t n_pairs,
+                    const nvb_seed_extend_params* P, uint32_t hit_capacity,
+                    const nvb_pair_params* pair_params, const nvb_pair_out* out,
+                    uint32_t* d_n_hits, void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!pair_params || !out || n_pairs > 0x3FFFFFFFu || !temp_bytes) return NVB_E_INVALID;
+    // the per-read best (score, end) of the single-end stage lands in the mate arrays first and is then refined per pair
+    return seed_extend_impl(fmi, d_genome, reads, 2u * n_pairs, P, hit_capacity, out->d_mate_score, out->d_mate_pos, d_n_hits, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, pair_params, out, d_temp, temp_bytes, stream);
 }

@@ -3,7 +3,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import Optional
 import torch
-from ._lib import lib, check, SeedExtendParamsStruct, BestAlignmentOutStruct
+from ._lib import lib, check, SeedExtendParamsStruct, BestAlignmentOutStruct, PairParamsStruct, PairOutStruct
 from .strings import PackedStringSet
 from .fmindex import FMIndexDevice
 from . import aln
@@ -95,6 +95,73 @@ def seed_extend(fmi: FMIndexDevice, genome: torch.Tensor, reads: PackedStringSet
         workspace = SeedExtendWorkspace(fmi, genome, reads, params, hit_capacity, keep_hits, traceback)
     tb = C.c_size_t(workspace.temp_bytes)
     check(_call(fmi, genome, reads, params, workspace, workspace.temp, tb), "nvb_seed_extend")
+    return workspace
+
+
+PAIR_UNPAIRED, PAIR_CONCORDANT, PAIR_RESCUED_MATE1, PAIR_RESCUED_MATE2 = 0, 1, 2, 4
+
+
+@dataclass
+class PairParams:
+    """fragment constraints of the paired-end stage (nvBowtie --minins / --maxins, FR orientation)"""
+    min_frag: int = 0
+    max_frag: int = 500
+    min_mate_score: int = 60          # a mate's alignment (anchor or rescued) must reach this score to take part in a pair
+    rescue_capacity: Optional[int] = None
+
+    def struct(self, n_pairs) -> PairParamsStruct:
+        p = PairParamsStruct()
+        p.min_frag, p.max_frag, p.min_mate_score = self.min_frag, self.max_frag, self.min_mate_score
+        p.rescue_capacity = 2 * n_pairs if self.rescue_capacity is None else self.rescue_capacity
+        return p
+
+
+class PairedWorkspace:
+    """outputs + temp storage of seed_extend_paired for repeated calls on equally-shaped batches"""
+
+    def __init__(self, fmi, genome, reads: PackedStringSet, params: SeedExtendParams, pair: PairParams, hit_capacity: int):
+        dev = fmi.device
+        assert reads.count % 2 == 0
+        self.n_pairs = n = reads.count // 2
+        self.hit_capacity = hit_capacity
+        self.pair_score = torch.empty(n, dtype=torch.int32, device=dev)
+        self.pair_flags = torch.empty(n, dtype=torch.int32, device=dev)
+        self.mate_score = torch.empty((2, n), dtype=torch.int32, device=dev)
+        self.mate_pos = torch.empty((2, n), dtype=torch.int32, device=dev)
+        self.mate_strand = torch.empty((2, n), dtype=torch.uint8, device=dev)
+        self.n_rescue = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.n_hits = torch.zeros(3, dtype=torch.int32, device=dev)
+        tb = C.c_size_t(0)
+        r = _call_paired(fmi, genome, reads, params, pair, self, None, tb)
+        if r != -2:
+            check(r, "nvb_seed_extend_paired(size query)")
+        self.temp = torch.empty(tb.value, dtype=torch.uint8, device=dev)
+        self.temp_bytes = tb.value
+
+
+def _call_paired(fmi, genome, reads, params, pair, ws, temp, tb):
+    s, rd, ps, pp = fmi.struct(), reads.struct(), params.struct(), pair.struct(ws.n_pairs)
+    po = PairOutStruct()
+    po.d_pair_score, po.d_pair_flags = ws.pair_score.data_ptr(), ws.pair_flags.data_ptr()
+    po.d_mate_score, po.d_mate_pos, po.d_mate_strand = ws.mate_score.data_ptr(), ws.mate_pos.data_ptr(), ws.mate_strand.data_ptr()
+    po.d_n_rescue = ws.n_rescue.data_ptr()
+    return lib().nvb_seed_extend_paired(C.byref(s), _p(genome), C.byref(rd), C.c_uint32(ws.n_pairs), C.byref(ps), C.c_uint32(ws.hit_capacity),
+                                        C.byref(pp), C.byref(po), _p(ws.n_hits), _p(temp), C.byref(tb),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+
+def seed_extend_paired(fmi: FMIndexDevice, genome: torch.Tensor, reads: PackedStringSet, params: SeedExtendParams, pair: PairParams,
+                       workspace: Optional[PairedWorkspace] = None, hit_capacity: Optional[int] = None):
+    """paired-end seed + extend (reads = mate 1 of every pair, then mate 2 of every pair): concordant pairs straight from the two
+    independent alignments, opposite-mate full-DP rescue for the rest (nvBowtie's best-approx paired flow,
+    score_opposite_inl.h:90-266).  Returns the workspace: .pair_score[n], .pair_flags[n], .mate_score/.mate_pos/.mate_strand[2,n],
+    .n_rescue[2] = (full-DP jobs run, wanted)"""
+    if workspace is None:
+        if hit_capacity is None:
+            hit_capacity = 32 * reads.count + 1024
+        workspace = PairedWorkspace(fmi, genome, reads, params, pair, hit_capacity)
+    tb = C.c_size_t(workspace.temp_bytes)
+    check(_call_paired(fmi, genome, reads, params, pair, workspace, workspace.temp, tb), "nvb_seed_extend_paired")
     return workspace
 
 

@@ -98,6 +98,37 @@ def sample_reads(genome_words, n, n_reads, read_len, sub_rate=0.01, indel_rate=0
     return torch.cat(out), torch.cat(poss), torch.cat(strands)
 
 
+def sample_pairs(genome_words, n, n_pairs, read_len, frag_mean=350.0, frag_sd=30.0, sub_rate=0.01, hard_frac=0.05, hard_sub_rate=0.2,
+                 device="cuda", seed=SEED_QUERIES ^ 0x7777, mut_seed=SEED_MUT ^ 0x7777, chunk=1 << 18):
+    """C5-shaped pairs, FR orientation: a fragment [p, p + frag) of the genome, one mate = its first read_len bases (forward), the
+    other = the reverse complement of its last read_len bases; odd pairs swap which mate is which.  A fraction `hard_frac` of the
+    second mates carries `hard_sub_rate` substitutions (mostly no exact seed survives: the opposite-mate rescue has to place them).
+    Returns (words [2*n_pairs, ceil(read_len/16)] int32 -- mate 1 of every pair, then mate 2 --, left int64[n_pairs], frag int64[n_pairs])"""
+    g, gm = _gen(seed, device), _gen(mut_seed, device)
+    m1, m2, lefts, frags = [], [], [], []
+    ar = torch.arange(read_len, device=device, dtype=torch.int64)[None, :]
+    for s in range(0, n_pairs, chunk):
+        m = min(chunk, n_pairs - s)
+        frag = (frag_mean + frag_sd * torch.randn(m, device=device, generator=g)).round().to(torch.int64).clamp_(read_len, int(frag_mean + 4 * frag_sd))
+        left = torch.randint(0, n - int(frag_mean + 4 * frag_sd) - 64, (m,), device=device, generator=g, dtype=torch.int64)
+        fw = gather_symbols(genome_words, left[:, None] + ar)
+        rv = (3 - gather_symbols(genome_words, (left + frag - read_len)[:, None] + ar)).flip(1)
+        swap = (torch.arange(s, s + m, device=device) & 1).bool()
+        a = torch.where(swap[:, None], rv, fw)
+        b = torch.where(swap[:, None], fw, rv)
+        hard = torch.rand(m, device=device, generator=gm) < hard_frac
+        for k, sym in enumerate((a, b)):
+            rate = torch.full((m, 1), sub_rate, device=device)
+            if k == 1:
+                rate = torch.where(hard[:, None], torch.full_like(rate, hard_sub_rate), rate)
+            rnd = torch.randint(0, 3, (m, read_len), device=device, generator=gm, dtype=torch.int64)
+            sub = torch.rand((m, read_len), device=device, generator=gm) < rate
+            sym = torch.where(sub, (sym + 1 + rnd) % 4, sym)
+            (m1 if k == 0 else m2).append(pack_2bit_be(sym))
+        lefts.append(left); frags.append(frag)
+    return torch.cat(m1 + m2), torch.cat(lefts), torch.cat(frags)
+
+
 def windows_for_reads(genome_len, pos, read_len, window_len, max_offset=15, device="cuda", seed=SEED_MUT ^ 0x5555):
     """C4: each read gets a `window_len` genome window containing it at offset <= max_offset"""
     g = _gen(seed, device)

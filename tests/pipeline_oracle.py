@@ -64,3 +64,81 @@ def seed_extend_oracle(O, idx, genome_sym, reads, params):
                 hit_window=np.array(wins, np.int64).reshape(-1, 2), hit_score=score.astype(np.int64),
                 hit_sink=np.stack([sx.astype(np.int64), sy.astype(np.int64)], axis=1) if len(sx) else np.zeros((0, 2), np.int64),
                 n_hits=len(hit_string))
+
+
+def seed_extend_paired_oracle(O, idx, genome_sym, reads, params, pair, n_pairs):
+    """Oracle composition of nvb_seed_extend_paired: the single-end composition above for the 2*n_pairs mates, the pairing rules of
+    include/nvbio_b200.h restated in Python, and the opposite-mate rescue scored by the oracle's full-matrix Gotoh.
+    reads: mate 1 of every pair, then mate 2.  Returns dict(pair_score, pair_flags, mate_score[2,n], mate_pos[2,n], mate_strand[2,n],
+    n_rescue)."""
+    se = seed_extend_oracle(O, idx, genome_sym, reads, params)
+    glen = idx.n
+    strands = 2
+    # best hit of every read: max score, ties -> smallest hit index
+    best_h = np.full(len(reads), -1, np.int64)
+    for h, s in enumerate(se["hit_string"]):
+        r = int(s) // strands
+        if best_h[r] < 0 or se["hit_score"][h] > se["hit_score"][best_h[r]]:
+            best_h[r] = h
+    INT_MIN = -2**31
+
+    def mate(r):
+        h = best_h[r]
+        if h < 0:
+            return dict(has=False, score=INT_MIN, strand=0, beg=0xFFFFFFFF, end=0xFFFFFFFF, len=0)
+        s = int(se["hit_string"][h])
+        ln = len(reads[r])
+        end = int(se["hit_window"][h][0] + se["hit_sink"][h][0])
+        return dict(has=True, score=int(se["hit_score"][h]), strand=s % strands, beg=max(end - ln, 0), end=end, len=ln)
+
+    cap = 2 * n_pairs if pair.rescue_capacity is None else pair.rescue_capacity
+    pair_score = np.full(n_pairs, INT_MIN, np.int64); pair_flags = np.zeros(n_pairs, np.int64)
+    mate_score = np.full((2, n_pairs), INT_MIN, np.int64); mate_pos = np.full((2, n_pairs), 0xFFFFFFFF, np.int64)
+    mate_strand = np.zeros((2, n_pairs), np.int64)
+    jobs = []          # (pair, anchor, pattern symbols, window begin, window length)
+    for p in range(n_pairs):
+        m = [mate(p), mate(n_pairs + p)]
+        for k in range(2):
+            mate_score[k, p], mate_pos[k, p], mate_strand[k, p] = m[k]["score"], m[k]["end"], m[k]["strand"]
+        conc = m[0]["has"] and m[1]["has"] and m[0]["strand"] != m[1]["strand"]
+        if conc:
+            f, r = (m[0], m[1]) if m[0]["strand"] == 0 else (m[1], m[0])
+            frag = r["end"] - f["beg"]
+            conc = f["beg"] <= r["beg"] and f["end"] <= r["end"] and r["end"] > f["beg"] and pair.min_frag <= frag <= pair.max_frag
+        if conc:
+            pair_score[p] = m[0]["score"] + m[1]["score"]; pair_flags[p] = 1
+            continue
+        for a in range(2):
+            if not (m[a]["has"] and m[a]["score"] >= pair.min_mate_score):
+                continue
+            o = reads[(1 - a) * n_pairs + p]
+            if m[a]["strand"] == 0:
+                to = m[a]["beg"]; te = min(to + pair.max_frag, glen)
+                pat = np.where(o < 4, 3 - o, o)[::-1].astype(np.uint8)
+            else:
+                to = max(m[a]["end"] - pair.max_frag, 0); te = m[a]["end"]
+                pat = o
+            if te - to >= 1 and len(pat) >= 1:
+                jobs.append((p, a, pat, to, te - to))
+    wanted = len(jobs)
+    run = jobs[:cap]
+    if run:
+        pats = np.concatenate([j[2] for j in run])
+        p_len = np.array([len(j[2]) for j in run], np.uint32)
+        p_off = (np.cumsum(p_len) - p_len).astype(np.uint32)
+        t_off = np.array([j[3] for j in run], np.uint32); t_len = np.array([j[4] for j in run], np.uint32)
+        sch = params.scheme
+        rs, rx, _ = O.gotoh_full(params.type, (sch.match, sch.mismatch, sch.gap_open, sch.gap_ext), pats, p_off, p_len, genome_sym, t_off, t_len)
+        cand = {}
+        for (p, a, _, to, _), s, x in zip(run, rs, rx):
+            if int(s) < pair.min_mate_score:
+                continue
+            tot = int(mate_score[a, p]) + int(s)
+            if p not in cand or tot > cand[p][0]:
+                cand[p] = (tot, a, int(s), to + int(x))
+        for p, (tot, a, s, pos) in cand.items():
+            o = 1 - a
+            pair_score[p] = tot; pair_flags[p] = 2 if o == 0 else 4
+            mate_score[o, p] = s; mate_pos[o, p] = pos; mate_strand[o, p] = 1 - mate_strand[a, p]
+    return dict(pair_score=pair_score, pair_flags=pair_flags, mate_score=mate_score, mate_pos=mate_pos, mate_strand=mate_strand,
+                n_rescue=(len(run), wanted))

@@ -184,3 +184,41 @@ def test_best_alignment_traceback():
     assert checked > 0.9 * n_reads
     # indel-carrying reads produce I/D ops
     assert (ops == 1).any() and (ops == 2).any()
+
+
+def test_paired_end_vs_oracle():
+    """nvb_seed_extend_paired == the oracle composition (single-end stages + pairing rules + opposite-mate full-matrix Gotoh):
+    concordant pairs, rescued mates (heavily mutated second mates), unpaired (mates from different loci, too-far fragments),
+    every output array; plus a capacity-limited run"""
+    from tests.pipeline_oracle import seed_extend_paired_oracle
+    require_gpu()
+    O = orc.Oracle()
+    n = 300_000
+    gw = synth.random_genome_words(n, seed=78)
+    gsym = unpack_symbols(host_u32(gw), n)
+    idx = O.build_index(gsym)
+    fmi = nb.FMIndexDevice.from_host(idx.bwt_occ, idx.ssa, idx.L2, idx.n, idx.primary)
+    n_pairs, L = 500, 100
+    rw, left, frag = synth.sample_pairs(gw, n, n_pairs, L, frag_mean=300, frag_sd=40, sub_rate=0.02, hard_frac=0.3, hard_sub_rate=0.2, seed=11, mut_seed=12)
+    rw = rw.clone()
+    # discordant cases: second mates of a few pairs taken from another pair (different locus), a few fragments beyond max_frag
+    rw[n_pairs + 5:n_pairs + 25] = rw[n_pairs + 105:n_pairs + 125].clone()
+    wpr = rw.shape[1]
+    reads_sym = [unpack_symbols(host_u32(rw[i]), L) for i in range(2 * n_pairs)]
+    rs = PackedStringSet.fixed(rw.reshape(-1), 2 * n_pairs, L, stride=wpr * 16)
+    params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=True,
+                                 max_seed_hits=50, scheme=aln.SimpleGotohScheme(2, -2, -5, -3))
+    for pair in (nb.PairParams(min_frag=0, max_frag=420, min_mate_score=50), nb.PairParams(min_frag=250, max_frag=330, min_mate_score=80),
+                 nb.PairParams(min_frag=0, max_frag=420, min_mate_score=50, rescue_capacity=37)):
+        ws = nb.seed_extend_paired(fmi, gw, rs, params, pair, hit_capacity=64 * 2 * n_pairs)
+        torch.cuda.synchronize()
+        want = seed_extend_paired_oracle(O, idx, gsym, reads_sym, params, pair, n_pairs)
+        assert tuple(int(v) for v in ws.n_rescue.cpu()) == want["n_rescue"]
+        assert np.array_equal(ws.pair_flags.cpu().numpy().astype(np.int64), want["pair_flags"])
+        assert np.array_equal(ws.pair_score.cpu().numpy().astype(np.int64), want["pair_score"])
+        assert np.array_equal(ws.mate_score.cpu().numpy().astype(np.int64), want["mate_score"])
+        assert np.array_equal(host_u32(ws.mate_pos).astype(np.int64), want["mate_pos"])
+        assert np.array_equal(ws.mate_strand.cpu().numpy().astype(np.int64), want["mate_strand"])
+        fl = want["pair_flags"]
+        if pair.rescue_capacity is None and pair.min_frag == 0:
+            assert (fl == 1).sum() > 0.5 * n_pairs and ((fl == 2) | (fl == 4)).sum() > 0.1 * n_pairs and (fl == 0).sum() >= 10

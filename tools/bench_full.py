@@ -14,7 +14,10 @@ def time_ms(fn, reps=3):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
 
-for (n, M, N) in ((200_000, 150, 500), (1_000_000, 150, 300), (10_000, 100, 1000), (100_000, 100, 1000)):
+CONFIGS = ((200_000, 150, 500), (1_000_000, 150, 300), (10_000, 100, 1000), (100_000, 100, 1000))
+if "--one" in sys.argv:
+    CONFIGS = CONFIGS[:1]
+for (n, M, N) in CONFIGS:
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     pw = torch.randint(-2**31, 2**31, (n, (M + 15) // 16), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
     tw = torch.randint(-2**31, 2**31, (n, (N + 15) // 16), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
