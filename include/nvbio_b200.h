@@ -198,6 +198,20 @@ int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb
                              const uint32_t* d_n, uint32_t n_max,
                              int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream);
 
+/* Full-matrix Gotoh traceback: score + sink as nvb_gotoh_score, plus the alignment itself.
+ *   d_ops[i*max_ops ..]  the backtracer's pushes in END -> START order (0 = SUBSTITUTION 'M', 1 = INSERTION 'I' (pattern symbol
+ *                        against a gap), 2 = DELETION 'D'), d_n_ops[i] their number (may exceed max_ops: then truncated)
+ *   d_source[i]          = (text begin, pattern begin) of the alignment; the soft clips of the pattern are
+ *                          pattern_len - sink.y at the end and source.y at the start
+ * Replaces aln::alignment_traceback<MAX_PATTERN_LEN,MAX_TEXT_LEN,CHECKPOINTS> with a Gotoh aligner (generic driver
+ * nvbio/alignment/alignment_inl.h:365-530; state machine gotoh/gotoh_inl.h:1806-1884) and its batched form
+ * BatchedAlignmentTraceback (batched_inl.h:607-860).  No checkpoints: d_temp holds the whole direction matrix, 4 bits per cell
+ * (max_text_len * ceil(max_pattern_len/32) * 16 bytes per alignment). */
+int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+                        int32_t* d_score, nvb_uint2* d_sink, nvb_uint2* d_source,
+                        uint8_t* d_ops, uint32_t max_ops, uint32_t* d_n_ops,
+                        void* d_temp, size_t* temp_bytes, void* stream);
+
 /* Banded Gotoh traceback.  For i < n: score, sink (end cells) as nvb_banded_gotoh_score, plus the
  * source (start cells) and the alignment as the backtracer's pushes in END -> START order, one byte per op
  * (0 = SUBSTITUTION 'M', 1 = INSERTION 'I', 2 = DELETION 'D'; nvbio::aln::DirectionVector) at d_ops[i*max_ops ..];

@@ -183,3 +183,31 @@ def batch_alignment_score(aligner: GotohAligner, patterns: PackedStringSet, text
     temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
     check(call(C.c_void_p(temp.data_ptr())), "nvb_gotoh_score")
     return score, sink
+
+
+def batch_alignment_traceback(aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet, max_ops: Optional[int] = None):
+    """aln::alignment_traceback (full-matrix Gotoh) for a batch (nvbio/alignment/alignment_inl.h:365-530, batched_inl.h:607-860).
+    Returns dict(score[n], sink[n,2], source[n,2], ops[n,max_ops] uint8 in END->START push order (0 M, 1 I, 2 D), n_ops[n])."""
+    L = lib()
+    n = patterns.count
+    dev = patterns.words.device
+    if max_ops is None:
+        max_ops = patterns.length + texts.length + 1
+    out = dict(score=torch.empty(n, dtype=torch.int32, device=dev), sink=torch.empty((n, 2), dtype=torch.int32, device=dev),
+               source=torch.empty((n, 2), dtype=torch.int32, device=dev), ops=torch.zeros((n, max_ops), dtype=torch.uint8, device=dev),
+               n_ops=torch.empty(n, dtype=torch.int32, device=dev))
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    tb = C.c_size_t(0)
+
+    def call(temp_ptr):
+        return L.nvb_gotoh_traceback(C.c_int(aligner.type), C.byref(sch), C.byref(p), C.byref(t), C.c_uint32(n),
+                                     C.c_void_p(out["score"].data_ptr()), C.c_void_p(out["sink"].data_ptr()),
+                                     C.c_void_p(out["source"].data_ptr()), C.c_void_p(out["ops"].data_ptr()), C.c_uint32(max_ops),
+                                     C.c_void_p(out["n_ops"].data_ptr()), temp_ptr, C.byref(tb), _stream())
+    r = call(None)
+    if r != -2:
+        check(r, "nvb_gotoh_traceback(size query)")
+    temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
+    check(call(C.c_void_p(temp.data_ptr())), "nvb_gotoh_traceback")
+    return out

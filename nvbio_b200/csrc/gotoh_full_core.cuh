@@ -18,11 +18,14 @@ namespace nvb {
 
 constexpr int FULL_W = 32;     // pattern columns per stripe
 
-template <int TYPE>
-__host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
+// DIRS: also emit the 4-bit direction vector of every cell (H source | E extended | F extended; the bits
+// GotohSubmatrixContext::new_cell stores, gotoh_inl.h:426-446) to dirs[row * dir_row_words + stripe * 4 ..]: one uint4 per
+// (text row, 32-column stripe), nibble k of word w = pattern column 32*stripe + 8*w + k.
+template <int TYPE, bool DIRS>
+__host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
-        int2* __restrict__ col, size_t col_stride)
+        int2* __restrict__ col, size_t col_stride, uint32_t* __restrict__ dirs = nullptr, uint32_t dir_row_words = 0)
 {
     SinkResult res; res.score = INT_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
     if (M == 0 || N == 0) return res;            // outside the supported domain (see header)
@@ -55,12 +58,23 @@ __host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
             int32_t Hd = diag_next;
             diag_next = Hl;
             H[0] = Hl;
+            uint32_t dw[4] = { 0u, 0u, 0u, 0u };
 #pragma unroll
             for (int j = 1; j <= FULL_W; ++j) {
-                F[j] = imax2(F[j] + Ge, H[j] + Go);                   // H[j] still holds the previous row
-                E    = imax2(E + Ge, H[j - 1] + Go);                  // H[j-1] is already this row
-                int32_t h = imax2(imax2(E, F[j]), Hd + ((g == q[j - 1]) ? S.match : S.mismatch));
+                const int32_t ftop = F[j] + Ge, htop = H[j] + Go;         // H[j] still holds the previous row
+                F[j] = imax2(ftop, htop);
+                const int32_t eleft = E + Ge, hleft = H[j - 1] + Go;      // H[j-1] is already this row
+                E    = imax2(eleft, hleft);
+                const int32_t diagonal = Hd + ((g == q[j - 1]) ? S.match : S.mismatch);
+                int32_t h = imax2(imax2(E, F[j]), diagonal);
                 if (TYPE == NVB_LOCAL) h = imax2(h, 0);
+                if (DIRS) {
+                    const int32_t top = F[j], left = E;
+                    uint32_t d = top > left ? (top > diagonal ? (uint32_t)DIR_DEL : (uint32_t)DIR_SUB) : (left > diagonal ? (uint32_t)DIR_INS : (uint32_t)DIR_SUB);
+                    if (TYPE == NVB_LOCAL && h == 0) d = DIR_SINK;
+                    d |= (eleft > hleft ? (uint32_t)DIR_INS_EXT : 0u) | (ftop > htop ? (uint32_t)DIR_DEL_EXT : 0u);
+                    dw[(j - 1) >> 3] |= d << (4 * ((j - 1) & 7));
+                }
                 Hd = H[j];
                 H[j] = h;
                 if (TYPE == NVB_LOCAL && b + (uint32_t)j <= M) {
@@ -69,6 +83,10 @@ __host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
                 }
             }
             if (!last) col[(size_t)r * col_stride] = make_int2(H[FULL_W], E);
+            if (DIRS) {
+                uint32_t* dp = dirs + (size_t)r * dir_row_words + (b / FULL_W) * 4u;
+                dp[0] = dw[0]; dp[1] = dw[1]; dp[2] = dw[2]; dp[3] = dw[3];
+            }
             if (TYPE == NVB_SEMI_GLOBAL && last) {
                 int32_t hM = H[1];
 #pragma unroll
@@ -89,6 +107,42 @@ __host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
         }
     }
     return res;
+}
+
+template <int TYPE>
+__host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
+        int2* __restrict__ col, size_t col_stride)
+{
+    return gotoh_full_impl<TYPE, false>(S, pwords, pbits, pbe, poff, M, twords, tbits, tbe, toff, N, col, col_stride);
+}
+
+// walk the direction matrix from the sink (state machine of nvbio/alignment/gotoh/gotoh_inl.h:1806-1884 plus the first-row /
+// first-column completion of the generic driver, alignment_inl.h:452-471); ops in END -> START order, returns their number
+template <int TYPE>
+__host__ __device__ inline uint32_t gotoh_full_walk(const uint32_t* __restrict__ dirs, uint32_t dir_row_words, const SinkResult& sink,
+                                                    uint8_t* __restrict__ ops, uint32_t max_ops, uint32_t& src_x, uint32_t& src_y)
+{
+    int32_t row = (int32_t)sink.x, col = (int32_t)sink.y - 1;          // row 1-based over the text, col 0-based over the pattern
+    uint32_t n_ops = 0, state = 0;                                      // HSTATE 0, ESTATE 1, FSTATE 2
+    while (row > 0 && col >= 0) {
+        const uint32_t op = (dirs[(size_t)(row - 1) * dir_row_words + ((uint32_t)col >> 3)] >> (4 * (col & 7))) & 15u;
+        const uint32_t h_op = op & 3u;
+        if (TYPE == NVB_LOCAL && state == 0 && h_op == DIR_SINK) break;
+        if (state == 1)      { if ((op & DIR_INS_EXT) == 0) state = 0; --col; if (n_ops < max_ops) ops[n_ops] = DIR_INS; ++n_ops; }
+        else if (state == 2) { if ((op & DIR_DEL_EXT) == 0) state = 0; --row; if (n_ops < max_ops) ops[n_ops] = DIR_DEL; ++n_ops; }
+        else {
+            if (h_op == DIR_INS) state = 1;
+            else if (h_op == DIR_DEL) state = 2;
+            else { --row; --col; if (n_ops < max_ops) ops[n_ops] = DIR_SUB; ++n_ops; }
+        }
+    }
+    uint32_t sx = (uint32_t)row, sy = (uint32_t)(col + 1);
+    if (TYPE != NVB_LOCAL && sx == 0u) for (; sy > 0u; --sy) { if (n_ops < max_ops) ops[n_ops] = DIR_INS; ++n_ops; }
+    if (TYPE == NVB_GLOBAL && sy == 0u) for (; sx > 0u; --sx) { if (n_ops < max_ops) ops[n_ops] = DIR_DEL; ++n_ops; }
+    src_x = sx; src_y = sy;
+    return n_ops;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -142,6 +142,34 @@ gotoh_full_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ co
     b.sink[a]  = make_uint2(r.x, r.y);
 }
 
+struct TracebackOut {
+    uint2* source; uint8_t* ops; uint32_t* n_ops; uint32_t max_ops; uint32_t* dirs; uint32_t dir_rows;
+};
+
+// full-matrix traceback: one alignment per thread; the DP writes one uint4 of direction nibbles per (text row, 32-column
+// stripe) to the alignment's slot, the same thread then walks it back from the sink
+template <int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_full_traceback_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ col, const TracebackOut o, const uint32_t dir_row_words)
+{
+    const uint32_t n = batch_count(b);
+    const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
+    if (a >= n) return;
+    uint32_t* dirs = o.dirs + (size_t)a * o.dir_rows * dir_row_words;
+    const uint32_t M = str_len(b.pat, a), N = str_len(b.txt, a);
+    SinkResult r; r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu;
+    if (N <= o.dir_rows && (M + 31u) / 32u * 4u <= dir_row_words)
+        r = gotoh_full_impl<TYPE, true>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), M,
+                                        b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), N, col + a, (size_t)b.n_max, dirs, dir_row_words);
+    b.score[a] = r.score;
+    b.sink[a]  = make_uint2(r.x, r.y);
+    uint32_t sx = 0xFFFFFFFFu, sy = 0xFFFFFFFFu, cnt = 0;
+    if (r.x != 0xFFFFFFFFu && r.y != 0xFFFFFFFFu)
+        cnt = gotoh_full_walk<TYPE>(dirs, dir_row_words, r, o.ops + (size_t)a * o.max_ops, o.max_ops, sx, sy);
+    o.source[a] = make_uint2(sx, sy);
+    o.n_ops[a]  = cnt;
+}
+
 // full-matrix Gotoh, packed: one PAIR of alignments per thread (a, a+1); pairs that break a precondition of the packed
 // path go to the todo list and are scored by gotoh_full_todo_kernel (int32)
 template <int TYPE, int MINB>
@@ -191,9 +219,6 @@ gotoh_full_todo_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict
 // traceback: one alignment per thread; DP with direction vectors into a per-alignment global scratch matrix
 // (M rows x DirWords<B>::N words -- no checkpoints / recomputation: 2.4 KB per 150 x 31 alignment is nothing in 180 GB),
 // then the H/E/F state-machine walk from the sink.
-struct TracebackOut {
-    uint2* source; uint8_t* ops; uint32_t* n_ops; uint32_t max_ops; uint32_t* dirs; uint32_t dir_rows;
-};
 
 template <int B, int TYPE>
 __global__ void __launch_bounds__(GENERIC_BLOCKDIM)
@@ -456,6 +481,41 @@ int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* s
     TracebackOut o;
     o.source = (uint2*)d_source; o.ops = d_ops; o.n_ops = d_n_ops; o.max_ops = max_ops; o.dirs = dirs; o.dir_rows = max_m;
     return dispatch_traceback(band_len, type, make_scheme(scheme), b, o, as_stream(stream));
+}
+
+int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+                        int32_t* d_score, nvb_uint2* d_sink, nvb_uint2* d_source,
+                        uint8_t* d_ops, uint32_t max_ops, uint32_t* d_n_ops,
+                        void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
+    if (type < 0 || type > 2) return NVB_E_INVALID;
+    if (scheme->d_qual_table) return NVB_E_UNSUPPORTED;
+    if (texts->length > 65535u || patterns->length > 65535u) return NVB_E_UNSUPPORTED;
+    const uint32_t max_m = patterns->length ? patterns->length : 1u, max_n = texts->length ? texts->length : 1u;
+    const uint32_t dir_row_words = (max_m + 31u) / 32u * 4u;
+    TempCarver tc(d_temp);
+    int2* col = tc.take<int2>((size_t)n * max_n);
+    uint32_t* dirs = tc.take<uint32_t>((size_t)n * max_n * dir_row_words);
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    if (n == 0) return NVB_OK;
+    if (!d_score || !d_sink || !d_source || !d_ops || !d_n_ops || max_ops == 0) return NVB_E_INVALID;
+    GotohBatch b;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = nullptr;
+    b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
+    TracebackOut o;
+    o.source = (uint2*)d_source; o.ops = d_ops; o.n_ops = d_n_ops; o.max_ops = max_ops; o.dirs = dirs; o.dir_rows = max_n;
+    const GotohScheme S = make_scheme(scheme);
+    const uint32_t grid = (n + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
+    cudaStream_t s = as_stream(stream);
+    switch (type) {
+    case NVB_GLOBAL: gotoh_full_traceback_kernel<NVB_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, o, dir_row_words); break;
+    case NVB_LOCAL:  gotoh_full_traceback_kernel<NVB_LOCAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, o, dir_row_words); break;
+    default:         gotoh_full_traceback_kernel<NVB_SEMI_GLOBAL><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, o, dir_row_words); break;
+    }
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
 }
 
 // test hook (declared in tests only): 0 = auto, 1 = generic int32 kernel for everything

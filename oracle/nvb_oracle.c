@@ -559,3 +559,99 @@ void orc_gotoh_full(int type, const orc_scheme* S,
     for (u32 i = 0; i < n; ++i)
         orc_gotoh_full_one(type, S, pat + p_off[i], p_len[i], txt + t_off[i], t_len[i], &score[i], &sink_x[i], &sink_y[i]);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * full-matrix Gotoh traceback: aln::alignment_traceback<MAX_PATTERN_LEN,MAX_TEXT_LEN,CHECKPOINTS> with a Gotoh aligner
+ * (generic driver nvbio/alignment/alignment_inl.h:365-488; direction vectors gotoh/gotoh_inl.h:514-555 + :426-446;
+ * state machine gotoh/gotoh_inl.h:1806-1884).  The checkpointing of the reference only bounds its memory: here the whole
+ * direction matrix is kept.  Per cell: hdir = top > left ? (top > diag ? DEL : SUB) : (left > diag ? INS : SUB) with
+ * top = F (text gap, DELETION), left = E (pattern gap, INSERTION); LOCAL cells with H == 0 are SINKs; the E / F extension
+ * bits say whether E / F were extended rather than opened.  Walk from the sink: H -> follow hdir; E -> push INSERTION, column-1,
+ * stay in E while the bit is set; F likewise with DELETION, row-1.  SEMI_GLOBAL / GLOBAL finish along the first row
+ * (INSERTIONs), GLOBAL along the first column (DELETIONs).  ops in END -> START order; clips = (M - sink.y, source.y).
+ * ---------------------------------------------------------------------------------------------- */
+u32 orc_gotoh_full_traceback_one(int type, const orc_scheme* S, const u8* P, u32 M, const u8* T, u32 N,
+                                 i32* out_score, u32* sink_xy, u32* source_xy, u8* ops, u32 max_ops, u32* clips)
+{
+    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    *out_score = best; sink_xy[0] = sink_xy[1] = source_xy[0] = source_xy[1] = 0xFFFFFFFFu; clips[0] = clips[1] = 0;
+    if (M == 0 || N == 0) return 0;
+    const i32 Go = S->pattern_gap_open, Ge = S->pattern_gap_ext;
+    const i32 INF = SHRT_MIN - (Go < Ge ? Go : Ge);
+    const size_t W = (size_t)M + 1;
+    i32* H = (i32*)malloc(sizeof(i32) * (N + 1) * W);
+    i32* Fp = (i32*)malloc(sizeof(i32) * W);                 /* F of the previous row */
+    u8* dir = (u8*)malloc((size_t)N * M);
+    for (u32 c = 0; c <= M; ++c) { H[c] = (type != 1) ? (c > 0 ? Go + Ge * (i32)(c - 1) : 0) : 0; Fp[c] = INF; }
+    for (u32 r = 1; r <= N; ++r)
+    {
+        H[r * W] = (type == 0) ? S->text_gap_open + S->text_gap_ext * (i32)(r - 1) : 0;
+        i32 E = (type == 1) ? 0 : INF;
+        for (u32 c = 1; c <= M; ++c)
+        {
+            const i32 ftop = Fp[c] + Ge, htop = H[(r - 1) * W + c] + Go;
+            const i32 f = imax(ftop, htop);
+            const u8 fdir = ftop > htop ? D_DEL_EXT : D_SUB;
+            const i32 eleft = E + Ge, hleft = H[r * W + c - 1] + Go;
+            E = imax(eleft, hleft);
+            const u8 edir = eleft > hleft ? D_INS_EXT : D_SUB;
+            const i32 diagonal = H[(r - 1) * W + c - 1] + ((T[r - 1] == P[c - 1]) ? S->match : S->mismatch);
+            const i32 top = f, left = E;
+            i32 h = imax(imax(left, top), diagonal);
+            if (type == 1) h = imax(h, 0);
+            u8 hdir = top > left ? (top > diagonal ? D_DEL : D_SUB) : (left > diagonal ? D_INS : D_SUB);
+            if (type == 1 && h == 0) hdir = D_SINK;
+            Fp[c] = f; H[r * W + c] = h;
+            dir[(size_t)(r - 1) * M + (c - 1)] = (u8)(hdir | edir | fdir);
+        }
+    }
+    if (type == 1)
+    {
+        for (u32 b = 0; b < M; b += 8)
+            for (u32 r = 1; r <= N; ++r)
+                for (u32 c = b + 1; c <= b + 8 && c <= M; ++c)
+                    sink_report(&best, &bx, &by, H[r * W + c], r, c);
+    }
+    else if (type == 2) { for (u32 r = 1; r <= N; ++r) sink_report(&best, &bx, &by, H[r * W + M], r, M); }
+    else sink_report(&best, &bx, &by, H[N * W + M], N, M);
+    *out_score = best;
+    u32 n_ops = 0;
+    if (bx != 0xFFFFFFFFu && by != 0xFFFFFFFFu)
+    {
+        sink_xy[0] = bx; sink_xy[1] = by;
+        clips[0] = M - by;
+        i32 row = (i32)bx, col = (i32)by - 1;          /* row 1-based over the text, col 0-based over the pattern */
+        int state = 0;                                  /* HSTATE 0, ESTATE 1, FSTATE 2 */
+        while (row > 0 && col >= 0)
+        {
+            const u8 op = dir[(size_t)(row - 1) * M + col];
+            const u8 h_op = op & 3u;
+            if (type == 1 && state == 0 && h_op == D_SINK) break;
+            if (state == 1)      { if ((op & D_INS_EXT) == 0) state = 0; --col; if (n_ops < max_ops) ops[n_ops] = D_INS; ++n_ops; }
+            else if (state == 2) { if ((op & D_DEL_EXT) == 0) state = 0; --row; if (n_ops < max_ops) ops[n_ops] = D_DEL; ++n_ops; }
+            else
+            {
+                if (h_op == D_INS) state = 1;
+                else if (h_op == D_DEL) state = 2;
+                else { --row; --col; if (n_ops < max_ops) ops[n_ops] = D_SUB; ++n_ops; }
+            }
+        }
+        u32 sx = (u32)row, sy = (u32)(col + 1);
+        if (type != 1 && sx == 0) for (; sy > 0; --sy) { if (n_ops < max_ops) ops[n_ops] = D_INS; ++n_ops; }
+        if (type == 0 && sy == 0) for (; sx > 0; --sx) { if (n_ops < max_ops) ops[n_ops] = D_DEL; ++n_ops; }
+        source_xy[0] = sx; source_xy[1] = sy;
+        clips[1] = sy;
+    }
+    free(H); free(Fp); free(dir);
+    return n_ops;
+}
+
+void orc_gotoh_full_traceback(int type, const orc_scheme* S,
+                              const u8* pat, const u32* p_off, const u32* p_len,
+                              const u8* txt, const u32* t_off, const u32* t_len, u32 n, u32 max_ops,
+                              i32* score, u32* sink_xy, u32* source_xy, u8* ops, u32* n_ops, u32* clips)
+{
+    for (u32 i = 0; i < n; ++i)
+        n_ops[i] = orc_gotoh_full_traceback_one(type, S, pat + p_off[i], p_len[i], txt + t_off[i], t_len[i],
+                                                &score[i], &sink_xy[2 * i], &source_xy[2 * i], ops + (size_t)i * max_ops, max_ops, &clips[2 * i]);
+}

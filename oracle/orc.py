@@ -157,6 +157,18 @@ def _oracle_traceback(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_
     return o
 
 
+def _oracle_full_traceback(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=1024):
+    """Oracle.gotoh_full_traceback: aln::alignment_traceback restated; ops END->START (0 M, 1 I, 2 D)"""
+    pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
+    if len(scheme) == 4:
+        scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+    s = np.array(scheme, dtype=np.int32)
+    self.lib.orc_gotoh_full_traceback(C.c_int(typ), _p(s), _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len),
+                                      C.c_uint32(n), C.c_uint32(max_ops), _p(o["score"]), _p(o["sink"]), _p(o["source"]), _p(o["ops"]),
+                                      _p(o["n_ops"]), _p(o["clips"]))
+    return o
+
+
 def _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops):
     pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
     p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
@@ -237,6 +249,15 @@ class Ref(_Base):
                             C.c_uint32(idx.primary), _p(rows), C.c_uint32(len(rows)), _p(out))
         return out
 
+    def gotoh_full_traceback(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=1024):
+        """aln::alignment_traceback<256,512,64>: ops in END->START push order (0 M, 1 I, 2 D)"""
+        pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
+        r = self.lib.ref_gotoh_full_traceback(C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]), C.c_int(scheme[2]), C.c_int(scheme[3]),
+                                              _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n), C.c_uint32(max_ops),
+                                              _p(o["score"]), _p(o["sink"]), _p(o["source"]), _p(o["ops"]), _p(o["n_ops"]), _p(o["clips"]))
+        assert r == 0, r
+        return o
+
     def banded_traceback(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=512):
         """aln::banded_alignment_traceback: ops in END->START push order (0 M, 1 I, 2 D)"""
         pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
@@ -291,6 +312,7 @@ def dna(s):
 
 
 Oracle.banded_traceback = _oracle_traceback
+Oracle.gotoh_full_traceback = _oracle_full_traceback
 
 
 def _full_args(pat, p_off, p_len, txt, t_off, t_len):

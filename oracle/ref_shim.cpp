@@ -167,9 +167,55 @@ void run_full(const aln::SimpleGotohScheme scheme,
     }
 }
 
+// full-matrix traceback through the reference's generic driver (alignment_inl.h:498-530) with its stack-allocated
+// checkpoints: patterns up to 256, texts up to 512 symbols, a checkpoint every 64 pattern columns
+template <aln::AlignmentType TYPE>
+void run_full_traceback(const aln::SimpleGotohScheme scheme,
+                   const uint8* pat, const uint32* p_off, const uint32* p_len,
+                   const uint8* txt, const uint32* t_off, const uint32* t_len,
+                   uint32 n, uint32 max_ops, int32* score, uint32* sink_xy, uint32* source_xy,
+                   uint8* ops, uint32* n_ops, uint32* clips)
+{
+    #pragma omp parallel for schedule(dynamic,4)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        RecordingBacktracer bt; bt.ops = ops + uint64(i)*max_ops; bt.n = 0; bt.cap = max_ops; bt.n_clips = 0; bt.clips[0] = bt.clips[1] = 0;
+        const aln::Alignment<int32> a = aln::alignment_traceback<256u,512u,64u>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),
+            str_view( p_len[i], pat + p_off[i] ),
+            aln::trivial_quality_string(),
+            str_view( t_len[i], txt + t_off[i] ),
+            INT_MIN,
+            bt );
+        score[i] = a.score;
+        sink_xy[2*i] = a.sink.x;     sink_xy[2*i+1] = a.sink.y;
+        source_xy[2*i] = a.source.x; source_xy[2*i+1] = a.source.y;
+        n_ops[i] = bt.n;
+        clips[2*i] = bt.clips[0]; clips[2*i+1] = bt.clips[1];
+    }
+}
+
 } // anonymous namespace
 
 extern "C" {
+
+// full-matrix Gotoh traceback: aln::alignment_traceback<256,512,64> (nvbio/alignment/alignment_inl.h:365-530)
+int ref_gotoh_full_traceback(int type, int match, int mismatch, int gap_open, int gap_ext,
+                     const uint8* pat, const uint32* p_off, const uint32* p_len,
+                     const uint8* txt, const uint32* t_off, const uint32* t_len,
+                     uint32 n, uint32 max_ops, int32* score, uint32* sink_xy, uint32* source_xy,
+                     uint8* ops, uint32* n_ops, uint32* clips)
+{
+    const aln::SimpleGotohScheme s( match, mismatch, gap_open, gap_ext );
+    for (uint32 i = 0; i < n; ++i) if (p_len[i] > 256u || t_len[i] > 512u) return -2;
+    switch (type)
+    {
+    case 0: run_full_traceback<aln::GLOBAL>     ( s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips ); return 0;
+    case 1: run_full_traceback<aln::LOCAL>      ( s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips ); return 0;
+    case 2: run_full_traceback<aln::SEMI_GLOBAL>( s, pat,p_off,p_len, txt,t_off,t_len, n, max_ops, score,sink_xy,source_xy,ops,n_ops,clips ); return 0;
+    }
+    return -1;
+}
 
 // full-matrix Gotoh score: aln::alignment_score<MAX_TEXT_LEN>(GotohAligner<TYPE,SimpleGotohScheme>, ...)
 // (nvbio/alignment/alignment_inl.h:95-125 -> gotoh/gotoh_inl.h:459-960, PatternBlockingTag); texts up to 4096 symbols

@@ -7,7 +7,8 @@ Run in the dev container only (needs /root/reference to have built oracle/_ref):
 The fixtures pin (a) the two banded-Gotoh problems asserted by the reference's own test
 (nvbio-test/alignment_test.cu:761-825), (b) seeded random banded problems for every BAND/TYPE the
 reference instantiates, incl. text symbols > 3 and ragged lengths, (c) a small FM-index
-(SA, BWT, occ, SSA, match ranges, locate results) incl. a repetitive text.
+(SA, BWT, occ, SSA, match ranges, locate results) incl. a repetitive text, (d) full-matrix Gotoh scores, sinks and
+tracebacks (gotoh_full.npz; `--only-full` regenerates just that file).
 """
 import os
 import sys
@@ -61,9 +62,68 @@ def random_problems(rng, n, band, max_m, alphabet_text=4, ragged=True):
             np.concatenate(txts), np.array(t_off, np.uint32), np.array(t_len, np.uint32))
 
 
+def full_problems(rng, n, max_m, max_n, paired=False):
+    """patterns drawn from a window of their own text with a few substitutions / an indel; `paired`: consecutive problems share
+    their shape (the packed two-per-thread kernel admits them)"""
+    pats, txts, po, pl, to, tl = [], [], [], [], [], []
+    a = b = 0
+    M = N = 0
+    for i in range(n):
+        if not paired or i % 2 == 0:
+            M = int(rng.integers(1, max_m + 1)); N = int(rng.integers(1, max_n + 1))
+        t = rng.integers(0, 4, N).astype(np.uint8)
+        if N > M + 2 and rng.random() < 0.8:
+            st = int(rng.integers(0, N - M - 1)); src = list(t[st:st + M + 2])
+            if rng.random() < 0.4 and M > 4:
+                k = int(rng.integers(1, M - 1))
+                if rng.random() < 0.5:
+                    del src[k]
+                else:
+                    src.insert(k, int(rng.integers(0, 4)))
+            p = np.array(src[:M], np.uint8)
+            for _k in range(int(rng.integers(0, 4))):
+                p[int(rng.integers(0, M))] = rng.integers(0, 4)
+        else:
+            p = rng.integers(0, 4, M).astype(np.uint8)
+        pats.append(p); txts.append(t); po.append(a); pl.append(M); a += M; to.append(b); tl.append(N); b += N
+    return (np.concatenate(pats), np.array(po, np.uint32), np.array(pl, np.uint32), np.concatenate(txts), np.array(to, np.uint32), np.array(tl, np.uint32))
+
+
+def make_full(ref):
+    """(d) full-matrix Gotoh: scores + sinks (aln::alignment_score) and tracebacks (aln::alignment_traceback<256,512,64>) of the
+    reference on its own 7 x 20 strings (alignment_test.cu:761-793) and on seeded random problems -> gotoh_full.npz"""
+    rng = np.random.default_rng(20240924)
+    out = {}
+    p, t = orc.dna(G1_P), orc.dna(G1_T)
+    for typ in (0, 1, 2):
+        a = ref.gotoh_full_traceback(typ, (2, -1, -1, -1), p, [0], [len(p)], t, [0], [len(t)], max_ops=64)
+        out[f"g1_t{typ}"] = np.array([a["score"][0], a["sink"][0][0], a["sink"][0][1], a["source"][0][0], a["source"][0][1]], np.int64)
+        out[f"g1_t{typ}_ops"] = a["ops"][0][:a["n_ops"][0]].copy()
+    cases, cid = [], 0
+    for typ in (0, 1, 2):
+        for scheme in ((2, -2, -5, -3), (2, -1, -2, -1), (0, -5, -8, -3), (1, -3, -2, -4)):
+            for paired in (False, True):
+                pr = full_problems(rng, 40, 150, 320, paired=paired)
+                s, x, y = ref.gotoh_full(typ, scheme, *pr)
+                tb = ref.gotoh_full_traceback(typ, scheme, *pr, max_ops=512)
+                assert np.array_equal(s, tb["score"]) and np.array_equal(x, tb["sink"][:, 0]) and np.array_equal(y, tb["sink"][:, 1])
+                for k, v in zip(("pat", "p_off", "p_len", "txt", "t_off", "t_len"), pr):
+                    out[f"f{cid}_{k}"] = v
+                out[f"f{cid}_res"] = np.stack([s.astype(np.int64), x.astype(np.int64), y.astype(np.int64),
+                                               tb["source"][:, 0].astype(np.int64), tb["source"][:, 1].astype(np.int64), tb["n_ops"].astype(np.int64)])
+                out[f"f{cid}_ops"] = np.concatenate([tb["ops"][i][:tb["n_ops"][i]] for i in range(len(s))])
+                cases.append((cid, typ) + scheme)
+                cid += 1
+    out["cases"] = np.array(cases, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "gotoh_full.npz"), **out)
+
+
 def main():
     assert orc.Ref.available(), "build oracle/_ref first: make -C oracle"
     ref = orc.Ref()
+    make_full(ref)
+    if "--only-full" in sys.argv:
+        print("wrote gotoh_full.npz"); return
     rng = np.random.default_rng(20240917)
     out = {}
 

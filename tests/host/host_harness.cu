@@ -200,6 +200,26 @@ int hh_gotoh_full_pair(int type, const int32_t* scheme6,
     return packed;
 }
 
+int hh_gotoh_full_traceback(int type, const int32_t* scheme6,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n, uint32_t max_ops,
+                  int32_t* score, uint32_t* sink_xy, uint32_t* source_xy, uint8_t* ops, uint32_t* n_ops) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = nullptr; S.one = 1u; S.keymul = 32u;
+    for (uint32_t a = 0; a < n; ++a) {
+        std::vector<int2> col(tlen[a] + 1);
+        const uint32_t rw = (plen[a] + 31u) / 32u * 4u;
+        std::vector<uint32_t> dirs((size_t)(tlen[a] + 1) * (rw ? rw : 4u));
+        SinkResult r;
+        uint32_t sx = 0xFFFFFFFFu, sy = 0xFFFFFFFFu, cnt = 0;
+#define HH_FT(T) { r = gotoh_full_impl<T, true>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1, dirs.data(), rw); \
+                   if (r.x != 0xFFFFFFFFu && r.y != 0xFFFFFFFFu) cnt = gotoh_full_walk<T>(dirs.data(), rw, r, ops + (size_t)a * max_ops, max_ops, sx, sy); }
+        if (type == 0) HH_FT(0) else if (type == 1) HH_FT(1) else HH_FT(2)
+#undef HH_FT
+        score[a] = r.score; sink_xy[2 * a] = r.x; sink_xy[2 * a + 1] = r.y; source_xy[2 * a] = sx; source_xy[2 * a + 1] = sy; n_ops[a] = cnt;
+    }
+    return 0;
+}
+
 int hh_gotoh_traceback(int band, int type, const int32_t* scheme6,
                        const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                        const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n, uint32_t max_ops,

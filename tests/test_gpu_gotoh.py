@@ -256,3 +256,52 @@ def test_full_matrix_packed_path(O, typ):
                 force_path(0)
             k = host_u32(k)
             assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, scheme, "int32")
+
+
+def test_full_matrix_golden_gpu():
+    """nvb_gotoh_score / nvb_gotoh_traceback == the committed outputs of the reference itself (tests/golden/gotoh_full.npz):
+    score, sink, source, op stream; the reference-asserted 4M1D3M CIGAR of alignment_test.cu:784-793"""
+    require_gpu()
+    g = np.load(os.path.join(GOLD, "gotoh_full.npz"))
+    p, t = orc.dna(G1_P), orc.dna(G1_T)
+    for typ, cig in ((0, "1M2D3M1D3M10D"), (1, "4M1D3M"), (2, "4M1D3M")):
+        P = PackedStringSet.from_symbols(p, [0], [len(p)], bits=2, big_endian=True)
+        T = PackedStringSet.from_symbols(t, [0], [len(t)], bits=2, big_endian=True)
+        tb = aln.batch_alignment_traceback(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -1, -1, -1)), P, T)
+        want = g[f"g1_t{typ}"]
+        got = [int(tb["score"][0])] + [int(v) for v in host_u32(tb["sink"])[0]] + [int(v) for v in host_u32(tb["source"])[0]]
+        assert got == [int(v) for v in want], (typ, got)
+        assert aln.cigar(tb["ops"][0].cpu().numpy(), int(tb["n_ops"][0])) == cig
+    for cid, typ, m, mm, go, ge in g["cases"]:
+        pr = [g[f"f{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        res, ops = g[f"f{cid}_res"], g[f"f{cid}_ops"]
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=2, big_endian=True)
+        T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2, big_endian=True)
+        al = aln.make_gotoh_aligner(int(typ), aln.SimpleGotohScheme(int(m), int(mm), int(go), int(ge)))
+        s, k = aln.batch_alignment_score(al, P, T)
+        k = host_u32(k)
+        assert np.array_equal(s.cpu().numpy().astype(np.int64), res[0]) and np.array_equal(k[:, 0].astype(np.int64), res[1]) and np.array_equal(k[:, 1].astype(np.int64), res[2]), cid
+        tb = aln.batch_alignment_traceback(al, P, T, max_ops=512)
+        src = host_u32(tb["source"]); n_ops = tb["n_ops"].cpu().numpy(); o = tb["ops"].cpu().numpy()
+        assert np.array_equal(tb["score"].cpu().numpy().astype(np.int64), res[0]) and np.array_equal(host_u32(tb["sink"])[:, 0].astype(np.int64), res[1])
+        assert np.array_equal(src[:, 0].astype(np.int64), res[3]) and np.array_equal(src[:, 1].astype(np.int64), res[4]) and np.array_equal(n_ops.astype(np.int64), res[5]), cid
+        assert np.array_equal(np.concatenate([o[i][:n_ops[i]] for i in range(len(n_ops))]), ops), cid
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_full_matrix_traceback_vs_oracle(O, typ):
+    from tests.test_host_core import full_problems
+    rng = np.random.default_rng(990 + typ)
+    for scheme in ((2, -1, -2, -1), (2, -2, -5, -3)):
+        pr = full_problems(rng, 400, max_m=180, max_n=420)
+        want = O.gotoh_full_traceback(typ, scheme, *pr, max_ops=640)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+        T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2, big_endian=True)
+        tb = aln.batch_alignment_traceback(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme)), P, T, max_ops=640)
+        n_ops = tb["n_ops"].cpu().numpy(); o = tb["ops"].cpu().numpy()
+        assert np.array_equal(tb["score"].cpu().numpy(), want["score"]) and np.array_equal(host_u32(tb["sink"]), want["sink"])
+        assert np.array_equal(host_u32(tb["source"]), want["source"]) and np.array_equal(n_ops.astype(np.uint32), want["n_ops"])
+        for i in range(len(n_ops)):
+            assert np.array_equal(o[i][:n_ops[i]], want["ops"][i][:n_ops[i]]), (typ, scheme, i)

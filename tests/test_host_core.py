@@ -430,3 +430,26 @@ def test_gotoh_full_pair(H, O, typ):
                                               _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
                 assert packed > 0 and (n_frac or packed == n)
                 assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, scheme, pbits, tbits)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_full_traceback(H, O, typ):
+    """full-matrix traceback (direction nibbles per 32-column stripe + state-machine walk) == the oracle (== the reference's
+    aln::alignment_traceback, pinned in tests/test_oracle.py): score, sink, source and every op"""
+    rng = np.random.default_rng(700 + typ)
+    for scheme in ((2, -1, -2, -1), (2, -2, -5, -3), (0, -5, -8, -3)):
+        pr = full_problems(rng, 100, max_m=140, max_n=300)
+        want = O.gotoh_full_traceback(typ, scheme, *pr, max_ops=512)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 2, True)
+        n = len(p_off)
+        score = np.zeros(n, np.int32); sink = np.zeros((n, 2), np.uint32); source = np.zeros((n, 2), np.uint32)
+        ops = np.zeros((n, 512), np.uint8); n_ops = np.zeros(n, np.uint32)
+        s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+        H.hh_gotoh_full_traceback(C.c_int(typ), _p(s6), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len),
+                                  _p(tw), C.c_uint32(2), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n), C.c_uint32(512),
+                                  _p(score), _p(sink), _p(source), _p(ops), _p(n_ops))
+        assert np.array_equal(score, want["score"]) and np.array_equal(sink, want["sink"]) and np.array_equal(source, want["source"])
+        assert np.array_equal(n_ops, want["n_ops"])
+        for i in range(n):
+            assert np.array_equal(ops[i, :n_ops[i]], want["ops"][i, :n_ops[i]]), (typ, scheme, i)

@@ -195,3 +195,43 @@ def test_full_matrix_gotoh_vs_reference(O, R):
             a, b = O.gotoh_full(typ, scheme, *pr), R.gotoh_full(typ, scheme, *pr)
             for u, v in zip(a, b):
                 assert np.array_equal(u, v), (typ, scheme)
+
+
+def test_full_matrix_traceback_vs_reference(O, R):
+    """aln::alignment_traceback<256,512,64> (full DP, checkpointed) == the C restatement (whole direction matrix): score, sink,
+    source, clips and every op; the reference's own 7 x 20 strings give 4M1D3M for LOCAL / SEMI_GLOBAL (alignment_test.cu:784-793)"""
+    from tests.test_host_core import full_problems
+    p, t = orc.dna(G1_P), orc.dna(G1_T)
+    for typ, cig in ((0, "1M2D3M1D3M10D"), (1, "4M1D3M"), (2, "4M1D3M")):
+        for E in (O, R):
+            a = E.gotoh_full_traceback(typ, (2, -1, -1, -1), p, [0], [len(p)], t, [0], [len(t)])
+            assert orc.rle(a["ops"][0][:a["n_ops"][0]]) == cig, (typ, E.kind)
+    rng = np.random.default_rng(17)
+    for typ in (0, 1, 2):
+        for scheme in ((2, -1, -2, -1), (2, -2, -5, -3), (0, -5, -8, -3)):
+            pr = full_problems(rng, 80, max_m=200, max_n=450)
+            a, b = O.gotoh_full_traceback(typ, scheme, *pr), R.gotoh_full_traceback(typ, scheme, *pr)
+            for k in ("score", "sink", "source", "n_ops", "clips"):
+                assert np.array_equal(a[k], b[k]), (typ, scheme, k)
+            for i in range(len(a["n_ops"])):
+                assert np.array_equal(a["ops"][i][:a["n_ops"][i]], b["ops"][i][:b["n_ops"][i]]), (typ, scheme, i)
+
+
+def _full_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "gotoh_full.npz"))
+
+
+def test_full_matrix_golden(O):
+    """the committed reference outputs (tests/golden/gotoh_full.npz: aln::alignment_score + aln::alignment_traceback run by
+    make_golden.py) == the oracle: score, sink, source and the op stream of every problem"""
+    g = _full_golden()
+    for cid, typ, m, mm, go, ge in g["cases"]:
+        pr = [g[f"f{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        res, ops = g[f"f{cid}_res"], g[f"f{cid}_ops"]
+        s, x, y = O.gotoh_full(int(typ), (int(m), int(mm), int(go), int(ge)), *pr)
+        assert np.array_equal(s.astype(np.int64), res[0]) and np.array_equal(x.astype(np.int64), res[1]) and np.array_equal(y.astype(np.int64), res[2])
+        tb = O.gotoh_full_traceback(int(typ), (int(m), int(mm), int(go), int(ge)), *pr, max_ops=512)
+        assert np.array_equal(tb["source"][:, 0].astype(np.int64), res[3]) and np.array_equal(tb["source"][:, 1].astype(np.int64), res[4])
+        assert np.array_equal(tb["n_ops"].astype(np.int64), res[5])
+        assert np.array_equal(np.concatenate([tb["ops"][i][:tb["n_ops"][i]] for i in range(len(s))]), ops)
