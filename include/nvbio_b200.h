@@ -182,6 +182,20 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
                            int32_t* d_score, nvb_uint2* d_sink,
                            void* d_temp, size_t* temp_bytes, void* stream);
 
+/* Windowed banded Gotoh score (second half): rows [window_begin, min(window_end, pattern length)) of every
+ * alignment still alive, the (H, F) band carried between calls in d_checkpoints (band_len short2 per alignment, clamped at
+ * SHRT_MIN+32 when stored), the BestSink in d_score / d_sink (in/out) and the reference's bool result in d_alive
+ * (0 = text shorter than pattern, or the band maximum can no longer reach d_min_score[i] + remaining_rows * match; such
+ * alignments are skipped by later passes).  window_begin == 0 initialises score / sink / alive.  d_min_score may be NULL
+ * (= INT_MIN: never give up).  Scoring a pattern in consecutive windows yields exactly nvb_banded_gotoh_score's result.
+ * Replaces aln::banded_alignment_score<BAND_LEN>(aligner, pattern, quals, text, min_score, window_begin, window_end, sink,
+ * checkpoint) (nvbio/alignment/banded_inl.h:178-218, gotoh_banded_inl.h:132-199,616-634,706-739), the per-pass body of
+ * BatchedBandedAlignmentScore<..., DeviceStagedThreadScheduler> (batched_banded_inl.h:170-241).  bands 3, 5, 7, 15, 31. */
+int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                                  const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
+                                  uint32_t window_begin, uint32_t window_end, const int32_t* d_min_score,
+                                  int16_t* d_checkpoints, int32_t* d_score, nvb_uint2* d_sink, uint8_t* d_alive, void* stream);
+
 /* Full-matrix (un-banded) Gotoh score: every pattern against the WHOLE of its text.
  * d_score / d_sink = BestSink<int32>{score, (text end, pattern end)}; pattern and text lengths must be >= 1 and
  * `patterns->length` / `texts->length` must bound them (<= 65535; the text bound sizes the boundary-column scratch).

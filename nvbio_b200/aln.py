@@ -211,3 +211,30 @@ def batch_alignment_traceback(aligner: GotohAligner, patterns: PackedStringSet, 
     temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=dev)
     check(call(C.c_void_p(temp.data_ptr())), "nvb_gotoh_traceback")
     return out
+
+
+class BandedWindowState:
+    """device state of a batch scored window by window (checkpoint bands, BestSinks, alive flags)"""
+
+    def __init__(self, n: int, band_len: int, device):
+        self.ckpt = torch.zeros((n, band_len, 2), dtype=torch.int16, device=device)
+        self.score = torch.empty(n, dtype=torch.int32, device=device)
+        self.sink = torch.empty((n, 2), dtype=torch.int32, device=device)
+        self.alive = torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def batch_banded_alignment_score_window(band_len: int, aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet,
+                                        window_begin: int, window_end: int, state: BandedWindowState,
+                                        min_score: Optional[torch.Tensor] = None, quals: Optional[torch.Tensor] = None):
+    """one [window_begin, window_end) pass of aln::banded_alignment_score<BAND_LEN>(..., window_begin, window_end, sink, checkpoint)
+    over a batch (nvbio/alignment/banded_inl.h:178-218); call with consecutive windows, starting at 0"""
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    check(lib().nvb_banded_gotoh_score_window(C.c_int(band_len), C.c_int(aligner.type), C.byref(sch), C.byref(p),
+                                              C.c_void_p(quals.data_ptr()) if quals is not None else None, C.byref(t), C.c_uint32(patterns.count),
+                                              C.c_uint32(window_begin), C.c_uint32(window_end),
+                                              C.c_void_p(min_score.data_ptr()) if min_score is not None else None,
+                                              C.c_void_p(state.ckpt.data_ptr()), C.c_void_p(state.score.data_ptr()),
+                                              C.c_void_p(state.sink.data_ptr()), C.c_void_p(state.alive.data_ptr()), _stream()),
+          "nvb_banded_gotoh_score_window")
+    return state

@@ -174,6 +174,85 @@ __host__ __device__ inline SinkResult gotoh_generic(const GotohScheme& S,
     return gotoh_generic_impl<B, TYPE, false>(S, pwords, pbits, pbe, poff, M, quals, twords, tbits, tbe, toff, N, nullptr);
 }
 
+// Windowed scoring: rows [wb, we) of the band only, carrying the (H, F) band between calls in a short2 checkpoint
+// (aln::banded_alignment_score<B>(..., window_begin, window_end, sink, checkpoint), banded_inl.h:178-218;
+// GotohCheckpointedScoringContext, gotoh_banded_inl.h:132-199; the early exit :616-634).  `res` is the caller's BestSink (in/out).
+// Returns false when N < M or when the band maximum can no longer reach min_score (the checkpoint is then left untouched).
+template <int B, int TYPE>
+__host__ __device__ inline bool gotoh_window(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
+        const uint8_t* __restrict__ quals,
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
+        uint32_t wb, uint32_t we, int32_t min_score, short2* __restrict__ ckpt, SinkResult& res)
+{
+    if (N < M) return false;
+    constexpr bool PACKED = packed_text_cache(B);
+    const int32_t Go = S.pgo, Ge = S.pge;
+    const int32_t INF = gotoh_infimum(S);
+    int32_t H[B], F[B];
+    uint32_t cache[B];
+    if (wb == 0) {
+        H[0] = 0;
+#pragma unroll
+        for (int j = 1; j < B; ++j) H[j] = (TYPE == NVB_GLOBAL) ? S.tgo + (j - 1) * S.tge : 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) F[j] = INF;
+    } else {
+#pragma unroll
+        for (int j = 0; j < B; ++j) { const short2 c = ckpt[j]; H[j] = c.x; F[j] = c.y; }
+    }
+    SymReaderRT tr(twords, tbits, tbe), pr(pwords, pbits, pbe);
+#pragma unroll
+    for (int j = 0; j < B - 1; ++j) {
+        const uint32_t g = (wb + (uint32_t)j < N) ? tr.get(toff + wb + j) : 255u;      // unchecked in the reference: 255 here
+        cache[j] = PACKED ? (g & 3u) : g;
+    }
+    for (uint32_t i = wb; i < we; ++i) {
+        const uint32_t q = pr.get(poff + i);
+        const uint32_t qq = quals ? quals[poff + i] : 0u;
+        const int32_t s_eq = S.qtab ? S.qtab[2 * qq]     : S.match;
+        const int32_t s_ne = S.qtab ? S.qtab[2 * qq + 1] : S.mismatch;
+        const uint32_t g_new = (i + (uint32_t)B - 1u < N) ? tr.get(toff + i + B - 1) : 255u;
+        int32_t E = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const uint32_t g = (j < B - 1) ? cache[j] : g_new;
+            if (j >= 1 && j < B - 1) cache[j - 1] = g;
+            if (j < B - 1) F[j] = imax2(F[j + 1] + Ge, H[j + 1] + Go); else F[j] = INF;
+            int32_t h = H[j] + ((g == q) ? s_eq : s_ne);
+            if (j < B - 1) h = imax2(h, F[j]);
+            if (j > 0)     h = imax2(h, E);
+            if (TYPE == NVB_LOCAL) {
+                h = imax2(h, 0);
+                if (res.score <= h) { res.score = h; res.x = i + (uint32_t)j + 1u; res.y = i + 1u; }
+            }
+            H[j] = h;
+            E = (j == 0) ? h + Go : imax2(h + Go, E + Ge);
+        }
+        cache[B - 2] = PACKED ? (g_new & 3u) : g_new;
+    }
+    if (we < M) {
+        int32_t mx = H[0];
+#pragma unroll
+        for (int j = 1; j < B; ++j) mx = imax2(mx, H[j]);
+        const long long thr = (long long)min_score + (long long)(M - we) * (long long)(S.qtab ? S.qtab[0] : S.match);
+        if ((long long)mx < thr) return false;
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) ckpt[j] = make_short2((short)imax2(H[j], SHRT_MIN + 32), (short)imax2(F[j], SHRT_MIN + 32));
+    if (we == M) {
+        if (TYPE == NVB_GLOBAL) {
+            if (res.score <= H[B - 1]) { res.score = H[B - 1]; res.x = M + (uint32_t)B - 1u; res.y = M; }
+        } else if (TYPE == NVB_SEMI_GLOBAL) {
+            const uint32_t m = umin2(M + (uint32_t)B - 1u, N) - (M - 1u);
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if ((j == 0 || (uint32_t)j < m) && res.score <= H[j]) { res.score = H[j]; res.x = M + (uint32_t)j; res.y = M; }
+        }
+    }
+    return true;
+}
+
 // Backtrack through the direction matrix from the sink (the H/E/F state machine of
 // priv::banded_alignment_traceback, gotoh_banded_inl.h:893-958, walked over the whole matrix instead of one
 // 32-row checkpoint window at a time).  Pushes ops in END -> START order (0 SUBSTITUTION 'M', 1 INSERTION 'I',

@@ -142,6 +142,37 @@ gotoh_full_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ co
     b.sink[a]  = make_uint2(r.x, r.y);
 }
 
+// windowed scoring: one alignment per thread, rows [wb, min(we, M)); checkpoints, BestSinks and alive flags live in HBM between passes
+struct WindowArgs { uint32_t wb, we; const int32_t* min_score; short2* ckpt; uint8_t* alive; };
+
+template <int B, int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_window_kernel(const GotohScheme S, const GotohBatch b, const WindowArgs w)
+{
+    const uint32_t n = batch_count(b);
+    const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
+    if (a >= n) return;
+    SinkResult r;
+    if (w.wb == 0) { r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu; b.score[a] = r.score; b.sink[a] = make_uint2(r.x, r.y); w.alive[a] = 1; }
+    else { if (!w.alive[a]) return; r.score = b.score[a]; const uint2 k = b.sink[a]; r.x = k.x; r.y = k.y; }
+    const uint32_t M = str_len(b.pat, a);
+    if (w.wb >= M) return;
+    const bool ok = gotoh_window<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), M, b.quals,
+                                          b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a),
+                                          w.wb, w.we < M ? w.we : M, w.min_score ? w.min_score[a] : INT_MIN, w.ckpt + (size_t)a * B, r);
+    b.score[a] = r.score; b.sink[a] = make_uint2(r.x, r.y);
+    w.alive[a] = ok ? 1 : 0;
+}
+
+template <int B, int TYPE>
+static int launch_window(const GotohScheme& S, const GotohBatch& b, const WindowArgs& w, cudaStream_t s)
+{
+    const uint32_t grid = (b.n_max + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
+    gotoh_window_kernel<B, TYPE><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, w);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
 struct TracebackOut {
     uint2* source; uint8_t* ops; uint32_t* n_ops; uint32_t max_ops; uint32_t* dirs; uint32_t dir_rows;
 };
@@ -481,6 +512,31 @@ int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* s
     TracebackOut o;
     o.source = (uint2*)d_source; o.ops = d_ops; o.n_ops = d_n_ops; o.max_ops = max_ops; o.dirs = dirs; o.dir_rows = max_m;
     return dispatch_traceback(band_len, type, make_scheme(scheme), b, o, as_stream(stream));
+}
+
+int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                                  const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
+                                  uint32_t window_begin, uint32_t window_end, const int32_t* d_min_score,
+                                  int16_t* d_checkpoints, int32_t* d_score, nvb_uint2* d_sink, uint8_t* d_alive, void* stream)
+{
+    if (!scheme || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
+    if (type < 0 || type > 2 || window_begin >= window_end) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    if (!d_checkpoints || !d_score || !d_sink || !d_alive) return NVB_E_INVALID;
+    GotohBatch b;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
+    b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
+    WindowArgs w; w.wb = window_begin; w.we = window_end; w.min_score = d_min_score; w.ckpt = (short2*)d_checkpoints; w.alive = d_alive;
+    const GotohScheme S = make_scheme(scheme);
+    cudaStream_t s = as_stream(stream);
+    switch (band_len) {
+    case 3:  NVB_TYPE_SWITCH(3,  launch_window, S, b, w, s)
+    case 5:  NVB_TYPE_SWITCH(5,  launch_window, S, b, w, s)
+    case 7:  NVB_TYPE_SWITCH(7,  launch_window, S, b, w, s)
+    case 15: NVB_TYPE_SWITCH(15, launch_window, S, b, w, s)
+    case 31: NVB_TYPE_SWITCH(31, launch_window, S, b, w, s)
+    default: return NVB_E_INVALID;
+    }
 }
 
 int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,

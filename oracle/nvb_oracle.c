@@ -384,6 +384,103 @@ void orc_banded_gotoh(int B, int type, const orc_scheme* S, const i32* qtab,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * windowed banded Gotoh score: aln::banded_alignment_score<B>(aligner, pattern, quals, text, min_score, window_begin, window_end,
+ * sink, checkpoint) (nvbio/alignment/banded_inl.h:178-218 -> gotoh_banded_inl.h:706-739 with GotohCheckpointedScoringContext
+ * :132-199): rows [wb, we) of the band only; wb > 0 starts from the checkpoint (H,F as short2 per band cell), every call stores
+ * the checkpoint of row `we` clamped at SHRT_MIN+32; when rows remain the call returns 0 if the band maximum can no longer
+ * reach min_score (:616-634); the final reports happen when we == M.  `best/bx/by` are the caller's BestSink (in/out).
+ * ---------------------------------------------------------------------------------------------- */
+int orc_banded_gotoh_window_one(int B, int type, const orc_scheme* S, const i32* qtab,
+                                const u8* P, const u8* Q, u32 M, const u8* T, u32 N, u32 wb, u32 we, i32 min_score,
+                                short* ckpt, i32* best_io, u32* bx_io, u32* by_io)
+{
+    i32 best = *best_io; u32 bx = *bx_io, by = *by_io;
+    if (N < M) return 0;
+    const int packed_cache = !(B == 3 || B == 5 || B == 7 || B == 15);
+    const i32 Go = S->pattern_gap_open, Ge = S->pattern_gap_ext;
+    const i32 INF = SHRT_MIN - imax(imax(Go, Ge), imax(S->text_gap_open, S->text_gap_ext));
+    i32 H[ORC_MAX_BAND], F[ORC_MAX_BAND]; u32 cache[ORC_MAX_BAND];
+    if (wb == 0)
+    {
+        H[0] = 0;
+        for (int j = 1; j < B; ++j) H[j] = (type == 0) ? S->text_gap_open + (j - 1) * S->text_gap_ext : 0;
+        for (int j = 0; j < B; ++j) F[j] = INF;
+    }
+    else for (int j = 0; j < B; ++j) { H[j] = ckpt[2 * j]; F[j] = ckpt[2 * j + 1]; }
+    for (int j = 0; j < B - 1; ++j) { const u32 g = (wb + (u32)j < N) ? T[wb + j] : 255u; cache[j] = packed_cache ? (g & 3u) : g; }
+#define SUB(g, q, qq) (qtab ? (((u8)(g) == (q)) ? qtab[2 * (qq)] : qtab[2 * (qq) + 1]) : (((u8)(g) == (q)) ? S->match : S->mismatch))
+    for (u32 i = wb; i < we; ++i)
+    {
+        const u8 q = P[i];
+        const u8 qq = Q ? Q[i] : 0;
+        {
+            F[0] = imax(F[1] + Ge, H[1] + Go);
+            const u32 g = cache[0];
+            i32 h = imax(F[0], H[0] + SUB(g, q, qq));
+            if (type == 1) { h = imax(h, 0); sink_report(&best, &bx, &by, h, i + 1, i + 1); }
+            H[0] = h;
+        }
+        i32 E = H[0] + Go;
+        for (int j = 1; j < B - 1; ++j)
+        {
+            F[j] = imax(F[j + 1] + Ge, H[j + 1] + Go);
+            const u32 g = cache[j]; cache[j - 1] = g;
+            i32 h = imax(imax(F[j], E), H[j] + SUB(g, q, qq));
+            if (type == 1) { h = imax(h, 0); sink_report(&best, &bx, &by, h, i + (u32)j + 1, i + 1); }
+            H[j] = h;
+            E = imax(h + Go, E + Ge);
+        }
+        const u8 g = (i + (u32)B - 1 < N) ? T[i + B - 1] : 255u;
+        cache[B - 2] = packed_cache ? (g & 3u) : g;
+        {
+            F[B - 1] = INF;
+            i32 h = imax(E, H[B - 1] + SUB(g, q, qq));
+            if (type == 1) { h = imax(h, 0); sink_report(&best, &bx, &by, h, i + (u32)B, i + 1); }
+            H[B - 1] = h;
+        }
+    }
+#undef SUB
+    *best_io = best; *bx_io = bx; *by_io = by;
+    if (we < M)
+    {
+        i32 mx = H[0];
+        for (int j = 1; j < B; ++j) mx = imax(mx, H[j]);
+        const long long thr = (long long)min_score + (long long)(M - we) * (qtab ? qtab[0] : S->match);
+        if ((long long)mx < thr) return 0;
+    }
+    for (int j = 0; j < B; ++j) { ckpt[2 * j] = (short)imax(H[j], SHRT_MIN + 32); ckpt[2 * j + 1] = (short)imax(F[j], SHRT_MIN + 32); }
+    if (we == M)
+    {
+        if (type == 0) sink_report(&best, &bx, &by, H[B - 1], M + (u32)B - 1, M);
+        else if (type == 2)
+        {
+            const u32 lim = (M + (u32)B - 1 < N ? M + (u32)B - 1 : N) - (M - 1);
+            sink_report(&best, &bx, &by, H[0], M, M);
+            for (int j = 1; j < B; ++j) if ((u32)j < lim) sink_report(&best, &bx, &by, H[j], M + (u32)j, M);
+        }
+        *best_io = best; *bx_io = bx; *by_io = by;
+    }
+    return 1;
+}
+
+/* window [wb, min(we, M)) of every alignment still alive; score/sink/ckpt/alive are in/out arrays (wb == 0 initialises them) */
+void orc_banded_gotoh_window(int B, int type, const orc_scheme* S, const i32* qtab,
+                             const u8* pat, const u8* qual, const u32* p_off, const u32* p_len,
+                             const u8* txt, const u32* t_off, const u32* t_len, u32 n, u32 wb, u32 we, const i32* min_score,
+                             short* ckpt, i32* score, u32* sink_x, u32* sink_y, u8* alive)
+{
+    for (u32 i = 0; i < n; ++i)
+    {
+        if (wb == 0) { score[i] = INT_MIN; sink_x[i] = sink_y[i] = 0xFFFFFFFFu; alive[i] = 1; }
+        if (!alive[i] || wb >= p_len[i]) continue;
+        const u32 e = we < p_len[i] ? we : p_len[i];
+        alive[i] = (u8)orc_banded_gotoh_window_one(B, type, S, qtab, pat + p_off[i], qual ? qual + p_off[i] : NULL, p_len[i],
+                                                   txt + t_off[i], t_len[i], wb, e, min_score ? min_score[i] : INT_MIN,
+                                                   ckpt + (size_t)i * 2 * B, &score[i], &sink_x[i], &sink_y[i]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * banded Gotoh traceback (nvbio/alignment/banded_inl.h:352-489 driver; direction vectors as produced by
  * gotoh_banded_inl.h:463-620 and stored by GotohSubmatrixContext::new_cell :325-337; state machine
  * gotoh_banded_inl.h:893-958).  The reference recomputes 32-row windows between checkpoints; walking one

@@ -157,6 +157,31 @@ def _oracle_traceback(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_
     return o
 
 
+def _window_state(n, band):
+    return dict(ckpt=np.zeros((n, band, 2), np.int16), score=np.zeros(n, np.int32), sx=np.zeros(n, np.uint32), sy=np.zeros(n, np.uint32),
+                alive=np.zeros(n, np.uint8))
+
+
+def _oracle_window(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, wb, we, state, min_score=None, qual=None, qtab=None):
+    """Oracle.banded_gotoh_window: one [wb, we) pass of the windowed banded score over a batch; `state` (from window_state) carries
+    the checkpoints, BestSinks and alive flags between passes"""
+    pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+    p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+    t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+    if len(scheme) == 4:
+        scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+    s = np.array(scheme, dtype=np.int32)
+    ms = None if min_score is None else np.ascontiguousarray(min_score, dtype=np.int32)
+    if qual is not None:
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    if qtab is not None:
+        qtab = np.ascontiguousarray(qtab, dtype=np.int32)
+    self.lib.orc_banded_gotoh_window(C.c_int(band), C.c_int(typ), _p(s), _p(qtab), _p(pat), _p(qual), _p(p_off), _p(p_len),
+                                     _p(txt), _p(t_off), _p(t_len), C.c_uint32(len(p_off)), C.c_uint32(wb), C.c_uint32(we), _p(ms),
+                                     _p(state["ckpt"]), _p(state["score"]), _p(state["sx"]), _p(state["sy"]), _p(state["alive"]))
+    return state
+
+
 def _oracle_full_traceback(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=1024):
     """Oracle.gotoh_full_traceback: aln::alignment_traceback restated; ops END->START (0 M, 1 I, 2 D)"""
     pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
@@ -249,6 +274,19 @@ class Ref(_Base):
                             C.c_uint32(idx.primary), _p(rows), C.c_uint32(len(rows)), _p(out))
         return out
 
+    def banded_gotoh_window(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, wb, we, state, min_score=None):
+        """aln::banded_alignment_score<BAND>(..., window_begin, window_end, sink, checkpoint) over a batch (one pass)"""
+        pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+        p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+        t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+        ms = None if min_score is None else np.ascontiguousarray(min_score, dtype=np.int32)
+        r = self.lib.ref_banded_gotoh_window(C.c_int(band), C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]), C.c_int(scheme[2]), C.c_int(scheme[3]),
+                                             _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(len(p_off)),
+                                             C.c_uint32(wb), C.c_uint32(we), _p(ms), _p(state["ckpt"]), _p(state["score"]), _p(state["sx"]),
+                                             _p(state["sy"]), _p(state["alive"]))
+        assert r == 0, r
+        return state
+
     def gotoh_full_traceback(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, max_ops=1024):
         """aln::alignment_traceback<256,512,64>: ops in END->START push order (0 M, 1 I, 2 D)"""
         pat, p_off, p_len, txt, t_off, t_len, n, o = _tb_args(pat, p_off, p_len, txt, t_off, t_len, max_ops)
@@ -313,6 +351,8 @@ def dna(s):
 
 Oracle.banded_traceback = _oracle_traceback
 Oracle.gotoh_full_traceback = _oracle_full_traceback
+Oracle.banded_gotoh_window = _oracle_window
+window_state = _window_state
 
 
 def _full_args(pat, p_off, p_len, txt, t_off, t_len):

@@ -93,6 +93,54 @@ int run_banded_type(int type, const aln::SimpleGotohScheme s,
     return -1;
 }
 
+// windowed scoring with a short2 checkpoint band (aln::banded_alignment_score<BAND>(..., window_begin, window_end, sink, checkpoint),
+// nvbio/alignment/banded_inl.h:178-218): what DeviceStagedThreadScheduler runs per pass (batched_banded_inl.h:170-241)
+template <uint32 BAND, aln::AlignmentType TYPE>
+void run_banded_window(const aln::SimpleGotohScheme scheme,
+                const uint8* pat, const uint32* p_off, const uint32* p_len,
+                const uint8* txt, const uint32* t_off, const uint32* t_len,
+                uint32 n, uint32 wb, uint32 we, const int32* min_score, short2* ckpt,
+                int32* score, uint32* sink_x, uint32* sink_y, uint8* alive)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        if (wb == 0) { score[i] = INT_MIN; sink_x[i] = sink_y[i] = uint32(-1); alive[i] = 1; }
+        if (!alive[i] || wb >= p_len[i]) continue;
+        aln::BestSink<int32> sink;
+        sink.score = score[i]; sink.sink = make_uint2( sink_x[i], sink_y[i] );
+        const bool r = aln::banded_alignment_score<BAND>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),
+            str_view( p_len[i], pat + p_off[i] ),
+            aln::trivial_quality_string(),
+            str_view( t_len[i], txt + t_off[i] ),
+            min_score ? min_score[i] : INT_MIN,
+            wb, nvbio::min( we, p_len[i] ),
+            sink,
+            ckpt + uint64(i)*BAND );
+        score[i]  = sink.score;
+        sink_x[i] = sink.sink.x;
+        sink_y[i] = sink.sink.y;
+        alive[i]  = r ? 1 : 0;
+    }
+}
+
+template <uint32 BAND>
+int run_banded_window_type(int type, const aln::SimpleGotohScheme s,
+                const uint8* pat, const uint32* p_off, const uint32* p_len,
+                const uint8* txt, const uint32* t_off, const uint32* t_len,
+                uint32 n, uint32 wb, uint32 we, const int32* min_score, short2* ckpt,
+                int32* score, uint32* sink_x, uint32* sink_y, uint8* alive)
+{
+    switch (type)
+    {
+    case 0: run_banded_window<BAND,aln::GLOBAL>     ( s, pat,p_off,p_len, txt,t_off,t_len, n, wb,we,min_score,ckpt, score,sink_x,sink_y,alive ); return 0;
+    case 1: run_banded_window<BAND,aln::LOCAL>      ( s, pat,p_off,p_len, txt,t_off,t_len, n, wb,we,min_score,ckpt, score,sink_x,sink_y,alive ); return 0;
+    case 2: run_banded_window<BAND,aln::SEMI_GLOBAL>( s, pat,p_off,p_len, txt,t_off,t_len, n, wb,we,min_score,ckpt, score,sink_x,sink_y,alive ); return 0;
+    }
+    return -1;
+}
+
 // a Backtracer (nvbio/alignment/alignment.h "Backtracer" concept) that records the pushed ops (end -> start order, as
 // TestBacktracker does, nvbio-test/alignment_test_utils.h:628-643) and the two clip lengths
 struct RecordingBacktracer
@@ -338,6 +386,22 @@ void ref_locate(const uint32* bwt_occ, const uint32* ssa, const uint32* L2, uint
 
 // banded Gotoh score with SimpleGotohScheme(match, mismatch, gap_open, gap_ext).
 // type: 0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL (nvbio/alignment/alignment_base.h:54)
+int ref_banded_gotoh_window(int band, int type, int match, int mismatch, int gap_open, int gap_ext,
+                     const uint8* pat, const uint32* p_off, const uint32* p_len,
+                     const uint8* txt, const uint32* t_off, const uint32* t_len,
+                     uint32 n, uint32 wb, uint32 we, const int32* min_score, short* ckpt,
+                     int32* score, uint32* sink_x, uint32* sink_y, uint8* alive)
+{
+    const aln::SimpleGotohScheme s( match, mismatch, gap_open, gap_ext );
+    switch (band)
+    {
+    case  7: return run_banded_window_type< 7>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, wb,we,min_score,(short2*)ckpt, score,sink_x,sink_y,alive );
+    case 15: return run_banded_window_type<15>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, wb,we,min_score,(short2*)ckpt, score,sink_x,sink_y,alive );
+    case 31: return run_banded_window_type<31>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, wb,we,min_score,(short2*)ckpt, score,sink_x,sink_y,alive );
+    }
+    return -1;
+}
+
 int ref_banded_gotoh(int band, int type, int match, int mismatch, int gap_open, int gap_ext,
                      const uint8* pat, const uint32* p_off, const uint32* p_len,
                      const uint8* txt, const uint32* t_off, const uint32* t_len,

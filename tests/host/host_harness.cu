@@ -86,6 +86,22 @@ static void run_generic(const GotohScheme& S, const uint32_t* pw, uint32_t pbits
     }
 }
 
+// mirrors gotoh_window_kernel
+template <int B, int TYPE>
+static void run_window(const GotohScheme& S, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                       const uint8_t* quals, const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
+                       uint32_t n, uint32_t wb, uint32_t we, const int32_t* min_score, int16_t* ckpt, int32_t* score, uint32_t* sx, uint32_t* sy, uint8_t* alive) {
+    for (uint32_t i = 0; i < n; ++i) {
+        SinkResult r;
+        if (wb == 0) { r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu; score[i] = r.score; sx[i] = r.x; sy[i] = r.y; alive[i] = 1; }
+        else { if (!alive[i]) continue; r.score = score[i]; r.x = sx[i]; r.y = sy[i]; }
+        if (wb >= plen[i]) continue;
+        const bool ok = gotoh_window<B, TYPE>(S, pw, pbits, pbe, poff[i], plen[i], quals, tw, tbits, tbe, toff[i], tlen[i],
+                                              wb, we < plen[i] ? we : plen[i], min_score ? min_score[i] : INT_MIN, (short2*)(ckpt + (size_t)i * 2 * B), r);
+        score[i] = r.score; sx[i] = r.x; sy[i] = r.y; alive[i] = ok ? 1 : 0;
+    }
+}
+
 // mirrors gotoh_pair_kernel: precondition check -> packed pair routine, else generic
 template <int B, int TYPE>
 static void run_pair(const GotohScheme& S, const uint8_t* quals, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
@@ -150,6 +166,19 @@ int hh_gotoh_generic(int band, int type, const int32_t* scheme6, const int32_t* 
     case 15: TYPE_SWITCH(15, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
     case 31: TYPE_SWITCH(31, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
     case 63: TYPE_SWITCH(63, run_generic, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, score, sx, sy)
+    }
+    return -1;
+}
+
+int hh_gotoh_window(int band, int type, const int32_t* scheme6, const int32_t* qtab,
+                    const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen, const uint8_t* quals,
+                    const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
+                    uint32_t n, uint32_t wb, uint32_t we, const int32_t* min_score, int16_t* ckpt, int32_t* score, uint32_t* sx, uint32_t* sy, uint8_t* alive) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab; S.one = 1u; S.keymul = 32u;
+    switch (band) {
+    case 7:  TYPE_SWITCH(7,  run_window, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, wb, we, min_score, ckpt, score, sx, sy, alive)
+    case 15: TYPE_SWITCH(15, run_window, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, wb, we, min_score, ckpt, score, sx, sy, alive)
+    case 31: TYPE_SWITCH(31, run_window, S, pw, pbits, pbe, poff, plen, quals, tw, tbits, tbe, toff, tlen, n, wb, we, min_score, ckpt, score, sx, sy, alive)
     }
     return -1;
 }

@@ -306,3 +306,37 @@ def test_full_matrix_traceback_vs_oracle(O, typ):
         assert np.array_equal(host_u32(tb["source"]), want["source"]) and np.array_equal(n_ops.astype(np.uint32), want["n_ops"])
         for i in range(len(n_ops)):
             assert np.array_equal(o[i][:n_ops[i]], want["ops"][i][:n_ops[i]]), (typ, scheme, i)
+
+
+@pytest.mark.parametrize("band", [7, 15, 31])
+def test_windowed_banded_score(O, band):
+    """nvb_banded_gotoh_score_window: pass-by-pass state (BestSink, checkpoint bands, alive flags) == the oracle, and scoring in
+    windows == nvb_banded_gotoh_score"""
+    from tests.golden.make_golden import random_problems
+    rng = np.random.default_rng(1200 + band)
+    for typ in (0, 1, 2):
+        scheme = (2, -2, -5, -3)
+        pr = random_problems(rng, 500, band, 140, alphabet_text=6)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        n = len(p_off)
+        P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+        T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=8, big_endian=False)
+        al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme))
+        whole = run(band, typ, scheme, pr)
+        for W, ms in ((32, None), (32, rng.integers(-60, 140, n).astype(np.int32))):
+            so = orc.window_state(n, band)
+            st = aln.BandedWindowState(n, band, "cuda")
+            msd = torch.from_numpy(ms).cuda() if ms is not None else None
+            for wb in range(0, 140, W):
+                O.banded_gotoh_window(band, typ, scheme, *pr, wb, wb + W, so, min_score=ms)
+                aln.batch_banded_alignment_score_window(band, al, P, T, wb, wb + W, st, min_score=msd)
+                torch.cuda.synchronize()
+                k = host_u32(st.sink)
+                assert np.array_equal(st.alive.cpu().numpy(), so["alive"]), (band, typ, wb)
+                assert np.array_equal(st.score.cpu().numpy(), so["score"]) and np.array_equal(k[:, 0], so["sx"]) and np.array_equal(k[:, 1], so["sy"]), (band, typ, wb)
+                alive = so["alive"].astype(bool)
+                assert np.array_equal(st.ckpt.cpu().numpy()[alive], so["ckpt"][alive]), (band, typ, wb)
+            if ms is None:
+                ok = so["alive"].astype(bool)
+                k = host_u32(st.sink)
+                assert np.array_equal(st.score.cpu().numpy()[ok], whole[0][ok]) and np.array_equal(k[ok, 0], whole[1][ok]) and np.array_equal(k[ok, 1], whole[2][ok])

@@ -453,3 +453,37 @@ def test_gotoh_full_traceback(H, O, typ):
         assert np.array_equal(n_ops, want["n_ops"])
         for i in range(n):
             assert np.array_equal(ops[i, :n_ops[i]], want["ops"][i, :n_ops[i]]), (typ, scheme, i)
+
+
+@pytest.mark.parametrize("band", [7, 15, 31])
+def test_gotoh_window(H, O, band):
+    """windowed banded scoring (checkpoint bands carried between passes, early exit on min_score) == the oracle pass by pass
+    (== aln::banded_alignment_score(..., window_begin, window_end, sink, checkpoint), pinned in tests/test_oracle.py), and the
+    last pass == the whole-pattern score"""
+    from tests.golden.make_golden import random_problems
+    rng = np.random.default_rng(800 + band)
+    for typ in (0, 1, 2):
+        for scheme in ((2, -2, -5, -3), (0, -5, -8, -3)):
+            pr = random_problems(rng, 50, band, 120, alphabet_text=6)
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            n = len(p_off)
+            whole = O.banded_gotoh(band, typ, scheme, *pr)
+            pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 8, False)
+            s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+            for W, ms in ((32, None), (13, None), (32, rng.integers(-60, 120, n).astype(np.int32))):
+                so = orc.window_state(n, band); sh = orc.window_state(n, band)
+                for wb in range(0, 120, W):
+                    O.banded_gotoh_window(band, typ, scheme, *pr, wb, wb + W, so, min_score=ms)
+                    H.hh_gotoh_window(C.c_int(band), C.c_int(typ), _p(s6), None, _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len), None,
+                                      _p(tw), C.c_uint32(8), C.c_uint32(0), _p(t_off), _p(t_len), C.c_uint32(n), C.c_uint32(wb), C.c_uint32(wb + W),
+                                      _p(ms) if ms is not None else None, _p(sh["ckpt"]), _p(sh["score"]), _p(sh["sx"]), _p(sh["sy"]), _p(sh["alive"]))
+                    for k in ("score", "sx", "sy", "alive"):
+                        assert np.array_equal(so[k], sh[k]), (band, typ, scheme, W, wb, k)
+                    al = so["alive"].astype(bool)
+                    assert np.array_equal(so["ckpt"][al], sh["ckpt"][al]), (band, typ, scheme, W, wb)
+                if ms is None:
+                    ok = whole[3].astype(bool)
+                    assert np.array_equal(sh["score"][ok], whole[0][ok]) and np.array_equal(sh["sx"][ok], whole[1][ok]) and np.array_equal(sh["sy"][ok], whole[2][ok])
+                    assert not sh["alive"][~ok].any()
+                else:
+                    assert 0.1 < sh["alive"].mean() < 0.98

@@ -235,3 +235,25 @@ def test_full_matrix_golden(O):
         assert np.array_equal(tb["source"][:, 0].astype(np.int64), res[3]) and np.array_equal(tb["source"][:, 1].astype(np.int64), res[4])
         assert np.array_equal(tb["n_ops"].astype(np.int64), res[5])
         assert np.array_equal(np.concatenate([tb["ops"][i][:tb["n_ops"][i]] for i in range(len(s))]), ops)
+
+
+def test_windowed_banded_score_vs_reference(O, R):
+    """aln::banded_alignment_score<B>(..., window_begin, window_end, sink, checkpoint) == the C restatement, pass by pass: BestSink,
+    short2 checkpoint bands and the early-exit result; compared where the reference is defined (it reads text[wb .. wb+B-2]
+    unchecked at a window start, so N >= M + B - 1)"""
+    from tests.golden.make_golden import random_problems
+    rng = np.random.default_rng(23)
+    for band in (7, 15, 31):
+        for typ in (0, 1, 2):
+            pr = random_problems(rng, 60, band, 150)
+            n = len(pr[1])
+            wd = pr[5] >= pr[2] + band - 1
+            for scheme, W, ms in (((2, -2, -5, -3), 32, None), ((0, -5, -8, -3), 17, None), ((2, -2, -5, -3), 32, rng.integers(-40, 160, n).astype(np.int32))):
+                so, sr = orc.window_state(n, band), orc.window_state(n, band)
+                for wb in range(0, 150, W):
+                    O.banded_gotoh_window(band, typ, scheme, *pr, wb, wb + W, so, min_score=ms)
+                    R.banded_gotoh_window(band, typ, scheme, *pr, wb, wb + W, sr, min_score=ms)
+                    for k in ("score", "sx", "sy", "alive"):
+                        assert np.array_equal(so[k][wd], sr[k][wd]), (band, typ, scheme, wb, k)
+                    al = so["alive"].astype(bool) & wd
+                    assert np.array_equal(so["ckpt"][al], sr["ckpt"][al]), (band, typ, scheme, wb)
