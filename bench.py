@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 kernel-level measurements")
     ap.add_argument("--pairs", type=int, default=500_000, help="read pairs per GPU per step of the paired-end (C5-shaped) measurement; 0 = skip")
+    ap.add_argument("--c5-total-pairs", type=int, default=100_000_000,
+                    help="total pairs of the paired-end job (BASELINE configs[4]: 100M), processed as ceil(total / (gpus x pairs)) steps per GPU")
     return ap.parse_args()
 
 
@@ -273,6 +275,68 @@ def workload_config(args, n, reads_per_gpu, world):
             "l2": "index (%.2f GB) and SSA exceed L2; a 512 MiB buffer is overwritten between timed steps" % (n / 64 * 32 / 1e9)}
 
 
+def c1_config(device, best_ms):
+    """BASELINE configs[0]: 10K x 100 bp reads, each against its own 1 Kbp reference, SimpleGotohScheme(2,-1,-2,-1) as sw-benchmark
+    sets it (sw-benchmark.cu:592-641): (i) what sw-benchmark runs -- the full-matrix DP, every type; (ii) the band-15 GLOBAL variant
+    the config name mentions (100 bp vs the 114 bp window of the read).  The reference's own host path (aln::alignment_score /
+    banded_alignment_score over OpenMP) is timed beside it on the same inputs and its results compared."""
+    import nvbio_b200 as nb
+    from nvbio_b200 import aln
+    from nvbio_b200.strings import PackedStringSet, pack_symbols
+    from oracle import orc
+    rng = np.random.default_rng(77)
+    n_al, M, N = 10_000, 100, 1000
+    txt = rng.integers(0, 4, (n_al, N)).astype(np.uint8)
+    st = rng.integers(0, N - M - 14, n_al)
+    pat = np.stack([txt[i, st[i]:st[i] + M] for i in range(n_al)])
+    pat = np.where(rng.random(pat.shape) < 0.02, rng.integers(0, 4, pat.shape), pat).astype(np.uint8)
+    p_off = np.arange(n_al, dtype=np.uint32) * M; p_len = np.full(n_al, M, np.uint32)
+    t_off = np.arange(n_al, dtype=np.uint32) * N; t_len = np.full(n_al, N, np.uint32)
+    P = PackedStringSet.from_symbols(pat.reshape(-1), p_off, p_len, bits=2, big_endian=True)
+    T = PackedStringSet.from_symbols(txt.reshape(-1), t_off, t_len, bits=2, big_endian=True)
+    w_off = (t_off + st).astype(np.uint32); w_len = np.full(n_al, M + 14, np.uint32)
+    Tw = PackedStringSet.from_symbols(txt.reshape(-1), w_off, w_len, bits=2, big_endian=True)
+    scheme = (2, -1, -2, -1)
+    R = orc.Ref() if orc.Ref.available() else None
+    if R is not None:
+        R.set_num_threads(len(os.sched_getaffinity(0)))
+    res = {"scheme": "SimpleGotohScheme(2,-1,-2,-1)", "cells_full": n_al * M * N, "cells_band15": n_al * M * 15}
+    for typ, name in ((0, "global"), (1, "local"), (2, "semi_global")):
+        al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme))
+        out = [None]
+
+        def go():
+            out[0] = aln.batch_alignment_score(al, P, T)
+        ms = best_ms(go, reps=3)
+        e = {"GCUPS": n_al * M * N / (ms * 1e-3) / 1e9, "ms": ms}
+        if R is not None:
+            t0 = time.perf_counter()
+            ws, wx, wy = R.gotoh_full(typ, scheme, pat.reshape(-1), p_off, p_len, txt.reshape(-1), t_off, t_len)
+            cpu_s = time.perf_counter() - t0
+            k = out[0][1].cpu().numpy().view(np.uint32)
+            e["reference_cpu_GCUPS"] = n_al * M * N / cpu_s / 1e9
+            e["bit_identical_to_reference"] = bool(np.array_equal(out[0][0].cpu().numpy(), ws) and np.array_equal(k[:, 0], wx) and np.array_equal(k[:, 1], wy))
+        res["full_matrix_" + name] = e
+    al = aln.make_gotoh_aligner(aln.GLOBAL, aln.SimpleGotohScheme(*scheme))
+    out = [None]
+
+    def go_b():
+        out[0] = aln.batch_banded_alignment_score(15, al, P, Tw)
+    ms = best_ms(go_b, reps=3)
+    e = {"GCUPS": n_al * M * 15 / (ms * 1e-3) / 1e9, "ms": ms}
+    if R is not None:
+        t0 = time.perf_counter()
+        ws, wx, wy, _ = R.banded_gotoh(15, 0, scheme, pat.reshape(-1), p_off, p_len, txt.reshape(-1), w_off, w_len)
+        cpu_s = time.perf_counter() - t0
+        k = out[0][1].cpu().numpy().view(np.uint32)
+        e["reference_cpu_GCUPS"] = n_al * M * 15 / cpu_s / 1e9
+        e["bit_identical_to_reference"] = bool(np.array_equal(out[0][0].cpu().numpy(), ws) and np.array_equal(k[:, 0], wx) and np.array_equal(k[:, 1], wy))
+        res["reference_cpu_cores"] = R.num_threads() if hasattr(R, "num_threads") else len(os.sched_getaffinity(0))
+    res["banded_15_global"] = e
+    res["note"] = "10K alignments = 5K two-per-thread DP threads: launch/occupancy-bound on 148 SMs, not a throughput figure (see C4 and the full-matrix sweep in profiles/)"
+    return res
+
+
 def other_configs(device):
     """BASELINE.json configs[1] (FM-index exact match, 1M x 22 bp seeds, 100 Mbp) and configs[3] (banded Gotoh LOCAL,
     10M x 151 bp vs 300 bp windows, (2,2,5,3), band sweep) -- the two kernel-level metrics of the headline string,
@@ -292,6 +356,11 @@ def other_configs(device):
         return best
     out = {}
     peak, _ = measured_peaks()
+    # ---- C1: sw-benchmark's case (BASELINE configs[0]) ----
+    try:
+        out["sw_benchmark_10Kx100bp_vs_1Kbp"] = c1_config(device, best_ms)
+    except Exception as e:
+        out["sw_benchmark_10Kx100bp_vs_1Kbp"] = {"error": repr(e)[:300]}
     # ---- C2 ----
     n = 100_000_000
     gw = synth.random_genome_words(n, device=device)
@@ -351,17 +420,26 @@ def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
     ws = PairedWorkspace(fmi, genome, rs, params, pair, 24 * 2 * n_pairs)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # a second batch so that consecutive steps do not see the same reads
+    words2, _, _ = synth.sample_pairs(genome, n, n_pairs, READ_LEN, frag_mean=350.0, frag_sd=30.0, sub_rate=0.01, hard_frac=0.05,
+                                      hard_sub_rate=0.2, device=device, seed=0x61ED + rank, mut_seed=0xD0FFEE + rank)
+    rs2 = PackedStringSet.fixed(words2.reshape(-1), 2 * n_pairs, READ_LEN, stride=wpr * 16)
     for _ in range(2):
-        flush.zero_(); nb.seed_extend_paired(fmi, genome, rs, params, pair, workspace=ws)
+        flush.zero_(); nb.seed_extend_paired(fmi, genome, rs2, params, pair, workspace=ws)
     barrier(world)
-    total, k = 0.0, 5
-    for _ in range(k):
+    # the whole configs[4] job: total pairs / (gpus x pairs per step) steps on every GPU, every step timed on the device
+    k = max(1, -(-args.c5_total_pairs // (world * n_pairs)))
+    total = 0.0
+    for i in range(k):
         flush.zero_()
-        ev0.record(); nb.seed_extend_paired(fmi, genome, rs, params, pair, workspace=ws); ev1.record()
+        ev0.record(); nb.seed_extend_paired(fmi, genome, rs2 if (i & 1) else rs, params, pair, workspace=ws); ev1.record()
         torch.cuda.synchronize()
         total += ev0.elapsed_time(ev1)
+    if k & 1 == 0:                                        # leave batch 0's results in the workspace for the checks below
+        nb.seed_extend_paired(fmi, genome, rs, params, pair, workspace=ws); torch.cuda.synchronize()
     barrier(world)
-    ms = nd.max_over_ranks(total, device) / k
+    total = nd.max_over_ranks(total, device)
+    ms = total / k
     flags = ws.pair_flags.cpu().numpy()
     run, wanted = [int(v) for v in ws.n_rescue.cpu()]
     kept, hits, _ = [int(v) for v in ws.n_hits.cpu()]
@@ -376,6 +454,9 @@ def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
                         "substitutions; both mates seeded+extended (band %d LOCAL), opposite-mate rescue by full-matrix Gotoh LOCAL in the "
                         "500 bp fragment window" % (n_pairs, READ_LEN, BAND),
             "Mreads_per_s": world * 2 * n_pairs / (ms * 1e-3) / 1e6, "Mpairs_per_s": world * n_pairs / (ms * 1e-3) / 1e6, "ms_per_step": ms, "n_gpus": world,
+            "job": {"total_pairs": k * world * n_pairs, "steps_per_gpu": k, "device_seconds": total * 1e-3,
+                    "note": "BASELINE configs[4] size (100M pairs of 2 x 150 bp) as steps of two alternating synthetic batches per GPU; device time = sum of "
+                            "the per-step CUDA-event times, max over ranks (L2 flushed between steps, input generation untimed)"},
             "pairs_concordant_frac": float((flags == 1).mean()), "pairs_rescued_frac": float(((flags == 2) | (flags == 4)).mean()),
             "pairs_unpaired_frac": float((flags == 0).mean()), "rescue_jobs_run": run, "rescue_jobs_wanted": wanted,
             "rescue_cells": run * READ_LEN * 500, "hits_truncated": bool(kept != hits),
