@@ -232,6 +232,173 @@ gotoh_full_pair_kernel(const GotohScheme S, const GotohBatch b, uint2* __restric
     }
 }
 
+// full-matrix Gotoh for SMALL batches: one WARP per pair of alignments.  Lane l owns pattern columns [l*W, l*W + W); at step t
+// it computes text row t - l of its columns (a wavefront over the lanes), receiving the left boundary (H, E) and the row's
+// substitution profile from lane l-1 by shuffle -- no boundary column in memory.  The row profiles are produced 32 rows at a
+// time (lane k builds the profile of row t0 + k) and fetched by a second shuffle.  LOCAL: every lane tracks the best key
+// (H << 4) | (stripe-in-lane << 3) | (column & 7) of its cells with the row kept beside it (an 8-aligned stripe boundary can
+// fall inside a lane's columns: W <= 8 means at most one); the (H, stripe, row, column) maxima of the lanes are then
+// max-reduced, which is the reference's report order.  Same admission rules and todo-list fallback as the pair kernel.
+constexpr int WARP_BLOCKDIM = 128;
+
+template <int TYPE, int W>
+__global__ void __launch_bounds__(WARP_BLOCKDIM)
+gotoh_full_warp_kernel(const GotohScheme S, const GotohBatch b, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t n = batch_count(b);
+    const uint32_t n_pairs = (n + 1u) >> 1;
+    const uint32_t p = (blockIdx.x * WARP_BLOCKDIM + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (p >= n_pairs) return;                                          // whole warps leave together
+    const uint32_t a0 = 2u * p, a1 = a0 + 1u;
+    const bool has1 = a1 < n;
+    const uint32_t M = str_len(b.pat, a0), N = str_len(b.txt, a0);
+    const uint32_t M1 = has1 ? str_len(b.pat, a1) : M, N1 = has1 ? str_len(b.txt, a1) : N;
+    const uint32_t po0 = str_off(b.pat, a0), po1 = str_off(b.pat, has1 ? a1 : a0);
+    const uint32_t to0 = str_off(b.txt, a0), to1 = str_off(b.txt, has1 ? a1 : a0);
+    bool ok = (M == M1) && (N == N1) && M >= 1u && N >= 1u && M <= 32u * (uint32_t)W;
+
+    const int32_t Go = S.pgo, Ge = S.pge;
+    const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
+    int32_t INF = SHRT_MIN - (Go < Ge ? Go : Ge);
+    if (INF + Ge < -32768) INF = -32768 - Ge;
+    const int32_t c_eq = S.match - Go, c_ne = S.mismatch - Go;
+    const int32_t beta = -Go;
+    const uint32_t beta2 = pack16(beta, beta);
+    const uint32_t GoX = (uint32_t)(Go * 65537);
+    const uint32_t INFx = (TYPE == NVB_LOCAL) ? pack16(INF + beta, INF + beta) : pack16(INF, INF);
+
+    const uint32_t c0 = lane * (uint32_t)W;                            // columns c0 + 1 .. c0 + W (1-based)
+    const uint32_t L = (M + (uint32_t)W - 1u) / (uint32_t)W;           // lanes that own a column
+    // selectors of the lane's columns, key constants of the LOCAL tracker
+    uint32_t sel[W], kmul[W], kadd[W];
+    {
+        uint32_t bad = 0u;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const uint32_t c = c0 + (uint32_t)k;                       // 0-based column
+            uint32_t q0 = 0u, q1 = 0u;
+            if (ok && c < M) { q0 = sym_at_rt(b.pat.words, b.pat.bits, b.pat.big_endian, po0 + c); q1 = sym_at_rt(b.pat.words, b.pat.bits, b.pat.big_endian, po1 + c); }
+            bad |= (q0 | q1) >> 2;
+            sel[k] = pair_selector(q0 & 3u, q1 & 3u);
+            const uint32_t sb = (c >> 3) - (c0 >> 3);                  // 0 or 1: which 8-column stripe of this lane
+            const uint32_t ka = (sb << 3) | (c & 7u);
+            kmul[k] = (c < M) ? 16u : 0u;
+            kadd[k] = (c < M) ? (ka | (ka << 16)) : 0u;
+        }
+        ok = ok && !__any_sync(FULL, bad != 0u);
+    }
+    if (!ok) {
+        if (lane == 0u) {
+            const uint32_t cnt = has1 ? 2u : 1u;
+            const uint32_t slot = atomicAdd(todo_count, cnt);
+            todo[slot] = a0;
+            if (has1) todo[slot + 1u] = a1;
+        }
+        return;
+    }
+
+    // previous-row state of the lane's columns: V = H (LOCAL) or H + Go; F biased like the pair kernel
+    uint32_t V[W + 1], F[W + 1];
+#pragma unroll
+    for (int k = 0; k <= W; ++k) {
+        int32_t h = 0;
+        if (TYPE != NVB_LOCAL) h = ((c0 + k > 0) ? Go + Ge * (int32_t)(c0 + k - 1) : 0) + Go;
+        V[k] = pack16(h, h);
+        F[k] = INFx;
+    }
+    uint32_t prevVl = V[0];                                            // diagonal input of the next row
+    uint32_t outV = 0u, outE = 0u, curP0 = 0u, curP1 = 0u, myP0 = 0u, myP1 = 0u;
+    int32_t bk0 = -1, bk1 = -1; uint32_t br0 = 0u, br1 = 0u;           // LOCAL: best key / row per half
+    int32_t ss0 = INT_MIN, ss1 = INT_MIN; uint32_t sx0 = 0u, sx1 = 0u; // SEMI_GLOBAL: best score / row per half (owner lane)
+    const uint32_t km = (M - 1u) % (uint32_t)W + 1u;                   // column M is V[km] of lane L - 1
+    const uint32_t steps = N + L - 1u;
+    for (uint32_t t = 0; t < steps; ++t) {
+        if ((t & 31u) == 0u) {                                         // profiles of text rows t .. t + 31, one per lane
+            const uint32_t rr = t + lane;
+            uint32_t g0 = 255u, g1 = 255u;
+            if (rr < N) { g0 = sym_at_rt(b.txt.words, b.txt.bits, b.txt.big_endian, to0 + rr); g1 = sym_at_rt(b.txt.words, b.txt.bits, b.txt.big_endian, to1 + rr); }
+            myP0 = sub_profile(g0, c_eq, c_ne); myP1 = sub_profile(g1, c_eq, c_ne);
+        }
+        const uint32_t rowP0 = __shfl_sync(FULL, myP0, t & 31u), rowP1 = __shfl_sync(FULL, myP1, t & 31u);
+        uint32_t inV = __shfl_up_sync(FULL, outV, 1), inE = __shfl_up_sync(FULL, outE, 1);
+        uint32_t inP0 = __shfl_up_sync(FULL, curP0, 1), inP1 = __shfl_up_sync(FULL, curP1, 1);
+        if (lane == 0u) {
+            const int32_t hl = (TYPE == NVB_GLOBAL) ? S.tgo + S.tge * (int32_t)t + Go : ((TYPE == NVB_LOCAL) ? 0 : Go);
+            inV = pack16(hl, hl);
+            inE = (TYPE == NVB_LOCAL) ? beta2 : INFx;
+            inP0 = rowP0; inP1 = rowP1;
+        }
+        const uint32_t r = t - lane;                                   // wraps for t < lane: then r >= N
+        if (r < N && lane < L) {
+            uint32_t E = inE, Vd = prevVl, Vleft = inV;
+            prevVl = inV;
+            uint32_t rowkey = 0u;
+#pragma unroll
+            for (int k = 1; k <= W; ++k) {
+                const uint32_t s = prmt(inP0, inP1, sel[k - 1]);
+                F[k] = NVB_VIADDMAX(F[k], Ge2, V[k]);
+                E    = NVB_VIADDMAX(E, Ge2, Vleft);
+                const uint32_t old = V[k];
+                if (TYPE == NVB_LOCAL) {
+                    const uint32_t hb = NVB_VIMAX3(NVB_VIADDMAX(Vd, s, F[k]), E, beta2);
+                    V[k] = hb * S.one + GoX;
+                    rowkey = NVB_VIMAX_U(rowkey, V[k] * kmul[k - 1] + kadd[k - 1]);
+                } else {
+                    V[k] = NVB_VIADD(NVB_VIMAX(NVB_VIADDMAX(Vd, s, F[k]), E), Go2);
+                }
+                Vleft = V[k];
+                Vd = old;
+            }
+            outV = V[W]; outE = E; curP0 = inP0; curP1 = inP1;
+            if (TYPE == NVB_LOCAL) {
+                const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
+                if ((k0 >> 3) >= (bk0 >> 3)) { bk0 = k0; br0 = r; }
+                if ((k1 >> 3) >= (bk1 >> 3)) { bk1 = k1; br1 = r; }
+            }
+            if (TYPE == NVB_SEMI_GLOBAL && lane == L - 1u) {
+                uint32_t vM = V[1];
+#pragma unroll
+                for (int k = 2; k <= W; ++k) if ((uint32_t)k == km) vM = V[k];
+                const int32_t h0 = half_lo(vM) - Go, h1 = half_hi(vM) - Go;
+                if (ss0 <= h0) { ss0 = h0; sx0 = r + 1u; }
+                if (ss1 <= h1) { ss1 = h1; sx1 = r + 1u; }
+            }
+        }
+    }
+    // results
+    SinkResult r0, r1;
+    if (TYPE == NVB_LOCAL) {
+        // (H, global 8-column stripe, row, column & 7) as one 64-bit key per half, max over the lanes
+        unsigned long long K0 = 0ull, K1 = 0ull;
+        if (lane < L) {
+            K0 = ((unsigned long long)(uint32_t)(bk0 >> 4) << 32) | ((unsigned long long)((c0 >> 3) + (((uint32_t)bk0 >> 3) & 1u)) << 24) | ((unsigned long long)br0 << 3) | ((uint32_t)bk0 & 7u);
+            K1 = ((unsigned long long)(uint32_t)(bk1 >> 4) << 32) | ((unsigned long long)((c0 >> 3) + (((uint32_t)bk1 >> 3) & 1u)) << 24) | ((unsigned long long)br1 << 3) | ((uint32_t)bk1 & 7u);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const unsigned long long o0 = __shfl_xor_sync(FULL, K0, d), o1 = __shfl_xor_sync(FULL, K1, d);
+            K0 = o0 > K0 ? o0 : K0; K1 = o1 > K1 ? o1 : K1;
+        }
+        r0.score = (int32_t)(K0 >> 32); r0.x = (uint32_t)((K0 >> 3) & 0x1FFFFFull) + 1u; r0.y = (uint32_t)((K0 >> 24) & 0xFFull) * 8u + (uint32_t)(K0 & 7ull) + 1u;
+        r1.score = (int32_t)(K1 >> 32); r1.x = (uint32_t)((K1 >> 3) & 0x1FFFFFull) + 1u; r1.y = (uint32_t)((K1 >> 24) & 0xFFull) * 8u + (uint32_t)(K1 & 7ull) + 1u;
+    } else {
+        uint32_t vM = V[1];
+#pragma unroll
+        for (int k = 2; k <= W; ++k) if ((uint32_t)k == km) vM = V[k];
+        int32_t s0 = (TYPE == NVB_GLOBAL) ? half_lo(vM) - Go : ss0, s1 = (TYPE == NVB_GLOBAL) ? half_hi(vM) - Go : ss1;
+        uint32_t x0 = (TYPE == NVB_GLOBAL) ? N : sx0, x1 = (TYPE == NVB_GLOBAL) ? N : sx1;
+        s0 = __shfl_sync(FULL, s0, (int)(L - 1u)); s1 = __shfl_sync(FULL, s1, (int)(L - 1u));
+        x0 = __shfl_sync(FULL, x0, (int)(L - 1u)); x1 = __shfl_sync(FULL, x1, (int)(L - 1u));
+        r0.score = s0; r0.x = x0; r0.y = M; r1.score = s1; r1.x = x1; r1.y = M;
+    }
+    if (lane == 0u) {
+        b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
+        if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
+    }
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(GENERIC_BLOCKDIM)
 gotoh_full_todo_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ col, const uint32_t* __restrict__ todo, const uint32_t* __restrict__ todo_count)
@@ -356,6 +523,8 @@ static inline int dir_words(int band) { return (band * 4 + 31) / 32; }
 
 // force_path: 0 auto, 1 generic only (used by tests to exercise both paths on the same inputs)
 static int g_force_path = 0;
+static int g_full_warp = 0;           // 0 = by batch size, 1 = always the warp-per-pair kernel, 2 = never (nvb_debug_full_warp)
+static uint32_t g_full_warp_max_pairs = 30000u;   // measured cross-over with the thread-per-pair kernel: ~50-60 K alignments
 static int g_full_minb = 0;          // 0 = per-type default; tuning knob of gotoh_full_pair_kernel's occupancy (nvb_debug_full_minb)
 
 static int banded_impl(int band, int type, const nvb_gotoh_scheme* scheme,
@@ -457,6 +626,31 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     // packed pairs first (the boundary columns of pair p live in the first half of `col`), then whatever they rejected
     NVB_CUDA_TRY(cudaMemsetAsync(todo_count, 0, sizeof(uint32_t), s));
     const uint32_t n_pairs = (n + 1u) >> 1;
+    // small batches: one warp per pair (a thread per pair would leave most of the 148 SMs idle); W columns per lane
+    const uint32_t max_m = patterns->length;
+    const bool use_warp = g_full_warp == 1 || (g_full_warp == 0 && n_pairs <= g_full_warp_max_pairs);
+    if (use_warp && max_m >= 1u && max_m <= 256u) {
+        const uint32_t Wc = (max_m + 31u) / 32u;
+        const uint32_t wgrid = (uint32_t)(((uint64_t)n_pairs * 32u + WARP_BLOCKDIM - 1) / WARP_BLOCKDIM);
+        const uint32_t tgrid2 = grid < 148u * 8u ? grid : 148u * 8u;
+#define NVB_FULL_WARP_W(T, WW) gotoh_full_warp_kernel<T, WW><<<wgrid, WARP_BLOCKDIM, 0, s>>>(S, b, todo, todo_count)
+#define NVB_FULL_WARP(T)                                                                                   \
+        switch (Wc) {                                                                                      \
+        case 1: NVB_FULL_WARP_W(T, 1); break; case 2: NVB_FULL_WARP_W(T, 2); break;                        \
+        case 3: NVB_FULL_WARP_W(T, 3); break; case 4: NVB_FULL_WARP_W(T, 4); break;                        \
+        case 5: NVB_FULL_WARP_W(T, 5); break; case 6: NVB_FULL_WARP_W(T, 6); break;                        \
+        case 7: NVB_FULL_WARP_W(T, 7); break; default: NVB_FULL_WARP_W(T, 8); break; }                     \
+        gotoh_full_todo_kernel<T><<<tgrid2, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, todo, todo_count);
+        switch (type) {
+        case NVB_GLOBAL: NVB_FULL_WARP(NVB_GLOBAL) break;
+        case NVB_LOCAL:  NVB_FULL_WARP(NVB_LOCAL) break;
+        default:         NVB_FULL_WARP(NVB_SEMI_GLOBAL) break;
+        }
+#undef NVB_FULL_WARP
+#undef NVB_FULL_WARP_W
+        NVB_LAUNCH_CHECK();
+        return NVB_OK;
+    }
     const uint32_t pgrid = (n_pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
     uint32_t tgrid = grid < 148u * 8u ? grid : 148u * 8u;
     // occupancy per type as measured (tools/bench_full.py): LOCAL and SEMI_GLOBAL run fastest spill-free at 2 CTAs/SM, GLOBAL at 3
@@ -577,5 +771,6 @@ int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_stri
 // test hook (declared in tests only): 0 = auto, 1 = generic int32 kernel for everything
 void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
 void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
+void nvb_debug_full_warp(int mode) { g_full_warp = mode; }
 
 } // extern "C"

@@ -243,12 +243,18 @@ def test_full_matrix_packed_path(O, typ):
             P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
             T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2, big_endian=True)
             al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme))
+            nb.lib().nvb_debug_full_warp(C.c_int(2))           # thread-per-pair kernel at its three occupancy variants
             for minb in (2, 3, 4):
                 nb.lib().nvb_debug_full_minb(C.c_int(minb))
                 s, k = aln.batch_alignment_score(al, P, T)
                 k = host_u32(k)
                 assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, scheme, n_frac, minb)
             nb.lib().nvb_debug_full_minb(C.c_int(0))
+            nb.lib().nvb_debug_full_warp(C.c_int(1))           # warp-per-pair wavefront kernel
+            s, k = aln.batch_alignment_score(al, P, T)
+            k = host_u32(k)
+            nb.lib().nvb_debug_full_warp(C.c_int(0))
+            assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, scheme, n_frac, "warp")
             force_path(1)
             try:
                 s, k = aln.batch_alignment_score(al, P, T)
@@ -340,3 +346,26 @@ def test_windowed_banded_score(O, band):
                 ok = so["alive"].astype(bool)
                 k = host_u32(st.sink)
                 assert np.array_equal(st.score.cpu().numpy()[ok], whole[0][ok]) and np.array_equal(k[ok, 0], whole[1][ok]) and np.array_equal(k[ok, 1], whole[2][ok])
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_full_matrix_warp_kernel_every_width(O, typ):
+    """gotoh_full_warp_kernel<TYPE, W> for every W = 1..8 (pattern lengths 1..256, incl. lengths that leave the last lane partly
+    empty and put an 8-column stripe boundary inside a lane), short and long texts (fewer rows than lanes), LOCAL tie order"""
+    from tests.test_host_core import paired_full_problems
+    rng = np.random.default_rng(1300 + typ)
+    nb.lib().nvb_debug_full_warp(C.c_int(1))
+    try:
+        for max_m in (7, 32, 33, 64, 90, 128, 150, 161, 200, 224, 256):
+            for scheme in ((2, -1, -2, -1), (2, -2, -5, -3)):
+                pr = paired_full_problems(rng, 150, max_m=max_m, max_n=330)
+                want = O.gotoh_full(typ, scheme, *pr)
+                pat, p_off, p_len, txt, t_off, t_len = pr
+                P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=2, big_endian=True)
+                P.length = max_m
+                T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2, big_endian=True)
+                s, k = aln.batch_alignment_score(aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(*scheme)), P, T)
+                k = host_u32(k)
+                assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, max_m, scheme)
+    finally:
+        nb.lib().nvb_debug_full_warp(C.c_int(0))

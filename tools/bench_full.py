@@ -14,7 +14,7 @@ def time_ms(fn, reps=3):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
 
-CONFIGS = ((200_000, 150, 500), (1_000_000, 150, 300), (10_000, 100, 1000), (100_000, 100, 1000))
+CONFIGS = ((200_000, 150, 500), (1_000_000, 150, 300), (10_000, 100, 1000), (100_000, 100, 1000), (20_000, 150, 500), (50_000, 150, 500))
 if "--one" in sys.argv:
     CONFIGS = CONFIGS[:1]
 for (n, M, N) in CONFIGS:
@@ -26,10 +26,15 @@ for (n, M, N) in CONFIGS:
     for typ in (1, 0, 2):
         al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -2, -5, -3))
         out = {"n": n, "M": M, "N": N, "type": typ}
+        nb.lib().nvb_debug_full_warp(C.c_int(2))
         for minb in (2, 3, 4):
             nb.lib().nvb_debug_full_minb(C.c_int(minb))
             ms = time_ms(lambda: aln.batch_alignment_score(al, P, T))
             out["packed_minb%d_gcups" % minb] = round(n * M * N / ms / 1e6, 1)
+        nb.lib().nvb_debug_full_warp(C.c_int(1))
+        ms = time_ms(lambda: aln.batch_alignment_score(al, P, T))
+        out["warp_gcups"] = round(n * M * N / ms / 1e6, 1)
+        nb.lib().nvb_debug_full_warp(C.c_int(0))
         nb.lib().nvb_debug_full_minb(C.c_int(0))
         nb.lib().nvb_debug_force_gotoh_path(C.c_int(1))
         ms = time_ms(lambda: aln.batch_alignment_score(al, P, T))
