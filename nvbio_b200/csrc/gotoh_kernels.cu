@@ -628,7 +628,8 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     const uint32_t n_pairs = (n + 1u) >> 1;
     // small batches: one warp per pair (a thread per pair would leave most of the 148 SMs idle); W columns per lane
     const uint32_t max_m = patterns->length;
-    const bool use_warp = g_full_warp == 1 || (g_full_warp == 0 && n_pairs <= g_full_warp_max_pairs);
+    // with a device-side count (`n` is then only a capacity) the batch is usually much smaller than its capacity: allow 4x
+    const bool use_warp = g_full_warp == 1 || (g_full_warp == 0 && n_pairs <= (d_n ? 4u : 1u) * g_full_warp_max_pairs);
     if (use_warp && max_m >= 1u && max_m <= 256u) {
         const uint32_t Wc = (max_m + 31u) / 32u;
         const uint32_t wgrid = (uint32_t)(((uint64_t)n_pairs * 32u + WARP_BLOCKDIM - 1) / WARP_BLOCKDIM);

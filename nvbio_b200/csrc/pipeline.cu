@@ -177,14 +177,26 @@ pipe_find_leaders_kernel(const uint32_t* __restrict__ counts, const uint32_t* __
                          const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
                          uint32_t* __restrict__ leader, uint32_t* __restrict__ flag)
 {
-    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
-    if (h >= counts[0]) return;
-    const uint32_t s = hit_string[h], o = t_off[h], l = t_len[h];
+    // the block's 256 hits plus the 64 before them, staged once in shared memory (the look-back re-reads them ~5x on average)
+    constexpr uint32_t BACK = 64u;
+    __shared__ uint32_t ss[256 + BACK], so[256 + BACK], sl[256 + BACK];
+    const uint32_t n = counts[0];
+    const uint32_t h0 = blockIdx.x * 256;
+    if (h0 >= n) return;
+    for (uint32_t i = threadIdx.x; i < 256 + BACK; i += 256) {
+        const int64_t g = (int64_t)h0 - BACK + i;
+        const bool in = g >= 0 && g < (int64_t)n;
+        ss[i] = in ? hit_string[g] : 0xFFFFFFFFu; so[i] = in ? t_off[g] : 0u; sl[i] = in ? t_len[g] : 0u;
+    }
+    __syncthreads();
+    const uint32_t h = h0 + threadIdx.x;
+    if (h >= n) return;
+    const uint32_t me = threadIdx.x + BACK;
+    const uint32_t s = ss[me], o = so[me], l = sl[me];
     uint32_t lead = h;
-    for (uint32_t back = 1; back <= 64u && back <= h; ++back) {
-        const uint32_t g = h - back;
-        if (hit_string[g] != s) break;
-        if (t_off[g] == o && t_len[g] == l) lead = g;
+    for (uint32_t back = 1; back <= BACK && back <= h; ++back) {
+        if (ss[me - back] != s) break;
+        if (so[me - back] == o && sl[me - back] == l) lead = h - back;
     }
     leader[h] = lead;
     flag[h] = (lead == h) ? 1u : 0u;
@@ -211,16 +223,21 @@ pipe_compact_jobs_kernel(const uint32_t* __restrict__ counts, const uint32_t* __
     jp_off[j] = p_off[h]; jp_len[j] = p_len[h]; jt_off[j] = t_off[h]; jt_len[j] = t_len[h];
 }
 
+// every hit receives its group's (score, sink); the best-per-read reduction (see pipe_reduce_kernel) rides along
 __global__ void __launch_bounds__(256)
-pipe_scatter_scores_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ leader, const uint32_t* __restrict__ job_idx,
-                           const int32_t* __restrict__ job_score, const uint2* __restrict__ job_sink,
-                           int32_t* __restrict__ score, uint2* __restrict__ sink)
+pipe_scatter_scores_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ leader, const uint32_t* __restrict__ job_idx,
+                           const int32_t* __restrict__ job_score, const uint2* __restrict__ job_sink, const uint32_t* __restrict__ hit_string,
+                           int32_t* __restrict__ score, uint2* __restrict__ sink, unsigned long long* __restrict__ best_key)
 {
     const uint32_t h = blockIdx.x * 256 + threadIdx.x;
     if (h >= counts[0]) return;
     const uint32_t j = job_idx[leader[h]];
-    score[h] = job_score[j];
+    const int32_t sc = job_score[j];
+    score[h] = sc;
     sink[h]  = job_sink[j];
+    const uint32_t read = hit_string[h] / g.strands;
+    const unsigned long long key = ((unsigned long long)((uint32_t)sc ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - h);
+    atomicMax(best_key + read, key);
 }
 
 // best hit per read: max score, ties -> smallest hit index (deterministic)
@@ -593,6 +610,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(5);
+    NVB_CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * n_reads, s));
     // 5. extension
     if (hit_capacity) {
         size_t gb = gotoh_bytes;
@@ -603,7 +621,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
             r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts + 2, hit_capacity,
                                                 job_score, (nvb_uint2*)job_sink, gotoh_tmp, &gb, stream);
             if (r != NVB_OK) return r;
-            pipe_scatter_scores_kernel<<<hgrid, 256, 0, s>>>(counts, leader, job_idx, job_score, job_sink, h_score, h_sink);
+            pipe_scatter_scores_kernel<<<hgrid, 256, 0, s>>>(g, counts, leader, job_idx, job_score, job_sink, hit_string, h_score, h_sink, best_key);
             NVB_LAUNCH_CHECK();
         } else {
             pats.d_words = str_words; pats.d_offsets = p_off; pats.d_lengths = p_len;
@@ -614,9 +632,8 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         }
     }
     NVB_STAGE(6);
-    // 6. best per read
-    NVB_CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * n_reads, s));
-    if (hit_capacity) {
+    // 6. best per read (with job de-duplication the reduction already happened in the scatter kernel)
+    if (hit_capacity && !dedup) {
         pipe_reduce_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, h_score, best_key);
         NVB_LAUNCH_CHECK();
     }
