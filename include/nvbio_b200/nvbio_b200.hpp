@@ -107,5 +107,49 @@ void batch_alignment_score(const GotohAligner<TYPE, scheme_type> aligner, const 
     check(nvb_gotoh_score(TYPE, &s, &patterns, &texts, n, d_scores, d_sinks, temp.ptr, &tb, stream), "nvb_gotoh_score");
 }
 
+/// the alignment of a traceback call, SoA over the batch: BestSink + Alignment<int32>::source + the backtracer's op stream
+struct TracebackArrays { int32_t* d_scores; nvb_uint2* d_sinks; nvb_uint2* d_sources; uint8_t* d_ops; uint32_t max_ops; uint32_t* d_n_ops; };
+
+/// batch form of aln::banded_alignment_traceback<BAND_LEN,...> (nvbio/alignment/banded_inl.h:352-489)
+template <uint32_t BAND_LEN, AlignmentType TYPE, typename scheme_type>
+void batch_banded_alignment_traceback(const GotohAligner<TYPE, scheme_type> aligner, const nvb_string_set& patterns, const nvb_string_set& texts,
+                                      uint32_t n, const TracebackArrays& out, device_buffer<char>& temp, cudaStream_t stream = 0)
+{
+    const nvb_gotoh_scheme s = aligner.scheme.abi();
+    size_t tb = 0;
+    int r = nvb_banded_gotoh_traceback(BAND_LEN, TYPE, &s, &patterns, nullptr, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops,
+                                       out.d_n_ops, nullptr, &tb, stream);
+    if (r != NVB_E_TEMP_SIZE) check(r, "nvb_banded_gotoh_traceback");
+    temp.resize(tb ? tb : 1);
+    check(nvb_banded_gotoh_traceback(BAND_LEN, TYPE, &s, &patterns, nullptr, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops,
+                                     out.d_n_ops, temp.ptr, &tb, stream), "nvb_banded_gotoh_traceback");
+}
+
+/// batch form of aln::alignment_traceback (full matrix; nvbio/alignment/alignment_inl.h:365-530)
+template <AlignmentType TYPE, typename scheme_type>
+void batch_alignment_traceback(const GotohAligner<TYPE, scheme_type> aligner, const nvb_string_set& patterns, const nvb_string_set& texts,
+                               uint32_t n, const TracebackArrays& out, device_buffer<char>& temp, cudaStream_t stream = 0)
+{
+    const nvb_gotoh_scheme s = aligner.scheme.abi();
+    size_t tb = 0;
+    int r = nvb_gotoh_traceback(TYPE, &s, &patterns, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops, out.d_n_ops, nullptr, &tb, stream);
+    if (r != NVB_E_TEMP_SIZE) check(r, "nvb_gotoh_traceback");
+    temp.resize(tb ? tb : 1);
+    check(nvb_gotoh_traceback(TYPE, &s, &patterns, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops, out.d_n_ops, temp.ptr, &tb, stream),
+          "nvb_gotoh_traceback");
+}
+
+/// one [window_begin, window_end) pass of aln::banded_alignment_score<BAND_LEN>(..., window_begin, window_end, sink, checkpoint)
+/// over a batch (nvbio/alignment/banded_inl.h:178-218); d_checkpoints holds BAND_LEN short2 per alignment
+template <uint32_t BAND_LEN, AlignmentType TYPE, typename scheme_type>
+void batch_banded_alignment_score_window(const GotohAligner<TYPE, scheme_type> aligner, const nvb_string_set& patterns, const nvb_string_set& texts,
+                                         uint32_t n, uint32_t window_begin, uint32_t window_end, const int32_t* d_min_scores, int16_t* d_checkpoints,
+                                         int32_t* d_scores, nvb_uint2* d_sinks, uint8_t* d_alive, cudaStream_t stream = 0)
+{
+    const nvb_gotoh_scheme s = aligner.scheme.abi();
+    check(nvb_banded_gotoh_score_window(BAND_LEN, TYPE, &s, &patterns, nullptr, &texts, n, window_begin, window_end, d_min_scores, d_checkpoints,
+                                        d_scores, d_sinks, d_alive, stream), "nvb_banded_gotoh_score_window");
+}
+
 } // namespace aln
 } // namespace nvbio_b200

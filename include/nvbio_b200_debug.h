@@ -1,0 +1,20 @@
+/* nvbio_b200_debug.h -- test / tuning hooks exported by libnvbio_b200.so.  NOT part of the drop-in ABI (include/nvbio_b200.h):
+ * they switch between the library's own GPU code paths so that the tests can exercise each of them and the microbenchmarks can
+ * compare them; none of them changes a result.  Process-wide, not thread-safe. */
+#ifndef NVBIO_B200_DEBUG_H
+#define NVBIO_B200_DEBUG_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* banded / full-matrix Gotoh: 0 = automatic, 1 = the int32 one-alignment-per-thread kernels for everything */
+void nvb_debug_force_gotoh_path(int path);
+/* full-matrix pair kernel occupancy variant: 0 = per-type default, 2 / 3 / 4 = minimum CTAs per SM */
+void nvb_debug_full_minb(int minb);
+/* full-matrix dispatch: 0 = by batch size, 1 = always the warp-per-pair kernel, 2 = never */
+void nvb_debug_full_warp(int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -8,6 +8,7 @@
 //
 // The path is bound by integer issue rate, not memory: ~0.1 KB moved per 4,650 cell updates (B=31, M=150).
 #include "gotoh_core.cuh"
+#include "../../include/nvbio_b200_debug.h"
 #include "gotoh_full_core.cuh"
 
 namespace nvb {
@@ -769,7 +770,7 @@ int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_stri
     return NVB_OK;
 }
 
-// test hook (declared in tests only): 0 = auto, 1 = generic int32 kernel for everything
+// test / tuning hooks (include/nvbio_b200_debug.h)
 void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
 void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
 void nvb_debug_full_warp(int mode) { g_full_warp = mode; }
