@@ -202,13 +202,15 @@ int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme
  * Replaces aln::alignment_score / aln::BatchedAlignmentScore<stream,DeviceThreadScheduler> with
  * GotohAligner<TYPE,SimpleGotohScheme> (default PatternBlockingTag; nvbio/alignment/alignment_inl.h:95-125,
  * gotoh/gotoh_inl.h:459-960, batched_inl.h:236-605) -- the DP sw-benchmark times (sw-benchmark.cu:592-641) and nvBowtie's
- * opposite-mate scoring.  LOCAL ties resolve in the reference's (8-column stripe, row, column) order. */
-int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+ * opposite-mate scoring.  LOCAL ties resolve in the reference's (8-column stripe, row, column) order.
+ * d_quals (one byte per pattern symbol, indexed like the pattern offsets; may be NULL) and scheme->d_qual_table select the
+ * quality-dependent substitution scores as in nvb_banded_gotoh_score; such batches run on the int32 kernel. */
+int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
                     int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream);
 
 /* Same, with the number of alignments read from device memory (*d_n, clamped to n_max): lets a producer kernel decide
  * the batch size without a host round trip (the opposite-mate stage of nvb_seed_extend_paired). */
-int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts,
+int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts,
                              const uint32_t* d_n, uint32_t n_max,
                              int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream);
 
@@ -221,7 +223,7 @@ int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb
  * nvbio/alignment/alignment_inl.h:365-530; state machine gotoh/gotoh_inl.h:1806-1884) and its batched form
  * BatchedAlignmentTraceback (batched_inl.h:607-860).  No checkpoints: d_temp holds the whole direction matrix, 4 bits per cell
  * (max_text_len * ceil(max_pattern_len/32) * 16 bytes per alignment). */
-int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
                         int32_t* d_score, nvb_uint2* d_sink, nvb_uint2* d_source,
                         uint8_t* d_ops, uint32_t max_ops, uint32_t* d_n_ops,
                         void* d_temp, size_t* temp_bytes, void* stream);

@@ -101,10 +101,10 @@ void batch_alignment_score(const GotohAligner<TYPE, scheme_type> aligner, const 
 {
     const nvb_gotoh_scheme s = aligner.scheme.abi();
     size_t tb = 0;
-    int r = nvb_gotoh_score(TYPE, &s, &patterns, &texts, n, d_scores, d_sinks, nullptr, &tb, stream);
+    int r = nvb_gotoh_score(TYPE, &s, &patterns, nullptr, &texts, n, d_scores, d_sinks, nullptr, &tb, stream);
     if (r != NVB_E_TEMP_SIZE) check(r, "nvb_gotoh_score");
     temp.resize(tb ? tb : 1);
-    check(nvb_gotoh_score(TYPE, &s, &patterns, &texts, n, d_scores, d_sinks, temp.ptr, &tb, stream), "nvb_gotoh_score");
+    check(nvb_gotoh_score(TYPE, &s, &patterns, nullptr, &texts, n, d_scores, d_sinks, temp.ptr, &tb, stream), "nvb_gotoh_score");
 }
 
 /// the alignment of a traceback call, SoA over the batch: BestSink + Alignment<int32>::source + the backtracer's op stream
@@ -132,10 +132,10 @@ void batch_alignment_traceback(const GotohAligner<TYPE, scheme_type> aligner, co
 {
     const nvb_gotoh_scheme s = aligner.scheme.abi();
     size_t tb = 0;
-    int r = nvb_gotoh_traceback(TYPE, &s, &patterns, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops, out.d_n_ops, nullptr, &tb, stream);
+    int r = nvb_gotoh_traceback(TYPE, &s, &patterns, nullptr, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops, out.d_n_ops, nullptr, &tb, stream);
     if (r != NVB_E_TEMP_SIZE) check(r, "nvb_gotoh_traceback");
     temp.resize(tb ? tb : 1);
-    check(nvb_gotoh_traceback(TYPE, &s, &patterns, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops, out.d_n_ops, temp.ptr, &tb, stream),
+    check(nvb_gotoh_traceback(TYPE, &s, &patterns, nullptr, &texts, n, out.d_scores, out.d_sinks, out.d_sources, out.d_ops, out.max_ops, out.d_n_ops, temp.ptr, &tb, stream),
           "nvb_gotoh_traceback");
 }
 

@@ -161,7 +161,7 @@ def cigar(ops_row, n_ops: int) -> str:
     return "".join(out)
 
 
-def batch_alignment_score(aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet):
+def batch_alignment_score(aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet, quals: Optional[torch.Tensor] = None):
     """aln::batch_alignment_score(aligner, patterns, texts, sinks, DeviceThreadScheduler(), ...) with a Gotoh aligner: the
     full-matrix DP of every pattern against its whole text (nvbio/alignment/batched_inl.h:984-1040).
     Returns (scores int32[n], sinks int32[n,2] = (text end, pattern end))."""
@@ -175,7 +175,8 @@ def batch_alignment_score(aligner: GotohAligner, patterns: PackedStringSet, text
     tb = C.c_size_t(0)
 
     def call(temp_ptr):
-        return L.nvb_gotoh_score(C.c_int(aligner.type), C.byref(sch), C.byref(p), C.byref(t), C.c_uint32(n),
+        return L.nvb_gotoh_score(C.c_int(aligner.type), C.byref(sch), C.byref(p), C.c_void_p(quals.data_ptr()) if quals is not None else None,
+                                 C.byref(t), C.c_uint32(n),
                                  C.c_void_p(score.data_ptr()), C.c_void_p(sink.data_ptr()), temp_ptr, C.byref(tb), _stream())
     r = call(None)
     if r != -2:
@@ -185,7 +186,8 @@ def batch_alignment_score(aligner: GotohAligner, patterns: PackedStringSet, text
     return score, sink
 
 
-def batch_alignment_traceback(aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet, max_ops: Optional[int] = None):
+def batch_alignment_traceback(aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet, max_ops: Optional[int] = None,
+                              quals: Optional[torch.Tensor] = None):
     """aln::alignment_traceback (full-matrix Gotoh) for a batch (nvbio/alignment/alignment_inl.h:365-530, batched_inl.h:607-860).
     Returns dict(score[n], sink[n,2], source[n,2], ops[n,max_ops] uint8 in END->START push order (0 M, 1 I, 2 D), n_ops[n])."""
     L = lib()
@@ -201,7 +203,8 @@ def batch_alignment_traceback(aligner: GotohAligner, patterns: PackedStringSet, 
     tb = C.c_size_t(0)
 
     def call(temp_ptr):
-        return L.nvb_gotoh_traceback(C.c_int(aligner.type), C.byref(sch), C.byref(p), C.byref(t), C.c_uint32(n),
+        return L.nvb_gotoh_traceback(C.c_int(aligner.type), C.byref(sch), C.byref(p), C.c_void_p(quals.data_ptr()) if quals is not None else None,
+                                     C.byref(t), C.c_uint32(n),
                                      C.c_void_p(out["score"].data_ptr()), C.c_void_p(out["sink"].data_ptr()),
                                      C.c_void_p(out["source"].data_ptr()), C.c_void_p(out["ops"].data_ptr()), C.c_uint32(max_ops),
                                      C.c_void_p(out["n_ops"].data_ptr()), temp_ptr, C.byref(tb), _stream())

@@ -25,7 +25,8 @@ template <int TYPE, bool DIRS>
 __host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
-        int2* __restrict__ col, size_t col_stride, uint32_t* __restrict__ dirs = nullptr, uint32_t dir_row_words = 0)
+        int2* __restrict__ col, size_t col_stride, uint32_t* __restrict__ dirs = nullptr, uint32_t dir_row_words = 0,
+        const uint8_t* __restrict__ quals = nullptr)
 {
     SinkResult res; res.score = INT_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
     if (M == 0 || N == 0) return res;            // outside the supported domain (see header)
@@ -35,10 +36,17 @@ __host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
     for (uint32_t b = 0; b < M; b += FULL_W) {
         const bool first = (b == 0), last = (b + FULL_W >= M);
         uint32_t q[FULL_W];
+        uint32_t qq4[FULL_W / 4];                 // the stripe's base qualities, four per word (quality-table schemes only)
         {
             SymReaderRT pr(pwords, pbits, pbe);
 #pragma unroll
             for (int j = 0; j < FULL_W; ++j) q[j] = (b + j < M) ? pr.get(poff + b + j) : 256u;     // 256 never equals a text symbol
+#pragma unroll
+            for (int w = 0; w < FULL_W / 4; ++w) qq4[w] = 0u;
+            if (S.qtab && quals) {
+#pragma unroll
+                for (int j = 0; j < FULL_W; ++j) if (b + j < M) qq4[j >> 2] |= (uint32_t)quals[poff + b + j] << (8 * (j & 3));
+            }
         }
         int32_t H[FULL_W + 1], F[FULL_W + 1];
 #pragma unroll
@@ -65,7 +73,9 @@ __host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
                 F[j] = imax2(ftop, htop);
                 const int32_t eleft = E + Ge, hleft = H[j - 1] + Go;      // H[j-1] is already this row
                 E    = imax2(eleft, hleft);
-                const int32_t diagonal = Hd + ((g == q[j - 1]) ? S.match : S.mismatch);
+                int32_t sub = (g == q[j - 1]) ? S.match : S.mismatch;
+                if (S.qtab) sub = S.qtab[2u * ((qq4[(j - 1) >> 2] >> (8 * ((j - 1) & 3))) & 255u) + ((g == q[j - 1]) ? 0u : 1u)];
+                const int32_t diagonal = Hd + sub;
                 int32_t h = imax2(imax2(E, F[j]), diagonal);
                 if (TYPE == NVB_LOCAL) h = imax2(h, 0);
                 if (DIRS) {
@@ -113,9 +123,9 @@ template <int TYPE>
 __host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
-        int2* __restrict__ col, size_t col_stride)
+        int2* __restrict__ col, size_t col_stride, const uint8_t* __restrict__ quals = nullptr)
 {
-    return gotoh_full_impl<TYPE, false>(S, pwords, pbits, pbe, poff, M, twords, tbits, tbe, toff, N, col, col_stride);
+    return gotoh_full_impl<TYPE, false>(S, pwords, pbits, pbe, poff, M, twords, tbits, tbe, toff, N, col, col_stride, nullptr, 0, quals);
 }
 
 // walk the direction matrix from the sink (state machine of nvbio/alignment/gotoh/gotoh_inl.h:1806-1884 plus the first-row /

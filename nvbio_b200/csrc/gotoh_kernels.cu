@@ -192,7 +192,7 @@ gotoh_full_traceback_kernel(const GotohScheme S, const GotohBatch b, int2* __res
     SinkResult r; r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu;
     if (N <= o.dir_rows && (M + 31u) / 32u * 4u <= dir_row_words)
         r = gotoh_full_impl<TYPE, true>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), M,
-                                        b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), N, col + a, (size_t)b.n_max, dirs, dir_row_words);
+                                        b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), N, col + a, (size_t)b.n_max, dirs, dir_row_words, b.quals);
     b.score[a] = r.score;
     b.sink[a]  = make_uint2(r.x, r.y);
     uint32_t sx = 0xFFFFFFFFu, sy = 0xFFFFFFFFu, cnt = 0;
@@ -409,7 +409,7 @@ gotoh_full_todo_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict
         const uint32_t a = todo[t];
         const SinkResult r = gotoh_full<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a),
                                               b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a),
-                                              col + a, (size_t)b.n_max);
+                                              col + a, (size_t)b.n_max, b.quals);
         b.score[a] = r.score;
         b.sink[a]  = make_uint2(r.x, r.y);
     }
@@ -591,13 +591,12 @@ int nvb_banded_gotoh_score_indirect(int band_len, int type, const nvb_gotoh_sche
     return banded_impl(band_len, type, scheme, patterns, d_quals, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
 }
 
-static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts,
+static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts,
                            const uint32_t* d_n, uint32_t n,
                            int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
 {
     if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
     if (type < 0 || type > 2) return NVB_E_INVALID;
-    if (scheme->d_qual_table) return NVB_E_UNSUPPORTED;                 // quality tables: banded path only (for now)
     if (texts->length > 65535u || patterns->length > 65535u) return NVB_E_UNSUPPORTED;
     TempCarver tc(d_temp);
     const bool need_col = patterns->length > (uint32_t)FULL_W;          // a single stripe needs no boundary column
@@ -609,7 +608,7 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     if (n == 0) return NVB_OK;
     if (!d_score || !d_sink) return NVB_E_INVALID;
     GotohBatch b;
-    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = nullptr;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;     // a quality table routes to the int32 kernel
     b.d_n = d_n; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
     const GotohScheme S = make_scheme(scheme);
     const uint32_t grid = (n + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
@@ -672,18 +671,18 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     return NVB_OK;
 }
 
-int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+int nvb_gotoh_score(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
                     int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
 {
-    return gotoh_full_impl(type, scheme, patterns, texts, nullptr, n, d_score, d_sink, d_temp, temp_bytes, stream);
+    return gotoh_full_impl(type, scheme, patterns, d_quals, texts, nullptr, n, d_score, d_sink, d_temp, temp_bytes, stream);
 }
 
-int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts,
+int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts,
                              const uint32_t* d_n, uint32_t n_max,
                              int32_t* d_score, nvb_uint2* d_sink, void* d_temp, size_t* temp_bytes, void* stream)
 {
     if (!d_n) return NVB_E_INVALID;
-    return gotoh_full_impl(type, scheme, patterns, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
+    return gotoh_full_impl(type, scheme, patterns, d_quals, texts, d_n, n_max, d_score, d_sink, d_temp, temp_bytes, stream);
 }
 
 int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* scheme,
@@ -735,14 +734,13 @@ int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme
     }
 }
 
-int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const nvb_string_set* texts, uint32_t n,
+int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
                         int32_t* d_score, nvb_uint2* d_sink, nvb_uint2* d_source,
                         uint8_t* d_ops, uint32_t max_ops, uint32_t* d_n_ops,
                         void* d_temp, size_t* temp_bytes, void* stream)
 {
     if (!scheme || !temp_bytes || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
     if (type < 0 || type > 2) return NVB_E_INVALID;
-    if (scheme->d_qual_table) return NVB_E_UNSUPPORTED;
     if (texts->length > 65535u || patterns->length > 65535u) return NVB_E_UNSUPPORTED;
     const uint32_t max_m = patterns->length ? patterns->length : 1u, max_n = texts->length ? texts->length : 1u;
     const uint32_t dir_row_words = (max_m + 31u) / 32u * 4u;
@@ -754,7 +752,7 @@ int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_stri
     if (n == 0) return NVB_OK;
     if (!d_score || !d_sink || !d_source || !d_ops || !d_n_ops || max_ops == 0) return NVB_E_INVALID;
     GotohBatch b;
-    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = nullptr;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
     b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
     TracebackOut o;
     o.source = (uint2*)d_source; o.ops = d_ops; o.n_ops = d_n_ops; o.max_ops = max_ops; o.dirs = dirs; o.dir_rows = max_n;

@@ -548,7 +548,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, pscan_bytes, pw_want, pw_idx, (int)n_reads, as_stream(stream)));
         pscan_tmp = tc.take<char>(pscan_bytes);
         rtxts.length = PP->max_frag;
-        const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, &rtxts, (const uint32_t*)16, cap, (int32_t*)16, (nvb_uint2*)16,
+        const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, nullptr, &rtxts, (const uint32_t*)16, cap, (int32_t*)16, (nvb_uint2*)16,
                                                nullptr, &full_bytes, stream);
         if (r != NVB_E_TEMP_SIZE && r != NVB_OK) return r;
         full_tmp = tc.take<char>(full_bytes);
@@ -674,7 +674,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
             rpats.d_words = str_words; rpats.d_offsets = rp_off; rpats.d_lengths = rp_len;
             rtxts.d_words = d_genome;  rtxts.d_offsets = rt_off; rtxts.d_lengths = rt_len;
             size_t fb = full_bytes;
-            const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, &rtxts, pcounts, cap, rs_score, (nvb_uint2*)rs_sink, full_tmp, &fb, stream);
+            const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, nullptr, &rtxts, pcounts, cap, rs_score, (nvb_uint2*)rs_sink, full_tmp, &fb, stream);
             if (r != NVB_OK) return r;
         }
         pair_finalize_kernel<<<pgrid, 256, 0, s>>>(n_pairs, *PP, pw_want, pw_idx, pw_toff, rs_score, rs_sink, PO->d_pair_score, PO->d_pair_flags,

@@ -610,7 +610,7 @@ void orc_banded_traceback(int B, int type, const orc_scheme* S,
  * a stripe row by row, so ties resolve to the last maximal cell in (stripe, row, column) order; SEMI_GLOBAL reports
  * H[r][M] for every row; GLOBAL reports H[N][M].  Requires M >= 1, N >= 1.
  * ---------------------------------------------------------------------------------------------- */
-void orc_gotoh_full_one(int type, const orc_scheme* S, const u8* P, u32 M, const u8* T, u32 N,
+void orc_gotoh_full_one(int type, const orc_scheme* S, const i32* qtab, const u8* P, const u8* Q, u32 M, const u8* T, u32 N,
                         i32* out_score, u32* out_x, u32* out_y)
 {
     i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
@@ -630,7 +630,8 @@ void orc_gotoh_full_one(int type, const orc_scheme* S, const u8* P, u32 M, const
         {
             const i32 f = imax(F[(r - 1) * W + c] + Ge, H[(r - 1) * W + c] + Go);
             const i32 e = imax(E[r * W + c - 1] + Ge, H[r * W + c - 1] + Go);
-            const i32 d = H[(r - 1) * W + c - 1] + ((T[r - 1] == P[c - 1]) ? S->match : S->mismatch);
+            const i32 s_eq = qtab ? qtab[2 * (Q ? Q[c - 1] : 0)] : S->match, s_ne = qtab ? qtab[2 * (Q ? Q[c - 1] : 0) + 1] : S->mismatch;
+            const i32 d = H[(r - 1) * W + c - 1] + ((T[r - 1] == P[c - 1]) ? s_eq : s_ne);
             i32 h = imax(imax(e, f), d);
             if (type == 1) h = imax(h, 0);
             F[r * W + c] = f; E[r * W + c] = e; H[r * W + c] = h;
@@ -649,12 +650,12 @@ void orc_gotoh_full_one(int type, const orc_scheme* S, const u8* P, u32 M, const
     *out_score = best; *out_x = bx; *out_y = by;
 }
 
-void orc_gotoh_full(int type, const orc_scheme* S,
-                    const u8* pat, const u32* p_off, const u32* p_len,
+void orc_gotoh_full(int type, const orc_scheme* S, const i32* qtab,
+                    const u8* pat, const u8* qual, const u32* p_off, const u32* p_len,
                     const u8* txt, const u32* t_off, const u32* t_len, u32 n, i32* score, u32* sink_x, u32* sink_y)
 {
     for (u32 i = 0; i < n; ++i)
-        orc_gotoh_full_one(type, S, pat + p_off[i], p_len[i], txt + t_off[i], t_len[i], &score[i], &sink_x[i], &sink_y[i]);
+        orc_gotoh_full_one(type, S, qtab, pat + p_off[i], qual ? qual + p_off[i] : NULL, p_len[i], txt + t_off[i], t_len[i], &score[i], &sink_x[i], &sink_y[i]);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -306,7 +306,22 @@ class Ref(_Base):
         return o
 
     def banded_gotoh(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
-        assert qual is None and qtab is None and len(scheme) == 4, "ref shim instantiates SimpleGotohScheme only"
+        if qtab is not None:
+            # the reference templates with a table-driven scheme (TableGotohScheme in ref_shim.cpp); bands 7 / 15 / 31
+            if len(scheme) == 4:
+                scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+            s6 = np.array(scheme, dtype=np.int32)
+            pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+            qual = np.ascontiguousarray(qual, dtype=np.uint8); qtab = np.ascontiguousarray(qtab, dtype=np.int32)
+            p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+            t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+            n = len(p_off)
+            score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32); ok = np.zeros(n, np.uint8)
+            r = self.lib.ref_banded_gotoh_q(C.c_int(band), C.c_int(typ), _p(s6), _p(qtab), _p(pat), _p(qual), _p(p_off), _p(p_len),
+                                            _p(txt), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy), _p(ok))
+            assert r == 0
+            return score, sx, sy, ok
+        assert qual is None and len(scheme) == 4, "without a table the ref shim instantiates SimpleGotohScheme"
         pat = np.ascontiguousarray(pat, dtype=np.uint8)
         txt = np.ascontiguousarray(txt, dtype=np.uint8)
         p_off = np.ascontiguousarray(p_off, dtype=np.uint32)
@@ -363,18 +378,36 @@ def _full_args(pat, p_off, p_len, txt, t_off, t_len):
     return pat, p_off, p_len, txt, t_off, t_len, n, np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
 
 
-def _oracle_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len):
-    """full-matrix Gotoh: (score, sink_x = text end, sink_y = pattern end)"""
+def _oracle_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
+    """full-matrix Gotoh: (score, sink_x = text end, sink_y = pattern end); optional per-base qualities + 256x2 score table"""
     pat, p_off, p_len, txt, t_off, t_len, n, score, sx, sy = _full_args(pat, p_off, p_len, txt, t_off, t_len)
     if len(scheme) == 4:
         scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
     s = np.array(scheme, dtype=np.int32)
-    self.lib.orc_gotoh_full(C.c_int(typ), _p(s), _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n),
+    if qual is not None:
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    if qtab is not None:
+        qtab = np.ascontiguousarray(qtab, dtype=np.int32)
+    self.lib.orc_gotoh_full(C.c_int(typ), _p(s), _p(qtab), _p(pat), _p(qual), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n),
                             _p(score), _p(sx), _p(sy))
     return score, sx, sy
 
 
-def _ref_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len):
+def _ref_full_q(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual, qtab):
+    pat, p_off, p_len, txt, t_off, t_len, n, score, sx, sy = _full_args(pat, p_off, p_len, txt, t_off, t_len)
+    if len(scheme) == 4:
+        scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+    s = np.array(scheme, dtype=np.int32)
+    qual = np.ascontiguousarray(qual, dtype=np.uint8); qtab = np.ascontiguousarray(qtab, dtype=np.int32)
+    r = self.lib.ref_gotoh_full_q(C.c_int(typ), _p(s), _p(qtab), _p(pat), _p(qual), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len),
+                                  C.c_uint32(n), _p(score), _p(sx), _p(sy))
+    assert r == 0
+    return score, sx, sy
+
+
+def _ref_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
+    if qtab is not None:
+        return _ref_full_q(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual, qtab)
     pat, p_off, p_len, txt, t_off, t_len, n, score, sx, sy = _full_args(pat, p_off, p_len, txt, t_off, t_len)
     r = self.lib.ref_gotoh_full(C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]), C.c_int(scheme[2]), C.c_int(scheme[3]),
                                 _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))

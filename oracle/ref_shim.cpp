@@ -55,6 +55,65 @@ fm_index_t make_index(const uint32* bwt_occ, const uint32* ssa, const uint32* L2
 
 typedef vector_view<const uint8*> str_view;
 
+// a table-driven Gotoh scheme for the reference templates (a model of the GotohScoringScheme concept, nvbio/alignment/utils.h:
+// 111-135): substitution scores by the pattern base's quality, table[2*q] on a match and table[2*q+1] on a mismatch -- the shape of
+// nvBowtie's SmithWatermanScoringScheme<QualCost,...> (scoring.h:203-317) once its float expressions are evaluated on the host
+struct TableGotohScheme
+{
+    const int32* tab; int32 pgo, pge, tgo, tge;
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 match(const uint8 q = 0)      const { return tab[2*q]; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 mismatch(const uint8 q = 0)   const { return tab[2*q+1]; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 mismatch(const uint8 a, const uint8 b, const uint8 q = 0) const { return tab[2*q+1]; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 substitution(const uint32 r_i, const uint32 q_j, const uint8 r, const uint8 q, const uint8 qq = 0) const { return q == r ? tab[2*qq] : tab[2*qq+1]; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 pattern_gap_open()            const { return pgo; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 pattern_gap_extension()       const { return pge; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 text_gap_open()               const { return tgo; }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE int32 text_gap_extension()          const { return tge; }
+};
+
+template <uint32 BAND, aln::AlignmentType TYPE>
+void run_banded_q(const TableGotohScheme scheme,
+                const uint8* pat, const uint8* qual, const uint32* p_off, const uint32* p_len,
+                const uint8* txt, const uint32* t_off, const uint32* t_len,
+                uint32 n, int32* score, uint32* sink_x, uint32* sink_y, uint8* ok)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        aln::BestSink<int32> sink;
+        const bool r = aln::banded_alignment_score<BAND>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),
+            str_view( p_len[i], pat + p_off[i] ),
+            str_view( p_len[i], qual + p_off[i] ),
+            str_view( t_len[i], txt + t_off[i] ),
+            INT_MIN,
+            sink );
+        score[i]  = sink.score; sink_x[i] = sink.sink.x; sink_y[i] = sink.sink.y;
+        if (ok) ok[i] = r ? 1 : 0;
+    }
+}
+
+template <aln::AlignmentType TYPE>
+void run_full_q(const TableGotohScheme scheme,
+              const uint8* pat, const uint8* qual, const uint32* p_off, const uint32* p_len,
+              const uint8* txt, const uint32* t_off, const uint32* t_len,
+              uint32 n, int32* score, uint32* sink_x, uint32* sink_y)
+{
+    #pragma omp parallel for schedule(dynamic,16)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        aln::BestSink<int32> sink;
+        aln::alignment_score<4096u>(
+            aln::make_gotoh_aligner<TYPE>( scheme ),
+            str_view( p_len[i], pat + p_off[i] ),
+            str_view( p_len[i], qual + p_off[i] ),
+            str_view( t_len[i], txt + t_off[i] ),
+            INT_MIN,
+            sink );
+        score[i]  = sink.score; sink_x[i] = sink.sink.x; sink_y[i] = sink.sink.y;
+    }
+}
+
 template <uint32 BAND, aln::AlignmentType TYPE>
 void run_banded(const aln::SimpleGotohScheme scheme,
                 const uint8* pat, const uint32* p_off, const uint32* p_len,
@@ -386,6 +445,37 @@ void ref_locate(const uint32* bwt_occ, const uint32* ssa, const uint32* L2, uint
 
 // banded Gotoh score with SimpleGotohScheme(match, mismatch, gap_open, gap_ext).
 // type: 0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL (nvbio/alignment/alignment_base.h:54)
+// quality-table scheme (6 gap/none constants come as scheme6 = {unused, unused, pgo, pge, tgo, tge}) through the same templates
+int ref_banded_gotoh_q(int band, int type, const int32* scheme6, const int32* qtab,
+                       const uint8* pat, const uint8* qual, const uint32* p_off, const uint32* p_len,
+                       const uint8* txt, const uint32* t_off, const uint32* t_len,
+                       uint32 n, int32* score, uint32* sink_x, uint32* sink_y, uint8* ok)
+{
+    TableGotohScheme s; s.tab = qtab; s.pgo = scheme6[2]; s.pge = scheme6[3]; s.tgo = scheme6[4]; s.tge = scheme6[5];
+#define REF_BQ(B) switch (type) { \
+    case 0: run_banded_q<B,aln::GLOBAL>     ( s, pat,qual,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok ); return 0; \
+    case 1: run_banded_q<B,aln::LOCAL>      ( s, pat,qual,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok ); return 0; \
+    case 2: run_banded_q<B,aln::SEMI_GLOBAL>( s, pat,qual,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok ); return 0; } return -1;
+    switch (band) { case 7: REF_BQ(7) case 15: REF_BQ(15) case 31: REF_BQ(31) }
+#undef REF_BQ
+    return -1;
+}
+
+int ref_gotoh_full_q(int type, const int32* scheme6, const int32* qtab,
+                     const uint8* pat, const uint8* qual, const uint32* p_off, const uint32* p_len,
+                     const uint8* txt, const uint32* t_off, const uint32* t_len,
+                     uint32 n, int32* score, uint32* sink_x, uint32* sink_y)
+{
+    TableGotohScheme s; s.tab = qtab; s.pgo = scheme6[2]; s.pge = scheme6[3]; s.tgo = scheme6[4]; s.tge = scheme6[5];
+    switch (type)
+    {
+    case 0: run_full_q<aln::GLOBAL>     ( s, pat,qual,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y ); return 0;
+    case 1: run_full_q<aln::LOCAL>      ( s, pat,qual,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y ); return 0;
+    case 2: run_full_q<aln::SEMI_GLOBAL>( s, pat,qual,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y ); return 0;
+    }
+    return -1;
+}
+
 int ref_banded_gotoh_window(int band, int type, int match, int mismatch, int gap_open, int gap_ext,
                      const uint8* pat, const uint32* p_off, const uint32* p_len,
                      const uint8* txt, const uint32* t_off, const uint32* t_len,

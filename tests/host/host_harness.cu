@@ -183,6 +183,22 @@ int hh_gotoh_window(int band, int type, const int32_t* scheme6, const int32_t* q
     return -1;
 }
 
+int hh_gotoh_full_q(int type, const int32_t* scheme6, const int32_t* qtab, const uint8_t* quals,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,
+                  int32_t* score, uint32_t* sx, uint32_t* sy) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab; S.one = 1u; S.keymul = 32u;
+    for (uint32_t a = 0; a < n; ++a) {
+        std::vector<int2> col(tlen[a] + 1);
+        SinkResult r;
+        if (type == 0)      r = gotoh_full<0>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1, quals);
+        else if (type == 1) r = gotoh_full<1>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1, quals);
+        else                r = gotoh_full<2>(S, pw, pbits, pbe, poff[a], plen[a], tw, tbits, tbe, toff[a], tlen[a], col.data(), 1, quals);
+        score[a] = r.score; sx[a] = r.x; sy[a] = r.y;
+    }
+    return 0;
+}
+
 int hh_gotoh_full(int type, const int32_t* scheme6,
                   const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                   const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,

@@ -53,16 +53,16 @@ def test_argument_validation_of_the_widened_api():
     tt = StringSetStruct(); tt.d_words = 16; tt.bits = 2; tt.big_endian = 1; tt.stride = 512; tt.length = 500
     sch = GotohSchemeStruct(); sch.match, sch.mismatch, sch.pattern_gap_open, sch.pattern_gap_ext, sch.text_gap_open, sch.text_gap_ext = 2, -2, -5, -3, -5, -3
     # type out of range / NULL scheme
-    assert L.nvb_gotoh_score(C.c_int(3), C.byref(sch), C.byref(ss), C.byref(tt), C.c_uint32(4), None, None, None, C.byref(tb), None) == -1
-    assert L.nvb_gotoh_score(C.c_int(1), None, C.byref(ss), C.byref(tt), C.c_uint32(4), None, None, None, C.byref(tb), None) == -1
+    assert L.nvb_gotoh_score(C.c_int(3), C.byref(sch), C.byref(ss), None, C.byref(tt), C.c_uint32(4), None, None, None, C.byref(tb), None) == -1
+    assert L.nvb_gotoh_score(C.c_int(1), None, C.byref(ss), None, C.byref(tt), C.c_uint32(4), None, None, None, C.byref(tb), None) == -1
     # size query: 8 B x (n + 1) x max text length for patterns longer than one stripe (+ the todo list)
-    assert L.nvb_gotoh_score(C.c_int(1), C.byref(sch), C.byref(ss), C.byref(tt), C.c_uint32(1000), None, None, None, C.byref(tb), None) == -2
+    assert L.nvb_gotoh_score(C.c_int(1), C.byref(sch), C.byref(ss), None, C.byref(tt), C.c_uint32(1000), None, None, None, C.byref(tb), None) == -2
     assert tb.value >= 8 * 1001 * 500
     big = StringSetStruct(); big.d_words = 16; big.bits = 2; big.big_endian = 1; big.stride = 70000; big.length = 70000
-    assert L.nvb_gotoh_score(C.c_int(1), C.byref(sch), C.byref(ss), C.byref(big), C.c_uint32(4), None, None, None, C.byref(tb), None) == -4
-    assert L.nvb_gotoh_score_indirect(C.c_int(1), C.byref(sch), C.byref(ss), C.byref(tt), None, C.c_uint32(4), None, None, None, C.byref(tb), None) == -1
+    assert L.nvb_gotoh_score(C.c_int(1), C.byref(sch), C.byref(ss), None, C.byref(big), C.c_uint32(4), None, None, None, C.byref(tb), None) == -4
+    assert L.nvb_gotoh_score_indirect(C.c_int(1), C.byref(sch), C.byref(ss), None, C.byref(tt), None, C.c_uint32(4), None, None, None, C.byref(tb), None) == -1
     tb2 = C.c_size_t(0)
-    assert L.nvb_gotoh_traceback(C.c_int(1), C.byref(sch), C.byref(ss), C.byref(tt), C.c_uint32(10), None, None, None, None, C.c_uint32(700), None,
+    assert L.nvb_gotoh_traceback(C.c_int(1), C.byref(sch), C.byref(ss), None, C.byref(tt), C.c_uint32(10), None, None, None, None, C.c_uint32(700), None,
                                  None, C.byref(tb2), None) == -2
     assert tb2.value >= 10 * 500 * (5 * 16 + 8)          # direction matrix + boundary column
     # windowed: empty window, unknown band

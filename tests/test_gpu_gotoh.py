@@ -369,3 +369,26 @@ def test_full_matrix_warp_kernel_every_width(O, typ):
                 assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), (typ, max_m, scheme)
     finally:
         nb.lib().nvb_debug_full_warp(C.c_int(0))
+
+
+def test_full_matrix_quality_table(O):
+    """nvb_gotoh_score / nvb_gotoh_traceback with nvBowtie's quality-dependent scheme (QualityGotohScheme -> 256 x 2 table): scores and
+    sinks == the oracle (pinned against the reference templates with a table-driven scheme); the traceback's score / sink agree"""
+    from tests.test_host_core import full_problems, paired_full_problems
+    rng = np.random.default_rng(1400)
+    sch = aln.QualityGotohScheme(match_bonus=2, mm_min=2, mm_max=6, read_gap_const=5, read_gap_coeff=3, ref_gap_const=5, ref_gap_coeff=3)
+    tup = (2, int(sch.table_host[0, 1]), sch.pgo, sch.pge, sch.tgo, sch.tge)
+    for typ in (0, 1, 2):
+        for pr in (full_problems(rng, 400, max_m=160, max_n=400), paired_full_problems(rng, 200, max_m=160, max_n=300)):
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            qual = rng.integers(0, 60, len(pat)).astype(np.uint8)
+            want = O.gotoh_full(typ, tup, *pr, qual=qual, qtab=sch.table_host)
+            P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+            T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2, big_endian=True)
+            q = torch.from_numpy(qual).cuda()
+            al = aln.make_gotoh_aligner(typ, sch)
+            s, k = aln.batch_alignment_score(al, P, T, quals=q)
+            k = host_u32(k)
+            assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), typ
+            tb = aln.batch_alignment_traceback(al, P, T, max_ops=600, quals=q)
+            assert np.array_equal(tb["score"].cpu().numpy(), want[0]) and np.array_equal(host_u32(tb["sink"])[:, 0], want[1])

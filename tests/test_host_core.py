@@ -487,3 +487,25 @@ def test_gotoh_window(H, O, band):
                     assert not sh["alive"][~ok].any()
                 else:
                     assert 0.1 < sh["alive"].mean() < 0.98
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_full_quality_table(H, O, typ):
+    """full-matrix int32 routine with per-base qualities and a 256 x 2 score table == the oracle (pinned against the reference
+    templates with a table-driven scheme in tests/test_oracle.py)"""
+    from tests.test_oracle import _nvbowtie_like_table
+    rng = np.random.default_rng(880 + typ)
+    qtab = _nvbowtie_like_table()
+    scheme = (0, 0, -8, -3, -7, -2)
+    pr = full_problems(rng, 120)
+    pat, p_off, p_len, txt, t_off, t_len = pr
+    qual = rng.integers(0, 64, len(pat)).astype(np.uint8)
+    want = O.gotoh_full(typ, scheme, *pr, qual=qual, qtab=qtab)
+    pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 2, True)
+    n = len(p_off)
+    score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+    s6 = np.array(scheme, np.int32)
+    qt = np.ascontiguousarray(qtab.reshape(-1))
+    H.hh_gotoh_full_q(C.c_int(typ), _p(s6), _p(qt), _p(qual), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len),
+                      _p(tw), C.c_uint32(2), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+    assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2])

@@ -257,3 +257,39 @@ def test_windowed_banded_score_vs_reference(O, R):
                         assert np.array_equal(so[k][wd], sr[k][wd]), (band, typ, scheme, wb, k)
                     al = so["alive"].astype(bool) & wd
                     assert np.array_equal(so["ckpt"][al], sr["ckpt"][al]), (band, typ, scheme, wb)
+
+
+def _nvbowtie_like_table():
+    """256 x 2 table shaped like nvBowtie's local-mode scheme: match 2, mismatch -(2 + min(q,40)/40 * 4)"""
+    t = np.zeros((256, 2), np.int32)
+    for q in range(256):
+        t[q, 0] = 2
+        t[q, 1] = -(2 + int(min(q, 40) / 40.0 * 4))
+    return t
+
+
+def test_quality_table_scheme_vs_reference(O, R):
+    """the quality-dependent substitution path of the oracle (banded and full-matrix) == the reference's own DP templates
+    instantiated with a table-driven scheme (TableGotohScheme in oracle/ref_shim.cpp, a model of the GotohScoringScheme concept),
+    incl. text gap costs that differ from the pattern's"""
+    from tests.golden.make_golden import random_problems
+    from tests.test_host_core import full_problems
+    rng = np.random.default_rng(31)
+    qtab = _nvbowtie_like_table()
+    scheme = (0, 0, -8, -3, -7, -2)
+    for band in (7, 15, 31):
+        for typ in (0, 1, 2):
+            pr = random_problems(rng, 80, band, 120)
+            qual = rng.integers(0, 64, len(pr[0])).astype(np.uint8)
+            a = O.banded_gotoh(band, typ, scheme, *pr, qual=qual, qtab=qtab)
+            b = R.banded_gotoh(band, typ, scheme, *pr, qual=qual, qtab=qtab)
+            ok = b[3].astype(bool)
+            for u, v in zip(a[:3], b[:3]):
+                assert np.array_equal(u[ok], v[ok]), (band, typ)
+    for typ in (0, 1, 2):
+        pr = full_problems(rng, 120)
+        qual = rng.integers(0, 64, len(pr[0])).astype(np.uint8)
+        a = O.gotoh_full(typ, scheme, *pr, qual=qual, qtab=qtab)
+        b = R.gotoh_full(typ, scheme, *pr, qual=qual, qtab=qtab)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v), typ
