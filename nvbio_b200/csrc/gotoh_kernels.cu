@@ -138,7 +138,7 @@ gotoh_full_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict__ co
     if (a >= n) return;
     const SinkResult r = gotoh_full<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a),
                                           b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a),
-                                          col + a, (size_t)b.n_max);
+                                          col + a, (size_t)b.n_max, b.quals);
     b.score[a] = r.score;
     b.sink[a]  = make_uint2(r.x, r.y);
 }
