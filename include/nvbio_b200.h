@@ -282,6 +282,9 @@ typedef struct nvb_seed_extend_params {
     uint32_t dedup_jobs;      /* 1: hits of a read that define the same (strand, window) alignment are scored once and
                                  the result copied to each of them (bit-identical per-hit outputs, fewer cells)       */
     nvb_gotoh_scheme scheme;
+    const uint8_t* d_read_quals; /* optional base qualities, one byte per read symbol: the quality of symbol p of read r is
+                                    d_read_quals[offset of read r in symbols + p] (the indexing of nvb_banded_gotoh_score's
+                                    d_quals); used with scheme.d_qual_table (nvBowtie's scoring); NULL = none        */
 } nvb_seed_extend_params;
 
 /* reads: n_reads strings (2- or 4-bit).  genome: 2-bit big-endian packed text of fmi->length symbols.

@@ -39,7 +39,7 @@ class GotohSchemeStruct(C.Structure):      # nvb_gotoh_scheme
 class SeedExtendParamsStruct(C.Structure):  # nvb_seed_extend_params
     _fields_ = [("seed_len", C.c_uint32), ("seed_interval", C.c_uint32), ("band_len", C.c_uint32),
                 ("type", C.c_uint32), ("both_strands", C.c_uint32), ("max_seed_hits", C.c_uint32),
-                ("dedup_jobs", C.c_uint32), ("scheme", GotohSchemeStruct)]
+                ("dedup_jobs", C.c_uint32), ("scheme", GotohSchemeStruct), ("d_read_quals", C.c_void_p)]
 
 
 class BestAlignmentOutStruct(C.Structure):   # nvb_best_alignment_out

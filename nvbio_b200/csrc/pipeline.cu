@@ -56,6 +56,18 @@ pipe_make_strings_kernel(const StrSet reads, const PipeGeom g, uint32_t* __restr
     out_words[t] = word;
 }
 
+// base qualities of the [fw, rc] strings: byte p of string s at out[s * stride + p] (the rc string's are the read's, reversed)
+__global__ void __launch_bounds__(256)
+pipe_make_quals_kernel(const StrSet reads, const PipeGeom g, const uint8_t* __restrict__ quals, uint8_t* __restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (uint64_t)g.n_strings * g.stride) return;
+    const uint32_t s = (uint32_t)(t / g.stride), p = (uint32_t)(t % g.stride);
+    const uint32_t read = s / g.strands, strand = s % g.strands;
+    const uint32_t off = str_off(reads, read), len = str_len(reads, read);
+    out[t] = (p < len) ? quals[off + (strand == 0 ? p : len - 1u - p)] : (uint8_t)0;
+}
+
 // 2-bit fast path of the above: whole words at a time.  16 consecutive symbols starting at any symbol offset are a
 // funnel shift of two words; the reverse complement of a word is ~brev(word) with the two bits of every symbol
 // swapped back.
@@ -492,6 +504,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     TempCarver tc(d_temp);
     uint32_t* str_words  = tc.take<uint32_t>((size_t)g.n_strings * (g.stride / spw) + 4);
     uint32_t* str_len_   = tc.take<uint32_t>(g.n_strings);
+    uint8_t*  str_quals  = P->d_read_quals ? tc.take<uint8_t>((size_t)g.n_strings * g.stride + 16) : nullptr;
     uint2*    ranges     = tc.take<uint2>(nq);
     uint32_t* sizes      = tc.take<uint32_t>(nq);
     uint32_t* excl       = tc.take<uint32_t>(nq);
@@ -574,6 +587,11 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         else if (g.bits == 2)             pipe_make_strings_kernel<2><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
         else                              pipe_make_strings_kernel<4><<<grid, 256, 0, s>>>(rd, g, str_words, str_len_);
         NVB_LAUNCH_CHECK();
+        if (str_quals) {
+            const uint64_t total = (uint64_t)g.n_strings * g.stride;
+            pipe_make_quals_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(rd, g, P->d_read_quals, str_quals);
+            NVB_LAUNCH_CHECK();
+        }
     }
     NVB_STAGE(1);
     // 2. seed ranges
@@ -618,7 +636,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         if (dedup) {
             pats.d_words = str_words; pats.d_offsets = jp_off; pats.d_lengths = jp_len;
             txts.d_words = d_genome;  txts.d_offsets = jt_off; txts.d_lengths = jt_len;
-            r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts + 2, hit_capacity,
+            r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, str_quals, &txts, counts + 2, hit_capacity,
                                                 job_score, (nvb_uint2*)job_sink, gotoh_tmp, &gb, stream);
             if (r != NVB_OK) return r;
             pipe_scatter_scores_kernel<<<hgrid, 256, 0, s>>>(g, counts, leader, job_idx, job_score, job_sink, hit_string, h_score, h_sink, best_key);
@@ -626,7 +644,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         } else {
             pats.d_words = str_words; pats.d_offsets = p_off; pats.d_lengths = p_len;
             txts.d_words = d_genome;  txts.d_offsets = t_off; txts.d_lengths = t_len;
-            r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, counts, hit_capacity,
+            r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, str_quals, &txts, counts, hit_capacity,
                                                 h_score, (nvb_uint2*)h_sink, gotoh_tmp, &gb, stream);
             if (r != NVB_OK) return r;
         }
@@ -650,7 +668,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         pats.d_words = str_words; pats.d_offsets = bp_off; pats.d_lengths = bp_len;
         txts.d_words = d_genome;  txts.d_offsets = bt_off; txts.d_lengths = bt_len;
         size_t tbb = tb_bytes;
-        const int r = nvb_banded_gotoh_traceback(P->band_len, P->type, &P->scheme, &pats, nullptr, &txts, n_reads,
+        const int r = nvb_banded_gotoh_traceback(P->band_len, P->type, &P->scheme, &pats, str_quals, &txts, n_reads,
                                                  b_score, (nvb_uint2*)b_sink, (nvb_uint2*)b_source, BA->d_ops, BA->max_ops, BA->d_n_ops,
                                                  tb_tmp, &tbb, stream);
         if (r != NVB_OK) return r;
@@ -674,7 +692,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
             rpats.d_words = str_words; rpats.d_offsets = rp_off; rpats.d_lengths = rp_len;
             rtxts.d_words = d_genome;  rtxts.d_offsets = rt_off; rtxts.d_lengths = rt_len;
             size_t fb = full_bytes;
-            const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, nullptr, &rtxts, pcounts, cap, rs_score, (nvb_uint2*)rs_sink, full_tmp, &fb, stream);
+            const int r = nvb_gotoh_score_indirect(P->type, &P->scheme, &rpats, str_quals, &rtxts, pcounts, cap, rs_score, (nvb_uint2*)rs_sink, full_tmp, &fb, stream);
             if (r != NVB_OK) return r;
         }
         pair_finalize_kernel<<<pgrid, 256, 0, s>>>(n_pairs, *PP, pw_want, pw_idx, pw_toff, rs_score, rs_sink, PO->d_pair_score, PO->d_pair_flags,

@@ -19,6 +19,7 @@ class SeedExtendParams:
     max_seed_hits: int = 100         # nvBowtie max_hits
     dedup_jobs: bool = True          # score identical (strand, window) jobs of a read once
     scheme: object = field(default_factory=lambda: aln.SimpleGotohScheme(2, -2, -5, -3))
+    read_quals: Optional[torch.Tensor] = None   # uint8 base qualities indexed like the read symbols (with a QualityGotohScheme)
 
     def struct(self) -> SeedExtendParamsStruct:
         p = SeedExtendParamsStruct()
@@ -27,6 +28,7 @@ class SeedExtendParams:
         p.max_seed_hits = self.max_seed_hits
         p.dedup_jobs = 1 if self.dedup_jobs else 0
         p.scheme = self.scheme.struct()
+        p.d_read_quals = self.read_quals.data_ptr() if self.read_quals is not None else None
         return p
 
 

@@ -3,17 +3,29 @@ nvbio_b200/csrc/pipeline.cu, each stage computed by the CPU oracle / reference l
 import numpy as np
 
 
-def seed_extend_oracle(O, idx, genome_sym, reads, params):
-    """reads: list of uint8 arrays.  Returns dict(best_score, best_pos, hit_string, hit_window, hit_score, hit_sink, n_hits)."""
+def _scheme_args(sch):
+    """(scheme tuple, qtab or None) of a SimpleGotohScheme / QualityGotohScheme"""
+    if hasattr(sch, "table_host"):
+        return (sch.match_bonus, int(sch.table_host[0, 1]), sch.pgo, sch.pge, sch.tgo, sch.tge), sch.table_host
+    return (sch.match, sch.mismatch, sch.gap_open, sch.gap_ext), None
+
+
+def seed_extend_oracle(O, idx, genome_sym, reads, params, quals=None):
+    """reads: list of uint8 arrays; quals: optional list of uint8 arrays (base qualities, with a QualityGotohScheme).
+    Returns dict(best_score, best_pos, hit_string, hit_window, hit_score, hit_sink, n_hits)."""
     L, I, B = params.seed_len, params.seed_interval, params.band_len
     n = idx.n
     strands = 2 if params.both_strands else 1
-    strings = []
-    for r in reads:
+    strings, squals = [], []
+    for i, r in enumerate(reads):
         strings.append(r)
+        if quals is not None:
+            squals.append(quals[i])
         if strands == 2:
             rc = np.where(r < 4, 3 - r, r)[::-1].astype(np.uint8)
             strings.append(rc)
+            if quals is not None:
+                squals.append(quals[i][::-1])
     max_len = max(len(r) for r in reads)
     K = (max_len - L) // I + 1
     # seeds
@@ -37,7 +49,7 @@ def seed_extend_oracle(O, idx, genome_sym, reads, params):
             hit_string.append(qi // K); seed_k.append(qi % K); rows.append(int(x) + j)
     rows = np.array(rows, np.uint32)
     pos = O.locate(idx, rows) if len(rows) else np.zeros(0, np.uint32)
-    p_sym, p_off, p_len, t_off, t_len, wins = [], [], [], [], [], []
+    p_sym, p_q, p_off, p_len, t_off, t_len, wins = [], [], [], [], [], [], []
     po = 0
     for s, k, p in zip(hit_string, seed_k, pos):
         ln_s = len(strings[s])
@@ -46,12 +58,14 @@ def seed_extend_oracle(O, idx, genome_sym, reads, params):
         gb = diag - B // 2 if diag > B // 2 else 0
         ge = min(gb + ln_s + B, n)
         p_sym.append(strings[s]); p_off.append(po); p_len.append(ln_s); po += ln_s
+        if quals is not None:
+            p_q.append(squals[s])
         t_off.append(gb); t_len.append(ge - gb); wins.append((gb, ge))
-    sch = params.scheme
-    scheme = (sch.match, sch.mismatch, sch.gap_open, sch.gap_ext)
+    scheme, qtab = _scheme_args(params.scheme)
     if hit_string:
         score, sx, sy, _ = O.banded_gotoh(B, params.type, scheme, np.concatenate(p_sym), np.array(p_off, np.uint32), np.array(p_len, np.uint32),
-                                          genome_sym, np.array(t_off, np.uint32), np.array(t_len, np.uint32))
+                                          genome_sym, np.array(t_off, np.uint32), np.array(t_len, np.uint32),
+                                          qual=np.concatenate(p_q) if quals is not None else None, qtab=qtab)
     else:
         score = np.zeros(0, np.int32); sx = sy = np.zeros(0, np.uint32)
     best_score = np.full(len(reads), -2**31, np.int64)
@@ -66,12 +80,12 @@ def seed_extend_oracle(O, idx, genome_sym, reads, params):
                 n_hits=len(hit_string))
 
 
-def seed_extend_paired_oracle(O, idx, genome_sym, reads, params, pair, n_pairs):
+def seed_extend_paired_oracle(O, idx, genome_sym, reads, params, pair, n_pairs, quals=None):
     """Oracle composition of nvb_seed_extend_paired: the single-end composition above for the 2*n_pairs mates, the pairing rules of
     include/nvbio_b200.h restated in Python, and the opposite-mate rescue scored by the oracle's full-matrix Gotoh.
     reads: mate 1 of every pair, then mate 2.  Returns dict(pair_score, pair_flags, mate_score[2,n], mate_pos[2,n], mate_strand[2,n],
     n_rescue)."""
-    se = seed_extend_oracle(O, idx, genome_sym, reads, params)
+    se = seed_extend_oracle(O, idx, genome_sym, reads, params, quals=quals)
     glen = idx.n
     strands = 2
     # best hit of every read: max score, ties -> smallest hit index
@@ -112,14 +126,17 @@ def seed_extend_paired_oracle(O, idx, genome_sym, reads, params, pair, n_pairs):
             if not (m[a]["has"] and m[a]["score"] >= pair.min_mate_score):
                 continue
             o = reads[(1 - a) * n_pairs + p]
+            oq = quals[(1 - a) * n_pairs + p] if quals is not None else None
             if m[a]["strand"] == 0:
                 to = m[a]["beg"]; te = min(to + pair.max_frag, glen)
                 pat = np.where(o < 4, 3 - o, o)[::-1].astype(np.uint8)
+                pq = oq[::-1] if oq is not None else None
             else:
                 to = max(m[a]["end"] - pair.max_frag, 0); te = m[a]["end"]
                 pat = o
+                pq = oq
             if te - to >= 1 and len(pat) >= 1:
-                jobs.append((p, a, pat, to, te - to))
+                jobs.append((p, a, pat, to, te - to, pq))
     wanted = len(jobs)
     run = jobs[:cap]
     if run:
@@ -127,10 +144,11 @@ def seed_extend_paired_oracle(O, idx, genome_sym, reads, params, pair, n_pairs):
         p_len = np.array([len(j[2]) for j in run], np.uint32)
         p_off = (np.cumsum(p_len) - p_len).astype(np.uint32)
         t_off = np.array([j[3] for j in run], np.uint32); t_len = np.array([j[4] for j in run], np.uint32)
-        sch = params.scheme
-        rs, rx, _ = O.gotoh_full(params.type, (sch.match, sch.mismatch, sch.gap_open, sch.gap_ext), pats, p_off, p_len, genome_sym, t_off, t_len)
+        scheme, qtab = _scheme_args(params.scheme)
+        rs, rx, _ = O.gotoh_full(params.type, scheme, pats, p_off, p_len, genome_sym, t_off, t_len,
+                                 qual=np.concatenate([j[5] for j in run]) if quals is not None else None, qtab=qtab)
         cand = {}
-        for (p, a, _, to, _), s, x in zip(run, rs, rx):
+        for (p, a, _, to, _, _), s, x in zip(run, rs, rx):
             if int(s) < pair.min_mate_score:
                 continue
             tot = int(mate_score[a, p]) + int(s)

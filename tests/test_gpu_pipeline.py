@@ -222,3 +222,49 @@ def test_paired_end_vs_oracle():
         fl = want["pair_flags"]
         if pair.rescue_capacity is None and pair.min_frag == 0:
             assert (fl == 1).sum() > 0.5 * n_pairs and ((fl == 2) | (fl == 4)).sum() > 0.1 * n_pairs and (fl == 0).sum() >= 10
+
+
+def test_seed_extend_with_base_qualities():
+    """nvBowtie's quality-dependent scoring through the composition: per-read qualities (reversed for the rc strings) reach the
+    banded extension and the opposite-mate DP; single-end and paired outputs == the oracle composition"""
+    from tests.pipeline_oracle import seed_extend_paired_oracle
+    require_gpu()
+    O = orc.Oracle()
+    n = 200_000
+    gw = synth.random_genome_words(n, seed=79)
+    gsym = unpack_symbols(host_u32(gw), n)
+    idx = O.build_index(gsym)
+    fmi = nb.FMIndexDevice.from_host(idx.bwt_occ, idx.ssa, idx.L2, idx.n, idx.primary)
+    n_pairs, L = 300, 100
+    rw, left, frag = synth.sample_pairs(gw, n, n_pairs, L, frag_mean=300, frag_sd=40, sub_rate=0.03, hard_frac=0.3, hard_sub_rate=0.2, seed=21, mut_seed=22)
+    wpr = rw.shape[1]
+    n_reads = 2 * n_pairs
+    reads_sym = [unpack_symbols(host_u32(rw[i]), L) for i in range(n_reads)]
+    rng = np.random.default_rng(8)
+    qual = rng.integers(0, 50, (n_reads, wpr * 16)).astype(np.uint8)          # laid out like the read stream (stride wpr*16 symbols)
+    quals = [qual[i, :L] for i in range(n_reads)]
+    rs = PackedStringSet.fixed(rw.reshape(-1), n_reads, L, stride=wpr * 16)
+    sch = aln.QualityGotohScheme(match_bonus=2, mm_min=2, mm_max=6, read_gap_const=5, read_gap_coeff=3, ref_gap_const=5, ref_gap_coeff=3)
+    params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=True, max_seed_hits=50, scheme=sch,
+                                 read_quals=torch.from_numpy(qual.reshape(-1)).cuda())
+    ws = nb.seed_extend(fmi, gw, rs, params, hit_capacity=64 * n_reads, keep_hits=True)
+    torch.cuda.synchronize()
+    want = seed_extend_oracle(O, idx, gsym, reads_sym, params, quals=quals)
+    kept = int(ws.n_hits[0])
+    assert kept == want["n_hits"]
+    assert np.array_equal(ws.hit_score.cpu().numpy()[:kept].astype(np.int64), want["hit_score"])
+    assert np.array_equal(host_u32(ws.hit_sink)[:kept].astype(np.int64), want["hit_sink"])
+    assert np.array_equal(ws.best_score.cpu().numpy().astype(np.int64), want["best_score"])
+    # the qualities matter: the same batch without them scores differently somewhere
+    plain = nb.seed_extend(fmi, gw, rs, nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=True,
+                                                           max_seed_hits=50, scheme=sch), hit_capacity=64 * n_reads, keep_hits=True)
+    assert not torch.equal(plain.hit_score[:kept], ws.hit_score[:kept])
+    pair = nb.PairParams(min_frag=0, max_frag=420, min_mate_score=40)
+    wp = nb.seed_extend_paired(fmi, gw, rs, params, pair, hit_capacity=64 * n_reads)
+    torch.cuda.synchronize()
+    wantp = seed_extend_paired_oracle(O, idx, gsym, reads_sym, params, pair, n_pairs, quals=quals)
+    assert tuple(int(v) for v in wp.n_rescue.cpu()) == wantp["n_rescue"] and wantp["n_rescue"][0] > 10
+    assert np.array_equal(wp.pair_flags.cpu().numpy().astype(np.int64), wantp["pair_flags"])
+    assert np.array_equal(wp.pair_score.cpu().numpy().astype(np.int64), wantp["pair_score"])
+    assert np.array_equal(wp.mate_score.cpu().numpy().astype(np.int64), wantp["mate_score"])
+    assert np.array_equal(host_u32(wp.mate_pos).astype(np.int64), wantp["mate_pos"])
