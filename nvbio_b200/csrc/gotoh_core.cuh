@@ -54,6 +54,44 @@ struct SymReaderRT {
     }
 };
 
+// Sequential reader for the per-row pattern symbols of the packed kernels: each word is normalised to big-endian symbol order
+// when it is loaded, so a symbol costs one shift to extract and one to advance (SymReaderRT::get recomputes word index and
+// shift amount per call).
+struct PatStream {
+    const uint32_t* wp; uint32_t w, left, bits, be, spw;
+    __host__ __device__ __forceinline__ static uint32_t bitrev32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+        return __brev(x);
+#else
+        x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1); x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+        x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4); x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+        return (x >> 16) | (x << 16);
+#endif
+    }
+    __host__ __device__ __forceinline__ uint32_t normalise(uint32_t x) const {
+        if (bits == 8) return ((x >> 24) & 0xFFu) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24);    // bytes are little-endian
+        if (be) return x;
+        uint32_t y = bitrev32(x);                                        // symbol order reversed, and the bits inside each symbol
+        if (bits == 2) return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+        return ((y & 0x11111111u) << 3) | ((y & 0x22222222u) << 1) | ((y >> 1) & 0x22222222u) | ((y >> 3) & 0x11111111u);
+    }
+    __host__ __device__ __forceinline__ PatStream(const uint32_t* words, uint32_t b, uint32_t e, uint32_t off)
+        : bits(b), be(e), spw(32u / b) {
+        const uint32_t lg = (b == 2 ? 4u : (b == 4 ? 3u : 2u));
+        const uint32_t r = off & (spw - 1u);
+        wp = words + (off >> lg);
+        w = normalise(*wp++) << (bits * r);        // r < spw, so the shift is < 32
+        left = spw - r;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+        if (left == 0u) { w = normalise(*wp++); left = spw; }
+        const uint32_t s = w >> (32u - bits);
+        w <<= bits;
+        --left;
+        return s;
+    }
+};
+
 struct SinkResult { int32_t score; uint32_t x, y; };
 
 // ---------------------------------------------------------------------------------------------
@@ -394,8 +432,8 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
     // per-row substitution profile of both alignments; with a quality table the two scores of a row come from
     // table[2*qual], table[2*qual+1] (nvBowtie's SmithWatermanScoringScheme::substitution)
 #define NVB_ROW_PROFILES(i)                                                                                   \
-    const uint32_t q0 = ((i) < M0) ? pr0.get(poff0 + (i)) : 255u;                                             \
-    const uint32_t q1 = ((i) < M1) ? pr1.get(poff1 + (i)) : 255u;                                             \
+    const uint32_t q0 = ((i) < M0) ? pr0.next() : 255u;                                                       \
+    const uint32_t q1 = ((i) < M1) ? pr1.next() : 255u;                                                       \
     int32_t e0 = c_eq, n0 = c_ne, e1 = c_eq, n1 = c_ne;                                                        \
     if (S.qtab) {                                                                                             \
         const uint32_t qq0 = (quals && (i) < M0) ? quals[poff0 + (i)] : 0u;                                   \
@@ -418,7 +456,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         for (int j = 0; j < B - 1; ++j) F[j] = INF2;
     }
 
-    SymReaderRT pr0(pwords, pbits, pbe), pr1(pwords, pbits, pbe);
+    PatStream pr0(pwords, pbits, pbe, poff0), pr1(pwords, pbits, pbe, poff1);
     const uint32_t Mmax = M0 > M1 ? M0 : M1;
     int32_t best0 = -1, best1 = -1; uint32_t bi0 = 0, bj0 = 0, bi1 = 0, bj1 = 0;
 
