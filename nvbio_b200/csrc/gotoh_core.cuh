@@ -419,7 +419,8 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         uint32_t N0, uint32_t N1,
         const uint16_t* sel, uint32_t sel_stride,
         SinkResult& r0, SinkResult& r1,
-        const uint8_t* __restrict__ quals = nullptr)
+        const uint8_t* __restrict__ quals = nullptr,
+        const uint32_t* prof_tab = nullptr)     // optional 256-entry table of sub_profile(q, c_eq, c_ne) (shared memory on the device)
 {
     const int32_t Go = S.pgo, Ge = S.pge;
     const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
@@ -441,8 +442,8 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         e0 = S.qtab[2 * qq0] - Go; n0 = S.qtab[2 * qq0 + 1] - Go;                                             \
         e1 = S.qtab[2 * qq1] - Go; n1 = S.qtab[2 * qq1 + 1] - Go;                                             \
     }                                                                                                         \
-    const uint32_t P0 = sub_profile(q0, e0, n0);                                                              \
-    const uint32_t P1 = sub_profile(q1, e1, n1);
+    const uint32_t P0 = (prof_tab && !S.qtab) ? prof_tab[q0] : sub_profile(q0, e0, n0);                       \
+    const uint32_t P1 = (prof_tab && !S.qtab) ? prof_tab[q1] : sub_profile(q1, e1, n1);
 
     uint32_t G[B], F[B - 1];
     {
@@ -458,7 +459,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
 
     PatStream pr0(pwords, pbits, pbe, poff0), pr1(pwords, pbits, pbe, poff1);
     const uint32_t Mmax = M0 > M1 ? M0 : M1;
-    int32_t best0 = -1, best1 = -1; uint32_t bi0 = 0, bj0 = 0, bi1 = 0, bj1 = 0;
+    int32_t bk0 = -1, bk1 = -1; uint32_t bi0 = 0, bi1 = 0;       // LOCAL: best row key (H << 5 | j) and its row, per half
 
     if (TYPE == NVB_LOCAL) {
         // LOCAL formulation, biased by beta = -Go so that the one plain add per cell (h + Go) is carry-free and can be
@@ -495,9 +496,10 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
                 rowkey = NVB_VIMAX_U(rowkey, key);
                 E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
             }
+            // later rows win ties: replace when H_row >= H_best, i.e. key_row >= (key_best with its column bits cleared)
             const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
-            if (i < M0 && (k0 >> 5) >= best0) { best0 = k0 >> 5; bi0 = i; bj0 = (uint32_t)k0 & 31u; }
-            if (i < M1 && (k1 >> 5) >= best1) { best1 = k1 >> 5; bi1 = i; bj1 = (uint32_t)k1 & 31u; }
+            if (i < M0 && k0 >= (bk0 & ~31)) { bk0 = k0; bi0 = i; }
+            if (i < M1 && k1 >= (bk1 & ~31)) { bk1 = k1; bi1 = i; }
         }
     } else {
         for (uint32_t i = 0; i < Mmax; ++i) {
@@ -525,8 +527,8 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
 
 #undef NVB_ROW_PROFILES
     if (TYPE == NVB_LOCAL) {
-        r0.score = best0; r0.x = bi0 + bj0 + 1u; r0.y = bi0 + 1u;
-        r1.score = best1; r1.x = bi1 + bj1 + 1u; r1.y = bi1 + 1u;
+        r0.score = bk0 >> 5; r0.x = bi0 + ((uint32_t)bk0 & 31u) + 1u; r0.y = bi0 + 1u;
+        r1.score = bk1 >> 5; r1.x = bi1 + ((uint32_t)bk1 & 31u) + 1u; r1.y = bi1 + 1u;
     } else if (TYPE == NVB_GLOBAL) {
         r0.score = half_lo(G[B - 1]) - Go; r0.x = M0 + (uint32_t)B - 1u; r0.y = M0;
         r1.score = half_hi(G[B - 1]) - Go; r1.x = M1 + (uint32_t)B - 1u; r1.y = M1;

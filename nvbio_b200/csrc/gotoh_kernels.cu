@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(PAIR_BLOCKDIM)
 gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
 {
     extern __shared__ uint16_t sel_smem[];            // [sel_rows][PAIR_BLOCKDIM]
+    // substitution profile of every possible pattern symbol (constant schemes): one LDS per row instead of building it
+    __shared__ uint32_t prof_tab[256];
+    for (uint32_t q = threadIdx.x; q < 256u; q += PAIR_BLOCKDIM) prof_tab[q] = sub_profile(q, S.match - S.pgo, S.mismatch - S.pgo);
+    __syncthreads();
     const uint32_t n = batch_count(b);
     const uint32_t n_pairs = (n + 1u) / 2u;
     uint16_t* my_sel = sel_smem + threadIdx.x;
@@ -121,7 +125,7 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
         SinkResult r0, r1;
         gotoh_pair<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
                             str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
-                            my_sel, PAIR_BLOCKDIM, r0, r1, b.quals);
+                            my_sel, PAIR_BLOCKDIM, r0, r1, b.quals, prof_tab);
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
         if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
     }
