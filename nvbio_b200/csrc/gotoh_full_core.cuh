@@ -21,8 +21,8 @@ constexpr int FULL_W = 32;     // pattern columns per stripe
 // DIRS: also emit the 4-bit direction vector of every cell (H source | E extended | F extended; the bits
 // GotohSubmatrixContext::new_cell stores, gotoh_inl.h:426-446) to dirs[row * dir_row_words + stripe * 4 ..]: one uint4 per
 // (text row, 32-column stripe), nibble k of word w = pattern column 32*stripe + 8*w + k.
-template <int TYPE, bool DIRS>
-__host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
+template <int TYPE, bool DIRS, bool QUAL>
+__host__ __device__ inline SinkResult gotoh_full_impl2(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
         int2* __restrict__ col, size_t col_stride, uint32_t* __restrict__ dirs = nullptr, uint32_t dir_row_words = 0,
@@ -43,7 +43,7 @@ __host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
             for (int j = 0; j < FULL_W; ++j) q[j] = (b + j < M) ? pr.get(poff + b + j) : 256u;     // 256 never equals a text symbol
 #pragma unroll
             for (int w = 0; w < FULL_W / 4; ++w) qq4[w] = 0u;
-            if (S.qtab && quals) {
+            if (QUAL && quals) {
 #pragma unroll
                 for (int j = 0; j < FULL_W; ++j) if (b + j < M) qq4[j >> 2] |= (uint32_t)quals[poff + b + j] << (8 * (j & 3));
             }
@@ -74,7 +74,7 @@ __host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
                 const int32_t eleft = E + Ge, hleft = H[j - 1] + Go;      // H[j-1] is already this row
                 E    = imax2(eleft, hleft);
                 int32_t sub = (g == q[j - 1]) ? S.match : S.mismatch;
-                if (S.qtab) sub = S.qtab[2u * ((qq4[(j - 1) >> 2] >> (8 * ((j - 1) & 3))) & 255u) + ((g == q[j - 1]) ? 0u : 1u)];
+                if (QUAL) sub = S.qtab[2u * ((qq4[(j - 1) >> 2] >> (8 * ((j - 1) & 3))) & 255u) + ((g == q[j - 1]) ? 0u : 1u)];
                 const int32_t diagonal = Hd + sub;
                 int32_t h = imax2(imax2(E, F[j]), diagonal);
                 if (TYPE == NVB_LOCAL) h = imax2(h, 0);
@@ -117,6 +117,18 @@ __host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
         }
     }
     return res;
+}
+
+// quality tables (a table look-up per cell) are compiled as a separate instantiation so that constant schemes do not pay for them
+template <int TYPE, bool DIRS>
+__host__ __device__ inline SinkResult gotoh_full_impl(const GotohScheme& S,
+        const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
+        const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
+        int2* __restrict__ col, size_t col_stride, uint32_t* __restrict__ dirs = nullptr, uint32_t dir_row_words = 0,
+        const uint8_t* __restrict__ quals = nullptr)
+{
+    if (S.qtab) return gotoh_full_impl2<TYPE, DIRS, true>(S, pwords, pbits, pbe, poff, M, twords, tbits, tbe, toff, N, col, col_stride, dirs, dir_row_words, quals);
+    return gotoh_full_impl2<TYPE, DIRS, false>(S, pwords, pbits, pbe, poff, M, twords, tbits, tbe, toff, N, col, col_stride, dirs, dir_row_words, quals);
 }
 
 template <int TYPE>
@@ -211,7 +223,7 @@ struct FullPairTrack { int32_t k0, k1; uint32_t r0, r1; int32_t s0, s1; uint32_t
 template <int TYPE, bool PARTIAL>
 __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, const bool first, const bool last, const uint32_t b,
         const uint32_t ncols, const uint32_t N, SymSeq t0, SymSeq t1, const uint16_t* sel, const uint32_t sel_stride,
-        uint2* __restrict__ col, const size_t col_stride, FullPairTrack& trk, uint32_t& g_last)
+        uint2* __restrict__ col, const size_t col_stride, FullPairTrack& trk, uint32_t& g_last, const uint32_t* prof_tab)
 {
     const int32_t Go = S.pgo, Ge = S.pge;
     const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
@@ -239,8 +251,9 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
     uint2 nxt = make_uint2(0u, 0u);
     if (!first) nxt = col[0];
     for (uint32_t r = 0; r < N; ++r) {
-        const uint32_t P0 = sub_profile(t0.next(), c_eq, c_ne);
-        const uint32_t P1 = sub_profile(t1.next(), c_eq, c_ne);
+        const uint32_t g0 = t0.next(), g1 = t1.next();
+        const uint32_t P0 = prof_tab ? prof_tab[g0] : sub_profile(g0, c_eq, c_ne);
+        const uint32_t P1 = prof_tab ? prof_tab[g1] : sub_profile(g1, c_eq, c_ne);
         uint32_t Vl, E;
         if (first) { Vl = left_h; E = left_e; left_h = NVB_VIADD(left_h, left_step); }
         else       { Vl = nxt.x; E = nxt.y; if (r + 1u < N) nxt = col[(size_t)(r + 1u) * col_stride]; }
@@ -269,8 +282,8 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
         if (!last) col[(size_t)r * col_stride] = make_uint2(V[FULL_W], E);
         if (TYPE == NVB_LOCAL) {
             const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
-            if ((k0 >> 3) >= (trk.k0 >> 3)) { trk.k0 = k0; trk.r0 = r; }
-            if ((k1 >> 3) >= (trk.k1 >> 3)) { trk.k1 = k1; trk.r1 = r; }
+            if (k0 >= (trk.k0 & ~7)) { trk.k0 = k0; trk.r0 = r; }       // (H, sub-stripe) >= the best's: later rows win ties
+            if (k1 >= (trk.k1 & ~7)) { trk.k1 = k1; trk.r1 = r; }
         }
         if (TYPE == NVB_SEMI_GLOBAL && last) {
             if (!PARTIAL) vM = V[FULL_W];
@@ -293,7 +306,8 @@ template <int TYPE>
 __host__ __device__ inline bool gotoh_full_pair(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff0, uint32_t poff1, uint32_t M,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff0, uint32_t toff1, uint32_t N,
-        uint2* __restrict__ col, size_t col_stride, uint16_t* sel, uint32_t sel_stride, SinkResult& r0, SinkResult& r1)
+        uint2* __restrict__ col, size_t col_stride, uint16_t* sel, uint32_t sel_stride, SinkResult& r0, SinkResult& r1,
+        const uint32_t* prof_tab = nullptr)      // optional 256-entry table of sub_profile(g, c_eq, c_ne) (shared memory on the device)
 {
     const int32_t Go = S.pgo;
     r0.score = INT_MIN; r0.x = r0.y = 0xFFFFFFFFu; r1 = r0;
@@ -316,8 +330,8 @@ __host__ __device__ inline bool gotoh_full_pair(const GotohScheme& S,
         trk.k0 = trk.k1 = -1; trk.r0 = trk.r1 = 0u;
         uint32_t g_last = 0u;
         const SymSeq t0(twords, tbits, tbe, toff0), t1(twords, tbits, tbe, toff1);
-        if (ncols == (uint32_t)FULL_W) full_pair_stripe<TYPE, false>(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last);
-        else                           full_pair_stripe<TYPE, true >(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last);
+        if (ncols == (uint32_t)FULL_W) full_pair_stripe<TYPE, false>(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last, prof_tab);
+        else                           full_pair_stripe<TYPE, true >(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last, prof_tab);
         if (TYPE == NVB_LOCAL) {
             if (r0.score <= (trk.k0 >> 5)) { r0.score = trk.k0 >> 5; r0.x = trk.r0 + 1u; r0.y = b + ((uint32_t)trk.k0 & 31u) + 1u; }
             if (r1.score <= (trk.k1 >> 5)) { r1.score = trk.k1 >> 5; r1.x = trk.r1 + 1u; r1.y = b + ((uint32_t)trk.k1 & 31u) + 1u; }

@@ -215,6 +215,10 @@ gotoh_full_pair_kernel(const GotohScheme S, const GotohBatch b, uint2* __restric
     const uint32_t n = batch_count(b);
     const uint32_t n_pairs = (n + 1u) >> 1;
     const uint32_t p = blockIdx.x * PAIR_BLOCKDIM + threadIdx.x;
+    // substitution profile of every possible text symbol: one LDS per row instead of building it
+    __shared__ uint32_t prof_tab[256];
+    for (uint32_t g = threadIdx.x; g < 256u; g += PAIR_BLOCKDIM) prof_tab[g] = sub_profile(g, S.match - S.pgo, S.mismatch - S.pgo);
+    __syncthreads();
     if (p >= n_pairs) return;
     const uint32_t a0 = 2u * p, a1 = a0 + 1u;
     const bool has1 = a1 < n;
@@ -225,7 +229,7 @@ gotoh_full_pair_kernel(const GotohScheme S, const GotohBatch b, uint2* __restric
     __shared__ uint16_t sel[FULL_W * PAIR_BLOCKDIM];
     if (ok) ok = gotoh_full_pair<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a0), str_off(b.pat, has1 ? a1 : a0), M0,
                                        b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a0), str_off(b.txt, has1 ? a1 : a0), N0,
-                                       col + p, (size_t)((b.n_max + 1u) >> 1), sel + threadIdx.x, PAIR_BLOCKDIM, r0, r1);
+                                       col + p, (size_t)((b.n_max + 1u) >> 1), sel + threadIdx.x, PAIR_BLOCKDIM, r0, r1, prof_tab);
     if (ok) {
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
         if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
