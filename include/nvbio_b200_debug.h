@@ -14,6 +14,9 @@ void nvb_debug_full_minb(int minb);
 /* full-matrix dispatch: 0 = by batch size, 1 = always the warp-per-pair kernel, 2 = never */
 void nvb_debug_full_warp(int mode);
 
+/* seed + extend composition: 0 = automatic (the per-read path when no per-hit output is requested), 1 = always the per-hit path */
+void nvb_debug_pipeline_path(int path);
+
 #ifdef __cplusplus
 }
 #endif

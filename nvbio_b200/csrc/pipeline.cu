@@ -180,6 +180,108 @@ pipe_expand_hits_kernel(const FmIndex f, const PipeGeom g, const uint2* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-read path (no per-hit outputs requested): one thread per read locates its hits and keeps only the distinct (strand, window)
+// alignment jobs -- no per-hit array is written at all.  Jobs are staged per CTA in shared memory and appended to the global
+// job list with one atomic per CTA; their order varies from run to run, the results do not (every job carries the index of the
+// first hit that produced it, and the best-per-read reduction breaks score ties by it exactly as the per-hit path does).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t RJ_BLOCK = 128;          // reads per CTA
+constexpr uint32_t RJ_STAGE = 640;          // staged jobs per CTA (average: ~1.2 per read)
+constexpr int      RJ_LOCAL = 6;            // distinct windows remembered per read (more are still scored, just not de-duplicated)
+
+__global__ void __launch_bounds__(RJ_BLOCK)
+pipe_read_jobs_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict__ ranges, const uint32_t* __restrict__ sizes,
+                      const uint32_t* __restrict__ excl, const uint32_t* __restrict__ slen, uint32_t* __restrict__ counts,
+                      uint32_t* __restrict__ j_string, uint32_t* __restrict__ j_first,
+                      uint32_t* __restrict__ jp_off, uint32_t* __restrict__ jp_len, uint32_t* __restrict__ jt_off, uint32_t* __restrict__ jt_len)
+{
+    __shared__ uint32_t st_string[RJ_STAGE], st_first[RJ_STAGE], st_toff[RJ_STAGE], st_tlen[RJ_STAGE];
+    __shared__ uint32_t s_cnt, s_base;
+    if (threadIdx.x == 0) s_cnt = 0u;
+    __syncthreads();
+    const uint32_t r = blockIdx.x * RJ_BLOCK + threadIdx.x;
+    const uint32_t kept = counts[0];
+    if (r < g.n_reads) {
+        uint32_t lk_s[RJ_LOCAL], lk_b[RJ_LOCAL], lk_e[RJ_LOCAL];
+        int n_local = 0;
+        for (uint32_t strand = 0; strand < g.strands; ++strand) {
+            const uint32_t s = r * g.strands + strand;
+            const uint32_t len = slen[s];
+            for (uint32_t k = 0; k < g.seeds_per_string; ++k) {
+                const uint32_t q = s * g.seeds_per_string + k;
+                const uint32_t sz = sizes[q];
+                if (sz == 0u) continue;
+                const uint32_t base = excl[q], x = ranges[q].x, seed_begin = k * g.seed_interval;
+                for (uint32_t j = 0; j < sz; ++j) {
+                    const uint32_t h = base + j;
+                    if (h >= kept) break;                                              // beyond the caller's capacity
+                    const uint32_t pos = fm_locate_one(f, x + j);
+                    const uint32_t diag = pos > seed_begin ? pos - seed_begin : 0u;
+                    const uint32_t gb = diag > g.band / 2u ? diag - g.band / 2u : 0u;
+                    const uint64_t ge64 = (uint64_t)gb + len + g.band;
+                    const uint32_t ge = ge64 < g.genome_len ? (uint32_t)ge64 : g.genome_len;
+                    bool seen = false;
+#pragma unroll
+                    for (int e = 0; e < RJ_LOCAL; ++e) seen |= (e < n_local) && lk_s[e] == s && lk_b[e] == gb && lk_e[e] == ge;
+                    if (seen) continue;
+#pragma unroll
+                    for (int e = 0; e < RJ_LOCAL; ++e) if (e == n_local) { lk_s[e] = s; lk_b[e] = gb; lk_e[e] = ge; }
+                    if (n_local < RJ_LOCAL) ++n_local;
+                    const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                    if (slot < RJ_STAGE) { st_string[slot] = s; st_first[slot] = h; st_toff[slot] = gb; st_tlen[slot] = ge - gb; }
+                    else {                                                             // staging full: straight to the global list
+                        const uint32_t o = atomicAdd(counts + 2, 1u);
+                        j_string[o] = s; j_first[o] = h; jp_off[o] = s * g.stride; jp_len[o] = len; jt_off[o] = gb; jt_len[o] = ge - gb;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_cnt < RJ_STAGE ? s_cnt : RJ_STAGE;
+    if (threadIdx.x == 0) s_base = n ? atomicAdd(counts + 2, n) : 0u;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += RJ_BLOCK) {
+        const uint32_t o = s_base + i, s = st_string[i];
+        j_string[o] = s; j_first[o] = st_first[i]; jp_off[o] = s * g.stride; jp_len[o] = slen[s]; jt_off[o] = st_toff[i]; jt_len[o] = st_tlen[i];
+    }
+}
+
+// best job per read: max score, ties -> the job whose first hit comes first (the per-hit path's "smallest hit index")
+__global__ void __launch_bounds__(256)
+pipe_reduce_jobs_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ j_string, const uint32_t* __restrict__ j_first,
+                        const int32_t* __restrict__ job_score, unsigned long long* __restrict__ best_key)
+{
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= counts[2]) return;
+    const unsigned long long key = ((unsigned long long)((uint32_t)job_score[j] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - j_first[j]);
+    atomicMax(best_key + j_string[j] / g.strands, key);
+}
+
+__global__ void __launch_bounds__(256)
+pipe_init_best_kernel(const uint32_t n_reads, int32_t* __restrict__ best_score, uint32_t* __restrict__ best_pos, uint8_t* __restrict__ best_strand)
+{
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n_reads) return;
+    best_score[r] = INT_MIN; best_pos[r] = 0xFFFFFFFFu; best_strand[r] = 0;
+}
+
+// the winning job of every read writes the read's result (first-hit indices are unique, so exactly one job matches the key)
+__global__ void __launch_bounds__(256)
+pipe_finalize_jobs_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ j_string, const uint32_t* __restrict__ j_first,
+                          const uint32_t* __restrict__ jt_off, const int32_t* __restrict__ job_score, const uint2* __restrict__ job_sink,
+                          const unsigned long long* __restrict__ best_key,
+                          int32_t* __restrict__ best_score, uint32_t* __restrict__ best_pos, uint8_t* __restrict__ best_strand)
+{
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= counts[2]) return;
+    const uint32_t s = j_string[j], read = s / g.strands;
+    const unsigned long long key = ((unsigned long long)((uint32_t)job_score[j] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - j_first[j]);
+    if (best_key[read] != key) return;
+    best_score[read] = job_score[j]; best_pos[read] = jt_off[j] + job_sink[j].x; best_strand[read] = (uint8_t)(s % g.strands);
+}
+
 // Hits of one string are contiguous (queries are ordered by string, then seed).  Several seeds of a read usually
 // vote for the same diagonal, i.e. the very same (string, window) alignment job: score it once.
 // leader[h] = the smallest h' <= h of the same string with the same window; flag[h] = (leader[h] == h).
@@ -243,7 +345,11 @@ pipe_scatter_scores_kernel(const PipeGeom g, const uint32_t* __restrict__ counts
 {
     const uint32_t h = blockIdx.x * 256 + threadIdx.x;
     if (h >= counts[0]) return;
-    const uint32_t j = job_idx[leader[h]];
+    // leader[h] is the earliest identical job within the look-back of h; it may itself have an earlier one: follow the chain to
+    // the hit that really was compacted into the job list (leader[l] == l)
+    uint32_t l = leader[h];
+    for (uint32_t nx = leader[l]; nx != l; nx = leader[l]) l = nx;
+    const uint32_t j = job_idx[l];
     const int32_t sc = job_score[j];
     score[h] = sc;
     sink[h]  = job_sink[j];
@@ -266,15 +372,17 @@ pipe_reduce_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const 
 
 __global__ void __launch_bounds__(256)
 pipe_finalize_kernel(const PipeGeom g, const unsigned long long* __restrict__ best_key, const uint32_t* __restrict__ t_off,
-                     const uint2* __restrict__ sink, int32_t* __restrict__ best_score, uint32_t* __restrict__ best_pos)
+                     const uint2* __restrict__ sink, const uint32_t* __restrict__ hit_string,
+                     int32_t* __restrict__ best_score, uint32_t* __restrict__ best_pos, uint8_t* __restrict__ best_strand)
 {
     const uint32_t r = blockIdx.x * 256 + threadIdx.x;
     if (r >= g.n_reads) return;
     const unsigned long long key = best_key[r];
-    if (key == 0ull) { best_score[r] = INT_MIN; best_pos[r] = 0xFFFFFFFFu; return; }
+    if (key == 0ull) { best_score[r] = INT_MIN; best_pos[r] = 0xFFFFFFFFu; if (best_strand) best_strand[r] = 0; return; }
     const uint32_t h = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
     best_score[r] = (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u);
     best_pos[r] = t_off[h] + sink[h].x;
+    if (best_strand) best_strand[r] = (uint8_t)(hit_string[h] % g.strands);
 }
 
 // the best hit of every read as an alignment job for the traceback (reads without a hit get an empty job)
@@ -322,19 +430,19 @@ pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, c
 // ---------------------------------------------------------------------------------------------
 struct MateBest { bool has; int32_t score; uint32_t strand, beg, end, len; };
 
-__device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, const unsigned long long* __restrict__ best_key,
-                                              const uint32_t* __restrict__ hit_string, const uint32_t* __restrict__ t_off,
-                                              const uint2* __restrict__ sink, const uint32_t* __restrict__ str_len)
+// the best alignment of read r as the single-end stages left it: score, end (one past the last aligned base), strand
+__device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, const int32_t* __restrict__ best_score,
+                                              const uint32_t* __restrict__ best_pos, const uint8_t* __restrict__ best_strand,
+                                              const uint32_t* __restrict__ str_len)
 {
     MateBest m; m.has = false; m.score = INT_MIN; m.strand = 0; m.beg = m.end = 0xFFFFFFFFu; m.len = 0;
-    const unsigned long long key = best_key[r];
-    if (key == 0ull) return m;
-    const uint32_t h = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    const uint32_t end = best_pos[r];
+    if (end == 0xFFFFFFFFu) return m;
     m.has = true;
-    m.score = (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u);
-    m.strand = hit_string[h] % g.strands;
-    m.len = str_len[hit_string[h]];
-    m.end = t_off[h] + sink[h].x;
+    m.score = best_score[r];
+    m.strand = best_strand[r];
+    m.len = str_len[r * g.strands];                 // both strands of a read have its length
+    m.end = end;
     m.beg = m.end > m.len ? m.end - m.len : 0u;
     return m;
 }
@@ -342,8 +450,8 @@ __device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, con
 // one thread per pair: concordance of the independent best alignments, else up to two opposite-mate jobs (slot 2p + anchor)
 __global__ void __launch_bounds__(256)
 pair_classify_kernel(const PipeGeom g, const uint32_t n_pairs, const nvb_pair_params pp,
-                     const unsigned long long* __restrict__ best_key, const uint32_t* __restrict__ hit_string,
-                     const uint32_t* __restrict__ t_off, const uint2* __restrict__ sink, const uint32_t* __restrict__ str_len,
+                     const int32_t* __restrict__ best_score, const uint32_t* __restrict__ best_pos, const uint8_t* __restrict__ best_strand,
+                     const uint32_t* __restrict__ str_len,
                      uint32_t* __restrict__ want, uint32_t* __restrict__ w_pstr, uint32_t* __restrict__ w_toff, uint32_t* __restrict__ w_tlen,
                      int32_t* __restrict__ pair_score, uint32_t* __restrict__ pair_flags,
                      int32_t* __restrict__ mate_score, uint32_t* __restrict__ mate_pos, uint8_t* __restrict__ mate_strand)
@@ -351,8 +459,8 @@ pair_classify_kernel(const PipeGeom g, const uint32_t n_pairs, const nvb_pair_pa
     const uint32_t p = blockIdx.x * 256 + threadIdx.x;
     if (p >= n_pairs) return;
     MateBest m[2];
-    m[0] = mate_best(g, p, best_key, hit_string, t_off, sink, str_len);
-    m[1] = mate_best(g, n_pairs + p, best_key, hit_string, t_off, sink, str_len);
+    m[0] = mate_best(g, p, best_score, best_pos, best_strand, str_len);
+    m[1] = mate_best(g, n_pairs + p, best_score, best_pos, best_strand, str_len);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         mate_score[k * n_pairs + p] = m[k].score; mate_pos[k * n_pairs + p] = m[k].end; mate_strand[k * n_pairs + p] = (uint8_t)m[k].strand;
@@ -453,6 +561,8 @@ extern "C" int nvb_seed_extend_stage_ms(float ms[7])
     return NVB_OK;
 }
 
+static int g_pipe_path = 0;            // 0 = automatic, 1 = always the per-hit path (nvb_debug_pipeline_path)
+
 static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,
                     const nvb_seed_extend_params* P, uint32_t hit_capacity,
@@ -510,26 +620,31 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     uint32_t* excl       = tc.take<uint32_t>(nq);
     uint32_t* counts     = tc.take<uint32_t>(4);          // [0] hits kept, [1] hits found, [2] unique alignment jobs
     const bool dedup = P->dedup_jobs != 0;
-    uint32_t* leader  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
-    uint32_t* flag    = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
-    uint32_t* job_idx = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    // per-read path: nobody asked for per-hit outputs, so no per-hit array needs to exist
+    const bool per_read = dedup && g_pipe_path != 1 && !d_hit_read && !d_hit_window && !d_hit_score && !d_hit_sink && !BA;
+    uint32_t* j_string = per_read ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* j_first  = per_read ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* leader  = (dedup && !per_read) ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* flag    = (dedup && !per_read) ? tc.take<uint32_t>(hit_capacity) : nullptr;
+    uint32_t* job_idx = (dedup && !per_read) ? tc.take<uint32_t>(hit_capacity) : nullptr;
     uint32_t* jp_off  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
     uint32_t* jp_len  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
     uint32_t* jt_off  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
     uint32_t* jt_len  = dedup ? tc.take<uint32_t>(hit_capacity) : nullptr;
     int32_t*  job_score = dedup ? tc.take<int32_t>(hit_capacity) : nullptr;
     uint2*    job_sink  = dedup ? tc.take<uint2>(hit_capacity) : nullptr;
-    uint32_t* hit_string = tc.take<uint32_t>(hit_capacity);
-    uint32_t* p_off      = tc.take<uint32_t>(hit_capacity);
-    uint32_t* p_len      = tc.take<uint32_t>(hit_capacity);
-    uint32_t* t_off      = tc.take<uint32_t>(hit_capacity);
-    uint32_t* t_len      = tc.take<uint32_t>(hit_capacity);
-    int32_t*  h_score    = d_hit_score ? d_hit_score : tc.take<int32_t>(hit_capacity);
-    uint2*    h_sink     = d_hit_sink ? (uint2*)d_hit_sink : tc.take<uint2>(hit_capacity);
+    uint32_t* hit_string = per_read ? nullptr : tc.take<uint32_t>(hit_capacity);
+    uint32_t* p_off      = per_read ? nullptr : tc.take<uint32_t>(hit_capacity);
+    uint32_t* p_len      = per_read ? nullptr : tc.take<uint32_t>(hit_capacity);
+    uint32_t* t_off      = per_read ? nullptr : tc.take<uint32_t>(hit_capacity);
+    uint32_t* t_len      = per_read ? nullptr : tc.take<uint32_t>(hit_capacity);
+    int32_t*  h_score    = d_hit_score ? d_hit_score : (per_read ? nullptr : tc.take<int32_t>(hit_capacity));
+    uint2*    h_sink     = d_hit_sink ? (uint2*)d_hit_sink : (per_read ? nullptr : tc.take<uint2>(hit_capacity));
     unsigned long long* best_key = tc.take<unsigned long long>(n_reads);
+    uint8_t* rb_strand = tc.take<uint8_t>((size_t)n_reads + 16);      // strand of every read's best alignment
     size_t scan_bytes = 0, scan2_bytes = 0;
     NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, sizes, excl, (int)nq, as_stream(stream)));
-    if (dedup && hit_capacity) {
+    if (dedup && !per_read && hit_capacity) {
         NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan2_bytes, flag, job_idx, (int)hit_capacity, as_stream(stream)));
         if (scan2_bytes > scan_bytes) scan_bytes = scan2_bytes;
     }
@@ -609,6 +724,36 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     NVB_STAGE(3);
     // 4. locate + windows
     const uint32_t hgrid = (hit_capacity + 255) / 256;
+    if (per_read) {
+        // 4'. per read: locate, window, distinct jobs; 5'. extension; 6'. best job per read
+        NVB_CUDA_TRY(cudaMemsetAsync(counts + 2, 0, sizeof(uint32_t), s));
+        NVB_CUDA_TRY(cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * n_reads, s));
+        if (hit_capacity) {
+            pipe_read_jobs_kernel<<<(n_reads + RJ_BLOCK - 1) / RJ_BLOCK, RJ_BLOCK, 0, s>>>(f, g, ranges, sizes, excl, str_len_, counts,
+                                                                                          j_string, j_first, jp_off, jp_len, jt_off, jt_len);
+            NVB_LAUNCH_CHECK();
+        }
+        NVB_STAGE(4);
+        NVB_STAGE(5);
+        if (hit_capacity) {
+            size_t gb = gotoh_bytes;
+            pats.d_words = str_words; pats.d_offsets = jp_off; pats.d_lengths = jp_len;
+            txts.d_words = d_genome;  txts.d_offsets = jt_off; txts.d_lengths = jt_len;
+            const int r = nvb_banded_gotoh_score_indirect(P->band_len, P->type, &P->scheme, &pats, str_quals, &txts, counts + 2, hit_capacity,
+                                                          job_score, (nvb_uint2*)job_sink, gotoh_tmp, &gb, stream);
+            if (r != NVB_OK) return r;
+        }
+        NVB_STAGE(6);
+        pipe_init_best_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(n_reads, d_best_score, d_best_pos, rb_strand);
+        NVB_LAUNCH_CHECK();
+        if (hit_capacity) {
+            pipe_reduce_jobs_kernel<<<hgrid, 256, 0, s>>>(g, counts, j_string, j_first, job_score, best_key);
+            NVB_LAUNCH_CHECK();
+            pipe_finalize_jobs_kernel<<<hgrid, 256, 0, s>>>(g, counts, j_string, j_first, jt_off, job_score, job_sink, best_key,
+                                                            d_best_score, d_best_pos, rb_strand);
+            NVB_LAUNCH_CHECK();
+        }
+    } else {
     if (hit_capacity) {
         pipe_expand_hits_kernel<<<(nq + 255) / 256, 256, 0, s>>>(f, g, ranges, sizes, excl, str_len_, counts, hit_string, p_off, p_len, t_off, t_len);
         NVB_LAUNCH_CHECK();
@@ -655,8 +800,9 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         pipe_reduce_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, h_score, best_key);
         NVB_LAUNCH_CHECK();
     }
-    pipe_finalize_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(g, best_key, t_off, h_sink, d_best_score, d_best_pos);
+    pipe_finalize_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(g, best_key, t_off, h_sink, hit_string, d_best_score, d_best_pos, rb_strand);
     NVB_LAUNCH_CHECK();
+    }
     if (hit_capacity && (d_hit_read || d_hit_window)) {
         pipe_export_hits_kernel<<<hgrid, 256, 0, s>>>(g, counts, hit_string, t_off, t_len, d_hit_read, (uint2*)d_hit_window);
         NVB_LAUNCH_CHECK();
@@ -678,7 +824,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     if (PP) {
         const uint32_t n_pairs = n_reads / 2u, cap = PP->rescue_capacity;
         const uint32_t pgrid = (n_pairs + 255) / 256, sgrid = (n_reads + 255) / 256;
-        pair_classify_kernel<<<pgrid, 256, 0, s>>>(g, n_pairs, *PP, best_key, hit_string, t_off, h_sink, str_len_,
+        pair_classify_kernel<<<pgrid, 256, 0, s>>>(g, n_pairs, *PP, d_best_score, d_best_pos, rb_strand, str_len_,
                                                     pw_want, pw_pstr, pw_toff, pw_tlen, PO->d_pair_score, PO->d_pair_flags,
                                                     PO->d_mate_score, PO->d_mate_pos, PO->d_mate_strand);
         NVB_LAUNCH_CHECK();
@@ -706,6 +852,8 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     g_stage_ev_valid = true;
     return NVB_OK;
 }
+
+extern "C" void nvb_debug_pipeline_path(int path) { g_pipe_path = path; }
 
 extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,

@@ -268,3 +268,68 @@ def test_seed_extend_with_base_qualities():
     assert np.array_equal(wp.pair_score.cpu().numpy().astype(np.int64), wantp["pair_score"])
     assert np.array_equal(wp.mate_score.cpu().numpy().astype(np.int64), wantp["mate_score"])
     assert np.array_equal(host_u32(wp.mate_pos).astype(np.int64), wantp["mate_pos"])
+
+
+@pytest.mark.parametrize("bits,ragged,cap_div", [(2, False, 0), (4, True, 0), (2, False, 3)])
+def test_per_read_path_equals_per_hit_path(bits, ragged, cap_div):
+    """the per-read path of nvb_seed_extend (taken when no per-hit output is requested: distinct jobs straight from a thread per
+    read, no per-hit arrays) gives the same best score / position per read and the same hit counts as the per-hit path, incl.
+    4-bit reads with N, ragged lengths, a repetitive genome (many hits per read) and a hit capacity that truncates"""
+    import ctypes as C
+    require_gpu()
+    n = 150_000
+    gw = synth.random_genome_words(n, seed=91)
+    gsym = unpack_symbols(host_u32(gw), n).copy()
+    gsym[60_000:90_000] = np.tile(gsym[1000:1500], 60)                 # a 500 bp unit repeated 60 times: reads there have many hits
+    gw = torch.from_numpy(pack_symbols(gsym, 2, True).view(np.int32)).cuda()
+    fmi, _ = nb.FMIndexDevice.from_text(gw, n)
+    n_reads, L = 3000, 120
+    rw, pos, strand = synth.sample_reads(gw, n, n_reads, L, sub_rate=0.02, indel_rate=0.003, seed=15, mut_seed=16)
+    wpr = rw.shape[1]
+    sym = np.stack([unpack_symbols(host_u32(rw[i]), L) for i in range(n_reads)])
+    if bits == 4:
+        rng = np.random.default_rng(5)
+        sym[rng.random(sym.shape) < 0.004] = 4
+    lens = np.full(n_reads, L, np.uint32)
+    if ragged:
+        lens = np.random.default_rng(6).integers(L - 60, L + 1, n_reads).astype(np.uint32)
+    spw = 32 // bits
+    stride = ((L + spw - 1) // spw) * spw
+    buf = np.zeros((n_reads, stride), np.uint8); buf[:, :L] = sym
+    words = torch.from_numpy(pack_symbols(buf.reshape(-1), bits, True).view(np.int32)).cuda()
+    rs = PackedStringSet(words=words, bits=bits, big_endian=True, offsets=(torch.arange(n_reads, device="cuda", dtype=torch.int32) * stride),
+                         lengths=dev_u32(lens), stride=0, length=L, count=n_reads)
+    params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=True, max_seed_hits=40,
+                                 scheme=aln.SimpleGotohScheme(2, -2, -5, -3))
+    probe = nb.seed_extend(fmi, gw, rs, params, hit_capacity=400 * n_reads)
+    total = int(probe.n_hits[1])
+    assert total > 20 * n_reads                                         # the repeat region really produces many hits
+    cap = 400 * n_reads if not cap_div else total // cap_div
+    L_ = nb.lib()
+    fast = nb.seed_extend(fmi, gw, rs, params, hit_capacity=cap)
+    torch.cuda.synchronize()
+    L_.nvb_debug_pipeline_path(C.c_int(1))
+    try:
+        slow = nb.seed_extend(fmi, gw, rs, params, hit_capacity=cap)
+        torch.cuda.synchronize()
+    finally:
+        L_.nvb_debug_pipeline_path(C.c_int(0))
+    assert torch.equal(fast.n_hits[:2], slow.n_hits[:2])
+    assert torch.equal(fast.best_score, slow.best_score) and torch.equal(fast.best_pos, slow.best_pos)
+    # ground truth without any de-duplication logic: every hit scored on its own (chains of identical jobs longer than the
+    # per-hit path's look-back occur in the repeat region and must resolve to the job that was really scored)
+    params.dedup_jobs = False
+    truth = nb.seed_extend(fmi, gw, rs, params, hit_capacity=cap, keep_hits=True)
+    params.dedup_jobs = True
+    L_.nvb_debug_pipeline_path(C.c_int(1))
+    try:
+        slow_hits = nb.seed_extend(fmi, gw, rs, params, hit_capacity=cap, keep_hits=True)
+        torch.cuda.synchronize()
+    finally:
+        L_.nvb_debug_pipeline_path(C.c_int(0))
+    k = int(truth.n_hits[0])
+    assert torch.equal(truth.hit_score[:k], slow_hits.hit_score[:k]) and torch.equal(truth.hit_sink[:k], slow_hits.hit_sink[:k])
+    assert torch.equal(truth.best_score, fast.best_score) and torch.equal(truth.best_pos, fast.best_pos)
+    assert int(fast.n_hits[2]) <= int(slow.n_hits[0]) and int(fast.n_hits[2]) > 0
+    if cap_div:
+        assert int(fast.n_hits[0]) == cap < total
