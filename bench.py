@@ -595,7 +595,7 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": workload_config(args, n, n_reads, world),
         "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "api": "nvbio_b200.StreamingSeedExtend (pinned host in/out, depth-2 pipelining, wall clock over K steps)"},
-        "gpu_launches": (10 if params.dedup_jobs else 8) * args.steps,     # own kernels per step on the per-read path (the cub scan not counted)
+        "gpu_launches": (9 if params.dedup_jobs else 8) * args.steps,      # own kernels per step on the per-read path (the cub scan not counted)
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -253,10 +253,11 @@ __global__ void __launch_bounds__(256)
 pipe_reduce_jobs_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ j_string, const uint32_t* __restrict__ j_first,
                         const int32_t* __restrict__ job_score, unsigned long long* __restrict__ best_key)
 {
-    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= counts[2]) return;
-    const unsigned long long key = ((unsigned long long)((uint32_t)job_score[j] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - j_first[j]);
-    atomicMax(best_key + j_string[j] / g.strands, key);
+    const uint32_t n = counts[2];
+    for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+        const unsigned long long key = ((unsigned long long)((uint32_t)job_score[j] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - j_first[j]);
+        atomicMax(best_key + j_string[j] / g.strands, key);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -274,12 +275,13 @@ pipe_finalize_jobs_kernel(const PipeGeom g, const uint32_t* __restrict__ counts,
                           const unsigned long long* __restrict__ best_key,
                           int32_t* __restrict__ best_score, uint32_t* __restrict__ best_pos, uint8_t* __restrict__ best_strand)
 {
-    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= counts[2]) return;
-    const uint32_t s = j_string[j], read = s / g.strands;
-    const unsigned long long key = ((unsigned long long)((uint32_t)job_score[j] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - j_first[j]);
-    if (best_key[read] != key) return;
-    best_score[read] = job_score[j]; best_pos[read] = jt_off[j] + job_sink[j].x; best_strand[read] = (uint8_t)(s % g.strands);
+    const uint32_t n = counts[2];
+    for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+        const uint32_t s = j_string[j], read = s / g.strands;
+        const unsigned long long key = ((unsigned long long)((uint32_t)job_score[j] ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - j_first[j]);
+        if (best_key[read] != key) continue;
+        best_score[read] = job_score[j]; best_pos[read] = jt_off[j] + job_sink[j].x; best_strand[read] = (uint8_t)(s % g.strands);
+    }
 }
 
 // Hits of one string are contiguous (queries are ordered by string, then seed).  Several seeds of a read usually
@@ -747,9 +749,11 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         pipe_init_best_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(n_reads, d_best_score, d_best_pos, rb_strand);
         NVB_LAUNCH_CHECK();
         if (hit_capacity) {
-            pipe_reduce_jobs_kernel<<<hgrid, 256, 0, s>>>(g, counts, j_string, j_first, job_score, best_key);
+            // the job count lives on the device: a resident grid striding over it instead of hit_capacity / 256 mostly empty CTAs
+            const uint32_t jgrid = hgrid < 148u * 16u ? hgrid : 148u * 16u;
+            pipe_reduce_jobs_kernel<<<jgrid, 256, 0, s>>>(g, counts, j_string, j_first, job_score, best_key);
             NVB_LAUNCH_CHECK();
-            pipe_finalize_jobs_kernel<<<hgrid, 256, 0, s>>>(g, counts, j_string, j_first, jt_off, job_score, job_sink, best_key,
+            pipe_finalize_jobs_kernel<<<jgrid, 256, 0, s>>>(g, counts, j_string, j_first, jt_off, job_score, job_sink, best_key,
                                                             d_best_score, d_best_pos, rb_strand);
             NVB_LAUNCH_CHECK();
         }
