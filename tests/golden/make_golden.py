@@ -118,10 +118,76 @@ def make_full(ref):
     np.savez_compressed(os.path.join(OUT, "gotoh_full.npz"), **out)
 
 
+def make_extras(ref):
+    """(e) windowed banded scoring pass by pass (aln::banded_alignment_score<B>(..., window_begin, window_end, sink, checkpoint)) and
+    (f) the quality-table scheme through the reference templates (TableGotohScheme in oracle/ref_shim.cpp) -> banded_extras.npz.
+    Windowed problems have N >= M + B - 1 (the reference reads text[wb .. wb+B-2] unchecked at a window start)."""
+    rng = np.random.default_rng(20240925)
+    out = {}
+    qtab = np.zeros((256, 2), np.int32)
+    for q in range(256):
+        qtab[q, 0] = 2
+        qtab[q, 1] = -(2 + int(min(q, 40) / 40.0 * 4))
+    out["qtab"] = qtab
+    wcases, qcases = [], []
+    cid = 0
+    for band in (7, 15, 31):
+        for typ in (0, 1, 2):
+            # windowed: fixed M = 100, windows of 32 rows, with and without a min-score cut-off
+            M = 100
+            pr = random_problems(rng, 40, band, M, ragged=False)
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            keep = t_len >= p_len + band - 1
+            idxs = np.nonzero(keep)[0]
+            pats = [pat[p_off[i]:p_off[i] + p_len[i]] for i in idxs]; txts = [txt[t_off[i]:t_off[i] + t_len[i]] for i in idxs]
+            p_len2 = np.array([len(x) for x in pats], np.uint32); t_len2 = np.array([len(x) for x in txts], np.uint32)
+            p_off2 = (np.cumsum(p_len2) - p_len2).astype(np.uint32); t_off2 = (np.cumsum(t_len2) - t_len2).astype(np.uint32)
+            pr2 = (np.concatenate(pats), p_off2, p_len2, np.concatenate(txts), t_off2, t_len2)
+            n = len(p_off2)
+            for ms in (None, rng.integers(-20, 150, n).astype(np.int32)):
+                st = orc.window_state(n, band)
+                snaps = []
+                for wb in range(0, M, 32):
+                    ref.banded_gotoh_window(band, typ, (2, -2, -5, -3), *pr2, wb, wb + 32, st, min_score=ms)
+                    snaps.append(np.concatenate([st["score"].astype(np.int64), st["sx"].astype(np.int64), st["sy"].astype(np.int64), st["alive"].astype(np.int64)]))
+                for k, v in zip(("pat", "p_off", "p_len", "txt", "t_off", "t_len"), pr2):
+                    out[f"w{cid}_{k}"] = v
+                out[f"w{cid}_ms"] = ms if ms is not None else np.zeros(0, np.int32)
+                out[f"w{cid}_snaps"] = np.stack(snaps)
+                out[f"w{cid}_ckpt"] = st["ckpt"].copy()
+                wcases.append((cid, band, typ))
+                cid += 1
+            # quality table, banded
+            pr = random_problems(rng, 40, band, 120)
+            qual = rng.integers(0, 64, len(pr[0])).astype(np.uint8)
+            s, x, y, ok = ref.banded_gotoh(band, typ, (0, 0, -8, -3, -7, -2), *pr, qual=qual, qtab=qtab)
+            for k, v in zip(("pat", "p_off", "p_len", "txt", "t_off", "t_len"), pr):
+                out[f"q{cid}_{k}"] = v
+            out[f"q{cid}_qual"] = qual
+            out[f"q{cid}_res"] = np.stack([s.astype(np.int64), x.astype(np.int64), y.astype(np.int64), ok.astype(np.int64)])
+            qcases.append((cid, band, typ))
+            cid += 1
+    for typ in (0, 1, 2):           # quality table, full matrix (band = 0 in the case list)
+        pr = full_problems(rng, 40, 150, 300)
+        qual = rng.integers(0, 64, len(pr[0])).astype(np.uint8)
+        s, x, y = ref.gotoh_full(typ, (0, 0, -8, -3, -7, -2), *pr, qual=qual, qtab=qtab)
+        for k, v in zip(("pat", "p_off", "p_len", "txt", "t_off", "t_len"), pr):
+            out[f"q{cid}_{k}"] = v
+        out[f"q{cid}_qual"] = qual
+        out[f"q{cid}_res"] = np.stack([s.astype(np.int64), x.astype(np.int64), y.astype(np.int64), np.ones(len(s), np.int64)])
+        qcases.append((cid, 0, typ))
+        cid += 1
+    out["wcases"] = np.array(wcases, np.int64); out["qcases"] = np.array(qcases, np.int64)
+    np.savez_compressed(os.path.join(OUT, "banded_extras.npz"), **out)
+
+
 def main():
     assert orc.Ref.available(), "build oracle/_ref first: make -C oracle"
     ref = orc.Ref()
+    if "--only-extras" in sys.argv:
+        make_extras(ref); print("wrote banded_extras.npz"); return
     make_full(ref)
+    make_extras(ref)
     if "--only-full" in sys.argv:
         print("wrote gotoh_full.npz"); return
     rng = np.random.default_rng(20240917)

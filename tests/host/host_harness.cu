@@ -217,6 +217,13 @@ int hh_gotoh_full(int type, const int32_t* scheme6,
 
 // packed pair version; alignments (2p, 2p+1) are paired when their lengths agree, else scored singly with gotoh_full
 // returns the number of alignments that took the packed path
+// host-side admission rule of the packed full-matrix path for a batch
+int hh_full_pair_path_ok(int type, const int32_t* scheme6, uint32_t max_m, uint32_t max_n) {
+    nvb_gotoh_scheme cs; cs.match = scheme6[0]; cs.mismatch = scheme6[1]; cs.pattern_gap_open = scheme6[2]; cs.pattern_gap_ext = scheme6[3];
+    cs.text_gap_open = scheme6[4]; cs.text_gap_ext = scheme6[5]; cs.d_qual_table = nullptr; cs.qual_table_min = cs.qual_table_max = 0;
+    return full_pair_path_ok(type, &cs, max_m, max_n) ? 1 : 0;
+}
+
 int hh_gotoh_full_pair(int type, const int32_t* scheme6,
                   const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                   const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,

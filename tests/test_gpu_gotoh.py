@@ -392,3 +392,55 @@ def test_full_matrix_quality_table(O):
             assert same((s.cpu().numpy(), k[:, 0], k[:, 1]), want), typ
             tb = aln.batch_alignment_traceback(al, P, T, max_ops=600, quals=q)
             assert np.array_equal(tb["score"].cpu().numpy(), want[0]) and np.array_equal(host_u32(tb["sink"])[:, 0], want[1])
+
+
+def test_windowed_and_quality_golden_gpu():
+    """nvb_banded_gotoh_score_window and the quality-table paths of nvb_banded_gotoh_score / nvb_gotoh_score == the committed
+    outputs of the reference itself (tests/golden/banded_extras.npz)"""
+    require_gpu()
+    g = np.load(os.path.join(GOLD, "banded_extras.npz"))
+    for cid, band, typ in g["wcases"]:
+        band, typ = int(band), int(typ)
+        pat, p_off, p_len, txt, t_off, t_len = [g[f"w{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        ms = g[f"w{cid}_ms"]
+        n = len(p_off)
+        P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+        T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=8, big_endian=False)
+        al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -2, -5, -3))
+        st = aln.BandedWindowState(n, band, "cuda")
+        msd = torch.from_numpy(ms).cuda() if len(ms) else None
+        for w, wb in enumerate(range(0, 100, 32)):
+            aln.batch_banded_alignment_score_window(band, al, P, T, wb, wb + 32, st, min_score=msd)
+            k = host_u32(st.sink)
+            snap = np.concatenate([st.score.cpu().numpy().astype(np.int64), k[:, 0].astype(np.int64), k[:, 1].astype(np.int64), st.alive.cpu().numpy().astype(np.int64)])
+            assert np.array_equal(snap, g[f"w{cid}_snaps"][w]), (cid, band, typ, wb)
+        alive = st.alive.cpu().numpy().astype(bool)
+        assert np.array_equal(st.ckpt.cpu().numpy()[alive], g[f"w{cid}_ckpt"][alive]), cid
+
+    class _TableScheme:                       # the fixture's table behind the scheme interface of nvbio_b200.aln
+        def __init__(self, tab):
+            self.table_host = np.ascontiguousarray(tab); self.table = torch.from_numpy(self.table_host).cuda()
+
+        def struct(self):
+            from nvbio_b200._lib import GotohSchemeStruct
+            s = GotohSchemeStruct()
+            s.match, s.mismatch, s.pattern_gap_open, s.pattern_gap_ext, s.text_gap_open, s.text_gap_ext = 0, 0, -8, -3, -7, -2
+            s.d_qual_table = self.table.data_ptr(); s.qual_table_min, s.qual_table_max = int(self.table_host.min()), int(self.table_host.max())
+            return s
+    sch = _TableScheme(g["qtab"])
+    for cid, band, typ in g["qcases"]:
+        band, typ = int(band), int(typ)
+        pat, p_off, p_len, txt, t_off, t_len = [g[f"q{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        qual, res = g[f"q{cid}_qual"], g[f"q{cid}_res"]
+        P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+        T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=2 if not band else 8, big_endian=bool(not band))
+        q = torch.from_numpy(qual).cuda()
+        al = aln.make_gotoh_aligner(typ, sch)
+        if band:
+            s, k = aln.batch_banded_alignment_score(band, al, P, T, quals=q)
+        else:
+            s, k = aln.batch_alignment_score(al, P, T, quals=q)
+        k = host_u32(k)
+        ok = res[3].astype(bool)
+        assert np.array_equal(s.cpu().numpy().astype(np.int64)[ok], res[0][ok]), (cid, band, typ)
+        assert np.array_equal(k[:, 0].astype(np.int64)[ok], res[1][ok]) and np.array_equal(k[:, 1].astype(np.int64)[ok], res[2][ok]), (cid, band, typ)

@@ -509,3 +509,42 @@ def test_gotoh_full_quality_table(H, O, typ):
     H.hh_gotoh_full_q(C.c_int(typ), _p(s6), _p(qt), _p(qual), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len),
                       _p(tw), C.c_uint32(2), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
     assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2])
+
+
+def test_packed_paths_hold_their_16bit_bounds(H, O):
+    """random schemes up to the edge of the admission rules (large gap / mismatch costs, long texts): whenever the host-side rule
+    admits a batch to a packed s16x2 path, the packed routine is bit-identical to the int32 oracle -- the bound leaves no room for a
+    wrap-around; schemes the rule rejects are counted, not tested"""
+    rng = np.random.default_rng(4242)
+    admitted_full = admitted_band = 0
+    for trial in range(60):
+        scheme = (int(rng.integers(0, 21)), -int(rng.integers(0, 41)), -int(rng.integers(1, 61)), -int(rng.integers(1, 31)))
+        s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+        typ = int(rng.integers(0, 3))
+        # full matrix
+        pr = paired_full_problems(rng, 20, max_m=120, max_n=200)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        if H.hh_full_pair_path_ok(C.c_int(typ), _p(s6), C.c_uint32(int(p_len.max())), C.c_uint32(int(t_len.max()))):
+            admitted_full += 1
+            want = O.gotoh_full(typ, scheme, *pr)
+            pw, tw = pack_symbols(pat, 2, True), pack_symbols(txt, 2, True)
+            n = len(p_off)
+            score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+            packed = H.hh_gotoh_full_pair(C.c_int(typ), _p(s6), _p(pw), C.c_uint32(2), C.c_uint32(1), _p(p_off), _p(p_len),
+                                          _p(tw), C.c_uint32(2), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+            assert packed == n
+            assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), ("full", typ, scheme)
+        # banded
+        band = int(rng.choice([7, 15, 31]))
+        prb = fixed_problems(rng, 40, band, 150, ragged=(typ == 1))
+        pat, p_off, p_len, txt, t_off, t_len = prb
+        n = len(p_off)
+        pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 2, True)
+        score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32); nf = np.zeros(1, np.uint32)
+        r = H.hh_gotoh_pair(C.c_int(band), C.c_int(typ), _p(s6), None, None, C.c_uint32(150), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len),
+                            _p(tw), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy), _p(nf))
+        if r == 0:
+            admitted_band += 1
+            want = O.banded_gotoh(band, typ, scheme, *prb)
+            assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), ("banded", band, typ, scheme)
+    assert admitted_full >= 20 and admitted_band >= 10

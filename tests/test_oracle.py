@@ -293,3 +293,36 @@ def test_quality_table_scheme_vs_reference(O, R):
         b = R.gotoh_full(typ, scheme, *pr, qual=qual, qtab=qtab)
         for u, v in zip(a, b):
             assert np.array_equal(u, v), typ
+
+
+def _extras_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "banded_extras.npz"))
+
+
+def test_windowed_and_quality_golden(O):
+    """committed outputs of the reference itself (tests/golden/banded_extras.npz, written by make_golden.py): windowed banded scoring
+    pass by pass (BestSink + alive flag after every 32-row window, final checkpoint band) and the quality-table scheme (banded and
+    full matrix) == the oracle"""
+    g = _extras_golden()
+    for cid, band, typ in g["wcases"]:
+        pr = [g[f"w{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        ms = g[f"w{cid}_ms"]; ms = ms if len(ms) else None
+        n = len(pr[1])
+        st = orc.window_state(n, int(band))
+        for w, wb in enumerate(range(0, 100, 32)):
+            O.banded_gotoh_window(int(band), int(typ), (2, -2, -5, -3), *pr, wb, wb + 32, st, min_score=ms)
+            snap = np.concatenate([st["score"].astype(np.int64), st["sx"].astype(np.int64), st["sy"].astype(np.int64), st["alive"].astype(np.int64)])
+            assert np.array_equal(snap, g[f"w{cid}_snaps"][w]), (cid, band, typ, wb)
+        al = st["alive"].astype(bool)
+        assert np.array_equal(st["ckpt"][al], g[f"w{cid}_ckpt"][al])
+    qtab = g["qtab"]
+    for cid, band, typ in g["qcases"]:
+        pr = [g[f"q{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        qual, res = g[f"q{cid}_qual"], g[f"q{cid}_res"]
+        if band:
+            s, x, y, _ = O.banded_gotoh(int(band), int(typ), (0, 0, -8, -3, -7, -2), *pr, qual=qual, qtab=qtab)
+        else:
+            s, x, y = O.gotoh_full(int(typ), (0, 0, -8, -3, -7, -2), *pr, qual=qual, qtab=qtab)
+        ok = res[3].astype(bool)
+        assert np.array_equal(s.astype(np.int64)[ok], res[0][ok]) and np.array_equal(x.astype(np.int64)[ok], res[1][ok]) and np.array_equal(y.astype(np.int64)[ok], res[2][ok]), (cid, band, typ)
