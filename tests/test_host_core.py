@@ -548,3 +548,34 @@ def test_packed_paths_hold_their_16bit_bounds(H, O):
             want = O.banded_gotoh(band, typ, scheme, *prb)
             assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), ("banded", band, typ, scheme)
     assert admitted_full >= 20 and admitted_band >= 10
+
+
+@pytest.mark.parametrize("pbits,pbe", [(2, 1), (2, 0), (4, 1), (4, 0), (8, 0), (8, 1)])
+def test_gotoh_pair_pattern_stream_formats(H, O, pbits, pbe):
+    """the packed banded routine reads its pattern through PatStream (words normalised to big-endian symbol order at refill):
+    every packing the ABI admits -- 2 / 4 / 8 bits, either endianness, patterns starting at arbitrary (unaligned) offsets"""
+    rng = np.random.default_rng(70 + pbits * 2 + pbe)
+    for band, typ in ((31, 1), (15, 2), (7, 0)):
+        pr = fixed_problems(rng, 61, band, 97, ragged=(typ == 1))        # 97-symbol patterns: offsets are not word multiples
+        r, got, nf = _gotoh_pair(H, band, typ, (2, -2, -5, -3, -5, -3), pr, 97, pbits=pbits, pbe=pbe)
+        assert r == 0
+        want = O.banded_gotoh(band, typ, (2, -2, -5, -3), *pr)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want[:3])), (pbits, pbe, band, typ)
+
+
+@pytest.mark.parametrize("pbits,pbe,tbits,tbe", [(2, 0, 2, 0), (4, 0, 4, 0), (2, 1, 4, 0), (8, 0, 2, 0), (4, 1, 2, 1)])
+def test_gotoh_full_pair_stream_formats(H, O, pbits, pbe, tbits, tbe):
+    """the packed full-matrix routine reads pattern and text through SymSeq: little-endian and mixed packings, unaligned offsets"""
+    rng = np.random.default_rng(90 + pbits + 3 * tbits + pbe + tbe)
+    for typ in (0, 1, 2):
+        pr = paired_full_problems(rng, 40, max_m=90, max_n=170)
+        want = O.gotoh_full(typ, (2, -2, -5, -3), *pr)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        pw, tw = pack_symbols(pat, pbits, bool(pbe)), pack_symbols(txt, tbits, bool(tbe))
+        n = len(p_off)
+        score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+        s6 = np.array((2, -2, -5, -3, -5, -3), np.int32)
+        packed = H.hh_gotoh_full_pair(C.c_int(typ), _p(s6), _p(pw), C.c_uint32(pbits), C.c_uint32(pbe), _p(p_off), _p(p_len),
+                                      _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+        assert packed == n
+        assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, pbits, pbe, tbits, tbe)
