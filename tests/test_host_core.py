@@ -579,3 +579,32 @@ def test_gotoh_full_pair_stream_formats(H, O, pbits, pbe, tbits, tbe):
                                       _p(tw), C.c_uint32(tbits), C.c_uint32(tbe), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
         assert packed == n
         assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, pbits, pbe, tbits, tbe)
+
+
+def test_gotoh_window_quality_table(H, O):
+    """windowed banded scoring with per-base qualities and a score table (the early-exit threshold then uses table[0] as the
+    reference's scoring.match(0) does): pass-by-pass == the oracle, last pass == the whole-pattern score"""
+    from tests.golden.make_golden import random_problems
+    from tests.test_oracle import _nvbowtie_like_table
+    rng = np.random.default_rng(901)
+    qtab = _nvbowtie_like_table(); qt = np.ascontiguousarray(qtab.reshape(-1))
+    scheme = (0, 0, -8, -3, -7, -2); s6 = np.array(scheme, np.int32)
+    for band, typ in ((31, 1), (15, 2), (7, 0)):
+        pr = random_problems(rng, 50, band, 110)
+        pat, p_off, p_len, txt, t_off, t_len = pr
+        n = len(p_off)
+        qual = rng.integers(0, 64, len(pat)).astype(np.uint8)
+        whole = O.banded_gotoh(band, typ, scheme, *pr, qual=qual, qtab=qtab)
+        pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 8, False)
+        for ms in (None, rng.integers(-60, 120, n).astype(np.int32)):
+            so = orc.window_state(n, band); sh = orc.window_state(n, band)
+            for wb in range(0, 110, 32):
+                O.banded_gotoh_window(band, typ, scheme, *pr, wb, wb + 32, so, min_score=ms, qual=qual, qtab=qtab)
+                H.hh_gotoh_window(C.c_int(band), C.c_int(typ), _p(s6), _p(qt), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len), _p(qual),
+                                  _p(tw), C.c_uint32(8), C.c_uint32(0), _p(t_off), _p(t_len), C.c_uint32(n), C.c_uint32(wb), C.c_uint32(wb + 32),
+                                  _p(ms) if ms is not None else None, _p(sh["ckpt"]), _p(sh["score"]), _p(sh["sx"]), _p(sh["sy"]), _p(sh["alive"]))
+                for k in ("score", "sx", "sy", "alive"):
+                    assert np.array_equal(so[k], sh[k]), (band, typ, wb, k)
+            if ms is None:
+                ok = whole[3].astype(bool)
+                assert np.array_equal(sh["score"][ok], whole[0][ok]) and np.array_equal(sh["sx"][ok], whole[1][ok])
