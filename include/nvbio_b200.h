@@ -220,7 +220,7 @@ int nvb_gotoh_score_indirect(int type, const nvb_gotoh_scheme* scheme, const nvb
  *   d_source[i]          = (text begin, pattern begin) of the alignment; the soft clips of the pattern are
  *                          pattern_len - sink.y at the end and source.y at the start
  * Replaces aln::alignment_traceback<MAX_PATTERN_LEN,MAX_TEXT_LEN,CHECKPOINTS> with a Gotoh aligner (generic driver
- * nvbio/alignment/alignment_inl.h:365-530; state machine gotoh/gotoh_inl.h:1806-1884) and its batched form
+ * nvbio/alignment/alignment_inl.h:365-530; state machine gotoh/gotoh_inl.h:1806-1871) and its batched form
  * BatchedAlignmentTraceback (batched_inl.h:607-860).  No checkpoints: d_temp holds the whole direction matrix, 4 bits per cell
  * (max_text_len * ceil(max_pattern_len/32) * 16 bytes per alignment). */
 int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,

@@ -140,7 +140,7 @@ __host__ __device__ inline SinkResult gotoh_full(const GotohScheme& S,
     return gotoh_full_impl<TYPE, false>(S, pwords, pbits, pbe, poff, M, twords, tbits, tbe, toff, N, col, col_stride, nullptr, 0, quals);
 }
 
-// walk the direction matrix from the sink (state machine of nvbio/alignment/gotoh/gotoh_inl.h:1806-1884 plus the first-row /
+// walk the direction matrix from the sink (state machine of nvbio/alignment/gotoh/gotoh_inl.h:1806-1871 plus the first-row /
 // first-column completion of the generic driver, alignment_inl.h:452-471); ops in END -> START order, returns their number
 template <int TYPE>
 __host__ __device__ inline uint32_t gotoh_full_walk(const uint32_t* __restrict__ dirs, uint32_t dir_row_words, const SinkResult& sink,

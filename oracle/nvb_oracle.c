@@ -661,7 +661,7 @@ void orc_gotoh_full(int type, const orc_scheme* S, const i32* qtab,
 /* ------------------------------------------------------------------------------------------------
  * full-matrix Gotoh traceback: aln::alignment_traceback<MAX_PATTERN_LEN,MAX_TEXT_LEN,CHECKPOINTS> with a Gotoh aligner
  * (generic driver nvbio/alignment/alignment_inl.h:365-488; direction vectors gotoh/gotoh_inl.h:514-555 + :426-446;
- * state machine gotoh/gotoh_inl.h:1806-1884).  The checkpointing of the reference only bounds its memory: here the whole
+ * state machine gotoh/gotoh_inl.h:1806-1871).  The checkpointing of the reference only bounds its memory: here the whole
  * direction matrix is kept.  Per cell: hdir = top > left ? (top > diag ? DEL : SUB) : (left > diag ? INS : SUB) with
  * top = F (text gap, DELETION), left = E (pattern gap, INSERTION); LOCAL cells with H == 0 are SINKs; the E / F extension
  * bits say whether E / F were extended rather than opened.  Walk from the sink: H -> follow hdir; E -> push INSERTION, column-1,
