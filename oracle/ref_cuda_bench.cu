@@ -6,6 +6,7 @@
 //            sinks, DeviceThreadScheduler(), ... )      nvbio/alignment/batched_inl.h:1067-1101
 //            -> batched_banded_alignment_score_kernel     nvbio/alignment/batched_banded_inl.h:78-162
 //   fm     : FMIndexFilterDevice<fm_index_type>::rank + locate   nvbio/fmindex/filter_inl.h:268-402
+//   approx : nvBowtie's detail::map<true> (one-mismatch seed search, a __device__ function)   nvBowtie/bowtie2/cuda/mapping_inl.h:128-220
 // Inputs are the arrays bench.py / the tests dump (same workload as the B200-native kernels); outputs are
 // written back so that the results can be compared bit for bit.
 //
@@ -23,6 +24,7 @@
 #include <nvbio/fmindex/filter.h>
 #include <nvbio/alignment/alignment.h>
 #include <nvbio/alignment/batched.h>
+#include <nvBowtie/bowtie2/cuda/mapping_inl.h>          // detail::map<find_exact>: nvBowtie's one-mismatch seed search (device function)
 #include <thrust/device_vector.h>
 #include <cstdio>
 #include <cstdlib>
@@ -231,6 +233,87 @@ static int run_fm(const std::string& dir)
     return 0;
 }
 
+// --------------------------------------------------------------------------------------------------
+// one-mismatch seed search: nvBowtie's own detail::map<true> (nvBowtie/bowtie2/cuda/mapping_inl.h:128-220) run over nq seeds of
+// L unpacked symbols (seed i at bytes [i*L, +L), read forwards), exact region [0, len1); every pushed SeedHit range is recorded
+// in push order (inclusive ranges), up to max_out per seed, with the push count and range_sum
+// --------------------------------------------------------------------------------------------------
+struct ApproxCollector
+{
+    uint2* out; uint32 n, cap;
+    NVBIO_FORCEINLINE NVBIO_DEVICE uint32 size() const { return 0u; }                   // never "full": nothing is ever popped
+    NVBIO_FORCEINLINE NVBIO_DEVICE void pop_bottom() {}
+    NVBIO_FORCEINLINE NVBIO_DEVICE void push(const bowtie2::cuda::SeedHit hit)
+    {
+        const uint2 r = hit.get_range();                                                // exclusive end (inclusive_to_exclusive)
+        if (n < cap) out[n] = make_uint2( r.x, r.y - 1u );
+        ++n;
+    }
+};
+struct SeedBytes
+{
+    const uint8* p;
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE uint8 operator[] (const uint32 i) const { return p[i]; }
+};
+
+template <typename fm_index_type>
+__global__ void ref_map_approx_kernel(const fm_index_type fmi, const uint8* seeds, const uint32 nq, const uint32 L, const uint32 len1,
+                                      const uint32 max_out, uint2* ranges, uint32* counts, uint32* sums)
+{
+    const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    SeedBytes q; q.p = seeds + uint64(i) * L;
+    ApproxCollector heap; heap.out = ranges + uint64(i) * max_out; heap.n = 0; heap.cap = max_out;
+    uint32 range_sum = 0, range_count = 0;
+    bowtie2::cuda::detail::map<true>( q, len1, L, fmi,
+        bowtie2::cuda::SeedHit::build_flags( STANDARD, FORWARD, 0u ),
+        heap, 0xFFFFFFFFu, range_sum, range_count );
+    counts[i] = heap.n; sums[i] = range_sum;
+}
+
+static int run_approx(const std::string& dir)
+{
+    const std::vector<uint32> meta = read_file<uint32>(dir + "/meta.bin");    // length, primary, L2[5], nq, L, len1, max_out
+    const uint32 length = meta[0], primary = meta[1], nq = meta[7], L = meta[8], len1 = meta[9], max_out = meta[10];
+    const std::vector<uint32> h_bwt_occ = read_file<uint32>(dir + "/bwt_occ.bin");
+    const std::vector<uint32> h_ssa     = read_file<uint32>(dir + "/ssa.bin");
+    const std::vector<uint8>  h_seeds   = read_file<uint8>(dir + "/seed_bytes.bin");
+    thrust::device_vector<uint32> d_bwt_occ(h_bwt_occ), d_ssa(h_ssa), d_L2(meta.begin() + 2, meta.begin() + 7);
+    thrust::device_vector<uint8>  d_seeds(h_seeds);
+    std::vector<uint32> h_ct(256); gen_bwt_count_table(h_ct.data());
+    thrust::device_vector<uint32> d_ct(h_ct);
+
+    typedef nvbio::cuda::ldg_pointer<uint4>                              bwt_occ_type;
+    typedef deinterleaved_iterator<2,0,bwt_occ_type>                     bwt_type;
+    typedef deinterleaved_iterator<2,1,bwt_occ_type>                     occ_type;
+    typedef nvbio::cuda::ldg_pointer<uint32>                             u32_ldg;
+    typedef PackedStream<bwt_type,uint8,2u,true>                         bwt_stream_type;
+    typedef SSA_index_multiple_context<16u,u32_ldg>                      ssa_type;
+    typedef rank_dictionary<2u,64u,bwt_stream_type,occ_type,u32_ldg>     rank_dict_type;
+    typedef fm_index<rank_dict_type,ssa_type>                            fm_index_type;
+    const bwt_occ_type p( (const uint4*)thrust::raw_pointer_cast(d_bwt_occ.data()) );
+    const fm_index_type fmi( length, primary, thrust::raw_pointer_cast(d_L2.data()),
+        rank_dict_type( bwt_stream_type( bwt_type(p) ), occ_type(p), u32_ldg( thrust::raw_pointer_cast(d_ct.data()) ) ),
+        ssa_type( u32_ldg( thrust::raw_pointer_cast(d_ssa.data()) ) ) );
+
+    thrust::device_vector<uint2>  d_ranges( uint64(nq) * max_out );
+    thrust::device_vector<uint32> d_counts(nq), d_sums(nq);
+    ref_map_approx_kernel<<<(nq + 127) / 128, 128>>>( fmi, thrust::raw_pointer_cast(d_seeds.data()), nq, L, len1, max_out,
+        thrust::raw_pointer_cast(d_ranges.data()), thrust::raw_pointer_cast(d_counts.data()), thrust::raw_pointer_cast(d_sums.data()) );
+    cudaDeviceSynchronize();
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+    std::vector<uint2> h_ranges( d_ranges.size() ); std::vector<uint32> h_counts(nq), h_sums(nq);
+    cudaMemcpy(h_ranges.data(), thrust::raw_pointer_cast(d_ranges.data()), sizeof(uint2) * h_ranges.size(), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_counts.data(), thrust::raw_pointer_cast(d_counts.data()), sizeof(uint32) * nq, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_sums.data(),   thrust::raw_pointer_cast(d_sums.data()),   sizeof(uint32) * nq, cudaMemcpyDeviceToHost);
+    write_file(dir + "/ref_ranges.bin", h_ranges.data(), h_ranges.size());
+    write_file(dir + "/ref_counts.bin", h_counts.data(), nq);
+    write_file(dir + "/ref_sums.bin", h_sums.data(), nq);
+    printf("{\"what\": \"nvBowtie detail::map<true> (one-mismatch seed search), sm_100a\", \"nq\": %u, \"L\": %u, \"len1\": %u}\n", nq, L, len1);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: ref_cuda_bench banded|fm <dir>\n"); return 1; }
@@ -238,5 +321,6 @@ int main(int argc, char** argv)
     if (mode == "banded") return run_banded(dir);
     if (mode == "fm")     return run_fm(dir);
     if (mode == "full")   return run_full(dir);
+    if (mode == "approx") return run_approx(dir);
     return 1;
 }
