@@ -21,11 +21,18 @@ def _p(a):
 
 @pytest.fixture(scope="module")
 def H():
-    deps = [SRC] + [os.path.join(HERE, "..", "nvbio_b200", "csrc", f) for f in ("fm_core.cuh", "gotoh_core.cuh", "common.cuh")]
-    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+    deps = [SRC] + [os.path.join(HERE, "..", "nvbio_b200", "csrc", f) for f in ("fm_core.cuh", "gotoh_core.cuh", "gotoh_full_core.cuh", "common.cuh")]
+    so, extra = SO, []
+    if os.environ.get("NVB_HOST_HARNESS_ASAN"):
+        # AddressSanitizer + UBSan build of the very same per-thread routines: run the file as
+        #   NVB_HOST_HARNESS_ASAN=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest tests/test_host_core.py
+        so = SO.replace(".so", "_asan.so")
+        extra = ["-g", "-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fsanitize=undefined", "-Xcompiler", "-fno-omit-frame-pointer",
+                 "-Xcompiler", "-fno-sanitize-recover=undefined"]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
-                               "-Wno-deprecated-declarations", "-Xcompiler", "-fPIC", "-shared", "-o", SO, SRC])
-    return C.CDLL(SO)
+                               "-Wno-deprecated-declarations", "-Xcompiler", "-fPIC", "-shared", "-o", so, SRC] + extra)
+    return C.CDLL(so)
 
 
 @pytest.fixture(scope="module")
