@@ -35,12 +35,18 @@ class QualityGotohScheme:
     expression of QualCost (scoring.h:96-100) is evaluated HERE, on the host, in float32 exactly as
     written, and shipped as a 256x2 int32 table."""
 
-    def __init__(self, match_bonus: int, mm_min: int, mm_max: int, read_gap_const: int, read_gap_coeff: int,
-                 ref_gap_const: int, ref_gap_coeff: int, device="cuda"):
+    @staticmethod
+    def host_table(match_bonus: int, mm_min: int, mm_max: int) -> np.ndarray:
+        """[256, 2] int32: (substitution on a match, on a mismatch) per base quality -- QualCost::operator() (scoring.h:96-100:
+        min + int(float(min(q,40) / 40.0f) * (max - min))) in float32, truncated towards zero like the C cast"""
         q = np.arange(256)
         frac = (np.minimum(q, 40).astype(np.float32) / np.float32(40.0)).astype(np.float32)
-        mmp = mm_min + (frac * np.float32(mm_max - mm_min)).astype(np.int32)
-        tab = np.stack([np.full(256, match_bonus, dtype=np.int32), (-mmp).astype(np.int32)], axis=1)
+        mmp = mm_min + np.trunc(frac * np.float32(mm_max - mm_min)).astype(np.int32)
+        return np.ascontiguousarray(np.stack([np.full(256, match_bonus, dtype=np.int32), (-mmp).astype(np.int32)], axis=1))
+
+    def __init__(self, match_bonus: int, mm_min: int, mm_max: int, read_gap_const: int, read_gap_coeff: int,
+                 ref_gap_const: int, ref_gap_coeff: int, device="cuda"):
+        tab = self.host_table(match_bonus, mm_min, mm_max)
         self.table_host = np.ascontiguousarray(tab)
         self.table = torch.from_numpy(self.table_host).to(device)
         self.pgo, self.pge = -read_gap_const - read_gap_coeff, -read_gap_coeff

@@ -305,6 +305,29 @@ class Ref(_Base):
         assert r == 0
         return o
 
+    def nvbowtie_scheme(self, preset=0, match_bonus=0, mm_min=2, mm_max=6, read_gap=(5, 3), ref_gap=(5, 3)):
+        """nvBowtie's own SmithWatermanScoringScheme<QualCost<int>,ConstantCost<int>> (scoring.h:203-317), compiled from the reference:
+        (table[256,2] = substitution on match / mismatch per base quality, gaps = (pattern open, ext, text open, ext),
+        (worst_score, perfect_score(100))).  preset 1 = scheme::local(), 2 = the default-constructed (end-to-end) scheme."""
+        tab = np.zeros(512, np.int32); gaps = np.zeros(4, np.int32); lim = np.zeros(2, np.int32)
+        self.lib.ref_nvbowtie_scheme(C.c_int(preset), C.c_int(match_bonus), C.c_int(mm_min), C.c_int(mm_max), C.c_int(read_gap[0]), C.c_int(read_gap[1]),
+                                     C.c_int(ref_gap[0]), C.c_int(ref_gap[1]), _p(tab), _p(gaps), _p(lim))
+        return tab.reshape(256, 2), tuple(int(v) for v in gaps), tuple(int(v) for v in lim)
+
+    def nvbowtie_banded(self, band, typ, pat, qual, p_off, p_len, txt, t_off, t_len, preset=0, match_bonus=0, mm_min=2, mm_max=6,
+                        read_gap=(5, 3), ref_gap=(5, 3)):
+        """aln::banded_alignment_score<band> with nvBowtie's real scheme object and per-base qualities (band 15 / 31; LOCAL / SEMI_GLOBAL)"""
+        pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8); qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+        t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+        n = len(p_off)
+        score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+        r = self.lib.ref_nvbowtie_banded(C.c_int(band), C.c_int(typ), C.c_int(preset), C.c_int(match_bonus), C.c_int(mm_min), C.c_int(mm_max),
+                                         C.c_int(read_gap[0]), C.c_int(read_gap[1]), C.c_int(ref_gap[0]), C.c_int(ref_gap[1]),
+                                         _p(pat), _p(qual), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(n), _p(score), _p(sx), _p(sy))
+        assert r == 0, r
+        return score, sx, sy
+
     def banded_gotoh(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
         if qtab is not None:
             # the reference templates with a table-driven scheme (TableGotohScheme in ref_shim.cpp); bands 7 / 15 / 31

@@ -181,6 +181,31 @@ def make_extras(ref):
     np.savez_compressed(os.path.join(OUT, "banded_extras.npz"), **out)
 
 
+def make_nvbowtie(ref, path=None):
+    """(g) nvBowtie's OWN scoring scheme object (SmithWatermanScoringScheme<QualCost<int>,ConstantCost<int>>, scoring.h:86-105,203-317,
+    compiled from the reference by oracle/ref_nvbowtie.cpp): the 256 x 2 substitution tables of its presets and of a few custom
+    constants, and banded DP results with per-base qualities under the --local preset -> nvbowtie_scheme.npz"""
+    out = {}
+    cfgs = [(1, 0, 0, 0), (2, 0, 0, 0), (0, 2, 2, 6), (0, 0, 2, 6), (0, 3, 1, 30), (0, 1, 3, 3), (0, 2, 6, 2), (0, 0, 0, 255)]
+    out["cfgs"] = np.array(cfgs, dtype=np.int32)
+    for i, (preset, mb, lo, hi) in enumerate(cfgs):
+        tab, gaps, lim = ref.nvbowtie_scheme(preset, mb, lo, hi)
+        out[f"tab{i}"] = tab; out[f"gaps{i}"] = np.array(gaps, np.int32); out[f"lim{i}"] = np.array(lim, np.int32)
+    rng = np.random.default_rng(97)
+    cases = []
+    for cid, (band, typ) in enumerate([(31, 1), (31, 2), (15, 1), (15, 2)]):
+        pr = random_problems(rng, 60, band, 150)
+        qual = rng.integers(0, 64, len(pr[0])).astype(np.uint8)
+        s, x, y = ref.nvbowtie_banded(band, typ, pr[0], qual, pr[1], pr[2], pr[3], pr[4], pr[5], preset=1)
+        for k, v in zip(("pat", "p_off", "p_len", "txt", "t_off", "t_len"), pr):
+            out[f"d{cid}_{k}"] = np.asarray(v)
+        out[f"d{cid}_qual"] = qual
+        out[f"d{cid}_res"] = np.stack([s.astype(np.int64), x.astype(np.int64), y.astype(np.int64)])
+        cases.append((cid, band, typ))
+    out["dcases"] = np.array(cases, dtype=np.int32)
+    np.savez_compressed(path or os.path.join(OUT, "nvbowtie_scheme.npz"), **out)
+
+
 def main():
     assert orc.Ref.available(), "build oracle/_ref first: make -C oracle"
     ref = orc.Ref()
@@ -260,6 +285,7 @@ def main():
             fm[f"{name}_{key}"] = v
     fm["count_table"] = ref.count_table()
     np.savez_compressed(os.path.join(OUT, "fmindex.npz"), **fm)
+    make_nvbowtie(ref)
     print("wrote", os.listdir(OUT))
 
 

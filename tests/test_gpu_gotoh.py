@@ -444,3 +444,20 @@ def test_windowed_and_quality_golden_gpu():
         ok = res[3].astype(bool)
         assert np.array_equal(s.cpu().numpy().astype(np.int64)[ok], res[0][ok]), (cid, band, typ)
         assert np.array_equal(k[:, 0].astype(np.int64)[ok], res[1][ok]) and np.array_equal(k[:, 1].astype(np.int64)[ok], res[2][ok]), (cid, band, typ)
+
+
+def test_quality_scheme_vs_nvbowtie_scheme_object():
+    """nvb_banded_gotoh_score with nvbio_b200.aln.QualityGotohScheme(--local constants) == aln::banded_alignment_score run with
+    nvBowtie's OWN scheme object SmithWatermanScoringScheme<QualCost<int>,ConstantCost<int>>::local() and per-base qualities
+    (committed outputs of the reference: tests/golden/nvbowtie_scheme.npz, make_golden.py make_nvbowtie); LOCAL + SEMI_GLOBAL, bands 15 / 31"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nvbowtie_scheme.npz"))
+    sch = aln.QualityGotohScheme(match_bonus=2, mm_min=2, mm_max=6, read_gap_const=5, read_gap_coeff=3, ref_gap_const=5, ref_gap_coeff=3)
+    assert np.array_equal(sch.table_host, g["tab0"])
+    for cid, band, typ in g["dcases"]:
+        pr = [g[f"d{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        res = g[f"d{cid}_res"]
+        ok = pr[5] >= pr[2]
+        s, x, y = run(int(band), int(typ), sch, pr, pbits=4, tbits=8, quals=g[f"d{cid}_qual"])
+        assert np.array_equal(np.asarray(s, np.int64)[ok], res[0][ok]) and np.array_equal(np.asarray(x, np.int64)[ok], res[1][ok]) \
+            and np.array_equal(np.asarray(y, np.int64)[ok], res[2][ok]), (cid, band, typ)

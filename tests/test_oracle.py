@@ -326,3 +326,44 @@ def test_windowed_and_quality_golden(O):
             s, x, y = O.gotoh_full(int(typ), (0, 0, -8, -3, -7, -2), *pr, qual=qual, qtab=qtab)
         ok = res[3].astype(bool)
         assert np.array_equal(s.astype(np.int64)[ok], res[0][ok]) and np.array_equal(x.astype(np.int64)[ok], res[1][ok]) and np.array_equal(y.astype(np.int64)[ok], res[2][ok]), (cid, band, typ)
+
+
+def _nvbowtie_golden():
+    return np.load(os.path.join(GOLD, "nvbowtie_scheme.npz"))
+
+
+def test_quality_table_generation_vs_nvbowtie_scheme():
+    """nvbio_b200.aln.QualityGotohScheme.host_table (the float32 QualCost expression evaluated on the host) == the 256 x 2 table of
+    nvBowtie's own SmithWatermanScoringScheme<QualCost<int>,ConstantCost<int>> object, entry by entry (fixture written by running the
+    reference's scoring.h, tests/golden/make_golden.py make_nvbowtie) -- presets --local and end-to-end, and custom constants"""
+    from nvbio_b200.aln import QualityGotohScheme
+    g = _nvbowtie_golden()
+    presets = {1: (2, 2, 6), 2: (0, 2, 6)}                 # scoring_inl.h:74-147: local() = match 2, mmp 2..6; default ctor = match 0
+    for i, (preset, mb, lo, hi) in enumerate(g["cfgs"]):
+        mb, lo, hi = presets.get(int(preset), (int(mb), int(lo), int(hi)))
+        assert np.array_equal(QualityGotohScheme.host_table(mb, lo, hi), g[f"tab{i}"]), (i, preset, mb, lo, hi)
+        assert tuple(g[f"gaps{i}"]) == (-8, -3, -8, -3)    # open = -(const + coeff), ext = -coeff (scoring.h:290-293)
+        assert int(g[f"lim{i}"][0]) == -65536              # worst_score (scoring.h:226-227)
+
+
+def test_quality_table_generation_vs_nvbowtie_scheme_live(R):
+    from nvbio_b200.aln import QualityGotohScheme
+    for mb, lo, hi in ((2, 2, 6), (0, 2, 6), (1, 0, 40), (5, 7, 7), (0, 1, 200)):
+        tab, gaps, lim = R.nvbowtie_scheme(0, mb, lo, hi, read_gap=(4, 2), ref_gap=(6, 1))
+        assert np.array_equal(QualityGotohScheme.host_table(mb, lo, hi), tab)
+        assert gaps == (-6, -2, -7, -1)
+
+
+def test_oracle_quality_dp_vs_nvbowtie_scheme(O):
+    """the oracle's banded DP with the host-evaluated table == aln::banded_alignment_score run with nvBowtie's real scheme object
+    and per-base qualities (--local preset; LOCAL and SEMI_GLOBAL, bands 15 / 31)"""
+    from nvbio_b200.aln import QualityGotohScheme
+    g = _nvbowtie_golden()
+    qtab = QualityGotohScheme.host_table(2, 2, 6)
+    for cid, band, typ in g["dcases"]:
+        pr = [g[f"d{cid}_{k}"] for k in ("pat", "p_off", "p_len", "txt", "t_off", "t_len")]
+        s, x, y, ok = O.banded_gotoh(int(band), int(typ), (0, 0, -8, -3, -8, -3), *pr, qual=g[f"d{cid}_qual"], qtab=qtab)
+        res = g[f"d{cid}_res"]
+        okb = ok.astype(bool)
+        assert okb.sum() > 30
+        assert np.array_equal(s.astype(np.int64)[okb], res[0][okb]) and np.array_equal(x.astype(np.int64)[okb], res[1][okb]) and np.array_equal(y.astype(np.int64)[okb], res[2][okb]), (cid, band, typ)
