@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
     ap.add_argument("--ktab-k", type=int, default=16, help="k of the k-mer range table (0 = none)")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-to-host (e2e) pipeline")
     ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 kernel-level measurements")
@@ -178,8 +179,21 @@ def make_reads(genome, n, n_reads, rank, device):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
-    """the reference's CPU path (oracle/_ref if present, else the C port) on a bounded sample per step"""
+def host_reference_index(fmi, with_ssa=True):
+    """the device index as host arrays in the REFERENCE'S format (SA sampled every 16 rows, no table), for the CPU checkers"""
+    from oracle import orc
+    ssa16 = None
+    if with_ssa:
+        step = 16 // fmi.sa_interval
+        ssa16 = np.ascontiguousarray(fmi.ssa[::step].contiguous().cpu().numpy().view(np.uint32))   # slice on the device: a full SA is 12 GB
+    return orc._Index(n=fmi.length, primary=fmi.primary, bwt_occ=fmi.bwt_occ.cpu().numpy().view(np.uint32), ssa=ssa16,
+                      L2=np.array(fmi.L2, dtype=np.uint32))
+
+
+def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True, parity_with=None):
+    """the reference's CPU path (oracle/_ref if present, else the C port) on a bounded sample per step.
+    parity_with = (nb, params): afterwards (untimed) the last sample's reads also go through nvb_seed_extend over THIS run's device
+    index and every per-hit score, the hit count and the best score per read are compared with the reference's"""
     from oracle import orc
     from oracle.cpu_pipeline import cpu_seed_extend
     from nvbio_b200 import synth
@@ -196,10 +210,7 @@ def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
         thread_options = [n_thr] + ([n_thr // 2] if n_thr >= 4 else [])
         E.set_num_threads(thread_options[0])
     cores = thread_options[0] if E.kind == "reference" else 1
-    host = fmi.to_host()
-    # the reference's index format samples the SA every 16 rows (SA_INT): slice the device index's denser array
-    ssa16 = np.ascontiguousarray(host["ssa"][::16 // host["sa_interval"]])
-    idx = orc._Index(n=host["n"], primary=host["primary"], bwt_occ=host["bwt_occ"], ssa=ssa16, L2=host["L2"])
+    idx = host_reference_index(fmi)
     gw = genome.cpu().numpy().view(np.uint32)
     nsample = args.cpu_sample
     times, res = [], None
@@ -233,6 +244,21 @@ def cpu_reference_leg(args, n, genome, fmi, steps, warmup, want_blocks=True):
     if want_blocks:
         out["blocks_per_seed"] = blocks_per_seed
         out["tail_blocks_per_seed"] = tail_blocks_per_seed
+    if parity_with is not None:
+        nb, params = parity_with
+        from nvbio_b200.strings import PackedStringSet
+        rs = PackedStringSet.fixed(rw.reshape(-1), nsample, READ_LEN, stride=rw.shape[1] * 16)
+        a = nb.seed_extend(fmi, genome, rs, params, hit_capacity=24 * nsample)                    # the path the benchmark times
+        b = nb.seed_extend(fmi, genome, rs, params, hit_capacity=24 * nsample, keep_hits=True)    # per-hit outputs
+        torch.cuda.synchronize()
+        kept, total, jobs = [int(v) for v in a.n_hits.cpu()]
+        best_ok = bool(np.array_equal(a.best_score.cpu().numpy().astype(np.int64), res["best_score"]) and
+                       np.array_equal(b.best_score.cpu().numpy().astype(np.int64), res["best_score"]))
+        hits_ok = bool(kept == total == res["n_hits"] and np.array_equal(b.hit_score[:total].cpu().numpy(), res["hit_score"]))
+        out["parity"] = {"ok": bool(best_ok and hits_ok), "reads": nsample, "hits": res["n_hits"], "best_score_per_read_identical": best_ok,
+                         "per_hit_scores_and_hit_count_identical": hits_ok,
+                         "against": "%s (nvbio::match -> locate -> aln::banded_alignment_score<31> -> max per read) over the same %d bp index in the "
+                                    "reference's format; device index: sa_interval=%d, ktab_k=%d" % (E.kind, n, fmi.sa_interval, fmi.ktab_k)}
     return out
 
 
@@ -258,7 +284,8 @@ def run_reference(args):
         "impl": "reference", "metric": "Mreads/s (150bp) seed+extend", "value": r["value"], "unit": "Mreads/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, n, args.cpu_sample, world=1),
+        "config": workload_config(args, n, args.reads, world=args.gpus),
+        "index": index_description(16, 0, n),
         "cpu_baseline": {"value": r["value"], "unit": "Mreads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                          "fm_match_Mseeds_s": r["mseeds_per_s"], "banded_gotoh_GCUPS": r["gcups"]},
         "e2e": {"value": r["value"], "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -267,12 +294,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n, reads_per_gpu, world):
-    return {"workload": "nvBowtie seed-and-extend: %d x %dbp single-end reads per GPU, %dbp seeds every %dbp on both strands, "
-                        "band=%d Gotoh LOCAL (2,-2,-5,-3), synthetic %.0f Mbp 2-bit genome / FM-index (occ every 64, SA every 16)"
-                        % (reads_per_gpu, READ_LEN, SEED_LEN, SEED_INTERVAL, BAND, n / 1e6),
-            "reads_per_gpu_per_step": reads_per_gpu, "genome_bp": n, "parallelism": "dp%d (index replicated by one NCCL broadcast)" % world,
-            "l2": "index (%.2f GB) and SSA exceed L2; a 512 MiB buffer is overwritten between timed steps" % (n / 64 * 32 / 1e9)}
+def workload_config(args, n, reads_per_gpu, world, index=None):
+    """`workload` names the job (the same for both arms); `index` says how THIS arm holds the FM-index"""
+    cfg = {"workload": "nvBowtie seed-and-extend: %d x %dbp single-end reads per GPU, %dbp seeds every %dbp on both strands, "
+                       "band=%d Gotoh LOCAL (2,-2,-5,-3), synthetic %.0f Mbp 2-bit genome, FM-index = 32-byte {bwt,occ} blocks (occ every 64)"
+                       % (reads_per_gpu, READ_LEN, SEED_LEN, SEED_INTERVAL, BAND, n / 1e6),
+           "reads_per_gpu_per_step": reads_per_gpu, "genome_bp": n, "parallelism": "dp%d (index replicated by one NCCL broadcast)" % world,
+           "l2": "index (%.2f GB of blocks alone) exceeds L2; a 512 MiB buffer is overwritten between timed steps" % (n / 64 * 32 / 1e9)}
+    if index is not None:
+        cfg["index"] = index
+    return cfg
+
+
+def index_description(sa_interval, ktab_k, n, nbytes=None):
+    d = {"sa_interval": sa_interval, "ktab_k": ktab_k,
+         "layout": "%s + %s" % ("full suffix array (4 B per base)" if sa_interval == 1 else "SA sampled every %d rows" % sa_interval,
+                                ("%d-mer SA-range table (4^%d x 8 B = %.1f GB)" % (ktab_k, ktab_k, 4 ** ktab_k * 8 / 1e9)) if ktab_k else "no k-mer table (the reference's format)")}
+    if nbytes is not None:
+        d["bytes_per_gpu"] = int(nbytes)
+    return d
 
 
 def c1_config(device, best_ms):
@@ -400,6 +440,25 @@ def other_configs(device):
         sweep["band_%d" % band] = {"GCUPS": n_al * M * band / (ms * 1e-3) / 1e9, "ms": ms}
     out["banded_gotoh_local_10Mx151bp_300bp_windows"] = dict(sweep, scheme="SimpleGotohScheme(2,-2,-5,-3)",
                                                              note="cells = n x 151 x BAND_LEN; integer-issue bound")
+    # ---- the reference's own CUDA kernels recompiled for sm_100a, same inputs, same run ----
+    del P, T, res, rw, pos, begin
+    torch.cuda.empty_cache()
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("compare_ref_cuda", os.path.join(ROOT, "tools", "compare_ref_cuda.py"))
+        crc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(crc)
+        if os.path.exists(crc.BIN):
+            fmi2, _ = nb.FMIndexDevice.from_text(gw, n)
+            out["vs_reference_cuda_sm100a"] = {
+                "banded_gotoh_1Mx150bp_band31": crc.banded_compare(gw, n, 1_000_000, 150),
+                "fm_index_filter_rank_locate_1Mx22bp": crc.fm_compare(fmi2, gw, n, 1_000_000, 22),
+                "note": "oracle/_ref/ref_cuda_bench = nvbio's batched_banded_alignment_score_kernel / FMIndexFilterDevice compiled from the "
+                        "reference's headers for sm_100a; speedup = reference ms / nvbio_b200 ms on identical inputs, results bit-compared"}
+        else:
+            out["vs_reference_cuda_sm100a"] = {"unavailable": "oracle/_ref/ref_cuda_bench not built"}
+    except Exception as e:
+        out["vs_reference_cuda_sm100a"] = {"error": repr(e)[:300]}
     return out
 
 
@@ -450,7 +509,40 @@ def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
     truth = np.where(strand == 0, l[None, :] + READ_LEN, (l + f)[None, :])
     placed = np.abs(pos - truth) <= 8
     paired = flags != 0
-    return {"workload": "%d FR pairs (2 x %d bp) per GPU per step, fragments ~N(350,30), 1%% substitutions, 5%% of the second mates with 20%% "
+    # ---- the same job host to host: packed pairs from pinned host memory in, per-pair results in host memory out (C ABI nvb_pipeline) ----
+    e2e = None
+    try:
+        host = [words.cpu().pin_memory(), words2.cpu().pin_memory()]
+        st = nb.StreamingSeedExtend(fmi, genome, params, 2 * n_pairs, READ_LEN, wpr, hit_capacity=24 * 2 * n_pairs, depth=args.depth, pair=pair)
+
+        def run(k_steps):
+            q, chk = [], 0
+            for i in range(k_steps):
+                q.append(st.submit(host[i & 1]))
+                if len(q) == args.depth:
+                    chk += int(st.result(q.pop(0))["pair_flags"][0])
+            while q:
+                last = st.result(q.pop(0)); chk += int(last["pair_flags"][0])
+            return last
+        run(max(3, args.depth))
+        barrier(world)
+        k2 = min(k, 40)
+        t0 = time.perf_counter()
+        last = run(k2)
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3
+        barrier(world)
+        e_ms = nd.max_over_ranks(e_ms, device) / k2
+        e2e = {"Mreads_per_s": world * 2 * n_pairs / (e_ms * 1e-3) / 1e6, "Mpairs_per_s": world * n_pairs / (e_ms * 1e-3) / 1e6, "ms_per_step": e_ms,
+               "steps": k2, "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes, "depth": args.depth,
+               "job_seconds_at_this_rate": k * e_ms * 1e-3,
+               "api": "C ABI nvb_pipeline (paired mode) via nvbio_b200.StreamingSeedExtend, wall clock over the steps, max over ranks"}
+        st.close()
+    except Exception as e:
+        if world > 1:
+            raise
+        e2e = {"error": repr(e)[:300]}
+    return {"e2e": e2e,"workload": "%d FR pairs (2 x %d bp) per GPU per step, fragments ~N(350,30), 1%% substitutions, 5%% of the second mates with 20%% "
                         "substitutions; both mates seeded+extended (band %d LOCAL), opposite-mate rescue by full-matrix Gotoh LOCAL in the "
                         "500 bp fragment window" % (n_pairs, READ_LEN, BAND),
             "Mreads_per_s": world * 2 * n_pairs / (ms * 1e-3) / 1e6, "Mpairs_per_s": world * n_pairs / (ms * 1e-3) / 1e6, "ms_per_step": ms, "n_gpus": world,
@@ -462,6 +554,98 @@ def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
             "rescue_cells": run * READ_LEN * 500, "hits_truncated": bool(kept != hits),
             "paired_and_both_mates_at_true_locus_frac": float((paired & placed[0] & placed[1]).mean()),
             "rank0_counts_only": True}
+
+
+def count_blocks(args, n, genome, fmi):
+    """algorithmic 32-byte blocks per seed of the reference algorithm (every LF step: its distinct {bwt,occ} blocks) and of
+    the steps left after the k-mer table look-up, counted exactly by the plain-C oracle on a sample of this workload's reads
+    (checker use: it counts, it is not timed).  The same count at every world size."""
+    from oracle import orc
+    nsample = min(args.cpu_sample, 5000)
+    O = orc.Oracle()
+    rw = make_reads(genome, n, nsample, 999, genome.device)
+    sym = _unpack_rows(rw.cpu().numpy().view(np.uint32), READ_LEN)
+    idx = host_reference_index(fmi, with_ssa=False)
+    strings = np.empty((2 * nsample, READ_LEN), np.uint8)
+    strings[0::2] = sym
+    strings[1::2] = (3 - sym)[:, ::-1]
+    K = (READ_LEN - SEED_LEN) // SEED_INTERVAL + 1
+    cols = (np.arange(K) * SEED_INTERVAL)[:, None] + np.arange(SEED_LEN)[None, :]
+    q = np.ascontiguousarray(strings[:, cols].reshape(-1))
+    nq = 2 * nsample * K
+    off = (np.arange(nq, dtype=np.uint32) * SEED_LEN).astype(np.uint32)
+    ln = np.full(nq, SEED_LEN, np.uint32)
+    _, blocks = O.match(idx, q, off, ln)
+    tail = blocks
+    if args.ktab_k:
+        _, tail = O.match(idx, q, off, ln, blocks_from_step=args.ktab_k)
+    return blocks / nq, tail / nq, nq
+
+
+def reference_format_fm_match(args, nb, fmi, n, genome, device, blocks_per_seed, peak):
+    """The kernel the north-star's HBM-roofline target names: backward search over the REFERENCE-FORMAT index (no k-mer table, HBM
+    resident: the 3 Gbp index's 1.5 GB of blocks), one launch of nvb_fm_match over this workload's 28 M 20-mers; algorithmic bytes =
+    32 B x distinct blocks per LF step (oracle count) + query + 8 B out."""
+    from nvbio_b200.strings import PackedStringSet
+    plain = nb.FMIndexDevice(fmi.bwt_occ, None, fmi.L2, n, fmi.primary, sa_interval=16)
+    n_reads = args.reads
+    rw = make_reads(genome, n, n_reads, 4242, device)
+    wpr = rw.shape[1]
+    K = (READ_LEN - SEED_LEN) // SEED_INTERVAL + 1
+    # seed k of read r = symbols [k*10, k*10+20) of the read's slot: an infix set over the packed reads
+    r = torch.arange(n_reads, device=device, dtype=torch.int64)[:, None] * (wpr * 16)
+    off = (r + torch.arange(K, device=device, dtype=torch.int64)[None, :] * SEED_INTERVAL).reshape(-1).to(torch.int32)
+    nq = n_reads * K
+    q = PackedStringSet(words=rw.reshape(-1), bits=2, big_endian=True, offsets=off, lengths=None, stride=0, length=SEED_LEN, count=nq)
+    ranges = torch.empty((nq, 2), dtype=torch.int32, device=device)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        nb.match(plain, q, out=ranges)
+    best = 1e30
+    for _ in range(5):
+        flush.zero_()
+        e0.record(); nb.match(plain, q, out=ranges); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    bps = 32.0 * blocks_per_seed + SEED_LEN * 2 / 8.0 + 8.0
+    gbs = nq * bps / (best * 1e-3) / 1e9
+    found = float((ranges[:, 0].to(torch.int64) & 0xFFFFFFFF <= (ranges[:, 1].to(torch.int64) & 0xFFFFFFFF)).float().mean())
+    return {"kernel": "fm_match_kernel (nvb_fm_match, reference-format index: no k-mer table)", "seeds": nq, "ms": best,
+            "Mseeds_per_s": nq / (best * 1e-3) / 1e6, "algorithmic_bytes_per_seed": bps, "blocks_per_seed": blocks_per_seed,
+            "achieved_GBs": gbs, "peak_GBs": peak, "frac": gbs / peak, "index_bytes": int(fmi.bwt_occ.numel() * 4),
+            "seeds_found_frac": found,
+            "note": "forward-strand 20-mers of %d reads (every one occurs in the genome up to the reads' 1%% substitutions); L2 flushed before every launch" % n_reads}
+
+
+def e2e_single(args, nb, fmi, genome, params, batches, n_reads, wpr, hit_capacity, world, nd, device, depth):
+    """host-to-host through the C ABI's nvb_pipeline (nvbio_b200.StreamingSeedExtend): every step copies ITS packed reads from pinned
+    host memory, runs the hot path and copies the per-read (score, position) back; `depth` batches in flight"""
+    host_reads = [b.cpu().pin_memory() for b in batches]
+    stream = nb.StreamingSeedExtend(fmi, genome, params, n_reads, READ_LEN, wpr, hit_capacity=hit_capacity, depth=depth)
+    last = {}
+
+    def run(k_steps):
+        q, chk = [], 0
+        for i in range(k_steps):
+            q.append(stream.submit(host_reads[i % 2]))
+            if len(q) == depth:
+                sc, _, nh = stream.result(q.pop(0)); chk += int(sc[0]) + int(nh[0])      # the host really reads the results
+        while q:
+            sc, _, nh = stream.result(q.pop(0)); chk += int(sc[0]) + int(nh[0])
+        last["score"] = sc.clone()
+        return chk
+    run(max(args.warmup, depth))
+    barrier(world)
+    t0 = time.perf_counter()
+    run(args.steps)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier(world)
+    ms = nd.max_over_ranks(ms, device) / args.steps
+    found = float((last["score"] > READ_LEN).float().mean())
+    h2d, d2h = stream.h2d_bytes, stream.d2h_bytes
+    stream.close()
+    return ms, h2d, d2h, found
 
 
 def run_ours(args):
@@ -523,37 +707,16 @@ def run_ours(args):
     value = world * n_reads / (ms_per_step * 1e-3) / 1e6
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
 
-    # ---- end to end through the public API with host buffers -----------------------------------
-    # StreamingSeedExtend: every step copies ITS packed reads from pinned host memory, runs the hot path and copies the
-    # per-read (score, position) back; with depth 2 the copies of one step overlap the kernels of its neighbour.
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
     # Inputs arrive from the host every step and the index (+SA +table) is far larger than L2, so no flush is needed here.
-    from nvbio_b200.pipeline import StreamingSeedExtend
-    host_reads = [b.cpu().pin_memory() for b in batches]
     del ws
     torch.cuda.empty_cache()
-    stream = StreamingSeedExtend(fmi, genome, params, n_reads, READ_LEN, wpr, hit_capacity=hit_capacity, depth=2)
-
-    def e2e_run(k_steps):
-        prev, chk = None, 0
-        for i in range(k_steps):
-            t = stream.submit(host_reads[i % 2])
-            if prev is not None:
-                sc, _, nh = stream.result(prev); chk += int(sc[0]) + int(nh[0])      # the host really reads the results
-            prev = t
-        sc, _, nh = stream.result(prev); chk += int(sc[0]) + int(nh[0])
-        return chk
-    e2e_run(args.warmup)
-    barrier(world)
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    barrier(world)
-    e2e_ms = nd.max_over_ranks(e2e_ms, device) / args.steps
+    e2e_ms, h2d, d2h, found = e2e_single(args, nb, fmi, genome, params, batches, n_reads, wpr, hit_capacity, world, nd, device, args.depth)
     e2e_value = world * n_reads / (e2e_ms * 1e-3) / 1e6
-    h2d = batches[0].numel() * 4
-    d2h = n_reads * 8 + 12
-    found = float((stream.slots[0]["host_score"] > READ_LEN).float().mean())
+    e2e_alt = None
+    if world == 1 and args.depth != 1:                  # the same with one batch in flight (no cross-batch overlap), for the record
+        ms1, _, _, _ = e2e_single(args, nb, fmi, genome, params, batches, n_reads, wpr, hit_capacity, world, nd, device, 1)
+        e2e_alt = {"depth": 1, "ms_per_step": ms1, "value": n_reads / (ms1 * 1e-3) / 1e6}
 
     # ---- paired-end composition (C5 shape), every world size --------------------------------------
     paired = None
@@ -568,19 +731,15 @@ def run_ours(args):
             paired = {"error": repr(e)[:300]}
     if rank != 0:
         return
-    # ---- CPU baseline + algorithmic bytes (rank 0, N=1 only) ----------------------------------
-    cpu = None
+    # ---- algorithmic bytes (rank 0, every N: the same oracle count), CPU baseline + parity on this very configuration (N=1) ----
     n_seeds = 2 * n_reads * ((READ_LEN - SEED_LEN) // SEED_INTERVAL + 1)
-    blocks_per_seed = tail_blocks = None
+    blocks_per_seed, tail_blocks, _ = count_blocks(args, n, genome, fmi)
+    cpu = parity = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_leg(args, n, genome, fmi, steps=1, warmup=1, want_blocks=True)
-        blocks_per_seed, tail_blocks = r["blocks_per_seed"], r["tail_blocks_per_seed"]
+        r = cpu_reference_leg(args, n, genome, fmi, steps=1, warmup=1, want_blocks=False, parity_with=(nb, params))
         cpu = {"value": r["value"], "unit": "Mreads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "fm_match_Mseeds_s": r["mseeds_per_s"], "banded_gotoh_GCUPS": r["gcups"]}
-    if blocks_per_seed is None:
-        # (L-1) + log4(n/64) blocks per seed: the closed form SURVEY.md 8d fits to the exact counts
-        blocks_per_seed = (SEED_LEN - 1) + float(np.log(max(n / 64.0, 1.0)) / np.log(4.0))
-        tail_blocks = max(blocks_per_seed - 2.0 * args.ktab_k + 1.0, 1.0) if args.ktab_k else blocks_per_seed
+        parity = r.get("parity")
     peak, peak_src = measured_peaks()
     # reference algorithm: every LF step fetches its distinct 32-byte blocks.  This kernel replaces the first
     # k steps by one 8-byte table entry (one 32-byte sector), so ITS necessary traffic is the tail blocks + that sector.
@@ -589,12 +748,16 @@ def run_ours(args):
     fm_ms = stage_ms["seed_match"]
     achieved = n_seeds * bytes_per_seed / (fm_ms * 1e-3) / 1e9
     cells = jobs * READ_LEN * BAND
+    idx_desc = index_description(fmi.sa_interval, fmi.ktab_k, n, fmi.nbytes() + genome.numel() * 4)
     line = {
         "metric": "Mreads/s (150bp) seed+extend", "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": workload_config(args, n, n_reads, world),
+        "index": idx_desc,
         "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "api": "nvbio_b200.StreamingSeedExtend (pinned host in/out, depth-2 pipelining, wall clock over K steps)"},
+                "api": "C ABI nvb_pipeline_submit / nvb_pipeline_wait via nvbio_b200.StreamingSeedExtend (pinned host in/out, %d batches in flight on "
+                       "separate compute streams, wall clock over K steps)" % args.depth,
+                "depth": args.depth, "one_batch_in_flight": e2e_alt},
         "gpu_launches": (9 if params.dedup_jobs else 8) * args.steps,      # own kernels per step on the per-read path (the cub scan not counted)
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
@@ -604,23 +767,31 @@ def run_ours(args):
                      "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": tail_blocks,
                      "reference_algorithm_bytes_per_seed": ref_bytes_per_seed, "reference_algorithm_blocks_per_seed": blocks_per_seed,
                      "reference_algorithm_equiv_GBs": n_seeds * ref_bytes_per_seed / (fm_ms * 1e-3) / 1e9,
-                     "note": "32 B x distinct {bwt,occ} blocks per LF step after the %d-mer table look-up (oracle count on the CPU "
-                             "sample) + one 32 B table sector + query + 8 B out; the reference algorithm (no table) needs "
+                     "note": "32 B x distinct {bwt,occ} blocks per LF step after the %d-mer table look-up (plain-C oracle count on a read sample of this "
+                             "workload, the same at every N) + one 32 B table sector + query + 8 B out; the reference algorithm (no table) needs "
                              "reference_algorithm_bytes_per_seed" % args.ktab_k},
         "stage_ms": stage_ms,
         "fm_match_Mseeds_s": n_seeds / (fm_ms * 1e-3) / 1e6,
         "banded_gotoh": {"alignments_per_step": hits, "distinct_jobs_scored": jobs, "GCUPS": cells / (stage_ms["extend"] * 1e-3) / 1e9,
                          "band": BAND, "note": "cells = distinct jobs x 150 x 31; integer-issue bound (DPX s16x2), not HBM"},
         "reads_found_frac": found,
-        "index": {"build_s": t_build, "broadcast_s": t_bcast, "bytes": fmi.nbytes() + genome.numel() * 4,
-                  "sa_interval": fmi.sa_interval, "ktab_k": fmi.ktab_k},
+        "index_build": {"build_s": t_build, "broadcast_s": t_bcast},
     }
+    if parity is not None:
+        line["parity_on_headline_config"] = parity["ok"]
+        line["parity"] = parity
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if paired is not None:
         line["paired_end"] = paired
     if world == 1 and not args.no_other_configs:
-        del stream, batches, flush
+        del batches, flush
+        torch.cuda.empty_cache()
+        try:
+            line["fm_match_reference_format"] = reference_format_fm_match(args, nb, fmi, n, genome, device, blocks_per_seed, peak)
+        except Exception as e:
+            line["fm_match_reference_format"] = {"error": repr(e)[:300]}
+        del fmi, genome
         torch.cuda.empty_cache()
         try:
             line["other_configs"] = other_configs(device)

@@ -7,6 +7,11 @@
  *
  * Every entry point names the reference interface it replaces (paths relative to the nvbio tree).
  * INTEGRATION.md shows the reference-side binding for each.
+ *
+ * Threads and devices.  Every call works on the CURRENT device of the calling thread (cudaSetDevice), and all `d_` pointers must
+ * belong to it.  The library keeps no state between calls except, per device, lazily-created profiling events and kernel
+ * attributes (both guarded; a host that drives several GPUs from one process -- nvBowtie's one compute thread per device -- may
+ * call from all of its threads at once).  Two concurrent calls must not share output or temp buffers.
  */
 #ifndef NVBIO_B200_H
 #define NVBIO_B200_H
@@ -341,6 +346,10 @@ int nvb_seed_extend_traceback(const nvb_fm_index* fmi, const uint32_t* d_genome,
  *     the other mate forward in [max(e - max_frag, 0), e)  (score_opposite_inl.h:177-191 with pe_overlap).  A rescue whose
  *     score reaches min_mate_score yields a candidate pair; the candidate with the larger score sum wins (tie: mate 1 as
  *     anchor).  No candidate: the pair is UNPAIRED and each mate keeps its own best alignment.
+ * A mate's alignment BEGIN is taken as (end - read length, clamped at 0), not from a traceback: with soft clips or indels the true
+ * start differs by a few bases, so pairs within that distance of min_frag / max_frag may be classified differently from a
+ * caller that traces every alignment (nvBowtie does); callers that need the exact extent can request the traceback
+ * (nvb_seed_extend_traceback) and re-check those pairs.
  * At most rescue_capacity full-DP jobs are run per call (in pair order; d_n_rescue[1] reports how many were wanted).
  * Outputs (mate m of pair p at index m*n_pairs + p): d_pair_score (sum of the two mates' scores, INT_MIN when unpaired),
  * d_pair_flags (NVB_PAIR_*), d_mate_score (INT_MIN = unaligned), d_mate_pos (genome coordinate one past the last aligned
@@ -368,6 +377,44 @@ int nvb_seed_extend_paired(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_seed_extend_params* params, uint32_t hit_capacity,
                     const nvb_pair_params* pair_params, const nvb_pair_out* out,
                     uint32_t* d_n_hits, void* d_temp, size_t* temp_bytes, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Host-buffer entry point: batches of reads in HOST memory in, per-read results in HOST memory out.
+ * Replaces nvBowtie's input thread -> compute thread hand-off and its per-stage cudaDeviceSynchronize
+ * (nvBowtie/bowtie2/cuda/compute_thread.cu:213-243, nvBowtie/bowtie2/cuda/defs.h:64, aligner_best_approx.h:219-241):
+ * `depth` batches are in flight at once -- the host->device copy of batch i+1 and the device->host copy of batch i-1
+ * overlap the kernels of batch i on separate streams, and consecutive batches run on DIFFERENT compute streams, so the
+ * memory-latency-bound seed search of one batch and the integer-issue-bound extension of its neighbour share the SMs.
+ *
+ * Reads: n_reads fixed-stride strings of `read_len` symbols, `words_per_read` 32-bit words each (big-endian packing,
+ * read_bits = 2 or 4).  pair_params != NULL: paired-end (reads = mate 1 of every pair, then mate 2; n_reads even).
+ * submit() takes a host pointer (pinned memory makes the copy asynchronous) that must stay valid until wait() returns for
+ * that ticket; wait() blocks until that batch's results are in the pipeline's own pinned host buffers and returns pointers
+ * to them (valid until `depth` further batches have been submitted).  One pipeline is used from one host thread.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nvb_pipeline nvb_pipeline;
+typedef struct nvb_pipeline_result {
+    const int32_t*  best_score;    /* [n_reads]  single end (NULL when paired) */
+    const uint32_t* best_pos;      /* [n_reads]  */
+    const uint32_t* n_hits;        /* [3] hits kept, found, distinct alignment jobs */
+    const int32_t*  pair_score;    /* [n_pairs]   paired end (NULL when single end), as nvb_pair_out */
+    const uint32_t* pair_flags;    /* [n_pairs]   */
+    const int32_t*  mate_score;    /* [2*n_pairs] */
+    const uint32_t* mate_pos;      /* [2*n_pairs] */
+    const uint8_t*  mate_strand;   /* [2*n_pairs] */
+    const uint32_t* n_rescue;      /* [2] */
+    float           device_ms;     /* device time of this batch's kernels (its compute stream), for reporting */
+} nvb_pipeline_result;
+
+int  nvb_pipeline_create(const nvb_fm_index* fmi, const uint32_t* d_genome, const nvb_seed_extend_params* params,
+                         const nvb_pair_params* pair_params /* NULL = single end */,
+                         uint32_t n_reads, uint32_t read_len, uint32_t words_per_read, uint32_t read_bits,
+                         uint32_t hit_capacity, uint32_t depth, nvb_pipeline** out);
+int  nvb_pipeline_submit(nvb_pipeline* p, const uint32_t* h_read_words, uint32_t* ticket);
+int  nvb_pipeline_wait(nvb_pipeline* p, uint32_t ticket, nvb_pipeline_result* out);
+/* bytes moved per batch: host -> device, device -> host */
+void nvb_pipeline_traffic(const nvb_pipeline* p, size_t* h2d_bytes, size_t* d2h_bytes);
+void nvb_pipeline_destroy(nvb_pipeline* p);
 
 /* Profiling aid (the reference wraps every stage in cuda::Timer, nvBowtie/bowtie2/cuda/aligner_best_approx.h:
  * 219-241): device time in ms of the seven stages of the most recent nvb_seed_extend call -- [fw,rc] strings,

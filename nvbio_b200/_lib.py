@@ -11,6 +11,7 @@ EXPORTS = [
     "nvb_fm_rank", "nvb_fm_rank4", "nvb_fm_match", "nvb_fm_match_approx", "nvb_fm_locate", "nvb_fm_filter_rank", "nvb_fm_filter_locate",
     "nvb_banded_gotoh_score", "nvb_banded_gotoh_score_indirect", "nvb_banded_gotoh_traceback", "nvb_gotoh_score", "nvb_gotoh_score_indirect", "nvb_banded_gotoh_score_window", "nvb_gotoh_traceback", "nvb_seed_extend_paired",
     "nvb_fm_build_occ", "nvb_fm_build_bwt", "nvb_fm_build_ktab", "nvb_seed_extend", "nvb_seed_extend_traceback", "nvb_seed_extend_stage_ms",
+    "nvb_pipeline_create", "nvb_pipeline_submit", "nvb_pipeline_wait", "nvb_pipeline_traffic", "nvb_pipeline_destroy",
 ]
 
 
@@ -56,6 +57,12 @@ class PairOutStruct(C.Structure):           # nvb_pair_out
                 ("d_mate_strand", C.c_void_p), ("d_n_rescue", C.c_void_p)]
 
 
+class PipelineResultStruct(C.Structure):    # nvb_pipeline_result
+    _fields_ = [("best_score", C.c_void_p), ("best_pos", C.c_void_p), ("n_hits", C.c_void_p), ("pair_score", C.c_void_p),
+                ("pair_flags", C.c_void_p), ("mate_score", C.c_void_p), ("mate_pos", C.c_void_p), ("mate_strand", C.c_void_p),
+                ("n_rescue", C.c_void_p), ("device_ms", C.c_float)]
+
+
 _lib = None
 
 
@@ -67,6 +74,8 @@ def lib():
                            "(there is no CPU fallback)" % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
         _lib.nvb_error_string.restype = C.c_char_p
+        _lib.nvb_pipeline_destroy.restype = None
+        _lib.nvb_pipeline_traffic.restype = None
         for name in EXPORTS:
             getattr(_lib, name)            # raises AttributeError if a symbol is not exported
     return _lib

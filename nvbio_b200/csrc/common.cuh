@@ -10,6 +10,8 @@
 
 namespace nvb {
 
+constexpr int NVB_MAX_DEVICES = 64;      // per-device state (function attributes, stage events) is kept in arrays of this size
+
 #define NVB_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return (int)_e; } while (0)
 #define NVB_LAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return (int)_e; } while (0)
 

@@ -101,6 +101,7 @@ fm_filter_locate_kernel(const FmIndex f, const uint2* __restrict__ ranges, const
     if (t >= count) return;
     const uint64_t h = begin + t;
     const uint32_t slot = upper_bound_u64(slots, n_queries, h);
+    if (slot >= n_queries) { hits[t] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); return; }   // h beyond the last hit: no row to locate
     const uint64_t base = slot ? slots[slot - 1] : 0ull;
     const uint32_t row = ranges[slot].x + (uint32_t)(h - base);
     hits[t] = make_uint2(fm_locate_one(f, row), slot);

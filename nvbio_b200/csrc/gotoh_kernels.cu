@@ -8,6 +8,7 @@
 //
 // The path is bound by integer issue rate, not memory: ~0.1 KB moved per 4,650 cell updates (B=31, M=150).
 #include "gotoh_core.cuh"
+#include <atomic>
 #include "../../include/nvbio_b200_debug.h"
 #include "gotoh_full_core.cuh"
 
@@ -476,10 +477,15 @@ template <int B, int TYPE>
 static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
 {
     const size_t smem = (size_t)sel_rows * PAIR_BLOCKDIM * sizeof(uint16_t);
-    static bool attr_done = false;      // per instantiation
-    if (!attr_done) {
+    // the attribute is per DEVICE: a host that drives several GPUs from one process (nvBowtie's one compute thread per
+    // device) must set it on each; one atomic flag per (instantiation, device)
+    static std::atomic<bool> attr_done[NVB_MAX_DEVICES];
+    int dev = 0;
+    NVB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= NVB_MAX_DEVICES) return NVB_E_UNSUPPORTED;
+    if (!attr_done[dev].load(std::memory_order_acquire)) {
         NVB_CUDA_TRY(cudaFuncSetAttribute(gotoh_pair_kernel<B, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        attr_done[dev].store(true, std::memory_order_release);
     }
     const uint32_t pairs = (b.n_max + 1u) / 2u;
     const uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;

@@ -12,6 +12,7 @@
 #include "fm_core.cuh"
 #include "gotoh_core.cuh"
 #include <cub/device/device_scan.cuh>
+#include <mutex>
 
 namespace nvb {
 
@@ -433,8 +434,8 @@ pipe_export_hits_kernel(const PipeGeom g, const uint32_t* __restrict__ counts, c
 struct MateBest { bool has; int32_t score; uint32_t strand, beg, end, len; };
 
 // the best alignment of read r as the single-end stages left it: score, end (one past the last aligned base), strand
-__device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, const int32_t* __restrict__ best_score,
-                                              const uint32_t* __restrict__ best_pos, const uint8_t* __restrict__ best_strand,
+__device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, const int32_t* best_score,
+                                              const uint32_t* best_pos, const uint8_t* __restrict__ best_strand,
                                               const uint32_t* __restrict__ str_len)
 {
     MateBest m; m.has = false; m.score = INT_MIN; m.strand = 0; m.beg = m.end = 0xFFFFFFFFu; m.len = 0;
@@ -452,11 +453,13 @@ __device__ __forceinline__ MateBest mate_best(const PipeGeom& g, uint32_t r, con
 // one thread per pair: concordance of the independent best alignments, else up to two opposite-mate jobs (slot 2p + anchor)
 __global__ void __launch_bounds__(256)
 pair_classify_kernel(const PipeGeom g, const uint32_t n_pairs, const nvb_pair_params pp,
-                     const int32_t* __restrict__ best_score, const uint32_t* __restrict__ best_pos, const uint8_t* __restrict__ best_strand,
+                     // best_score / best_pos ARE mate_score / mate_pos in the paired entry point (the single-end stage writes the per-read
+                     // bests straight into the mate arrays): no __restrict__ / const on either view
+                     const int32_t* best_score, const uint32_t* best_pos, const uint8_t* __restrict__ best_strand,
                      const uint32_t* __restrict__ str_len,
                      uint32_t* __restrict__ want, uint32_t* __restrict__ w_pstr, uint32_t* __restrict__ w_toff, uint32_t* __restrict__ w_tlen,
                      int32_t* __restrict__ pair_score, uint32_t* __restrict__ pair_flags,
-                     int32_t* __restrict__ mate_score, uint32_t* __restrict__ mate_pos, uint8_t* __restrict__ mate_strand)
+                     int32_t* mate_score, uint32_t* mate_pos, uint8_t* __restrict__ mate_strand)
 {
     const uint32_t p = blockIdx.x * 256 + threadIdx.x;
     if (p >= n_pairs) return;
@@ -548,18 +551,38 @@ pair_finalize_kernel(const uint32_t n_pairs, const nvb_pair_params pp, const uin
 
 using namespace nvb;
 
-// stage boundaries of the most recent nvb_seed_extend call (events are recorded on the caller's stream; they
-// cost no synchronisation).  [0]=start, then after: strings, seed match, slots, locate+windows, job dedup, extension, reduce
-static cudaEvent_t g_stage_ev[8];
-static bool g_stage_ev_ready = false;
-static bool g_stage_ev_valid = false;
-#define NVB_STAGE(i) do { if (g_stage_ev_ready) NVB_CUDA_TRY(cudaEventRecord(g_stage_ev[i], s)); } while (0)
+// stage boundaries of the most recent nvb_seed_extend call ON EACH DEVICE (events are recorded on the caller's stream; they
+// cost no synchronisation).  [0]=start, then after: strings, seed match, slots, locate+windows, job dedup, extension, reduce.
+// Events belong to the device that created them, so the set is per device, created under a mutex on first use; a host that
+// drives several GPUs from one process (one compute thread per device) gets one set per GPU.  Callers that run several
+// batches of one device concurrently (nvb_pipeline) pass their own events instead.
+struct StageEvents { cudaEvent_t ev[8]; bool ready, valid; };
+static StageEvents g_stage[NVB_MAX_DEVICES];
+static std::mutex  g_stage_mutex;
+static int default_stage_events(StageEvents** out)
+{
+    int dev = 0;
+    NVB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= NVB_MAX_DEVICES) return NVB_E_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    StageEvents& S = g_stage[dev];
+    if (!S.ready) {
+        for (int i = 0; i < 8; ++i) NVB_CUDA_TRY(cudaEventCreate(&S.ev[i]));
+        S.ready = true;
+    }
+    *out = &S;
+    return NVB_OK;
+}
+#define NVB_STAGE(i) do { NVB_CUDA_TRY(cudaEventRecord(SE->ev[i], s)); } while (0)
 
 extern "C" int nvb_seed_extend_stage_ms(float ms[7])
 {
-    if (!ms || !g_stage_ev_valid) return NVB_E_INVALID;
-    NVB_CUDA_TRY(cudaEventSynchronize(g_stage_ev[7]));
-    for (int i = 0; i < 7; ++i) NVB_CUDA_TRY(cudaEventElapsedTime(&ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
+    if (!ms) return NVB_E_INVALID;
+    StageEvents* SE = nullptr;
+    { const int r = default_stage_events(&SE); if (r != NVB_OK) return r; }
+    if (!SE->valid) return NVB_E_INVALID;
+    NVB_CUDA_TRY(cudaEventSynchronize(SE->ev[7]));
+    for (int i = 0; i < 7; ++i) NVB_CUDA_TRY(cudaEventElapsedTime(&ms[i], SE->ev[i], SE->ev[i + 1]));
     return NVB_OK;
 }
 
@@ -599,6 +622,8 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     const uint64_t nq64 = (uint64_t)g.n_strings * g.seeds_per_string;
     if (nq64 > 0x7FFFFFFFull) return NVB_E_UNSUPPORTED;
     const uint32_t nq = (uint32_t)nq64;
+    // hit slots are a uint32 exclusive sum of the clamped range sizes: the worst case must fit
+    if (nq64 * (uint64_t)P->max_seed_hits > 0xFFFFFFFFull) return NVB_E_UNSUPPORTED;
 
     // the extension's own temp requirement
     nvb_string_set pats, txts;
@@ -690,10 +715,8 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     cudaStream_t s = as_stream(stream);
     const FmIndex f = make_fmindex(fmi);
     const StrSet rd = make_strset(reads);
-    if (!g_stage_ev_ready) {
-        for (int i = 0; i < 8; ++i) NVB_CUDA_TRY(cudaEventCreate(&g_stage_ev[i]));
-        g_stage_ev_ready = true;
-    }
+    StageEvents* SE = nullptr;
+    { const int r = default_stage_events(&SE); if (r != NVB_OK) return r; }
     NVB_STAGE(0);
 
     // 1. [fw, rc] strings
@@ -853,7 +876,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     if (!dedup) NVB_CUDA_TRY(cudaMemcpyAsync(counts + 2, counts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     if (d_n_hits) NVB_CUDA_TRY(cudaMemcpyAsync(d_n_hits, counts, 3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     NVB_STAGE(7);
-    g_stage_ev_valid = true;
+    SE->valid = true;
     return NVB_OK;
 }
 

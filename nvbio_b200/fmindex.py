@@ -217,6 +217,8 @@ class FMIndexFilterDevice:
     def locate(self, begin: int, end: int, hits: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self._fmi is None:
             raise NvbError("FMIndexFilterDevice.locate() before rank()")
+        if not (0 <= begin <= end <= self._n_hits):
+            raise NvbError("FMIndexFilterDevice.locate: [begin, end) must lie inside [0, n_hits()]")
         if hits is None:
             hits = torch.empty((end - begin, 2), dtype=torch.int32, device=self._fmi.device)
         s = self._fmi.struct()

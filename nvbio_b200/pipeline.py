@@ -177,62 +177,74 @@ def last_stage_ms():
     return dict(zip(STAGES, [float(v) for v in ms]))
 
 
-class StreamingSeedExtend:
-    """Host-to-host batches: the production entry point (nvBowtie's input thread -> compute thread hand-off,
-    nvBowtie/bowtie2/cuda/compute_thread.cu:213-243, without the per-stage cudaDeviceSynchronize).
+def _host_view(ptr, count, dtype):
+    """a torch tensor over `count` elements of pinned host memory owned by the C library (no copy)"""
+    nbytes = count * torch.tensor([], dtype=dtype).element_size()
+    buf = (C.c_char * nbytes).from_address(ptr)
+    return torch.frombuffer(buf, dtype=dtype, count=count)
 
-    `submit(host_words)` enqueues H2D copy -> seed_extend -> D2H copy of (best_score, best_pos) on three streams
-    and returns a ticket; `result(ticket)` waits for that batch only.  With depth >= 2 the copies of one batch
-    overlap the kernels of its neighbours.  host_words must be a pinned int32 tensor [n_reads, words_per_read]."""
+
+class StreamingSeedExtend:
+    """Host-to-host batches through the C ABI's nvb_pipeline (include/nvbio_b200.h): the production entry point that replaces
+    nvBowtie's input thread -> compute thread hand-off (nvBowtie/bowtie2/cuda/compute_thread.cu:213-243) and its per-stage
+    cudaDeviceSynchronize.
+
+    `submit(host_words)` enqueues H2D copy -> seed_extend[_paired] -> D2H copy of the per-read results and returns a ticket;
+    `result(ticket)` waits for that batch only.  `depth` batches are in flight: copies overlap kernels, and consecutive batches
+    run on different compute streams.  host_words: int32 tensor [n_reads, words_per_read] in host memory (pinned = async copy).
+    pair: PairParams for paired-end batches (reads = mate 1 of every pair, then mate 2)."""
 
     def __init__(self, fmi: FMIndexDevice, genome: torch.Tensor, params: SeedExtendParams, n_reads: int, read_len: int,
-                 words_per_read: int, hit_capacity: Optional[int] = None, depth: int = 2, bits: int = 2):
-        self.fmi, self.genome, self.params = fmi, genome, params
-        self.n_reads, self.read_len, self.wpr, self.bits = n_reads, read_len, words_per_read, bits
-        dev = fmi.device
-        self.h2d, self.compute, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+                 words_per_read: int, hit_capacity: Optional[int] = None, depth: int = 2, bits: int = 2, pair: Optional["PairParams"] = None):
+        self.fmi, self.genome, self.params, self.pair = fmi, genome, params, pair          # keep the device buffers alive
+        self.n_reads, self.read_len, self.wpr, self.bits, self.depth = n_reads, read_len, words_per_read, bits, depth
         if hit_capacity is None:
             hit_capacity = 32 * n_reads + 1024
-        self.slots = []
-        for _ in range(depth):
-            dev_in = torch.empty((n_reads, words_per_read), dtype=torch.int32, device=dev)
-            rs = self._as_set(dev_in)
-            ws = SeedExtendWorkspace(fmi, genome, rs, params, hit_capacity, keep_hits=False)
-            self.slots.append(dict(dev_in=dev_in, rs=rs, ws=ws,
-                                   host_score=torch.empty(n_reads, dtype=torch.int32).pin_memory(),
-                                   host_pos=torch.empty(n_reads, dtype=torch.int32).pin_memory(),
-                                   host_nhits=torch.empty(3, dtype=torch.int32).pin_memory(),
-                                   ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False))
-        self._next = 0
-
-    def _as_set(self, words):
-        spw = 32 // self.bits
-        return PackedStringSet.fixed(words.reshape(-1), self.n_reads, self.read_len, stride=self.wpr * spw, bits=self.bits)
+        self._params_struct = params.struct()
+        s = fmi.struct()
+        pp = pair.struct(n_reads // 2) if pair is not None else None
+        self._h = C.c_void_p()
+        with torch.cuda.device(fmi.device):
+            check(lib().nvb_pipeline_create(C.byref(s), C.c_void_p(genome.data_ptr()), C.byref(self._params_struct),
+                                            C.byref(pp) if pp is not None else None,
+                                            C.c_uint32(n_reads), C.c_uint32(read_len), C.c_uint32(words_per_read), C.c_uint32(bits),
+                                            C.c_uint32(hit_capacity), C.c_uint32(depth), C.byref(self._h)), "nvb_pipeline_create")
+        h2d, d2h = C.c_size_t(0), C.c_size_t(0)
+        lib().nvb_pipeline_traffic(self._h, C.byref(h2d), C.byref(d2h))
+        self.h2d_bytes, self.d2h_bytes = int(h2d.value), int(d2h.value)
+        self._keep = {}
+        self.last_device_ms = None
 
     def submit(self, host_words: torch.Tensor) -> int:
-        k = self._next % len(self.slots)
-        self._next += 1
-        s = self.slots[k]
-        if s["busy"]:
-            s["ev_out"].synchronize()           # the slot's previous results must have left the device
-        with torch.cuda.stream(self.h2d):
-            s["dev_in"].copy_(host_words, non_blocking=True)
-            s["ev_in"].record(self.h2d)
-        with torch.cuda.stream(self.compute):
-            self.compute.wait_event(s["ev_in"])
-            seed_extend(self.fmi, self.genome, s["rs"], self.params, workspace=s["ws"])
-            s["ev_done"].record(self.compute)
-        with torch.cuda.stream(self.d2h):
-            self.d2h.wait_event(s["ev_done"])
-            s["host_score"].copy_(s["ws"].best_score, non_blocking=True)
-            s["host_pos"].copy_(s["ws"].best_pos, non_blocking=True)
-            s["host_nhits"].copy_(s["ws"].n_hits, non_blocking=True)
-            s["ev_out"].record(self.d2h)
-        s["busy"] = True
-        return k
+        assert not host_words.is_cuda and host_words.is_contiguous() and host_words.numel() == self.n_reads * self.wpr
+        t = C.c_uint32(0)
+        check(lib().nvb_pipeline_submit(self._h, C.c_void_p(host_words.data_ptr()), C.byref(t)), "nvb_pipeline_submit")
+        self._keep[int(t.value)] = host_words                # the copy is asynchronous: keep the source alive until result()
+        return int(t.value)
 
     def result(self, ticket: int):
-        s = self.slots[ticket]
-        s["ev_out"].synchronize()
-        s["busy"] = False
-        return s["host_score"], s["host_pos"], s["host_nhits"]
+        """single end: (best_score[n], best_pos[n], n_hits[3]); paired: dict of the nvb_pair_out arrays -- views of the pipeline's
+        pinned host buffers, valid until `depth` further batches have been submitted"""
+        from ._lib import PipelineResultStruct
+        r = PipelineResultStruct()
+        check(lib().nvb_pipeline_wait(self._h, C.c_uint32(ticket), C.byref(r)), "nvb_pipeline_wait")
+        self._keep.pop(ticket, None)
+        self.last_device_ms = float(r.device_ms)
+        n = self.n_reads
+        if self.pair is None:
+            return _host_view(r.best_score, n, torch.int32), _host_view(r.best_pos, n, torch.int32), _host_view(r.n_hits, 3, torch.int32)
+        return dict(pair_score=_host_view(r.pair_score, n // 2, torch.int32), pair_flags=_host_view(r.pair_flags, n // 2, torch.int32),
+                    mate_score=_host_view(r.mate_score, n, torch.int32).view(2, n // 2), mate_pos=_host_view(r.mate_pos, n, torch.int32).view(2, n // 2),
+                    mate_strand=_host_view(r.mate_strand, n, torch.uint8).view(2, n // 2), n_rescue=_host_view(r.n_rescue, 2, torch.int32),
+                    n_hits=_host_view(r.n_hits, 3, torch.int32))
+
+    def close(self):
+        if self._h:
+            lib().nvb_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

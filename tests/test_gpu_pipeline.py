@@ -224,6 +224,46 @@ def test_paired_end_vs_oracle():
             assert (fl == 1).sum() > 0.5 * n_pairs and ((fl == 2) | (fl == 4)).sum() > 0.1 * n_pairs and (fl == 0).sum() >= 10
 
 
+def test_streaming_paired_host_api():
+    """nvb_pipeline (host buffers in / out, several batches in flight on different compute streams) in paired-end mode ==
+    nvb_seed_extend_paired on the same batches, batch by batch, incl. the slot reuse after `depth` submissions"""
+    require_gpu()
+    n = 400_000
+    gw = synth.random_genome_words(n, seed=91)
+    fmi, _ = nb.FMIndexDevice.from_text(gw, n, sa_interval=1)
+    fmi.build_ktab(8)
+    n_pairs, L = 3000, 150
+    params = nb.SeedExtendParams()
+    pair = nb.PairParams(min_frag=0, max_frag=500, min_mate_score=80, rescue_capacity=1024)
+    batches, want = [], []
+    for b in range(5):
+        rw, _, _ = synth.sample_pairs(gw, n, n_pairs, L, frag_mean=350.0, frag_sd=30.0, sub_rate=0.01, hard_frac=0.1, hard_sub_rate=0.2,
+                                      seed=100 + b, mut_seed=200 + b)
+        rw = rw.contiguous()
+        rs = PackedStringSet.fixed(rw.reshape(-1), 2 * n_pairs, L, stride=rw.shape[1] * 16)
+        ws = nb.seed_extend_paired(fmi, gw, rs, params, pair, hit_capacity=24 * 2 * n_pairs)
+        torch.cuda.synchronize()
+        want.append({k: getattr(ws, k).cpu().clone() for k in ("pair_score", "pair_flags", "mate_score", "mate_pos", "mate_strand", "n_rescue")})
+        batches.append(rw.cpu().pin_memory())
+    for depth in (1, 2, 3):
+        st = nb.StreamingSeedExtend(fmi, gw, params, 2 * n_pairs, L, batches[0].shape[1], hit_capacity=24 * 2 * n_pairs, depth=depth, pair=pair)
+        assert st.h2d_bytes == batches[0].numel() * 4 and st.d2h_bytes >= n_pairs * (4 + 4 + 8 + 8 + 2)
+        inflight = []
+        for b in range(5):
+            inflight.append((b, st.submit(batches[b])))
+            if len(inflight) == depth:
+                bb, t = inflight.pop(0)
+                got = st.result(t)
+                for k, v in want[bb].items():
+                    assert torch.equal(got[k].reshape(v.shape), v), (depth, bb, k)
+        for bb, t in inflight:
+            got = st.result(t)
+            for k, v in want[bb].items():
+                assert torch.equal(got[k].reshape(v.shape), v), (depth, bb, k)
+        assert st.last_device_ms > 0
+        st.close()
+
+
 def test_seed_extend_with_base_qualities():
     """nvBowtie's quality-dependent scoring through the composition: per-read qualities (reversed for the rc strings) reach the
     banded extension and the opposite-mate DP; single-end and paired outputs == the oracle composition"""
