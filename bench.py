@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
     ap.add_argument("--ktab-k", type=int, default=16, help="k of the k-mer range table (0 = none)")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-to-host (e2e) pipeline")
+    ap.add_argument("--e2e-sweep", action="store_true", help="also time the host-to-host pipeline with other (depth, compute streams) shapes")
     ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 kernel-level measurements")
@@ -515,7 +516,7 @@ def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
         host = [words.cpu().pin_memory(), words2.cpu().pin_memory()]
         st = nb.StreamingSeedExtend(fmi, genome, params, 2 * n_pairs, READ_LEN, wpr, hit_capacity=24 * 2 * n_pairs, depth=args.depth, pair=pair)
 
-        def run(k_steps):
+        def run_stream(k_steps):
             q, chk = [], 0
             for i in range(k_steps):
                 q.append(st.submit(host[i & 1]))
@@ -524,11 +525,11 @@ def paired_end_config(args, nb, fmi, genome, n, params, device, world, nd):
             while q:
                 last = st.result(q.pop(0)); chk += int(last["pair_flags"][0])
             return last
-        run(max(3, args.depth))
+        run_stream(max(3, args.depth))
         barrier(world)
         k2 = min(k, 40)
         t0 = time.perf_counter()
-        last = run(k2)
+        last = run_stream(k2)
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t0) * 1e3
         barrier(world)
@@ -714,9 +715,13 @@ def run_ours(args):
     e2e_ms, h2d, d2h, found = e2e_single(args, nb, fmi, genome, params, batches, n_reads, wpr, hit_capacity, world, nd, device, args.depth)
     e2e_value = world * n_reads / (e2e_ms * 1e-3) / 1e6
     e2e_alt = None
-    if world == 1 and args.depth != 1:                  # the same with one batch in flight (no cross-batch overlap), for the record
-        ms1, _, _, _ = e2e_single(args, nb, fmi, genome, params, batches, n_reads, wpr, hit_capacity, world, nd, device, 1)
-        e2e_alt = {"depth": 1, "ms_per_step": ms1, "value": n_reads / (ms1 * 1e-3) / 1e6}
+    if world == 1 and args.e2e_sweep:                   # other pipeline shapes, for the record: (batches in flight, compute streams)
+        e2e_alt = []
+        for dep, streams in ((1, 1), (2, 1), (3, 1), (2, 2), (3, 3)):
+            os.environ["NVB_PIPELINE_COMPUTE_STREAMS"] = str(streams)
+            ms1, _, _, _ = e2e_single(args, nb, fmi, genome, params, batches, n_reads, wpr, hit_capacity, world, nd, device, dep)
+            e2e_alt.append({"depth": dep, "compute_streams": streams, "ms_per_step": ms1, "value": n_reads / (ms1 * 1e-3) / 1e6})
+        os.environ.pop("NVB_PIPELINE_COMPUTE_STREAMS", None)
 
     # ---- paired-end composition (C5 shape), every world size --------------------------------------
     paired = None
@@ -755,9 +760,9 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": workload_config(args, n, n_reads, world),
         "index": idx_desc,
         "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "api": "C ABI nvb_pipeline_submit / nvb_pipeline_wait via nvbio_b200.StreamingSeedExtend (pinned host in/out, %d batches in flight on "
-                       "separate compute streams, wall clock over K steps)" % args.depth,
-                "depth": args.depth, "one_batch_in_flight": e2e_alt},
+                "api": "C ABI nvb_pipeline_submit / nvb_pipeline_wait via nvbio_b200.StreamingSeedExtend (pinned host in/out, %d batches in flight: copy-in, "
+                       "compute and copy-out streams; wall clock over K steps)" % args.depth,
+                "depth": args.depth, "compute_streams": int(os.environ.get("NVB_PIPELINE_COMPUTE_STREAMS", "1")), "sweep": e2e_alt},
         "gpu_launches": (9 if params.dedup_jobs else 8) * args.steps,      # own kernels per step on the per-read path (the cub scan not counted)
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),

@@ -383,8 +383,9 @@ int nvb_seed_extend_paired(const nvb_fm_index* fmi, const uint32_t* d_genome,
  * Replaces nvBowtie's input thread -> compute thread hand-off and its per-stage cudaDeviceSynchronize
  * (nvBowtie/bowtie2/cuda/compute_thread.cu:213-243, nvBowtie/bowtie2/cuda/defs.h:64, aligner_best_approx.h:219-241):
  * `depth` batches are in flight at once -- the host->device copy of batch i+1 and the device->host copy of batch i-1
- * overlap the kernels of batch i on separate streams, and consecutive batches run on DIFFERENT compute streams, so the
- * memory-latency-bound seed search of one batch and the integer-issue-bound extension of its neighbour share the SMs.
+ * overlap the kernels of batch i on separate streams.  By default all batches share ONE compute stream (their kernels run back
+ * to back); the environment variable NVB_PIPELINE_COMPUTE_STREAMS=k (read at creation) spreads consecutive batches over k
+ * compute streams so that kernels of neighbouring batches may share the SMs (measured: profiles/README.md).
  *
  * Reads: n_reads fixed-stride strings of `read_len` symbols, `words_per_read` 32-bit words each (big-endian packing,
  * read_bits = 2 or 4).  pair_params != NULL: paired-end (reads = mate 1 of every pair, then mate 2; n_reads even).

@@ -20,6 +20,7 @@
 #include <thrust/scan.h>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
+#include <cstdio>
 
 namespace nvbio {
 
@@ -149,11 +150,20 @@ private:
     {
         if (m_view.d_bwt_occ == NULL)
             m_view = view_type::get( m_index );
-        b200::check( nvb_fm_filter_locate( &m_view,
-                                           (const nvb_uint2*)thrust::raw_pointer_cast( m_ranges.data() ),
-                                           (const uint64_t*)thrust::raw_pointer_cast( m_slots.data() ),
-                                           m_n_queries, begin, end,
-                                           (nvb_uint2*)b200::raw_device_pointer( hits ), NULL ), "nvb_fm_filter_locate" );
+        const int r = nvb_fm_filter_locate( &m_view,
+                                            (const nvb_uint2*)thrust::raw_pointer_cast( m_ranges.data() ),
+                                            (const uint64_t*)thrust::raw_pointer_cast( m_slots.data() ),
+                                            m_n_queries, begin, end,
+                                            (nvb_uint2*)b200::raw_device_pointer( hits ), NULL );
+        if (r != NVB_OK)
+        {
+            char msg[512];
+            snprintf( msg, sizeof(msg), "nvb_fm_filter_locate(index{blocks %p, ssa %p, n %u, primary %u, sa_interval %u}, ranges %p, slots %p, queries %u, [%llu, %llu), hits %p)",
+                      m_view.d_bwt_occ, (const void*)m_view.d_ssa, m_view.length, m_view.primary, m_view.sa_interval,
+                      (const void*)thrust::raw_pointer_cast( m_ranges.data() ), (const void*)thrust::raw_pointer_cast( m_slots.data() ), m_n_queries,
+                      (unsigned long long)begin, (unsigned long long)end, (const void*)b200::raw_device_pointer( hits ) );
+            b200::check( r, msg );
+        }
         b200::stats().fm_locate++;
     }
     template <typename hits_iterator>

@@ -7,6 +7,7 @@
 // batches use different compute streams, so their kernels may share the SMs (the seed search leaves the integer pipes
 // half idle, the extension leaves DRAM idle).
 #include "common.cuh"
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -16,6 +17,8 @@ struct nvb_pipeline {
     int device;
     nvb_fm_index fmi; const uint32_t* d_genome; nvb_seed_extend_params params; nvb_pair_params pair; bool paired;
     uint32_t n_reads, read_len, wpr, bits, hit_capacity, depth;
+    uint32_t n_compute;                 // compute streams shared round-robin by the slots (NVB_PIPELINE_COMPUTE_STREAMS, default 1)
+    cudaStream_t compute[16];
     cudaStream_t h2d, d2h;
     struct Slot {
         cudaStream_t compute;
@@ -75,7 +78,7 @@ extern "C" void nvb_pipeline_destroy(nvb_pipeline* p)
     if (!p) return;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(p->device);
     for (auto& s : p->slots) {
-        if (s.compute) { cudaStreamSynchronize(s.compute); cudaStreamDestroy(s.compute); }
+        if (s.compute) cudaStreamSynchronize(s.compute);
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_temp) cudaFree(s.d_temp);
         if (s.d_out) cudaFree(s.d_out);
@@ -85,6 +88,7 @@ extern "C" void nvb_pipeline_destroy(nvb_pipeline* p)
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
+    for (uint32_t i = 0; i < p->n_compute; ++i) if (p->compute[i]) cudaStreamDestroy(p->compute[i]);
     if (p->h2d) cudaStreamDestroy(p->h2d);
     if (p->d2h) cudaStreamDestroy(p->d2h);
     cudaSetDevice(prev);
@@ -106,6 +110,10 @@ extern "C" int nvb_pipeline_create(const nvb_fm_index* fmi, const uint32_t* d_ge
     if (pair_params) p->pair = *pair_params;
     p->n_reads = n_reads; p->read_len = read_len; p->wpr = words_per_read; p->bits = read_bits; p->hit_capacity = hit_capacity; p->depth = depth;
     p->h2d = p->d2h = nullptr; p->next = 0;
+    p->n_compute = 1;
+    if (const char* e = getenv("NVB_PIPELINE_COMPUTE_STREAMS")) { const int v = atoi(e); if (v >= 1) p->n_compute = (uint32_t)v; }
+    if (p->n_compute > depth) p->n_compute = depth;
+    for (int i = 0; i < 16; ++i) p->compute[i] = nullptr;
     int rc = NVB_OK;
 #define PIPE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
     {
@@ -113,11 +121,13 @@ extern "C" int nvb_pipeline_create(const nvb_fm_index* fmi, const uint32_t* d_ge
         size_t out_bytes = 0; layout(p, &out_bytes);
         PIPE_TRY(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
         PIPE_TRY(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
+        for (uint32_t i = 0; i < p->n_compute; ++i) PIPE_TRY(cudaStreamCreateWithFlags(&p->compute[i], cudaStreamNonBlocking));
         p->slots.resize(depth);
         for (auto& s : p->slots) { s = nvb_pipeline::Slot(); }
+        uint32_t k = 0;
         for (auto& s : p->slots) {
             s.out_bytes = out_bytes; s.busy = false;
-            PIPE_TRY(cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking));
+            s.compute = p->compute[k++ % p->n_compute];
             PIPE_TRY(cudaMalloc((void**)&s.d_in, (size_t)n_reads * words_per_read * sizeof(uint32_t) + 64));
             PIPE_TRY(cudaMalloc((void**)&s.d_out, out_bytes));
             PIPE_TRY(cudaHostAlloc((void**)&s.h_out, out_bytes, cudaHostAllocDefault));
