@@ -89,19 +89,38 @@ struct packed_iterator< PackedStream<It,Sym,BITS_T,BE_T,uint32> >
 };
 
 // ------------------------------------------------------------------------------------------------------
-// strings: anything whose begin() is a supported packed iterator (vector_view<PackedStream>, Infix<...>)
+// strings over a supported packed iterator: vector_view<PackedStream> and Infix<string, coords>
+// (only __host__ __device__ members of the reference types are used: Infix::begin() is host-only, infix.h:229-245)
 // ------------------------------------------------------------------------------------------------------
-template <typename S>
-struct packed_string
+template <typename S> struct packed_string
 {
-    typedef typename std::decay< decltype( std::declval<const S&>().begin() ) >::type   iterator;
-    typedef packed_iterator<iterator>                                                    traits;
+    static const bool   supported = false;
+    static const uint32 BITS = 0u;
+    static const uint32 BE   = 0u;
+};
+template <typename It, typename Index>
+struct packed_string< vector_view<It,Index> >
+{
+    typedef vector_view<It,Index>   type;
+    typedef packed_iterator<It>     traits;
     static const bool   supported = traits::supported;
     static const uint32 BITS = traits::BITS;
     static const uint32 BE   = traits::BE;
-    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static const uint32* words(const S& s)  { return traits::words( s.begin() ); }
-    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static uint32        offset(const S& s) { return traits::offset( s.begin() ); }
-    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static uint32        length(const S& s) { return uint32( s.size() ); }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static const uint32* words(const type& s)  { return traits::words( s.begin() ); }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static uint32        offset(const type& s) { return traits::offset( s.begin() ); }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static uint32        length(const type& s) { return uint32( s.size() ); }
+};
+template <typename StringType, typename CoordType>
+struct packed_string< Infix<StringType,CoordType> >
+{
+    typedef Infix<StringType,CoordType> type;
+    typedef packed_string<StringType>   base;
+    static const bool   supported = base::supported;
+    static const uint32 BITS = base::BITS;
+    static const uint32 BE   = base::BE;
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static const uint32* words(const type& s)  { return base::words( s.m_string ); }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static uint32        offset(const type& s) { return base::offset( s.m_string ) + uint32( s.range().x ); }
+    NVBIO_FORCEINLINE NVBIO_HOST_DEVICE static uint32        length(const type& s) { return uint32( s.size() ); }
 };
 
 // ------------------------------------------------------------------------------------------------------

@@ -95,6 +95,23 @@ __host__ __device__ __forceinline__ void load_block_if(FmBlock& b, const FmBlock
 #endif
 }
 
+// scattered 4- and 8-byte gathers (SA entries, k-mer table entries): like the block gathers they ask L2 for 64 bytes of the line
+// instead of all 128 (a plain LDG drags the whole line from DRAM for 8 useful bytes)
+__host__ __device__ __forceinline__ uint32_t gather_u32(const uint32_t* __restrict__ p) {
+#ifdef __CUDA_ARCH__
+    uint32_t v; asm volatile("ld.global.nc" NVB_FM_LD_QUAL ".u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+#else
+    return *p;
+#endif
+}
+__host__ __device__ __forceinline__ uint2 gather_u2(const uint2* __restrict__ p) {
+#ifdef __CUDA_ARCH__
+    uint2 v; asm volatile("ld.global.nc" NVB_FM_LD_QUAL ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+#else
+    return *p;
+#endif
+}
+
 // one-hot flags (at bit 30-2s) of the symbols of w equal to c
 __host__ __device__ __forceinline__ uint32_t eq_flags(uint32_t w, uint32_t pat) {
     const uint32_t d = w ^ pat;
@@ -200,7 +217,7 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
             u |= (c & 3u) << (2u * j);
         }
         if (!has_n) {                                   // an N among them: take the step-by-step path below
-            const uint2 r = f.ktab[u];
+            const uint2 r = gather_u2(f.ktab + u);
             x = r.x; y = r.y; s = f.ktab_k;
         }
     }
@@ -212,6 +229,57 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
         fm_step(f, c, x, y);
     }
     ox = x; oy = y;
+}
+
+// match() + locate() of one query in one pass, for callers that only need the hit POSITIONS of narrow ranges (the per-read
+// seed + extend path): as soon as the range is a single row (x == y) and the index keeps the full suffix array, the remaining
+// LF steps are replaced by one SA gather and a comparison of the not-yet-consumed symbols with the text itself:
+//     LF from a single row x with symbol c is non-empty  <=>  bwt[x] == c  <=>  text[SA[x] - 1] == c   (and then SA[x'] = SA[x] - 1),
+// so `rem` further steps succeed  <=>  text[SA[x] - rem, SA[x]) == the rem symbols still to consume, and the located position is
+// SA[x] - rem -- exactly what locate(match(p)) returns for a single-row result (the `$` row has SA = 0 and fails, as its LF step
+// does).  Returns FM_EMPTY, FM_RANGE (general inclusive range in (x, y); caller locates), or FM_LOCATED (single hit at text
+// position x).  Backward order only (flags == 0); symbols > 3 never match.
+enum { FM_EMPTY = 0, FM_RANGE = 1, FM_LOCATED = 2 };
+template <int BITS, bool BE>
+__host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& f, const uint32_t* __restrict__ genome,
+                                                                 const uint32_t* __restrict__ words, uint32_t off, uint32_t len,
+                                                                 uint32_t& ox, uint32_t& oy)
+{
+    SymReader<BITS, BE> rd(words);
+    uint32_t x = 0, y = f.n, s = 0;
+    if (f.ktab_k && len >= f.ktab_k) {
+        uint32_t u = 0; bool has_n = false;
+        for (uint32_t j = 0; j < f.ktab_k; ++j) {
+            const uint32_t c = rd.get(off + len - 1u - j);
+            has_n |= (c > 3u);
+            u |= (c & 3u) << (2u * j);
+        }
+        if (!has_n) {
+            const uint2 r = gather_u2(f.ktab + u);
+            x = r.x; y = r.y; s = f.ktab_k;
+        }
+    }
+    const bool full_sa = (f.sa_shift == 0u) && genome != nullptr;
+    for (; s < len && x <= y; ++s) {
+        if (full_sa && x == y) {
+            const uint32_t rem = len - s;                 // symbols [0, rem) of the query are still to be consumed
+            const uint32_t pos = gather_u32(f.ssa + x);
+            if (pos == 0xFFFFFFFFu || pos < rem) return FM_EMPTY;
+            const uint32_t p0 = pos - rem;
+            SymReader<2, true> tr(genome);
+            bool same = true;
+            for (uint32_t i = 0; i < rem; ++i) same &= (rd.get(off + i) == tr.get(p0 + i));
+            if (!same) return FM_EMPTY;
+            ox = p0; oy = 0xFFFFFFFFu;
+            return FM_LOCATED;
+        }
+        const uint32_t c = rd.get(off + len - 1u - s);
+        if (c > 3u) return FM_EMPTY;
+        fm_step(f, c, x, y);
+    }
+    if (x > y) return FM_EMPTY;
+    ox = x; oy = y;
+    return FM_RANGE;
 }
 
 // nvBowtie's map<find_exact>(query, len1, len2, ...) (nvBowtie/bowtie2/cuda/mapping_inl.h:128-220): hits that match
@@ -291,7 +359,7 @@ __host__ __device__ __forceinline__ uint32_t fm_locate_one(const FmIndex& f, uin
         }
         ++t;
     }
-    return f.ssa[j >> f.sa_shift] + t;
+    return gather_u32(f.ssa + (j >> f.sa_shift)) + t;
 }
 
 } // namespace nvb

@@ -113,11 +113,14 @@ pipe_make_strings_2bit_be_kernel(const StrSet reads, const PipeGeom g, uint32_t*
     out_words[t] = word;
 }
 
-// one thread per (string, seed slot): SA range of the seed, and its clamped size
+// one thread per (string, seed slot): SA range of the seed, and its clamped size.
+// genome != NULL (the per-read path on an index with the full suffix array): single-row ranges are located on the spot --
+// ranges[q] = (text position, 0xFFFFFFFF), see fm_match_locate_one -- so that neither the remaining LF steps nor the later SA
+// gather of that hit are needed; wider ranges stay SA ranges.
 template <int BITS>
 __global__ void __launch_bounds__(256)
 pipe_seed_match_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __restrict__ words, const uint32_t* __restrict__ slen,
-                       uint2* __restrict__ ranges, uint32_t* __restrict__ sizes)
+                       const uint32_t* __restrict__ genome, uint2* __restrict__ ranges, uint32_t* __restrict__ sizes)
 {
     const uint32_t q = blockIdx.x * 256 + threadIdx.x;
     if (q >= g.n_strings * g.seeds_per_string) return;
@@ -125,10 +128,14 @@ pipe_seed_match_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __rest
     const uint32_t len = slen[s];
     const uint32_t pos = k * g.seed_interval;
     uint32_t x = 1, y = 0;
-    if (pos + g.seed_len <= len)
-        fm_match_one<BITS, true>(f, words, s * g.stride + pos, g.seed_len, 0u, x, y);
+    if (pos + g.seed_len <= len) {
+        if (genome) {
+            if (fm_match_locate_one<BITS, true>(f, genome, words, s * g.stride + pos, g.seed_len, x, y) == FM_EMPTY) { x = 1; y = 0; }
+        } else
+            fm_match_one<BITS, true>(f, words, s * g.stride + pos, g.seed_len, 0u, x, y);
+    }
     ranges[q] = make_uint2(x, y);
-    const uint32_t sz = (x <= y) ? (y - x + 1u) : 0u;
+    const uint32_t sz = (y == 0xFFFFFFFFu) ? 1u : ((x <= y) ? (y - x + 1u) : 0u);
     sizes[q] = sz < g.max_seed_hits ? sz : g.max_seed_hits;
 }
 
@@ -213,11 +220,13 @@ pipe_read_jobs_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict
                 const uint32_t q = s * g.seeds_per_string + k;
                 const uint32_t sz = sizes[q];
                 if (sz == 0u) continue;
-                const uint32_t base = excl[q], x = ranges[q].x, seed_begin = k * g.seed_interval;
+                const uint2 rq = ranges[q];
+                const uint32_t base = excl[q], x = rq.x, seed_begin = k * g.seed_interval;
+                const bool located = rq.y == 0xFFFFFFFFu;                              // already a text position (fm_match_locate_one)
                 for (uint32_t j = 0; j < sz; ++j) {
                     const uint32_t h = base + j;
                     if (h >= kept) break;                                              // beyond the caller's capacity
-                    const uint32_t pos = fm_locate_one(f, x + j);
+                    const uint32_t pos = located ? x : fm_locate_one(f, x + j);
                     const uint32_t diag = pos > seed_begin ? pos - seed_begin : 0u;
                     const uint32_t gb = diag > g.band / 2u ? diag - g.band / 2u : 0u;
                     const uint64_t ge64 = (uint64_t)gb + len + g.band;
@@ -586,7 +595,7 @@ extern "C" int nvb_seed_extend_stage_ms(float ms[7])
     return NVB_OK;
 }
 
-static int g_pipe_path = 0;            // 0 = automatic, 1 = always the per-hit path (nvb_debug_pipeline_path)
+static int g_pipe_path = 0;            // 0 = automatic, 1 = always the per-hit path, 2 = per-read path without the in-kernel locate (nvb_debug_pipeline_path)
 
 static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,
@@ -737,8 +746,10 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     // 2. seed ranges
     {
         const uint32_t grid = (nq + 255) / 256;
-        if (g.bits == 2) pipe_seed_match_kernel<2><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, ranges, sizes);
-        else             pipe_seed_match_kernel<4><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, ranges, sizes);
+        // per-read path + full suffix array: single-row ranges are located inside the match kernel (g_pipe_path 2 switches that off)
+        const uint32_t* loc_genome = (per_read && f.sa_shift == 0u && g_pipe_path != 2) ? d_genome : nullptr;
+        if (g.bits == 2) pipe_seed_match_kernel<2><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
+        else             pipe_seed_match_kernel<4><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(2);

@@ -68,6 +68,20 @@ void hh_fm_match_approx(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n,
     }
 }
 
+// fm_match_locate_one over an index with the full suffix array: out[3*i] = status (0 empty, 1 range, 2 located), then (x, y)
+void hh_fm_match_locate(const uint32_t* bwt_occ, const uint32_t* full_sa, const uint32_t* L2, uint32_t n, uint32_t primary,
+                        const uint32_t* genome, const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len,
+                        uint32_t nq, uint32_t* out, const uint32_t* ktab, uint32_t ktab_k) {
+    const FmIndex f = mk(bwt_occ, full_sa, L2, n, primary, 1, ktab, ktab_k);
+    for (uint32_t i = 0; i < nq; ++i) {
+        uint32_t x = 0, y = 0, st = 0;
+        if (bits == 2) st = fm_match_locate_one<2, true>(f, genome, words, off[i], len[i], x, y);
+        else           st = fm_match_locate_one<4, true>(f, genome, words, off[i], len[i], x, y);
+        (void)be;
+        out[3 * i] = st; out[3 * i + 1] = x; out[3 * i + 2] = y;
+    }
+}
+
 void hh_fm_locate(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
                   const uint32_t* rows, uint32_t nq, uint32_t* out, uint32_t sa_interval) {
     const FmIndex f = mk(bwt_occ, ssa, L2, n, primary, sa_interval);

