@@ -142,6 +142,55 @@ int nvb_fm_match_approx(const nvb_fm_index* fmi, const nvb_string_set* queries, 
                         uint32_t exact_len, int find_exact, uint32_t max_out,
                         nvb_uint2* d_ranges, uint32_t* d_counts, uint32_t* d_range_sums, void* stream);
 
+/* -------------------------------------------------------------------------------------------
+ * nvBowtie's seed-mapping stage: for every queued read, the seeds at symbol offsets
+ *     begin + retry * (seed_freq / (max_reseed + 1)) + k * seed_freq      while the seed fits
+ * are searched on both strands -- exactly (EXACT) or with one substitution outside the first subseed_len consumed symbols
+ * (APPROX) -- and their SA ranges kept in a BOUNDED per-read priority deque of at most max_hits SeedHits ordered by range
+ * size.  Replaces map_queues_kernel<EXACT_MAPPING|APPROX_MAPPING> (nvBowtie/bowtie2/cuda/mapping_inl.h:229-366, 539-591),
+ * the entry points map / map_exact / map_approx (mapping.cu:63-188) and the deque storage (seed_hit_deque_array.h:157-204).
+ * CASE_PRUNING mapping needs the reverse index and is not implemented.
+ *   reads            4-bit (DNA_N) or 2-bit big-endian strings; nvBowtie reads the forward strand of a seed front to back
+ *                    (NVB_MATCH_FORWARD_ORDER) and the other strand back to front, complemented (mapping_inl.h:263-309)
+ *   d_queue          read ids to process (PingPongQueuesView::in_queue), or NULL = 0 .. n_queue-1
+ *   d_seed_freq      optional per-read seed interval (nvBowtie evaluates SimpleFunc(read length) in float on the device,
+ *                    params.cpp:157-158: evaluate it on the host); NULL = params->seed_freq for every read
+ *   d_hits           arena of max_hits slots per READ ID: the read's hits sorted by range size (ascending, stable in push
+ *                    order = the order pop_top() yields); d_counts[read id] = their number
+ *   d_reseed[i]      (optional) 1 when queue entry i found no range or range_sum >= rep_seeds * range_count (:586-588)
+ *   d_range_stats    (optional) [2*i] = range_sum, [2*i+1] = range_count of queue entry i
+ * A full deque drops a largest range before every further push, as the reference does (pop_bottom, then push); among equally
+ * large ranges the most recently pushed one goes (an interval heap's choice depends on its layout): the kept range SIZES, the
+ * statistics and -- whenever a read pushes at most max_hits hits -- the complete hit sets equal the reference's. */
+typedef struct nvb_seed_hit {          /* bowtie2::cuda::SeedHit, seed_hit.h:54-98,230-232 (8 bytes) */
+    uint32_t range_begin;              /* SA range [range_begin, range_begin + delta) -- EXCLUSIVE end */
+    uint32_t bits;                     /* delta:20 | pos_in_read:10 | rc:1 | index_dir:1 (low to high) */
+} nvb_seed_hit;
+#define NVB_MAP_EXACT  0u
+#define NVB_MAP_APPROX 1u
+#define NVB_MAP_MAX_PUSHES 100u        /* an approximate seed of length L pushes at most 3 L + 1 ranges: L <= 33 */
+typedef struct nvb_map_params {
+    uint32_t algorithm;                /* NVB_MAP_EXACT | NVB_MAP_APPROX */
+    uint32_t seed_len, seed_freq;      /* ParamsPOD::seed_len, seed_freq(read_len) evaluated on the host */
+    uint32_t max_hits, max_reseed, rep_seeds, subseed_len, min_read_len;
+    uint32_t fw, rc;                   /* search the forward / the reverse-complement strand */
+} nvb_map_params;
+int nvb_map_seeds(const nvb_fm_index* fmi, const nvb_string_set* reads, const uint32_t* d_queue, uint32_t n_queue, uint32_t retry,
+                  const nvb_map_params* params, const uint32_t* d_seed_freq,
+                  nvb_seed_hit* d_hits, uint32_t* d_counts, uint8_t* d_reseed, uint32_t* d_range_stats, void* stream);
+
+/* Two-phase locate of queued SA rows (nvBowtie/bowtie2/cuda/locate_inl.h:122-210; nvbio/fmindex/fmindex_inl.h:502-569
+ * locate_ssa_iterator / lookup_ssa_iterator): init walks LF to the next sampled row, lookup adds the sampled position.
+ * d_idx (optional) is the sorting permutation nvBowtie passes as idx_queue: entry t works on element d_idx[t] of the arrays. */
+int nvb_fm_locate_init(const nvb_fm_index* fmi, const uint32_t* d_rows, const uint32_t* d_idx, uint32_t n,
+                       uint32_t* d_sampled_row, uint32_t* d_steps, void* stream);
+int nvb_fm_locate_lookup(const nvb_fm_index* fmi, const uint32_t* d_sampled_row, const uint32_t* d_steps, const uint32_t* d_idx, uint32_t n,
+                         uint32_t* d_pos, void* stream);
+/* locate with the rows radix-sorted first "to gather locality" (aligner_best_approx.h:737-756): same positions as nvb_fm_locate,
+ * returned in the input order. */
+int nvb_fm_locate_sorted(const nvb_fm_index* fmi, const uint32_t* d_rows, uint32_t n, uint32_t* d_pos,
+                         void* d_temp, size_t* temp_bytes, void* stream);
+
 /* d_pos[i] = text position of SA row d_rows[i]  (row 0 -> 0xFFFFFFFF as in the reference).
  * Replaces nvbio::locate(fm_index,i) (nvbio/fmindex/fmindex_inl.h:471-499) with
  * SSA_index_multiple_context<16>::fetch (nvbio/fmindex/ssa_inl.h:487-504). */

@@ -173,6 +173,72 @@ def locate(fmi: FMIndexDevice, rows: torch.Tensor) -> torch.Tensor:
     return out
 
 
+MAP_EXACT, MAP_APPROX = 0, 1
+
+
+class MapParamsStruct(C.Structure):         # nvb_map_params
+    _fields_ = [(k, C.c_uint32) for k in ("algorithm", "seed_len", "seed_freq", "max_hits", "max_reseed", "rep_seeds", "subseed_len",
+                                          "min_read_len", "fw", "rc")]
+
+
+def map_seeds(fmi: FMIndexDevice, reads: PackedStringSet, algorithm: int = MAP_EXACT, seed_len: int = 22, seed_freq: int = 10, max_hits: int = 100,
+              max_reseed: int = 2, rep_seeds: int = 1000, subseed_len: int = 0, min_read_len: int = 12, fw: bool = True, rc: bool = True,
+              queue: Optional[torch.Tensor] = None, retry: int = 0, seed_freq_per_read: Optional[torch.Tensor] = None):
+    """nvBowtie's seed mapping stage (map_queues_kernel<EXACT|APPROX>, mapping_inl.h:229-366,539-591) for a read batch.
+    Returns (hits int32 [n_reads, max_hits, 2] = (range_begin, packed bits) sorted by range size, counts [n_reads],
+    reseed uint8 [n_queue], stats int32 [n_queue, 2] = (range_sum, range_count))."""
+    n_reads = reads.count
+    n_queue = n_reads if queue is None else queue.numel()
+    dev = fmi.device
+    hits = torch.zeros((n_reads, max_hits, 2), dtype=torch.int32, device=dev)
+    counts = torch.zeros(n_reads, dtype=torch.int32, device=dev)
+    reseed = torch.full((n_queue,), 7, dtype=torch.uint8, device=dev)
+    stats = torch.zeros((n_queue, 2), dtype=torch.int32, device=dev)
+    p = MapParamsStruct(algorithm, seed_len, seed_freq, max_hits, max_reseed, rep_seeds, subseed_len, min_read_len, int(fw), int(rc))
+    s, q = fmi.struct(), reads.struct()
+    check(lib().nvb_map_seeds(C.byref(s), C.byref(q), C.c_void_p(queue.data_ptr()) if queue is not None else None, C.c_uint32(n_queue), C.c_uint32(retry),
+                              C.byref(p), C.c_void_p(seed_freq_per_read.data_ptr()) if seed_freq_per_read is not None else None,
+                              C.c_void_p(hits.data_ptr()), C.c_void_p(counts.data_ptr()), C.c_void_p(reseed.data_ptr()), C.c_void_p(stats.data_ptr()),
+                              _stream()), "nvb_map_seeds")
+    return hits, counts, reseed, stats
+
+
+def locate_init(fmi: FMIndexDevice, rows: torch.Tensor, idx: Optional[torch.Tensor] = None):
+    """first pass of nvBowtie's two-pass locate (locate_inl.h:122-166): (sampled SA row, LF steps) per queued row"""
+    n = rows.numel()
+    r = torch.empty(n, dtype=torch.int32, device=rows.device); t = torch.empty(n, dtype=torch.int32, device=rows.device)
+    s = fmi.struct()
+    check(lib().nvb_fm_locate_init(C.byref(s), C.c_void_p(rows.data_ptr()), C.c_void_p(idx.data_ptr()) if idx is not None else None, C.c_uint32(n),
+                                   C.c_void_p(r.data_ptr()), C.c_void_p(t.data_ptr()), _stream()), "nvb_fm_locate_init")
+    return r, t
+
+
+def locate_lookup(fmi: FMIndexDevice, sampled_rows: torch.Tensor, steps: torch.Tensor, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """second pass (locate_inl.h:168-210): ssa[row / SA_INT] + steps"""
+    n = sampled_rows.numel()
+    out = torch.empty(n, dtype=torch.int32, device=sampled_rows.device)
+    s = fmi.struct()
+    check(lib().nvb_fm_locate_lookup(C.byref(s), C.c_void_p(sampled_rows.data_ptr()), C.c_void_p(steps.data_ptr()),
+                                     C.c_void_p(idx.data_ptr()) if idx is not None else None, C.c_uint32(n), C.c_void_p(out.data_ptr()), _stream()),
+          "nvb_fm_locate_lookup")
+    return out
+
+
+def locate_sorted(fmi: FMIndexDevice, rows: torch.Tensor) -> torch.Tensor:
+    """locate() with the SA rows radix-sorted first to gather locality (aligner_best_approx.h:737-756); positions in input order"""
+    n = rows.numel()
+    out = torch.empty(n, dtype=torch.int32, device=rows.device)
+    s = fmi.struct()
+    tb = C.c_size_t(0)
+    r = lib().nvb_fm_locate_sorted(C.byref(s), C.c_void_p(rows.data_ptr()), C.c_uint32(n), C.c_void_p(out.data_ptr()), None, C.byref(tb), _stream())
+    if r != -2:
+        check(r, "nvb_fm_locate_sorted(size query)")
+    temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=rows.device)
+    check(lib().nvb_fm_locate_sorted(C.byref(s), C.c_void_p(rows.data_ptr()), C.c_uint32(n), C.c_void_p(out.data_ptr()), C.c_void_p(temp.data_ptr()),
+                                     C.byref(tb), _stream()), "nvb_fm_locate_sorted")
+    return out
+
+
 class FMIndexFilterDevice:
     """nvbio::FMIndexFilter<device_tag, fm_index_type> (nvbio/fmindex/filter.h:145-214):
     rank() -> n_hits, then ranges()/slots()/n_hits() and locate(begin, end) -> (text pos, query id) hits."""

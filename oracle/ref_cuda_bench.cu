@@ -25,7 +25,10 @@
 #include <nvbio/alignment/alignment.h>
 #include <nvbio/alignment/batched.h>
 #include <nvBowtie/bowtie2/cuda/mapping_inl.h>          // detail::map<find_exact>: nvBowtie's one-mismatch seed search (device function)
+#include <nvbio/io/sequence/sequence.h>
+#include <nvbio/io/sequence/sequence_access.h>
 #include <thrust/device_vector.h>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -314,6 +317,99 @@ static int run_approx(const std::string& dir)
     return 0;
 }
 
+// --------------------------------------------------------------------------------------------------
+// nvBowtie's seed mapping stage: its own map_queues_kernel<EXACT_MAPPING | APPROX_MAPPING> (nvBowtie/bowtie2/cuda/mapping_inl.h:539-591,
+// seed_mapper<>::enact :229-366) over a DNA_N read batch, the production index type, a PingPong input queue and a real
+// SeedHitDequeArray; every read's deque (as stored: interval-heap order), its size and the reseed flags are written back
+// --------------------------------------------------------------------------------------------------
+template <bowtie2::cuda::detail::MappingAlgorithm ALGO, typename batch_type, typename fm_index_type>
+static void launch_mapq(const batch_type reads, const fm_index_type fmi, const uint32 retry, const nvbio::cuda::PingPongQueuesView<uint32> queues,
+                        uint8* reseed, bowtie2::cuda::SeedHitDequeArrayDeviceView hits, const bowtie2::cuda::ParamsPOD params, const bool fw, const bool rc)
+{
+    const uint32 blocks = (queues.in_size + bowtie2::cuda::BLOCKDIM - 1) / bowtie2::cuda::BLOCKDIM;
+    bowtie2::cuda::detail::map_queues_kernel<ALGO> <<<blocks, bowtie2::cuda::BLOCKDIM>>>( reads, fmi, fmi, retry, queues, reseed, hits, params, fw, rc );
+}
+
+static int run_mapq(const std::string& dir)
+{
+    // meta: length, primary, L2[5], n_reads, n_queue, algo, seed_len, seed_freq, max_hits, max_reseed, rep_seeds, subseed_len, min_read_len, retry, fw, rc, arena
+    const std::vector<uint32> meta = read_file<uint32>(dir + "/meta.bin");
+    const uint32 length = meta[0], primary = meta[1], n_reads = meta[7], n_queue = meta[8], algo = meta[9];
+    const std::vector<uint32> h_bwt_occ = read_file<uint32>(dir + "/bwt_occ.bin");
+    const std::vector<uint32> h_ssa     = read_file<uint32>(dir + "/ssa.bin");
+    const std::vector<uint32> h_reads   = read_file<uint32>(dir + "/read_words.bin");      // DNA_N: 4 bits per symbol, big-endian
+    const std::vector<uint32> h_index   = read_file<uint32>(dir + "/read_index.bin");      // n_reads + 1 symbol offsets
+    const std::vector<uint32> h_queue   = read_file<uint32>(dir + "/queue.bin");
+    thrust::device_vector<uint32> d_bwt_occ(h_bwt_occ), d_ssa(h_ssa), d_L2(meta.begin() + 2, meta.begin() + 7), d_reads(h_reads), d_index(h_index), d_queue(h_queue);
+    std::vector<uint32> h_ct(256); gen_bwt_count_table(h_ct.data());
+    thrust::device_vector<uint32> d_ct(h_ct);
+
+    typedef nvbio::cuda::ldg_pointer<uint4>                              bwt_occ_type;
+    typedef deinterleaved_iterator<2,0,bwt_occ_type>                     bwt_type;
+    typedef deinterleaved_iterator<2,1,bwt_occ_type>                     occ_type;
+    typedef nvbio::cuda::ldg_pointer<uint32>                             u32_ldg;
+    typedef PackedStream<bwt_type,uint8,2u,true>                         bwt_stream_type;
+    typedef SSA_index_multiple_context<16u,u32_ldg>                      ssa_type;
+    typedef rank_dictionary<2u,64u,bwt_stream_type,occ_type,u32_ldg>     rank_dict_type;
+    typedef fm_index<rank_dict_type,ssa_type>                            fm_index_type;
+    const bwt_occ_type p( (const uint4*)thrust::raw_pointer_cast(d_bwt_occ.data()) );
+    const fm_index_type fmi( length, primary, thrust::raw_pointer_cast(d_L2.data()),
+        rank_dict_type( bwt_stream_type( bwt_type(p) ), occ_type(p), u32_ldg( thrust::raw_pointer_cast(d_ct.data()) ) ),
+        ssa_type( u32_ldg( thrust::raw_pointer_cast(d_ssa.data()) ) ) );
+
+    uint32 max_len = 0u; for (uint32 i = 0; i < n_reads; ++i) max_len = nvbio::max( max_len, h_index[i+1] - h_index[i] );
+    io::SequenceDataInfo info;
+    info.m_alphabet = DNA_N; info.m_n_seqs = n_reads; info.m_name_stream_len = 0u;
+    info.m_sequence_stream_len = h_index[n_reads]; info.m_sequence_stream_words = uint32( h_reads.size() );
+    info.m_has_qualities = 0u; info.m_min_sequence_len = 1u; info.m_max_sequence_len = max_len; info.m_avg_sequence_len = max_len;
+    const io::ConstSequenceDataView view( info, thrust::raw_pointer_cast(d_reads.data()), thrust::raw_pointer_cast(d_index.data()), NULL, NULL, NULL );
+    typedef io::SequenceDataAccess<DNA_N> batch_type;
+    const batch_type reads( view );
+
+    bowtie2::cuda::ParamsPOD params;
+    memset( &params, 0, sizeof(params) );
+    params.seed_len = meta[10];
+    params.seed_freq = bowtie2::cuda::SimpleFunc( bowtie2::cuda::SimpleFunc::LinearFunc, float(meta[11]), 0.0f );     // a constant
+    params.max_hits = meta[12]; params.max_reseed = meta[13]; params.rep_seeds = meta[14]; params.subseed_len = meta[15]; params.min_read_len = meta[16];
+    const uint32 retry = meta[17]; const bool fw = meta[18] != 0u, rc = meta[19] != 0u; const uint32 arena = meta[20];
+
+    // the deque array: global arena + per-read counts / indices + the bump-allocator pools (seed_hit_deque_array.h:62-75,157-204)
+    thrust::device_vector<bowtie2::cuda::SeedHit> d_hits( arena );
+    thrust::device_vector<uint32> d_counts( n_reads, 0u ), d_hindex( n_reads, 0u ), d_pindex( n_reads, 0u ), d_pool( 1, 0u ), d_ppool( 1, 0u );
+    thrust::device_vector<float>  d_probs( 2u * arena + 1024u );
+    bowtie2::cuda::SeedHitDequeArrayDeviceView hits(
+        nvbio::device_view( d_counts ), nvbio::device_view( d_hindex ), nvbio::device_view( d_hits ), nvbio::device_view( d_pindex ),
+        nvbio::device_view( d_probs ), nvbio::device_view( d_pool ), nvbio::device_view( d_ppool ) );
+    thrust::device_vector<uint8> d_reseed( n_queue, uint8(7) );
+
+    nvbio::cuda::PingPongQueuesView<uint32> queues;
+    queues.in_size   = n_queue;
+    queues.in_queue  = thrust::raw_pointer_cast( d_queue.data() );
+    queues.out_size  = NULL;
+    queues.out_queue = NULL;
+
+    if (algo == 0u) launch_mapq<bowtie2::cuda::detail::EXACT_MAPPING>( reads, fmi, retry, queues, thrust::raw_pointer_cast(d_reseed.data()), hits, params, fw, rc );
+    else            launch_mapq<bowtie2::cuda::detail::APPROX_MAPPING>( reads, fmi, retry, queues, thrust::raw_pointer_cast(d_reseed.data()), hits, params, fw, rc );
+    cudaDeviceSynchronize();
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+
+    std::vector<uint32> h_counts( n_reads ), h_hindex( n_reads ), h_pool( 1 ); std::vector<uint8> h_reseed( n_queue );
+    std::vector<uint2> h_hits( arena );                                                  // SeedHit = 8 bytes: (range_begin, packed bits)
+    cudaMemcpy( h_counts.data(), thrust::raw_pointer_cast(d_counts.data()), 4u * n_reads, cudaMemcpyDeviceToHost );
+    cudaMemcpy( h_hindex.data(), thrust::raw_pointer_cast(d_hindex.data()), 4u * n_reads, cudaMemcpyDeviceToHost );
+    cudaMemcpy( h_pool.data(),   thrust::raw_pointer_cast(d_pool.data()),   4u, cudaMemcpyDeviceToHost );
+    cudaMemcpy( h_reseed.data(), thrust::raw_pointer_cast(d_reseed.data()), n_queue, cudaMemcpyDeviceToHost );
+    cudaMemcpy( h_hits.data(),   thrust::raw_pointer_cast(d_hits.data()),   8u * size_t(arena), cudaMemcpyDeviceToHost );
+    write_file( dir + "/ref_counts.bin", h_counts.data(), n_reads );
+    write_file( dir + "/ref_index.bin",  h_hindex.data(), n_reads );
+    write_file( dir + "/ref_reseed.bin", h_reseed.data(), n_queue );
+    write_file( dir + "/ref_hits.bin",   h_hits.data(),   arena );
+    printf("{\"what\": \"nvBowtie map_queues_kernel<%s>, sm_100a\", \"reads\": %u, \"queue\": %u, \"arena_used\": %u, \"sizeof_SeedHit\": %u}\n",
+           algo == 0u ? "EXACT_MAPPING" : "APPROX_MAPPING", n_reads, n_queue, h_pool[0], uint32(sizeof(bowtie2::cuda::SeedHit)));
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: ref_cuda_bench banded|fm <dir>\n"); return 1; }
@@ -322,5 +418,6 @@ int main(int argc, char** argv)
     if (mode == "fm")     return run_fm(dir);
     if (mode == "full")   return run_full(dir);
     if (mode == "approx") return run_approx(dir);
+    if (mode == "mapq")   return run_mapq(dir);
     return 1;
 }

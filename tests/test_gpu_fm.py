@@ -257,3 +257,26 @@ def test_match_approx_one_mismatch(O):
             got = [tuple(x) for x in r[i, :c[i]]]
             assert got == want[i], (i, exact_len)
             assert s[i] == sum(y - x + 1 for x, y in want[i])
+
+
+@pytest.mark.parametrize("interval", [16, 4, 1])
+def test_two_phase_and_sorted_locate(O, interval):
+    """nvBowtie's two-pass locate (locate_init -> locate_lookup, locate_inl.h:122-210) through a sorting permutation, and the
+    radix-sorted one-pass variant (aligner_best_approx.h:737-756): positions == nvbio::locate for every row, in input order"""
+    require_gpu()
+    rng = np.random.default_rng(interval)
+    n = 50_000
+    text = np.concatenate([rng.integers(0, 4, n // 2), np.tile(rng.integers(0, 4, 97), n)[: n - n // 2]]).astype(np.uint8)
+    idx = O.build_index(text)
+    ssa = idx.sa[::interval].astype(np.uint32).copy(); ssa[0] = 0xFFFFFFFF
+    fmi = nb.FMIndexDevice.from_host(idx.bwt_occ, ssa, idx.L2, idx.n, idx.primary, sa_interval=interval)
+    rows = rng.integers(0, n + 1, 20000).astype(np.uint32); rows[:3] = (0, idx.primary, n)
+    want = O.locate(idx, rows)
+    d_rows = dev_u32(rows)
+    perm = dev_u32(rng.permutation(len(rows)).astype(np.uint32))
+    for p in (None, perm):
+        r, t = nb.locate_init(fmi, d_rows, p)
+        assert (host_u32(r) % interval == 0).all() and (host_u32(t) < interval).all()
+        assert np.array_equal(host_u32(nb.locate_lookup(fmi, r, t, p)), want)
+    assert np.array_equal(host_u32(nb.locate_sorted(fmi, d_rows)), want)
+    assert np.array_equal(host_u32(nb.locate(fmi, d_rows)), want)
