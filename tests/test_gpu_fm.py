@@ -276,7 +276,7 @@ def test_two_phase_and_sorted_locate(O, interval):
     perm = dev_u32(rng.permutation(len(rows)).astype(np.uint32))
     for p in (None, perm):
         r, t = nb.locate_init(fmi, d_rows, p)
-        assert (host_u32(r) % interval == 0).all() and (host_u32(t) < interval).all()
+        assert (host_u32(r) % interval == 0).all()             # a sampled row; the number of LF steps is geometric, not bounded by the interval
         assert np.array_equal(host_u32(nb.locate_lookup(fmi, r, t, p)), want)
     assert np.array_equal(host_u32(nb.locate_sorted(fmi, d_rows)), want)
     assert np.array_equal(host_u32(nb.locate(fmi, d_rows)), want)

@@ -85,8 +85,8 @@ def _reads_4bit(gw, n, n_reads, rng, min_len=30, max_len=150, with_n=True):
 
 
 @pytest.mark.parametrize("algo,seed_len,seed_freq,max_hits,subseed,retry,fw,rc",
-                         [(0, 22, 10, 100, 0, 0, 1, 1), (0, 20, 7, 100, 0, 1, 1, 1), (0, 16, 5, 8, 0, 0, 1, 0),
-                          (1, 22, 10, 100, 11, 0, 1, 1), (1, 16, 8, 100, 0, 2, 0, 1), (1, 20, 10, 12, 10, 0, 1, 1)])
+                         [(0, 22, 10, 100, 0, 0, 1, 1), (0, 20, 7, 100, 0, 1, 1, 1), (0, 16, 5, 3, 0, 0, 1, 0),
+                          (1, 22, 10, 100, 11, 0, 1, 1), (1, 16, 8, 100, 0, 2, 0, 1), (1, 20, 10, 4, 10, 0, 1, 1)])
 def test_map_seeds_equals_nvbowtie_map_queues_kernel(tool, algo, seed_len, seed_freq, max_hits, subseed, retry, fw, rc):
     """nvb_map_seeds == nvBowtie's own map_queues_kernel<EXACT_MAPPING|APPROX_MAPPING> (mapping_inl.h:539-591) run on the device over the
     same DNA_N reads, index and input queue: deque sizes, reseed flags and -- per read -- the SeedHits themselves as multisets (the

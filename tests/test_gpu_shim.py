@@ -63,3 +63,29 @@ def test_batch_program_identical_with_and_without_shim(binaries, tmp_path):
     c = b2["b200_calls"]
     assert c["banded"] == 21 and c["full"] == 9 and c["fallbacks"] == 0, c
     print("batch GCUPS: reference", {k: ref[k] for k in ref if k.endswith("gcups")}, "shim", {k: b2[k] for k in b2 if k.endswith("gcups")})
+
+
+def test_nvbowtie_mapping_entry_points_identical(tmp_path):
+    """boundary B-A2: nvBowtie's non-template map_exact / map_approx / map / gather_ranges (nvBowtie/bowtie2/cuda/mapping.h) called on
+    nvBowtie's own PODs by ONE harness object, linked once against nvBowtie's mapping.cu (compiled where it lies) and once against
+    tests/shim/nvbowtie_mapping_b200.cu + libnvbio_b200.so: deque sizes, the SeedHits of every read (canonical order), the range sizes
+    in pop_top() order, reseed flags and gather_ranges totals are identical; both leave valid priority deques behind"""
+    require_gpu()
+    ref, b2 = os.path.join(BIN, "nvbowtie_harness_ref"), os.path.join(BIN, "nvbowtie_harness_b200")
+    if not (os.path.exists(ref) and os.path.exists(b2)):
+        pytest.skip("tests/shim/_bin/nvbowtie_harness_* not built (needs /root/reference at build time)")
+    outs = {}
+    for name, binary in (("ref", ref), ("b200", b2)):
+        d = str(tmp_path / name); os.makedirs(d)
+        r = subprocess.run([binary, d, "400000", "4000"], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, "%s failed: %s" % (name, (r.stderr or r.stdout)[-800:])
+        outs[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    files = _same_dumps(str(tmp_path / "ref"), str(tmp_path / "b200"))
+    assert "exact_r0_hits.bin" in files and "approx_r0_hits.bin" in files and "exact_tiny_sizes.bin" in files
+    for cfg in ("exact_r0", "exact_r1", "exact_fw", "approx_r0", "approx_rc", "map_sub", "map_nosub", "exact_tiny"):
+        a, b = outs["ref"][cfg], outs["b200"][cfg]
+        assert a["hits"] == b["hits"] > 0 and a["range_total"] == b["range_total"] and a["full_deques"] == b["full_deques"], (cfg, a, b)
+        assert a["pop_order_ok"] == 1 and b["pop_order_ok"] == 1, cfg
+    assert outs["ref"]["exact_tiny"]["full_deques"] > 100
+    print("nvBowtie mapping ms: reference", {k: v["ms"] for k, v in outs["ref"].items() if isinstance(v, dict)},
+          "b200", {k: v["ms"] for k, v in outs["b200"].items() if isinstance(v, dict)})
