@@ -40,8 +40,18 @@ using nvbio::b200::stats;
 // ------------------------------------------------------------------------------------------------------
 template <typename stream_type> struct stream_binding { static const bool bound = false; };
 
+/// defaults a binding inherits: the length bounds come from the stream itself (a binding may hide them, e.g. for a stream whose
+/// own accessors do not compile: nvBowtie's BestScoreStream::max_pattern_length() calls a reads.max_read_len() that does not exist)
+template <typename stream_type>
+struct binding_defaults
+{
+    static uint32 max_pattern_length(const stream_type& s) { return s.max_pattern_length(); }
+    static uint32 max_text_length   (const stream_type& s) { return s.max_text_length(); }
+};
+
 template <typename aligner_type, typename pattern_set, typename text_set, typename sink_iterator>
-struct stream_binding< priv::AlignmentStream<aligner_type,pattern_set,trivial_quality_string_set,text_set,sink_iterator> >
+struct stream_binding< priv::AlignmentStream<aligner_type,pattern_set,trivial_quality_string_set,text_set,sink_iterator> > :
+    public binding_defaults< priv::AlignmentStream<aligner_type,pattern_set,trivial_quality_string_set,text_set,sink_iterator> >
 {
     typedef priv::AlignmentStream<aligner_type,pattern_set,trivial_quality_string_set,text_set,sink_iterator> stream_type;
     typedef typename stream_type::context_type      context_type;
@@ -66,7 +76,7 @@ struct gotoh_scheme_of< GotohAligner<TYPE_T,SimpleGotohScheme,algorithm_tag> >
 {
     static const bool supported = true;
     static const int  TYPE      = int(TYPE_T);           // GLOBAL 0, LOCAL 1, SEMI_GLOBAL 2 == NVB_GLOBAL / NVB_LOCAL / NVB_SEMI_GLOBAL
-    static nvb_gotoh_scheme get(const GotohAligner<TYPE_T,SimpleGotohScheme,algorithm_tag>& a)
+    static nvb_gotoh_scheme get(const GotohAligner<TYPE_T,SimpleGotohScheme,algorithm_tag>& a, thrust::device_vector<int32>&)
     {
         nvb_gotoh_scheme s;
         s.match = a.scheme.m_match;               s.mismatch = a.scheme.m_mismatch;
@@ -135,6 +145,38 @@ __global__ void output_kernel(const stream_type stream, const int32* score, cons
     stream.output( i, &context );
 }
 
+// a binding may declare `static const bool materialise_patterns = true`: its patterns are not plain substrings of a packed stream
+// (e.g. nvBowtie reads them reversed and / or complemented through a ReadLoader) -- then the engine calls the stream's OWN
+// load_strings() once per alignment and writes pattern symbols and base qualities to byte buffers the DP kernels read
+template <typename binding, typename = void> struct materialises_patterns { static const bool value = false; };
+template <typename binding> struct materialises_patterns<binding, typename std::enable_if<binding::materialise_patterns>::type> { static const bool value = true; };
+
+template <typename stream_type>
+__global__ void materialise_kernel(const stream_type stream, const uint32 p_stride, uint8* pat, uint8* qual,
+                                   uint32* p_off, uint32* p_len, uint32* t_off, uint32* t_len)
+{
+    typedef stream_binding<stream_type>             binding;
+    typedef typename stream_type::context_type      context_type;
+    typedef typename stream_type::strings_type      strings_type;
+    typedef typename binding::text_string           text_string;
+    const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= stream.size()) return;
+    context_type context;
+    uint32 pl = 0u, to = 0u, tl = 0u;
+    if (stream.init_context( i, &context ))
+    {
+        pl = stream.pattern_length( i, &context );
+        strings_type strings;
+        stream.load_strings( i, 0u, pl, &context, &strings );
+        uint8* p = pat  + size_t(i) * p_stride;
+        uint8* q = qual + size_t(i) * p_stride;
+        for (uint32 j = 0; j < pl; ++j) { p[j] = uint8( strings.pattern[j] ); q[j] = uint8( strings.quals[j] ); }
+        const text_string t = binding::text( stream, i, &context );
+        to = nvbio::b200::packed_string<text_string>::offset( t ); tl = nvbio::b200::packed_string<text_string>::length( t );
+    }
+    p_off[i] = i * p_stride; p_len[i] = pl; t_off[i] = to; t_len[i] = tl;
+}
+
 /// the common body of the accelerated enact() functions
 template <typename stream_type>
 struct engine
@@ -142,8 +184,8 @@ struct engine
     typedef stream_binding<stream_type>                     binding;
     typedef typename stream_type::aligner_type              aligner_type;
     typedef gotoh_scheme_of<aligner_type>                   scheme_of;
-    typedef typename binding::pattern_string                pattern_string;
     typedef typename binding::text_string                   text_string;
+    static const bool MATERIALISE = materialises_patterns<binding>::value;
 
     /// band_len == 0: full matrix
     void enact(const stream_type& stream, const uint32 band_len)
@@ -156,27 +198,26 @@ struct engine
         uint32* p_off = thrust::raw_pointer_cast( m_layout.data() );
         uint32* p_len = p_off + n; uint32* t_off = p_len + n; uint32* t_len = t_off + n;
         const uint32 grid = (n + 127u) / 128u;
-        layout_kernel<<<grid,128>>>( stream, p_off, p_len, t_off, t_len );
 
         nvb_string_set P, T;
-        P.d_words = (const uint32_t*)binding::pattern_words( stream );
-        P.bits = nvbio::b200::packed_string<pattern_string>::BITS; P.big_endian = nvbio::b200::packed_string<pattern_string>::BE;
-        P.d_offsets = p_off; P.d_lengths = p_len; P.stride = 0u; P.length = stream.max_pattern_length();
+        const uint8_t* d_quals = NULL;
+        stage( stream, grid, p_off, p_len, t_off, t_len, P, d_quals, std::integral_constant<bool,MATERIALISE>() );
+        P.d_offsets = p_off; P.d_lengths = p_len; P.stride = 0u; P.length = binding::max_pattern_length( stream );
         T.d_words = (const uint32_t*)binding::text_words( stream );
         T.bits = nvbio::b200::packed_string<text_string>::BITS;    T.big_endian = nvbio::b200::packed_string<text_string>::BE;
-        T.d_offsets = t_off; T.d_lengths = t_len; T.stride = 0u; T.length = stream.max_text_length();
+        T.d_offsets = t_off; T.d_lengths = t_len; T.stride = 0u; T.length = binding::max_text_length( stream );
 
-        const nvb_gotoh_scheme scheme = scheme_of::get( stream.aligner() );
+        const nvb_gotoh_scheme scheme = scheme_of::get( stream.aligner(), m_table );
         int32_t*   d_score = (int32_t*)thrust::raw_pointer_cast( m_score.data() );
         nvb_uint2* d_sink  = (nvb_uint2*)thrust::raw_pointer_cast( m_sink.data() );
         size_t bytes = 0u;
-        int r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, NULL, &T, n, d_score, d_sink, NULL, &bytes, NULL )
-                         : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, NULL, &T, n, d_score, d_sink, NULL, &bytes, NULL );
+        int r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, NULL, &bytes, NULL )
+                         : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, NULL, &bytes, NULL );
         if (r != NVB_E_TEMP_SIZE) check( r, "DP temp size query" );
         if (m_temp.size() < bytes + 256u) m_temp.resize( bytes + 256u );
         bytes = m_temp.size();
-        r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, NULL, &T, n, d_score, d_sink, thrust::raw_pointer_cast( m_temp.data() ), &bytes, NULL )
-                     : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, NULL, &T, n, d_score, d_sink, thrust::raw_pointer_cast( m_temp.data() ), &bytes, NULL );
+        r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, thrust::raw_pointer_cast( m_temp.data() ), &bytes, NULL )
+                     : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, thrust::raw_pointer_cast( m_temp.data() ), &bytes, NULL );
         check( r, band_len ? "nvb_banded_gotoh_score" : "nvb_gotoh_score" );
 
         output_kernel<<<grid,128>>>( stream, (const int32*)d_score, (const uint2*)thrust::raw_pointer_cast( m_sink.data() ) );
@@ -187,6 +228,33 @@ struct engine
     thrust::device_vector<int32>    m_score;
     thrust::device_vector<uint2>    m_sink;
     thrust::device_vector<uint8>    m_temp;
+    thrust::device_vector<uint8>    m_pat, m_qual;          // materialised patterns / qualities
+    thrust::device_vector<int32>    m_table;                // quality-dependent substitution table (scheme_of::get)
+
+private:
+    // patterns readable in place
+    void stage(const stream_type& stream, const uint32 grid, uint32* p_off, uint32* p_len, uint32* t_off, uint32* t_len,
+               nvb_string_set& P, const uint8_t*& d_quals, std::false_type)
+    {
+        typedef typename binding::pattern_string pattern_string;
+        layout_kernel<<<grid,128>>>( stream, p_off, p_len, t_off, t_len );
+        P.d_words = (const uint32_t*)binding::pattern_words( stream );
+        P.bits = nvbio::b200::packed_string<pattern_string>::BITS; P.big_endian = nvbio::b200::packed_string<pattern_string>::BE;
+        d_quals = NULL;
+    }
+    // patterns (and qualities) copied out through the stream's own loaders
+    void stage(const stream_type& stream, const uint32 grid, uint32* p_off, uint32* p_len, uint32* t_off, uint32* t_len,
+               nvb_string_set& P, const uint8_t*& d_quals, std::true_type)
+    {
+        const uint32 p_stride = (binding::max_pattern_length( stream ) + 3u) & ~3u;
+        m_pat.resize( size_t(stream.size()) * p_stride + 16u );
+        m_qual.resize( size_t(stream.size()) * p_stride + 16u );
+        materialise_kernel<<<grid,128>>>( stream, p_stride, thrust::raw_pointer_cast( m_pat.data() ), thrust::raw_pointer_cast( m_qual.data() ),
+                                          p_off, p_len, t_off, t_len );
+        P.d_words = (const uint32_t*)thrust::raw_pointer_cast( m_pat.data() );
+        P.bits = 8u; P.big_endian = 0u;
+        d_quals = (const uint8_t*)thrust::raw_pointer_cast( m_qual.data() );
+    }
 };
 
 struct no_engine {};

@@ -128,7 +128,8 @@ int main(int argc, char** argv)
         }
         const bool flip = rng.below( 2u ) == 1u;
         h_index[r] = cursor;
-        for (uint32 j = 0; j < len; ++j) R[cursor + j] = flip ? (sym[len-1u-j] < 4u ? 3u - sym[len-1u-j] : 4u) : sym[j];
+        // nvBowtie keeps reads REVERSED in memory: the forward strand is searched by consuming the stored read front to back (mapping_inl.h:263-270)
+        for (uint32 j = 0; j < len; ++j) R[cursor + len - 1u - j] = flip ? (sym[len-1u-j] < 4u ? 3u - sym[len-1u-j] : 4u) : sym[j];
         cursor += len;
     }
     h_index[n_reads] = cursor;
@@ -219,7 +220,7 @@ int main(int argc, char** argv)
         // gather_ranges over an inclusive scan of the counts, then pop everything
         std::vector<uint32> h_scan( n_reads ); uint32 acc = 0u; for (uint32 r = 0; r < n_reads; ++r) { acc += h_counts[r]; h_scan[r] = acc; }
         thrust::device_vector<uint32> d_scan( h_scan ); thrust::device_vector<uint64> d_ranges( acc + 1u );
-        gather_ranges( acc, n_reads, hits, thrust::raw_pointer_cast( d_scan.data() ), thrust::raw_pointer_cast( d_ranges.data() ) );
+        if (acc) gather_ranges( acc, n_reads, hits, thrust::raw_pointer_cast( d_scan.data() ), thrust::raw_pointer_cast( d_ranges.data() ) );      // (the reference launches an empty grid for 0)
         cuda_check( "gather_ranges" );
         std::vector<uint64> h_ranges( acc ); if (acc) cudaMemcpy( h_ranges.data(), thrust::raw_pointer_cast( d_ranges.data() ), 8u * size_t(acc), cudaMemcpyDeviceToHost );
         uint64 range_total = 0u; for (size_t i = 0; i < h_ranges.size(); ++i) range_total += h_ranges[i];

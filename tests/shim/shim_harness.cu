@@ -433,7 +433,7 @@ struct TestStream
 // the whole binding of a user stream: where its strings are ...
 namespace b200 {
 template <typename aligner_type, uint32 M, uint32 N>
-struct stream_binding< TestStream<aligner_type,M,N> >
+struct stream_binding< TestStream<aligner_type,M,N> > : public binding_defaults< TestStream<aligner_type,M,N> >
 {
     typedef TestStream<aligner_type,M,N>                            stream_type;
     typedef typename stream_type::context_type                      context_type;

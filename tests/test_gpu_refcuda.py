@@ -79,7 +79,7 @@ def _reads_4bit(gw, n, n_reads, rng, min_len=30, max_len=150, with_n=True):
             s = (3 - s)[::-1].copy()
         if with_n and r % 7 == 0:
             s[rng.integers(0, L, 2)] = 4
-        syms.append(s); index.append(index[-1] + L)
+        syms.append(s[::-1].copy()); index.append(index[-1] + L)      # nvBowtie stores reads reversed (mapping_inl.h:263-270)
     allsym = np.concatenate(syms).astype(np.uint8)
     return allsym, np.array(index, np.uint32), pack_symbols(np.concatenate([allsym, np.zeros(16, np.uint8)]), 4, True)
 

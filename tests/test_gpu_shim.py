@@ -89,3 +89,27 @@ def test_nvbowtie_mapping_entry_points_identical(tmp_path):
     assert outs["ref"]["exact_tiny"]["full_deques"] > 100
     print("nvBowtie mapping ms: reference", {k: v["ms"] for k, v in outs["ref"].items() if isinstance(v, dict)},
           "b200", {k: v["ms"] for k, v in outs["b200"].items() if isinstance(v, dict)})
+
+
+def test_nvbowtie_score_best_identical_with_and_without_shim(tmp_path):
+    """boundary B-B2: nvBowtie's best-score extension (detail::banded_score_best = the body of score_best_t / score_best,
+    score_best_inl.h:154-234) on nvBowtie's own types -- reversed DNA_N reads with base qualities, 2-bit genome, HitQueues,
+    SmithWatermanScoringScheme<> (--local preset and end-to-end default, quality-dependent mismatch penalties), ParamsPOD -- compiled
+    as is and with include/nvbio_b200/shim/nvbowtie_scoring.h: hit.score (incl. the worst_score clamp) and hit.sink of every hit equal"""
+    require_gpu()
+    ref, b2 = os.path.join(BIN, "nvbowtie_score_harness_ref"), os.path.join(BIN, "nvbowtie_score_harness_b200")
+    if not (os.path.exists(ref) and os.path.exists(b2)):
+        pytest.skip("tests/shim/_bin/nvbowtie_score_harness_* not built (needs /root/reference at build time)")
+    outs = {}
+    for name, binary in (("ref", ref), ("b200", b2)):
+        d = str(tmp_path / name); os.makedirs(d)
+        r = subprocess.run([binary, d, "2000000", "20000", "200000"], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, "%s failed: %s" % (name, (r.stderr or r.stdout)[-800:])
+        outs[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    files = _same_dumps(str(tmp_path / "ref"), str(tmp_path / "b200"))
+    assert len(files) == 8
+    import numpy as np
+    sc = np.fromfile(str(tmp_path / "ref" / "local_b31_score.bin"), np.int32)
+    assert (sc > 60).mean() > 0.5 and (sc != 12345).all()
+    assert outs["b200"]["b200_calls"] == {"banded": 12, "fallbacks": 0}
+    print("nvBowtie score_best ms: reference", {k: v for k, v in outs["ref"].items() if k.endswith("_ms")}, "b200", {k: v for k, v in outs["b200"].items() if k.endswith("_ms")})
