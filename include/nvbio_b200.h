@@ -152,6 +152,7 @@ int nvb_fm_match_approx(const nvb_fm_index* fmi, const nvb_string_set* queries, 
  * CASE_PRUNING mapping needs the reverse index and is not implemented.
  *   reads            4-bit (DNA_N) or 2-bit big-endian strings; nvBowtie reads the forward strand of a seed front to back
  *                    (NVB_MATCH_FORWARD_ORDER) and the other strand back to front, complemented (mapping_inl.h:263-309)
+ *                    A seed containing an N is skipped by both mappers (as the reference's N test does, mapping_inl.h:258,346).
  *   d_queue          read ids to process (PingPongQueuesView::in_queue), or NULL = 0 .. n_queue-1
  *   d_seed_freq      optional per-read seed interval (nvBowtie evaluates SimpleFunc(read length) in float on the device,
  *                    params.cpp:157-158: evaluate it on the host); NULL = params->seed_freq for every read

@@ -168,9 +168,16 @@ __global__ void materialise_kernel(const stream_type stream, const uint32 p_stri
         pl = stream.pattern_length( i, &context );
         strings_type strings;
         stream.load_strings( i, 0u, pl, &context, &strings );
-        uint8* p = pat  + size_t(i) * p_stride;
-        uint8* q = qual + size_t(i) * p_stride;
-        for (uint32 j = 0; j < pl; ++j) { p[j] = uint8( strings.pattern[j] ); q[j] = uint8( strings.quals[j] ); }
+        // four symbols per store (p_stride is a multiple of 4 and the buffers are word aligned)
+        uint32* p = reinterpret_cast<uint32*>( pat  + size_t(i) * p_stride );
+        uint32* q = reinterpret_cast<uint32*>( qual + size_t(i) * p_stride );
+        for (uint32 j = 0; j < pl; j += 4u)
+        {
+            uint32 pw = 0u, qw = 0u;
+            for (uint32 k = 0; k < 4u; ++k)
+                if (j + k < pl) { pw |= uint32( uint8( strings.pattern[j + k] ) ) << (8u * k); qw |= uint32( uint8( strings.quals[j + k] ) ) << (8u * k); }
+            p[j >> 2] = pw; q[j >> 2] = qw;
+        }
         const text_string t = binding::text( stream, i, &context );
         to = nvbio::b200::packed_string<text_string>::offset( t ); tl = nvbio::b200::packed_string<text_string>::length( t );
     }

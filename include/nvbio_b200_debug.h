@@ -13,6 +13,8 @@ void nvb_debug_force_gotoh_path(int path);
 void nvb_debug_full_minb(int minb);
 /* full-matrix dispatch: 0 = by batch size, 1 = always the warp-per-pair kernel, 2 = never */
 void nvb_debug_full_warp(int mode);
+/* 0: always the run-time-format pair kernel (PFMT 0); 1 (default): the compile-time 2- / 4-bit big-endian kernels where they apply */
+void nvb_debug_pair_format(int on);
 
 /* seed + extend composition: 0 = automatic (the per-read path when no per-hit output is requested), 1 = always the per-hit path */
 void nvb_debug_pipeline_path(int path);

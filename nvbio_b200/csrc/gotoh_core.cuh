@@ -92,6 +92,31 @@ struct PatStream {
     }
 };
 
+// The same for a pattern format known at compile time (BITS-bit symbols, big-endian words: nvBowtie's 4-bit reads, 2-bit reads): no
+// run-time format dispatch in the per-row fetch -- a shift to extract, a shift to advance, a counter
+template <int BITS>
+struct PatStreamBE {
+    const uint32_t* wp; uint32_t w, left;
+    __host__ __device__ __forceinline__ PatStreamBE(const uint32_t* words, uint32_t /*bits*/, uint32_t /*be*/, uint32_t off) {
+        constexpr uint32_t SPW = 32u / BITS, LG = (BITS == 2 ? 4u : 3u);
+        const uint32_t r = off & (SPW - 1u);
+        wp = words + (off >> LG);
+        w = *wp++ << (BITS * r);
+        left = SPW - r;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+        constexpr uint32_t SPW = 32u / BITS;
+        if (left == 0u) { w = *wp++; left = SPW; }
+        const uint32_t s = w >> (32u - BITS);
+        w <<= BITS;
+        --left;
+        return s;
+    }
+};
+template <int PFMT> struct PatStreamOf      { typedef PatStream type; };
+template <>         struct PatStreamOf<2>   { typedef PatStreamBE<2> type; };
+template <>         struct PatStreamOf<4>   { typedef PatStreamBE<4> type; };
+
 struct SinkResult { int32_t score; uint32_t x, y; };
 
 // ---------------------------------------------------------------------------------------------
@@ -412,7 +437,9 @@ static inline uint32_t nvb_host_vmaxu2(uint32_t a, uint32_t b) {
 //   text is 2-bit; TYPE != LOCAL => M0 == M1; scheme admitted by pair_path_ok().
 // sel: selectors of text columns t = 0 .. max(M0,M1)+B-2, element t at sel[t*sel_stride]
 // (shared memory on the device: conflict-free u16 column per thread).
-template <int B, int TYPE>
+// PFMT: 0 = pattern format and quality table handled at run time; 2 / 4 = 2- / 4-bit big-endian patterns AND no quality table, both
+// known at compile time (the dispatcher guarantees it): the per-row preamble loses its format dispatch and its table branch
+template <int B, int TYPE, int PFMT = 0>
 __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe,
         uint32_t poff0, uint32_t M0, uint32_t poff1, uint32_t M1,
@@ -436,14 +463,14 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
     const uint32_t q0 = ((i) < M0) ? pr0.next() : 255u;                                                       \
     const uint32_t q1 = ((i) < M1) ? pr1.next() : 255u;                                                       \
     int32_t e0 = c_eq, n0 = c_ne, e1 = c_eq, n1 = c_ne;                                                        \
-    if (S.qtab) {                                                                                             \
+    if (PFMT == 0 && S.qtab) {                                                                                \
         const uint32_t qq0 = (quals && (i) < M0) ? quals[poff0 + (i)] : 0u;                                   \
         const uint32_t qq1 = (quals && (i) < M1) ? quals[poff1 + (i)] : 0u;                                   \
         e0 = S.qtab[2 * qq0] - Go; n0 = S.qtab[2 * qq0 + 1] - Go;                                             \
         e1 = S.qtab[2 * qq1] - Go; n1 = S.qtab[2 * qq1 + 1] - Go;                                             \
     }                                                                                                         \
-    const uint32_t P0 = (prof_tab && !S.qtab) ? prof_tab[q0] : sub_profile(q0, e0, n0);                       \
-    const uint32_t P1 = (prof_tab && !S.qtab) ? prof_tab[q1] : sub_profile(q1, e1, n1);
+    const uint32_t P0 = (prof_tab && (PFMT != 0 || !S.qtab)) ? prof_tab[q0] : sub_profile(q0, e0, n0);        \
+    const uint32_t P1 = (prof_tab && (PFMT != 0 || !S.qtab)) ? prof_tab[q1] : sub_profile(q1, e1, n1);
 
     uint32_t G[B], F[B - 1];
     {
@@ -457,7 +484,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         for (int j = 0; j < B - 1; ++j) F[j] = INF2;
     }
 
-    PatStream pr0(pwords, pbits, pbe, poff0), pr1(pwords, pbits, pbe, poff1);
+    typename PatStreamOf<PFMT>::type pr0(pwords, pbits, pbe, poff0), pr1(pwords, pbits, pbe, poff1);
     const uint32_t Mmax = M0 > M1 ? M0 : M1;
     int32_t bk0 = -1, bk1 = -1; uint32_t bi0 = 0, bi1 = 0;       // LOCAL: best row key (H << 5 | j) and its row, per half
 

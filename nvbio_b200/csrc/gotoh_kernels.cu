@@ -14,6 +14,8 @@
 
 namespace nvb {
 
+static bool g_pair_fmt_ok = true;       // nvb_debug_pair_format(0) forces the run-time-format kernel (tests compare the two)
+
 constexpr int PAIR_BLOCKDIM    = 128;
 constexpr int GENERIC_BLOCKDIM = 128;
 
@@ -47,7 +49,7 @@ gotoh_generic_kernel(const GotohScheme S, const GotohBatch b, const uint32_t* __
     }
 }
 
-template <int B, int TYPE>
+template <int B, int TYPE, int PFMT>
 __global__ void __launch_bounds__(PAIR_BLOCKDIM)
 gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
 {
@@ -124,7 +126,7 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
         }
 
         SinkResult r0, r1;
-        gotoh_pair<B, TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
+        gotoh_pair<B, TYPE, PFMT>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
                             str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
                             my_sel, PAIR_BLOCKDIM, r0, r1, b.quals, prof_tab);
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
@@ -473,8 +475,8 @@ static int launch_generic(const GotohScheme& S, const GotohBatch& b, const uint3
     return NVB_OK;
 }
 
-template <int B, int TYPE>
-static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
+template <int B, int TYPE, int PFMT>
+static int launch_pair_fmt(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
 {
     const size_t smem = (size_t)sel_rows * PAIR_BLOCKDIM * sizeof(uint16_t);
     // the attribute is per DEVICE: a host that drives several GPUs from one process (nvBowtie's one compute thread per
@@ -484,14 +486,22 @@ static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_r
     NVB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= NVB_MAX_DEVICES) return NVB_E_UNSUPPORTED;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        NVB_CUDA_TRY(cudaFuncSetAttribute(gotoh_pair_kernel<B, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NVB_CUDA_TRY(cudaFuncSetAttribute(gotoh_pair_kernel<B, TYPE, PFMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done[dev].store(true, std::memory_order_release);
     }
     const uint32_t pairs = (b.n_max + 1u) / 2u;
     const uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
-    gotoh_pair_kernel<B, TYPE><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
+    gotoh_pair_kernel<B, TYPE, PFMT><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
+}
+// pattern format known at compile time (2- / 4-bit big-endian, no quality table): the specialised kernels; anything else: PFMT 0
+template <int B, int TYPE>
+static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
+{
+    if (!S.qtab && b.pat.big_endian && b.pat.bits == 2u && g_pair_fmt_ok) return launch_pair_fmt<B, TYPE, 2>(S, b, sel_rows, todo, todo_count, s);
+    if (!S.qtab && b.pat.big_endian && b.pat.bits == 4u && g_pair_fmt_ok) return launch_pair_fmt<B, TYPE, 4>(S, b, sel_rows, todo, todo_count, s);
+    return launch_pair_fmt<B, TYPE, 0>(S, b, sel_rows, todo, todo_count, s);
 }
 
 #define NVB_TYPE_SWITCH(BAND, FN, ...)                                            \
@@ -786,5 +796,6 @@ int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_stri
 void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
 void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
 void nvb_debug_full_warp(int mode) { g_full_warp = mode; }
+void nvb_debug_pair_format(int on) { nvb::g_pair_fmt_ok = on != 0; }
 
 } // extern "C"

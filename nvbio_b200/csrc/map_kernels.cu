@@ -65,10 +65,12 @@ map_seeds_kernel(const FmIndex f, const StrSet reads, const uint32_t* __restrict
     SymReader<BITS, true> rd(reads.words);
 
     for (uint32_t pos = begin + g.retry * stride; pos + seed_len <= end; pos += (seed_freq ? seed_freq : 1u)) {
-        // seeds with N's: exact mapping skips a seed with any N, approximate mapping one with two or more (mapping_inl.h:258, 343)
+        // seeds with N's: BOTH mappers skip a seed with any N.  The approximate one asks util::count_occurrences(seed, len, 4, 2) -- which
+        // returns the COUNT (capped at 2), not "count >= 2" -- inside an if(): one N already makes it true (mapping_inl.h:258, 343-346;
+        // nvbio/basic/numbers.h:108-122), so map()'s own single-N handling is never reached from here
         uint32_t n_cnt = 0u;
         for (uint32_t i = 0; i < seed_len; ++i) n_cnt += (rd.get(pos + i) > 3u) ? 1u : 0u;
-        if (n_cnt >= (g.algorithm == NVB_MAP_EXACT ? 1u : 2u)) continue;
+        if (n_cnt >= 1u) continue;
         const uint32_t pos_fw = end - pos - seed_len, pos_rc = pos - begin;     // SeedHit::m_pos of the two strands (:267, :301)
         if (g.algorithm == NVB_MAP_EXACT) {
             uint32_t x, y;

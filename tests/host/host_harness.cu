@@ -141,7 +141,10 @@ static void run_pair(const GotohScheme& S, const uint8_t* quals, const uint32_t*
             sel[t] = (uint16_t)pair_selector(g0, g1);
         }
         SinkResult q0, q1;
-        gotoh_pair<B, TYPE>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
+        // the kernel dispatcher's rule (launch_pair): compile-time pattern format for 2- / 4-bit big-endian patterns without a quality table
+        if (!S.qtab && pbe && pbits == 2)      gotoh_pair<B, TYPE, 2>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
+        else if (!S.qtab && pbe && pbits == 4) gotoh_pair<B, TYPE, 4>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
+        else                                   gotoh_pair<B, TYPE, 0>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
         score[a0] = q0.score; sx[a0] = q0.x; sy[a0] = q0.y;
         if (has1) { score[a1] = q1.score; sx[a1] = q1.x; sy[a1] = q1.y; }
     }
