@@ -115,6 +115,21 @@ int nvb_fm_rank(const nvb_fm_index* fmi, const uint32_t* d_k, const uint8_t* d_c
  * rank_dictionary_inl.h:539-573, the count-table popc_2bit_all path used by nvBowtie's 1-mismatch mapper). */
 int nvb_fm_rank4(const nvb_fm_index* fmi, const uint32_t* d_k, uint32_t n, uint32_t* d_out4, void* stream);
 
+/* Generic rank dictionary: a PLAIN big-endian 2-bit packed text over 32- or 64-bit words with a separate
+ * occurrence table sampled every K symbols (K a multiple of the symbols per word), 32- or 64-bit counters -- the form the
+ * reference's tests and its 64-bit indices instantiate.  Replaces dispatch_rank<2,K,PackedStream<...,2,true,index_type>,Occ,CT,
+ * word_type,index_type>::run / run4 (nvbio/fmindex/rank_dictionary_inl.h:243-422) and build_occurrence_table<2,K> (:42-77).
+ *   d_occ[4k + c]    = #c in text[0, kK)          (index_bits wide)
+ *   nvb_dict_rank    d_out[t] = #c[t] in text[0, i[t]]  (i and out index_bits wide; i == all ones -> 0)
+ *   nvb_dict_rank4   d_out4[4t + c] for c = A,C,G,T
+ *   nvb_dict_build_occ  builds d_occ (ceil(n/K) * 4 counters) on the device; h_counts (optional) = the four symbol totals */
+int nvb_dict_rank(const void* d_text, uint32_t word_bits, const void* d_occ, uint32_t index_bits, uint32_t K,
+                  const void* d_i, const uint8_t* d_c, uint32_t n, void* d_out, void* stream);
+int nvb_dict_rank4(const void* d_text, uint32_t word_bits, const void* d_occ, uint32_t index_bits, uint32_t K,
+                   const void* d_i, uint32_t n, void* d_out4, void* stream);
+int nvb_dict_build_occ(const void* d_text, uint32_t word_bits, uint64_t n_symbols, uint32_t K, uint32_t index_bits, void* d_occ, uint64_t h_counts[4],
+                       void* d_temp, size_t* temp_bytes, void* stream);
+
 #define NVB_MATCH_FORWARD_ORDER 1u  /* consume the query left-to-right instead of right-to-left   */
 #define NVB_MATCH_COMPLEMENT    2u  /* complement each symbol (c<4 ? 3-c : c) before ranking      */
 /* FORWARD_ORDER|COMPLEMENT is how nvBowtie searches the reverse-complement strand of a seed over the

@@ -5,7 +5,7 @@ interface for those paths; torch is used only for device memory, streams and tor
 from ._lib import NvbError, lib, LIB_PATH                                        # noqa: F401
 from .strings import PackedStringSet, pack_symbols, unpack_symbols               # noqa: F401
 from .fmindex import (FMIndexDevice, FMIndexFilterDevice, rank, rank4, match, match_approx, locate, map_seeds, locate_init, locate_lookup, locate_sorted,  # noqa: F401
-                      MAP_EXACT, MAP_APPROX,
+                      MAP_EXACT, MAP_APPROX, dict_rank, dict_build_occ,
                       MATCH_FORWARD_ORDER, MATCH_COMPLEMENT)
 from . import aln                                                                # noqa: F401
 from .pipeline import SeedExtendParams, seed_extend, StreamingSeedExtend, PairParams, seed_extend_paired     # noqa: F401

@@ -141,6 +141,43 @@ __host__ __device__ __forceinline__ uint32_t block_symbol(const FmBlock& b, uint
     return (w >> (30u - 2u * (r & 15u))) & 3u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// generic rank dictionary: the reference's dispatch_rank for a PLAIN big-endian 2-bit PackedStream over
+// 32- or 64-bit words with a separate occurrence table sampled every K symbols, 32- or 64-bit counters
+// (rank_dictionary_inl.h:243-422; the form its tests and 64-bit indices use).  rank(dict, i, c) = #c in text[0, i];
+// i == all-ones -> 0.  K is a multiple of the symbols per word.
+// ---------------------------------------------------------------------------------------------
+template <typename W> struct dict_word {};
+template <> struct dict_word<uint32_t> { static constexpr uint32_t SPW = 16u; static constexpr uint32_t ODD = 0x55555555u; };
+template <> struct dict_word<uint64_t> { static constexpr uint32_t SPW = 32u; static constexpr uint64_t ODD = 0x5555555555555555ull; };
+
+// occurrences of c among the first `keep` symbols (1..SPW) of word w
+template <typename W>
+__host__ __device__ __forceinline__ uint32_t word_rank(W w, uint32_t c, uint32_t keep) {
+    constexpr uint32_t SPW = dict_word<W>::SPW;
+    const W pat = (W)c * dict_word<W>::ODD;
+    const W d = w ^ pat;
+    W flags = ~(d | (d >> 1)) & dict_word<W>::ODD;
+    flags &= (W)(~(W)0) << (2u * (SPW - keep));
+#ifdef __CUDA_ARCH__
+    return sizeof(W) == 8 ? (uint32_t)__popcll((unsigned long long)flags) : (uint32_t)__popc((uint32_t)flags);
+#else
+    return (uint32_t)__builtin_popcountll((unsigned long long)flags);
+#endif
+}
+template <typename W, typename I>
+__host__ __device__ __forceinline__ I dict_rank(const W* __restrict__ text, const I* __restrict__ occ, uint32_t K, I i, uint32_t c) {
+    if (i == (I)(~(I)0)) return (I)0;
+    constexpr uint32_t SPW = dict_word<W>::SPW;
+    const uint64_t k = (uint64_t)(i / K);
+    const uint32_t r = (uint32_t)(i - (I)(k * K));               // offset inside the block, 0..K-1
+    const uint32_t m = r / SPW;
+    const uint64_t off = k * (K / SPW);
+    I out = occ[k * 4u + c];
+    for (uint32_t j = 0; j < m; ++j) out += word_rank<W>(text[off + j], c, SPW);
+    return out + word_rank<W>(text[off + m], c, (r % SPW) + 1u);
+}
+
 // rank(fmi, k, c)  (fmindex_inl.h:36-57)
 __host__ __device__ __forceinline__ uint32_t fm_rank1(const FmIndex& f, uint32_t k, uint32_t c) {
     if (k == 0xFFFFFFFFu) return 0u;

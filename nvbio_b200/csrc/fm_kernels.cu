@@ -61,6 +61,46 @@ fm_locate_kernel(const FmIndex f, const uint32_t* __restrict__ rows, uint32_t n,
     out[i] = fm_locate_one(f, rows[i]);
 }
 
+template <typename W, typename I>
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+dict_rank_kernel(const W* __restrict__ text, const I* __restrict__ occ, uint32_t K, const I* __restrict__ idx, const uint8_t* __restrict__ c, uint32_t n,
+                 I* __restrict__ out, int all4)
+{
+    const uint32_t t = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (t >= n) return;
+    if (all4) { for (uint32_t s = 0; s < 4u; ++s) out[4u * (size_t)t + s] = dict_rank<W, I>(text, occ, K, idx[t], s); }
+    else out[t] = dict_rank<W, I>(text, occ, K, idx[t], c[t] & 3u);
+}
+
+// generic build_occurrence_table<2,K> (rank_dictionary_inl.h:42-77): per-block symbol counts, then their exclusive scan
+template <typename W, typename I>
+__global__ void __launch_bounds__(256)
+dict_block_counts_kernel(const W* __restrict__ text, uint64_t n_symbols, uint32_t K, uint64_t n_blocks, uint64_t lane_len, I* __restrict__ counts /* [4][n_blocks + 1] */)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k > n_blocks) return;
+    I cnt[4] = { 0, 0, 0, 0 };
+    if (k < n_blocks) {
+        constexpr uint32_t SPW = dict_word<W>::SPW;
+        const uint64_t first = k * K;
+        const uint64_t valid = (n_symbols - first) < K ? (n_symbols - first) : K;
+        for (uint32_t j = 0; j * SPW < valid; ++j) {
+            const uint32_t keep = (valid - (uint64_t)j * SPW) < SPW ? (uint32_t)(valid - (uint64_t)j * SPW) : SPW;
+            const W w = text[k * (K / SPW) + j];
+            for (uint32_t s = 0; s < 4u; ++s) cnt[s] += word_rank<W>(w, s, keep);
+        }
+    }
+    for (uint32_t s = 0; s < 4u; ++s) counts[s * lane_len + k] = cnt[s];
+}
+template <typename I>
+__global__ void __launch_bounds__(256)
+dict_interleave_occ_kernel(const I* __restrict__ scan, uint64_t n_blocks, uint64_t lane_len, I* __restrict__ occ)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n_blocks) return;
+    for (uint32_t c = 0; c < 4u; ++c) occ[4u * k + c] = scan[c * lane_len + k];
+}
+
 // one level of the k-mer table: entry v of level t-1 (the range of a (t-1)-mer w) fans out to the four
 // t-mers c.w (c prepended = consumed next by the backward search).  The c=0 child overwrites its own parent.
 __global__ void __launch_bounds__(FM_BLOCKDIM)
@@ -155,6 +195,44 @@ occ_interleave_kernel(const uint32_t* __restrict__ bwt, const uint4* __restrict_
     b.bwt[0] = ws[0]; b.bwt[1] = ws[1]; b.bwt[2] = ws[2]; b.bwt[3] = ws[3];
     b.occ[0] = o.x; b.occ[1] = o.y; b.occ[2] = o.z; b.occ[3] = o.w;
     out[k] = b;
+}
+
+template <typename W, typename I>
+static int dict_rank_launch(const void* text, const void* occ, uint32_t K, const void* idx, const uint8_t* c, uint32_t n, void* out, int all4, cudaStream_t s)
+{
+    dict_rank_kernel<W, I><<<(n + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, s>>>((const W*)text, (const I*)occ, K, (const I*)idx, c, n, (I*)out, all4);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+template <typename W, typename I>
+static int dict_build_occ_impl(const void* d_text, uint64_t n_symbols, uint32_t K, void* d_occ, uint64_t h_counts[4], void* d_temp, size_t* temp_bytes, cudaStream_t s)
+{
+    const uint64_t n_blocks = (n_symbols + K - 1) / K;
+    const uint64_t lane_len = n_blocks + 1;                       // one extra entry per symbol: its total
+    TempCarver tc(d_temp);
+    I* counts = tc.take<I>(4 * lane_len);                         // lane-major: counts[c * lane_len + k]
+    I* scan   = tc.take<I>(4 * lane_len);
+    size_t scan_bytes = 0;
+    NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, scan, (long long)lane_len, s));
+    char* scan_tmp = tc.take<char>(scan_bytes);
+    const size_t need = tc.total();
+    if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
+    const uint32_t grid = (uint32_t)((lane_len + 255) / 256);
+    dict_block_counts_kernel<W, I><<<grid, 256, 0, s>>>((const W*)d_text, n_symbols, K, n_blocks, lane_len, counts);
+    NVB_LAUNCH_CHECK();
+    for (uint32_t c = 0; c < 4u; ++c)
+        NVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts + c * lane_len, scan + c * lane_len, (long long)lane_len, s));
+    dict_interleave_occ_kernel<I><<<grid, 256, 0, s>>>(scan, n_blocks, lane_len, (I*)d_occ);
+    NVB_LAUNCH_CHECK();
+    if (h_counts) {
+        for (int c = 0; c < 4; ++c) {
+            I tot;
+            NVB_CUDA_TRY(cudaMemcpyAsync(&tot, scan + c * lane_len + n_blocks, sizeof(I), cudaMemcpyDeviceToHost, s));
+            NVB_CUDA_TRY(cudaStreamSynchronize(s));
+            h_counts[c] = (uint64_t)tot;
+        }
+    }
+    return NVB_OK;
 }
 
 } // namespace nvb
@@ -288,6 +366,45 @@ int nvb_fm_filter_locate(const nvb_fm_index* fmi, const nvb_uint2* d_ranges, con
                                                                         n_queries, begin, count, (uint2*)d_hits);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
+}
+
+static bool dict_args_ok(uint32_t word_bits, uint32_t index_bits, uint32_t K)
+{
+    if (!(word_bits == 32 || word_bits == 64) || !(index_bits == 32 || index_bits == 64)) return false;
+    return K != 0 && K % (word_bits / 2u) == 0;
+}
+int nvb_dict_rank(const void* d_text, uint32_t word_bits, const void* d_occ, uint32_t index_bits, uint32_t K,
+                  const void* d_i, const uint8_t* d_c, uint32_t n, void* d_out, void* stream)
+{
+    if (!dict_args_ok(word_bits, index_bits, K) || (n && (!d_text || !d_occ || !d_i || !d_c || !d_out))) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    cudaStream_t s = as_stream(stream);
+    if (word_bits == 32) return index_bits == 32 ? dict_rank_launch<uint32_t, uint32_t>(d_text, d_occ, K, d_i, d_c, n, d_out, 0, s)
+                                                 : dict_rank_launch<uint32_t, uint64_t>(d_text, d_occ, K, d_i, d_c, n, d_out, 0, s);
+    return index_bits == 32 ? dict_rank_launch<uint64_t, uint32_t>(d_text, d_occ, K, d_i, d_c, n, d_out, 0, s)
+                            : dict_rank_launch<uint64_t, uint64_t>(d_text, d_occ, K, d_i, d_c, n, d_out, 0, s);
+}
+int nvb_dict_rank4(const void* d_text, uint32_t word_bits, const void* d_occ, uint32_t index_bits, uint32_t K,
+                   const void* d_i, uint32_t n, void* d_out4, void* stream)
+{
+    if (!dict_args_ok(word_bits, index_bits, K) || (n && (!d_text || !d_occ || !d_i || !d_out4))) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    cudaStream_t s = as_stream(stream);
+    if (word_bits == 32) return index_bits == 32 ? dict_rank_launch<uint32_t, uint32_t>(d_text, d_occ, K, d_i, nullptr, n, d_out4, 1, s)
+                                                 : dict_rank_launch<uint32_t, uint64_t>(d_text, d_occ, K, d_i, nullptr, n, d_out4, 1, s);
+    return index_bits == 32 ? dict_rank_launch<uint64_t, uint32_t>(d_text, d_occ, K, d_i, nullptr, n, d_out4, 1, s)
+                            : dict_rank_launch<uint64_t, uint64_t>(d_text, d_occ, K, d_i, nullptr, n, d_out4, 1, s);
+}
+
+int nvb_dict_build_occ(const void* d_text, uint32_t word_bits, uint64_t n_symbols, uint32_t K, uint32_t index_bits, void* d_occ, uint64_t h_counts[4],
+                       void* d_temp, size_t* temp_bytes, void* stream)
+{
+    if (!dict_args_ok(word_bits, index_bits, K) || !temp_bytes || (n_symbols && (!d_text || !d_occ))) return NVB_E_INVALID;
+    cudaStream_t s = as_stream(stream);
+    if (word_bits == 32) return index_bits == 32 ? dict_build_occ_impl<uint32_t, uint32_t>(d_text, n_symbols, K, d_occ, h_counts, d_temp, temp_bytes, s)
+                                                 : dict_build_occ_impl<uint32_t, uint64_t>(d_text, n_symbols, K, d_occ, h_counts, d_temp, temp_bytes, s);
+    return index_bits == 32 ? dict_build_occ_impl<uint64_t, uint32_t>(d_text, n_symbols, K, d_occ, h_counts, d_temp, temp_bytes, s)
+                            : dict_build_occ_impl<uint64_t, uint64_t>(d_text, n_symbols, K, d_occ, h_counts, d_temp, temp_bytes, s);
 }
 
 int nvb_fm_build_occ(const uint32_t* d_bwt, uint32_t n, void* d_bwt_occ, uint32_t h_L2[5],

@@ -173,6 +173,41 @@ def locate(fmi: FMIndexDevice, rows: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def dict_rank(text_words: torch.Tensor, occ: torch.Tensor, K: int, i: torch.Tensor, c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """generic rank dictionary (rank_dictionary_inl.h:243-422): text_words / occ / i are int32 or int64 tensors (32- or 64-bit words and
+    counters, bit patterns of the unsigned values); returns rank(i, c) [n], or all four symbols [n, 4] when c is None"""
+    wb = 32 if text_words.dtype == torch.int32 else 64
+    ib = 32 if occ.dtype == torch.int32 else 64
+    assert i.dtype == occ.dtype
+    n = i.numel()
+    if c is None:
+        out = torch.empty((n, 4), dtype=occ.dtype, device=i.device)
+        check(lib().nvb_dict_rank4(C.c_void_p(text_words.data_ptr()), C.c_uint32(wb), C.c_void_p(occ.data_ptr()), C.c_uint32(ib), C.c_uint32(K),
+                                   C.c_void_p(i.data_ptr()), C.c_uint32(n), C.c_void_p(out.data_ptr()), _stream()), "nvb_dict_rank4")
+        return out
+    out = torch.empty(n, dtype=occ.dtype, device=i.device)
+    check(lib().nvb_dict_rank(C.c_void_p(text_words.data_ptr()), C.c_uint32(wb), C.c_void_p(occ.data_ptr()), C.c_uint32(ib), C.c_uint32(K),
+                              C.c_void_p(i.data_ptr()), C.c_void_p(c.data_ptr()), C.c_uint32(n), C.c_void_p(out.data_ptr()), _stream()), "nvb_dict_rank")
+    return out
+
+
+def dict_build_occ(text_words: torch.Tensor, n_symbols: int, K: int, index_bits: int = 32):
+    """build_occurrence_table<2,K> on the device (rank_dictionary_inl.h:42-77): returns (occ, [count A, C, G, T])"""
+    wb = 32 if text_words.dtype == torch.int32 else 64
+    n_blocks = (n_symbols + K - 1) // K
+    occ = torch.empty(n_blocks * 4, dtype=torch.int32 if index_bits == 32 else torch.int64, device=text_words.device)
+    counts = (C.c_uint64 * 4)()
+    tb = C.c_size_t(0)
+    r = lib().nvb_dict_build_occ(C.c_void_p(text_words.data_ptr()), C.c_uint32(wb), C.c_uint64(n_symbols), C.c_uint32(K), C.c_uint32(index_bits),
+                                 C.c_void_p(occ.data_ptr()), counts, None, C.byref(tb), _stream())
+    if r != -2:
+        check(r, "nvb_dict_build_occ(size query)")
+    temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device=text_words.device)
+    check(lib().nvb_dict_build_occ(C.c_void_p(text_words.data_ptr()), C.c_uint32(wb), C.c_uint64(n_symbols), C.c_uint32(K), C.c_uint32(index_bits),
+                                   C.c_void_p(occ.data_ptr()), counts, C.c_void_p(temp.data_ptr()), C.byref(tb), _stream()), "nvb_dict_build_occ")
+    return occ, [int(v) for v in counts]
+
+
 MAP_EXACT, MAP_APPROX = 0, 1
 
 

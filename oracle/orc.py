@@ -305,6 +305,20 @@ class Ref(_Base):
         assert r == 0
         return o
 
+    def generic_rank(self, word_bits, K, text, qi, qc):
+        """the reference's generic rank_dictionary (plain big-endian 2-bit PackedStream over 32- / 64-bit words, occ every K symbols;
+        rank_dictionary_inl.h:243-422, build_occurrence_table :42-77): returns (words, occ, ranks)"""
+        text = np.ascontiguousarray(text, dtype=np.uint8); n = len(text)
+        wdt = np.uint32 if word_bits == 32 else np.uint64
+        spw = word_bits // 2
+        words = np.zeros((n + spw - 1) // spw + 4, dtype=wdt)
+        occ = np.zeros(((n + K - 1) // K + 1) * 4, dtype=wdt)
+        qi = np.ascontiguousarray(qi, dtype=np.uint64); qc = np.ascontiguousarray(qc, dtype=np.uint8)
+        out = np.zeros(len(qi), dtype=np.uint64)
+        r = self.lib.ref_generic_rank(C.c_int(word_bits), C.c_uint32(K), C.c_uint64(n), _p(text), _p(words), _p(occ), _p(qi), _p(qc), C.c_uint32(len(qi)), _p(out))
+        assert r == 0, (word_bits, K)
+        return words, occ[:((n + K - 1) // K) * 4], out
+
     def nvbowtie_scheme(self, preset=0, match_bonus=0, mm_min=2, mm_max=6, read_gap=(5, 3), ref_gap=(5, 3)):
         """nvBowtie's own SmithWatermanScoringScheme<QualCost<int>,ConstantCost<int>> (scoring.h:203-317), compiled from the reference:
         (table[256,2] = substitution on match / mismatch per base quality, gaps = (pattern open, ext, text open, ext),
@@ -440,3 +454,24 @@ def _ref_full(self, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None
 
 Oracle.gotoh_full = _oracle_full
 Ref.gotoh_full = _ref_full
+
+
+def generic_rank_oracle(text, qi, qc, word_bits, K):
+    """plain restatement of the generic rank dictionary (test infrastructure): words = text packed big-endian into word_bits-wide words,
+    occ[4k + c] = #c in text[0, kK), rank(i, c) = #c in text[0, i] (i = all ones -> 0)"""
+    text = np.asarray(text, dtype=np.uint8); n = len(text)
+    spw = word_bits // 2
+    wdt = np.uint32 if word_bits == 32 else np.uint64
+    pad = np.zeros((-n) % spw, np.uint8)
+    t = np.concatenate([text, pad]).reshape(-1, spw).astype(np.uint64)
+    sh = (word_bits - 2 - 2 * np.arange(spw)).astype(np.uint64)
+    words = np.bitwise_or.reduce(t << sh, axis=1).astype(wdt)
+    onehot = (text[:, None] == np.arange(4)[None, :]).astype(np.uint64)
+    pref = np.concatenate([np.zeros((1, 4), np.uint64), np.cumsum(onehot, axis=0)])          # pref[i] = counts in text[0, i)
+    n_blocks = (n + K - 1) // K
+    occ = pref[np.arange(n_blocks) * K].reshape(-1).astype(wdt)
+    qi = np.asarray(qi, dtype=np.uint64)
+    allones = qi == np.uint64(0xFFFFFFFFFFFFFFFF)
+    idx = np.where(allones, 0, qi).astype(np.int64)
+    ranks = np.where(allones, 0, pref[idx + 1, np.asarray(qc, dtype=np.int64)]).astype(np.uint64)
+    return words, occ, ranks

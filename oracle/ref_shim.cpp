@@ -304,6 +304,25 @@ void run_full_traceback(const aln::SimpleGotohScheme scheme,
 
 } // anonymous namespace
 
+// generic rank dictionary: the reference's rank_dictionary over a PLAIN big-endian 2-bit PackedStream of 32- or 64-bit
+// words with a separate occ table every K symbols -- the two instantiations its own rank_test.cu:144-232 runs, plus other K.
+// Packs `text` (n symbols), builds the table with build_occurrence_table<2,K>, answers rank(dict, i, c); words / occ are returned raw.
+template <typename W, typename I, uint32 K>
+static void generic_rank_impl(uint64 n, const uint8* text, W* words, I* occ, const uint64* qi, const uint8* qc, uint32 nq, uint64* out)
+{
+    typedef PackedStream<W*,uint8,2u,true,I>        wstream_t;
+    typedef PackedStream<const W*,uint8,2u,true,I>  stream_t;
+    wstream_t T( words );
+    for (uint64 i = 0; i < n; ++i) T[I(i)] = text[i];
+    I cnt[4];
+    build_occurrence_table<2u,K>( stream_t( words ), stream_t( words ) + I(n), occ, cnt );
+    uint32 ct[256]; gen_bwt_count_table( ct );
+    typedef rank_dictionary<2u,K,stream_t,const I*,const uint32*> dict_t;
+    const dict_t dict( stream_t( words ), occ, ct );
+    for (uint32 q = 0; q < nq; ++q)
+        out[q] = uint64( rank( dict, qi[q] == ~uint64(0) ? I(-1) : I(qi[q]), uint32( qc[q] ) ) );
+}
+
 extern "C" {
 
 // full-matrix Gotoh traceback: aln::alignment_traceback<256,512,64> (nvbio/alignment/alignment_inl.h:365-530)
@@ -507,6 +526,17 @@ int ref_banded_gotoh(int band, int type, int match, int mismatch, int gap_open, 
     case 31: return run_banded_type<31>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
     case 63: return run_banded_type<63>( type, s, pat,p_off,p_len, txt,t_off,t_len, n, score,sink_x,sink_y,ok );
     }
+    return -1;
+}
+
+
+int ref_generic_rank(int word_bits, uint32 K, uint64 n, const uint8* text, void* words, void* occ, const uint64* qi, const uint8* qc, uint32 nq, uint64* out)
+{
+    if (word_bits == 32 && K == 64)  { generic_rank_impl<uint32,uint32,64> ( n, text, (uint32*)words, (uint32*)occ, qi, qc, nq, out ); return 0; }
+    if (word_bits == 32 && K == 128) { generic_rank_impl<uint32,uint32,128>( n, text, (uint32*)words, (uint32*)occ, qi, qc, nq, out ); return 0; }
+    if (word_bits == 32 && K == 16)  { generic_rank_impl<uint32,uint32,16> ( n, text, (uint32*)words, (uint32*)occ, qi, qc, nq, out ); return 0; }
+    if (word_bits == 64 && K == 64)  { generic_rank_impl<uint64,uint64,64> ( n, text, (uint64*)words, (uint64*)occ, qi, qc, nq, out ); return 0; }
+    if (word_bits == 64 && K == 256) { generic_rank_impl<uint64,uint64,256>( n, text, (uint64*)words, (uint64*)occ, qi, qc, nq, out ); return 0; }
     return -1;
 }
 

@@ -206,6 +206,23 @@ def make_nvbowtie(ref, path=None):
     np.savez_compressed(path or os.path.join(OUT, "nvbowtie_scheme.npz"), **out)
 
 
+def make_generic_rank(ref):
+    """(h) generic rank dictionary: packed words, occ tables and rank answers of the reference's rank_dictionary over
+    plain 32- / 64-bit-word streams (the instantiations of nvbio-test/rank_test.cu:144-232, plus other K) -> generic_rank.npz"""
+    out = {}
+    rng = np.random.default_rng(5)
+    cfgs = [(32, 64, 1000), (32, 128, 4097), (32, 16, 333), (64, 64, 2048), (64, 256, 5001)]
+    out["cfgs"] = np.array(cfgs, dtype=np.int64)
+    for i, (wb, K, n) in enumerate(cfgs):
+        text = rng.integers(0, 4, n).astype(np.uint8)
+        qi = np.concatenate([rng.integers(0, n, 500).astype(np.uint64), np.array([0, n - 1, K - 1, K, 0xFFFFFFFFFFFFFFFF], dtype=np.uint64)])
+        qc = rng.integers(0, 4, len(qi)).astype(np.uint8)
+        words, occ, ranks = ref.generic_rank(wb, K, text, qi, qc)
+        out[f"text{i}"] = text; out[f"qi{i}"] = qi; out[f"qc{i}"] = qc
+        out[f"words{i}"] = words[: (n + wb // 2 - 1) // (wb // 2)]; out[f"occ{i}"] = occ; out[f"ranks{i}"] = ranks
+    np.savez_compressed(os.path.join(OUT, "generic_rank.npz"), **out)
+
+
 def main():
     assert orc.Ref.available(), "build oracle/_ref first: make -C oracle"
     ref = orc.Ref()
@@ -286,6 +303,7 @@ def main():
     fm["count_table"] = ref.count_table()
     np.savez_compressed(os.path.join(OUT, "fmindex.npz"), **fm)
     make_nvbowtie(ref)
+    make_generic_rank(ref)
     print("wrote", os.listdir(OUT))
 
 

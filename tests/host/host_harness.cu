@@ -82,6 +82,14 @@ void hh_fm_match_locate(const uint32_t* bwt_occ, const uint32_t* full_sa, const 
     }
 }
 
+// generic rank dictionary (dict_rank<W,I>): out[q] = rank(i[q], c[q]), all as uint64
+void hh_dict_rank(const void* text, uint32_t word_bits, const void* occ, uint32_t K, const uint64_t* qi, const uint8_t* qc, uint32_t nq, uint64_t* out) {
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (word_bits == 32) out[q] = dict_rank<uint32_t, uint32_t>((const uint32_t*)text, (const uint32_t*)occ, K, qi[q] == ~0ull ? 0xFFFFFFFFu : (uint32_t)qi[q], qc[q]);
+        else                 out[q] = dict_rank<uint64_t, uint64_t>((const uint64_t*)text, (const uint64_t*)occ, K, qi[q], qc[q]);
+    }
+}
+
 void hh_fm_locate(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
                   const uint32_t* rows, uint32_t nq, uint32_t* out, uint32_t sa_interval) {
     const FmIndex f = mk(bwt_occ, ssa, L2, n, primary, sa_interval);

@@ -280,3 +280,26 @@ def test_two_phase_and_sorted_locate(O, interval):
         assert np.array_equal(host_u32(nb.locate_lookup(fmi, r, t, p)), want)
     assert np.array_equal(host_u32(nb.locate_sorted(fmi, d_rows)), want)
     assert np.array_equal(host_u32(nb.locate(fmi, d_rows)), want)
+
+
+def test_generic_rank_dictionary_gpu():
+    """nvb_dict_rank / nvb_dict_rank4 / nvb_dict_build_occ == the reference's rank_dictionary over plain 32- / 64-bit
+    word streams and build_occurrence_table<2,K> (committed fixture generated by running the reference)"""
+    require_gpu()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "generic_rank.npz"))
+    for i, (wb, K, n) in enumerate(g["cfgs"]):
+        wb, K, n = int(wb), int(K), int(n)
+        sdt, tdt = (np.int32, torch.int32) if wb == 32 else (np.int64, torch.int64)
+        words = torch.from_numpy(np.concatenate([g[f"words{i}"], np.zeros(4, g[f"words{i}"].dtype)]).view(sdt)).cuda()
+        occ = torch.from_numpy(g[f"occ{i}"].view(sdt).copy()).cuda()
+        qi = g[f"qi{i}"]
+        qi_dev = torch.from_numpy((qi & (0xFFFFFFFF if wb == 32 else 0xFFFFFFFFFFFFFFFF)).astype(np.uint32 if wb == 32 else np.uint64).view(sdt)).cuda()
+        qc = torch.from_numpy(g[f"qc{i}"].copy()).cuda()
+        mask = np.uint64(0xFFFFFFFF if wb == 32 else 0xFFFFFFFFFFFFFFFF)
+        got = nb.dict_rank(words, occ, K, qi_dev, qc).cpu().numpy().view(np.uint32 if wb == 32 else np.uint64).astype(np.uint64)
+        assert np.array_equal(got, g[f"ranks{i}"]), (wb, K, n)
+        all4 = nb.dict_rank(words, occ, K, qi_dev).cpu().numpy().view(np.uint32 if wb == 32 else np.uint64).astype(np.uint64)
+        assert np.array_equal(all4[np.arange(len(qi)), g[f"qc{i}"]], g[f"ranks{i}"])
+        built, counts = nb.dict_build_occ(words, n, K, index_bits=wb)
+        assert np.array_equal(built.cpu().numpy().view(np.uint32 if wb == 32 else np.uint64), g[f"occ{i}"]), (wb, K, n)
+        assert counts == [int((g[f"text{i}"] == c).sum()) for c in range(4)]

@@ -318,6 +318,17 @@ def approx_expected(O, idx, q, offs, lens, exact_len, find_exact, fwd, comp):
     return exp
 
 
+def test_generic_rank_dictionary(H):
+    """product's dict_rank<W,I> (generic rank dictionary) == the reference's answers on the committed fixture"""
+    g = np.load(os.path.join(HERE, "golden", "generic_rank.npz"))
+    for i, (wb, K, n) in enumerate(g["cfgs"]):
+        qi = np.ascontiguousarray(g[f"qi{i}"]); qc = np.ascontiguousarray(g[f"qc{i}"])
+        words = np.concatenate([g[f"words{i}"], np.zeros(4, g[f"words{i}"].dtype)]); occ = np.ascontiguousarray(g[f"occ{i}"])
+        out = np.zeros(len(qi), np.uint64)
+        H.hh_dict_rank(_p(words), C.c_uint32(int(wb)), _p(occ), C.c_uint32(int(K)), _p(qi), _p(qc), C.c_uint32(len(qi)), _p(out))
+        assert np.array_equal(out, g[f"ranks{i}"]), (wb, K, n)
+
+
 @pytest.mark.parametrize("n,k", [(300, 0), (300, 3), (5000, 0), (5000, 4), (5000, 6), (70, 2)])
 def test_fm_match_locate_shortcut(H, O, n, k):
     """fm_match_locate_one (single-row ranges located through the full SA + a text comparison instead of the remaining LF steps)

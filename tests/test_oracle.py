@@ -367,3 +367,13 @@ def test_oracle_quality_dp_vs_nvbowtie_scheme(O):
         okb = ok.astype(bool)
         assert okb.sum() > 30
         assert np.array_equal(s.astype(np.int64)[okb], res[0][okb]) and np.array_equal(x.astype(np.int64)[okb], res[1][okb]) and np.array_equal(y.astype(np.int64)[okb], res[2][okb]), (cid, band, typ)
+
+
+def test_generic_rank_dictionary_golden():
+    """the plain restatement of the generic rank dictionary (32- / 64-bit words, occ every K) == the reference's
+    rank_dictionary / build_occurrence_table<2,K> on the committed fixture (packed words, occ table, ranks incl. i = -1)"""
+    g = np.load(os.path.join(GOLD, "generic_rank.npz"))
+    for i, (wb, K, n) in enumerate(g["cfgs"]):
+        w, o, r = orc.generic_rank_oracle(g[f"text{i}"], g[f"qi{i}"], g[f"qc{i}"], int(wb), int(K))
+        assert np.array_equal(w, g[f"words{i}"]) and np.array_equal(o, g[f"occ{i}"]) and np.array_equal(r, g[f"ranks{i}"]), (wb, K, n)
+        assert int(r[-1]) == 0                               # i = all ones
