@@ -34,6 +34,10 @@ extern "C" {
 
 typedef struct nvb_uint2 { uint32_t x, y; } nvb_uint2;
 
+/* score of an alignment sink that received no report: nvbio's Field_traits<int32>::min() (nvbio/basic/numbers.h:832-836), the value
+ * aln::BestSink<int32> / Best2Sink<int32> are constructed with (sink_inl.h:40,73-78) */
+#define NVB_SINK_MIN (-(1 << 30))
+
 /* ---------------------------------------------------------------------------------------------
  * Data views
  * ------------------------------------------------------------------------------------------- */
@@ -230,7 +234,7 @@ int nvb_fm_filter_locate(const nvb_fm_index* fmi, const nvb_uint2* d_ranges, con
 
 /* For i < n: banded DP of patterns[i] (rows) against texts[i] (band anchored at text offset 0),
  * d_score[i] / d_sink[i] = BestSink<int32>{score, sink=(text_end, pattern_end)}; an alignment with
- * text_len < pattern_len leaves the sink at its defaults (INT_MIN, (-1,-1)).
+ * text_len < pattern_len leaves the sink at its defaults (NVB_SINK_MIN, (-1,-1)).
  * band_len in {3,5,7,15,31,63}.  d_quals (one byte per pattern symbol, indexed like the pattern
  * stream) may be NULL (trivial_quality_string).
  * Replaces aln::BatchedBandedAlignmentScore<BAND_LEN,stream,DeviceThreadScheduler>::enact and
@@ -265,6 +269,15 @@ int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme
                                   const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
                                   uint32_t window_begin, uint32_t window_end, const int32_t* d_min_score,
                                   int16_t* d_checkpoints, int32_t* d_score, nvb_uint2* d_sink, uint8_t* d_alive, void* stream);
+
+/* Banded Gotoh score with aln::Best2Sink<int32>(distinct_dist) (nvbio/alignment/sink.h:114-147, sink_inl.h:70-116) instead of BestSink: the
+ * best alignment (last maximal report wins) and the best one whose text end is more than distinct_dist away from it -- the second-best
+ * score a MAPQ estimate needs.  d_out6[6*i ..] = (score1, sink1.x, sink1.y, score2, sink2.x, sink2.y); unset entries keep the sink's
+ * defaults (NVB_SINK_MIN, 0xFFFFFFFF).  Every report the reference makes reaches the sink in its order (LOCAL: every cell, row by row).
+ * One alignment per thread on the int32 kernel; bands 3, 5, 7, 15, 31, 63. */
+int nvb_banded_gotoh_score_best2(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                                 const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
+                                 uint32_t distinct_dist, int32_t* d_out6, void* stream);
 
 /* Full-matrix (un-banded) Gotoh score: every pattern against the WHOLE of its text.
  * d_score / d_sink = BestSink<int32>{score, (text end, pattern end)}; pattern and text lengths must be >= 1 and

@@ -247,3 +247,16 @@ def batch_banded_alignment_score_window(band_len: int, aligner: GotohAligner, pa
                                               C.c_void_p(state.sink.data_ptr()), C.c_void_p(state.alive.data_ptr()), _stream()),
           "nvb_banded_gotoh_score_window")
     return state
+
+
+def batch_banded_alignment_score_best2(band_len: int, aligner: GotohAligner, patterns: PackedStringSet, texts: PackedStringSet, distinct_dist: int = 0,
+                                       quals: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """banded Gotoh score into aln::Best2Sink<int32>(distinct_dist) (sink.h:114-147): int32 [n, 6] = (score1, sink1.x, sink1.y, score2, sink2.x, sink2.y)"""
+    n = patterns.count
+    out = torch.empty((n, 6), dtype=torch.int32, device=patterns.words.device)
+    sch = aligner.scheme.struct()
+    p, t = patterns.struct(), texts.struct()
+    check(lib().nvb_banded_gotoh_score_best2(C.c_int(band_len), C.c_int(aligner.type), C.byref(sch), C.byref(p),
+                                             C.c_void_p(quals.data_ptr()) if quals is not None else None, C.byref(t), C.c_uint32(n),
+                                             C.c_uint32(distinct_dist), C.c_void_p(out.data_ptr()), _stream()), "nvb_banded_gotoh_score_best2")
+    return out

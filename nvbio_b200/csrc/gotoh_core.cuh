@@ -126,6 +126,17 @@ struct SinkResult { int32_t score; uint32_t x, y; };
 enum { DIR_SUB = 0, DIR_INS = 1, DIR_DEL = 2, DIR_SINK = 3, DIR_INS_EXT = 4, DIR_DEL_EXT = 8 };
 template <int B> struct DirWords { static constexpr int N = (B * 4 + 31) / 32; };     // 4 bits per band cell
 
+// aln::Best2Sink<int32> (nvbio/alignment/sink.h:114-147, sink_inl.h:70-116): the best alignment (ties: the last report wins) and the
+// best one whose text end lies more than `dist` away from it -- fed with the very reports BestSink receives
+struct Best2 {
+    int32_t s1, s2; uint32_t x1, y1, x2, y2, dist;
+    __host__ __device__ __forceinline__ void init(uint32_t d) { s1 = s2 = NVB_SINK_MIN; x1 = y1 = x2 = y2 = 0xFFFFFFFFu; dist = d; }
+    __host__ __device__ __forceinline__ void report(int32_t s, uint32_t x, uint32_t y) {
+        if (s1 <= s) { s1 = s; x1 = x; y1 = y; }
+        else if (s2 <= s && (x + dist < x1 || x > x1 + dist)) { s2 = s; x2 = x; y2 = y; }
+    }
+};
+
 // DIRS: also emit, per row, the packed 4-bit direction vectors (H | E | F flow) of every band cell to
 // dirs[row * DirWords<B>::N ..] -- exactly the bits GotohSubmatrixContext::new_cell stores (gotoh_banded_inl.h:325-337)
 template <int B, int TYPE, bool DIRS>
@@ -133,9 +144,9 @@ __host__ __device__ inline SinkResult gotoh_generic_impl(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff, uint32_t M,
         const uint8_t* __restrict__ quals,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff, uint32_t N,
-        uint32_t* __restrict__ dirs)
+        uint32_t* __restrict__ dirs, Best2* best2 = nullptr)
 {
-    SinkResult res; res.score = INT_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
+    SinkResult res; res.score = NVB_SINK_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
     if (N < M) return res;
 
     constexpr bool PACKED = packed_text_cache(B);
@@ -198,6 +209,7 @@ __host__ __device__ inline SinkResult gotoh_generic_impl(const GotohScheme& S,
                 h = imax2(h, 0);
                 if (DIRS && h == 0) hdir = DIR_SINK;
                 if (best <= h) { best = h; bpos = (i << 6) | (uint32_t)j; }
+                if (best2) best2->report(h, i + (uint32_t)j + 1u, i + 1u);
             }
             H[j] = h;
             if (DIRS) dw[j >> 3] |= (hdir | edir | fdir) << (4 * (j & 7));
@@ -218,12 +230,17 @@ __host__ __device__ inline SinkResult gotoh_generic_impl(const GotohScheme& S,
         if (M > 0) { res.score = best; res.x = (bpos >> 6) + (bpos & 63u) + 1u; res.y = (bpos >> 6) + 1u; }
     } else if (TYPE == NVB_GLOBAL) {
         res.score = H[B - 1]; res.x = M + (uint32_t)B - 1u; res.y = M;
+        if (best2) best2->report(H[B - 1], M + (uint32_t)B - 1u, M);
     } else {
         const uint32_t m = umin2(M + (uint32_t)B - 1u, N) - (M - 1u);
         res.score = H[0]; res.x = M; res.y = M;
+        if (best2) best2->report(H[0], M, M);
 #pragma unroll
         for (int j = 1; j < B; ++j)
-            if ((uint32_t)j < m && res.score <= H[j]) { res.score = H[j]; res.x = M + (uint32_t)j; }
+            if ((uint32_t)j < m) {
+                if (res.score <= H[j]) { res.score = H[j]; res.x = M + (uint32_t)j; }
+                if (best2) best2->report(H[j], M + (uint32_t)j, M);
+            }
     }
     return res;
 }

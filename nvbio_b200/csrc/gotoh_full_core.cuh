@@ -28,7 +28,7 @@ __host__ __device__ inline SinkResult gotoh_full_impl2(const GotohScheme& S,
         int2* __restrict__ col, size_t col_stride, uint32_t* __restrict__ dirs = nullptr, uint32_t dir_row_words = 0,
         const uint8_t* __restrict__ quals = nullptr)
 {
-    SinkResult res; res.score = INT_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
+    SinkResult res; res.score = NVB_SINK_MIN; res.x = 0xFFFFFFFFu; res.y = 0xFFFFFFFFu;
     if (M == 0 || N == 0) return res;            // outside the supported domain (see header)
     const int32_t Go = S.pgo, Ge = S.pge;
     const int32_t INF = SHRT_MIN - (Go < Ge ? Go : Ge);
@@ -310,7 +310,7 @@ __host__ __device__ inline bool gotoh_full_pair(const GotohScheme& S,
         const uint32_t* prof_tab = nullptr)      // optional 256-entry table of sub_profile(g, c_eq, c_ne) (shared memory on the device)
 {
     const int32_t Go = S.pgo;
-    r0.score = INT_MIN; r0.x = r0.y = 0xFFFFFFFFu; r1 = r0;
+    r0.score = NVB_SINK_MIN; r0.x = r0.y = 0xFFFFFFFFu; r1 = r0;
     FullPairTrack trk; trk.s0 = trk.s1 = INT_MIN; trk.x0 = trk.x1 = 0u;
     for (uint32_t b = 0; b < M; b += FULL_W) {
         const bool first = (b == 0), last = (b + FULL_W >= M);

@@ -49,6 +49,28 @@ gotoh_generic_kernel(const GotohScheme S, const GotohBatch b, const uint32_t* __
     }
 }
 
+// Best2Sink variant of the int32 kernel: out6[a] = (score1, sink1.x, sink1.y, score2, sink2.x, sink2.y)
+template <int B, int TYPE>
+__global__ void __launch_bounds__(GENERIC_BLOCKDIM)
+gotoh_best2_kernel(const GotohScheme S, const GotohBatch b, uint32_t distinct_dist, int32_t* __restrict__ out6)
+{
+    const uint32_t n = batch_count(b);
+    const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
+    if (a >= n) return;
+    Best2 b2; b2.init(distinct_dist);
+    gotoh_generic_impl<B, TYPE, false>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a), b.quals,
+                                       b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a), nullptr, &b2);
+    int32_t* o = out6 + 6 * (size_t)a;
+    o[0] = b2.s1; o[1] = (int32_t)b2.x1; o[2] = (int32_t)b2.y1; o[3] = b2.s2; o[4] = (int32_t)b2.x2; o[5] = (int32_t)b2.y2;
+}
+template <int B, int TYPE>
+static int launch_best2(const GotohScheme& S, const GotohBatch& b, uint32_t distinct_dist, int32_t* out6, cudaStream_t s)
+{
+    gotoh_best2_kernel<B, TYPE><<<(b.n_max + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM, GENERIC_BLOCKDIM, 0, s>>>(S, b, distinct_dist, out6);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
 template <int B, int TYPE, int PFMT>
 __global__ void __launch_bounds__(PAIR_BLOCKDIM)
 gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
@@ -161,7 +183,7 @@ gotoh_window_kernel(const GotohScheme S, const GotohBatch b, const WindowArgs w)
     const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
     if (a >= n) return;
     SinkResult r;
-    if (w.wb == 0) { r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu; b.score[a] = r.score; b.sink[a] = make_uint2(r.x, r.y); w.alive[a] = 1; }
+    if (w.wb == 0) { r.score = NVB_SINK_MIN; r.x = r.y = 0xFFFFFFFFu; b.score[a] = r.score; b.sink[a] = make_uint2(r.x, r.y); w.alive[a] = 1; }
     else { if (!w.alive[a]) return; r.score = b.score[a]; const uint2 k = b.sink[a]; r.x = k.x; r.y = k.y; }
     const uint32_t M = str_len(b.pat, a);
     if (w.wb >= M) return;
@@ -196,7 +218,7 @@ gotoh_full_traceback_kernel(const GotohScheme S, const GotohBatch b, int2* __res
     if (a >= n) return;
     uint32_t* dirs = o.dirs + (size_t)a * o.dir_rows * dir_row_words;
     const uint32_t M = str_len(b.pat, a), N = str_len(b.txt, a);
-    SinkResult r; r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu;
+    SinkResult r; r.score = NVB_SINK_MIN; r.x = r.y = 0xFFFFFFFFu;
     if (N <= o.dir_rows && (M + 31u) / 32u * 4u <= dir_row_words)
         r = gotoh_full_impl<TYPE, true>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), M,
                                         b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), N, col + a, (size_t)b.n_max, dirs, dir_row_words, b.quals);
@@ -440,7 +462,7 @@ gotoh_traceback_kernel(const GotohScheme S, const GotohBatch b, const TracebackO
     if (a >= n) return;
     uint32_t* dirs = o.dirs + (size_t)a * o.dir_rows * NW;
     const uint32_t M = str_len(b.pat, a);
-    SinkResult r; r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu;
+    SinkResult r; r.score = NVB_SINK_MIN; r.x = r.y = 0xFFFFFFFFu;
     if (M <= o.dir_rows)
         r = gotoh_generic_impl<B, TYPE, true>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), M, b.quals,
                                               b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a), dirs);
@@ -754,6 +776,30 @@ int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme
     case 7:  NVB_TYPE_SWITCH(7,  launch_window, S, b, w, s)
     case 15: NVB_TYPE_SWITCH(15, launch_window, S, b, w, s)
     case 31: NVB_TYPE_SWITCH(31, launch_window, S, b, w, s)
+    default: return NVB_E_INVALID;
+    }
+}
+
+int nvb_banded_gotoh_score_best2(int band_len, int type, const nvb_gotoh_scheme* scheme,
+                                 const nvb_string_set* patterns, const uint8_t* d_quals, const nvb_string_set* texts, uint32_t n,
+                                 uint32_t distinct_dist, int32_t* d_out6, void* stream)
+{
+    if (!scheme || !valid_strset(patterns) || !valid_strset(texts)) return NVB_E_INVALID;
+    if (type < 0 || type > 2) return NVB_E_INVALID;
+    if (n == 0) return NVB_OK;
+    if (!d_out6) return NVB_E_INVALID;
+    GotohBatch b;
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
+    b.d_n = nullptr; b.n_max = n; b.score = nullptr; b.sink = nullptr;
+    const GotohScheme S = make_scheme(scheme);
+    cudaStream_t s = as_stream(stream);
+    switch (band_len) {
+    case 3:  NVB_TYPE_SWITCH(3,  launch_best2, S, b, distinct_dist, d_out6, s)
+    case 5:  NVB_TYPE_SWITCH(5,  launch_best2, S, b, distinct_dist, d_out6, s)
+    case 7:  NVB_TYPE_SWITCH(7,  launch_best2, S, b, distinct_dist, d_out6, s)
+    case 15: NVB_TYPE_SWITCH(15, launch_best2, S, b, distinct_dist, d_out6, s)
+    case 31: NVB_TYPE_SWITCH(31, launch_best2, S, b, distinct_dist, d_out6, s)
+    case 63: NVB_TYPE_SWITCH(63, launch_best2, S, b, distinct_dist, d_out6, s)
     default: return NVB_E_INVALID;
     }
 }

@@ -296,10 +296,22 @@ typedef struct {
 static inline i32 imax(i32 a, i32 b) { return a > b ? a : b; }
 
 #define ORC_MAX_BAND 64
+/* score of a sink that received no report: Field_traits<int32>::min() (nvbio/basic/numbers.h:832-836) */
+#define ORC_SINK_MIN (-(1 << 30))
 
+/* optional aln::Best2Sink<int32> fed with the same reports (nvbio/alignment/sink.h:114-147, sink_inl.h:70-116): when set, every
+ * report() of the DP also reaches it */
+typedef struct { i32 s1, s2; u32 x1, y1, x2, y2, dist; } orc_best2;
+static orc_best2* g_best2 = NULL;
+static inline void best2_report(orc_best2* b, i32 s, u32 x, u32 y)
+{
+    if (b->s1 <= s) { b->s1 = s; b->x1 = x; b->y1 = y; }
+    else if (b->s2 <= s && (x + b->dist < b->x1 || x > b->x1 + b->dist)) { b->s2 = s; b->x2 = x; b->y2 = y; }
+}
 static inline void sink_report(i32* best, u32* bx, u32* by, i32 s, u32 x, u32 y)
 {
     if (*best <= s) { *best = s; *bx = x; *by = y; }
+    if (g_best2) best2_report(g_best2, s, x, y);
 }
 
 /* returns 1 when scored, 0 when text_len < pattern_len (score/sink left at BestSink defaults) */
@@ -307,7 +319,7 @@ int orc_banded_gotoh_one(int B, int type, const orc_scheme* S, const i32* qtab,
                          const u8* P, const u8* Q, u32 M, const u8* T, u32 N,
                          i32* out_score, u32* out_x, u32* out_y)
 {
-    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    i32 best = ORC_SINK_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
     *out_score = best; *out_x = bx; *out_y = by;
     if (N < M) return 0;
 
@@ -380,6 +392,22 @@ void orc_banded_gotoh(int B, int type, const orc_scheme* S, const i32* qtab,
             pat + p_off[i], qual ? qual + p_off[i] : NULL, p_len[i],
             txt + t_off[i], t_len[i], &score[i], &sink_x[i], &sink_y[i]);
         if (ok) ok[i] = (u8)r;
+    }
+}
+
+/* banded Gotoh with a Best2Sink: out6[i] = (score1, sink1.x, sink1.y, score2, sink2.x, sink2.y) as int64 */
+void orc_banded_gotoh_best2(int B, int type, const orc_scheme* S, const u8* pat, const u32* p_off, const u32* p_len,
+                            const u8* txt, const u32* t_off, const u32* t_len, u32 n, u32 distinct_dist, long long* out6)
+{
+    for (u32 i = 0; i < n; ++i)
+    {
+        orc_best2 b = { ORC_SINK_MIN, ORC_SINK_MIN, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, distinct_dist };
+        i32 sc; u32 x, y;
+        g_best2 = &b;
+        orc_banded_gotoh_one(B, type, S, NULL, pat + p_off[i], NULL, p_len[i], txt + t_off[i], t_len[i], &sc, &x, &y);
+        g_best2 = NULL;
+        long long* o = out6 + 6 * (size_t)i;
+        o[0] = b.s1; o[1] = b.x1; o[2] = b.y1; o[3] = b.s2; o[4] = b.x2; o[5] = b.y2;
     }
 }
 
@@ -471,7 +499,7 @@ void orc_banded_gotoh_window(int B, int type, const orc_scheme* S, const i32* qt
 {
     for (u32 i = 0; i < n; ++i)
     {
-        if (wb == 0) { score[i] = INT_MIN; sink_x[i] = sink_y[i] = 0xFFFFFFFFu; alive[i] = 1; }
+        if (wb == 0) { score[i] = ORC_SINK_MIN; sink_x[i] = sink_y[i] = 0xFFFFFFFFu; alive[i] = 1; }
         if (!alive[i] || wb >= p_len[i]) continue;
         const u32 e = we < p_len[i] ? we : p_len[i];
         alive[i] = (u8)orc_banded_gotoh_window_one(B, type, S, qtab, pat + p_off[i], qual ? qual + p_off[i] : NULL, p_len[i],
@@ -494,7 +522,7 @@ u32 orc_banded_traceback_one(int B, int type, const orc_scheme* S,
                              const u8* P, u32 M, const u8* T, u32 N,
                              i32* out_score, u32* sink_xy, u32* source_xy, u8* ops, u32 max_ops, u32* clips)
 {
-    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    i32 best = ORC_SINK_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
     *out_score = best; sink_xy[0] = sink_xy[1] = source_xy[0] = source_xy[1] = 0xFFFFFFFFu; clips[0] = clips[1] = 0;
     if (N < M) return 0;
     const int packed_cache = !(B == 3 || B == 5 || B == 7 || B == 15);
@@ -613,7 +641,7 @@ void orc_banded_traceback(int B, int type, const orc_scheme* S,
 void orc_gotoh_full_one(int type, const orc_scheme* S, const i32* qtab, const u8* P, const u8* Q, u32 M, const u8* T, u32 N,
                         i32* out_score, u32* out_x, u32* out_y)
 {
-    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    i32 best = ORC_SINK_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
     const i32 Go = S->pattern_gap_open, Ge = S->pattern_gap_ext;
     const i32 INF = SHRT_MIN - (Go < Ge ? Go : Ge);
     const size_t W = (size_t)M + 1;
@@ -671,7 +699,7 @@ void orc_gotoh_full(int type, const orc_scheme* S, const i32* qtab,
 u32 orc_gotoh_full_traceback_one(int type, const orc_scheme* S, const u8* P, u32 M, const u8* T, u32 N,
                                  i32* out_score, u32* sink_xy, u32* source_xy, u8* ops, u32 max_ops, u32* clips)
 {
-    i32 best = INT_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
+    i32 best = ORC_SINK_MIN; u32 bx = 0xFFFFFFFFu, by = 0xFFFFFFFFu;
     *out_score = best; sink_xy[0] = sink_xy[1] = source_xy[0] = source_xy[1] = 0xFFFFFFFFu; clips[0] = clips[1] = 0;
     if (M == 0 || N == 0) return 0;
     const i32 Go = S->pattern_gap_open, Ge = S->pattern_gap_ext;

@@ -117,6 +117,19 @@ class Oracle(_Base):
         self.last_locate_steps = int(steps)
         return out
 
+    def banded_gotoh_best2(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, distinct_dist=0):
+        """the plain-C banded DP feeding a restated aln::Best2Sink<int32>: int64 [n, 6]"""
+        pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+        p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+        t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+        if len(scheme) == 4:
+            scheme = (scheme[0], scheme[1], scheme[2], scheme[3], scheme[2], scheme[3])
+        s6 = np.array(scheme, dtype=np.int32)
+        out = np.zeros((len(p_off), 6), dtype=np.int64)
+        self.lib.orc_banded_gotoh_best2(C.c_int(band), C.c_int(typ), _p(s6), _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len),
+                                        C.c_uint32(len(p_off)), C.c_uint32(distinct_dist), _p(out))
+        return out
+
     def banded_gotoh(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=None, qtab=None):
         """scheme = (match, mismatch, gap_open, gap_ext) or a 6-tuple
         (match, mismatch, pattern_gap_open, pattern_gap_ext, text_gap_open, text_gap_ext)."""
@@ -318,6 +331,17 @@ class Ref(_Base):
         r = self.lib.ref_generic_rank(C.c_int(word_bits), C.c_uint32(K), C.c_uint64(n), _p(text), _p(words), _p(occ), _p(qi), _p(qc), C.c_uint32(len(qi)), _p(out))
         assert r == 0, (word_bits, K)
         return words, occ[:((n + K - 1) // K) * 4], out
+
+    def banded_gotoh_best2(self, band, typ, scheme, pat, p_off, p_len, txt, t_off, t_len, distinct_dist=0):
+        """aln::banded_alignment_score<band> into aln::Best2Sink<int32>(distinct_dist): int64 [n, 6] (bands 7 / 15 / 31)"""
+        pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+        p_off = np.ascontiguousarray(p_off, dtype=np.uint32); p_len = np.ascontiguousarray(p_len, dtype=np.uint32)
+        t_off = np.ascontiguousarray(t_off, dtype=np.uint32); t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+        out = np.zeros((len(p_off), 6), dtype=np.int64)
+        r = self.lib.ref_banded_gotoh_best2(C.c_int(band), C.c_int(typ), C.c_int(scheme[0]), C.c_int(scheme[1]), C.c_int(scheme[2]), C.c_int(scheme[3]),
+                                            _p(pat), _p(p_off), _p(p_len), _p(txt), _p(t_off), _p(t_len), C.c_uint32(len(p_off)), C.c_uint32(distinct_dist), _p(out))
+        assert r == 0
+        return out
 
     def nvbowtie_scheme(self, preset=0, match_bonus=0, mm_min=2, mm_max=6, read_gap=(5, 3), ref_gap=(5, 3)):
         """nvBowtie's own SmithWatermanScoringScheme<QualCost<int>,ConstantCost<int>> (scoring.h:203-317), compiled from the reference:

@@ -540,4 +540,27 @@ int ref_generic_rank(int word_bits, uint32 K, uint64 n, const uint8* text, void*
     return -1;
 }
 
+
+// banded Gotoh with aln::Best2Sink<int32>(distinct_dist) (nvbio/alignment/sink.h:114-147): out6 = (score1, sink1, score2, sink2) per alignment
+int ref_banded_gotoh_best2(int band, int type, int match, int mismatch, int gap_open, int gap_ext,
+                           const uint8* pat, const uint32* p_off, const uint32* p_len, const uint8* txt, const uint32* t_off, const uint32* t_len,
+                           uint32 n, uint32 distinct_dist, long long* out6)
+{
+    const aln::SimpleGotohScheme s( match, mismatch, gap_open, gap_ext );
+    #pragma omp parallel for schedule(static)
+    for (int64 i = 0; i < int64(n); ++i)
+    {
+        aln::Best2Sink<int32> sink( distinct_dist );
+        const str_view P( p_len[i], pat + p_off[i] ), T( t_len[i], txt + t_off[i] );
+#define B2(B, TY) aln::banded_alignment_score<B>( aln::make_gotoh_aligner<TY>( s ), P, T, INT_MIN, sink )
+        if (band == 15) { if (type == 0) B2(15, aln::GLOBAL); else if (type == 1) B2(15, aln::LOCAL); else B2(15, aln::SEMI_GLOBAL); }
+        else if (band == 31) { if (type == 0) B2(31, aln::GLOBAL); else if (type == 1) B2(31, aln::LOCAL); else B2(31, aln::SEMI_GLOBAL); }
+        else { if (type == 0) B2(7, aln::GLOBAL); else if (type == 1) B2(7, aln::LOCAL); else B2(7, aln::SEMI_GLOBAL); }
+#undef B2
+        long long* o = out6 + 6 * i;
+        o[0] = sink.score1; o[1] = sink.sink1.x; o[2] = sink.sink1.y; o[3] = sink.score2; o[4] = sink.sink2.x; o[5] = sink.sink2.y;
+    }
+    return (band == 7 || band == 15 || band == 31) ? 0 : -1;
+}
+
 } // extern "C"

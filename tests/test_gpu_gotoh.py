@@ -98,7 +98,7 @@ def test_mixed_batch_fallback_list(O):
     # text shorter than the pattern -> BestSink defaults
     short = (np.zeros(10, np.uint8), np.array([0], np.uint32), np.array([10], np.uint32), np.zeros(8, np.uint8), np.array([0], np.uint32), np.array([5], np.uint32))
     s, x, y = run(31, 1, (2, -2, -5, -3), short, pbits=2, tbits=2, tbe=True)
-    assert int(s[0]) == -2**31 and int(x[0]) == 0xFFFFFFFF and int(y[0]) == 0xFFFFFFFF
+    assert int(s[0]) == -2**30 and int(x[0]) == 0xFFFFFFFF            # NVB_SINK_MIN = the reference's Field_traits<int32>::min() and int(y[0]) == 0xFFFFFFFF
 
 
 def test_quality_table_scheme(O):
@@ -461,3 +461,23 @@ def test_quality_scheme_vs_nvbowtie_scheme_object():
         s, x, y = run(int(band), int(typ), sch, pr, pbits=4, tbits=8, quals=g[f"d{cid}_qual"])
         assert np.array_equal(np.asarray(s, np.int64)[ok], res[0][ok]) and np.array_equal(np.asarray(x, np.int64)[ok], res[1][ok]) \
             and np.array_equal(np.asarray(y, np.int64)[ok], res[2][ok]), (cid, band, typ)
+
+
+def test_best2_sink(O):
+    """nvb_banded_gotoh_score_best2 == the banded DP feeding aln::Best2Sink<int32>(distinct_dist) (oracle restatement, itself pinned to the
+    reference templates in tests/test_oracle.py): best and distinct second-best (score, sink) of every alignment"""
+    rng = np.random.default_rng(8)
+    for band in (7, 15, 31):
+        for typ in (0, 1, 2):
+            for dist in (0, 10):
+                pr = random_problems(rng, 500, band, 150)
+                pat, p_off, p_len, txt, t_off, t_len = pr
+                P = PackedStringSet.from_symbols(pat, p_off, p_len, bits=4, big_endian=True)
+                T = PackedStringSet.from_symbols(txt, t_off, t_len, bits=8, big_endian=False)
+                got = aln.batch_banded_alignment_score_best2(band, aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -2, -5, -3)), P, T, distinct_dist=dist)
+                torch.cuda.synchronize()
+                want = O.banded_gotoh_best2(band, typ, (2, -2, -5, -3), *pr, distinct_dist=dist)
+                g = got.cpu().numpy().astype(np.int64)
+                g[:, [1, 2, 4, 5]] &= 0xFFFFFFFF
+                valid = t_len >= p_len
+                assert np.array_equal(g[valid], want[valid]), (band, typ, dist)

