@@ -75,7 +75,7 @@ struct PatStream {
         if (bits == 2) return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
         return ((y & 0x11111111u) << 3) | ((y & 0x22222222u) << 1) | ((y >> 1) & 0x22222222u) | ((y >> 3) & 0x11111111u);
     }
-    __host__ __device__ __forceinline__ PatStream(const uint32_t* words, uint32_t b, uint32_t e, uint32_t off)
+    __host__ __device__ __forceinline__ PatStream(const uint32_t* words, uint32_t b, uint32_t e, uint32_t off, uint32_t /*len*/ = 0u)
         : bits(b), be(e), spw(32u / b) {
         const uint32_t lg = (b == 2 ? 4u : (b == 4 ? 3u : 2u));
         const uint32_t r = off & (spw - 1u);
@@ -96,17 +96,21 @@ struct PatStream {
 // run-time format dispatch in the per-row fetch -- a shift to extract, a shift to advance, a counter
 template <int BITS>
 struct PatStreamBE {
-    const uint32_t* wp; uint32_t w, left;
-    __host__ __device__ __forceinline__ PatStreamBE(const uint32_t* words, uint32_t /*bits*/, uint32_t /*be*/, uint32_t off) {
+    // one word of look-ahead: the word after the current one is requested when the current one is taken into use, 16 / 8 rows before
+    // its first symbol is needed, so the row loop never waits for a global load (never beyond the pattern's last word)
+    const uint32_t* wp; const uint32_t* last; uint32_t w, nxt, left;
+    __host__ __device__ __forceinline__ PatStreamBE(const uint32_t* words, uint32_t /*bits*/, uint32_t /*be*/, uint32_t off, uint32_t len) {
         constexpr uint32_t SPW = 32u / BITS, LG = (BITS == 2 ? 4u : 3u);
         const uint32_t r = off & (SPW - 1u);
         wp = words + (off >> LG);
-        w = *wp++ << (BITS * r);
+        last = words + ((off + (len ? len - 1u : 0u)) >> LG);
+        w = *wp << (BITS * r);
+        nxt = (wp < last) ? wp[1] : 0u;
         left = SPW - r;
     }
     __host__ __device__ __forceinline__ uint32_t next() {
         constexpr uint32_t SPW = 32u / BITS;
-        if (left == 0u) { w = *wp++; left = SPW; }
+        if (left == 0u) { ++wp; w = nxt; nxt = (wp < last) ? wp[1] : 0u; left = SPW; }
         const uint32_t s = w >> (32u - BITS);
         w <<= BITS;
         --left;
@@ -501,7 +505,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         for (int j = 0; j < B - 1; ++j) F[j] = INF2;
     }
 
-    typename PatStreamOf<PFMT>::type pr0(pwords, pbits, pbe, poff0), pr1(pwords, pbits, pbe, poff1);
+    typename PatStreamOf<PFMT>::type pr0(pwords, pbits, pbe, poff0, M0), pr1(pwords, pbits, pbe, poff1, M1);
     const uint32_t Mmax = M0 > M1 ? M0 : M1;
     int32_t bk0 = -1, bk1 = -1; uint32_t bi0 = 0, bi1 = 0;       // LOCAL: best row key (H << 5 | j) and its row, per half
 

@@ -164,7 +164,7 @@ void run_banded_window(const aln::SimpleGotohScheme scheme,
     #pragma omp parallel for schedule(static)
     for (int64 i = 0; i < int64(n); ++i)
     {
-        if (wb == 0) { score[i] = INT_MIN; sink_x[i] = sink_y[i] = uint32(-1); alive[i] = 1; }
+        if (wb == 0) { const aln::BestSink<int32> fresh; score[i] = fresh.score; sink_x[i] = fresh.sink.x; sink_y[i] = fresh.sink.y; alive[i] = 1; }   // the reference's own defaults
         if (!alive[i] || wb >= p_len[i]) continue;
         aln::BestSink<int32> sink;
         sink.score = score[i]; sink.sink = make_uint2( sink_x[i], sink_y[i] );

@@ -115,7 +115,7 @@ static void run_window(const GotohScheme& S, const uint32_t* pw, uint32_t pbits,
                        uint32_t n, uint32_t wb, uint32_t we, const int32_t* min_score, int16_t* ckpt, int32_t* score, uint32_t* sx, uint32_t* sy, uint8_t* alive) {
     for (uint32_t i = 0; i < n; ++i) {
         SinkResult r;
-        if (wb == 0) { r.score = INT_MIN; r.x = r.y = 0xFFFFFFFFu; score[i] = r.score; sx[i] = r.x; sy[i] = r.y; alive[i] = 1; }
+        if (wb == 0) { r.score = NVB_SINK_MIN; r.x = r.y = 0xFFFFFFFFu; score[i] = r.score; sx[i] = r.x; sy[i] = r.y; alive[i] = 1; }
         else { if (!alive[i]) continue; r.score = score[i]; r.x = sx[i]; r.y = sy[i]; }
         if (wb >= plen[i]) continue;
         const bool ok = gotoh_window<B, TYPE>(S, pw, pbits, pbe, poff[i], plen[i], quals, tw, tbits, tbe, toff[i], tlen[i],
