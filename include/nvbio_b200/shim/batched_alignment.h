@@ -30,6 +30,9 @@ namespace b200 {
 
 using nvbio::b200::check;
 using nvbio::b200::stats;
+using nvbio::b200::scratch;
+using nvbio::b200::SCRATCH_LAYOUT; using nvbio::b200::SCRATCH_SCORE; using nvbio::b200::SCRATCH_SINK; using nvbio::b200::SCRATCH_TEMP;
+using nvbio::b200::SCRATCH_PATTERNS; using nvbio::b200::SCRATCH_QUALS;
 
 // ------------------------------------------------------------------------------------------------------
 // customisation point: where do the strings of a stream live?
@@ -76,7 +79,7 @@ struct gotoh_scheme_of< GotohAligner<TYPE_T,SimpleGotohScheme,algorithm_tag> >
 {
     static const bool supported = true;
     static const int  TYPE      = int(TYPE_T);           // GLOBAL 0, LOCAL 1, SEMI_GLOBAL 2 == NVB_GLOBAL / NVB_LOCAL / NVB_SEMI_GLOBAL
-    static nvb_gotoh_scheme get(const GotohAligner<TYPE_T,SimpleGotohScheme,algorithm_tag>& a, thrust::device_vector<int32>&)
+    static nvb_gotoh_scheme get(const GotohAligner<TYPE_T,SimpleGotohScheme,algorithm_tag>& a)
     {
         nvb_gotoh_scheme s;
         s.match = a.scheme.m_match;               s.mismatch = a.scheme.m_mismatch;
@@ -199,10 +202,7 @@ struct engine
     {
         const uint32 n = stream.size();
         if (n == 0u) return;
-        m_layout.resize( 4u * size_t(n) );
-        m_score.resize( n );
-        m_sink.resize( n );
-        uint32* p_off = thrust::raw_pointer_cast( m_layout.data() );
+        uint32* p_off = (uint32*)scratch( SCRATCH_LAYOUT, 4u * size_t(n) * sizeof(uint32) );
         uint32* p_len = p_off + n; uint32* t_off = p_len + n; uint32* t_len = t_off + n;
         const uint32 grid = (n + 127u) / 128u;
 
@@ -214,29 +214,22 @@ struct engine
         T.bits = nvbio::b200::packed_string<text_string>::BITS;    T.big_endian = nvbio::b200::packed_string<text_string>::BE;
         T.d_offsets = t_off; T.d_lengths = t_len; T.stride = 0u; T.length = binding::max_text_length( stream );
 
-        const nvb_gotoh_scheme scheme = scheme_of::get( stream.aligner(), m_table );
-        int32_t*   d_score = (int32_t*)thrust::raw_pointer_cast( m_score.data() );
-        nvb_uint2* d_sink  = (nvb_uint2*)thrust::raw_pointer_cast( m_sink.data() );
+        const nvb_gotoh_scheme scheme = scheme_of::get( stream.aligner() );
+        int32_t*   d_score = (int32_t*)scratch( SCRATCH_SCORE, size_t(n) * sizeof(int32_t) );
+        nvb_uint2* d_sink  = (nvb_uint2*)scratch( SCRATCH_SINK, size_t(n) * sizeof(nvb_uint2) );
         size_t bytes = 0u;
         int r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, NULL, &bytes, NULL )
                          : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, NULL, &bytes, NULL );
         if (r != NVB_E_TEMP_SIZE) check( r, "DP temp size query" );
-        if (m_temp.size() < bytes + 256u) m_temp.resize( bytes + 256u );
-        bytes = m_temp.size();
-        r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, thrust::raw_pointer_cast( m_temp.data() ), &bytes, NULL )
-                     : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, thrust::raw_pointer_cast( m_temp.data() ), &bytes, NULL );
+        void* d_temp = scratch( SCRATCH_TEMP, bytes + 256u );
+        bytes += 256u;
+        r = band_len ? nvb_banded_gotoh_score( int(band_len), scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, d_temp, &bytes, NULL )
+                     : nvb_gotoh_score( scheme_of::TYPE, &scheme, &P, d_quals, &T, n, d_score, d_sink, d_temp, &bytes, NULL );
         check( r, band_len ? "nvb_banded_gotoh_score" : "nvb_gotoh_score" );
 
-        output_kernel<<<grid,128>>>( stream, (const int32*)d_score, (const uint2*)thrust::raw_pointer_cast( m_sink.data() ) );
+        output_kernel<<<grid,128>>>( stream, (const int32*)d_score, (const uint2*)d_sink );
         if (band_len) stats().banded_score++; else stats().full_score++;
     }
-
-    thrust::device_vector<uint32>   m_layout;
-    thrust::device_vector<int32>    m_score;
-    thrust::device_vector<uint2>    m_sink;
-    thrust::device_vector<uint8>    m_temp;
-    thrust::device_vector<uint8>    m_pat, m_qual;          // materialised patterns / qualities
-    thrust::device_vector<int32>    m_table;                // quality-dependent substitution table (scheme_of::get)
 
 private:
     // patterns readable in place
@@ -254,13 +247,12 @@ private:
                nvb_string_set& P, const uint8_t*& d_quals, std::true_type)
     {
         const uint32 p_stride = (binding::max_pattern_length( stream ) + 3u) & ~3u;
-        m_pat.resize( size_t(stream.size()) * p_stride + 16u );
-        m_qual.resize( size_t(stream.size()) * p_stride + 16u );
-        materialise_kernel<<<grid,128>>>( stream, p_stride, thrust::raw_pointer_cast( m_pat.data() ), thrust::raw_pointer_cast( m_qual.data() ),
-                                          p_off, p_len, t_off, t_len );
-        P.d_words = (const uint32_t*)thrust::raw_pointer_cast( m_pat.data() );
+        uint8* d_pat  = (uint8*)scratch( SCRATCH_PATTERNS, size_t(stream.size()) * p_stride + 16u );
+        uint8* d_qual = (uint8*)scratch( SCRATCH_QUALS,    size_t(stream.size()) * p_stride + 16u );
+        materialise_kernel<<<grid,128>>>( stream, p_stride, d_pat, d_qual, p_off, p_len, t_off, t_len );
+        P.d_words = (const uint32_t*)d_pat;
         P.bits = 8u; P.big_endian = 0u;
-        d_quals = (const uint8_t*)thrust::raw_pointer_cast( m_qual.data() );
+        d_quals = d_qual;
     }
 };
 

@@ -37,15 +37,15 @@ struct gotoh_scheme_of< GotohAligner<TYPE_T, bowtie2::cuda::SmithWatermanScoring
     typedef bowtie2::cuda::SmithWatermanScoringScheme<MMCost,NCost> scheme_type;
     static const bool supported = true;
     static const int  TYPE      = int(TYPE_T);
-    static nvb_gotoh_scheme get(const GotohAligner<TYPE_T,scheme_type,algorithm_tag>& a, thrust::device_vector<int32>& table)
+    static nvb_gotoh_scheme get(const GotohAligner<TYPE_T,scheme_type,algorithm_tag>& a)
     {
-        table.resize( 512u );
-        qual_table_kernel<<<1,256>>>( a.scheme, thrust::raw_pointer_cast( table.data() ) );
+        int32* table = (int32*)nvbio::b200::scratch( nvbio::b200::SCRATCH_TABLE, 512u * sizeof(int32) );
+        qual_table_kernel<<<1,256>>>( a.scheme, table );
         nvb_gotoh_scheme s;
         s.match = a.scheme.match( 0 );                         s.mismatch = a.scheme.mismatch( 0 );
         s.pattern_gap_open = a.scheme.pattern_gap_open();      s.pattern_gap_ext = a.scheme.pattern_gap_extension();
         s.text_gap_open    = a.scheme.text_gap_open();         s.text_gap_ext    = a.scheme.text_gap_extension();
-        s.d_qual_table = thrust::raw_pointer_cast( table.data() );
+        s.d_qual_table = table;
         // bounds of the table's values for the packed 16-bit path: the host evaluation, widened by one for float rounding differences
         int32 lo = 0, hi = 0;
         for (uint32 q = 0; q < 256u; ++q)

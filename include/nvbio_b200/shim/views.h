@@ -47,6 +47,44 @@ struct shim_stats
 inline shim_stats& stats() { static shim_stats s = { 0u, 0u, 0u, 0u, 0u }; return s; }
 
 // ------------------------------------------------------------------------------------------------------
+// grow-only device scratch, one arena per (host thread, slot).  The reference's convenience functions construct a batch object per
+// call (batched_inl.h:984-1101) and thrust::device_vector members would cost a cudaMalloc + cudaFree each, which is more than
+// the DP of a small batch takes.  Every shim launch goes to the legacy default stream, so consecutive calls that reuse an arena are
+// ordered; growing an arena goes through cudaFree, which synchronises.  The arenas are released at process exit by the driver.
+// ------------------------------------------------------------------------------------------------------
+enum scratch_slot { SCRATCH_LAYOUT = 0, SCRATCH_SCORE, SCRATCH_SINK, SCRATCH_TEMP, SCRATCH_PATTERNS, SCRATCH_QUALS, SCRATCH_TABLE, SCRATCH_SLOTS };
+
+inline void* scratch(const scratch_slot slot, const size_t bytes)
+{
+    struct arena { void* ptr; size_t bytes; int device; };
+    static thread_local arena arenas[SCRATCH_SLOTS] = {};
+    int device = 0;
+    if (cudaGetDevice( &device ) != cudaSuccess) check( NVB_E_INVALID, "cudaGetDevice" );
+    arena& a = arenas[slot];
+    if (a.ptr == NULL || a.device != device || a.bytes < bytes)
+    {
+        if (a.ptr)
+        {
+            if (a.device != device) { cudaSetDevice( a.device ); cudaFree( a.ptr ); cudaSetDevice( device ); }
+            else                      cudaFree( a.ptr );
+            a.ptr = NULL; a.bytes = 0u;
+        }
+        size_t cap = bytes + bytes / 2u;
+        if (cap < (size_t(1u) << 16)) cap = size_t(1u) << 16;
+        cap = (cap + 255u) & ~size_t(255u);
+        if (cudaMalloc( &a.ptr, cap ) != cudaSuccess)
+        {
+            cudaGetLastError();
+            cap = (bytes + 255u) & ~size_t(255u);
+            if (cudaMalloc( &a.ptr, cap ) != cudaSuccess) { a.ptr = NULL; check( NVB_E_INVALID, "device scratch allocation" ); }
+        }
+        a.bytes = cap; a.device = device;
+    }
+    return a.ptr;
+}
+template <typename T> inline T* scratch(const scratch_slot slot, const size_t count, const T*) { return (T*)scratch( slot, count * sizeof(T) ); }
+
+// ------------------------------------------------------------------------------------------------------
 // word iterators whose raw device pointer can be recovered
 // ------------------------------------------------------------------------------------------------------
 template <typename It> struct word_pointer { static const bool supported = false; typedef void value_type; };

@@ -15,6 +15,8 @@ void nvb_debug_full_minb(int minb);
 void nvb_debug_full_warp(int mode);
 /* 0: always the run-time-format pair kernel (PFMT 0); 1 (default): the compile-time 2- / 4-bit big-endian kernels where they apply */
 void nvb_debug_pair_format(int on);
+/* 1 (default): the banded pair kernels keep two pattern rows in flight per thread; 0: one row per loop iteration */
+void nvb_debug_pair_rows2(int on);
 
 /* seed + extend composition: 0 = automatic (the per-read path when no per-hit output is requested), 1 = always the per-hit path */
 void nvb_debug_pipeline_path(int path);

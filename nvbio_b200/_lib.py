@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnvbio_b200.so")
+LIB_PATH = os.environ.get("NVBIO_B200_LIB") or os.path.join(_HERE, "libnvbio_b200.so")     # (the override is for A/B experiments on kernels)
 
 EXPORTS = [
     "nvb_version", "nvb_error_string",

@@ -108,13 +108,46 @@ struct PatStreamBE {
         nxt = (wp < last) ? wp[1] : 0u;
         left = SPW - r;
     }
+    // branch-free (selects and one predicated load), so that the row loop of gotoh_pair is a single basic block; past the end of
+    // the pattern it keeps delivering symbol 0
     __host__ __device__ __forceinline__ uint32_t next() {
         constexpr uint32_t SPW = 32u / BITS;
-        if (left == 0u) { ++wp; w = nxt; nxt = (wp < last) ? wp[1] : 0u; left = SPW; }
+        const bool refill = (left == 0u);
+        const bool more = refill && (wp + 1 < last);
+        const uint32_t fresh = more ? wp[2] : 0u;
+        w = refill ? nxt : w;
+        nxt = refill ? fresh : nxt;
+        wp += refill ? 1 : 0;
+        left = refill ? SPW : left;
         const uint32_t s = w >> (32u - BITS);
         w <<= BITS;
         --left;
         return s;
+    }
+};
+// Word-at-a-time reader of a BITS-bit big-endian pattern: next() returns the next 32 / BITS symbols ALIGNED to the top of a word
+// (a funnel shift of two consecutive stream words; the pattern may start at any symbol offset), with one word of look-ahead.
+// Past the pattern's last word it delivers zeros and touches no memory.
+template <int BITS>
+struct PatChunksBE {
+    const uint32_t* wp; const uint32_t* last; uint32_t cur, nxt, sh;
+    __host__ __device__ __forceinline__ PatChunksBE(const uint32_t* words, uint32_t off, uint32_t len) {
+        constexpr uint32_t SPW = 32u / BITS, LG = (BITS == 2 ? 4u : 3u);
+        wp = words + (off >> LG);
+        last = words + ((off + (len ? len - 1u : 0u)) >> LG);
+        sh = BITS * (off & (SPW - 1u));
+        cur = *wp;
+        nxt = (wp < last) ? wp[1] : 0u;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+#ifdef __CUDA_ARCH__
+        const uint32_t c = __funnelshift_l(nxt, cur, sh);
+#else
+        const uint32_t c = sh ? ((cur << sh) | (nxt >> (32u - sh))) : cur;
+#endif
+        ++wp; cur = nxt;
+        nxt = (wp < last) ? wp[1] : 0u;
+        return c;
     }
 };
 template <int PFMT> struct PatStreamOf      { typedef PatStream type; };
@@ -436,6 +469,7 @@ static inline bool pair_path_ok(int B, int type, const nvb_gotoh_scheme* s, uint
 #define NVB_VIADDMAX_RELU(a, b, c) __viaddmax_s16x2_relu((a), (b), (c))
 #define NVB_VIMAX_RELU(a, b)       __vimax_s16x2_relu((a), (b))
 #define NVB_VIMAX3(a, b, c)        __vimax3_s16x2((a), (b), (c))
+#define NVB_VIMAX3_U(a, b, c)      __vimax3_u16x2((a), (b), (c))
 #ifdef __CUDA_ARCH__
 #define NVB_VIMAX(a, b)            __vmaxs2((a), (b))
 #define NVB_VIADD(a, b)            __vadd2((a), (b))
@@ -453,6 +487,92 @@ static inline uint32_t nvb_host_vmaxu2(uint32_t a, uint32_t b) {
 #define NVB_VIMAX_U(a, b)          nvb_host_vmaxu2((a), (b))
 #endif
 
+// one LOCAL band cell of the packed pair (see the formulation in gotoh_pair), in three steps so that the cells of two rows can be
+// written interleaved (pair_local_cell2); j is a compile-time constant after unrolling.
+//   front: selector -> substitution scores, F[j], t' = max(H_diag + s, F')      (independent of the row's E chain, except cell B-1)
+//   h    : h' = max(t', E', beta)                                               (chain)
+//   back : H = h' + Go (IMAD), key, row maximum of the keys, E' = max(E' + Ge, H)   (chain)
+template <int B>
+__host__ __device__ __forceinline__ uint32_t pair_local_front(const GotohScheme& S, const int j, const uint32_t (&G)[B], uint32_t (&F)[B - 1],
+        const uint16_t* srow, const uint32_t sel_stride, const uint32_t P0, const uint32_t P1, const uint32_t Ge2, const uint32_t INFb2, const uint32_t E)
+{
+    const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
+    if (j == B - 1) return NVB_VIADDMAX(G[j], s, E);
+    F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INFb2, Ge2, G[j + 1]);
+    return NVB_VIADDMAX(G[j], s, F[j]);
+}
+template <int B>
+__host__ __device__ __forceinline__ uint32_t pair_local_h(const int j, const uint32_t t, const uint32_t E, const uint32_t beta2)
+{
+    return (j == 0 || j == B - 1) ? NVB_VIMAX(t, beta2) : NVB_VIMAX3(t, E, beta2);
+}
+template <int B>
+__host__ __device__ __forceinline__ void pair_local_back(const GotohScheme& S, const int j, uint32_t (&G)[B], const uint32_t hb,
+        const uint32_t Ge2, const uint32_t GoX, uint32_t& E, uint32_t& rowkey, uint32_t& pk)
+{
+    G[j] = hb * S.one + GoX;                                       // IMAD: H = h' + Go per half
+    const uint32_t key = G[j] * S.keymul + (uint32_t)(j | (j << 16));   // IMAD: (H << 5) | j per half, H < 2048
+    // row maximum of the keys, two cells per VIMNMX3.U16x2 (pk holds the even cell's key until the odd one arrives)
+    if (j & 1)           rowkey = NVB_VIMAX3_U(rowkey, pk, key);
+    else if (j == B - 1) rowkey = NVB_VIMAX_U(rowkey, key);
+    else                 pk = key;
+    E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
+}
+template <int B>
+__host__ __device__ __forceinline__ void pair_local_cell(const GotohScheme& S, const int j, uint32_t (&G)[B], uint32_t (&F)[B - 1],
+        const uint16_t* srow, const uint32_t sel_stride, const uint32_t P0, const uint32_t P1,
+        const uint32_t Ge2, const uint32_t beta2, const uint32_t GoX, const uint32_t INFb2, uint32_t& E, uint32_t& rowkey, uint32_t& pk)
+{
+    const uint32_t t = pair_local_front<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, INFb2, E);
+    const uint32_t hb = pair_local_h<B>(j, t, E, beta2);
+    pair_local_back<B>(S, j, G, hb, Ge2, GoX, E, rowkey, pk);
+}
+// cell jA of row A and cell jB = jA - 2 of the row below it, statement by statement: the two rows' chains alternate in the
+// instruction stream.  (Row A touches G/F[jA], [jA+1]; row B touches [jB], [jB+1] = [jA-2], [jA-1]: disjoint.)
+template <int B>
+__host__ __device__ __forceinline__ void pair_local_cell2(const GotohScheme& S, const int jA, const int jB, uint32_t (&G)[B], uint32_t (&F)[B - 1],
+        const uint16_t* srowA, const uint16_t* srowB, const uint32_t sel_stride,
+        const uint32_t PA0, const uint32_t PA1, const uint32_t PB0, const uint32_t PB1,
+        const uint32_t Ge2, const uint32_t beta2, const uint32_t GoX, const uint32_t INFb2,
+        uint32_t& EA, uint32_t& rkA, uint32_t& pkA, uint32_t& EB, uint32_t& rkB, uint32_t& pkB)
+{
+    const uint32_t tA = pair_local_front<B>(S, jA, G, F, srowA, sel_stride, PA0, PA1, Ge2, INFb2, EA);
+    const uint32_t tB = pair_local_front<B>(S, jB, G, F, srowB, sel_stride, PB0, PB1, Ge2, INFb2, EB);
+    const uint32_t hA = pair_local_h<B>(jA, tA, EA, beta2);
+    const uint32_t hB = pair_local_h<B>(jB, tB, EB, beta2);
+    pair_local_back<B>(S, jA, G, hA, Ge2, GoX, EA, rkA, pkA);
+    pair_local_back<B>(S, jB, G, hB, Ge2, GoX, EB, rkB, pkB);
+}
+
+// GLOBAL / SEMI_GLOBAL cells: the same front (with the unbiased infimum), h = max(t, E), G = h + Go as a packed add (values may
+// be negative: no carry-free IMAD here), no sink keys (the sink is read off the last row)
+template <int B>
+__host__ __device__ __forceinline__ void pair_nl_back(const int j, uint32_t (&G)[B], const uint32_t t, const uint32_t Ge2, const uint32_t Go2, uint32_t& E)
+{
+    const uint32_t h = (j == 0 || j == B - 1) ? t : NVB_VIMAX(t, E);
+    G[j] = NVB_VIADD(h, Go2);
+    E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
+}
+template <int B>
+__host__ __device__ __forceinline__ void pair_nl_cell(const GotohScheme& S, const int j, uint32_t (&G)[B], uint32_t (&F)[B - 1],
+        const uint16_t* srow, const uint32_t sel_stride, const uint32_t P0, const uint32_t P1,
+        const uint32_t Ge2, const uint32_t Go2, const uint32_t INF2, uint32_t& E)
+{
+    const uint32_t t = pair_local_front<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, INF2, E);
+    pair_nl_back<B>(j, G, t, Ge2, Go2, E);
+}
+template <int B>
+__host__ __device__ __forceinline__ void pair_nl_cell2(const GotohScheme& S, const int jA, const int jB, uint32_t (&G)[B], uint32_t (&F)[B - 1],
+        const uint16_t* srowA, const uint16_t* srowB, const uint32_t sel_stride,
+        const uint32_t PA0, const uint32_t PA1, const uint32_t PB0, const uint32_t PB1,
+        const uint32_t Ge2, const uint32_t Go2, const uint32_t INF2, uint32_t& EA, uint32_t& EB)
+{
+    const uint32_t tA = pair_local_front<B>(S, jA, G, F, srowA, sel_stride, PA0, PA1, Ge2, INF2, EA);
+    const uint32_t tB = pair_local_front<B>(S, jB, G, F, srowB, sel_stride, PB0, PB1, Ge2, INF2, EB);
+    pair_nl_back<B>(jA, G, tA, Ge2, Go2, EA);
+    pair_nl_back<B>(jB, G, tB, Ge2, Go2, EB);
+}
+
 // Preconditions (checked by the caller, else the generic path is used):
 //   M0,M1 >= 1; N_k >= M_k + B - 1 (no pad symbol is ever read inside an alignment's own rows);
 //   text is 2-bit; TYPE != LOCAL => M0 == M1; scheme admitted by pair_path_ok().
@@ -460,7 +580,11 @@ static inline uint32_t nvb_host_vmaxu2(uint32_t a, uint32_t b) {
 // (shared memory on the device: conflict-free u16 column per thread).
 // PFMT: 0 = pattern format and quality table handled at run time; 2 / 4 = 2- / 4-bit big-endian patterns AND no quality table, both
 // known at compile time (the dispatcher guarantees it): the per-row preamble loses its format dispatch and its table branch
-template <int B, int TYPE, int PFMT = 0>
+// ROWS2: two pattern rows per loop iteration, the second one trailing the first by two band cells.  A row is one serial
+// chain h' -> H -> E' (three dependent instructions per cell); two rows in flight give every thread two independent chains, which is
+// what hides the ALU latency at 4 warps per scheduler.  The in-place update of G[] / F[] stays valid: row i+1 reads cells j, j+1 of
+// row i after row i has written them (it is at cell j+2) and row i never looks back.
+template <int B, int TYPE, int PFMT = 0, bool ROWS2 = false>
 __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe,
         uint32_t poff0, uint32_t M0, uint32_t poff1, uint32_t M1,
@@ -481,8 +605,9 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
     // per-row substitution profile of both alignments; with a quality table the two scores of a row come from
     // table[2*qual], table[2*qual+1] (nvBowtie's SmithWatermanScoringScheme::substitution)
 #define NVB_ROW_PROFILES(i)                                                                                   \
-    const uint32_t q0 = ((i) < M0) ? pr0.next() : 255u;                                                       \
-    const uint32_t q1 = ((i) < M1) ? pr1.next() : 255u;                                                       \
+    /* fixed-format streams run on past the end (symbol 0): rows beyond an alignment's own length are never reported */ \
+    const uint32_t q0 = (PFMT != 0 || (i) < M0) ? pr0.next() : 255u;                                          \
+    const uint32_t q1 = (PFMT != 0 || (i) < M1) ? pr1.next() : 255u;                                          \
     int32_t e0 = c_eq, n0 = c_ne, e1 = c_eq, n1 = c_ne;                                                        \
     if (PFMT == 0 && S.qtab) {                                                                                \
         const uint32_t qq0 = (quals && (i) < M0) ? quals[poff0 + (i)] : 0u;                                   \
@@ -522,54 +647,133 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
         for (int j = 0; j < B; ++j) G[j] = 0u;
 #pragma unroll
         for (int j = 0; j < B - 1; ++j) F[j] = INFb2;
-        for (uint32_t i = 0; i < Mmax; ++i) {
+        // later rows win ties: replace when H_row >= H_best, i.e. key_row >= (key_best with its column bits cleared)
+#define NVB_LOCAL_ROW_END(i, rowkey)                                                                            \
+        {   const int32_t k0 = (int32_t)((rowkey) & 0xFFFFu), k1 = (int32_t)((rowkey) >> 16);                  \
+            if ((i) < M0 && k0 >= (bk0 & ~31)) { bk0 = k0; bi0 = (i); }                                         \
+            if ((i) < M1 && k1 >= (bk1 & ~31)) { bk1 = k1; bi1 = (i); } }
+        uint32_t i = 0;
+        constexpr int SK = 2;                                      // ROWS2: row i+1 trails row i by two cells (one would read a stale G)
+#define NVB_LOCAL_TWO_ROWS(i, PA0, PA1, PB0, PB1)                                                               \
+        {   const uint16_t* srowA = sel + (size_t)(i) * sel_stride;                                                 \
+            const uint16_t* srowB = srowA + sel_stride;                                                             \
+            uint32_t EA = 0, EB = 0, rkA = 0, rkB = 0, pkA = 0, pkB = 0;                                        \
+            _Pragma("unroll")                                                                                   \
+            for (int jj = 0; jj < B + SK; ++jj) {                                                               \
+                if (jj >= SK && jj < B)                                                                         \
+                    pair_local_cell2<B>(S, jj, jj - SK, G, F, srowA, srowB, sel_stride, PA0, PA1, PB0, PB1, Ge2, beta2, GoX, INFb2, \
+                                              EA, rkA, pkA, EB, rkB, pkB);                                      \
+                else if (jj < B) pair_local_cell<B>(S, jj,      G, F, srowA, sel_stride, PA0, PA1, Ge2, beta2, GoX, INFb2, EA, rkA, pkA); \
+                else             pair_local_cell<B>(S, jj - SK, G, F, srowB, sel_stride, PB0, PB1, Ge2, beta2, GoX, INFb2, EB, rkB, pkB); \
+            }                                                                                                   \
+            NVB_LOCAL_ROW_END(i, rkA)                                                                           \
+            NVB_LOCAL_ROW_END((i) + 1u, rkB) }
+        if (ROWS2 && PFMT != 0) {
+            // compile-time pattern format: the symbols of 16 (2-bit) / 8 (4-bit) rows arrive as one aligned word per alignment, so
+            // a row costs a shift per alignment instead of a stream refill check (rows past an alignment's own length read zeros
+            // and are never reported)
+            constexpr uint32_t PB_ = (PFMT != 0) ? (uint32_t)PFMT : 2u, SPW = 32u / PB_, QM = (1u << PB_) - 1u;
+            PatChunksBE<(int)PB_> pc0(pwords, poff0, M0), pc1(pwords, poff1, M1);
+            uint32_t c0 = 0, c1 = 0;
+            for (uint32_t base = 0; base < Mmax; base += SPW) {
+                c0 = pc0.next(); c1 = pc1.next();
+                const uint32_t end = (base + SPW < Mmax) ? base + SPW : Mmax;
+                for (; i + 1u < end; i += 2u) {
+                    const uint32_t qa0 = c0 >> (32u - PB_), qb0 = (c0 >> (32u - 2u * PB_)) & QM;
+                    const uint32_t qa1 = c1 >> (32u - PB_), qb1 = (c1 >> (32u - 2u * PB_)) & QM;
+                    c0 <<= 2u * PB_; c1 <<= 2u * PB_;
+                    const uint32_t PA0 = prof_tab ? prof_tab[qa0] : sub_profile(qa0, c_eq, c_ne), PA1 = prof_tab ? prof_tab[qa1] : sub_profile(qa1, c_eq, c_ne);
+                    const uint32_t PB0 = prof_tab ? prof_tab[qb0] : sub_profile(qb0, c_eq, c_ne), PB1 = prof_tab ? prof_tab[qb1] : sub_profile(qb1, c_eq, c_ne);
+                    NVB_LOCAL_TWO_ROWS(i, PA0, PA1, PB0, PB1)
+                }
+            }
+            if (i < Mmax) {                                        // odd number of rows: the last one, its symbols at the top of c0 / c1
+                const uint32_t q0 = c0 >> (32u - PB_), q1 = c1 >> (32u - PB_);
+                const uint32_t P0 = prof_tab ? prof_tab[q0] : sub_profile(q0, c_eq, c_ne), P1 = prof_tab ? prof_tab[q1] : sub_profile(q1, c_eq, c_ne);
+                const uint16_t* srow = sel + (size_t)i * sel_stride;
+                uint32_t E = 0, rowkey = 0, pk = 0;
+#pragma unroll
+                for (int j = 0; j < B; ++j)
+                    pair_local_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, beta2, GoX, INFb2, E, rowkey, pk);
+                NVB_LOCAL_ROW_END(i, rowkey)
+                ++i;
+            }
+        } else if (ROWS2) {
+            for (; i + 1u < Mmax; i += 2u) {
+                uint32_t PA0, PA1, PB0, PB1;
+                { NVB_ROW_PROFILES(i)      PA0 = P0; PA1 = P1; }
+                { NVB_ROW_PROFILES(i + 1u) PB0 = P0; PB1 = P1; }
+                NVB_LOCAL_TWO_ROWS(i, PA0, PA1, PB0, PB1)
+            }
+        }
+        if (!(ROWS2 && PFMT != 0))                                 // (that path has consumed every row)
+        for (; i < Mmax; ++i) {
             NVB_ROW_PROFILES(i)
             const uint16_t* srow = sel + (size_t)i * sel_stride;
-            uint32_t E = 0, rowkey = 0;
+            uint32_t E = 0, rowkey = 0, pk = 0;
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
-                uint32_t hb;
-                if (j == 0) {
-                    F[0] = NVB_VIADDMAX(F[1], Ge2, G[1]);
-                    hb = NVB_VIMAX(NVB_VIADDMAX(G[0], s, F[0]), beta2);
-                } else if (j < B - 1) {
-                    F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INFb2, Ge2, G[j + 1]);
-                    hb = NVB_VIMAX3(NVB_VIADDMAX(G[j], s, F[j]), E, beta2);
-                } else {
-                    hb = NVB_VIMAX(NVB_VIADDMAX(G[j], s, E), beta2);
-                }
-                G[j] = hb * S.one + GoX;                                       // IMAD: H = h' + Go per half
-                const uint32_t key = G[j] * S.keymul + (uint32_t)(j | (j << 16));   // IMAD: (H << 5) | j per half, H < 2048
-                rowkey = NVB_VIMAX_U(rowkey, key);
-                E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
-            }
-            // later rows win ties: replace when H_row >= H_best, i.e. key_row >= (key_best with its column bits cleared)
-            const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
-            if (i < M0 && k0 >= (bk0 & ~31)) { bk0 = k0; bi0 = i; }
-            if (i < M1 && k1 >= (bk1 & ~31)) { bk1 = k1; bi1 = i; }
+            for (int j = 0; j < B; ++j)
+                pair_local_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, beta2, GoX, INFb2, E, rowkey, pk);
+            NVB_LOCAL_ROW_END(i, rowkey)
         }
+#undef NVB_LOCAL_ROW_END
+#undef NVB_LOCAL_TWO_ROWS
     } else {
-        for (uint32_t i = 0; i < Mmax; ++i) {
+        // GLOBAL / SEMI_GLOBAL (M0 == M1): the same loop structure as LOCAL
+        uint32_t i = 0;
+        constexpr int SK = 2;
+#define NVB_NL_TWO_ROWS(i, PA0, PA1, PB0, PB1)                                                                  \
+        {   const uint16_t* srowA = sel + (size_t)(i) * sel_stride;                                             \
+            const uint16_t* srowB = srowA + sel_stride;                                                         \
+            uint32_t EA = 0, EB = 0;                                                                            \
+            _Pragma("unroll")                                                                                   \
+            for (int jj = 0; jj < B + SK; ++jj) {                                                               \
+                if (jj >= SK && jj < B)                                                                         \
+                    pair_nl_cell2<B>(S, jj, jj - SK, G, F, srowA, srowB, sel_stride, PA0, PA1, PB0, PB1, Ge2, Go2, INF2, EA, EB); \
+                else if (jj < B) pair_nl_cell<B>(S, jj,      G, F, srowA, sel_stride, PA0, PA1, Ge2, Go2, INF2, EA); \
+                else             pair_nl_cell<B>(S, jj - SK, G, F, srowB, sel_stride, PB0, PB1, Ge2, Go2, INF2, EB); \
+            } }
+        if (ROWS2 && PFMT != 0) {
+            constexpr uint32_t PB_ = (PFMT != 0) ? (uint32_t)PFMT : 2u, SPW = 32u / PB_, QM = (1u << PB_) - 1u;
+            PatChunksBE<(int)PB_> pc0(pwords, poff0, M0), pc1(pwords, poff1, M1);
+            uint32_t c0 = 0, c1 = 0;
+            for (uint32_t base = 0; base < Mmax; base += SPW) {
+                c0 = pc0.next(); c1 = pc1.next();
+                const uint32_t end = (base + SPW < Mmax) ? base + SPW : Mmax;
+                for (; i + 1u < end; i += 2u) {
+                    const uint32_t qa0 = c0 >> (32u - PB_), qb0 = (c0 >> (32u - 2u * PB_)) & QM;
+                    const uint32_t qa1 = c1 >> (32u - PB_), qb1 = (c1 >> (32u - 2u * PB_)) & QM;
+                    c0 <<= 2u * PB_; c1 <<= 2u * PB_;
+                    const uint32_t PA0 = prof_tab ? prof_tab[qa0] : sub_profile(qa0, c_eq, c_ne), PA1 = prof_tab ? prof_tab[qa1] : sub_profile(qa1, c_eq, c_ne);
+                    const uint32_t PB0 = prof_tab ? prof_tab[qb0] : sub_profile(qb0, c_eq, c_ne), PB1 = prof_tab ? prof_tab[qb1] : sub_profile(qb1, c_eq, c_ne);
+                    NVB_NL_TWO_ROWS(i, PA0, PA1, PB0, PB1)
+                }
+            }
+            if (i < Mmax) {
+                const uint32_t q0 = c0 >> (32u - PB_), q1 = c1 >> (32u - PB_);
+                const uint32_t P0 = prof_tab ? prof_tab[q0] : sub_profile(q0, c_eq, c_ne), P1 = prof_tab ? prof_tab[q1] : sub_profile(q1, c_eq, c_ne);
+                const uint16_t* srow = sel + (size_t)i * sel_stride;
+                uint32_t E = 0;
+#pragma unroll
+                for (int j = 0; j < B; ++j) pair_nl_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, Go2, INF2, E);
+                ++i;
+            }
+        } else if (ROWS2) {
+            for (; i + 1u < Mmax; i += 2u) {
+                uint32_t PA0, PA1, PB0, PB1;
+                { NVB_ROW_PROFILES(i)      PA0 = P0; PA1 = P1; }
+                { NVB_ROW_PROFILES(i + 1u) PB0 = P0; PB1 = P1; }
+                NVB_NL_TWO_ROWS(i, PA0, PA1, PB0, PB1)
+            }
+        }
+#undef NVB_NL_TWO_ROWS
+        if (!(ROWS2 && PFMT != 0))
+        for (; i < Mmax; ++i) {
             NVB_ROW_PROFILES(i)
             const uint16_t* srow = sel + (size_t)i * sel_stride;
             uint32_t E = 0;
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const uint32_t s = prmt(P0, P1, (uint32_t)srow[(size_t)j * sel_stride]);
-                uint32_t h;
-                if (j == 0) {
-                    F[0] = NVB_VIADDMAX(F[1], Ge2, G[1]);
-                    h = NVB_VIADDMAX(G[0], s, F[0]);
-                } else if (j < B - 1) {
-                    F[j] = (j < B - 2) ? NVB_VIADDMAX(F[j + 1], Ge2, G[j + 1]) : NVB_VIADDMAX(INF2, Ge2, G[j + 1]);
-                    h = NVB_VIMAX(NVB_VIADDMAX(G[j], s, F[j]), E);
-                } else {
-                    h = NVB_VIADDMAX(G[j], s, E);
-                }
-                G[j] = NVB_VIADD(h, Go2);
-                E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
-            }
+            for (int j = 0; j < B; ++j) pair_nl_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, Go2, INF2, E);
         }
     }
 

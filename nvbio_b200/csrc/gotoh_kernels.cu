@@ -14,6 +14,7 @@
 
 namespace nvb {
 
+static int g_pair_rows2 = 1;            // nvb_debug_pair_rows2(0): one row per loop iteration in the pair kernels
 static bool g_pair_fmt_ok = true;       // nvb_debug_pair_format(0) forces the run-time-format kernel (tests compare the two)
 
 constexpr int PAIR_BLOCKDIM    = 128;
@@ -71,11 +72,18 @@ static int launch_best2(const GotohScheme& S, const GotohBatch& b, uint32_t dist
     return NVB_OK;
 }
 
-template <int B, int TYPE, int PFMT>
-__global__ void __launch_bounds__(PAIR_BLOCKDIM)
+// a word of sixteen 2-bit symbols with their order reversed (little-endian <-> big-endian symbol order)
+__device__ __forceinline__ uint32_t swap_2bit_order(uint32_t x) {
+    const uint32_t r = __brev(x);
+    return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+// ROWS2: two pattern rows in flight per thread (gotoh_pair)
+template <int B, int TYPE, int PFMT, bool ROWS2>
+__global__ void __launch_bounds__(PAIR_BLOCKDIM, 4)
 gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
 {
-    extern __shared__ uint16_t sel_smem[];            // [sel_rows][PAIR_BLOCKDIM]
+    extern __shared__ uint16_t sel_smem[];            // [sel_rows rounded up to 16][PAIR_BLOCKDIM]
     // substitution profile of every possible pattern symbol (constant schemes): one LDS per row instead of building it
     __shared__ uint32_t prof_tab[256];
     for (uint32_t q = threadIdx.x; q < 256u; q += PAIR_BLOCKDIM) prof_tab[q] = sub_profile(q, S.match - S.pgo, S.mismatch - S.pgo);
@@ -118,37 +126,57 @@ gotoh_pair_kernel(const GotohScheme S, const GotohBatch b, uint32_t sel_rows, ui
             const uint32_t sh0 = 2u * (t0 & 15u), sh1 = 2u * (t1 & 15u);
             const uint32_t last0 = (t0 + N0 - 1u) >> 4, last1 = (t1 + N1 - 1u) >> 4;   // last word holding a window symbol
             const uint32_t nw = (L + 15u) >> 4;
-            uint32_t p0 = w[w0], p1 = w[w1];
-#pragma unroll 2
-            for (uint32_t k = 0; k < nw; ++k) {
-                // never touch a word beyond the window's last one (symbols past N are defined as 0 below anyway)
-                const uint32_t n0 = (w0 + k + 1u <= last0) ? w[w0 + k + 1u] : 0u;
-                const uint32_t n1 = (w1 + k + 1u <= last1) ? w[w1 + k + 1u] : 0u;
-                uint32_t c0, c1;
-                if (be) {
-                    c0 = sh0 ? ((p0 << sh0) | (n0 >> (32u - sh0))) : p0;
-                    c1 = sh1 ? ((p1 << sh1) | (n1 >> (32u - sh1))) : p1;
-                } else {
-                    c0 = sh0 ? ((p0 >> sh0) | (n0 << (32u - sh0))) : p0;
-                    c1 = sh1 ? ((p1 >> sh1) | (n1 << (32u - sh1))) : p1;
-                }
-                p0 = n0; p1 = n1;
-                const uint32_t first = k << 4;
+            // the window words are fetched eight (+1) per alignment at a time, all loads of a batch independent of each other: a
+            // thread pays two or three DRAM round trips for its two windows instead of one per word (the windows sit at random
+            // genome positions, and at 16 warps per SM nobody else hides that latency)
+            // (the shared array is sized for whole words of 16 columns, so no per-column bound checks: symbols past a window's end
+            // are masked to 0 per word, columns past L are written and never read)
+            for (uint32_t kb = 0; kb < nw; kb += 8u) {
+                uint32_t a0[9], a1[9];
 #pragma unroll
-                for (uint32_t s16 = 0; s16 < 16u; ++s16) {
-                    const uint32_t t = first + s16;
-                    if (t < L) {
-                        const uint32_t shf = be ? (30u - 2u * s16) : (2u * s16);
-                        const uint32_t g0 = (t < N0) ? ((c0 >> shf) & 3u) : 0u;
-                        const uint32_t g1 = (t < N1) ? ((c1 >> shf) & 3u) : 0u;
-                        my_sel[t * PAIR_BLOCKDIM] = (uint16_t)pair_selector(g0, g1);
+                for (uint32_t q = 0; q < 9u; ++q) {
+                    // never touch a word beyond the window's last one
+                    a0[q] = (w0 + kb + q <= last0) ? w[w0 + kb + q] : 0u;
+                    a1[q] = (w1 + kb + q <= last1) ? w[w1 + kb + q] : 0u;
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < 8u; ++q) {
+                    const uint32_t k = kb + q;
+                    if (k < nw) {
+                        uint32_t c0, c1;
+                        if (be) {
+                            c0 = sh0 ? ((a0[q] << sh0) | (a0[q + 1] >> (32u - sh0))) : a0[q];
+                            c1 = sh1 ? ((a1[q] << sh1) | (a1[q + 1] >> (32u - sh1))) : a1[q];
+                        } else {
+                            c0 = sh0 ? ((a0[q] >> sh0) | (a0[q + 1] << (32u - sh0))) : a0[q];
+                            c1 = sh1 ? ((a1[q] >> sh1) | (a1[q + 1] << (32u - sh1))) : a1[q];
+                        }
+                        const uint32_t first = k << 4;
+                        // symbols of this word inside the window: v0, v1 in [0, 16]; the rest read as symbol 0
+                        const uint32_t v0 = N0 > first ? (N0 - first < 16u ? N0 - first : 16u) : 0u;
+                        const uint32_t v1 = N1 > first ? (N1 - first < 16u ? N1 - first : 16u) : 0u;
+                        const uint32_t m0 = v0 >= 16u ? 0xFFFFFFFFu : (be ? ~(0xFFFFFFFFu >> (2u * v0)) : ((1u << (2u * v0)) - 1u));
+                        const uint32_t m1 = v1 >= 16u ? 0xFFFFFFFFu : (be ? ~(0xFFFFFFFFu >> (2u * v1)) : ((1u << (2u * v1)) - 1u));
+                        c0 &= m0; c1 &= m1;
+                        if (!be) { c0 = swap_2bit_order(c0); c1 = swap_2bit_order(c1); }        // first symbol in the top bits from here on
+                        // four columns at a time: one byte of each window side by side, then per column a shift, a mask and an IMAD
+                        //   x = g0 | g1 << 8;  pair_selector(g0, g1) = 0xC480 + x * 0x11
+#pragma unroll
+                        for (uint32_t by = 0; by < 4u; ++by) {
+                            const uint32_t W = prmt(c0, c1, (3u - by) | ((7u - by) << 4) | 0x3200u);      // byte `by` (from the top) of c0 | of c1 << 8
+#pragma unroll
+                            for (uint32_t m = 0; m < 4u; ++m) {
+                                const uint32_t x = (W >> (6u - 2u * m)) & 0x0303u;
+                                my_sel[(first + 4u * by + m) * PAIR_BLOCKDIM] = (uint16_t)(x * 0x11u + 0xC480u);
+                            }
+                        }
                     }
                 }
             }
         }
 
         SinkResult r0, r1;
-        gotoh_pair<B, TYPE, PFMT>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
+        gotoh_pair<B, TYPE, PFMT, ROWS2>(S, b.pat.words, b.pat.bits, b.pat.big_endian,
                             str_off(b.pat, a0), M0, str_off(b.pat, a1), M1, N0, N1,
                             my_sel, PAIR_BLOCKDIM, r0, r1, b.quals, prof_tab);
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
@@ -497,10 +525,10 @@ static int launch_generic(const GotohScheme& S, const GotohBatch& b, const uint3
     return NVB_OK;
 }
 
-template <int B, int TYPE, int PFMT>
+template <int B, int TYPE, int PFMT, bool ROWS2>
 static int launch_pair_fmt(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
 {
-    const size_t smem = (size_t)sel_rows * PAIR_BLOCKDIM * sizeof(uint16_t);
+    const size_t smem = (size_t)((sel_rows + 15u) & ~15u) * PAIR_BLOCKDIM * sizeof(uint16_t);   // whole words of 16 columns
     // the attribute is per DEVICE: a host that drives several GPUs from one process (nvBowtie's one compute thread per
     // device) must set it on each; one atomic flag per (instantiation, device)
     static std::atomic<bool> attr_done[NVB_MAX_DEVICES];
@@ -508,22 +536,28 @@ static int launch_pair_fmt(const GotohScheme& S, const GotohBatch& b, uint32_t s
     NVB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= NVB_MAX_DEVICES) return NVB_E_UNSUPPORTED;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        NVB_CUDA_TRY(cudaFuncSetAttribute(gotoh_pair_kernel<B, TYPE, PFMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NVB_CUDA_TRY(cudaFuncSetAttribute(gotoh_pair_kernel<B, TYPE, PFMT, ROWS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done[dev].store(true, std::memory_order_release);
     }
     const uint32_t pairs = (b.n_max + 1u) / 2u;
     const uint32_t grid = (pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
-    gotoh_pair_kernel<B, TYPE, PFMT><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
+    gotoh_pair_kernel<B, TYPE, PFMT, ROWS2><<<grid, PAIR_BLOCKDIM, smem, s>>>(S, b, sel_rows, todo, todo_count);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
+}
+template <int B, int TYPE, int PFMT>
+static int launch_pair_rows(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
+{
+    if (g_pair_rows2) return launch_pair_fmt<B, TYPE, PFMT, true>(S, b, sel_rows, todo, todo_count, s);
+    return launch_pair_fmt<B, TYPE, PFMT, false>(S, b, sel_rows, todo, todo_count, s);
 }
 // pattern format known at compile time (2- / 4-bit big-endian, no quality table): the specialised kernels; anything else: PFMT 0
 template <int B, int TYPE>
 static int launch_pair(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
 {
-    if (!S.qtab && b.pat.big_endian && b.pat.bits == 2u && g_pair_fmt_ok) return launch_pair_fmt<B, TYPE, 2>(S, b, sel_rows, todo, todo_count, s);
-    if (!S.qtab && b.pat.big_endian && b.pat.bits == 4u && g_pair_fmt_ok) return launch_pair_fmt<B, TYPE, 4>(S, b, sel_rows, todo, todo_count, s);
-    return launch_pair_fmt<B, TYPE, 0>(S, b, sel_rows, todo, todo_count, s);
+    if (!S.qtab && b.pat.big_endian && b.pat.bits == 2u && g_pair_fmt_ok) return launch_pair_rows<B, TYPE, 2>(S, b, sel_rows, todo, todo_count, s);
+    if (!S.qtab && b.pat.big_endian && b.pat.bits == 4u && g_pair_fmt_ok) return launch_pair_rows<B, TYPE, 4>(S, b, sel_rows, todo, todo_count, s);
+    return launch_pair_rows<B, TYPE, 0>(S, b, sel_rows, todo, todo_count, s);
 }
 
 #define NVB_TYPE_SWITCH(BAND, FN, ...)                                            \
@@ -601,7 +635,7 @@ static int banded_impl(int band, int type, const nvb_gotoh_scheme* scheme,
     // nvbio/alignment/batched_inl.h:1067-1101)
     const uint32_t max_m = patterns->length;
     const uint32_t sel_rows = max_m + (uint32_t)band - 1u;
-    const size_t smem = (size_t)sel_rows * PAIR_BLOCKDIM * sizeof(uint16_t);
+    const size_t smem = (size_t)((sel_rows + 15u) & ~15u) * PAIR_BLOCKDIM * sizeof(uint16_t);          // as launch_pair_fmt sizes it (two-byte selectors)
     const bool fast = (g_force_path != 1) && texts->bits == 2 && max_m >= 1 && smem <= 200u * 1024u &&
                       pair_path_ok(band, type, scheme, max_m);
     if (!fast) return dispatch_generic(band, type, S, b, nullptr, nullptr, n_max, s);
@@ -842,6 +876,7 @@ int nvb_gotoh_traceback(int type, const nvb_gotoh_scheme* scheme, const nvb_stri
 void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
 void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
 void nvb_debug_full_warp(int mode) { g_full_warp = mode; }
+void nvb_debug_pair_rows2(int on) { nvb::g_pair_rows2 = on; }
 void nvb_debug_pair_format(int on) { nvb::g_pair_fmt_ok = on != 0; }
 
 } // extern "C"

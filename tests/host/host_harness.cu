@@ -125,6 +125,8 @@ static void run_window(const GotohScheme& S, const uint32_t* pw, uint32_t pbits,
 }
 
 // mirrors gotoh_pair_kernel: precondition check -> packed pair routine, else generic
+static int g_hh_rows2 = 1;
+
 template <int B, int TYPE>
 static void run_pair(const GotohScheme& S, const uint8_t* quals, const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                      const uint32_t* tw, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen,
@@ -150,9 +152,14 @@ static void run_pair(const GotohScheme& S, const uint8_t* quals, const uint32_t*
         }
         SinkResult q0, q1;
         // the kernel dispatcher's rule (launch_pair): compile-time pattern format for 2- / 4-bit big-endian patterns without a quality table
-        if (!S.qtab && pbe && pbits == 2)      gotoh_pair<B, TYPE, 2>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
-        else if (!S.qtab && pbe && pbits == 4) gotoh_pair<B, TYPE, 4>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
-        else                                   gotoh_pair<B, TYPE, 0>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals);
+#define HH_PAIR2(PF, R2) gotoh_pair<B, TYPE, PF, R2>(S, pw, pbits, pbe, poff[a0], M0, poff[a1], M1, N0, N1, sel.data(), 1, q0, q1, quals)
+        // two rows in flight per loop iteration (the kernels' default), unless switched off
+#define HH_PAIR(PF) do { if (g_hh_rows2) HH_PAIR2(PF, true); else HH_PAIR2(PF, false); } while (0)
+        if (!S.qtab && pbe && pbits == 2)      HH_PAIR(2);
+        else if (!S.qtab && pbe && pbits == 4) HH_PAIR(4);
+        else                                   HH_PAIR(0);
+#undef HH_PAIR
+#undef HH_PAIR2
         score[a0] = q0.score; sx[a0] = q0.x; sy[a0] = q0.y;
         if (has1) { score[a1] = q1.score; sx[a1] = q1.x; sy[a1] = q1.y; }
     }
@@ -309,6 +316,9 @@ int hh_gotoh_traceback(int band, int type, const int32_t* scheme6,
     }
     return -1;
 }
+
+// 1 (default): two pattern rows in flight per loop iteration, as the kernels do; 0: one row
+void hh_set_pair_rows2(int on) { g_hh_rows2 = on; }
 
 // returns -2 when the scheme is not admissible for the packed path
 int hh_gotoh_pair(int band, int type, const int32_t* scheme6, const int32_t* qtab, const uint8_t* quals, uint32_t max_m,

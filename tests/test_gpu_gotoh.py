@@ -76,6 +76,15 @@ def test_packed_path_vs_oracle(O, band, typ):
             for pbits, tbe in ((2, True), (4, False)):
                 force_path(0)
                 assert same(run(band, typ, scheme, pr, pbits=pbits, tbits=2, tbe=tbe, max_m=150), want), (band, typ, scheme, ragged)
+            # kernel variants: run-time pattern format instead of the compile-time 2- / 4-bit big-endian readers; one pattern row per
+            # loop iteration instead of two in flight
+            for fmt, rows2 in ((0, 1), (1, 0), (0, 0)):
+                L = nb.lib()
+                L.nvb_debug_pair_format(C.c_int(fmt)); L.nvb_debug_pair_rows2(C.c_int(rows2))
+                try:
+                    assert same(run(band, typ, scheme, pr, pbits=4, tbits=2, tbe=True, max_m=150), want), (band, typ, scheme, ragged, fmt, rows2)
+                finally:
+                    L.nvb_debug_pair_format(C.c_int(1)); L.nvb_debug_pair_rows2(C.c_int(1))
             force_path(1)
             try:
                 assert same(run(band, typ, scheme, pr, pbits=2, tbits=2, tbe=True, max_m=150), want)

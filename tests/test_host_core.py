@@ -197,9 +197,12 @@ def _gotoh_pair(H, band, typ, scheme6, pr, max_m, pbits=2, pbe=1, tbe=1, qtab=No
     return r, (score, sx, sy), nf.value
 
 
+@pytest.mark.parametrize("rows2", [1, 0])
 @pytest.mark.parametrize("band", [7, 15, 31])
 @pytest.mark.parametrize("typ", [0, 1, 2])
-def test_gotoh_pair(H, O, band, typ):
+def test_gotoh_pair(H, O, band, typ, rows2):
+    """rows2: two pattern rows in flight per loop iteration (odd and even pattern lengths, ragged pairs) / one row"""
+    H.hh_set_pair_rows2(C.c_int(rows2))
     rng = np.random.default_rng(100 + band + typ)
     for scheme in ((2, -2, -5, -3), (2, -1, -1, -1), (0, -5, -8, -3), (1, -3, -2, -4), (2, -6, -8, -3)):
         s6 = scheme + (scheme[2], scheme[3])

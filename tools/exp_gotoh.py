@@ -8,29 +8,38 @@ import nvbio_b200 as nb
 from nvbio_b200 import aln, synth
 from nvbio_b200.strings import PackedStringSet
 
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--n-al", type=int, default=4_000_000)
+ap.add_argument("--bands", type=int, nargs="*", default=[7, 15, 31])
+ap.add_argument("--fmts", type=int, nargs="*", default=[1, 0], help="1 = compile-time pattern format kernels, 0 = run-time format")
+ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--types", type=int, nargs="*", default=[1], help="0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL")
+ap.add_argument("--rows2", type=int, nargs="*", default=[1, 0], help="1 = two pattern rows in flight per thread (LOCAL), 0 = one")
+args = ap.parse_args()
 n = 100_000_000
 gw = synth.random_genome_words(n)
-n_al, M, W = 4_000_000, 151, 300
+n_al, M, W = args.n_al, 151, 300
 rw, pos, _ = synth.sample_reads(gw, n, n_al, M, rc_half=False)
 begin = synth.windows_for_reads(n, pos, M, W)
 P = PackedStringSet.fixed(rw.reshape(-1), n_al, M, stride=rw.shape[1] * 16)
 T = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=begin.to(torch.int32), lengths=None, stride=0, length=W, count=n_al)
-al = aln.make_gotoh_aligner(aln.LOCAL, aln.SimpleGotohScheme(2, -2, -5, -3))
 res = (torch.empty(n_al, dtype=torch.int32, device="cuda"), torch.empty((n_al, 2), dtype=torch.int32, device="cuda"))
 L = nb.lib()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = {}
-for fmt in (1, 0, 1, 0):
-    L.nvb_debug_pair_format(C.c_int(fmt))
-    for band in (7, 15, 31):
+for fmt, rows2 in [(f, r2) for f in args.fmts for r2 in args.rows2]:
+    L.nvb_debug_pair_format(C.c_int(fmt)); L.nvb_debug_pair_rows2(C.c_int(rows2))
+    for band, typ in [(b, t) for t in args.types for b in args.bands]:
+        al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -2, -5, -3))
         temp = torch.empty(aln.banded_temp_bytes(band, al, P, T) + 256, dtype=torch.uint8, device="cuda")
         aln.batch_banded_alignment_score(band, al, P, T, out=res, temp=temp); torch.cuda.synchronize()
         best = 1e30
-        for _ in range(4):
+        for _ in range(args.reps):
             e0.record(); aln.batch_banded_alignment_score(band, al, P, T, out=res, temp=temp); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        key = (band,)
+        key = (band, typ)
         chk = int(res[0].to(torch.int64).sum().item())
         if key in ref: assert ref[key] == chk, "results differ between the two kernels"
         ref[key] = chk
-        print(json.dumps({"pfmt_kernels": bool(fmt), "band": band, "ms": best, "GCUPS": n_al * M * band / best / 1e6}))
+        print(json.dumps({"pfmt_kernels": bool(fmt), "rows2": bool(rows2), "type": typ, "band": band, "ms": best, "GCUPS": n_al * M * band / best / 1e6}))
