@@ -491,7 +491,9 @@ static inline uint32_t nvb_host_vmaxu2(uint32_t a, uint32_t b) {
 // written interleaved (pair_local_cell2); j is a compile-time constant after unrolling.
 //   front: selector -> substitution scores, F[j], t' = max(H_diag + s, F')      (independent of the row's E chain, except cell B-1)
 //   h    : h' = max(t', E', beta)                                               (chain)
-//   back : H = h' + Go (IMAD), key, row maximum of the keys, E' = max(E' + Ge, H)   (chain)
+//   back : H = h' + Go, key (IMAD), row maximum of the keys, E' = max(E' + Ge, H)   (chain)
+struct PairLocalConsts { uint32_t Ge2, GoX, beta2, INFb2; };     // packed per-half constants of the LOCAL pair cells
+
 template <int B>
 __host__ __device__ __forceinline__ uint32_t pair_local_front(const GotohScheme& S, const int j, const uint32_t (&G)[B], uint32_t (&F)[B - 1],
         const uint16_t* srow, const uint32_t sel_stride, const uint32_t P0, const uint32_t P1, const uint32_t Ge2, const uint32_t INFb2, const uint32_t E)
@@ -510,22 +512,25 @@ template <int B>
 __host__ __device__ __forceinline__ void pair_local_back(const GotohScheme& S, const int j, uint32_t (&G)[B], const uint32_t hb,
         const uint32_t Ge2, const uint32_t GoX, uint32_t& E, uint32_t& rowkey, uint32_t& pk)
 {
-    G[j] = hb * S.one + GoX;                                       // IMAD: H = h' + Go per half
+    // H = h' + Go per half, ONE 32-bit add (both halves stay >= 0: no borrow).  With two rows in flight this value is consumed two
+    // cells later by the row below, so it is a plain integer add (ALU pipe, short latency) and not an IMAD: measured on C4, band 31,
+    // 5.27 vs 4.90 TCUPS (profiles/README.md, r02); the key below is off every chain and stays an IMAD on the FMA pipe.
+    G[j] = hb + GoX;
     const uint32_t key = G[j] * S.keymul + (uint32_t)(j | (j << 16));   // IMAD: (H << 5) | j per half, H < 2048
     // row maximum of the keys, two cells per VIMNMX3.U16x2 (pk holds the even cell's key until the odd one arrives)
     if (j & 1)           rowkey = NVB_VIMAX3_U(rowkey, pk, key);
     else if (j == B - 1) rowkey = NVB_VIMAX_U(rowkey, key);
     else                 pk = key;
-    E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
+    if (j < B - 1) E = (j == 0) ? G[0] : NVB_VIADDMAX(E, Ge2, G[j]);
 }
 template <int B>
 __host__ __device__ __forceinline__ void pair_local_cell(const GotohScheme& S, const int j, uint32_t (&G)[B], uint32_t (&F)[B - 1],
         const uint16_t* srow, const uint32_t sel_stride, const uint32_t P0, const uint32_t P1,
-        const uint32_t Ge2, const uint32_t beta2, const uint32_t GoX, const uint32_t INFb2, uint32_t& E, uint32_t& rowkey, uint32_t& pk)
+        const PairLocalConsts& K, uint32_t& E, uint32_t& rowkey, uint32_t& pk)
 {
-    const uint32_t t = pair_local_front<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, INFb2, E);
-    const uint32_t hb = pair_local_h<B>(j, t, E, beta2);
-    pair_local_back<B>(S, j, G, hb, Ge2, GoX, E, rowkey, pk);
+    const uint32_t t = pair_local_front<B>(S, j, G, F, srow, sel_stride, P0, P1, K.Ge2, K.INFb2, E);
+    const uint32_t hb = pair_local_h<B>(j, t, E, K.beta2);
+    pair_local_back<B>(S, j, G, hb, K.Ge2, K.GoX, E, rowkey, pk);
 }
 // cell jA of row A and cell jB = jA - 2 of the row below it, statement by statement: the two rows' chains alternate in the
 // instruction stream.  (Row A touches G/F[jA], [jA+1]; row B touches [jB], [jB+1] = [jA-2], [jA-1]: disjoint.)
@@ -533,15 +538,15 @@ template <int B>
 __host__ __device__ __forceinline__ void pair_local_cell2(const GotohScheme& S, const int jA, const int jB, uint32_t (&G)[B], uint32_t (&F)[B - 1],
         const uint16_t* srowA, const uint16_t* srowB, const uint32_t sel_stride,
         const uint32_t PA0, const uint32_t PA1, const uint32_t PB0, const uint32_t PB1,
-        const uint32_t Ge2, const uint32_t beta2, const uint32_t GoX, const uint32_t INFb2,
+        const PairLocalConsts& K,
         uint32_t& EA, uint32_t& rkA, uint32_t& pkA, uint32_t& EB, uint32_t& rkB, uint32_t& pkB)
 {
-    const uint32_t tA = pair_local_front<B>(S, jA, G, F, srowA, sel_stride, PA0, PA1, Ge2, INFb2, EA);
-    const uint32_t tB = pair_local_front<B>(S, jB, G, F, srowB, sel_stride, PB0, PB1, Ge2, INFb2, EB);
-    const uint32_t hA = pair_local_h<B>(jA, tA, EA, beta2);
-    const uint32_t hB = pair_local_h<B>(jB, tB, EB, beta2);
-    pair_local_back<B>(S, jA, G, hA, Ge2, GoX, EA, rkA, pkA);
-    pair_local_back<B>(S, jB, G, hB, Ge2, GoX, EB, rkB, pkB);
+    const uint32_t tA = pair_local_front<B>(S, jA, G, F, srowA, sel_stride, PA0, PA1, K.Ge2, K.INFb2, EA);
+    const uint32_t tB = pair_local_front<B>(S, jB, G, F, srowB, sel_stride, PB0, PB1, K.Ge2, K.INFb2, EB);
+    const uint32_t hA = pair_local_h<B>(jA, tA, EA, K.beta2);
+    const uint32_t hB = pair_local_h<B>(jB, tB, EB, K.beta2);
+    pair_local_back<B>(S, jA, G, hA, K.Ge2, K.GoX, EA, rkA, pkA);
+    pair_local_back<B>(S, jB, G, hB, K.Ge2, K.GoX, EB, rkB, pkB);
 }
 
 // GLOBAL / SEMI_GLOBAL cells: the same front (with the unbiased infimum), h = max(t, E), G = h + Go as a packed add (values may
@@ -635,18 +640,22 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
     int32_t bk0 = -1, bk1 = -1; uint32_t bi0 = 0, bi1 = 0;       // LOCAL: best row key (H << 5 | j) and its row, per half
 
     if (TYPE == NVB_LOCAL) {
-        // LOCAL formulation, biased by beta = -Go so that the one plain add per cell (h + Go) is carry-free and can be
-        // an IMAD on the FMA pipe:  G[] holds H itself (>= 0), F[] and E hold F+beta / E+beta, h' = h+beta >= beta.
+        // LOCAL formulation, biased by beta = -Go so that the one plain add per cell (h' + Go) is carry-free, i.e. ONE 32-bit add for
+        // both halves:  G[] holds H itself (>= 0), F[] and E hold F+beta / E+beta, h' = h+beta >= beta.
         //   F'[j] = max(F'[j+1]+Ge, H[j+1]);  t' = max(H[j] + (S-Go), F'[j]);  h' = max(t', E', beta);
-        //   H[j] = h' + Go  (IMAD: both halves stay >= 0);  E' = max(E'+Ge, H[j])
+        //   H[j] = h' + Go;  E' = max(E'+Ge, H[j]);  sink key (H << 5) | j = one IMAD on the FMA pipe.
+        // (A variant that biases by |Ge| as well, so that the chain is E' -> h' -> E' with H and E'+Ge formed off the chain by
+        // IMADs, was measured slower: 4.47 TCUPS against 5.27 on C4, band 31 -- every extra IMAD costs issue bandwidth.)
         const int32_t beta = -Go;
-        const uint32_t beta2 = pack16(beta, beta);
-        const uint32_t GoX = (uint32_t)(Go * 65537);                  // Go in both halves, as ONE 32-bit addend
-        const uint32_t INFb2 = pack16(INF + beta, INF + beta);
+        PairLocalConsts K;
+        K.Ge2 = Ge2;
+        K.GoX = (uint32_t)(Go * 65537);                            // Go in both halves, as ONE 32-bit addend
+        K.beta2 = pack16(beta, beta);
+        K.INFb2 = pack16(INF + beta, INF + beta);
 #pragma unroll
         for (int j = 0; j < B; ++j) G[j] = 0u;
 #pragma unroll
-        for (int j = 0; j < B - 1; ++j) F[j] = INFb2;
+        for (int j = 0; j < B - 1; ++j) F[j] = K.INFb2;
         // later rows win ties: replace when H_row >= H_best, i.e. key_row >= (key_best with its column bits cleared)
 #define NVB_LOCAL_ROW_END(i, rowkey)                                                                            \
         {   const int32_t k0 = (int32_t)((rowkey) & 0xFFFFu), k1 = (int32_t)((rowkey) >> 16);                  \
@@ -661,10 +670,10 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
             _Pragma("unroll")                                                                                   \
             for (int jj = 0; jj < B + SK; ++jj) {                                                               \
                 if (jj >= SK && jj < B)                                                                         \
-                    pair_local_cell2<B>(S, jj, jj - SK, G, F, srowA, srowB, sel_stride, PA0, PA1, PB0, PB1, Ge2, beta2, GoX, INFb2, \
+                    pair_local_cell2<B>(S, jj, jj - SK, G, F, srowA, srowB, sel_stride, PA0, PA1, PB0, PB1, K, \
                                               EA, rkA, pkA, EB, rkB, pkB);                                      \
-                else if (jj < B) pair_local_cell<B>(S, jj,      G, F, srowA, sel_stride, PA0, PA1, Ge2, beta2, GoX, INFb2, EA, rkA, pkA); \
-                else             pair_local_cell<B>(S, jj - SK, G, F, srowB, sel_stride, PB0, PB1, Ge2, beta2, GoX, INFb2, EB, rkB, pkB); \
+                else if (jj < B) pair_local_cell<B>(S, jj,      G, F, srowA, sel_stride, PA0, PA1, K, EA, rkA, pkA); \
+                else             pair_local_cell<B>(S, jj - SK, G, F, srowB, sel_stride, PB0, PB1, K, EB, rkB, pkB); \
             }                                                                                                   \
             NVB_LOCAL_ROW_END(i, rkA)                                                                           \
             NVB_LOCAL_ROW_END((i) + 1u, rkB) }
@@ -694,7 +703,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
                 uint32_t E = 0, rowkey = 0, pk = 0;
 #pragma unroll
                 for (int j = 0; j < B; ++j)
-                    pair_local_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, beta2, GoX, INFb2, E, rowkey, pk);
+                    pair_local_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, K, E, rowkey, pk);
                 NVB_LOCAL_ROW_END(i, rowkey)
                 ++i;
             }
@@ -713,7 +722,7 @@ __host__ __device__ inline void gotoh_pair(const GotohScheme& S,
             uint32_t E = 0, rowkey = 0, pk = 0;
 #pragma unroll
             for (int j = 0; j < B; ++j)
-                pair_local_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, Ge2, beta2, GoX, INFb2, E, rowkey, pk);
+                pair_local_cell<B>(S, j, G, F, srow, sel_stride, P0, P1, K, E, rowkey, pk);
             NVB_LOCAL_ROW_END(i, rowkey)
         }
 #undef NVB_LOCAL_ROW_END

@@ -223,7 +223,38 @@ def make_generic_rank(ref):
     np.savez_compressed(os.path.join(OUT, "generic_rank.npz"), **out)
 
 
+def make_nvbwt_files():
+    """(i) index FILES written by the reference's own writer code: nvBWT's save_bwt() / save_ssa() (nvBWT/nvBWT.cu:314-351, compiled by
+    oracle/ref_nvbwt_writer.cu) are called with the arrays of two indices of fmindex.npz, exactly as nvBWT's build() calls them
+    (nvBWT.cu:394-405, 514-515) -> nvbwt_files.npz holds the bytes of the .bwt / .sa files.  Note the reference's save_ssa() writes
+    `&cumFreq` (the address of its pointer argument) where the four cumulative counts belong, so bytes 4..20 of a .sa file written
+    by nvBWT are arbitrary; they are zeroed in the fixture and listed in `sa_unspecified`."""
+    import ctypes as C, tempfile
+    W = C.CDLL(os.path.join(OUT, "..", "..", "oracle", "_ref", "libnvbwt_writer.so"), mode=os.RTLD_LAZY)
+    fm = np.load(os.path.join(OUT, "fmindex.npz"))
+    out = {}
+    for name in ("rand", "rep", "tiny"):
+        n = len(fm[f"{name}_text"]); primary = int(fm[f"{name}_primary"][0])
+        cum = np.ascontiguousarray(fm[f"{name}_L2"][1:5], dtype=np.uint32)
+        words = np.ascontiguousarray(fm[f"{name}_bwt_occ"].reshape(-1, 8)[:, :4]).reshape(-1).astype(np.uint32)
+        seq_words = (n + 15) // 16
+        ssa = np.ascontiguousarray(fm[f"{name}_ssa"], dtype=np.uint32)
+        ssa_len = (n + 16) // 16
+        assert len(ssa) >= ssa_len and len(words) >= seq_words
+        with tempfile.TemporaryDirectory() as d:
+            b, a = os.path.join(d, "x.bwt").encode(), os.path.join(d, "x.sa").encode()
+            W.ref_nvbwt_save_bwt(C.c_uint(n), C.c_uint(seq_words), C.c_uint(primary), cum.ctypes.data_as(C.c_void_p), words.ctypes.data_as(C.c_void_p), b)
+            W.ref_nvbwt_save_ssa(C.c_uint(n), C.c_uint(16), C.c_uint(ssa_len), C.c_uint(primary), cum.ctypes.data_as(C.c_void_p), ssa.ctypes.data_as(C.c_void_p), a)
+            bwt_bytes = np.fromfile(b.decode(), dtype=np.uint8); sa_bytes = np.fromfile(a.decode(), dtype=np.uint8)
+        sa_bytes[4:20] = 0
+        out[f"{name}_bwt_file"] = bwt_bytes; out[f"{name}_sa_file"] = sa_bytes
+    out["sa_unspecified"] = np.array([4, 20], np.uint32)
+    np.savez_compressed(os.path.join(OUT, "nvbwt_files.npz"), **out)
+
+
 def main():
+    if "--only-nvbwt" in sys.argv:
+        make_nvbwt_files(); print("wrote nvbwt_files.npz"); return
     assert orc.Ref.available(), "build oracle/_ref first: make -C oracle"
     ref = orc.Ref()
     if "--only-extras" in sys.argv:
@@ -304,6 +335,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "fmindex.npz"), **fm)
     make_nvbowtie(ref)
     make_generic_rank(ref)
+    make_nvbwt_files()
     print("wrote", os.listdir(OUT))
 
 

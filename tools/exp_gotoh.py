@@ -16,6 +16,7 @@ ap.add_argument("--fmts", type=int, nargs="*", default=[1, 0], help="1 = compile
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--types", type=int, nargs="*", default=[1], help="0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL")
 ap.add_argument("--rows2", type=int, nargs="*", default=[1, 0], help="1 = two pattern rows in flight per thread (LOCAL), 0 = one")
+ap.add_argument("--check-file", default=None, help="JSON of result checksums shared between runs (e.g. of different library builds)")
 args = ap.parse_args()
 n = 100_000_000
 gw = synth.random_genome_words(n)
@@ -28,6 +29,8 @@ res = (torch.empty(n_al, dtype=torch.int32, device="cuda"), torch.empty((n_al, 2
 L = nb.lib()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = {}
+if args.check_file and os.path.exists(args.check_file):
+    ref = {tuple(int(v) for v in k.split(',')): c for k, c in json.load(open(args.check_file)).items()}
 for fmt, rows2 in [(f, r2) for f in args.fmts for r2 in args.rows2]:
     L.nvb_debug_pair_format(C.c_int(fmt)); L.nvb_debug_pair_rows2(C.c_int(rows2))
     for band, typ in [(b, t) for t in args.types for b in args.bands]:
@@ -43,3 +46,5 @@ for fmt, rows2 in [(f, r2) for f in args.fmts for r2 in args.rows2]:
         if key in ref: assert ref[key] == chk, "results differ between the two kernels"
         ref[key] = chk
         print(json.dumps({"pfmt_kernels": bool(fmt), "rows2": bool(rows2), "type": typ, "band": band, "ms": best, "GCUPS": n_al * M * band / best / 1e6}))
+if args.check_file:
+    json.dump({"%d,%d" % k: c for k, c in ref.items()}, open(args.check_file, "w"))
