@@ -259,6 +259,7 @@ struct fm_index_view<
         v.sa_interval = SA_INT;
         v.d_ktab      = NULL;
         v.ktab_k      = 0u;
+        v.ktab_located = 0u;
         cudaPointerAttributes attr;
         const bool on_device = cudaPointerGetAttributes( &attr, f.m_L2 ) == cudaSuccess &&
                                (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);

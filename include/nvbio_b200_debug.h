@@ -17,6 +17,9 @@ void nvb_debug_full_warp(int mode);
 void nvb_debug_pair_format(int on);
 /* 1 (default): the banded pair kernels keep two pattern rows in flight per thread; 0: one row per loop iteration */
 void nvb_debug_pair_rows2(int on);
+/* bytes of unused dynamic shared memory added to every banded pair-kernel CTA: measures what a landing buffer (e.g. for bulk
+   copies of the text windows) would cost in resident CTAs per SM */
+void nvb_debug_pair_extra_smem(int bytes);
 
 /* seed + extend composition: 0 = automatic (the per-read path when no per-hit output is requested), 1 = always the per-hit path */
 void nvb_debug_pipeline_path(int path);

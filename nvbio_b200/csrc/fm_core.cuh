@@ -27,6 +27,7 @@ struct FmIndex {
     uint32_t L2[5];
     uint32_t sa_mask, sa_shift;    // sampled-SA interval I = 1 << sa_shift, mask = I - 1
     uint32_t ktab_k;
+    uint32_t ktab_located;         // 1: table entries are 16 bytes {x, y, SA[x] (valid when x == y), 0} (nvb_fm_build_ktab_located)
     // constant-index selects keep the struct in the kernel-parameter constant bank (a dynamic L2[c]
     // would force a local-memory copy of the whole struct)
     __host__ __device__ __forceinline__ uint32_t l2(uint32_t c) const {
@@ -52,6 +53,7 @@ static inline FmIndex make_fmindex(const nvb_fm_index* f) {
     r.sa_shift = 0; while ((1u << r.sa_shift) < I) ++r.sa_shift;
     r.sa_mask = (1u << r.sa_shift) - 1u;
     r.ktab = (const uint2*)f->d_ktab; r.ktab_k = f->d_ktab ? f->ktab_k : 0u;
+    r.ktab_located = (f->d_ktab && f->ktab_located) ? 1u : 0u;
     return r;
 }
 
@@ -100,6 +102,13 @@ __host__ __device__ __forceinline__ void load_block_if(FmBlock& b, const FmBlock
 __host__ __device__ __forceinline__ uint32_t gather_u32(const uint32_t* __restrict__ p) {
 #ifdef __CUDA_ARCH__
     uint32_t v; asm volatile("ld.global.nc" NVB_FM_LD_QUAL ".u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+#else
+    return *p;
+#endif
+}
+__host__ __device__ __forceinline__ uint4 gather_u4(const uint4* __restrict__ p) {
+#ifdef __CUDA_ARCH__
+    uint4 v; asm volatile("ld.global.nc" NVB_FM_LD_QUAL ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
 #else
     return *p;
 #endif
@@ -254,7 +263,7 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
             u |= (c & 3u) << (2u * j);
         }
         if (!has_n) {                                   // an N among them: take the step-by-step path below
-            const uint2 r = gather_u2(f.ktab + u);
+            const uint2 r = gather_u2(f.ktab_located ? (const uint2*)((const uint4*)f.ktab + u) : f.ktab + u);
             x = r.x; y = r.y; s = f.ktab_k;
         }
     }
@@ -266,6 +275,17 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
         fm_step(f, c, x, y);
     }
     ox = x; oy = y;
+}
+
+// symbols [a, a + cnt) (1 <= cnt <= 16) of a 2-bit big-endian stream in the TOP 2*cnt bits of the result (the low bits are
+// unspecified); touches the second word only when the window really reaches into it
+__host__ __device__ __forceinline__ uint32_t be2_window(const uint32_t* __restrict__ words, uint32_t a, uint32_t cnt)
+{
+    const uint32_t wi = a >> 4, r = a & 15u;
+    const uint32_t w0 = words[wi];
+    if (r == 0u) return w0;
+    const uint32_t w1 = (r + cnt > 16u) ? words[wi + 1u] : 0u;
+    return (w0 << (2u * r)) | (w1 >> (32u - 2u * r));
 }
 
 // match() + locate() of one query in one pass, for callers that only need the hit POSITIONS of narrow ranges (the per-read
@@ -284,28 +304,49 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
 {
     SymReader<BITS, BE> rd(words);
     uint32_t x = 0, y = f.n, s = 0;
+    uint32_t known_pos = 0u; bool have_pos = false;
     if (f.ktab_k && len >= f.ktab_k) {
         uint32_t u = 0; bool has_n = false;
-        for (uint32_t j = 0; j < f.ktab_k; ++j) {
-            const uint32_t c = rd.get(off + len - 1u - j);
-            has_n |= (c > 3u);
-            u |= (c & 3u) << (2u * j);
+        if (BITS == 2 && BE) {
+            // the table index IS the big-endian bit pattern of the last k symbols: one funnel shift instead of k symbol reads
+            u = be2_window(words, off + len - f.ktab_k, f.ktab_k) >> (32u - 2u * f.ktab_k);
+        } else {
+            for (uint32_t j = 0; j < f.ktab_k; ++j) {
+                const uint32_t c = rd.get(off + len - 1u - j);
+                has_n |= (c > 3u);
+                u |= (c & 3u) << (2u * j);
+            }
         }
         if (!has_n) {
-            const uint2 r = gather_u2(f.ktab + u);
-            x = r.x; y = r.y; s = f.ktab_k;
+            if (f.ktab_located) {                       // the entry of a single-row k-mer carries SA[x]: no SA gather below
+                const uint4 e = gather_u4((const uint4*)f.ktab + u);
+                x = e.x; y = e.y; known_pos = e.z; have_pos = (e.x == e.y);
+            } else {
+                const uint2 r = gather_u2(f.ktab + u);
+                x = r.x; y = r.y;
+            }
+            s = f.ktab_k;
         }
     }
     const bool full_sa = (f.sa_shift == 0u) && genome != nullptr;
     for (; s < len && x <= y; ++s) {
         if (full_sa && x == y) {
             const uint32_t rem = len - s;                 // symbols [0, rem) of the query are still to be consumed
-            const uint32_t pos = gather_u32(f.ssa + x);
+            // (have_pos can only be set on the first pass: a single-row range returns from this branch)
+            const uint32_t pos = have_pos ? known_pos : gather_u32(f.ssa + x);
             if (pos == 0xFFFFFFFFu || pos < rem) return FM_EMPTY;
             const uint32_t p0 = pos - rem;
-            SymReader<2, true> tr(genome);
             bool same = true;
-            for (uint32_t i = 0; i < rem; ++i) same &= (rd.get(off + i) == tr.get(p0 + i));
+            if (BITS == 2 && BE) {
+                // both sides are 2-bit big-endian streams: compare up to 16 symbols per step as bit patterns
+                for (uint32_t i = 0; i < rem; i += 16u) {
+                    const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
+                    same &= ((be2_window(words, off + i, cnt) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
+                }
+            } else {
+                SymReader<2, true> tr(genome);
+                for (uint32_t i = 0; i < rem; ++i) same &= (rd.get(off + i) == tr.get(p0 + i));
+            }
             if (!same) return FM_EMPTY;
             ox = p0; oy = 0xFFFFFFFFu;
             return FM_LOCATED;

@@ -117,6 +117,29 @@ fm_ktab_level_kernel(const FmIndex f, uint2* __restrict__ tab, uint32_t prev_ent
     }
 }
 
+// the same with 16-byte entries {x, y, -, -}, and the pass that fills SA[x] into the single-row ones
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_ktab16_level_kernel(const FmIndex f, uint4* __restrict__ tab, uint32_t prev_entries)
+{
+    const uint32_t v = blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (v >= prev_entries) return;
+    const uint4 r = tab[v];
+#pragma unroll
+    for (int c = 3; c >= 0; --c) {
+        uint32_t x = r.x, y = r.y;
+        if (x <= y) fm_step(f, (uint32_t)c, x, y);
+        tab[(size_t)c * prev_entries + v] = make_uint4(x, y, 0u, 0u);
+    }
+}
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_ktab16_locate_kernel(const FmIndex f, uint4* __restrict__ tab, uint64_t entries)
+{
+    const uint64_t v = (uint64_t)blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (v >= entries) return;
+    const uint4 e = tab[v];
+    if (e.x == e.y) tab[v].z = f.ssa[e.x];              // full suffix array (checked by the caller): SA[x], 0xFFFFFFFF for the `$` row
+}
+
 // range sizes as uint64 (filter_inl.h:36-42: 1 + y - x in uint32 arithmetic, widened)
 struct RangeSize {
     __host__ __device__ __forceinline__ uint64_t operator()(const uint2& r) const { return (uint64_t)(uint32_t)(1u + r.y - r.x); }
@@ -258,7 +281,7 @@ const char* nvb_error_string(int err)
 int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream)
 {
     if (!valid_fmindex(fmi) || k < 1 || k > 16 || !d_ktab) return NVB_E_INVALID;
-    nvb_fm_index plain = *fmi; plain.d_ktab = nullptr; plain.ktab_k = 0;
+    nvb_fm_index plain = *fmi; plain.d_ktab = nullptr; plain.ktab_k = 0; plain.ktab_located = 0;
     const FmIndex f = make_fmindex(&plain);
     cudaStream_t s = as_stream(stream);
     const uint2 root = make_uint2(0u, fmi->length);
@@ -269,6 +292,27 @@ int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, vo
         fm_ktab_level_kernel<<<(prev + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, s>>>(f, (uint2*)d_ktab, prev);
         NVB_LAUNCH_CHECK();
     }
+    return NVB_OK;
+}
+
+int nvb_fm_build_ktab_located(const nvb_fm_index* fmi, uint32_t k, void* d_ktab16, void* stream)
+{
+    if (!valid_fmindex(fmi) || k < 1 || k > 16 || !d_ktab16 || ((uintptr_t)d_ktab16 & 15u)) return NVB_E_INVALID;
+    if (fmi->sa_interval != 1u || !fmi->d_ssa) return NVB_E_UNSUPPORTED;
+    nvb_fm_index plain = *fmi; plain.d_ktab = nullptr; plain.ktab_k = 0; plain.ktab_located = 0;
+    const FmIndex f = make_fmindex(&plain);
+    cudaStream_t s = as_stream(stream);
+    const uint4 root = make_uint4(0u, fmi->length, 0u, 0u);
+    NVB_CUDA_TRY(cudaMemcpyAsync(d_ktab16, &root, sizeof(uint4), cudaMemcpyHostToDevice, s));
+    NVB_CUDA_TRY(cudaStreamSynchronize(s));              // `root` lives on this stack frame
+    uint32_t prev = 1;
+    for (uint32_t t = 1; t <= k; ++t, prev *= 4u) {
+        fm_ktab16_level_kernel<<<(prev + FM_BLOCKDIM - 1) / FM_BLOCKDIM, FM_BLOCKDIM, 0, s>>>(f, (uint4*)d_ktab16, prev);
+        NVB_LAUNCH_CHECK();
+    }
+    const uint64_t entries = 1ull << (2u * k);
+    fm_ktab16_locate_kernel<<<(uint32_t)((entries + FM_BLOCKDIM - 1) / FM_BLOCKDIM), FM_BLOCKDIM, 0, s>>>(f, (uint4*)d_ktab16, entries);
+    NVB_LAUNCH_CHECK();
     return NVB_OK;
 }
 

@@ -220,19 +220,48 @@ struct SymSeq {
 
 struct FullPairTrack { int32_t k0, k1; uint32_t r0, r1; int32_t s0, s1; uint32_t x0, x1; };   // LOCAL: best key/row; SEMI: best score/row
 
+// per-row state of the packed full-matrix stripe: left neighbour / diagonal / E of the cell being computed, the row's sink bookkeeping
+struct FullRow { uint32_t Vl, Vd, E, rowkey, vM, vlast; };
+struct FullConsts { uint32_t Ge2, Go2, GoX, beta2, keymul; };
+
+// one cell (column j = 1..FULL_W of the stripe) of text row R; V[j] / F[j] hold the previous row's values on entry and this row's on exit
+template <int TYPE, bool PARTIAL>
+__host__ __device__ __forceinline__ void full_pair_cell(const int j, uint32_t (&V)[FULL_W + 1], uint32_t (&F)[FULL_W + 1], FullRow& R,
+        const uint32_t P0, const uint32_t P1, const uint16_t* sel, const uint32_t sel_stride, const uint32_t ncols, const FullConsts& K)
+{
+    const uint32_t s = prmt(P0, P1, (uint32_t)sel[(size_t)(j - 1) * sel_stride]);
+    F[j] = NVB_VIADDMAX(F[j], K.Ge2, V[j]);
+    R.E  = NVB_VIADDMAX(R.E, K.Ge2, (j == 1) ? R.Vl : V[j - 1]);
+    const uint32_t old = V[j];
+    if (TYPE == NVB_LOCAL) {
+        const uint32_t hb = NVB_VIMAX3(NVB_VIADDMAX(R.Vd, s, F[j]), R.E, K.beta2);
+        V[j] = hb + K.GoX;                                                    // H = h' + Go per half, one 32-bit add (carry-free)
+        const uint32_t key = V[j] * K.keymul + (uint32_t)((j - 1) | ((j - 1) << 16));   // IMAD
+        if (!PARTIAL || (uint32_t)j <= ncols) R.rowkey = NVB_VIMAX_U(R.rowkey, key);
+    } else {
+        const uint32_t h = NVB_VIMAX(NVB_VIADDMAX(R.Vd, s, F[j]), R.E);
+        V[j] = NVB_VIADD(h, K.Go2);
+        if (TYPE == NVB_SEMI_GLOBAL && PARTIAL && (uint32_t)j == ncols) R.vM = V[j];
+    }
+    if (j == FULL_W) R.vlast = V[j];
+    R.Vd = old;
+}
+
+// Two text rows per loop iteration, the second one two columns behind the first (the same idea as in the banded kernel, gotoh_core.cuh:
+// a row is one serial chain E -> h' -> H; two rows in flight give a thread two independent chains).  The in-place V[] / F[] update
+// stays valid: row r+1 reads column j only after row r has written it, and keeps its own diagonal (the value it overwrote).
 template <int TYPE, bool PARTIAL>
 __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, const bool first, const bool last, const uint32_t b,
         const uint32_t ncols, const uint32_t N, SymSeq t0, SymSeq t1, const uint16_t* sel, const uint32_t sel_stride,
         uint2* __restrict__ col, const size_t col_stride, FullPairTrack& trk, uint32_t& g_last, const uint32_t* prof_tab)
 {
     const int32_t Go = S.pgo, Ge = S.pge;
-    const uint32_t Go2 = pack16(Go, Go), Ge2 = pack16(Ge, Ge);
     int32_t INF = SHRT_MIN - (Go < Ge ? Go : Ge);
     if (INF + Ge < -32768) INF = -32768 - Ge;
     const int32_t c_eq = S.match - Go, c_ne = S.mismatch - Go;
     const int32_t beta = -Go;
-    const uint32_t beta2 = pack16(beta, beta);
-    const uint32_t GoX = (uint32_t)(Go * 65537);
+    FullConsts K;
+    K.Ge2 = pack16(Ge, Ge); K.Go2 = pack16(Go, Go); K.GoX = (uint32_t)(Go * 65537); K.beta2 = pack16(beta, beta); K.keymul = S.keymul;
     const uint32_t INFx = (TYPE == NVB_LOCAL) ? pack16(INF + beta, INF + beta) : pack16(INF, INF);
 
     // arrays of the PREVIOUS row: V[j] = H (LOCAL) or H + Go (otherwise) of column b + j; F[j] likewise biased for LOCAL
@@ -247,51 +276,63 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
     uint32_t diag_next = V[0];
     uint32_t left_h = (TYPE == NVB_LOCAL) ? 0u : pack16(((TYPE == NVB_GLOBAL) ? S.tgo : 0) + Go, ((TYPE == NVB_GLOBAL) ? S.tgo : 0) + Go);
     const uint32_t left_step = (TYPE == NVB_GLOBAL) ? pack16(S.tge, S.tge) : 0u;
-    const uint32_t left_e = (TYPE == NVB_LOCAL) ? beta2 : INFx;
-    uint2 nxt = make_uint2(0u, 0u);
-    if (!first) nxt = col[0];
-    for (uint32_t r = 0; r < N; ++r) {
-        const uint32_t g0 = t0.next(), g1 = t1.next();
-        const uint32_t P0 = prof_tab ? prof_tab[g0] : sub_profile(g0, c_eq, c_ne);
-        const uint32_t P1 = prof_tab ? prof_tab[g1] : sub_profile(g1, c_eq, c_ne);
-        uint32_t Vl, E;
-        if (first) { Vl = left_h; E = left_e; left_h = NVB_VIADD(left_h, left_step); }
-        else       { Vl = nxt.x; E = nxt.y; if (r + 1u < N) nxt = col[(size_t)(r + 1u) * col_stride]; }
-        uint32_t Vd = diag_next;
-        diag_next = Vl;
-        V[0] = Vl;
-        uint32_t rowkey = 0u, vM = 0u;
+    const uint32_t left_e = (TYPE == NVB_LOCAL) ? K.beta2 : INFx;
+
+    // the boundary column (H, E) of the stripe to the left, fetched one row pair ahead of its use
+    uint2 nA = make_uint2(0u, 0u), nB = nA;
+    if (!first) { nA = col[0]; if (N > 1u) nB = col[col_stride]; }
+#define NVB_FULL_ROW_BEGIN(R, c_)                                                                               \
+    {   if (first) { R.Vl = left_h; R.E = left_e; left_h = NVB_VIADD(left_h, left_step); }                      \
+        else       { R.Vl = c_.x; R.E = c_.y; }                                                                 \
+        R.Vd = diag_next; diag_next = R.Vl; R.rowkey = 0u; R.vM = 0u; R.vlast = 0u; }
+#define NVB_FULL_ROW_END(R, r)                                                                                  \
+    {   if (!last) col[(size_t)(r) * col_stride] = make_uint2(R.vlast, R.E);                                    \
+        if (TYPE == NVB_LOCAL) {                                                                                \
+            const int32_t k0 = (int32_t)(R.rowkey & 0xFFFFu), k1 = (int32_t)(R.rowkey >> 16);                   \
+            if (k0 >= (trk.k0 & ~7)) { trk.k0 = k0; trk.r0 = (r); }   /* (H, sub-stripe) >= the best's: later rows win ties */ \
+            if (k1 >= (trk.k1 & ~7)) { trk.k1 = k1; trk.r1 = (r); }                                             \
+        }                                                                                                       \
+        if (TYPE == NVB_SEMI_GLOBAL && last) {                                                                  \
+            const uint32_t vm_ = PARTIAL ? R.vM : R.vlast;                                                      \
+            const int32_t h0 = half_lo(vm_) - Go, h1 = half_hi(vm_) - Go;                                       \
+            if (trk.s0 <= h0) { trk.s0 = h0; trk.x0 = (r) + 1u; }                                               \
+            if (trk.s1 <= h1) { trk.s1 = h1; trk.x1 = (r) + 1u; }                                               \
+        } }
+
+    constexpr int SK = 2;
+    uint32_t r = 0;
+    for (; r + 1u < N; r += 2u) {
+        const uint32_t ga0 = t0.next(), ga1 = t1.next(), gb0 = t0.next(), gb1 = t1.next();
+        const uint32_t PA0 = prof_tab ? prof_tab[ga0] : sub_profile(ga0, c_eq, c_ne), PA1 = prof_tab ? prof_tab[ga1] : sub_profile(ga1, c_eq, c_ne);
+        const uint32_t PB0 = prof_tab ? prof_tab[gb0] : sub_profile(gb0, c_eq, c_ne), PB1 = prof_tab ? prof_tab[gb1] : sub_profile(gb1, c_eq, c_ne);
+        FullRow A, B;
+        NVB_FULL_ROW_BEGIN(A, nA)
+        NVB_FULL_ROW_BEGIN(B, nB)
+        if (!first) {
+            if (r + 2u < N) nA = col[(size_t)(r + 2u) * col_stride];
+            if (r + 3u < N) nB = col[(size_t)(r + 3u) * col_stride];
+        }
 #pragma unroll
-        for (int j = 1; j <= FULL_W; ++j) {
-            const uint32_t s = prmt(P0, P1, (uint32_t)sel[(size_t)(j - 1) * sel_stride]);
-            F[j] = NVB_VIADDMAX(F[j], Ge2, V[j]);
-            E    = NVB_VIADDMAX(E, Ge2, V[j - 1]);
-            const uint32_t old = V[j];
-            if (TYPE == NVB_LOCAL) {
-                const uint32_t hb = NVB_VIMAX3(NVB_VIADDMAX(Vd, s, F[j]), E, beta2);
-                V[j] = hb * S.one + GoX;                                              // IMAD: H = h' + Go per half (carry-free)
-                const uint32_t key = V[j] * S.keymul + (uint32_t)((j - 1) | ((j - 1) << 16));
-                if (!PARTIAL || (uint32_t)j <= ncols) rowkey = NVB_VIMAX_U(rowkey, key);
-            } else {
-                const uint32_t h = NVB_VIMAX(NVB_VIADDMAX(Vd, s, F[j]), E);
-                V[j] = NVB_VIADD(h, Go2);
-                if (TYPE == NVB_SEMI_GLOBAL && PARTIAL && (uint32_t)j == ncols) vM = V[j];
-            }
-            Vd = old;
+        for (int jj = 1; jj <= FULL_W + SK; ++jj) {
+            if (jj <= FULL_W) full_pair_cell<TYPE, PARTIAL>(jj,      V, F, A, PA0, PA1, sel, sel_stride, ncols, K);
+            if (jj > SK)      full_pair_cell<TYPE, PARTIAL>(jj - SK, V, F, B, PB0, PB1, sel, sel_stride, ncols, K);
         }
-        if (!last) col[(size_t)r * col_stride] = make_uint2(V[FULL_W], E);
-        if (TYPE == NVB_LOCAL) {
-            const int32_t k0 = (int32_t)(rowkey & 0xFFFFu), k1 = (int32_t)(rowkey >> 16);
-            if (k0 >= (trk.k0 & ~7)) { trk.k0 = k0; trk.r0 = r; }       // (H, sub-stripe) >= the best's: later rows win ties
-            if (k1 >= (trk.k1 & ~7)) { trk.k1 = k1; trk.r1 = r; }
-        }
-        if (TYPE == NVB_SEMI_GLOBAL && last) {
-            if (!PARTIAL) vM = V[FULL_W];
-            const int32_t h0 = half_lo(vM) - Go, h1 = half_hi(vM) - Go;
-            if (trk.s0 <= h0) { trk.s0 = h0; trk.x0 = r + 1u; }
-            if (trk.s1 <= h1) { trk.s1 = h1; trk.x1 = r + 1u; }
-        }
+        V[0] = B.Vl;
+        NVB_FULL_ROW_END(A, r)
+        NVB_FULL_ROW_END(B, r + 1u)
     }
+    if (r < N) {
+        const uint32_t g0 = t0.next(), g1 = t1.next();
+        const uint32_t P0 = prof_tab ? prof_tab[g0] : sub_profile(g0, c_eq, c_ne), P1 = prof_tab ? prof_tab[g1] : sub_profile(g1, c_eq, c_ne);
+        FullRow A;
+        NVB_FULL_ROW_BEGIN(A, nA)
+#pragma unroll
+        for (int j = 1; j <= FULL_W; ++j) full_pair_cell<TYPE, PARTIAL>(j, V, F, A, P0, P1, sel, sel_stride, ncols, K);
+        V[0] = A.Vl;
+        NVB_FULL_ROW_END(A, r)
+    }
+#undef NVB_FULL_ROW_BEGIN
+#undef NVB_FULL_ROW_END
     if (TYPE == NVB_GLOBAL && last) {
         uint32_t v = V[FULL_W];
         if (PARTIAL) {

@@ -14,6 +14,7 @@
 
 namespace nvb {
 
+static int g_pair_extra_smem = 0;       // nvb_debug_pair_extra_smem: bytes of unused dynamic shared memory added to every pair-kernel CTA (occupancy experiments)
 static int g_pair_rows2 = 1;            // nvb_debug_pair_rows2(0): one row per loop iteration in the pair kernels
 static bool g_pair_fmt_ok = true;       // nvb_debug_pair_format(0) forces the run-time-format kernel (tests compare the two)
 
@@ -528,7 +529,7 @@ static int launch_generic(const GotohScheme& S, const GotohBatch& b, const uint3
 template <int B, int TYPE, int PFMT, bool ROWS2>
 static int launch_pair_fmt(const GotohScheme& S, const GotohBatch& b, uint32_t sel_rows, uint32_t* todo, uint32_t* todo_count, cudaStream_t s)
 {
-    const size_t smem = (size_t)((sel_rows + 15u) & ~15u) * PAIR_BLOCKDIM * sizeof(uint16_t);   // whole words of 16 columns
+    const size_t smem = (size_t)((sel_rows + 15u) & ~15u) * PAIR_BLOCKDIM * sizeof(uint16_t) + (size_t)g_pair_extra_smem;   // whole words of 16 columns
     // the attribute is per DEVICE: a host that drives several GPUs from one process (nvBowtie's one compute thread per
     // device) must set it on each; one atomic flag per (instantiation, device)
     static std::atomic<bool> attr_done[NVB_MAX_DEVICES];
@@ -877,6 +878,7 @@ void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
 void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
 void nvb_debug_full_warp(int mode) { g_full_warp = mode; }
 void nvb_debug_pair_rows2(int on) { nvb::g_pair_rows2 = on; }
+void nvb_debug_pair_extra_smem(int bytes) { nvb::g_pair_extra_smem = bytes > 0 ? bytes : 0; }
 void nvb_debug_pair_format(int on) { nvb::g_pair_fmt_ok = on != 0; }
 
 } // extern "C"

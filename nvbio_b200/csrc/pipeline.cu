@@ -117,8 +117,9 @@ pipe_make_strings_2bit_be_kernel(const StrSet reads, const PipeGeom g, uint32_t*
 // genome != NULL (the per-read path on an index with the full suffix array): single-row ranges are located on the spot --
 // ranges[q] = (text position, 0xFFFFFFFF), see fm_match_locate_one -- so that neither the remaining LF steps nor the later SA
 // gather of that hit are needed; wider ranges stay SA ranges.
+// (8 CTAs of 256 threads per SM = every warp slot: the kernel lives on gathers in flight, so the register budget is 32)
 template <int BITS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 pipe_seed_match_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __restrict__ words, const uint32_t* __restrict__ slen,
                        const uint32_t* __restrict__ genome, uint2* __restrict__ ranges, uint32_t* __restrict__ sizes)
 {

@@ -35,6 +35,7 @@ class FMIndexDevice:
         self.length, self.primary = int(length), int(primary)
         self.sa_interval = int(sa_interval)        # 16 = the reference's SA_INT; 1 = full suffix array
         self.ktab, self.ktab_k = ktab, int(ktab_k)  # optional k-mer range table (B200 extension)
+        self.ktab_located = False                   # True: 16-byte entries {x, y, SA[x], 0} (build_ktab(k, located=True))
 
     # -- views ------------------------------------------------------------------------------
     def struct(self) -> FmIndexStruct:
@@ -47,6 +48,7 @@ class FMIndexDevice:
         s.sa_interval = self.sa_interval
         s.d_ktab = self.ktab.data_ptr() if self.ktab is not None else None
         s.ktab_k = self.ktab_k if self.ktab is not None else 0
+        s.ktab_located = 1 if (self.ktab is not None and self.ktab_located) else 0
         return s
 
     @property
@@ -57,12 +59,17 @@ class FMIndexDevice:
         return (self.bwt_occ.numel() * 4 + (self.ssa.numel() * 4 if self.ssa is not None else 0) +
                 (self.ktab.numel() * 4 if self.ktab is not None else 0))
 
-    def build_ktab(self, k: int = 12):
-        """k-mer range table (4^k x uint2): replaces the first k LF steps of every match()"""
-        tab = torch.empty((4 ** k, 2), dtype=torch.int32, device=self.device)
+    def build_ktab(self, k: int = 12, located: bool = False):
+        """k-mer range table (4^k x uint2): replaces the first k LF steps of every match().  located=True builds 16-byte entries
+        {x, y, SA[x], 0} instead (needs the full suffix array): a seed whose k-mer occurs once is located by the look-up itself"""
+        self.ktab = None                                   # release a previous table before allocating the new one
+        tab = torch.empty((4 ** k, 4 if located else 2), dtype=torch.int32, device=self.device)
         s = self.struct()
-        check(lib().nvb_fm_build_ktab(C.byref(s), C.c_uint32(k), C.c_void_p(tab.data_ptr()), _stream()), "nvb_fm_build_ktab")
-        self.ktab, self.ktab_k = tab, k
+        if located:
+            check(lib().nvb_fm_build_ktab_located(C.byref(s), C.c_uint32(k), C.c_void_p(tab.data_ptr()), _stream()), "nvb_fm_build_ktab_located")
+        else:
+            check(lib().nvb_fm_build_ktab(C.byref(s), C.c_uint32(k), C.c_void_p(tab.data_ptr()), _stream()), "nvb_fm_build_ktab")
+        self.ktab, self.ktab_k, self.ktab_located = tab, k, bool(located)
         return self
 
     # -- construction -----------------------------------------------------------------------

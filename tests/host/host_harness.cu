@@ -10,10 +10,10 @@
 using namespace nvb;
 
 static FmIndex mk(const uint32_t* bwt_occ, const uint32_t* ssa, const uint32_t* L2, uint32_t n, uint32_t primary,
-                  uint32_t sa_interval = 16, const uint32_t* ktab = nullptr, uint32_t ktab_k = 0) {
+                  uint32_t sa_interval = 16, const uint32_t* ktab = nullptr, uint32_t ktab_k = 0, uint32_t ktab_located = 0) {
     nvb_fm_index c; c.d_bwt_occ = bwt_occ; c.d_ssa = ssa; c.length = n; c.primary = primary;
     for (int i = 0; i < 5; ++i) c.L2[i] = L2[i];
-    c.sa_interval = sa_interval; c.d_ktab = (const nvb_uint2*)ktab; c.ktab_k = ktab_k;
+    c.sa_interval = sa_interval; c.d_ktab = (const nvb_uint2*)ktab; c.ktab_k = ktab_k; c.ktab_located = ktab_located;
     return make_fmindex(&c);
 }
 
@@ -42,10 +42,18 @@ void hh_fm_build_ktab(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, u
         }
 }
 
+// 8-byte entries {x, y} -> 16-byte entries {x, y, SA[x] when x == y, 0} (what nvb_fm_build_ktab_located produces)
+void hh_fm_ktab_locate(const uint32_t* ktab8, const uint32_t* full_sa, uint32_t k, uint32_t* ktab16) {
+    for (uint64_t v = 0; v < (1ull << (2u * k)); ++v) {
+        const uint32_t x = ktab8[2 * v], y = ktab8[2 * v + 1];
+        ktab16[4 * v] = x; ktab16[4 * v + 1] = y; ktab16[4 * v + 2] = (x == y) ? full_sa[x] : 0u; ktab16[4 * v + 3] = 0u;
+    }
+}
+
 void hh_fm_match(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary,
                  const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len, uint32_t nq,
-                 uint32_t flags, uint32_t* out_xy, const uint32_t* ktab, uint32_t ktab_k) {
-    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary, 16, ktab, ktab_k);
+                 uint32_t flags, uint32_t* out_xy, const uint32_t* ktab, uint32_t ktab_k, uint32_t ktab_located) {
+    const FmIndex f = mk(bwt_occ, nullptr, L2, n, primary, 16, ktab, ktab_k, ktab_located);
     for (uint32_t i = 0; i < nq; ++i) {
         uint32_t x, y;
 #define CALL(B, E) fm_match_one<B, E>(f, words, off[i], len[i], flags, x, y)
@@ -71,8 +79,8 @@ void hh_fm_match_approx(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n,
 // fm_match_locate_one over an index with the full suffix array: out[3*i] = status (0 empty, 1 range, 2 located), then (x, y)
 void hh_fm_match_locate(const uint32_t* bwt_occ, const uint32_t* full_sa, const uint32_t* L2, uint32_t n, uint32_t primary,
                         const uint32_t* genome, const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len,
-                        uint32_t nq, uint32_t* out, const uint32_t* ktab, uint32_t ktab_k) {
-    const FmIndex f = mk(bwt_occ, full_sa, L2, n, primary, 1, ktab, ktab_k);
+                        uint32_t nq, uint32_t* out, const uint32_t* ktab, uint32_t ktab_k, uint32_t ktab_located) {
+    const FmIndex f = mk(bwt_occ, full_sa, L2, n, primary, 1, ktab, ktab_k, ktab_located);
     for (uint32_t i = 0; i < nq; ++i) {
         uint32_t x = 0, y = 0, st = 0;
         if (bits == 2) st = fm_match_locate_one<2, true>(f, genome, words, off[i], len[i], x, y);

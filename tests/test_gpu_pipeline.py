@@ -310,6 +310,49 @@ def test_seed_extend_with_base_qualities():
     assert np.array_equal(host_u32(wp.mate_pos).astype(np.int64), wantp["mate_pos"])
 
 
+def test_single_row_fold_and_located_table():
+    """full suffix array: the per-read path locates single-row ranges inside the match kernel (SA gather + text compare instead of the
+    remaining LF steps), and with the 16-byte located k-mer table the SA gather of a single-row k-mer comes with the table entry;
+    every combination gives the per-hit path's results on a genome with a repeat family (multi-row ranges) and reads with N"""
+    import ctypes as C
+    require_gpu()
+    n = 300_000
+    gw = synth.random_genome_words(n, seed=77)
+    gsym = unpack_symbols(host_u32(gw), n).copy()
+    gsym[100_000:130_000] = np.tile(gsym[2000:2300], 100)
+    gw = torch.from_numpy(pack_symbols(gsym, 2, True).view(np.int32)).cuda()
+    n_reads, L = 4000, 150
+    rw, pos, strand = synth.sample_reads(gw, n, n_reads, L, sub_rate=0.01, indel_rate=0.001, seed=21, mut_seed=22)
+    sym = np.stack([unpack_symbols(host_u32(rw[i]), L) for i in range(n_reads)])
+    sym[np.random.default_rng(8).random(sym.shape) < 0.002] = 4
+    stride = ((L + 7) // 8) * 8
+    buf = np.zeros((n_reads, stride), np.uint8); buf[:, :L] = sym
+    words = torch.from_numpy(pack_symbols(buf.reshape(-1), 4, True).view(np.int32)).cuda()
+    rs = PackedStringSet.fixed(words, n_reads, L, stride=stride, bits=4)
+    params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=True, max_seed_hits=40,
+                                 scheme=aln.SimpleGotohScheme(2, -2, -5, -3))
+    L_ = nb.lib()
+    results = {}
+    for name, k, located in (("plain", 0, False), ("ktab", 8, False), ("located", 8, True), ("located5", 5, True)):
+        fmi, _ = nb.FMIndexDevice.from_text(gw, n, sa_interval=1)
+        if k:
+            fmi.build_ktab(k, located=located)
+        fast = nb.seed_extend(fmi, gw, rs, params, hit_capacity=100 * n_reads)
+        torch.cuda.synchronize()
+        L_.nvb_debug_pipeline_path(C.c_int(1))
+        try:
+            slow = nb.seed_extend(fmi, gw, rs, params, hit_capacity=100 * n_reads)
+            torch.cuda.synchronize()
+        finally:
+            L_.nvb_debug_pipeline_path(C.c_int(0))
+        assert torch.equal(fast.n_hits[:2], slow.n_hits[:2]), name
+        assert torch.equal(fast.best_score, slow.best_score) and torch.equal(fast.best_pos, slow.best_pos), name
+        results[name] = (fast.best_score.clone(), fast.best_pos.clone(), fast.n_hits[:2].clone())
+    for name in ("ktab", "located", "located5"):
+        assert all(torch.equal(a, b) for a, b in zip(results[name], results["plain"])), name
+    assert int((results["plain"][0] > 200).sum()) > n_reads // 2
+
+
 @pytest.mark.parametrize("bits,ragged,cap_div", [(2, False, 0), (4, True, 0), (2, False, 3)])
 def test_per_read_path_equals_per_hit_path(bits, ragged, cap_div):
     """the per-read path of nvb_seed_extend (taken when no per-hit output is requested: distinct jobs straight from a thread per

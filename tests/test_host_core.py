@@ -69,7 +69,7 @@ def test_fm_core(H, O, n):
         words = pack_symbols(q, bits, bool(be))
         got = np.zeros((nq, 2), np.uint32)
         H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(bits), C.c_uint32(be),
-                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), None, C.c_uint32(0))
+                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), None, C.c_uint32(0), C.c_uint32(0))
         assert np.array_equal(got, want), (bits, be)
     # N rule on a 4-bit stream
     qn = q.copy(); qn[offs[5] + lens[5] - 1] = 4          # last symbol = first one consumed
@@ -77,27 +77,32 @@ def test_fm_core(H, O, n):
     got = np.zeros((nq, 2), np.uint32)
     words = pack_symbols(qn, 4, True)
     H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(4), C.c_uint32(1),
-                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), None, C.c_uint32(0))
+                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), None, C.c_uint32(0), C.c_uint32(0))
     assert np.array_equal(got, want_n) and tuple(got[5]) == (1, 0)
     # forward-order + complement == backward search of the reverse complement
     rc = np.concatenate([(3 - q[o:o + l])[::-1] for o, l in zip(offs, lens)]).astype(np.uint8)
     want_rc, _ = O.match(idx, rc, offs, lens)
     words = pack_symbols(q, 2, True)
     H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
-                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(3), _p(got), None, C.c_uint32(0))
+                  _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(3), _p(got), None, C.c_uint32(0), C.c_uint32(0))
     assert np.array_equal(got, want_rc)
     # k-mer table: identical ranges with the first k steps looked up (incl. empty ranges, N's, short queries)
     for k in (1, 3, 6):
         ktab = np.zeros(2 * 4 ** k, np.uint32)
         H.hh_fm_build_ktab(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), C.c_uint32(k), _p(ktab))
-        for flags, w in ((0, want), (3, want_rc)):
-            H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
-                          _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(flags), _p(got), _p(ktab), C.c_uint32(k))
-            assert np.array_equal(got, w), (k, flags)
-        wn = pack_symbols(qn, 4, True)
-        H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(wn), C.c_uint32(4), C.c_uint32(1),
-                      _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), _p(ktab), C.c_uint32(k))
-        assert np.array_equal(got, want_n), k
+        # ... and the same through the 16-byte "located" entries {x, y, SA[x], 0}
+        full_sa = idx.sa.astype(np.uint32).copy(); full_sa[0] = 0xFFFFFFFF
+        ktab16 = np.zeros(4 * 4 ** k, np.uint32)
+        H.hh_fm_ktab_locate(_p(ktab), _p(full_sa), C.c_uint32(k), _p(ktab16))
+        for tab, located in ((ktab, 0), (ktab16, 1)):
+            for flags, w in ((0, want), (3, want_rc)):
+                H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
+                              _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(flags), _p(got), _p(tab), C.c_uint32(k), C.c_uint32(located))
+                assert np.array_equal(got, w), (k, flags, located)
+            wn = pack_symbols(qn, 4, True)
+            H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(wn), C.c_uint32(4), C.c_uint32(1),
+                          _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(0), _p(got), _p(tab), C.c_uint32(k), C.c_uint32(located))
+            assert np.array_equal(got, want_n), (k, located)
     # locate
     rows = rng.integers(0, n + 1, 300).astype(np.uint32); rows[:3] = (0, idx.primary, n)
     out = np.zeros(300, np.uint32)
@@ -332,17 +337,20 @@ def test_generic_rank_dictionary(H):
         assert np.array_equal(out, g[f"ranks{i}"]), (wb, K, n)
 
 
+@pytest.mark.parametrize("bits", [4, 2])
 @pytest.mark.parametrize("n,k", [(300, 0), (300, 3), (5000, 0), (5000, 4), (5000, 6), (70, 2)])
-def test_fm_match_locate_shortcut(H, O, n, k):
+def test_fm_match_locate_shortcut(H, O, n, k, bits):
     """fm_match_locate_one (single-row ranges located through the full SA + a text comparison instead of the remaining LF steps)
     == match() followed by locate(): same emptiness, same range when it stays wider than one row, and for single-row results the
-    very position locate(match(p)) returns -- incl. repeats, N's, seeds running off the text start, queries shorter than k"""
+    very position locate(match(p)) returns -- incl. repeats, N's, seeds running off the text start, queries shorter than k.
+    bits = 2: the 2-bit big-endian fast path (table index and text comparison as bit patterns; no N's in a 2-bit stream); query
+    lengths up to 40 so that the comparison spans more than one 16-symbol chunk"""
     rng = np.random.default_rng(n * 7 + k)
     unit = rng.integers(0, 4, 37).astype(np.uint8)
     text = np.concatenate([rng.integers(0, 4, n // 2), np.tile(unit, n)[: n - n // 2]]).astype(np.uint8)    # second half: a tandem repeat
     idx = O.build_index(text)
     nq = 600
-    lens = rng.integers(1, 24, nq).astype(np.uint32)
+    lens = rng.integers(1, 41 if bits == 2 else 24, nq).astype(np.uint32)
     offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
     q = rng.integers(0, 4, int(lens.sum())).astype(np.uint8)
     for i in range(nq):
@@ -352,7 +360,7 @@ def test_fm_match_locate_shortcut(H, O, n, k):
             q[offs[i]:offs[i] + L] = text[st:st + L]
             if i % 7 == 0:
                 q[offs[i] + int(rng.integers(0, L))] ^= 1                    # one substitution
-            if i % 11 == 0:
+            if i % 11 == 0 and bits == 4:
                 q[offs[i] + int(rng.integers(0, L))] = 4                     # an N
     want, _ = O.match(idx, q, offs, lens)
     full_sa = idx.sa.astype(np.uint32).copy(); full_sa[0] = 0xFFFFFFFF
@@ -361,10 +369,18 @@ def test_fm_match_locate_shortcut(H, O, n, k):
     if k:
         ktab = np.zeros(2 * 4 ** k, np.uint32)
         H.hh_fm_build_ktab(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), C.c_uint32(k), _p(ktab))
-    words = pack_symbols(q, 4, True)
+    words = np.concatenate([pack_symbols(q, bits, True), np.zeros(2, np.uint32)])
     out = np.zeros((nq, 3), np.uint32)
-    H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(4), C.c_uint32(1),
-                         _p(offs), _p(lens), C.c_uint32(nq), _p(out), _p(ktab), C.c_uint32(k))
+    H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits), C.c_uint32(1),
+                         _p(offs), _p(lens), C.c_uint32(nq), _p(out), _p(ktab), C.c_uint32(k), C.c_uint32(0))
+    if k:
+        # the 16-byte located table answers the same (status, x, y) without the SA gather for single-row k-mers
+        ktab16 = np.zeros(4 * 4 ** k, np.uint32)
+        H.hh_fm_ktab_locate(_p(ktab), _p(full_sa), C.c_uint32(k), _p(ktab16))
+        out16 = np.zeros((nq, 3), np.uint32)
+        H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits),
+                             C.c_uint32(1), _p(offs), _p(lens), C.c_uint32(nq), _p(out16), _p(ktab16), C.c_uint32(k), C.c_uint32(1))
+        assert np.array_equal(out16, out)
     n_loc = 0
     for i in range(nq):
         x, y = int(want[i, 0]), int(want[i, 1])

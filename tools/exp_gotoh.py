@@ -16,6 +16,7 @@ ap.add_argument("--fmts", type=int, nargs="*", default=[1, 0], help="1 = compile
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--types", type=int, nargs="*", default=[1], help="0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL")
 ap.add_argument("--rows2", type=int, nargs="*", default=[1, 0], help="1 = two pattern rows in flight per thread (LOCAL), 0 = one")
+ap.add_argument("--extra-smem", type=int, nargs="*", default=[0], help="unused dynamic shared memory per CTA (occupancy experiment)")
 ap.add_argument("--check-file", default=None, help="JSON of result checksums shared between runs (e.g. of different library builds)")
 args = ap.parse_args()
 n = 100_000_000
@@ -31,8 +32,8 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 ref = {}
 if args.check_file and os.path.exists(args.check_file):
     ref = {tuple(int(v) for v in k.split(',')): c for k, c in json.load(open(args.check_file)).items()}
-for fmt, rows2 in [(f, r2) for f in args.fmts for r2 in args.rows2]:
-    L.nvb_debug_pair_format(C.c_int(fmt)); L.nvb_debug_pair_rows2(C.c_int(rows2))
+for fmt, rows2, xs in [(f, r2, x) for f in args.fmts for r2 in args.rows2 for x in args.extra_smem]:
+    L.nvb_debug_pair_format(C.c_int(fmt)); L.nvb_debug_pair_rows2(C.c_int(rows2)); L.nvb_debug_pair_extra_smem(C.c_int(xs))
     for band, typ in [(b, t) for t in args.types for b in args.bands]:
         al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -2, -5, -3))
         temp = torch.empty(aln.banded_temp_bytes(band, al, P, T) + 256, dtype=torch.uint8, device="cuda")
@@ -45,6 +46,6 @@ for fmt, rows2 in [(f, r2) for f in args.fmts for r2 in args.rows2]:
         chk = int(res[0].to(torch.int64).sum().item())
         if key in ref: assert ref[key] == chk, "results differ between the two kernels"
         ref[key] = chk
-        print(json.dumps({"pfmt_kernels": bool(fmt), "rows2": bool(rows2), "type": typ, "band": band, "ms": best, "GCUPS": n_al * M * band / best / 1e6}))
+        print(json.dumps({"pfmt_kernels": bool(fmt), "rows2": bool(rows2), "extra_smem": xs, "type": typ, "band": band, "ms": best, "GCUPS": n_al * M * band / best / 1e6}))
 if args.check_file:
     json.dump({"%d,%d" % k: c for k, c in ref.items()}, open(args.check_file, "w"))
