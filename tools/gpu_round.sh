@@ -5,7 +5,7 @@ TAG=${1:-rXX}
 mkdir -p gpurun_out
 ( time timeout 2400 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-( python bench.py --steps 10 --warmup 3 ) > gpurun_out/bench_default.log 2>&1
+( python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_default.log 2>&1
 ( timeout 900 python tools/compare_ref_cuda.py ) > gpurun_out/compare_ref_cuda.log 2>&1
 ( timeout 900 python tools/bench_full.py ) > gpurun_out/bench_full.log 2>&1
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs --pairs 0"
