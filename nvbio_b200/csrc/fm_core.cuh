@@ -240,6 +240,17 @@ __host__ __device__ __forceinline__ void fm_step(const FmIndex& f, uint32_t c, u
     y = base + ry;
 }
 
+// symbols [a, a + cnt) (1 <= cnt <= 16) of a 2-bit big-endian stream in the TOP 2*cnt bits of the result (the low bits are
+// unspecified); touches the second word only when the window really reaches into it
+__host__ __device__ __forceinline__ uint32_t be2_window(const uint32_t* __restrict__ words, uint32_t a, uint32_t cnt)
+{
+    const uint32_t wi = a >> 4, r = a & 15u;
+    const uint32_t w0 = words[wi];
+    if (r == 0u) return w0;
+    const uint32_t w1 = (r + cnt > 16u) ? words[wi + 1u] : 0u;
+    return (w0 << (2u * r)) | (w1 >> (32u - 2u * r));
+}
+
 // match() of one query read through a SymReader; FORWARD consumes left-to-right, COMPLEMENT maps
 // c<4 -> 3-c (nvBowtie's reverse-complement seed search over the forward index).
 template <int BITS, bool BE>
@@ -255,12 +266,18 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
         // the first k symbols consumed are the LAST k symbols of the effective pattern: look their range up.
         // ktab[u] is match() of that k-mer, which also reproduces the reference's early exit on an empty range.
         uint32_t u = 0; bool has_n = false;
-        for (uint32_t j = 0; j < f.ktab_k; ++j) {
-            const uint32_t i = fwd ? j : (len - 1u - j);
-            uint32_t c = rd.get(off + i);
-            has_n |= (c > 3u);
-            if (comp) c = 3u - c;
-            u |= (c & 3u) << (2u * j);
+        if (BITS == 2 && BE && !fwd) {
+            // backward order over a 2-bit big-endian stream: the index is the bit pattern of the last k symbols (complemented: ~)
+            const uint32_t w = be2_window(words, off + len - f.ktab_k, f.ktab_k);
+            u = (comp ? ~w : w) >> (32u - 2u * f.ktab_k);
+        } else {
+            for (uint32_t j = 0; j < f.ktab_k; ++j) {
+                const uint32_t i = fwd ? j : (len - 1u - j);
+                uint32_t c = rd.get(off + i);
+                has_n |= (c > 3u);
+                if (comp) c = 3u - c;
+                u |= (c & 3u) << (2u * j);
+            }
         }
         if (!has_n) {                                   // an N among them: take the step-by-step path below
             const uint2 r = gather_u2(f.ktab_located ? (const uint2*)((const uint4*)f.ktab + u) : f.ktab + u);
@@ -277,15 +294,29 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
     ox = x; oy = y;
 }
 
-// symbols [a, a + cnt) (1 <= cnt <= 16) of a 2-bit big-endian stream in the TOP 2*cnt bits of the result (the low bits are
-// unspecified); touches the second word only when the window really reaches into it
-__host__ __device__ __forceinline__ uint32_t be2_window(const uint32_t* __restrict__ words, uint32_t a, uint32_t cnt)
+// the same for a 4-bit big-endian stream (nvBowtie's read format): symbols [a, a + cnt) (1 <= cnt <= 16) squeezed to 2 bits each
+// in the top 2*cnt bits of the result; `has_n` is set when one of them is > 3
+__host__ __device__ __forceinline__ uint32_t squeeze_nibbles(uint32_t x)      // 8 nibbles -> 16 bits (the low 2 bits of each)
 {
-    const uint32_t wi = a >> 4, r = a & 15u;
+    uint32_t t = x & 0x33333333u;
+    t = (t | (t >> 2)) & 0x0F0F0F0Fu;
+    t = (t | (t >> 4)) & 0x00FF00FFu;
+    return (t | (t >> 8)) & 0x0000FFFFu;
+}
+__host__ __device__ __forceinline__ uint32_t be4_window(const uint32_t* __restrict__ words, uint32_t a, uint32_t cnt, bool& has_n)
+{
+    const uint32_t wi = a >> 3, r = a & 7u, sh = 4u * r;
+    const uint32_t nw = (r + cnt + 7u) >> 3;                          // words the window touches: 1..3
     const uint32_t w0 = words[wi];
-    if (r == 0u) return w0;
-    const uint32_t w1 = (r + cnt > 16u) ? words[wi + 1u] : 0u;
-    return (w0 << (2u * r)) | (w1 >> (32u - 2u * r));
+    const uint32_t w1 = nw > 1u ? words[wi + 1u] : 0u;
+    const uint32_t w2 = nw > 2u ? words[wi + 2u] : 0u;
+    uint32_t hi = r ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;         // symbols 0..7 of the window
+    uint32_t lo = r ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;         // symbols 8..15
+    // symbols beyond cnt are not part of the window: clear them before the N test
+    if (cnt < 8u)       { hi &= ~(0xFFFFFFFFu >> (4u * cnt)); lo = 0u; }
+    else if (cnt < 16u) { lo &= (cnt == 8u) ? 0u : ~(0xFFFFFFFFu >> (4u * (cnt - 8u))); }
+    has_n |= ((hi | lo) & 0xCCCCCCCCu) != 0u;
+    return (squeeze_nibbles(hi) << 16) | squeeze_nibbles(lo);
 }
 
 // match() + locate() of one query in one pass, for callers that only need the hit POSITIONS of narrow ranges (the per-read
@@ -310,6 +341,8 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
         if (BITS == 2 && BE) {
             // the table index IS the big-endian bit pattern of the last k symbols: one funnel shift instead of k symbol reads
             u = be2_window(words, off + len - f.ktab_k, f.ktab_k) >> (32u - 2u * f.ktab_k);
+        } else if (BITS == 4 && BE) {
+            u = be4_window(words, off + len - f.ktab_k, f.ktab_k, has_n) >> (32u - 2u * f.ktab_k);
         } else {
             for (uint32_t j = 0; j < f.ktab_k; ++j) {
                 const uint32_t c = rd.get(off + len - 1u - j);
@@ -343,6 +376,13 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
                     const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
                     same &= ((be2_window(words, off + i, cnt) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
                 }
+            } else if (BITS == 4 && BE) {
+                bool n_left = false;                                         // an N among the unread symbols matches nothing
+                for (uint32_t i = 0; i < rem; i += 16u) {
+                    const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
+                    same &= ((be4_window(words, off + i, cnt, n_left) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
+                }
+                same &= !n_left;
             } else {
                 SymReader<2, true> tr(genome);
                 for (uint32_t i = 0; i < rem; ++i) same &= (rd.get(off + i) == tr.get(p0 + i));
