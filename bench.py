@@ -104,17 +104,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_traffic(kernel, **cfg):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` captures (profiles/traffic.json), when
-    one exists for exactly this configuration; else None"""
+def measured_traffic(kernel, field="dram_bytes_per_launch", **cfg):
+    """a per-launch counter of `kernel` (default: DRAM bytes) from the committed `ncu --set full` captures (profiles/traffic.json),
+    when one exists for exactly this configuration; else None"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         for e in json.load(open(p)):
             if e["kernel"] == kernel and all(e.get(k) == v for k, v in cfg.items()):
-                return e["dram_bytes_per_launch"]
+                return e.get(field)
     except Exception:
         pass
     return None
+
+
+def gather_rate(ms, **cfg):
+    """second denominator for the seed-match kernel: its L2 read requests per launch (ncu capture of exactly this configuration)
+    over the live launch time, against the measured rate of dependent random 16-byte gathers on this part"""
+    req = measured_traffic("pipe_seed_match_kernel", "l2_read_requests_per_launch", **cfg)
+    ceil = measured_traffic("pipe_seed_match_kernel", "gather_ceiling_G_per_s", **cfg)
+    if not req or not ceil:
+        return None
+    ach = req / (ms * 1e-3) / 1e9
+    return {"l2_read_requests_per_launch": req, "achieved_G_per_s": ach, "ceiling_G_per_s": ceil, "frac": ach / ceil,
+            "source": measured_traffic("pipe_seed_match_kernel", "gather_ceiling_source", **cfg)}
 
 
 def measured_peaks():
@@ -772,6 +784,8 @@ def run_ours(args):
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic("pipe_seed_match_kernel", ktab_k=args.ktab_k, genome_bp=n, reads=n_reads, ktab_located=bool(fmi.ktab_located), single_row_fold=(fmi.sa_interval == 1)),
                      "peak_source": peak_src, "ms_per_launch": fm_ms,
+                     "gather_rate": gather_rate(fm_ms, ktab_k=args.ktab_k, genome_bp=n, reads=n_reads, ktab_located=bool(fmi.ktab_located),
+                                                single_row_fold=(fmi.sa_interval == 1)),
                      "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": tail_blocks,
                      "reference_algorithm_bytes_per_seed": ref_bytes_per_seed, "reference_algorithm_blocks_per_seed": blocks_per_seed,
                      "reference_algorithm_equiv_GBs": n_seeds * ref_bytes_per_seed / (fm_ms * 1e-3) / 1e9,
