@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
     ap.add_argument("--ktab-k", type=int, default=16, help="k of the k-mer range table (0 = none)")
-    ap.add_argument("--ktab-located", type=int, default=1, help="1: 16-byte table entries {x, y, SA[x], 0} (needs --sa-interval 1; 69 GB at k = 16), 0: 8-byte {x, y}")
+    ap.add_argument("--ktab-located", type=int, default=1, help="1: 16-byte table entries {x, y, SA[x], SA[y]} (needs --sa-interval 1; 69 GB at k = 16), 0: 8-byte {x, y}")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-to-host (e2e) pipeline")
     ap.add_argument("--e2e-sweep", action="store_true", help="also time the host-to-host pipeline with other (depth, compute streams) shapes")
     ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
@@ -325,7 +325,7 @@ def index_description(sa_interval, ktab_k, n, nbytes=None, located=False):
     d = {"sa_interval": sa_interval, "ktab_k": ktab_k, "ktab_located": bool(located and ktab_k),
          "layout": "%s + %s" % ("full suffix array (4 B per base)" if sa_interval == 1 else "SA sampled every %d rows" % sa_interval,
                                 ("%d-mer SA-range table (4^%d x %d B = %.1f GB%s)" % (ktab_k, ktab_k, eb, 4 ** ktab_k * eb / 1e9,
-                                                                                     "; entries {x, y, SA[x]}" if located else "")) if ktab_k else "no k-mer table (the reference's format)")}
+                                                                                     "; entries {x, y, SA[x], SA[y]}" if located else "")) if ktab_k else "no k-mer table (the reference's format)")}
     if nbytes is not None:
         d["bytes_per_gpu"] = int(nbytes)
     return d

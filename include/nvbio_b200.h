@@ -62,9 +62,10 @@ typedef struct nvb_fm_index {
                                     as a 2k-bit number, first symbol most significant), built by
                                     nvb_fm_build_ktab; replaces the first k LF steps of match()     */
     uint32_t        ktab_k;      /* 0 = no table */
-    uint32_t        ktab_located;/* 0: d_ktab holds 8-byte entries {x, y};  1: 16-byte entries {x, y, SA[x], 0} built by
-                                    nvb_fm_build_ktab_located (SA[x] valid when x == y): a seed whose k-mer occurs once is
-                                    located by the table look-up itself.  Ranges are identical either way.  */
+    uint32_t        ktab_located;/* 0: d_ktab holds 8-byte entries {x, y};  1: 16-byte entries {x, y, SA[x], SA[y]} built by
+                                    nvb_fm_build_ktab_located (SA[x] valid when y == x, both when y == x + 1): a seed whose
+                                    k-mer occurs once or twice is located by the look-up + a text comparison, without walking the
+                                    range on.  Ranges are identical either way.  */
 } nvb_fm_index;
 
 /* A set of strings stored in one packed symbol stream (nvbio PackedStream semantics,
@@ -354,8 +355,8 @@ int nvb_fm_build_bwt(const uint32_t* d_text, uint32_t n, uint32_t* d_bwt, uint32
  * k in [1,16] (8.6 GB at k=15, 34 GB at k=16).  fmi->d_ktab / ktab_k are ignored on input. */
 int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, void* stream);
 
-/* The same table with 16-byte entries {x, y, SA[x], 0} (d_ktab16: 4^k * 16 bytes, 16-byte aligned; 69 GB at k = 16 -- HBM capacity
- * traded for one dependent gather per seed).  SA[x] is filled for single-row entries (x == y) and needs the full suffix array
+/* The same table with 16-byte entries {x, y, SA[x], SA[y]} (d_ktab16: 4^k * 16 bytes, 16-byte aligned; 69 GB at k = 16 -- HBM capacity
+ * traded for dependent gathers).  The SA values are filled for ranges of one row (x == y) or two (y == x + 1) and need the full suffix array
  * (fmi->sa_interval == 1), else NVB_E_UNSUPPORTED.  Use with nvb_fm_index.d_ktab = d_ktab16, ktab_located = 1. */
 int nvb_fm_build_ktab_located(const nvb_fm_index* fmi, uint32_t k, void* d_ktab16, void* stream);
 

@@ -27,7 +27,7 @@ struct FmIndex {
     uint32_t L2[5];
     uint32_t sa_mask, sa_shift;    // sampled-SA interval I = 1 << sa_shift, mask = I - 1
     uint32_t ktab_k;
-    uint32_t ktab_located;         // 1: table entries are 16 bytes {x, y, SA[x] (valid when x == y), 0} (nvb_fm_build_ktab_located)
+    uint32_t ktab_located;         // 1: table entries are 16 bytes {x, y, SA[x], SA[y]} (SA values filled for ranges of one or two rows; nvb_fm_build_ktab_located)
     // constant-index selects keep the struct in the kernel-parameter constant bank (a dynamic L2[c]
     // would force a local-memory copy of the whole struct)
     __host__ __device__ __forceinline__ uint32_t l2(uint32_t c) const {
@@ -335,7 +335,7 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
 {
     SymReader<BITS, BE> rd(words);
     uint32_t x = 0, y = f.n, s = 0;
-    uint32_t known_pos = 0u; bool have_pos = false;
+    uint32_t known_pos = 0u, known_pos2 = 0u; bool have_pos = false, have_two = false;
     if (f.ktab_k && len >= f.ktab_k) {
         uint32_t u = 0; bool has_n = false;
         if (BITS == 2 && BE) {
@@ -353,7 +353,7 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
         if (!has_n) {
             if (f.ktab_located) {                       // the entry of a single-row k-mer carries SA[x]: no SA gather below
                 const uint4 e = gather_u4((const uint4*)f.ktab + u);
-                x = e.x; y = e.y; known_pos = e.z; have_pos = (e.x == e.y);
+                x = e.x; y = e.y; known_pos = e.z; known_pos2 = e.w; have_pos = (e.x == e.y); have_two = (e.y == e.x + 1u);
             } else {
                 const uint2 r = gather_u2(f.ktab + u);
                 x = r.x; y = r.y;
@@ -362,33 +362,46 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
         }
     }
     const bool full_sa = (f.sa_shift == 0u) && genome != nullptr;
+    // does text[pos - rem, pos) equal the first `rem` (not yet consumed) symbols of the query?  (pos = SA of the row reached so far)
+    auto prefix_matches = [&](const uint32_t pos, const uint32_t rem) -> bool {
+        if (pos == 0xFFFFFFFFu || pos < rem) return false;
+        const uint32_t p0 = pos - rem;
+        bool same = true;
+        if (BITS == 2 && BE) {
+            // both sides are 2-bit big-endian streams: compare up to 16 symbols per step as bit patterns
+            for (uint32_t i = 0; i < rem; i += 16u) {
+                const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
+                same &= ((be2_window(words, off + i, cnt) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
+            }
+        } else if (BITS == 4 && BE) {
+            bool n_left = false;                                             // an N among the unread symbols matches nothing
+            for (uint32_t i = 0; i < rem; i += 16u) {
+                const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
+                same &= ((be4_window(words, off + i, cnt, n_left) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
+            }
+            same &= !n_left;
+        } else {
+            SymReader<2, true> tr(genome);
+            for (uint32_t i = 0; i < rem; ++i) same &= (rd.get(off + i) == tr.get(p0 + i));
+        }
+        return same;
+    };
+    if (have_two && full_sa && s < len) {
+        // a k-mer with exactly two occurrences: both candidates are checked against the text (two independent reads) instead of
+        // walking the range on; exactly one survivor = the single row the remaining LF steps would have reached, none = empty,
+        // both = a genuine repeat of the whole query: that one takes the general path below
+        const uint32_t rem = len - s;
+        const bool m0 = prefix_matches(known_pos, rem), m1 = prefix_matches(known_pos2, rem);
+        if (!m0 && !m1) return FM_EMPTY;
+        if (m0 != m1) { ox = (m0 ? known_pos : known_pos2) - rem; oy = 0xFFFFFFFFu; return FM_LOCATED; }
+    }
     for (; s < len && x <= y; ++s) {
         if (full_sa && x == y) {
             const uint32_t rem = len - s;                 // symbols [0, rem) of the query are still to be consumed
             // (have_pos can only be set on the first pass: a single-row range returns from this branch)
             const uint32_t pos = have_pos ? known_pos : gather_u32(f.ssa + x);
-            if (pos == 0xFFFFFFFFu || pos < rem) return FM_EMPTY;
-            const uint32_t p0 = pos - rem;
-            bool same = true;
-            if (BITS == 2 && BE) {
-                // both sides are 2-bit big-endian streams: compare up to 16 symbols per step as bit patterns
-                for (uint32_t i = 0; i < rem; i += 16u) {
-                    const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
-                    same &= ((be2_window(words, off + i, cnt) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
-                }
-            } else if (BITS == 4 && BE) {
-                bool n_left = false;                                         // an N among the unread symbols matches nothing
-                for (uint32_t i = 0; i < rem; i += 16u) {
-                    const uint32_t cnt = rem - i < 16u ? rem - i : 16u;
-                    same &= ((be4_window(words, off + i, cnt, n_left) ^ be2_window(genome, p0 + i, cnt)) >> (32u - 2u * cnt)) == 0u;
-                }
-                same &= !n_left;
-            } else {
-                SymReader<2, true> tr(genome);
-                for (uint32_t i = 0; i < rem; ++i) same &= (rd.get(off + i) == tr.get(p0 + i));
-            }
-            if (!same) return FM_EMPTY;
-            ox = p0; oy = 0xFFFFFFFFu;
+            if (!prefix_matches(pos, rem)) return FM_EMPTY;
+            ox = pos - rem; oy = 0xFFFFFFFFu;
             return FM_LOCATED;
         }
         const uint32_t c = rd.get(off + len - 1u - s);

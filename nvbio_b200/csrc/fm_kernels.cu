@@ -117,7 +117,7 @@ fm_ktab_level_kernel(const FmIndex f, uint2* __restrict__ tab, uint32_t prev_ent
     }
 }
 
-// the same with 16-byte entries {x, y, -, -}, and the pass that fills SA[x] into the single-row ones
+// the same with 16-byte entries {x, y, -, -}, and the pass that fills the SA values into the one- and two-row ones
 __global__ void __launch_bounds__(FM_BLOCKDIM)
 fm_ktab16_level_kernel(const FmIndex f, uint4* __restrict__ tab, uint32_t prev_entries)
 {
@@ -137,7 +137,9 @@ fm_ktab16_locate_kernel(const FmIndex f, uint4* __restrict__ tab, uint64_t entri
     const uint64_t v = (uint64_t)blockIdx.x * FM_BLOCKDIM + threadIdx.x;
     if (v >= entries) return;
     const uint4 e = tab[v];
-    if (e.x == e.y) tab[v].z = f.ssa[e.x];              // full suffix array (checked by the caller): SA[x], 0xFFFFFFFF for the `$` row
+    // full suffix array (checked by the caller): SA[x] (0xFFFFFFFF for the `$` row) for one-row ranges, SA[x] and SA[y] for two-row ones
+    if (e.x == e.y)           tab[v].z = f.ssa[e.x];
+    else if (e.y == e.x + 1u) { tab[v].z = f.ssa[e.x]; tab[v].w = f.ssa[e.y]; }
 }
 
 // range sizes as uint64 (filter_inl.h:36-42: 1 + y - x in uint32 arithmetic, widened)

@@ -35,7 +35,7 @@ class FMIndexDevice:
         self.length, self.primary = int(length), int(primary)
         self.sa_interval = int(sa_interval)        # 16 = the reference's SA_INT; 1 = full suffix array
         self.ktab, self.ktab_k = ktab, int(ktab_k)  # optional k-mer range table (B200 extension)
-        self.ktab_located = False                   # True: 16-byte entries {x, y, SA[x], 0} (build_ktab(k, located=True))
+        self.ktab_located = False                   # True: 16-byte entries {x, y, SA[x], SA[y]} (build_ktab(k, located=True))
 
     # -- views ------------------------------------------------------------------------------
     def struct(self) -> FmIndexStruct:
@@ -61,7 +61,7 @@ class FMIndexDevice:
 
     def build_ktab(self, k: int = 12, located: bool = False):
         """k-mer range table (4^k x uint2): replaces the first k LF steps of every match().  located=True builds 16-byte entries
-        {x, y, SA[x], 0} instead (needs the full suffix array): a seed whose k-mer occurs once is located by the look-up itself"""
+        {x, y, SA[x], SA[y]} instead (needs the full suffix array): a seed whose k-mer occurs once or twice is located by the look-up itself"""
         self.ktab = None                                   # release a previous table before allocating the new one
         tab = torch.empty((4 ** k, 4 if located else 2), dtype=torch.int32, device=self.device)
         s = self.struct()

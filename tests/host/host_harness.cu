@@ -42,11 +42,12 @@ void hh_fm_build_ktab(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, u
         }
 }
 
-// 8-byte entries {x, y} -> 16-byte entries {x, y, SA[x] when x == y, 0} (what nvb_fm_build_ktab_located produces)
+// 8-byte entries {x, y} -> 16-byte entries {x, y, SA[x], SA[y]} (SA values for one- and two-row ranges: what nvb_fm_build_ktab_located produces)
 void hh_fm_ktab_locate(const uint32_t* ktab8, const uint32_t* full_sa, uint32_t k, uint32_t* ktab16) {
     for (uint64_t v = 0; v < (1ull << (2u * k)); ++v) {
         const uint32_t x = ktab8[2 * v], y = ktab8[2 * v + 1];
-        ktab16[4 * v] = x; ktab16[4 * v + 1] = y; ktab16[4 * v + 2] = (x == y) ? full_sa[x] : 0u; ktab16[4 * v + 3] = 0u;
+        ktab16[4 * v] = x; ktab16[4 * v + 1] = y;
+        ktab16[4 * v + 2] = (x == y || y == x + 1u) ? full_sa[x] : 0u; ktab16[4 * v + 3] = (y == x + 1u) ? full_sa[y] : 0u;
     }
 }
 

@@ -210,7 +210,7 @@ def test_ktab_gives_identical_ranges(O, k):
     qs = PackedStringSet.from_symbols(q2, offs, lens, bits=2)
     for flags in (0, nb.MATCH_FORWARD_ORDER | nb.MATCH_COMPLEMENT, nb.MATCH_FORWARD_ORDER, nb.MATCH_COMPLEMENT):
         assert torch.equal(nb.match(tab, qs, flags=flags), nb.match(plain, qs, flags=flags)), flags
-    # 16-byte "located" entries {x, y, SA[x], 0} (nvb_fm_build_ktab_located; needs the full suffix array): same ranges from every entry
+    # 16-byte "located" entries {x, y, SA[x], SA[y]} (nvb_fm_build_ktab_located; needs the full suffix array): same ranges from every entry
     # point, and SA[x] stored for exactly the single-row k-mers
     full, _ = nb.FMIndexDevice.from_text(dev_u32(pack_symbols(text, 2, True)), len(text), sa_interval=1)
     loc = full.build_ktab(k, located=True)
@@ -218,6 +218,8 @@ def test_ktab_gives_identical_ranges(O, k):
     assert t16.shape == (4 ** k, 4) and np.array_equal(t16[:len(kmers), :2], want_tab)
     single = t16[:, 0] == t16[:, 1]
     assert np.array_equal(t16[single, 2], host_u32(full.ssa)[t16[single, 0]]) and (single.any() or k < 9)
+    two = t16[:, 1] == t16[:, 0] + 1                        # two-row ranges carry both SA values
+    assert np.array_equal(t16[two, 2], host_u32(full.ssa)[t16[two, 0]]) and np.array_equal(t16[two, 3], host_u32(full.ssa)[t16[two, 1]])
     for flags in (0, nb.MATCH_FORWARD_ORDER | nb.MATCH_COMPLEMENT):
         assert torch.equal(nb.match(loc, qs, flags=flags), nb.match(plain, qs, flags=flags)), flags
     with pytest.raises(nb.NvbError):

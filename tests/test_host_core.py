@@ -90,7 +90,7 @@ def test_fm_core(H, O, n):
     for k in (1, 3, 6):
         ktab = np.zeros(2 * 4 ** k, np.uint32)
         H.hh_fm_build_ktab(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), C.c_uint32(k), _p(ktab))
-        # ... and the same through the 16-byte "located" entries {x, y, SA[x], 0}
+        # ... and the same through the 16-byte "located" entries {x, y, SA[x], SA[y]}
         full_sa = idx.sa.astype(np.uint32).copy(); full_sa[0] = 0xFFFFFFFF
         ktab16 = np.zeros(4 * 4 ** k, np.uint32)
         H.hh_fm_ktab_locate(_p(ktab), _p(full_sa), C.c_uint32(k), _p(ktab16))
@@ -380,7 +380,16 @@ def test_fm_match_locate_shortcut(H, O, n, k, bits):
         out16 = np.zeros((nq, 3), np.uint32)
         H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits),
                              C.c_uint32(1), _p(offs), _p(lens), C.c_uint32(nq), _p(out16), _p(ktab16), C.c_uint32(k), C.c_uint32(1))
-        assert np.array_equal(out16, out)
+        # same answers; a single row may come back as FM_RANGE (x, x) on one path and FM_LOCATED (its position) on the other (a k-mer
+        # with two occurrences is resolved by two text comparisons when the table carries both SA values): compare by meaning
+        def norm(o):
+            o = o.copy()
+            one = (o[:, 0] == 1) & (o[:, 1] == o[:, 2])
+            if one.any():
+                o[one, 1] = O.locate(idx, o[one, 1].astype(np.uint32)); o[one, 2] = 0xFFFFFFFF; o[one, 0] = 2
+            return o
+        assert np.array_equal(norm(out16), norm(out))
+        assert (out16[:, 0] == 2).sum() >= (out[:, 0] == 2).sum()
     n_loc = 0
     for i in range(nq):
         x, y = int(want[i, 0]), int(want[i, 1])
