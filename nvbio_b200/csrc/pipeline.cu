@@ -214,16 +214,21 @@ pipe_read_jobs_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict
     if (r < g.n_reads) {
         uint32_t lk_s[RJ_LOCAL], lk_b[RJ_LOCAL], lk_e[RJ_LOCAL];
         int n_local = 0;
+        // hit slots of this read: the scan's value at its first seed plus a running sum of the (clamped) range sizes, which are
+        // recomputed from the ranges exactly as the match kernel stored them -- one 8-byte load per seed instead of 16
+        uint32_t run = excl[r * g.strands * g.seeds_per_string];
         for (uint32_t strand = 0; strand < g.strands; ++strand) {
             const uint32_t s = r * g.strands + strand;
             const uint32_t len = slen[s];
             for (uint32_t k = 0; k < g.seeds_per_string; ++k) {
                 const uint32_t q = s * g.seeds_per_string + k;
-                const uint32_t sz = sizes[q];
-                if (sz == 0u) continue;
                 const uint2 rq = ranges[q];
-                const uint32_t base = excl[q], x = rq.x, seed_begin = k * g.seed_interval;
                 const bool located = rq.y == 0xFFFFFFFFu;                              // already a text position (fm_match_locate_one)
+                const uint32_t full = located ? 1u : ((rq.x <= rq.y) ? (rq.y - rq.x + 1u) : 0u);
+                const uint32_t sz = full < g.max_seed_hits ? full : g.max_seed_hits;
+                if (sz == 0u) continue;
+                const uint32_t base = run, x = rq.x, seed_begin = k * g.seed_interval;
+                run += sz;
                 for (uint32_t j = 0; j < sz; ++j) {
                     const uint32_t h = base + j;
                     if (h >= kept) break;                                              // beyond the caller's capacity

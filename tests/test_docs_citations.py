@@ -6,7 +6,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-DOCS = ["include/nvbio_b200.h", "include/nvbio_b200/nvbio_b200.hpp", "DESIGN.md", "INTEGRATION.md", "oracle/nvb_oracle.c", "oracle/ref_shim.cpp",
+DOCS = ["include/nvbio_b200.h", "DESIGN.md", "INTEGRATION.md", "oracle/nvb_oracle.c", "oracle/ref_shim.cpp",
         "oracle/ref_cuda_bench.cu", "oracle/orc.py", "oracle/cpu_pipeline.py",
         "nvbio_b200/csrc/common.cuh", "nvbio_b200/csrc/fm_core.cuh", "nvbio_b200/csrc/fm_kernels.cu", "nvbio_b200/csrc/gotoh_core.cuh",
         "nvbio_b200/csrc/gotoh_full_core.cuh", "nvbio_b200/csrc/gotoh_kernels.cu", "nvbio_b200/csrc/sa_build.cu", "nvbio_b200/csrc/pipeline.cu",
