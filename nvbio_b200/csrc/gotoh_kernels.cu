@@ -735,8 +735,9 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     }
     const uint32_t pgrid = (n_pairs + PAIR_BLOCKDIM - 1) / PAIR_BLOCKDIM;
     uint32_t tgrid = grid < 148u * 8u ? grid : 148u * 8u;
-    // occupancy per type as measured (tools/bench_full.py): LOCAL and SEMI_GLOBAL run fastest spill-free at 2 CTAs/SM, GLOBAL at 3
-    const int minb = g_full_minb ? g_full_minb : (type == NVB_GLOBAL ? 3 : 2);
+    // occupancy as measured (tools/bench_full.py, profiles/r02_bench_full_matrix.jsonl): with two text rows in flight every type runs
+    // fastest spill-free at 2 CTAs per SM (210-250 registers)
+    const int minb = g_full_minb ? g_full_minb : 2;
 #define NVB_FULL_PAIR(T)                                                                                               \
     if (minb == 2)      gotoh_full_pair_kernel<T, 2><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
     else if (minb == 4)        gotoh_full_pair_kernel<T, 4><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
