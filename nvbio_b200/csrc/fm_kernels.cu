@@ -9,7 +9,7 @@
 
 namespace nvb {
 
-constexpr int FM_BLOCKDIM = 256;
+constexpr int FM_BLOCKDIM = 128;          // queries finish after different numbers of gathers: small CTAs hand their warp slots on sooner (see pipeline.cu, SEED_BLOCK)
 
 __global__ void __launch_bounds__(FM_BLOCKDIM)
 fm_rank_kernel(const FmIndex f, const uint32_t* __restrict__ k, const uint8_t* __restrict__ c, uint32_t n,

@@ -117,13 +117,16 @@ pipe_make_strings_2bit_be_kernel(const StrSet reads, const PipeGeom g, uint32_t*
 // genome != NULL (the per-read path on an index with the full suffix array): single-row ranges are located on the spot --
 // ranges[q] = (text position, 0xFFFFFFFF), see fm_match_locate_one -- so that neither the remaining LF steps nor the later SA
 // gather of that hit are needed; wider ranges stay SA ranges.
-// (8 CTAs of 256 threads per SM = every warp slot: the kernel lives on gathers in flight, so the register budget is 32)
+// (2048 threads per SM = every warp slot: the kernel lives on gathers in flight, so the register budget is 32)
+// CTA size: seeds finish after 1 to 6 gathers, and a CTA's warp slots are only handed on when its last warp is done -- small CTAs
+// keep more of the 64 slots busy (measured, seed-match stage at C3: 512 threads 1.47 ms, 256 1.40, 128 1.35, 64 1.35)
+constexpr uint32_t SEED_BLOCK = 128;
 template <int BITS>
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(SEED_BLOCK, 2048 / SEED_BLOCK)
 pipe_seed_match_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __restrict__ words, const uint32_t* __restrict__ slen,
                        const uint32_t* __restrict__ genome, uint2* __restrict__ ranges, uint32_t* __restrict__ sizes)
 {
-    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t q = blockIdx.x * SEED_BLOCK + threadIdx.x;
     if (q >= g.n_strings * g.seeds_per_string) return;
     const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
     const uint32_t len = slen[s];
@@ -751,11 +754,11 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     NVB_STAGE(1);
     // 2. seed ranges
     {
-        const uint32_t grid = (nq + 255) / 256;
+        const uint32_t grid = (nq + SEED_BLOCK - 1) / SEED_BLOCK;
         // per-read path + full suffix array: single-row ranges are located inside the match kernel (g_pipe_path 2 switches that off)
         const uint32_t* loc_genome = (per_read && f.sa_shift == 0u && g_pipe_path != 2) ? d_genome : nullptr;
-        if (g.bits == 2) pipe_seed_match_kernel<2><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
-        else             pipe_seed_match_kernel<4><<<grid, 256, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
+        if (g.bits == 2) pipe_seed_match_kernel<2><<<grid, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
+        else             pipe_seed_match_kernel<4><<<grid, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(2);
