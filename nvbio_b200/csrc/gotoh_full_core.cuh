@@ -181,9 +181,12 @@ __host__ __device__ inline uint32_t gotoh_full_walk(const uint32_t* __restrict__
 // ---------------------------------------------------------------------------------------------
 static inline bool full_pair_path_ok(int type, const nvb_gotoh_scheme* s, uint32_t max_m, uint32_t max_n) {
     const int64_t Go = s->pattern_gap_open, Ge = s->pattern_gap_ext;
-    if (s->d_qual_table) return false;
     if (Go >= 0 || Ge >= 0 || s->text_gap_open >= 0 || s->text_gap_ext >= 0) return false;
-    const int64_t s_lo = s->match < s->mismatch ? s->match : s->mismatch, s_hi = s->match > s->mismatch ? s->match : s->mismatch;
+    int64_t s_lo = s->match < s->mismatch ? s->match : s->mismatch, s_hi = s->match > s->mismatch ? s->match : s->mismatch;
+    if (s->d_qual_table) {                               // quality-dependent scores: the caller's bounds on the table's values
+        if (s->qual_table_min == 0 && s->qual_table_max == 0) return false;      // unknown: the int32 kernel
+        s_lo = s->qual_table_min; s_hi = s->qual_table_max;
+    }
     int64_t mx = s_lo < 0 ? -s_lo : s_lo; if (s_hi > mx) mx = s_hi; if (-s_hi > mx) mx = -s_hi;
     if (-Go > mx) mx = -Go; if (-Ge > mx) mx = -Ge;
     if (-(int64_t)s->text_gap_open > mx) mx = -(int64_t)s->text_gap_open;
@@ -225,11 +228,14 @@ struct FullRow { uint32_t Vl, Vd, E, rowkey, vM, vlast; };
 struct FullConsts { uint32_t Ge2, Go2, GoX, beta2, keymul; };
 
 // one cell (column j = 1..FULL_W of the stripe) of text row R; V[j] / F[j] hold the previous row's values on entry and this row's on exit
-template <int TYPE, bool PARTIAL>
+// QUAL (quality-dependent substitution scores, nvBowtie's scheme): the score depends on the pattern COLUMN's base quality, so the
+// roles are swapped -- `colp` holds two 4-byte profiles per column (indexed by the TEXT symbol) and P0 carries the row's selector
+template <int TYPE, bool PARTIAL, bool QUAL>
 __host__ __device__ __forceinline__ void full_pair_cell(const int j, uint32_t (&V)[FULL_W + 1], uint32_t (&F)[FULL_W + 1], FullRow& R,
-        const uint32_t P0, const uint32_t P1, const uint16_t* sel, const uint32_t sel_stride, const uint32_t ncols, const FullConsts& K)
+        const uint32_t P0, const uint32_t P1, const uint16_t* sel, const uint32_t* colp, const uint32_t sel_stride, const uint32_t ncols, const FullConsts& K)
 {
-    const uint32_t s = prmt(P0, P1, (uint32_t)sel[(size_t)(j - 1) * sel_stride]);
+    const uint32_t s = QUAL ? prmt(colp[(size_t)(2 * (j - 1)) * sel_stride], colp[(size_t)(2 * (j - 1) + 1) * sel_stride], P0)
+                            : prmt(P0, P1, (uint32_t)sel[(size_t)(j - 1) * sel_stride]);
     F[j] = NVB_VIADDMAX(F[j], K.Ge2, V[j]);
     R.E  = NVB_VIADDMAX(R.E, K.Ge2, (j == 1) ? R.Vl : V[j - 1]);
     const uint32_t old = V[j];
@@ -250,10 +256,10 @@ __host__ __device__ __forceinline__ void full_pair_cell(const int j, uint32_t (&
 // Two text rows per loop iteration, the second one two columns behind the first (the same idea as in the banded kernel, gotoh_core.cuh:
 // a row is one serial chain E -> h' -> H; two rows in flight give a thread two independent chains).  The in-place V[] / F[] update
 // stays valid: row r+1 reads column j only after row r has written it, and keeps its own diagonal (the value it overwrote).
-template <int TYPE, bool PARTIAL>
+template <int TYPE, bool PARTIAL, bool QUAL>
 __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, const bool first, const bool last, const uint32_t b,
-        const uint32_t ncols, const uint32_t N, SymSeq t0, SymSeq t1, const uint16_t* sel, const uint32_t sel_stride,
-        uint2* __restrict__ col, const size_t col_stride, FullPairTrack& trk, uint32_t& g_last, const uint32_t* prof_tab)
+        const uint32_t ncols, const uint32_t N, SymSeq t0, SymSeq t1, const uint16_t* sel, const uint32_t* colp, const uint32_t sel_stride,
+        uint2* __restrict__ col, const size_t col_stride, FullPairTrack& trk, uint32_t& g_last, const uint32_t* prof_tab, uint32_t& bad_text)
 {
     const int32_t Go = S.pgo, Ge = S.pge;
     int32_t INF = SHRT_MIN - (Go < Ge ? Go : Ge);
@@ -303,8 +309,14 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
     uint32_t r = 0;
     for (; r + 1u < N; r += 2u) {
         const uint32_t ga0 = t0.next(), ga1 = t1.next(), gb0 = t0.next(), gb1 = t1.next();
-        const uint32_t PA0 = prof_tab ? prof_tab[ga0] : sub_profile(ga0, c_eq, c_ne), PA1 = prof_tab ? prof_tab[ga1] : sub_profile(ga1, c_eq, c_ne);
-        const uint32_t PB0 = prof_tab ? prof_tab[gb0] : sub_profile(gb0, c_eq, c_ne), PB1 = prof_tab ? prof_tab[gb1] : sub_profile(gb1, c_eq, c_ne);
+        uint32_t PA0, PA1, PB0, PB1;
+        if (QUAL) {                                   // row selectors from the text symbols (a text symbol > 3 has no selector: the caller bails out)
+            bad_text |= (ga0 | ga1 | gb0 | gb1) >> 2;
+            PA0 = pair_selector(ga0 & 3u, ga1 & 3u); PB0 = pair_selector(gb0 & 3u, gb1 & 3u); PA1 = PB1 = 0u;
+        } else {
+            PA0 = prof_tab ? prof_tab[ga0] : sub_profile(ga0, c_eq, c_ne); PA1 = prof_tab ? prof_tab[ga1] : sub_profile(ga1, c_eq, c_ne);
+            PB0 = prof_tab ? prof_tab[gb0] : sub_profile(gb0, c_eq, c_ne); PB1 = prof_tab ? prof_tab[gb1] : sub_profile(gb1, c_eq, c_ne);
+        }
         FullRow A, B;
         NVB_FULL_ROW_BEGIN(A, nA)
         NVB_FULL_ROW_BEGIN(B, nB)
@@ -314,8 +326,8 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
         }
 #pragma unroll
         for (int jj = 1; jj <= FULL_W + SK; ++jj) {
-            if (jj <= FULL_W) full_pair_cell<TYPE, PARTIAL>(jj,      V, F, A, PA0, PA1, sel, sel_stride, ncols, K);
-            if (jj > SK)      full_pair_cell<TYPE, PARTIAL>(jj - SK, V, F, B, PB0, PB1, sel, sel_stride, ncols, K);
+            if (jj <= FULL_W) full_pair_cell<TYPE, PARTIAL, QUAL>(jj,      V, F, A, PA0, PA1, sel, colp, sel_stride, ncols, K);
+            if (jj > SK)      full_pair_cell<TYPE, PARTIAL, QUAL>(jj - SK, V, F, B, PB0, PB1, sel, colp, sel_stride, ncols, K);
         }
         V[0] = B.Vl;
         NVB_FULL_ROW_END(A, r)
@@ -323,11 +335,13 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
     }
     if (r < N) {
         const uint32_t g0 = t0.next(), g1 = t1.next();
-        const uint32_t P0 = prof_tab ? prof_tab[g0] : sub_profile(g0, c_eq, c_ne), P1 = prof_tab ? prof_tab[g1] : sub_profile(g1, c_eq, c_ne);
+        uint32_t P0, P1;
+        if (QUAL) { bad_text |= (g0 | g1) >> 2; P0 = pair_selector(g0 & 3u, g1 & 3u); P1 = 0u; }
+        else      { P0 = prof_tab ? prof_tab[g0] : sub_profile(g0, c_eq, c_ne); P1 = prof_tab ? prof_tab[g1] : sub_profile(g1, c_eq, c_ne); }
         FullRow A;
         NVB_FULL_ROW_BEGIN(A, nA)
 #pragma unroll
-        for (int j = 1; j <= FULL_W; ++j) full_pair_cell<TYPE, PARTIAL>(j, V, F, A, P0, P1, sel, sel_stride, ncols, K);
+        for (int j = 1; j <= FULL_W; ++j) full_pair_cell<TYPE, PARTIAL, QUAL>(j, V, F, A, P0, P1, sel, colp, sel_stride, ncols, K);
         V[0] = A.Vl;
         NVB_FULL_ROW_END(A, r)
     }
@@ -343,16 +357,21 @@ __host__ __device__ __forceinline__ void full_pair_stripe(const GotohScheme& S, 
     }
 }
 
-template <int TYPE>
+// QUAL: `colp` (two words per stripe column, same stride as `sel`) replaces `sel`; `quals` = one base quality per pattern symbol at
+// the symbols' own offsets (NULL: quality 0 everywhere); S.qtab is the 256 x 2 table.  A pattern N is then simply a column whose
+// profile is all-mismatch; a text symbol > 3 makes the routine return false (the caller scores the pair with the int32 kernel).
+template <int TYPE, bool QUAL = false>
 __host__ __device__ inline bool gotoh_full_pair(const GotohScheme& S,
         const uint32_t* __restrict__ pwords, uint32_t pbits, uint32_t pbe, uint32_t poff0, uint32_t poff1, uint32_t M,
         const uint32_t* __restrict__ twords, uint32_t tbits, uint32_t tbe, uint32_t toff0, uint32_t toff1, uint32_t N,
         uint2* __restrict__ col, size_t col_stride, uint16_t* sel, uint32_t sel_stride, SinkResult& r0, SinkResult& r1,
-        const uint32_t* prof_tab = nullptr)      // optional 256-entry table of sub_profile(g, c_eq, c_ne) (shared memory on the device)
+        const uint32_t* prof_tab = nullptr,      // optional 256-entry table of sub_profile(g, c_eq, c_ne) (shared memory on the device)
+        uint32_t* colp = nullptr, const uint8_t* __restrict__ quals = nullptr)
 {
     const int32_t Go = S.pgo;
     r0.score = NVB_SINK_MIN; r0.x = r0.y = 0xFFFFFFFFu; r1 = r0;
     FullPairTrack trk; trk.s0 = trk.s1 = INT_MIN; trk.x0 = trk.x1 = 0u;
+    uint32_t bad_text = 0u;
     for (uint32_t b = 0; b < M; b += FULL_W) {
         const bool first = (b == 0), last = (b + FULL_W >= M);
         const uint32_t ncols = last ? M - b : (uint32_t)FULL_W;
@@ -363,16 +382,24 @@ __host__ __device__ inline bool gotoh_full_pair(const GotohScheme& S,
             for (int j = 0; j < FULL_W; ++j) {
                 uint32_t q0 = 0u, q1 = 0u;
                 if ((uint32_t)j < ncols) { q0 = p0.next(); q1 = p1.next(); }
-                bad |= (q0 | q1) >> 2;
-                sel[(size_t)j * sel_stride] = (uint16_t)pair_selector(q0 & 3u, q1 & 3u);
+                if (QUAL) {
+                    const uint32_t qq0 = (quals && (uint32_t)j < ncols) ? quals[poff0 + b + j] : 0u;
+                    const uint32_t qq1 = (quals && (uint32_t)j < ncols) ? quals[poff1 + b + j] : 0u;
+                    colp[(size_t)(2 * j) * sel_stride]     = sub_profile(q0, S.qtab[2 * qq0] - Go, S.qtab[2 * qq0 + 1] - Go);
+                    colp[(size_t)(2 * j + 1) * sel_stride] = sub_profile(q1, S.qtab[2 * qq1] - Go, S.qtab[2 * qq1 + 1] - Go);
+                } else {
+                    bad |= (q0 | q1) >> 2;
+                    sel[(size_t)j * sel_stride] = (uint16_t)pair_selector(q0 & 3u, q1 & 3u);
+                }
             }
             if (bad) return false;            // a pattern symbol >= 4 (N): not expressible as a 2-bit selector
         }
         trk.k0 = trk.k1 = -1; trk.r0 = trk.r1 = 0u;
         uint32_t g_last = 0u;
         const SymSeq t0(twords, tbits, tbe, toff0), t1(twords, tbits, tbe, toff1);
-        if (ncols == (uint32_t)FULL_W) full_pair_stripe<TYPE, false>(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last, prof_tab);
-        else                           full_pair_stripe<TYPE, true >(S, first, last, b, ncols, N, t0, t1, sel, sel_stride, col, col_stride, trk, g_last, prof_tab);
+        if (ncols == (uint32_t)FULL_W) full_pair_stripe<TYPE, false, QUAL>(S, first, last, b, ncols, N, t0, t1, sel, colp, sel_stride, col, col_stride, trk, g_last, prof_tab, bad_text);
+        else                           full_pair_stripe<TYPE, true,  QUAL>(S, first, last, b, ncols, N, t0, t1, sel, colp, sel_stride, col, col_stride, trk, g_last, prof_tab, bad_text);
+        if (QUAL && bad_text) return false;                     // an N in the text: no row selector for it
         if (TYPE == NVB_LOCAL) {
             if (r0.score <= (trk.k0 >> 5)) { r0.score = trk.k0 >> 5; r0.x = trk.r0 + 1u; r0.y = b + ((uint32_t)trk.k0 & 31u) + 1u; }
             if (r1.score <= (trk.k1 >> 5)) { r1.score = trk.k1 >> 5; r1.x = trk.r1 + 1u; r1.y = b + ((uint32_t)trk.k1 & 31u) + 1u; }

@@ -262,7 +262,8 @@ gotoh_full_traceback_kernel(const GotohScheme S, const GotohBatch b, int2* __res
 
 // full-matrix Gotoh, packed: one PAIR of alignments per thread (a, a+1); pairs that break a precondition of the packed
 // path go to the todo list and are scored by gotoh_full_todo_kernel (int32)
-template <int TYPE, int MINB>
+// QUAL: quality-dependent substitution scores (S.qtab + b.quals): per-column profiles in shared memory instead of selectors
+template <int TYPE, int MINB, bool QUAL = false>
 __global__ void __launch_bounds__(PAIR_BLOCKDIM, MINB)
 gotoh_full_pair_kernel(const GotohScheme S, const GotohBatch b, uint2* __restrict__ col, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
 {
@@ -280,10 +281,12 @@ gotoh_full_pair_kernel(const GotohScheme S, const GotohBatch b, uint2* __restric
     const uint32_t M1 = has1 ? str_len(b.pat, a1) : M0, N1 = has1 ? str_len(b.txt, a1) : N0;
     bool ok = (M0 == M1) && (N0 == N1) && M0 >= 1u && N0 >= 1u;
     SinkResult r0, r1;
-    __shared__ uint16_t sel[FULL_W * PAIR_BLOCKDIM];
-    if (ok) ok = gotoh_full_pair<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a0), str_off(b.pat, has1 ? a1 : a0), M0,
+    __shared__ uint16_t sel[QUAL ? 1 : FULL_W * PAIR_BLOCKDIM];
+    __shared__ uint32_t colp[QUAL ? 2 * FULL_W * PAIR_BLOCKDIM : 1];
+    if (ok) ok = gotoh_full_pair<TYPE, QUAL>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a0), str_off(b.pat, has1 ? a1 : a0), M0,
                                        b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a0), str_off(b.txt, has1 ? a1 : a0), N0,
-                                       col + p, (size_t)((b.n_max + 1u) >> 1), sel + threadIdx.x, PAIR_BLOCKDIM, r0, r1, prof_tab);
+                                       col + p, (size_t)((b.n_max + 1u) >> 1), QUAL ? sel : sel + threadIdx.x, PAIR_BLOCKDIM, r0, r1, prof_tab,
+                                       QUAL ? colp + threadIdx.x : colp, b.quals);
     if (ok) {
         b.score[a0] = r0.score; b.sink[a0] = make_uint2(r0.x, r0.y);
         if (has1) { b.score[a1] = r1.score; b.sink[a1] = make_uint2(r1.x, r1.y); }
@@ -689,7 +692,7 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     if (n == 0) return NVB_OK;
     if (!d_score || !d_sink) return NVB_E_INVALID;
     GotohBatch b;
-    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;     // a quality table routes to the int32 kernel
+    b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
     b.d_n = d_n; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
     const GotohScheme S = make_scheme(scheme);
     const uint32_t grid = (n + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
@@ -711,7 +714,7 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     const uint32_t max_m = patterns->length;
     // with a device-side count (`n` is then only a capacity) the batch is usually much smaller than its capacity: allow 4x
     const bool use_warp = g_full_warp == 1 || (g_full_warp == 0 && n_pairs <= (d_n ? 4u : 1u) * g_full_warp_max_pairs);
-    if (use_warp && max_m >= 1u && max_m <= 256u) {
+    if (use_warp && max_m >= 1u && max_m <= 256u && !S.qtab) {           // (the warp kernel has no quality-table form)
         const uint32_t Wc = (max_m + 31u) / 32u;
         const uint32_t wgrid = (uint32_t)(((uint64_t)n_pairs * 32u + WARP_BLOCKDIM - 1) / WARP_BLOCKDIM);
         const uint32_t tgrid2 = grid < 148u * 8u ? grid : 148u * 8u;
@@ -743,6 +746,21 @@ static int gotoh_full_impl(int type, const nvb_gotoh_scheme* scheme, const nvb_s
     else if (minb == 4)        gotoh_full_pair_kernel<T, 4><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
     else                       gotoh_full_pair_kernel<T, 3><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); \
     gotoh_full_todo_kernel<T><<<tgrid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, todo, todo_count);
+    if (S.qtab) {
+        // quality-dependent scores: per-column profiles (32 KB of shared memory per CTA), 2 CTAs per SM
+        switch (type) {
+        case NVB_GLOBAL: gotoh_full_pair_kernel<NVB_GLOBAL, 2, true><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); break;
+        case NVB_LOCAL:  gotoh_full_pair_kernel<NVB_LOCAL, 2, true><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); break;
+        default:         gotoh_full_pair_kernel<NVB_SEMI_GLOBAL, 2, true><<<pgrid, PAIR_BLOCKDIM, 0, s>>>(S, b, (uint2*)col, todo, todo_count); break;
+        }
+        switch (type) {
+        case NVB_GLOBAL: gotoh_full_todo_kernel<NVB_GLOBAL><<<tgrid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, todo, todo_count); break;
+        case NVB_LOCAL:  gotoh_full_todo_kernel<NVB_LOCAL><<<tgrid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, todo, todo_count); break;
+        default:         gotoh_full_todo_kernel<NVB_SEMI_GLOBAL><<<tgrid, GENERIC_BLOCKDIM, 0, s>>>(S, b, col, todo, todo_count); break;
+        }
+        NVB_LAUNCH_CHECK();
+        return NVB_OK;
+    }
     switch (type) {
     case NVB_GLOBAL: NVB_FULL_PAIR(NVB_GLOBAL) break;
     case NVB_LOCAL:  NVB_FULL_PAIR(NVB_LOCAL) break;

@@ -293,6 +293,49 @@ int hh_gotoh_full_pair(int type, const int32_t* scheme6,
     return packed;
 }
 
+// the packed full-matrix routine in its quality-table form (per-column profiles); falls back to the int32 routine pair by pair like
+// the kernel's todo list; returns the number of alignments that took the packed path, -2 when the scheme is not admitted
+int hh_gotoh_full_pair_qual(int type, const int32_t* scheme6, const int32_t* qtab, const uint8_t* quals,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,
+                  uint32_t max_m, uint32_t max_n, int32_t* score, uint32_t* sx, uint32_t* sy) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab; S.one = 1u; S.keymul = 32u;
+    nvb_gotoh_scheme cs; cs.match = S.match; cs.mismatch = S.mismatch; cs.pattern_gap_open = S.pgo; cs.pattern_gap_ext = S.pge;
+    cs.text_gap_open = S.tgo; cs.text_gap_ext = S.tge; cs.d_qual_table = qtab;
+    int32_t lo = qtab[0], hi = qtab[0];
+    for (int i = 0; i < 512; ++i) { lo = qtab[i] < lo ? qtab[i] : lo; hi = qtab[i] > hi ? qtab[i] : hi; }
+    cs.qual_table_min = lo; cs.qual_table_max = hi;
+    if (!full_pair_path_ok(type, &cs, max_m, max_n)) return -2;
+    int packed = 0;
+    for (uint32_t a = 0; a < n; a += 2) {
+        const uint32_t a1 = (a + 1 < n) ? a + 1 : a;
+        std::vector<uint2> col(tlen[a] + 1);
+        uint32_t colp[2 * FULL_W];
+        SinkResult r0, r1;
+        bool ok = plen[a] == plen[a1] && tlen[a] == tlen[a1] && plen[a] >= 1 && tlen[a] >= 1;
+        if (ok) {
+            if (type == 0)      ok = gotoh_full_pair<0, true>(S, pw, pbits, pbe, poff[a], poff[a1], plen[a], tw, tbits, tbe, toff[a], toff[a1], tlen[a], col.data(), 1, nullptr, 1, r0, r1, nullptr, colp, quals);
+            else if (type == 1) ok = gotoh_full_pair<1, true>(S, pw, pbits, pbe, poff[a], poff[a1], plen[a], tw, tbits, tbe, toff[a], toff[a1], tlen[a], col.data(), 1, nullptr, 1, r0, r1, nullptr, colp, quals);
+            else                ok = gotoh_full_pair<2, true>(S, pw, pbits, pbe, poff[a], poff[a1], plen[a], tw, tbits, tbe, toff[a], toff[a1], tlen[a], col.data(), 1, nullptr, 1, r0, r1, nullptr, colp, quals);
+        }
+        if (ok) {
+            packed += (a1 != a) ? 2 : 1;
+            score[a] = r0.score; sx[a] = r0.x; sy[a] = r0.y;
+            if (a1 != a) { score[a1] = r1.score; sx[a1] = r1.x; sy[a1] = r1.y; }
+        } else {
+            for (uint32_t k = a; k <= a1; ++k) {
+                std::vector<int2> c1(tlen[k] + 1);
+                SinkResult r;
+                if (type == 0)      r = gotoh_full_impl<0, false>(S, pw, pbits, pbe, poff[k], plen[k], tw, tbits, tbe, toff[k], tlen[k], c1.data(), 1, nullptr, 0, quals);
+                else if (type == 1) r = gotoh_full_impl<1, false>(S, pw, pbits, pbe, poff[k], plen[k], tw, tbits, tbe, toff[k], tlen[k], c1.data(), 1, nullptr, 0, quals);
+                else                r = gotoh_full_impl<2, false>(S, pw, pbits, pbe, poff[k], plen[k], tw, tbits, tbe, toff[k], tlen[k], c1.data(), 1, nullptr, 0, quals);
+                score[k] = r.score; sx[k] = r.x; sy[k] = r.y;
+            }
+        }
+    }
+    return packed;
+}
+
 int hh_gotoh_full_traceback(int type, const int32_t* scheme6,
                   const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                   const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n, uint32_t max_ops,

@@ -675,6 +675,40 @@ def test_gotoh_full_pair_stream_formats(H, O, pbits, pbe, tbits, tbe):
         assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, pbits, pbe, tbits, tbe)
 
 
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_gotoh_full_pair_quality_table(H, O, typ):
+    """the packed full-matrix routine with quality-dependent substitution scores (per-column profiles indexed by the text symbol, the row's
+    selector from the two text symbols) == the oracle's table-driven full DP: pairs of equal shape take the packed path (patterns with N
+    included: an N column is an all-mismatch profile), pairs of different shape and texts with N the int32 routine"""
+    from tests.test_oracle import _nvbowtie_like_table
+    rng = np.random.default_rng(4400 + typ)
+    qtab = _nvbowtie_like_table(); qt = np.ascontiguousarray(qtab.reshape(-1).astype(np.int32))
+    scheme = (int(qtab[0, 0]), int(qtab[0, 1]), -8, -3, -7, -2); s6 = np.array(scheme, np.int32)
+    most = 0
+    for n_frac, text_n in ((0.0, False), (0.02, False), (0.0, True)):
+        for pr_i, pr in enumerate((paired_full_problems(rng, 60, max_m=150, max_n=300), full_problems(rng, 60, max_m=100, max_n=200))):
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            pat = pat.copy(); txt = txt.copy()
+            if n_frac:
+                pat[rng.random(len(pat)) < n_frac] = 4
+            if text_n:
+                txt[rng.random(len(txt)) < 0.002] = 4
+            qual = rng.integers(0, 60, len(pat)).astype(np.uint8)
+            want = O.gotoh_full(typ, scheme, pat, p_off, p_len, txt, t_off, t_len, qual=qual, qtab=qtab)
+            pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 4, True)
+            n = len(p_off)
+            score = np.zeros(n, np.int32); sx = np.zeros(n, np.uint32); sy = np.zeros(n, np.uint32)
+            packed = H.hh_gotoh_full_pair_qual(C.c_int(typ), _p(s6), _p(qt), _p(qual), _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len),
+                                               _p(tw), C.c_uint32(4), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n),
+                                               C.c_uint32(int(max(p_len))), C.c_uint32(int(max(t_len))), _p(score), _p(sx), _p(sy))
+            assert packed >= 0
+            assert np.array_equal(score, want[0]) and np.array_equal(sx, want[1]) and np.array_equal(sy, want[2]), (typ, n_frac, text_n, packed)
+            most = max(most, packed)
+            if not text_n and pr_i == 0:
+                assert packed == n                    # equal-shape pairs, no N in the text: everything through the packed routine
+    assert most > 0
+
+
 def test_gotoh_window_quality_table(H, O):
     """windowed banded scoring with per-base qualities and a score table (the early-exit threshold then uses table[0] as the
     reference's scoring.match(0) does): pass-by-pass == the oracle, last pass == the whole-pattern score"""

@@ -40,4 +40,15 @@ for (n, M, N) in CONFIGS:
         ms = time_ms(lambda: aln.batch_alignment_score(al, P, T))
         nb.lib().nvb_debug_force_gotoh_path(C.c_int(0))
         out["int32_gcups"] = round(n * M * N / ms / 1e6, 1)
+        if (n, M, N) == CONFIGS[0]:
+            # nvBowtie's quality-dependent scheme (256 x 2 table + one base quality per pattern symbol): packed per-column-profile kernel vs int32
+            qs = aln.QualityGotohScheme(match_bonus=2, mm_min=2, mm_max=6, read_gap_const=5, read_gap_coeff=3, ref_gap_const=5, ref_gap_coeff=3)
+            alq = aln.make_gotoh_aligner(typ, qs)
+            quals = torch.randint(0, 41, (n * pw.shape[1] * 16,), dtype=torch.uint8, device="cuda", generator=g)
+            ms = time_ms(lambda: aln.batch_alignment_score(alq, P, T, quals=quals))
+            out["quality_packed_gcups"] = round(n * M * N / ms / 1e6, 1)
+            nb.lib().nvb_debug_force_gotoh_path(C.c_int(1))
+            ms = time_ms(lambda: aln.batch_alignment_score(alq, P, T, quals=quals))
+            nb.lib().nvb_debug_force_gotoh_path(C.c_int(0))
+            out["quality_int32_gcups"] = round(n * M * N / ms / 1e6, 1)
         print(json.dumps(out), flush=True)
