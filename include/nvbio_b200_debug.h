@@ -17,6 +17,9 @@ void nvb_debug_full_warp(int mode);
 void nvb_debug_pair_format(int on);
 /* 1 (default): the banded pair kernels keep two pattern rows in flight per thread; 0: one row per loop iteration */
 void nvb_debug_pair_rows2(int on);
+/* 1 (default): nvb_banded_gotoh_traceback resolves gap-free alignments from the score kernels' sink (gapless fast path) and runs the
+   direction-matrix traceback only for the others; 0: the direction-matrix traceback for every alignment */
+void nvb_debug_traceback_fast(int on);
 /* bytes of unused dynamic shared memory added to every banded pair-kernel CTA: measures what a landing buffer (e.g. for bulk
    copies of the text windows) would cost in resident CTAs per SM */
 void nvb_debug_pair_extra_smem(int bytes);

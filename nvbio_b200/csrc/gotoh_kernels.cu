@@ -14,6 +14,7 @@
 
 namespace nvb {
 
+static int g_traceback_fast = 1;        // nvb_debug_traceback_fast(0): every alignment through the full (direction-matrix) traceback
 static int g_pair_extra_smem = 0;       // nvb_debug_pair_extra_smem: bytes of unused dynamic shared memory added to every pair-kernel CTA (occupancy experiments)
 static int g_pair_rows2 = 1;            // nvb_debug_pair_rows2(0): one row per loop iteration in the pair kernels
 static bool g_pair_fmt_ok = true;       // nvb_debug_pair_format(0) forces the run-time-format kernel (tests compare the two)
@@ -484,14 +485,15 @@ gotoh_full_todo_kernel(const GotohScheme S, const GotohBatch b, int2* __restrict
 // (M rows x DirWords<B>::N words -- no checkpoints / recomputation: 2.4 KB per 150 x 31 alignment is nothing in 180 GB),
 // then the H/E/F state-machine walk from the sink.
 
+// todo != NULL: only the alignments listed there (those the gapless fast path could not resolve), todo_count on the device
 template <int B, int TYPE>
 __global__ void __launch_bounds__(GENERIC_BLOCKDIM)
-gotoh_traceback_kernel(const GotohScheme S, const GotohBatch b, const TracebackOut o)
+gotoh_traceback_kernel(const GotohScheme S, const GotohBatch b, const TracebackOut o, const uint32_t* __restrict__ todo, const uint32_t* __restrict__ todo_count)
 {
     constexpr int NW = DirWords<B>::N;
-    const uint32_t n = batch_count(b);
-    const uint32_t a = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x;
-    if (a >= n) return;
+    const uint32_t n = todo ? *todo_count : batch_count(b);
+    for (uint32_t i = blockIdx.x * GENERIC_BLOCKDIM + threadIdx.x; i < n; i += gridDim.x * GENERIC_BLOCKDIM) {
+    const uint32_t a = todo ? todo[i] : i;
     uint32_t* dirs = o.dirs + (size_t)a * o.dir_rows * NW;
     const uint32_t M = str_len(b.pat, a);
     SinkResult r; r.score = NVB_SINK_MIN; r.x = r.y = 0xFFFFFFFFu;
@@ -505,13 +507,49 @@ gotoh_traceback_kernel(const GotohScheme S, const GotohBatch b, const TracebackO
         cnt = gotoh_walk<B, TYPE>(dirs, r, o.ops + (size_t)a * o.max_ops, o.max_ops, sx, sy);
     o.source[a] = make_uint2(sx, sy);
     o.n_ops[a]  = cnt;
+    }
+}
+
+// gapless fast path (gapless_traceback, gotoh_core.cuh): score and sink are already in b.score / b.sink (from the score kernels); the
+// alignments it resolves get their source, op count and all-substitution op string, the others are appended to the todo list
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+gotoh_traceback_gapless_kernel(const GotohScheme S, const GotohBatch b, const TracebackOut o, uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
+{
+    const uint32_t a = blockIdx.x * 256 + threadIdx.x;
+    const bool in_range = a < b.n_max;
+    uint32_t len = 0u;
+    bool done = false;
+    if (in_range) {
+        const uint2 k = b.sink[a];
+        done = gapless_traceback<TYPE>(S, b.pat.words, b.pat.bits, b.pat.big_endian, str_off(b.pat, a), str_len(b.pat, a), b.quals,
+                                       b.txt.words, b.txt.bits, b.txt.big_endian, str_off(b.txt, a), str_len(b.txt, a), b.score[a], k.x, k.y, len);
+        if (done) {
+            o.source[a] = make_uint2(k.x - len, k.y - len);
+            o.n_ops[a]  = len;
+        } else {
+            todo[atomicAdd(todo_count, 1u)] = a;
+        }
+    }
+    // the op strings, a warp per row: 32 consecutive bytes per store instead of 32 rows touched by each
+    const uint32_t lane = threadIdx.x & 31u, a0 = a - lane;
+    const uint32_t wrote = __ballot_sync(0xffffffffu, done);
+    for (uint32_t w = wrote; w; w &= w - 1u) {
+        const uint32_t src = __ffs(w) - 1u;
+        uint32_t m = __shfl_sync(0xffffffffu, len, src);
+        m = m < o.max_ops ? m : o.max_ops;
+        uint8_t* ops = o.ops + (size_t)(a0 + src) * o.max_ops;
+        for (uint32_t i = lane; i < m; i += 32u) ops[i] = (uint8_t)DIR_SUB;
+    }
 }
 
 template <int B, int TYPE>
-static int launch_traceback(const GotohScheme& S, const GotohBatch& b, const TracebackOut& o, cudaStream_t s)
+static int launch_traceback(const GotohScheme& S, const GotohBatch& b, const TracebackOut& o, const uint32_t* todo, const uint32_t* todo_count, cudaStream_t s)
 {
+    // (with a todo list the count lives on the device: the grid is sized for the whole batch and the surplus CTAs leave at once --
+    // a capped, striding grid left most of the SMs' thread slots empty when only a minority of the alignments is listed)
     const uint32_t grid = (b.n_max + GENERIC_BLOCKDIM - 1) / GENERIC_BLOCKDIM;
-    gotoh_traceback_kernel<B, TYPE><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, o);
+    gotoh_traceback_kernel<B, TYPE><<<grid, GENERIC_BLOCKDIM, 0, s>>>(S, b, o, todo, todo_count);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
 }
@@ -593,14 +631,14 @@ static int dispatch_pair(int band, int type, const GotohScheme& S, const GotohBa
     return NVB_E_INVALID;
 }
 
-static int dispatch_traceback(int band, int type, const GotohScheme& S, const GotohBatch& b, const TracebackOut& o, cudaStream_t s)
+static int dispatch_traceback(int band, int type, const GotohScheme& S, const GotohBatch& b, const TracebackOut& o, const uint32_t* todo, const uint32_t* todo_count, cudaStream_t s)
 {
     switch (band) {
-    case 3:  NVB_TYPE_SWITCH(3,  launch_traceback, S, b, o, s)
-    case 5:  NVB_TYPE_SWITCH(5,  launch_traceback, S, b, o, s)
-    case 7:  NVB_TYPE_SWITCH(7,  launch_traceback, S, b, o, s)
-    case 15: NVB_TYPE_SWITCH(15, launch_traceback, S, b, o, s)
-    case 31: NVB_TYPE_SWITCH(31, launch_traceback, S, b, o, s)
+    case 3:  NVB_TYPE_SWITCH(3,  launch_traceback, S, b, o, todo, todo_count, s)
+    case 5:  NVB_TYPE_SWITCH(5,  launch_traceback, S, b, o, todo, todo_count, s)
+    case 7:  NVB_TYPE_SWITCH(7,  launch_traceback, S, b, o, todo, todo_count, s)
+    case 15: NVB_TYPE_SWITCH(15, launch_traceback, S, b, o, todo, todo_count, s)
+    case 31: NVB_TYPE_SWITCH(31, launch_traceback, S, b, o, todo, todo_count, s)
     }
     return NVB_E_INVALID;
 }
@@ -797,16 +835,39 @@ int nvb_banded_gotoh_traceback(int band_len, int type, const nvb_gotoh_scheme* s
     const uint32_t max_m = patterns->length ? patterns->length : 1u;
     TempCarver tc(d_temp);
     uint32_t* dirs = tc.take<uint32_t>((size_t)n * max_m * dir_words(band_len));
+    uint32_t* todo_count = tc.take<uint32_t>(4);
+    uint32_t* todo       = tc.take<uint32_t>((size_t)n + 2);
+    size_t score_bytes = 0;                                   // scratch of the score pass, carved behind the rest
+    {
+        const int r = banded_impl(band_len, type, scheme, patterns, d_quals, texts, nullptr, n, nullptr, nullptr, nullptr, &score_bytes, nullptr);
+        if (r != NVB_E_TEMP_SIZE && r != NVB_OK) return r;
+    }
+    char* score_tmp = tc.take<char>(score_bytes + 256);
     const size_t need = tc.total();
     if (!d_temp || *temp_bytes < need) { *temp_bytes = need; return NVB_E_TEMP_SIZE; }
     if (n == 0) return NVB_OK;
     if (!d_score || !d_sink || !d_source || !d_ops || !d_n_ops || max_ops == 0) return NVB_E_INVALID;
+    cudaStream_t s = as_stream(stream);
     GotohBatch b;
     b.pat = make_strset(patterns); b.txt = make_strset(texts); b.quals = d_quals;
     b.d_n = nullptr; b.n_max = n; b.score = d_score; b.sink = (uint2*)d_sink;
     TracebackOut o;
     o.source = (uint2*)d_source; o.ops = d_ops; o.n_ops = d_n_ops; o.max_ops = max_ops; o.dirs = dirs; o.dir_rows = max_m;
-    return dispatch_traceback(band_len, type, make_scheme(scheme), b, o, as_stream(stream));
+    const GotohScheme S = make_scheme(scheme);
+    if (!g_traceback_fast || type == NVB_GLOBAL)
+        return dispatch_traceback(band_len, type, S, b, o, nullptr, nullptr, s);
+    // 1. score + sink with the score kernels (DPX where admitted); 2. the gapless fast path resolves every alignment whose optimal path
+    // has no gap (most reads) from the sink alone; 3. the rest goes through the direction-matrix traceback
+    {
+        size_t sb = score_bytes + 256;
+        const int r = banded_impl(band_len, type, scheme, patterns, d_quals, texts, nullptr, n, d_score, d_sink, score_tmp, &sb, stream);
+        if (r != NVB_OK) return r;
+    }
+    NVB_CUDA_TRY(cudaMemsetAsync(todo_count, 0, sizeof(uint32_t), s));
+    if (type == NVB_LOCAL) gotoh_traceback_gapless_kernel<NVB_LOCAL><<<(n + 255u) / 256u, 256, 0, s>>>(S, b, o, todo, todo_count);
+    else                   gotoh_traceback_gapless_kernel<NVB_SEMI_GLOBAL><<<(n + 255u) / 256u, 256, 0, s>>>(S, b, o, todo, todo_count);
+    NVB_LAUNCH_CHECK();
+    return dispatch_traceback(band_len, type, S, b, o, todo, todo_count, s);
 }
 
 int nvb_banded_gotoh_score_window(int band_len, int type, const nvb_gotoh_scheme* scheme,
@@ -897,6 +958,7 @@ void nvb_debug_force_gotoh_path(int path) { g_force_path = path; }
 void nvb_debug_full_minb(int minb) { g_full_minb = minb; }
 void nvb_debug_full_warp(int mode) { g_full_warp = mode; }
 void nvb_debug_pair_rows2(int on) { nvb::g_pair_rows2 = on; }
+void nvb_debug_traceback_fast(int on) { nvb::g_traceback_fast = on; }
 void nvb_debug_pair_extra_smem(int bytes) { nvb::g_pair_extra_smem = bytes > 0 ? bytes : 0; }
 void nvb_debug_pair_format(int on) { nvb::g_pair_fmt_ok = on != 0; }
 

@@ -336,6 +336,22 @@ int hh_gotoh_full_pair_qual(int type, const int32_t* scheme6, const int32_t* qta
     return packed;
 }
 
+// gapless fast path of the banded traceback: ok[a] = 1 and len[a] = number of substitutions when the alignment (score, sink) is resolved
+int hh_gapless_traceback(int type, const int32_t* scheme6, const int32_t* qtab, const uint8_t* quals,
+                  const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
+                  const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n,
+                  const int32_t* score, const uint32_t* sink_xy, uint32_t* len, uint8_t* ok) {
+    GotohScheme S; S.match = scheme6[0]; S.mismatch = scheme6[1]; S.pgo = scheme6[2]; S.pge = scheme6[3]; S.tgo = scheme6[4]; S.tge = scheme6[5]; S.qtab = qtab; S.one = 1u; S.keymul = 32u;
+    for (uint32_t a = 0; a < n; ++a) {
+        uint32_t l = 0; bool r;
+        if (type == 0)      r = gapless_traceback<0>(S, pw, pbits, pbe, poff[a], plen[a], quals, tw, tbits, tbe, toff[a], tlen[a], score[a], sink_xy[2 * a], sink_xy[2 * a + 1], l);
+        else if (type == 1) r = gapless_traceback<1>(S, pw, pbits, pbe, poff[a], plen[a], quals, tw, tbits, tbe, toff[a], tlen[a], score[a], sink_xy[2 * a], sink_xy[2 * a + 1], l);
+        else                r = gapless_traceback<2>(S, pw, pbits, pbe, poff[a], plen[a], quals, tw, tbits, tbe, toff[a], tlen[a], score[a], sink_xy[2 * a], sink_xy[2 * a + 1], l);
+        len[a] = l; ok[a] = r ? 1 : 0;
+    }
+    return 0;
+}
+
 int hh_gotoh_full_traceback(int type, const int32_t* scheme6,
                   const uint32_t* pw, uint32_t pbits, uint32_t pbe, const uint32_t* poff, const uint32_t* plen,
                   const uint32_t* tw, uint32_t tbits, uint32_t tbe, const uint32_t* toff, const uint32_t* tlen, uint32_t n, uint32_t max_ops,

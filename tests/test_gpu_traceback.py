@@ -68,3 +68,42 @@ def test_traceback_vs_oracle(O, band, typ):
                 prev = op
             assert (j, i) == (int(got["sink"][a][0]), int(got["sink"][a][1]))
             assert s == int(got["score"][a]), (a, s, got["score"][a])
+
+
+@pytest.mark.parametrize("typ", [1, 2])
+def test_gapless_fast_path_equals_direction_matrix_traceback(O, typ):
+    """reads with few indels (most alignments are resolved by the gapless fast path from the score kernels' sink): every output equals
+    the oracle's traceback, and equals the direction-matrix traceback run for every alignment (nvb_debug_traceback_fast(0))"""
+    import ctypes as C
+    rng = np.random.default_rng(77 + typ)
+    for band, scheme in ((31, (2, -2, -5, -3)), (15, (2, -6, -8, -3)), (7, (1, -1, -1, -1))):
+        n, m = 1500, 120
+        pats, txts, p_off, p_len, t_off, t_len = [], [], [], [], [], []
+        po = to = 0
+        for a in range(n):
+            N = m + band
+            t = rng.integers(0, 4, N).astype(np.uint8)
+            j = int(rng.integers(0, band)); p = []
+            indel = 0.0 if a % 3 else 0.01
+            while len(p) < m:
+                r = rng.random()
+                if r < indel and j < N: p.append(int(rng.integers(0, 4)))
+                elif r < 2 * indel: j += 1
+                elif j < N:
+                    c = int(t[j]); c = int(rng.integers(0, 4)) if rng.random() < 0.03 else c
+                    p.append(c); j += 1
+                else: p.append(int(rng.integers(0, 4)))
+            pats.append(np.array(p[:m], np.uint8)); txts.append(t)
+            p_off.append(po); p_len.append(m); po += m; t_off.append(to); t_len.append(N); to += N
+        pr = (np.concatenate(pats), np.array(p_off, np.uint32), np.array(p_len, np.uint32), np.concatenate(txts), np.array(t_off, np.uint32), np.array(t_len, np.uint32))
+        want = O.banded_traceback(band, typ, scheme, *pr)
+        assert int((want["ops"].max(axis=1) == 0).sum()) > n // 3          # plenty of gap-free alignments
+        fast = run(band, typ, scheme, pr)
+        nb.lib().nvb_debug_traceback_fast(C.c_int(0))
+        try:
+            full = run(band, typ, scheme, pr)
+        finally:
+            nb.lib().nvb_debug_traceback_fast(C.c_int(1))
+        for k in ("score", "sink", "source", "n_ops", "ops"):
+            assert np.array_equal(fast[k], want[k]), (band, typ, k)
+            assert np.array_equal(full[k], want[k]), (band, typ, k, "full")

@@ -676,6 +676,40 @@ def test_gotoh_full_pair_stream_formats(H, O, pbits, pbe, tbits, tbe):
 
 
 @pytest.mark.parametrize("typ", [0, 1, 2])
+@pytest.mark.parametrize("band", [7, 15, 31])
+def test_gapless_traceback_fast_path(H, O, band, typ):
+    """gapless_traceback (the fast path of nvb_banded_gotoh_traceback): whenever it claims an alignment from (score, sink) alone, the
+    oracle's traceback (pinned to the reference's) is exactly that all-substitution suffix of the sink's diagonal -- reads with and
+    without indels, N's in pattern and text (never claimed through), every scheme; GLOBAL is never claimed"""
+    rng = np.random.default_rng(band * 11 + typ)
+    claimed = 0
+    for scheme in ((2, -2, -5, -3), (2, -6, -8, -3), (1, -1, -1, -1), (0, -5, -8, -3)):
+        for with_n in (False, True):
+            pr = list(fixed_problems(rng, 120, band, 90, ragged=(typ == 1)))
+            if with_n:
+                pr[0] = pr[0].copy(); pr[0][rng.random(len(pr[0])) < 0.01] = 4
+                pr[3] = pr[3].copy(); pr[3][rng.random(len(pr[3])) < 0.01] = 4
+            pat, p_off, p_len, txt, t_off, t_len = pr
+            want = O.banded_traceback(band, typ, scheme, *pr, max_ops=256)
+            n = len(p_off)
+            pw, tw = pack_symbols(pat, 4, True), pack_symbols(txt, 4, True)
+            s6 = np.array(scheme + (scheme[2], scheme[3]), np.int32)
+            ln = np.zeros(n, np.uint32); ok = np.zeros(n, np.uint8)
+            sink = np.ascontiguousarray(want["sink"].astype(np.uint32))
+            H.hh_gapless_traceback(C.c_int(typ), _p(s6), None, None, _p(pw), C.c_uint32(4), C.c_uint32(1), _p(p_off), _p(p_len),
+                                   _p(tw), C.c_uint32(4), C.c_uint32(1), _p(t_off), _p(t_len), C.c_uint32(n),
+                                   _p(np.ascontiguousarray(want["score"].astype(np.int32))), _p(sink), _p(ln), _p(ok))
+            if typ == 0:
+                assert not ok.any()
+            for a in np.nonzero(ok)[0]:
+                L = int(ln[a])
+                assert int(want["n_ops"][a]) == L and not want["ops"][a][:L].any(), (band, typ, scheme, a)
+                assert tuple(int(v) for v in want["source"][a]) == (int(sink[a, 0]) - L, int(sink[a, 1]) - L), (band, typ, scheme, a)
+            claimed += int(ok.sum())
+    assert typ == 0 or claimed > 20
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
 def test_gotoh_full_pair_quality_table(H, O, typ):
     """the packed full-matrix routine with quality-dependent substitution scores (per-column profiles indexed by the text symbol, the row's
     selector from the two text symbols) == the oracle's table-driven full DP: pairs of equal shape take the packed path (patterns with N

@@ -11,13 +11,13 @@ n = 50_000_000
 gw = synth.random_genome_words(n)
 n_al, M, W = 1_000_000, 150, 181
 rw, pos, _ = synth.sample_reads(gw, n, n_al, M, rc_half=False)
-begin = (pos - 15).clamp_(0)
 P = PackedStringSet.fixed(rw.reshape(-1), n_al, M, stride=rw.shape[1] * 16)
-T = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=begin.to(torch.int32), lengths=None, stride=0, length=W, count=n_al)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for typ in (1, 2):
     al = aln.make_gotoh_aligner(typ, aln.SimpleGotohScheme(2, -2, -5, -3))
     for band in (31, 15):
+        begin = (pos - band // 2).clamp_(0)                  # the read's own diagonal sits mid-band
+        T = PackedStringSet(words=gw, bits=2, big_endian=True, offsets=begin.to(torch.int32), lengths=None, stride=0, length=M + band - 1, count=n_al)
         def score(): return aln.batch_banded_alignment_score(band, al, P, T)
         def trace(): return aln.batch_banded_alignment_traceback(band, al, P, T)
         out = {}
