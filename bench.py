@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--sa-interval", type=int, default=1, help="sampled-SA interval of the device index (16 = reference format, 1 = full SA)")
     ap.add_argument("--ktab-k", type=int, default=16, help="k of the k-mer range table (0 = none)")
-    ap.add_argument("--ktab-located", type=int, default=1, help="1: 16-byte table entries {x, y, SA[x], SA[y]} (needs --sa-interval 1; 69 GB at k = 16), 0: 8-byte {x, y}")
+    ap.add_argument("--ktab-located", type=int, default=2, help="0: 8-byte table entries {x, y}; 1: 16-byte entries {x, y, SA[x], SA[y]} (needs --sa-interval 1; 69 GB at k = 16); "
+                    "2: the same, one-row entries also hold the 16 text symbols before SA[x] (nvb_fm_build_ktab_context)")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-to-host (e2e) pipeline")
     ap.add_argument("--e2e-sweep", action="store_true", help="also time the host-to-host pipeline with other (depth, compute streams) shapes")
     ap.add_argument("--no-dedup", action="store_true", help="score every hit separately (no job de-duplication)")
@@ -180,7 +181,8 @@ def build_index(args, rank, world, device):
         barrier(world); t_bcast = time.perf_counter() - t0
     if args.ktab_k > 0 and args.impl == "ours":
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        fmi.build_ktab(args.ktab_k, located=bool(args.ktab_located) and args.sa_interval == 1)   # every rank derives the table from its replica
+        fmi.build_ktab(args.ktab_k, located=bool(args.ktab_located) and args.sa_interval == 1,    # every rank derives the table from its replica
+                       text=genome if args.ktab_located == 2 else None)
         torch.cuda.synchronize(); t_build += time.perf_counter() - t0
     return n, genome, fmi, t_build, t_bcast
 
@@ -322,10 +324,10 @@ def workload_config(args, n, reads_per_gpu, world, index=None):
 
 def index_description(sa_interval, ktab_k, n, nbytes=None, located=False):
     eb = 16 if located else 8
-    d = {"sa_interval": sa_interval, "ktab_k": ktab_k, "ktab_located": bool(located and ktab_k),
+    d = {"sa_interval": sa_interval, "ktab_k": ktab_k, "ktab_located": int(located) if ktab_k else 0,
          "layout": "%s + %s" % ("full suffix array (4 B per base)" if sa_interval == 1 else "SA sampled every %d rows" % sa_interval,
                                 ("%d-mer SA-range table (4^%d x %d B = %.1f GB%s)" % (ktab_k, ktab_k, eb, 4 ** ktab_k * eb / 1e9,
-                                                                                     "; entries {x, y, SA[x], SA[y]}" if located else "")) if ktab_k else "no k-mer table (the reference's format)")}
+                                                                                     ("; entries {x, y, SA[x], SA[y]}" + (", one-row entries {x, x, SA[x], 16 text symbols before SA[x]}" if int(located) == 2 else "")) if located else "")) if ktab_k else "no k-mer table (the reference's format)")}
     if nbytes is not None:
         d["bytes_per_gpu"] = int(nbytes)
     return d
@@ -786,9 +788,9 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic("pipe_seed_match_kernel", ktab_k=args.ktab_k, genome_bp=n, reads=n_reads, ktab_located=bool(fmi.ktab_located), single_row_fold=(fmi.sa_interval == 1)),
+                     "traffic": measured_traffic("pipe_seed_match_kernel", ktab_k=args.ktab_k, genome_bp=n, reads=n_reads, ktab_located=int(fmi.ktab_located), single_row_fold=(fmi.sa_interval == 1)),
                      "peak_source": peak_src, "ms_per_launch": fm_ms,
-                     "gather_rate": gather_rate(fm_ms, ktab_k=args.ktab_k, genome_bp=n, reads=n_reads, ktab_located=bool(fmi.ktab_located),
+                     "gather_rate": gather_rate(fm_ms, ktab_k=args.ktab_k, genome_bp=n, reads=n_reads, ktab_located=int(fmi.ktab_located),
                                                 single_row_fold=(fmi.sa_interval == 1)),
                      "algorithmic_bytes_per_seed": bytes_per_seed, "blocks_per_seed": tail_blocks,
                      "reference_algorithm_bytes_per_seed": ref_bytes_per_seed, "reference_algorithm_blocks_per_seed": blocks_per_seed,

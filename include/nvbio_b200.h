@@ -65,7 +65,9 @@ typedef struct nvb_fm_index {
     uint32_t        ktab_located;/* 0: d_ktab holds 8-byte entries {x, y};  1: 16-byte entries {x, y, SA[x], SA[y]} built by
                                     nvb_fm_build_ktab_located (SA[x] valid when y == x, both when y == x + 1): a seed whose
                                     k-mer occurs once or twice is located by the look-up + a text comparison, without walking the
-                                    range on.  Ranges are identical either way.  */
+                                    range on;  2: the same table built by nvb_fm_build_ktab_context -- the last word of a ONE-row
+                                    entry (y == x) holds the 16 text symbols before SA[x] instead, so that such a seed (up to k + 16
+                                    symbols long) is resolved by the look-up alone.  Ranges are identical in every case.  */
 } nvb_fm_index;
 
 /* A set of strings stored in one packed symbol stream (nvbio PackedStream semantics,
@@ -359,6 +361,11 @@ int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, vo
  * traded for dependent gathers).  The SA values are filled for ranges of one row (x == y) or two (y == x + 1) and need the full suffix array
  * (fmi->sa_interval == 1), else NVB_E_UNSUPPORTED.  Use with nvb_fm_index.d_ktab = d_ktab16, ktab_located = 1. */
 int nvb_fm_build_ktab_located(const nvb_fm_index* fmi, uint32_t k, void* d_ktab16, void* stream);
+
+/* nvb_fm_build_ktab_located + text context: for every one-row entry the unused last word is filled with the (up to) 16 symbols of
+ * d_text (2-bit big-endian, the text the index was built from) that precede SA[x], symbol SA[x]-1 in the two lowest bits.
+ * Use with nvb_fm_index.d_ktab = d_ktab16, ktab_located = 2. */
+int nvb_fm_build_ktab_context(const nvb_fm_index* fmi, uint32_t k, const uint32_t* d_text, void* d_ktab16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Seed + extend composition (the fmmap / nvBowtie hot loop: seeds -> match -> locate -> window ->

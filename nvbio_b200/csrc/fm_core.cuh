@@ -28,6 +28,7 @@ struct FmIndex {
     uint32_t sa_mask, sa_shift;    // sampled-SA interval I = 1 << sa_shift, mask = I - 1
     uint32_t ktab_k;
     uint32_t ktab_located;         // 1: table entries are 16 bytes {x, y, SA[x], SA[y]} (SA values filled for ranges of one or two rows; nvb_fm_build_ktab_located)
+                                   // 2: the same, and the last word of a ONE-row entry holds the 16 text symbols before SA[x] (nvb_fm_build_ktab_context)
     // constant-index selects keep the struct in the kernel-parameter constant bank (a dynamic L2[c]
     // would force a local-memory copy of the whole struct)
     __host__ __device__ __forceinline__ uint32_t l2(uint32_t c) const {
@@ -42,7 +43,7 @@ static inline bool valid_fmindex(const nvb_fm_index* f) {
     if (!f || !f->d_bwt_occ) return false;
     const uint32_t I = f->sa_interval;
     if (I != 0 && (I & (I - 1)) != 0) return false;           // power of two
-    if (f->d_ktab && (f->ktab_k < 1 || f->ktab_k > 16)) return false;
+    if (f->d_ktab && (f->ktab_k < 1 || f->ktab_k > 16 || f->ktab_located > 2u)) return false;
     return true;
 }
 static inline FmIndex make_fmindex(const nvb_fm_index* f) {
@@ -53,7 +54,7 @@ static inline FmIndex make_fmindex(const nvb_fm_index* f) {
     r.sa_shift = 0; while ((1u << r.sa_shift) < I) ++r.sa_shift;
     r.sa_mask = (1u << r.sa_shift) - 1u;
     r.ktab = (const uint2*)f->d_ktab; r.ktab_k = f->d_ktab ? f->ktab_k : 0u;
-    r.ktab_located = (f->d_ktab && f->ktab_located) ? 1u : 0u;
+    r.ktab_located = f->d_ktab ? f->ktab_located : 0u;
     return r;
 }
 
@@ -400,6 +401,19 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
             const uint32_t rem = len - s;                 // symbols [0, rem) of the query are still to be consumed
             // (have_pos can only be set on the first pass: a single-row range returns from this branch)
             const uint32_t pos = have_pos ? known_pos : gather_u32(f.ssa + x);
+            if (have_pos && f.ktab_located == 2u && rem <= 16u) {
+                // the entry also carries the 16 text symbols before SA[x] (symbol SA[x]-1 in the lowest bits): the comparison needs
+                // no read of the text at all -- the look-up was this seed's only gather
+                if (pos == 0xFFFFFFFFu || pos < rem) return FM_EMPTY;
+                uint32_t qw = 0u; bool n_left = false;
+                if (BITS == 2 && BE)      qw = be2_window(words, off, rem) >> (32u - 2u * rem);
+                else if (BITS == 4 && BE) qw = be4_window(words, off, rem, n_left) >> (32u - 2u * rem);
+                else for (uint32_t i = 0; i < rem; ++i) { const uint32_t c = rd.get(off + i); n_left |= (c > 3u); qw = (qw << 2) | (c & 3u); }
+                const uint32_t mask = rem == 16u ? 0xFFFFFFFFu : ((1u << (2u * rem)) - 1u);
+                if (n_left || ((qw ^ known_pos2) & mask) != 0u) return FM_EMPTY;
+                ox = pos - rem; oy = 0xFFFFFFFFu;
+                return FM_LOCATED;
+            }
             if (!prefix_matches(pos, rem)) return FM_EMPTY;
             ox = pos - rem; oy = 0xFFFFFFFFu;
             return FM_LOCATED;

@@ -142,6 +142,19 @@ fm_ktab16_locate_kernel(const FmIndex f, uint4* __restrict__ tab, uint64_t entri
     else if (e.y == e.x + 1u) { tab[v].z = f.ssa[e.x]; tab[v].w = f.ssa[e.y]; }
 }
 
+// one-row entries of a located table: .w = the (up to) 16 text symbols before SA[x], symbol SA[x]-1 in the lowest two bits
+__global__ void __launch_bounds__(FM_BLOCKDIM)
+fm_ktab16_context_kernel(const uint32_t* __restrict__ text, uint4* __restrict__ tab, uint64_t entries)
+{
+    const uint64_t v = (uint64_t)blockIdx.x * FM_BLOCKDIM + threadIdx.x;
+    if (v >= entries) return;
+    const uint4 e = tab[v];
+    if (e.x != e.y) return;
+    const uint32_t pos = e.z;
+    const uint32_t cnt = (pos == 0xFFFFFFFFu) ? 0u : (pos < 16u ? pos : 16u);
+    tab[v].w = cnt ? (be2_window(text, pos - cnt, cnt) >> (32u - 2u * cnt)) : 0u;
+}
+
 // range sizes as uint64 (filter_inl.h:36-42: 1 + y - x in uint32 arithmetic, widened)
 struct RangeSize {
     __host__ __device__ __forceinline__ uint64_t operator()(const uint2& r) const { return (uint64_t)(uint32_t)(1u + r.y - r.x); }
@@ -314,6 +327,17 @@ int nvb_fm_build_ktab_located(const nvb_fm_index* fmi, uint32_t k, void* d_ktab1
     }
     const uint64_t entries = 1ull << (2u * k);
     fm_ktab16_locate_kernel<<<(uint32_t)((entries + FM_BLOCKDIM - 1) / FM_BLOCKDIM), FM_BLOCKDIM, 0, s>>>(f, (uint4*)d_ktab16, entries);
+    NVB_LAUNCH_CHECK();
+    return NVB_OK;
+}
+
+int nvb_fm_build_ktab_context(const nvb_fm_index* fmi, uint32_t k, const uint32_t* d_text, void* d_ktab16, void* stream)
+{
+    if (!d_text) return NVB_E_INVALID;
+    const int r = nvb_fm_build_ktab_located(fmi, k, d_ktab16, stream);
+    if (r != NVB_OK) return r;
+    const uint64_t entries = 1ull << (2u * k);
+    fm_ktab16_context_kernel<<<(uint32_t)((entries + FM_BLOCKDIM - 1) / FM_BLOCKDIM), FM_BLOCKDIM, 0, as_stream(stream)>>>(d_text, (uint4*)d_ktab16, entries);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
 }

@@ -35,7 +35,7 @@ class FMIndexDevice:
         self.length, self.primary = int(length), int(primary)
         self.sa_interval = int(sa_interval)        # 16 = the reference's SA_INT; 1 = full suffix array
         self.ktab, self.ktab_k = ktab, int(ktab_k)  # optional k-mer range table (B200 extension)
-        self.ktab_located = False                   # True: 16-byte entries {x, y, SA[x], SA[y]} (build_ktab(k, located=True))
+        self.ktab_located = 0                       # 1: 16-byte entries {x, y, SA[x], SA[y]} (build_ktab(k, located=True)); 2: + text context (text=...)
 
     # -- views ------------------------------------------------------------------------------
     def struct(self) -> FmIndexStruct:
@@ -48,7 +48,7 @@ class FMIndexDevice:
         s.sa_interval = self.sa_interval
         s.d_ktab = self.ktab.data_ptr() if self.ktab is not None else None
         s.ktab_k = self.ktab_k if self.ktab is not None else 0
-        s.ktab_located = 1 if (self.ktab is not None and self.ktab_located) else 0
+        s.ktab_located = int(self.ktab_located) if self.ktab is not None else 0
         return s
 
     @property
@@ -59,17 +59,23 @@ class FMIndexDevice:
         return (self.bwt_occ.numel() * 4 + (self.ssa.numel() * 4 if self.ssa is not None else 0) +
                 (self.ktab.numel() * 4 if self.ktab is not None else 0))
 
-    def build_ktab(self, k: int = 12, located: bool = False):
+    def build_ktab(self, k: int = 12, located: bool = False, text: Optional[torch.Tensor] = None):
         """k-mer range table (4^k x uint2): replaces the first k LF steps of every match().  located=True builds 16-byte entries
-        {x, y, SA[x], SA[y]} instead (needs the full suffix array): a seed whose k-mer occurs once or twice is located by the look-up itself"""
+        {x, y, SA[x], SA[y]} instead (needs the full suffix array): a seed whose k-mer occurs once or twice is located by the look-up
+        itself.  With text (the 2-bit big-endian words the index was built from) one-row entries also carry the 16 symbols before
+        SA[x] (nvb_fm_build_ktab_context): such a seed needs no read of the text at all."""
         self.ktab = None                                   # release a previous table before allocating the new one
         tab = torch.empty((4 ** k, 4 if located else 2), dtype=torch.int32, device=self.device)
         s = self.struct()
-        if located:
+        if located and text is not None:
+            assert text.is_cuda and text.dtype == torch.int32
+            check(lib().nvb_fm_build_ktab_context(C.byref(s), C.c_uint32(k), C.c_void_p(text.data_ptr()), C.c_void_p(tab.data_ptr()), _stream()),
+                  "nvb_fm_build_ktab_context")
+        elif located:
             check(lib().nvb_fm_build_ktab_located(C.byref(s), C.c_uint32(k), C.c_void_p(tab.data_ptr()), _stream()), "nvb_fm_build_ktab_located")
         else:
             check(lib().nvb_fm_build_ktab(C.byref(s), C.c_uint32(k), C.c_void_p(tab.data_ptr()), _stream()), "nvb_fm_build_ktab")
-        self.ktab, self.ktab_k, self.ktab_located = tab, k, bool(located)
+        self.ktab, self.ktab_k, self.ktab_located = tab, k, (2 if (located and text is not None) else (1 if located else 0))
         return self
 
     # -- construction -----------------------------------------------------------------------

@@ -51,6 +51,16 @@ void hh_fm_ktab_locate(const uint32_t* ktab8, const uint32_t* full_sa, uint32_t 
     }
 }
 
+// ... + the text context of one-row entries (what nvb_fm_build_ktab_context adds): .w = the up to 16 symbols before SA[x]
+void hh_fm_ktab_context(uint32_t* ktab16, uint32_t k, const uint32_t* text_words) {
+    for (uint64_t v = 0; v < (1ull << (2u * k)); ++v) {
+        if (ktab16[4 * v] != ktab16[4 * v + 1]) continue;
+        const uint32_t pos = ktab16[4 * v + 2];
+        const uint32_t cnt = (pos == 0xFFFFFFFFu) ? 0u : (pos < 16u ? pos : 16u);
+        ktab16[4 * v + 3] = cnt ? (be2_window(text_words, pos - cnt, cnt) >> (32u - 2u * cnt)) : 0u;
+    }
+}
+
 void hh_fm_match(const uint32_t* bwt_occ, const uint32_t* L2, uint32_t n, uint32_t primary,
                  const uint32_t* words, uint32_t bits, uint32_t be, const uint32_t* off, const uint32_t* len, uint32_t nq,
                  uint32_t flags, uint32_t* out_xy, const uint32_t* ktab, uint32_t ktab_k, uint32_t ktab_located) {

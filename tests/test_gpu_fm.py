@@ -222,6 +222,21 @@ def test_ktab_gives_identical_ranges(O, k):
     assert np.array_equal(t16[two, 2], host_u32(full.ssa)[t16[two, 0]]) and np.array_equal(t16[two, 3], host_u32(full.ssa)[t16[two, 1]])
     for flags in (0, nb.MATCH_FORWARD_ORDER | nb.MATCH_COMPLEMENT):
         assert torch.equal(nb.match(loc, qs, flags=flags), nb.match(plain, qs, flags=flags)), flags
+    # ... + text context (nvb_fm_build_ktab_context): the last word of a one-row entry = the up to 16 symbols before SA[x]
+    tw = dev_u32(np.concatenate([pack_symbols(text, 2, True), np.zeros(2, np.uint32)]))
+    ctx = full.build_ktab(k, located=True, text=tw)
+    assert ctx.ktab_located == 2
+    c16 = host_u32(ctx.ktab)
+    assert np.array_equal(c16[:, :3], t16[:, :3]) and np.array_equal(c16[~single, 3], t16[~single, 3])
+    for v in np.flatnonzero(single)[:: max(1, int(single.sum()) // 500)]:
+        pos = int(c16[v, 2])
+        cnt = 0 if pos == 0xFFFFFFFF else min(pos, 16)
+        want_ctx = 0
+        for sym in text[pos - cnt:pos] if cnt else []:
+            want_ctx = (want_ctx << 2) | int(sym)
+        assert int(c16[v, 3]) == want_ctx, (v, pos)
+    for flags in (0, nb.MATCH_FORWARD_ORDER | nb.MATCH_COMPLEMENT):
+        assert torch.equal(nb.match(ctx, qs, flags=flags), nb.match(plain, qs, flags=flags)), flags
     with pytest.raises(nb.NvbError):
         upload(idx).build_ktab(k, located=True)                 # sampled SA: unsupported
 

@@ -49,7 +49,7 @@ def H():
     genome = synth.random_genome_words(N)
     fmi, _ = nb.FMIndexDevice.from_text(genome, N, sa_interval=SA_INTERVAL)
     torch.cuda.empty_cache()
-    fmi.build_ktab(KTAB_K, located=True)          # bench.py's default: 16-byte entries {x, y, SA[x], SA[y]}
+    fmi.build_ktab(KTAB_K, located=True, text=genome)   # bench.py's default: 16-byte entries {x, y, SA[x], SA[y] | text context}
     torch.cuda.synchronize()
     gwh = host_u32(genome)
     return dict(genome=genome, fmi=fmi, gwh=gwh)

@@ -312,7 +312,8 @@ def test_seed_extend_with_base_qualities():
 
 def test_single_row_fold_and_located_table():
     """full suffix array: the per-read path locates single-row ranges inside the match kernel (SA gather + text compare instead of the
-    remaining LF steps), and with the 16-byte located k-mer table the SA gather of a single-row k-mer comes with the table entry;
+    remaining LF steps), with the 16-byte located k-mer table the SA gather of a single-row k-mer comes with the table entry, and
+    with its text context the comparison needs no read of the text either;
     every combination gives the per-hit path's results on a genome with a repeat family (multi-row ranges) and reads with N"""
     import ctypes as C
     require_gpu()
@@ -333,10 +334,10 @@ def test_single_row_fold_and_located_table():
                                  scheme=aln.SimpleGotohScheme(2, -2, -5, -3))
     L_ = nb.lib()
     results = {}
-    for name, k, located in (("plain", 0, False), ("ktab", 8, False), ("located", 8, True), ("located5", 5, True)):
+    for name, k, located in (("plain", 0, 0), ("ktab", 8, 0), ("located", 8, 1), ("located5", 5, 1), ("context", 8, 2), ("context3", 3, 2)):
         fmi, _ = nb.FMIndexDevice.from_text(gw, n, sa_interval=1)
         if k:
-            fmi.build_ktab(k, located=located)
+            fmi.build_ktab(k, located=bool(located), text=gw if located == 2 else None)      # context3: 17 symbols left > the 16 of context
         fast = nb.seed_extend(fmi, gw, rs, params, hit_capacity=100 * n_reads)
         torch.cuda.synchronize()
         L_.nvb_debug_pipeline_path(C.c_int(1))
@@ -348,7 +349,7 @@ def test_single_row_fold_and_located_table():
         assert torch.equal(fast.n_hits[:2], slow.n_hits[:2]), name
         assert torch.equal(fast.best_score, slow.best_score) and torch.equal(fast.best_pos, slow.best_pos), name
         results[name] = (fast.best_score.clone(), fast.best_pos.clone(), fast.n_hits[:2].clone())
-    for name in ("ktab", "located", "located5"):
+    for name in ("ktab", "located", "located5", "context", "context3"):
         assert all(torch.equal(a, b) for a, b in zip(results[name], results["plain"])), name
     assert int((results["plain"][0] > 200).sum()) > n_reads // 2
 

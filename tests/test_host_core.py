@@ -390,6 +390,14 @@ def test_fm_match_locate_shortcut(H, O, n, k, bits):
             return o
         assert np.array_equal(norm(out16), norm(out))
         assert (out16[:, 0] == 2).sum() >= (out[:, 0] == 2).sum()
+        # ... and with the text context in one-row entries (ktab_located = 2): the same answers as the located table, field by field
+        # (seeds longer than k + 16 still compare against the text)
+        ktab_ctx = ktab16.copy()
+        H.hh_fm_ktab_context(_p(ktab_ctx), C.c_uint32(k), _p(gw))
+        out_ctx = np.zeros((nq, 3), np.uint32)
+        H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits),
+                             C.c_uint32(1), _p(offs), _p(lens), C.c_uint32(nq), _p(out_ctx), _p(ktab_ctx), C.c_uint32(k), C.c_uint32(2))
+        assert np.array_equal(out_ctx, out16)
     n_loc = 0
     for i in range(nq):
         x, y = int(want[i, 0]), int(want[i, 1])

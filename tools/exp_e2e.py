@@ -14,7 +14,7 @@ dev = torch.device("cuda", 0)
 genome = synth.random_genome_words(n, device=dev)
 fmi, _ = nb.FMIndexDevice.from_text(genome, n, sa_interval=1)
 torch.cuda.empty_cache()
-fmi.build_ktab(16 if n > 1e9 else 12, located=True)
+fmi.build_ktab(16 if n > 1e9 else 12, located=True, text=genome)
 params = nb.SeedExtendParams()
 batches = [synth.sample_reads(genome, n, n_reads, 150, sub_rate=0.01, indel_rate=0.001, device=dev, seed=5 + b, mut_seed=9 + b)[0].contiguous() for b in range(2)]
 wpr = batches[0].shape[1]

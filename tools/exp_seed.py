@@ -13,7 +13,7 @@ from nvbio_b200.pipeline import SeedExtendWorkspace, last_stage_ms
 ap = argparse.ArgumentParser()
 ap.add_argument("--genome-mbp", type=float, default=3000.0)
 ap.add_argument("--reads", type=int, default=1_000_000)
-ap.add_argument("--variants", nargs="*", default=["16:0", "16:1", "15:1", "15:0", "14:1", "16:1"], help="k:located")
+ap.add_argument("--variants", nargs="*", default=["16:0", "16:1", "15:1", "15:0", "14:1", "16:1"], help="k:located (located 0 = {x, y} entries, 1 = + SA values, 2 = + text context)")
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
 
@@ -31,7 +31,7 @@ for v in args.variants:
     k, located = (int(x) for x in v.split(":"))
     fmi.ktab = None; torch.cuda.empty_cache()
     if k:
-        fmi.build_ktab(k, located=bool(located))
+        fmi.build_ktab(k, located=bool(located), text=genome if located == 2 else None)
     ws = SeedExtendWorkspace(fmi, genome, rs, params, 24 * args.reads, keep_hits=False)
     for _ in range(3):
         flush.zero_(); nb.seed_extend(fmi, genome, rs, params, workspace=ws)
@@ -45,6 +45,6 @@ for v in args.variants:
     if ref is None:
         ref = chk
     assert chk == ref, "results differ between table formats"
-    print(json.dumps({"ktab_k": k, "located": bool(located), "table_GB": round((4 ** k) * (16 if located else 8) / 1e9, 1) if k else 0,
+    print(json.dumps({"ktab_k": k, "located": located, "table_GB": round((4 ** k) * (16 if located else 8) / 1e9, 1) if k else 0,
                       "stage_ms": {kk: round(vv / args.steps, 4) for kk, vv in acc.items()}}), flush=True)
     del ws
