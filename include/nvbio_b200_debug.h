@@ -27,6 +27,10 @@ void nvb_debug_pair_extra_smem(int bytes);
 /* seed + extend composition: 0 = automatic (the per-read path when no per-hit output is requested), 1 = always the per-hit path */
 void nvb_debug_pipeline_path(int path);
 
+/* seed-match stage of the per-read path with a k-mer table: 1 (default) = seeds on k-mers with three or more occurrences are finished
+   by a second kernel, 0 = one pass.  Same results; for A/B timing and tests */
+void nvb_debug_seed_split(int on);
+
 #ifdef __cplusplus
 }
 #endif

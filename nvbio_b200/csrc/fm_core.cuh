@@ -328,8 +328,13 @@ __host__ __device__ __forceinline__ uint32_t be4_window(const uint32_t* __restri
 // SA[x] - rem -- exactly what locate(match(p)) returns for a single-row result (the `$` row has SA = 0 and fails, as its LF step
 // does).  Returns FM_EMPTY, FM_RANGE (general inclusive range in (x, y); caller locates), or FM_LOCATED (single hit at text
 // position x).  Backward order only (flags == 0); symbols > 3 never match.
-enum { FM_EMPTY = 0, FM_RANGE = 1, FM_LOCATED = 2 };
-template <int BITS, bool BE>
+// MODE (the seed-match stage splits its seeds by how many dependent gathers they need, so that a warp does not wait on its slowest
+// lane): FM_WHOLE = everything in one call;  FM_DEFER = stop after the table look-up when the k-mer occurs three or more times (or
+// twice, with both occurrences spelling the whole query) and return FM_DEFERRED with the range reached so far in (ox, oy);
+// FM_RESUME = continue such a query: (ox, oy) hold that range on entry, the first ktab_k steps are taken as done ((0, n) = none).
+enum { FM_EMPTY = 0, FM_RANGE = 1, FM_LOCATED = 2, FM_DEFERRED = 3 };
+enum { FM_WHOLE = 0, FM_DEFER = 1, FM_RESUME = 2 };
+template <int BITS, bool BE, int MODE = FM_WHOLE>
 __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& f, const uint32_t* __restrict__ genome,
                                                                  const uint32_t* __restrict__ words, uint32_t off, uint32_t len,
                                                                  uint32_t& ox, uint32_t& oy)
@@ -337,7 +342,8 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
     SymReader<BITS, BE> rd(words);
     uint32_t x = 0, y = f.n, s = 0;
     uint32_t known_pos = 0u, known_pos2 = 0u; bool have_pos = false, have_two = false;
-    if (f.ktab_k && len >= f.ktab_k) {
+    if (MODE == FM_RESUME) { x = ox; y = oy; s = (x == 0u && y == f.n) ? 0u : f.ktab_k; }   // (0, n): deferred before any step (no look-up: an N, a short query)
+    if (MODE != FM_RESUME && f.ktab_k && len >= f.ktab_k) {
         uint32_t u = 0; bool has_n = false;
         if (BITS == 2 && BE) {
             // the table index IS the big-endian bit pattern of the last k symbols: one funnel shift instead of k symbol reads
@@ -396,6 +402,7 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
         if (!m0 && !m1) return FM_EMPTY;
         if (m0 != m1) { ox = (m0 ? known_pos : known_pos2) - rem; oy = 0xFFFFFFFFu; return FM_LOCATED; }
     }
+    if (MODE == FM_DEFER && s < len && x < y) { ox = x; oy = y; return FM_DEFERRED; }
     for (; s < len && x <= y; ++s) {
         if (full_sa && x == y) {
             const uint32_t rem = len - s;                 // symbols [0, rem) of the query are still to be consumed
@@ -418,6 +425,7 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
             ox = pos - rem; oy = 0xFFFFFFFFu;
             return FM_LOCATED;
         }
+        if (MODE == FM_DEFER) { ox = x; oy = y; return FM_DEFERRED; }     // (a single row without the full suffix array: walks on later)
         const uint32_t c = rd.get(off + len - 1u - s);
         if (c > 3u) return FM_EMPTY;
         fm_step(f, c, x, y);

@@ -121,26 +121,84 @@ pipe_make_strings_2bit_be_kernel(const StrSet reads, const PipeGeom g, uint32_t*
 // CTA size: seeds finish after 1 to 6 gathers, and a CTA's warp slots are only handed on when its last warp is done -- small CTAs
 // keep more of the 64 slots busy (measured, seed-match stage at C3: 512 threads 1.47 ms, 256 1.40, 128 1.35, 64 1.35)
 constexpr uint32_t SEED_BLOCK = 128;
-template <int BITS>
+constexpr uint32_t SEED_TODO_LISTS = 64;                     // todo lists (and counters) of the two-pass seed match
+constexpr uint32_t SEED_TODO_PITCH = 32;                     // words between two counters: one 128-byte line each
+constexpr uint32_t SEED_ITER = 8;                            // seeds per thread in its first pass
+// DEFER: a seed whose k-mer occurs three or more times needs ~6 dependent gathers where the others need 1 to 3, and a warp's slot is
+// held until its slowest lane is done -- such seeds are only looked up here (ranges[q] = the k-mer's range) and appended to `todo`;
+// pipe_seed_match_wide_kernel finishes them, all lanes of its warps equally deep
+template <int BITS, bool DEFER>
 __global__ void __launch_bounds__(SEED_BLOCK, 2048 / SEED_BLOCK)
 pipe_seed_match_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __restrict__ words, const uint32_t* __restrict__ slen,
-                       const uint32_t* __restrict__ genome, uint2* __restrict__ ranges, uint32_t* __restrict__ sizes)
+                       const uint32_t* __restrict__ genome, uint2* __restrict__ ranges, uint32_t* __restrict__ sizes,
+                       uint32_t* __restrict__ todo, uint32_t* __restrict__ todo_count)
 {
-    const uint32_t q = blockIdx.x * SEED_BLOCK + threadIdx.x;
-    if (q >= g.n_strings * g.seeds_per_string) return;
-    const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
-    const uint32_t len = slen[s];
-    const uint32_t pos = k * g.seed_interval;
-    uint32_t x = 1, y = 0;
-    if (pos + g.seed_len <= len) {
-        if (genome) {
-            if (fm_match_locate_one<BITS, true>(f, genome, words, s * g.stride + pos, g.seed_len, x, y) == FM_EMPTY) { x = 1; y = 0; }
-        } else
-            fm_match_one<BITS, true>(f, words, s * g.stride + pos, g.seed_len, 0u, x, y);
+    // DEFER: SEED_ITER consecutive chunks of seeds per CTA (its seeds are done after one or two gathers: fewer, longer-lived CTAs; on its
+    // own this measured no difference -- what bounded the first version of this pass was its atomics, see below)
+    constexpr uint32_t ITER = DEFER ? SEED_ITER : 1u;
+#pragma unroll 1
+    for (uint32_t it = 0; it < ITER; ++it) {
+        const uint32_t q = (blockIdx.x * ITER + it) * SEED_BLOCK + threadIdx.x;
+        const bool live = q < g.n_strings * g.seeds_per_string;
+        if (!DEFER && !live) return;
+        uint32_t x = 1, y = 0;
+        bool deferred = false;
+        if (live) {
+            const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
+            const uint32_t len = slen[s];
+            const uint32_t pos = k * g.seed_interval;
+            if (pos + g.seed_len <= len) {
+                if (genome) {
+                    const uint32_t st = fm_match_locate_one<BITS, true, DEFER ? FM_DEFER : FM_WHOLE>(f, genome, words, s * g.stride + pos, g.seed_len, x, y);
+                    if (st == FM_EMPTY) { x = 1; y = 0; }
+                    deferred = DEFER && st == FM_DEFERRED;
+                } else
+                    fm_match_one<BITS, true>(f, words, s * g.stride + pos, g.seed_len, 0u, x, y);
+            }
+            ranges[q] = make_uint2(x, y);
+            if (!deferred) {
+                const uint32_t sz = (y == 0xFFFFFFFFu) ? 1u : ((x <= y) ? (y - x + 1u) : 0u);
+                sizes[q] = sz < g.max_seed_hits ? sz : g.max_seed_hits;
+            }
+        }
+        if (DEFER) {
+            // one atomic per warp, spread over SEED_TODO_LISTS counters, each in its own 128-byte line.  Measured (C3, 0.9 M atomics per
+            // launch): one counter 2.1 ms for this kernel, 64 counters in adjacent words 1.5 ms, 64 counters one line apart 0.9 ms (= 0.93
+            // of the gather ceiling) -- same-line atomics serialise in the L2.  List c takes the CTAs with blockIdx % LISTS == c, so its
+            // capacity ceil(gridDim / LISTS) * SEED_BLOCK * SEED_ITER can never overflow
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, deferred);
+            if (m) {
+                const uint32_t lane = threadIdx.x & 31u, list = blockIdx.x % SEED_TODO_LISTS;
+                const uint32_t cap = ((gridDim.x + SEED_TODO_LISTS - 1u) / SEED_TODO_LISTS) * SEED_BLOCK * SEED_ITER;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(todo_count + list * SEED_TODO_PITCH, (uint32_t)__popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (deferred) todo[(size_t)list * cap + base + __popc(m & ((1u << lane) - 1u))] = q;
+            }
+        }
     }
-    ranges[q] = make_uint2(x, y);
-    const uint32_t sz = (y == 0xFFFFFFFFu) ? 1u : ((x <= y) ? (y - x + 1u) : 0u);
-    sizes[q] = sz < g.max_seed_hits ? sz : g.max_seed_hits;
+}
+// the deferred seeds: resume from the k-mer's range.  CTA b works on list b % LISTS (gridDim is a multiple of LISTS), striding over it:
+// the lists' lengths live on the device.  seed_grid = gridDim of the first pass (defines the lists' capacity)
+template <int BITS>
+__global__ void __launch_bounds__(SEED_BLOCK, 2048 / SEED_BLOCK)
+pipe_seed_match_wide_kernel(const FmIndex f, const PipeGeom g, const uint32_t* __restrict__ words,
+                            const uint32_t* __restrict__ genome, uint2* __restrict__ ranges, uint32_t* __restrict__ sizes,
+                            const uint32_t* __restrict__ todo, const uint32_t* __restrict__ todo_count, const uint32_t seed_grid)
+{
+    const uint32_t list = blockIdx.x % SEED_TODO_LISTS, per_list = gridDim.x / SEED_TODO_LISTS;
+    const uint32_t cap = ((seed_grid + SEED_TODO_LISTS - 1u) / SEED_TODO_LISTS) * SEED_BLOCK * SEED_ITER;
+    const uint32_t n = todo_count[list * SEED_TODO_PITCH];
+    for (uint32_t t = (blockIdx.x / SEED_TODO_LISTS) * SEED_BLOCK + threadIdx.x; t < n; t += per_list * SEED_BLOCK) {
+        const uint32_t q = todo[(size_t)list * cap + t];
+        const uint32_t s = q / g.seeds_per_string, k = q % g.seeds_per_string;
+        const uint2 r = ranges[q];
+        uint32_t x = r.x, y = r.y;
+        if (fm_match_locate_one<BITS, true, FM_RESUME>(f, genome, words, s * g.stride + k * g.seed_interval, g.seed_len, x, y) == FM_EMPTY) { x = 1; y = 0; }
+        ranges[q] = make_uint2(x, y);
+        const uint32_t sz = (y == 0xFFFFFFFFu) ? 1u : ((x <= y) ? (y - x + 1u) : 0u);
+        sizes[q] = sz < g.max_seed_hits ? sz : g.max_seed_hits;
+    }
 }
 
 __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t v)
@@ -604,6 +662,7 @@ extern "C" int nvb_seed_extend_stage_ms(float ms[7])
     return NVB_OK;
 }
 
+static int g_seed_split = 1;           // 0 = the located seed match in one pass (nvb_debug_seed_split)
 static int g_pipe_path = 0;            // 0 = automatic, 1 = always the per-hit path, 2 = per-read path without the in-kernel locate (nvb_debug_pipeline_path)
 
 static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
@@ -662,8 +721,9 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     uint8_t*  str_quals  = P->d_read_quals ? tc.take<uint8_t>((size_t)g.n_strings * g.stride + 16) : nullptr;
     uint2*    ranges     = tc.take<uint2>(nq);
     uint32_t* sizes      = tc.take<uint32_t>(nq);
-    uint32_t* excl       = tc.take<uint32_t>(nq);
+    uint32_t* excl       = tc.take<uint32_t>((size_t)nq + (SEED_TODO_LISTS + 1u) * SEED_BLOCK * SEED_ITER);   // (+ slack: before the scan it holds the seed-match todo lists)
     uint32_t* counts     = tc.take<uint32_t>(4);          // [0] hits kept, [1] hits found, [2] unique alignment jobs
+    uint32_t* seed_todo_n = tc.take<uint32_t>(SEED_TODO_LISTS * SEED_TODO_PITCH);
     const bool dedup = P->dedup_jobs != 0;
     // per-read path: nobody asked for per-hit outputs, so no per-hit array needs to exist
     const bool per_read = dedup && g_pipe_path != 1 && !d_hit_read && !d_hit_window && !d_hit_score && !d_hit_sink && !BA;
@@ -757,8 +817,22 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         const uint32_t grid = (nq + SEED_BLOCK - 1) / SEED_BLOCK;
         // per-read path + full suffix array: single-row ranges are located inside the match kernel (g_pipe_path 2 switches that off)
         const uint32_t* loc_genome = (per_read && f.sa_shift == 0u && g_pipe_path != 2) ? d_genome : nullptr;
-        if (g.bits == 2) pipe_seed_match_kernel<2><<<grid, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
-        else             pipe_seed_match_kernel<4><<<grid, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes);
+        // with a k-mer table the located path runs in two passes: seeds on k-mers with >= 3 occurrences are finished by a second kernel
+        // (the lists live in `excl`, which the scan below overwrites)
+        const bool split = loc_genome && f.ktab_k && g.seed_len > f.ktab_k && g_seed_split;
+        if (split) {
+            NVB_CUDA_TRY(cudaMemsetAsync(seed_todo_n, 0, SEED_TODO_LISTS * SEED_TODO_PITCH * sizeof(uint32_t), s));
+            const uint32_t grid1 = (grid + SEED_ITER - 1u) / SEED_ITER;
+            if (g.bits == 2) pipe_seed_match_kernel<2, true><<<grid1, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes, excl, seed_todo_n);
+            else             pipe_seed_match_kernel<4, true><<<grid1, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes, excl, seed_todo_n);
+            NVB_LAUNCH_CHECK();
+            const uint32_t wgrid = SEED_TODO_LISTS * 37u;                                  // 2368 CTAs = 148 SMs x 16 resident CTAs
+            if (g.bits == 2) pipe_seed_match_wide_kernel<2><<<wgrid, SEED_BLOCK, 0, s>>>(f, g, str_words, loc_genome, ranges, sizes, excl, seed_todo_n, grid1);
+            else             pipe_seed_match_wide_kernel<4><<<wgrid, SEED_BLOCK, 0, s>>>(f, g, str_words, loc_genome, ranges, sizes, excl, seed_todo_n, grid1);
+        } else {
+            if (g.bits == 2) pipe_seed_match_kernel<2, false><<<grid, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes, nullptr, nullptr);
+            else             pipe_seed_match_kernel<4, false><<<grid, SEED_BLOCK, 0, s>>>(f, g, str_words, str_len_, loc_genome, ranges, sizes, nullptr, nullptr);
+        }
         NVB_LAUNCH_CHECK();
     }
     NVB_STAGE(2);
@@ -901,6 +975,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
 }
 
 extern "C" void nvb_debug_pipeline_path(int path) { g_pipe_path = path; }
+extern "C" void nvb_debug_seed_split(int on) { g_seed_split = on; }
 
 extern "C" int nvb_seed_extend(const nvb_fm_index* fmi, const uint32_t* d_genome,
                     const nvb_string_set* reads, uint32_t n_reads,

@@ -101,6 +101,27 @@ void hh_fm_match_locate(const uint32_t* bwt_occ, const uint32_t* full_sa, const 
     }
 }
 
+// the same through the two-pass form the seed-match stage uses: FM_DEFER first, FM_RESUME for the seeds it hands back; returns their number
+uint32_t hh_fm_match_locate_split(const uint32_t* bwt_occ, const uint32_t* full_sa, const uint32_t* L2, uint32_t n, uint32_t primary,
+                                  const uint32_t* genome, const uint32_t* words, uint32_t bits, const uint32_t* off, const uint32_t* len,
+                                  uint32_t nq, uint32_t* out, const uint32_t* ktab, uint32_t ktab_k, uint32_t ktab_located) {
+    const FmIndex f = mk(bwt_occ, full_sa, L2, n, primary, 1, ktab, ktab_k, ktab_located);
+    uint32_t deferred = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        uint32_t x = 0, y = 0, st = 0;
+        if (bits == 2) st = fm_match_locate_one<2, true, FM_DEFER>(f, genome, words, off[i], len[i], x, y);
+        else           st = fm_match_locate_one<4, true, FM_DEFER>(f, genome, words, off[i], len[i], x, y);
+        if (st == FM_DEFERRED) {
+            ++deferred;
+            if (bits == 2) st = fm_match_locate_one<2, true, FM_RESUME>(f, genome, words, off[i], len[i], x, y);
+            else           st = fm_match_locate_one<4, true, FM_RESUME>(f, genome, words, off[i], len[i], x, y);
+            if (st == FM_EMPTY) x = y = 0;                  // (x, y) are only defined for the other two states
+        }
+        out[3 * i] = st; out[3 * i + 1] = x; out[3 * i + 2] = y;
+    }
+    return deferred;
+}
+
 // generic rank dictionary (dict_rank<W,I>): out[q] = rank(i[q], c[q]), all as uint64
 void hh_dict_rank(const void* text, uint32_t word_bits, const void* occ, uint32_t K, const uint64_t* qi, const uint8_t* qc, uint32_t nq, uint64_t* out) {
     for (uint32_t q = 0; q < nq; ++q) {

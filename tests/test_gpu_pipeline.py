@@ -348,6 +348,15 @@ def test_single_row_fold_and_located_table():
             L_.nvb_debug_pipeline_path(C.c_int(0))
         assert torch.equal(fast.n_hits[:2], slow.n_hits[:2]), name
         assert torch.equal(fast.best_score, slow.best_score) and torch.equal(fast.best_pos, slow.best_pos), name
+        if k:
+            # the seed-match stage in one pass instead of two (seeds on repeated k-mers finished by a second kernel): same results
+            L_.nvb_debug_seed_split(C.c_int(0))
+            try:
+                one = nb.seed_extend(fmi, gw, rs, params, hit_capacity=100 * n_reads)
+                torch.cuda.synchronize()
+            finally:
+                L_.nvb_debug_seed_split(C.c_int(1))
+            assert torch.equal(fast.n_hits[:2], one.n_hits[:2]) and torch.equal(fast.best_score, one.best_score) and torch.equal(fast.best_pos, one.best_pos), name
         results[name] = (fast.best_score.clone(), fast.best_pos.clone(), fast.n_hits[:2].clone())
     for name in ("ktab", "located", "located5", "context", "context3"):
         assert all(torch.equal(a, b) for a, b in zip(results[name], results["plain"])), name

@@ -398,6 +398,18 @@ def test_fm_match_locate_shortcut(H, O, n, k, bits):
         H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits),
                              C.c_uint32(1), _p(offs), _p(lens), C.c_uint32(nq), _p(out_ctx), _p(ktab_ctx), C.c_uint32(k), C.c_uint32(2))
         assert np.array_equal(out_ctx, out16)
+    # the two-pass form of the seed-match stage (FM_DEFER, then FM_RESUME for what it hands back) == the single call, for every table
+    # format (without a table every multi-row query is handed back at step 0)
+    tabs = [(None, 0, 0)] if not k else [(ktab, k, 0), (ktab16, k, 1), (ktab_ctx, k, 2)]
+    for tab, kk, loc in tabs:
+        whole, split = np.zeros((nq, 3), np.uint32), np.zeros((nq, 3), np.uint32)
+        H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits),
+                             C.c_uint32(1), _p(offs), _p(lens), C.c_uint32(nq), _p(whole), _p(tab), C.c_uint32(kk), C.c_uint32(loc))
+        H.hh_fm_match_locate_split.restype = C.c_uint32
+        nd = H.hh_fm_match_locate_split(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words),
+                                        C.c_uint32(bits), _p(offs), _p(lens), C.c_uint32(nq), _p(split), _p(tab), C.c_uint32(kk), C.c_uint32(loc))
+        assert np.array_equal(split, whole), (kk, loc)
+        assert 0 < nd <= nq and (nd < nq or not kk)
     n_loc = 0
     for i in range(nq):
         x, y = int(want[i, 0]), int(want[i, 1])
