@@ -31,6 +31,11 @@ void nvb_debug_pipeline_path(int path);
    by a second kernel, 0 = one pass.  Same results; for A/B timing and tests */
 void nvb_debug_seed_split(int on);
 
+/* extension stage of the per-read path (LOCAL, constant scheme, 2-bit reads): 1 (default) = a read that equals its window on a band
+   diagonal gets score = match * len and its sink without running the DP (exact: nothing can score more), 0 = every job through the
+   DP kernels.  Same results; for A/B timing and tests */
+void nvb_debug_perfect_shortcut(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -363,6 +363,59 @@ def test_single_row_fold_and_located_table():
     assert int((results["plain"][0] > 200).sum()) > n_reads // 2
 
 
+@pytest.mark.parametrize("sub_rate", [0.0, 0.004, 0.02])
+def test_perfect_match_shortcut(sub_rate):
+    """a read that equals its window on a band diagonal gets score = match * len and the sink of the LARGEST such diagonal without running
+    the DP (pipe_perfect_jobs_kernel): same best score / position per read and the same counts as with every job through the
+    DP kernels, and as the per-hit path -- on a genome with a period-7 tandem repeat (several perfect diagonals inside one band), a
+    period-300 repeat family, reads at the genome's ends (clamped and truncated windows) and ragged read lengths"""
+    import ctypes as C
+    require_gpu()
+    n = 200_000
+    gw = synth.random_genome_words(n, seed=123)
+    gsym = unpack_symbols(host_u32(gw), n).copy()
+    gsym[50_000:70_000] = np.tile(gsym[1000:1007], 20_000 // 7 + 1)[:20_000]
+    gsym[120_000:150_000] = np.tile(gsym[2000:2300], 100)
+    gw = torch.from_numpy(pack_symbols(np.concatenate([gsym, np.zeros(128, np.uint8)]), 2, True).view(np.int32)).cuda()
+    n_reads, L = 6000, 150
+    rw, pos, strand = synth.sample_reads(gw, n, n_reads, L, sub_rate=sub_rate, indel_rate=0.0005 if sub_rate else 0.0, seed=31, mut_seed=32)
+    sym = np.stack([unpack_symbols(host_u32(rw[i]), L) for i in range(n_reads)])
+    # reads hanging on the genome's two ends
+    for i, st in enumerate((0, 3, 9, n - L, n - L - 2, n - L - 20)):
+        sym[i] = gsym[st:st + L]
+    lens = np.full(n_reads, L, np.uint32); lens[10:400] = np.random.default_rng(4).integers(60, L + 1, 390)
+    stride = ((L + 15) // 16) * 16
+    buf = np.zeros((n_reads, stride), np.uint8); buf[:, :L] = sym
+    words = torch.from_numpy(pack_symbols(buf.reshape(-1), 2, True).view(np.int32)).cuda()
+    rs = PackedStringSet(words=words, bits=2, big_endian=True, offsets=torch.arange(n_reads, dtype=torch.int32, device="cuda") * stride,
+                         lengths=torch.from_numpy(lens.view(np.int32)).cuda(), stride=0, length=L, count=n_reads)
+    fmi, _ = nb.FMIndexDevice.from_text(gw, n, sa_interval=1)
+    fmi.build_ktab(8, located=True, text=gw)
+    L_ = nb.lib()
+    for scheme in (aln.SimpleGotohScheme(2, -2, -5, -3), aln.SimpleGotohScheme(1, -4, -6, -1)):
+        params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=aln.LOCAL, both_strands=True, max_seed_hits=30, scheme=scheme)
+        fast = nb.seed_extend(fmi, gw, rs, params, hit_capacity=200 * n_reads)
+        torch.cuda.synchronize()
+        L_.nvb_debug_perfect_shortcut(C.c_int(0))
+        try:
+            full = nb.seed_extend(fmi, gw, rs, params, hit_capacity=200 * n_reads)
+            torch.cuda.synchronize()
+        finally:
+            L_.nvb_debug_perfect_shortcut(C.c_int(1))
+        L_.nvb_debug_pipeline_path(C.c_int(1))
+        try:
+            slow = nb.seed_extend(fmi, gw, rs, params, hit_capacity=200 * n_reads)
+            torch.cuda.synchronize()
+        finally:
+            L_.nvb_debug_pipeline_path(C.c_int(0))
+        for other in (full, slow):
+            assert torch.equal(fast.best_score, other.best_score) and torch.equal(fast.best_pos, other.best_pos)
+            assert torch.equal(fast.n_hits[:2], other.n_hits[:2])
+        assert torch.equal(fast.n_hits, full.n_hits)
+        if sub_rate == 0.0:
+            assert int((fast.best_score == scheme.match * torch.from_numpy(lens.astype(np.int32)).cuda()).sum()) > 0.95 * n_reads
+
+
 @pytest.mark.parametrize("bits,ragged,cap_div", [(2, False, 0), (4, True, 0), (2, False, 3)])
 def test_per_read_path_equals_per_hit_path(bits, ragged, cap_div):
     """the per-read path of nvb_seed_extend (taken when no per-hit output is requested: distinct jobs straight from a thread per

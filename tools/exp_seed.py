@@ -13,7 +13,8 @@ from nvbio_b200.pipeline import SeedExtendWorkspace, last_stage_ms
 ap = argparse.ArgumentParser()
 ap.add_argument("--genome-mbp", type=float, default=3000.0)
 ap.add_argument("--reads", type=int, default=1_000_000)
-ap.add_argument("--variants", nargs="*", default=["16:0", "16:1", "15:1", "15:0", "14:1", "16:1"], help="k:located[:split] (located 0 = {x, y} entries, 1 = + SA values, 2 = + text context; split 0 = seed match in one pass)")
+ap.add_argument("--variants", nargs="*", default=["16:0", "16:1", "15:1", "15:0", "14:1", "16:1"], help="k:located[:split[:perfect]] (located 0 = {x, y} entries, 1 = + SA values, 2 = + text context; split 0 = seed match in one pass; "
+                "perfect 0 = every alignment job through the DP kernels)")
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
 
@@ -28,8 +29,8 @@ params = nb.SeedExtendParams(seed_len=20, seed_interval=10, band_len=31, type=al
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 ref = None
 for v in args.variants:
-    k, located, split = (tuple(int(x) for x in v.split(":")) + (1,))[:3]
-    nb.lib().nvb_debug_seed_split(ctypes.c_int(split))
+    k, located, split, perfect = (tuple(int(x) for x in v.split(":")) + (1, 1))[:4]
+    nb.lib().nvb_debug_seed_split(ctypes.c_int(split)); nb.lib().nvb_debug_perfect_shortcut(ctypes.c_int(perfect))
     fmi.ktab = None; torch.cuda.empty_cache()
     if k:
         fmi.build_ktab(k, located=bool(located), text=genome if located == 2 else None)
@@ -46,6 +47,6 @@ for v in args.variants:
     if ref is None:
         ref = chk
     assert chk == ref, "results differ between table formats"
-    print(json.dumps({"ktab_k": k, "located": located, "split": split, "table_GB": round((4 ** k) * (16 if located else 8) / 1e9, 1) if k else 0,
+    print(json.dumps({"ktab_k": k, "located": located, "split": split, "perfect": perfect, "table_GB": round((4 ** k) * (16 if located else 8) / 1e9, 1) if k else 0,
                       "stage_ms": {kk: round(vv / args.steps, 4) for kk, vv in acc.items()}}), flush=True)
     del ws
