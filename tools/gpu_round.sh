@@ -10,7 +10,7 @@ echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 ( timeout 900 python tools/bench_full.py ) > gpurun_out/bench_full.log 2>&1
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs --pairs 0"
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'nvb::|cub::' -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:pipe_seed_match -s 3 -c 1 -f -o gpurun_out/prof_seed_match_$TAG $B > gpurun_out/ncu_seed.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:pipe_seed_match -s 2 -c 2 -f -o gpurun_out/prof_seed_match_$TAG $B > gpurun_out/ncu_seed.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:gotoh_pair_kernel -s 3 -c 1 -f -o gpurun_out/prof_gotoh_pair_$TAG $B > gpurun_out/ncu_gotoh.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log | head -2
 grep -o '"value": [0-9.]*' gpurun_out/bench_default.log | head -2; grep -o '"stage_ms": {[^}]*}' gpurun_out/bench_default.log
