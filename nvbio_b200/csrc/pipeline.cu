@@ -325,16 +325,22 @@ pipe_read_jobs_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict
     }
 }
 
-// Exact shortcut of the LOCAL extension for reads that match their window without a single difference (most reads of a real run):
-// with match > 0 >= every gap penalty and mismatch <= match no alignment can score more than match * M, and only an all-match diagonal
-// over the whole read reaches it -- so if the read equals the text on band diagonal jj, the banded DP's result is score = match * M at
-// the sink (M + jj, M), where jj is the LARGEST such diagonal (BestSink keeps the last maximal cell in row-major order, sink_inl.h:39-65;
-// a score of match * M only exists in the last row).  Such jobs get their result here; the others are compacted into the list the DP
-// kernels run over.  Only full windows (N >= M + band - 1: no pad symbol inside the band) and 2-bit reads qualify.  (A first version
-// that tried all band diagonals for every job cost 0.39 ms per million reads -- 2,250 warp instructions per job -- against the 0.16 ms
-// of DP it saved at 1 % substitutions; now a job that differs on the seed's own diagonal leaves after one or two word compares.)
+// Exact shortcut of the LOCAL extension for reads that lie on their seed's diagonal with (almost) no difference -- most reads of a
+// real run.  With match > 0 > mismatch, gap-open penalties < 0 and gap-extension penalties <= 0:
+//   * an alignment that contains a gap scores at most  G = match * M + max(pattern_gap_open, text_gap_open)  (at most M matched
+//     columns, and a gap costs at least its first base);
+//   * an alignment without a gap lies on ONE band diagonal, and the best of those is the maximum-sum segment of that diagonal's
+//     match / mismatch scores (H along the diagonal with only the diagonal move: h = max(0, h + s)).
+// So if the best segment of the seed's own diagonal scores MORE than G, and no other band diagonal can reach it (match * its number
+// of equal positions stays below), that score is the band's maximum and every cell holding it lies on this diagonal: the DP's result
+// is (best, last row where h == best) -- BestSink keeps the last maximal cell in row-major order (sink_inl.h:39-65).  A read without
+// any difference (score match * M, only reachable in the last row) may tie with other equal diagonals (tandem repeats): the largest
+// one wins.  Such jobs get their result here; the others are compacted into the list the DP kernels run over.  Only full windows
+// (N >= M + band - 1: no pad symbol inside the band) and 2-bit reads qualify.  (A first version that tried all band diagonals for
+// every job cost 0.39 ms per million reads -- 2,250 warp instructions per job -- against the 0.16 ms of DP it saved; now a job that
+// differs too much on the seed's own diagonal leaves after one or two word compares.)
 __global__ void __launch_bounds__(256)
-pipe_perfect_jobs_kernel(const PipeGeom g, const int32_t match, const uint32_t* __restrict__ counts,
+pipe_perfect_jobs_kernel(const PipeGeom g, const int32_t match, const int32_t mismatch, const int32_t max_gap_open, const uint32_t* __restrict__ counts,
                          const uint32_t* __restrict__ str_words, const uint32_t* __restrict__ genome,
                          const uint32_t* __restrict__ jp_off, const uint32_t* __restrict__ jp_len,
                          const uint32_t* __restrict__ jt_off, const uint32_t* __restrict__ jt_len,
@@ -344,15 +350,19 @@ pipe_perfect_jobs_kernel(const PipeGeom g, const int32_t match, const uint32_t* 
 {
     __shared__ uint32_t s_warp[8], s_base;
     const uint32_t n = counts[2];
-    // does the read equal the text on band diagonal jj?
-    auto equal_on = [&](const uint32_t po, const uint32_t M, const uint32_t t) -> bool {
-        bool same = true;
-        for (uint32_t i = 0; i < M && same; i += 16u) {
-            const uint32_t cnt = M - i < 16u ? M - i : 16u;
-            same = ((be2_window(str_words, po + i, cnt) ^ be2_window(genome, t + i, cnt)) >> (32u - 2u * cnt)) == 0u;
-        }
-        return same;
+    // one bit per differing symbol (bit 2k = symbol cnt-1-k) of read[i, i+cnt) against text[t+i, ...)
+    auto diff_bits = [&](const uint32_t po, const uint32_t t, const uint32_t i, const uint32_t cnt) -> uint32_t {
+        const uint32_t x = (be2_window(str_words, po + i, cnt) ^ be2_window(genome, t + i, cnt)) >> (32u - 2u * cnt);
+        return (x | (x >> 1)) & 0x55555555u;
     };
+    // number of differing symbols on the diagonal starting at text position t, counting stops once it exceeds `limit`
+    auto differences = [&](const uint32_t po, const uint32_t M, const uint32_t t, const uint32_t limit) -> uint32_t {
+        uint32_t mm = 0;
+        for (uint32_t i = 0; i < M && mm <= limit; i += 16u) mm += (uint32_t)__popc(diff_bits(po, t, i, M - i < 16u ? M - i : 16u));
+        return mm;
+    };
+    // differences a gapless alignment may have and still beat every gapped one: match * (M - mm) > match * M + max_gap_open
+    const uint32_t mm_max = (uint32_t)((-max_gap_open + match - 1) / match) - 1u;
     for (uint32_t base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {       // (whole CTAs stay in the loop: barriers below)
         const uint32_t j = base + threadIdx.x;
         bool todo = false;
@@ -360,14 +370,59 @@ pipe_perfect_jobs_kernel(const PipeGeom g, const int32_t match, const uint32_t* 
         if (j < n) {
             po = jp_off[j]; M = jp_len[j]; to = jt_off[j]; N = jt_len[j];
             todo = true;
-            // the window was cut band/2 before the seed's diagonal (pipe_read_jobs_kernel), so that is where a read without differences
-            // lies; a window clamped at the text start (to == 0) has it somewhere below: those few take the DP
+            // the window was cut band/2 before the seed's diagonal (pipe_read_jobs_kernel), so that is where such a read lies; a window
+            // clamped at the text start (to == 0) has it somewhere below: those few take the DP
             const uint32_t j0 = g.band / 2u;
-            if (M >= 1u && to != 0u && N >= M + g.band - 1u && equal_on(po, M, to + j0)) {
-                uint32_t jj = g.band - 1u;                                         // the LAST maximal cell wins: largest equal diagonal
-                while (jj > j0 && !equal_on(po, M, to + jj)) --jj;
-                job_score[j] = match * (int32_t)M; job_sink[j] = make_uint2(M + jj, M);
-                todo = false;
+            if (M >= 1u && to != 0u && N >= M + g.band - 1u) {
+                // one pass over the seed's diagonal: its differences (at most mm_max, else the DP) and, from the runs of equal symbols
+                // between them, the maximum-sum segment with the LAST end among equals.  (mismatch < 0, so h peaks at the ends of runs;
+                // a symbol-by-symbol version of this loop cost 1,500 warp instructions per job)
+                int32_t h = 0, best = 0; uint32_t end = 0, prev = 0, mm0 = 0;
+                for (uint32_t i = 0; i < M && mm0 <= mm_max; i += 16u) {
+                    const uint32_t cnt = M - i < 16u ? M - i : 16u;
+                    uint32_t d = diff_bits(po, to + j0, i, cnt);
+                    while (d && mm0 <= mm_max) {
+                        const uint32_t bit = 31u - (uint32_t)__clz(d);                 // highest set bit = first differing symbol of the word
+                        const uint32_t p = i + (cnt - 1u - (bit >> 1));
+                        d &= ~(1u << bit);
+                        h += match * (int32_t)(p - prev);
+                        if (h >= best) { best = h; end = p; }
+                        h += mismatch; h = h > 0 ? h : 0;
+                        prev = p + 1u; ++mm0;
+                    }
+                }
+                if (mm0 <= mm_max) {
+                    h += match * (int32_t)(M - prev);
+                    if (h >= best) { best = h; end = M; }
+                }
+                if (mm0 <= mm_max && best > match * (int32_t)M + max_gap_open) {
+                    // Can another band diagonal reach `best`?  Only with at most t differences (match * equal positions bounds its score).
+                    // The first 16 symbols decide that for nearly every diagonal: they are compared against all band offsets from four
+                    // text words held in registers (a full comparison only follows for a diagonal they do not rule out).
+                    const bool perfect = (mm0 == 0u);
+                    const uint32_t t = (uint32_t)((match * (int32_t)M - best) / match);
+                    const uint32_t c16 = M < 16u ? M : 16u;
+                    const uint32_t r0 = be2_window(str_words, po, c16) >> (32u - 2u * c16);
+                    const uint32_t wi = to >> 4, r = to & 15u, wl = (to + N - 1u) >> 4;          // wl: last word holding a window symbol
+                    const uint32_t g0 = genome[wi], g1 = (wi + 1u <= wl) ? genome[wi + 1u] : 0u;
+                    const uint32_t g2 = (wi + 2u <= wl) ? genome[wi + 2u] : 0u, g3 = (wi + 3u <= wl) ? genome[wi + 3u] : 0u;
+                    bool alone = true;
+                    uint32_t jtop = j0;                                                         // largest diagonal without a difference
+                    for (uint32_t jj = 0; jj < g.band; ++jj) {
+                        if (jj == j0) continue;
+                        const uint32_t off = r + jj, idx = off >> 4, sh = 2u * (off & 15u);      // band <= 32: idx <= 2
+                        const uint32_t hi = idx == 0u ? g0 : (idx == 1u ? g1 : g2), lo = idx == 0u ? g1 : (idx == 1u ? g2 : g3);
+                        const uint32_t win = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+                        const uint32_t x = (win >> (32u - 2u * c16)) ^ r0;
+                        if ((uint32_t)__popc((x | (x >> 1)) & 0x55555555u) > t) continue;
+                        const uint32_t full = differences(po, M, to + jj, t);
+                        if (full > t) continue;
+                        if (perfect) { if (jj > jtop) jtop = jj; }                              // (full == 0: another diagonal without a difference)
+                        else alone = false;
+                    }
+                    if (perfect)    { job_score[j] = best; job_sink[j] = make_uint2(M + jtop, M); todo = false; }
+                    else if (alone) { job_score[j] = best; job_sink[j] = make_uint2(end + j0, end); todo = false; }
+                }
             }
         }
         // compaction of the others: one atomic per CTA (same-address atomics serialise, ~2.4 ns each on this part)
@@ -815,8 +870,8 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
     uint2*    job_sink  = dedup ? tc.take<uint2>(hit_capacity) : nullptr;
     // exact shortcut for reads that equal their window (pipe_perfect_jobs_kernel): the DP then runs over a compacted job list
     const nvb_gotoh_scheme& SC = P->scheme;
-    const bool eligible = per_read && P->type == NVB_LOCAL && g.bits == 2 && !SC.d_qual_table && SC.match > 0 && SC.mismatch <= SC.match &&
-                          SC.pattern_gap_open <= 0 && SC.pattern_gap_ext <= 0 && SC.text_gap_open <= 0 && SC.text_gap_ext <= 0;
+    const bool eligible = per_read && P->type == NVB_LOCAL && g.bits == 2 && P->band_len <= 32 && !SC.d_qual_table && SC.match > 0 && SC.mismatch < 0 &&
+                          SC.pattern_gap_open < 0 && SC.pattern_gap_ext <= 0 && SC.text_gap_open < 0 && SC.text_gap_ext <= 0;
     const bool shortcut = eligible && g_perfect_shortcut;              // (the debug switch does not change the temp layout)
     uint32_t* dp_p_off = eligible ? tc.take<uint32_t>(hit_capacity) : nullptr;
     uint32_t* dp_p_len = eligible ? tc.take<uint32_t>(hit_capacity) : nullptr;
@@ -945,7 +1000,7 @@ static int seed_extend_impl(const nvb_fm_index* fmi, const uint32_t* d_genome,
         if (hit_capacity && shortcut) {
             const uint32_t jgrid = hgrid < 148u * 8u ? hgrid : 148u * 8u;
             NVB_CUDA_TRY(cudaMemsetAsync(dp_count, 0, sizeof(uint32_t), s));
-            pipe_perfect_jobs_kernel<<<jgrid, 256, 0, s>>>(g, SC.match, counts, str_words, d_genome, jp_off, jp_len, jt_off, jt_len, job_score, job_sink,
+            pipe_perfect_jobs_kernel<<<jgrid, 256, 0, s>>>(g, SC.match, SC.mismatch, SC.pattern_gap_open > SC.text_gap_open ? SC.pattern_gap_open : SC.text_gap_open, counts, str_words, d_genome, jp_off, jp_len, jt_off, jt_len, job_score, job_sink,
                                                            dp_p_off, dp_p_len, dp_t_off, dp_t_len, dp_job, dp_count);
             NVB_LAUNCH_CHECK();
             size_t gb = gotoh_bytes;

@@ -384,6 +384,19 @@ def test_perfect_match_shortcut(sub_rate):
     for i, st in enumerate((0, 3, 9, n - L, n - L - 2, n - L - 20)):
         sym[i] = gsym[st:st + L]
     lens = np.full(n_reads, L, np.uint32); lens[10:400] = np.random.default_rng(4).integers(60, L + 1, 390)
+    # reads with one, two or three substitutions at chosen places (the ends, next to the ends, adjacent, spread out): the few-difference
+    # branch of the shortcut (maximum-sum segment of the diagonal, last end among equals) incl. its boundary cases; some of them inside
+    # the period-7 repeat, where other diagonals are as good and the DP has to decide
+    places = [(0,), (1,), (L - 1,), (L - 2,), (0, 1), (L - 2, L - 1), (0, L - 1), (1, L - 2), (2, 3), (74,), (74, 75), (10, 140), (0, 1, 2),
+              (L - 3, L - 2, L - 1), (3, 70), (5,), (L - 6,), (2,), (L - 3,), (37, 111)]
+    rng_c = np.random.default_rng(17)
+    for k, pl in enumerate(places * 3):
+        i = 400 + k
+        st = int(rng_c.integers(52_000, 68_000)) if k % 3 == 2 else int(rng_c.integers(80_000, 110_000))
+        sym[i] = gsym[st:st + L]
+        for q in pl:
+            sym[i, q] = (sym[i, q] + 1 + (k % 3)) % 4
+        lens[i] = L
     stride = ((L + 15) // 16) * 16
     buf = np.zeros((n_reads, stride), np.uint8); buf[:, :L] = sym
     words = torch.from_numpy(pack_symbols(buf.reshape(-1), 2, True).view(np.int32)).cuda()
