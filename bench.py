@@ -800,8 +800,11 @@ def run_ours(args):
                              "reference_algorithm_bytes_per_seed" % args.ktab_k},
         "stage_ms": stage_ms,
         "fm_match_Mseeds_s": n_seeds / (fm_ms * 1e-3) / 1e6,
-        "banded_gotoh": {"alignments_per_step": hits, "distinct_jobs_scored": jobs, "GCUPS": cells / (stage_ms["extend"] * 1e-3) / 1e9,
-                         "band": BAND, "note": "cells = distinct jobs x 150 x 31; integer-issue bound (DPX s16x2), not HBM"},
+        "banded_gotoh": {"alignments_per_step": hits, "distinct_jobs_scored": jobs, "effective_GCUPS": cells / (stage_ms["extend"] * 1e-3) / 1e9,
+                         "band": BAND, "note": "cells = distinct jobs x 150 x 31 over the extension stage's time.  EFFECTIVE rate: jobs whose read lies on the "
+                                               "seed's diagonal with 0-1 substitutions get their (bit-identical) result from the exact shortcut without "
+                                               "running the DP (DESIGN.md 3.7; 42 % of the jobs at this error rate); the DP kernel's own rate is "
+                                               "other_configs' C4 line (integer-issue bound, DPX s16x2)"},
         "reads_found_frac": found,
         "index_build": {"build_s": t_build, "broadcast_s": t_bcast},
     }
