@@ -89,9 +89,13 @@ __global__ void __launch_bounds__(256)
 pipe_make_strings_2bit_be_kernel(const StrSet reads, const PipeGeom g, uint32_t* __restrict__ out_words, uint32_t* __restrict__ out_len)
 {
     const uint32_t words_per_string = g.stride / 16u;
-    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= (uint64_t)g.n_strings * words_per_string) return;
-    const uint32_t s = (uint32_t)(t / words_per_string), w = (uint32_t)(t % words_per_string);
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x, total = (uint64_t)g.n_strings * words_per_string;
+    if (t >= total) return;
+    // 32-bit index arithmetic whenever the word count allows it (measured: no difference -- the stage's 0.10 ms per million reads are the
+    // first touch of the input after the L2 flush between steps and the write-back of that flush, not this kernel's instructions)
+    uint32_t s, w;
+    if (total <= 0xFFFFFFFFull) { s = (uint32_t)t / words_per_string; w = (uint32_t)t - s * words_per_string; }
+    else                        { s = (uint32_t)(t / words_per_string); w = (uint32_t)(t % words_per_string); }
     const uint32_t read = s / g.strands, strand = s % g.strands;
     const uint32_t off = str_off(reads, read), len = str_len(reads, read);
     if (w == 0) out_len[s] = len;
