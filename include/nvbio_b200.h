@@ -67,7 +67,10 @@ typedef struct nvb_fm_index {
                                     k-mer occurs once or twice is located by the look-up + a text comparison, without walking the
                                     range on;  2: the same table built by nvb_fm_build_ktab_context -- the last word of a ONE-row
                                     entry (y == x) holds the 16 text symbols before SA[x] instead, so that such a seed (up to k + 16
-                                    symbols long) is resolved by the look-up alone.  Ranges are identical in every case.  */
+                                    symbols long) is resolved by the look-up alone; and, when length < 0xC0000000, a TWO-row entry is
+                                    stored as {x, 0xC0000000 | a | b << 14, SA[x], SA[x+1]} (y = x + 1 implied; a, b = the 7 symbols before
+                                    SA[x], SA[x+1]), which resolves seeds up to k + 7 symbols the same way.  Ranges are identical in
+                                    every case.  */
 } nvb_fm_index;
 
 /* A set of strings stored in one packed symbol stream (nvbio PackedStream semantics,
@@ -363,8 +366,8 @@ int nvb_fm_build_ktab(const nvb_fm_index* fmi, uint32_t k, nvb_uint2* d_ktab, vo
 int nvb_fm_build_ktab_located(const nvb_fm_index* fmi, uint32_t k, void* d_ktab16, void* stream);
 
 /* nvb_fm_build_ktab_located + text context: for every one-row entry the unused last word is filled with the (up to) 16 symbols of
- * d_text (2-bit big-endian, the text the index was built from) that precede SA[x], symbol SA[x]-1 in the two lowest bits.
- * Use with nvb_fm_index.d_ktab = d_ktab16, ktab_located = 2. */
+ * d_text (2-bit big-endian, the text the index was built from) that precede SA[x], symbol SA[x]-1 in the two lowest bits; two-row
+ * entries are packed as described at nvb_fm_index.ktab_located.  Use with nvb_fm_index.d_ktab = d_ktab16, ktab_located = 2. */
 int nvb_fm_build_ktab_context(const nvb_fm_index* fmi, uint32_t k, const uint32_t* d_text, void* d_ktab16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

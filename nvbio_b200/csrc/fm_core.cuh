@@ -252,6 +252,14 @@ __host__ __device__ __forceinline__ uint32_t be2_window(const uint32_t* __restri
     return (w0 << (2u * r)) | (w1 >> (32u - 2u * r));
 }
 
+// Context tables (ktab_located == 2) of an index with fewer than 0xC0000000 rows pack a TWO-row entry {x, x + 1, SA[x], SA[x + 1]} as
+// {x, 0xC0000000 | ctxA | ctxB << 14, SA[x], SA[x + 1]}: y = x + 1 is implied (no valid row index reaches 0xC0000000) and the freed
+// bits hold the 7 text symbols before SA[x] (ctxA) and before SA[x + 1] (ctxB), last symbol in the lowest two bits
+constexpr uint32_t KTAB_TWO_ROW_MARK = 0xC0000000u;
+__host__ __device__ __forceinline__ bool ktab_two_row_marker(const FmIndex& f, const uint32_t y) {
+    return f.ktab_located == 2u && f.n < KTAB_TWO_ROW_MARK && y >= KTAB_TWO_ROW_MARK;
+}
+
 // match() of one query read through a SymReader; FORWARD consumes left-to-right, COMPLEMENT maps
 // c<4 -> 3-c (nvBowtie's reverse-complement seed search over the forward index).
 template <int BITS, bool BE>
@@ -282,7 +290,7 @@ __host__ __device__ __forceinline__ void fm_match_one(const FmIndex& f, const ui
         }
         if (!has_n) {                                   // an N among them: take the step-by-step path below
             const uint2 r = gather_u2(f.ktab_located ? (const uint2*)((const uint4*)f.ktab + u) : f.ktab + u);
-            x = r.x; y = r.y; s = f.ktab_k;
+            x = r.x; y = ktab_two_row_marker(f, r.y) ? r.x + 1u : r.y; s = f.ktab_k;
         }
     }
     for (; s < len && x <= y; ++s) {
@@ -341,7 +349,7 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
 {
     SymReader<BITS, BE> rd(words);
     uint32_t x = 0, y = f.n, s = 0;
-    uint32_t known_pos = 0u, known_pos2 = 0u; bool have_pos = false, have_two = false;
+    uint32_t known_pos = 0u, known_pos2 = 0u, ctx2 = 0u; bool have_pos = false, have_two = false, two_ctx = false;
     if (MODE == FM_RESUME) { x = ox; y = oy; s = (x == 0u && y == f.n) ? 0u : f.ktab_k; }   // (0, n): deferred before any step (no look-up: an N, a short query)
     if (MODE != FM_RESUME && f.ktab_k && len >= f.ktab_k) {
         uint32_t u = 0; bool has_n = false;
@@ -360,7 +368,9 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
         if (!has_n) {
             if (f.ktab_located) {                       // the entry of a single-row k-mer carries SA[x]: no SA gather below
                 const uint4 e = gather_u4((const uint4*)f.ktab + u);
-                x = e.x; y = e.y; known_pos = e.z; known_pos2 = e.w; have_pos = (e.x == e.y); have_two = (e.y == e.x + 1u);
+                x = e.x; y = e.y; known_pos = e.z; known_pos2 = e.w;
+                if (ktab_two_row_marker(f, y)) { ctx2 = y; y = x + 1u; two_ctx = true; }
+                have_pos = (x == y); have_two = (y == x + 1u);
             } else {
                 const uint2 r = gather_u2(f.ktab + u);
                 x = r.x; y = r.y;
@@ -398,7 +408,19 @@ __host__ __device__ __forceinline__ uint32_t fm_match_locate_one(const FmIndex& 
         // walking the range on; exactly one survivor = the single row the remaining LF steps would have reached, none = empty,
         // both = a genuine repeat of the whole query: that one takes the general path below
         const uint32_t rem = len - s;
-        const bool m0 = prefix_matches(known_pos, rem), m1 = prefix_matches(known_pos2, rem);
+        bool m0, m1;
+        if (two_ctx && rem <= 7u) {
+            // both candidates' preceding symbols came with the entry: no read of the text
+            uint32_t qw = 0u; bool n_left = false;
+            if (BITS == 2 && BE)      qw = be2_window(words, off, rem) >> (32u - 2u * rem);
+            else if (BITS == 4 && BE) qw = be4_window(words, off, rem, n_left) >> (32u - 2u * rem);
+            else for (uint32_t i = 0; i < rem; ++i) { const uint32_t c = rd.get(off + i); n_left |= (c > 3u); qw = (qw << 2) | (c & 3u); }
+            const uint32_t mask = (1u << (2u * rem)) - 1u;
+            m0 = !n_left && known_pos  != 0xFFFFFFFFu && known_pos  >= rem && ((qw ^ ctx2) & mask) == 0u;
+            m1 = !n_left && known_pos2 != 0xFFFFFFFFu && known_pos2 >= rem && ((qw ^ (ctx2 >> 14)) & mask) == 0u;
+        } else {
+            m0 = prefix_matches(known_pos, rem); m1 = prefix_matches(known_pos2, rem);
+        }
         if (!m0 && !m1) return FM_EMPTY;
         if (m0 != m1) { ox = (m0 ? known_pos : known_pos2) - rem; oy = 0xFFFFFFFFu; return FM_LOCATED; }
     }

@@ -142,17 +142,22 @@ fm_ktab16_locate_kernel(const FmIndex f, uint4* __restrict__ tab, uint64_t entri
     else if (e.y == e.x + 1u) { tab[v].z = f.ssa[e.x]; tab[v].w = f.ssa[e.y]; }
 }
 
-// one-row entries of a located table: .w = the (up to) 16 text symbols before SA[x], symbol SA[x]-1 in the lowest two bits
+// one-row entries of a located table: .w = the (up to) 16 text symbols before SA[x], symbol SA[x]-1 in the lowest two bits;
+// two-row entries (index with fewer than 0xC0000000 rows): .y = marker | the 7 symbols before SA[x] | those before SA[x+1] << 14
+__device__ __forceinline__ uint32_t text_before(const uint32_t* __restrict__ text, const uint32_t pos, const uint32_t want)
+{
+    const uint32_t cnt = (pos == 0xFFFFFFFFu) ? 0u : (pos < want ? pos : want);
+    return cnt ? (be2_window(text, pos - cnt, cnt) >> (32u - 2u * cnt)) : 0u;
+}
 __global__ void __launch_bounds__(FM_BLOCKDIM)
-fm_ktab16_context_kernel(const uint32_t* __restrict__ text, uint4* __restrict__ tab, uint64_t entries)
+fm_ktab16_context_kernel(const uint32_t* __restrict__ text, uint4* __restrict__ tab, uint64_t entries, uint32_t n_rows)
 {
     const uint64_t v = (uint64_t)blockIdx.x * FM_BLOCKDIM + threadIdx.x;
     if (v >= entries) return;
     const uint4 e = tab[v];
-    if (e.x != e.y) return;
-    const uint32_t pos = e.z;
-    const uint32_t cnt = (pos == 0xFFFFFFFFu) ? 0u : (pos < 16u ? pos : 16u);
-    tab[v].w = cnt ? (be2_window(text, pos - cnt, cnt) >> (32u - 2u * cnt)) : 0u;
+    if (e.x == e.y) tab[v].w = text_before(text, e.z, 16u);
+    else if (e.y == e.x + 1u && n_rows < KTAB_TWO_ROW_MARK)
+        tab[v].y = KTAB_TWO_ROW_MARK | text_before(text, e.z, 7u) | (text_before(text, e.w, 7u) << 14);
 }
 
 // range sizes as uint64 (filter_inl.h:36-42: 1 + y - x in uint32 arithmetic, widened)
@@ -337,7 +342,7 @@ int nvb_fm_build_ktab_context(const nvb_fm_index* fmi, uint32_t k, const uint32_
     const int r = nvb_fm_build_ktab_located(fmi, k, d_ktab16, stream);
     if (r != NVB_OK) return r;
     const uint64_t entries = 1ull << (2u * k);
-    fm_ktab16_context_kernel<<<(uint32_t)((entries + FM_BLOCKDIM - 1) / FM_BLOCKDIM), FM_BLOCKDIM, 0, as_stream(stream)>>>(d_text, (uint4*)d_ktab16, entries);
+    fm_ktab16_context_kernel<<<(uint32_t)((entries + FM_BLOCKDIM - 1) / FM_BLOCKDIM), FM_BLOCKDIM, 0, as_stream(stream)>>>(d_text, (uint4*)d_ktab16, entries, fmi->length);
     NVB_LAUNCH_CHECK();
     return NVB_OK;
 }

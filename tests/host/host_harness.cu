@@ -51,13 +51,18 @@ void hh_fm_ktab_locate(const uint32_t* ktab8, const uint32_t* full_sa, uint32_t 
     }
 }
 
-// ... + the text context of one-row entries (what nvb_fm_build_ktab_context adds): .w = the up to 16 symbols before SA[x]
-void hh_fm_ktab_context(uint32_t* ktab16, uint32_t k, const uint32_t* text_words) {
+// ... + the text context (what nvb_fm_build_ktab_context adds): one-row entries .w = the up to 16 symbols before SA[x]; two-row entries
+// (n < 0xC0000000) .y = marker | the 7 symbols before SA[x] | those before SA[x+1] << 14
+static uint32_t hh_text_before(const uint32_t* text_words, uint32_t pos, uint32_t want) {
+    const uint32_t cnt = (pos == 0xFFFFFFFFu) ? 0u : (pos < want ? pos : want);
+    return cnt ? (be2_window(text_words, pos - cnt, cnt) >> (32u - 2u * cnt)) : 0u;
+}
+void hh_fm_ktab_context(uint32_t* ktab16, uint32_t k, const uint32_t* text_words, uint32_t n) {
     for (uint64_t v = 0; v < (1ull << (2u * k)); ++v) {
-        if (ktab16[4 * v] != ktab16[4 * v + 1]) continue;
-        const uint32_t pos = ktab16[4 * v + 2];
-        const uint32_t cnt = (pos == 0xFFFFFFFFu) ? 0u : (pos < 16u ? pos : 16u);
-        ktab16[4 * v + 3] = cnt ? (be2_window(text_words, pos - cnt, cnt) >> (32u - 2u * cnt)) : 0u;
+        const uint32_t x = ktab16[4 * v], y = ktab16[4 * v + 1];
+        if (x == y) ktab16[4 * v + 3] = hh_text_before(text_words, ktab16[4 * v + 2], 16u);
+        else if (y == x + 1u && n < KTAB_TWO_ROW_MARK)
+            ktab16[4 * v + 1] = KTAB_TWO_ROW_MARK | hh_text_before(text_words, ktab16[4 * v + 2], 7u) | (hh_text_before(text_words, ktab16[4 * v + 3], 7u) << 14);
     }
 }
 

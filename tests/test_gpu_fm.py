@@ -227,7 +227,17 @@ def test_ktab_gives_identical_ranges(O, k):
     ctx = full.build_ktab(k, located=True, text=tw)
     assert ctx.ktab_located == 2
     c16 = host_u32(ctx.ktab)
-    assert np.array_equal(c16[:, :3], t16[:, :3]) and np.array_equal(c16[~single, 3], t16[~single, 3])
+    assert np.array_equal(c16[:, 0], t16[:, 0]) and np.array_equal(c16[:, 2], t16[:, 2]) and np.array_equal(c16[~single, 3], t16[~single, 3])
+    # two-row entries: y = x + 1 is implied by a marker; the freed bits hold the 7 symbols before SA[x] and before SA[x + 1]
+    assert np.array_equal(c16[~two, 1], t16[~two, 1]) and (c16[two, 1] >> 30 == 3).all()
+    def before(pos, want):
+        cnt = 0 if pos == 0xFFFFFFFF else min(pos, want)
+        v = 0
+        for sym in text[pos - cnt:pos] if cnt else []:
+            v = (v << 2) | int(sym)
+        return v
+    for v in np.flatnonzero(two)[:: max(1, int(two.sum()) // 300)]:
+        assert int(c16[v, 1]) == (0xC0000000 | before(int(c16[v, 2]), 7) | (before(int(c16[v, 3]), 7) << 14)), v
     for v in np.flatnonzero(single)[:: max(1, int(single.sum()) // 500)]:
         pos = int(c16[v, 2])
         cnt = 0 if pos == 0xFFFFFFFF else min(pos, 16)

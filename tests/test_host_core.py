@@ -94,7 +94,12 @@ def test_fm_core(H, O, n):
         full_sa = idx.sa.astype(np.uint32).copy(); full_sa[0] = 0xFFFFFFFF
         ktab16 = np.zeros(4 * 4 ** k, np.uint32)
         H.hh_fm_ktab_locate(_p(ktab), _p(full_sa), C.c_uint32(k), _p(ktab16))
-        for tab, located in ((ktab, 0), (ktab16, 1)):
+        # ... and with the text context packed into one- and two-row entries (ktab_located = 2; two-row entries carry a marker instead of y)
+        ktab_ctx = ktab16.copy()
+        H.hh_fm_ktab_context(_p(ktab_ctx), C.c_uint32(k), _p(pack_symbols(np.concatenate([text, np.zeros(64, np.uint8)]), 2, True)), C.c_uint32(n))
+        two = ktab16[1::4] == ktab16[0::4] + 1
+        assert np.array_equal(ktab_ctx[1::4][two] >> 30, np.full(int(two.sum()), 3, np.uint32)) and np.array_equal(ktab_ctx[1::4][~two], ktab16[1::4][~two])
+        for tab, located in ((ktab, 0), (ktab16, 1), (ktab_ctx, 2)):
             for flags, w in ((0, want), (3, want_rc)):
                 H.hh_fm_match(_p(idx.bwt_occ), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(words), C.c_uint32(2), C.c_uint32(1),
                               _p(offs), _p(lens), C.c_uint32(nq), C.c_uint32(flags), _p(got), _p(tab), C.c_uint32(k), C.c_uint32(located))
@@ -393,7 +398,7 @@ def test_fm_match_locate_shortcut(H, O, n, k, bits):
         # ... and with the text context in one-row entries (ktab_located = 2): the same answers as the located table, field by field
         # (seeds longer than k + 16 still compare against the text)
         ktab_ctx = ktab16.copy()
-        H.hh_fm_ktab_context(_p(ktab_ctx), C.c_uint32(k), _p(gw))
+        H.hh_fm_ktab_context(_p(ktab_ctx), C.c_uint32(k), _p(gw), C.c_uint32(n))
         out_ctx = np.zeros((nq, 3), np.uint32)
         H.hh_fm_match_locate(_p(idx.bwt_occ), _p(full_sa), _p(idx.L2), C.c_uint32(n), C.c_uint32(idx.primary), _p(gw), _p(words), C.c_uint32(bits),
                              C.c_uint32(1), _p(offs), _p(lens), C.c_uint32(nq), _p(out_ctx), _p(ktab_ctx), C.c_uint32(k), C.c_uint32(2))
