@@ -784,7 +784,10 @@ def run_ours(args):
                 "api": "C ABI nvb_pipeline_submit / nvb_pipeline_wait via nvbio_b200.StreamingSeedExtend (pinned host in/out, %d batches in flight: copy-in, "
                        "compute and copy-out streams; wall clock from an empty pipeline to the last result read on the host)" % args.depth,
                 "steps": max(args.steps, 60), "depth": args.depth, "compute_streams": int(os.environ.get("NVB_PIPELINE_COMPUTE_STREAMS", "1")), "sweep": e2e_alt},
-        "gpu_launches": (9 if params.dedup_jobs else 8) * args.steps,      # own kernels per step on the per-read path (the cub scan not counted)
+        # own kernels per step on the per-read path (the cub scan not counted): strings, seed match (+ its second pass when a k-mer table and
+        # the full SA are present), count, read jobs, (shortcut check, scatter: LOCAL with a constant scheme), DP pair kernel, DP generic
+        # kernel, init, reduce, finalize
+        "gpu_launches": ((9 + 2 + (1 if (fmi.ktab_k and fmi.sa_interval == 1 and SEED_LEN > fmi.ktab_k) else 0)) if params.dedup_jobs else 8) * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "pipe_seed_match_kernel (FM-index backward search, %d seeds x %d LF steps)" % (n_seeds, SEED_LEN),
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
