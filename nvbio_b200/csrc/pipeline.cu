@@ -11,6 +11,7 @@
 // reduction: fmmap.cu:365-385.
 #include "fm_core.cuh"
 #include "gotoh_core.cuh"
+#include "pipeline_core.cuh"
 #include <cub/device/device_scan.cuh>
 #include <mutex>
 
@@ -329,20 +330,9 @@ pipe_read_jobs_kernel(const FmIndex f, const PipeGeom g, const uint2* __restrict
     }
 }
 
-// Exact shortcut of the LOCAL extension for reads that lie on their seed's diagonal with (almost) no difference -- most reads of a
-// real run.  With match > 0 > mismatch, gap-open penalties < 0 and gap-extension penalties <= 0:
-//   * an alignment that contains a gap scores at most  G = match * M + max(pattern_gap_open, text_gap_open)  (at most M matched
-//     columns, and a gap costs at least its first base);
-//   * an alignment without a gap lies on ONE band diagonal, and the best of those is the maximum-sum segment of that diagonal's
-//     match / mismatch scores (H along the diagonal with only the diagonal move: h = max(0, h + s)).
-// So if the best segment of the seed's own diagonal scores MORE than G, and no other band diagonal can reach it (match * its number
-// of equal positions stays below), that score is the band's maximum and every cell holding it lies on this diagonal: the DP's result
-// is (best, last row where h == best) -- BestSink keeps the last maximal cell in row-major order (sink_inl.h:39-65).  A read without
-// any difference (score match * M, only reachable in the last row) may tie with other equal diagonals (tandem repeats): the largest
-// one wins.  Such jobs get their result here; the others are compacted into the list the DP kernels run over.  Only full windows
-// (N >= M + band - 1: no pad symbol inside the band) and 2-bit reads qualify.  (A first version that tried all band diagonals for
-// every job cost 0.39 ms per million reads -- 2,250 warp instructions per job -- against the 0.16 ms of DP it saved; now a job that
-// differs too much on the seed's own diagonal leaves after one or two word compares.)
+// Exact shortcut of the LOCAL extension (gapless_job_shortcut, pipeline_core.cuh): jobs whose result it proves get it here; the others
+// are compacted into the list the DP kernels run over.  (Earlier versions of the check: all band diagonals for every job 0.39 ms per
+// million reads, a symbol-by-symbol segment loop 0.29 ms, per-diagonal text reads 0.22 ms; now 0.14 ms.)
 __global__ void __launch_bounds__(256)
 pipe_perfect_jobs_kernel(const PipeGeom g, const int32_t match, const int32_t mismatch, const int32_t max_gap_open, const uint32_t* __restrict__ counts,
                          const uint32_t* __restrict__ str_words, const uint32_t* __restrict__ genome,
@@ -354,80 +344,16 @@ pipe_perfect_jobs_kernel(const PipeGeom g, const int32_t match, const int32_t mi
 {
     __shared__ uint32_t s_warp[8], s_base;
     const uint32_t n = counts[2];
-    // one bit per differing symbol (bit 2k = symbol cnt-1-k) of read[i, i+cnt) against text[t+i, ...)
-    auto diff_bits = [&](const uint32_t po, const uint32_t t, const uint32_t i, const uint32_t cnt) -> uint32_t {
-        const uint32_t x = (be2_window(str_words, po + i, cnt) ^ be2_window(genome, t + i, cnt)) >> (32u - 2u * cnt);
-        return (x | (x >> 1)) & 0x55555555u;
-    };
-    // number of differing symbols on the diagonal starting at text position t, counting stops once it exceeds `limit`
-    auto differences = [&](const uint32_t po, const uint32_t M, const uint32_t t, const uint32_t limit) -> uint32_t {
-        uint32_t mm = 0;
-        for (uint32_t i = 0; i < M && mm <= limit; i += 16u) mm += (uint32_t)__popc(diff_bits(po, t, i, M - i < 16u ? M - i : 16u));
-        return mm;
-    };
-    // differences a gapless alignment may have and still beat every gapped one: match * (M - mm) > match * M + max_gap_open
-    const uint32_t mm_max = (uint32_t)((-max_gap_open + match - 1) / match) - 1u;
     for (uint32_t base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {       // (whole CTAs stay in the loop: barriers below)
         const uint32_t j = base + threadIdx.x;
         bool todo = false;
         uint32_t po = 0, M = 0, to = 0, N = 0;
         if (j < n) {
             po = jp_off[j]; M = jp_len[j]; to = jt_off[j]; N = jt_len[j];
-            todo = true;
-            // the window was cut band/2 before the seed's diagonal (pipe_read_jobs_kernel), so that is where such a read lies; a window
-            // clamped at the text start (to == 0) has it somewhere below: those few take the DP
-            const uint32_t j0 = g.band / 2u;
-            if (M >= 1u && to != 0u && N >= M + g.band - 1u) {
-                // one pass over the seed's diagonal: its differences (at most mm_max, else the DP) and, from the runs of equal symbols
-                // between them, the maximum-sum segment with the LAST end among equals.  (mismatch < 0, so h peaks at the ends of runs;
-                // a symbol-by-symbol version of this loop cost 1,500 warp instructions per job)
-                int32_t h = 0, best = 0; uint32_t end = 0, prev = 0, mm0 = 0;
-                for (uint32_t i = 0; i < M && mm0 <= mm_max; i += 16u) {
-                    const uint32_t cnt = M - i < 16u ? M - i : 16u;
-                    uint32_t d = diff_bits(po, to + j0, i, cnt);
-                    while (d && mm0 <= mm_max) {
-                        const uint32_t bit = 31u - (uint32_t)__clz(d);                 // highest set bit = first differing symbol of the word
-                        const uint32_t p = i + (cnt - 1u - (bit >> 1));
-                        d &= ~(1u << bit);
-                        h += match * (int32_t)(p - prev);
-                        if (h >= best) { best = h; end = p; }
-                        h += mismatch; h = h > 0 ? h : 0;
-                        prev = p + 1u; ++mm0;
-                    }
-                }
-                if (mm0 <= mm_max) {
-                    h += match * (int32_t)(M - prev);
-                    if (h >= best) { best = h; end = M; }
-                }
-                if (mm0 <= mm_max && best > match * (int32_t)M + max_gap_open) {
-                    // Can another band diagonal reach `best`?  Only with at most t differences (match * equal positions bounds its score).
-                    // The first 16 symbols decide that for nearly every diagonal: they are compared against all band offsets from four
-                    // text words held in registers (a full comparison only follows for a diagonal they do not rule out).
-                    const bool perfect = (mm0 == 0u);
-                    const uint32_t t = (uint32_t)((match * (int32_t)M - best) / match);
-                    const uint32_t c16 = M < 16u ? M : 16u;
-                    const uint32_t r0 = be2_window(str_words, po, c16) >> (32u - 2u * c16);
-                    const uint32_t wi = to >> 4, r = to & 15u, wl = (to + N - 1u) >> 4;          // wl: last word holding a window symbol
-                    const uint32_t g0 = genome[wi], g1 = (wi + 1u <= wl) ? genome[wi + 1u] : 0u;
-                    const uint32_t g2 = (wi + 2u <= wl) ? genome[wi + 2u] : 0u, g3 = (wi + 3u <= wl) ? genome[wi + 3u] : 0u;
-                    bool alone = true;
-                    uint32_t jtop = j0;                                                         // largest diagonal without a difference
-                    for (uint32_t jj = 0; jj < g.band; ++jj) {
-                        if (jj == j0) continue;
-                        const uint32_t off = r + jj, idx = off >> 4, sh = 2u * (off & 15u);      // band <= 32: idx <= 2
-                        const uint32_t hi = idx == 0u ? g0 : (idx == 1u ? g1 : g2), lo = idx == 0u ? g1 : (idx == 1u ? g2 : g3);
-                        const uint32_t win = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
-                        const uint32_t x = (win >> (32u - 2u * c16)) ^ r0;
-                        if ((uint32_t)__popc((x | (x >> 1)) & 0x55555555u) > t) continue;
-                        const uint32_t full = differences(po, M, to + jj, t);
-                        if (full > t) continue;
-                        if (perfect) { if (jj > jtop) jtop = jj; }                              // (full == 0: another diagonal without a difference)
-                        else alone = false;
-                    }
-                    if (perfect)    { job_score[j] = best; job_sink[j] = make_uint2(M + jtop, M); todo = false; }
-                    else if (alone) { job_score[j] = best; job_sink[j] = make_uint2(end + j0, end); todo = false; }
-                }
-            }
+            int32_t score = 0; uint32_t sx = 0, sy = 0;
+            if (gapless_job_shortcut(str_words, genome, po, M, to, N, g.band, match, mismatch, max_gap_open, score, sx, sy)) {
+                job_score[j] = score; job_sink[j] = make_uint2(sx, sy);
+            } else todo = true;
         }
         // compaction of the others: one atomic per CTA (same-address atomics serialise, ~2.4 ns each on this part)
         const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;

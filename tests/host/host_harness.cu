@@ -5,6 +5,7 @@
 #include "../../nvbio_b200/csrc/fm_core.cuh"
 #include "../../nvbio_b200/csrc/gotoh_core.cuh"
 #include "../../nvbio_b200/csrc/gotoh_full_core.cuh"
+#include "../../nvbio_b200/csrc/pipeline_core.cuh"
 #include <vector>
 
 using namespace nvb;
@@ -125,6 +126,17 @@ uint32_t hh_fm_match_locate_split(const uint32_t* bwt_occ, const uint32_t* full_
         out[3 * i] = st; out[3 * i + 1] = x; out[3 * i + 2] = y;
     }
     return deferred;
+}
+
+// gapless_job_shortcut over n jobs: solved[a] = 1 and (score[a], sink_xy[2a..]) when the routine proves the LOCAL band result
+void hh_gapless_job_shortcut(const uint32_t* str_words, const uint32_t* genome_words, const uint32_t* po, const uint32_t* M, const uint32_t* to,
+                             const uint32_t* N, uint32_t n, uint32_t band, int32_t match, int32_t mismatch, int32_t max_gap_open,
+                             uint8_t* solved, int32_t* score, uint32_t* sink_xy) {
+    for (uint32_t a = 0; a < n; ++a) {
+        int32_t sc = 0; uint32_t sx = 0, sy = 0;
+        solved[a] = gapless_job_shortcut(str_words, genome_words, po[a], M[a], to[a], N[a], band, match, mismatch, max_gap_open, sc, sx, sy) ? 1 : 0;
+        score[a] = sc; sink_xy[2 * a] = sx; sink_xy[2 * a + 1] = sy;
+    }
 }
 
 // generic rank dictionary (dict_rank<W,I>): out[q] = rank(i[q], c[q]), all as uint64

@@ -795,3 +795,56 @@ def test_gotoh_window_quality_table(H, O):
             if ms is None:
                 ok = whole[3].astype(bool)
                 assert np.array_equal(sh["score"][ok], whole[0][ok]) and np.array_equal(sh["sx"][ok], whole[1][ok])
+
+@pytest.mark.parametrize("band", [31, 15, 8])
+def test_gapless_job_shortcut(H, O, band):
+    """gapless_job_shortcut (the exact shortcut of the LOCAL extension in nvb_seed_extend): whenever it claims a job, (score, sink) are
+    exactly what the oracle's banded DP (pinned to the reference's) returns -- reads with 0..4 substitutions at random and at chosen
+    places (the ends, next to the ends, adjacent), reads with an indel (never provable), tandem repeats of period 1, 2, 3, 7 and 40 (other
+    band diagonals as good as the seed's), short and ragged reads, windows longer than the band needs, four schemes"""
+    rng = np.random.default_rng(900 + band)
+    n_txt = 60_000
+    text = rng.integers(0, 4, n_txt).astype(np.uint8)
+    for st, period in ((5_000, 1), (8_000, 2), (11_000, 3), (14_000, 7), (20_000, 40)):
+        text[st:st + 2_500] = np.tile(text[st:st + period], 2_500 // period + 1)[:2_500]
+    n = 3_000
+    stride = 160
+    M = np.full(n, 150, np.uint32); M[:600] = rng.integers(1, 151, 600)
+    pos = rng.integers(100, n_txt - 400, n)
+    pos[600:1500] = rng.integers(5_000, 22_000, 900)                    # inside / across the repeats
+    reads = np.zeros((n, stride), np.uint8)
+    places = [(0,), (1,), (-1,), (-2,), (0, 1), (-2, -1), (0, -1), (1, -2), (2, 3), (70,), (70, 71), (10, -10), (0, 1, 2), (-3, -2, -1), (3, 70)]
+    for a in range(n):
+        m = int(M[a]); r = text[pos[a]:pos[a] + m].copy()
+        kind = a % 7
+        if kind in (1, 2, 3):                                           # 1..4 random substitutions
+            for q in rng.integers(0, m, rng.integers(1, 5)):
+                r[q] = (r[q] + 1 + rng.integers(0, 3)) % 4
+        elif kind == 4:                                                 # chosen places
+            for q in places[(a // 7) % len(places)]:
+                if -m <= q < m:
+                    r[q] = (r[q] + 1 + (a % 3)) % 4
+        elif kind == 5 and m > 20:                                      # an indel
+            cut = int(rng.integers(5, m - 5))
+            r = np.concatenate([r[:cut], r[cut + 1:], text[pos[a] + m:pos[a] + m + 1]]) if a % 2 else np.concatenate([r[:cut], [(r[cut] + 1) % 4], r[cut:m - 1]])
+        reads[a, :m] = r
+    to = (pos - band // 2).astype(np.uint32)
+    N = (M + band - 1 + (np.arange(n) % 3) * 5).astype(np.uint32)       # some windows longer than needed
+    N[5::50] = M[5::50] + band - 2                                      # ... and a few too short: never claimed
+    po = (np.arange(n) * stride).astype(np.uint32)
+    sw = np.concatenate([pack_symbols(reads.reshape(-1), 2, True), np.zeros(2, np.uint32)])
+    gw = np.concatenate([pack_symbols(np.concatenate([text, np.zeros(64, np.uint8)]), 2, True), np.zeros(2, np.uint32)])
+    total = 0
+    for scheme in ((2, -2, -5, -3), (1, -4, -6, -1), (2, -6, -8, -3), (3, -1, -2, -2)):
+        ws, wx, wy, _ = O.banded_gotoh(band, 1, scheme, reads.reshape(-1), po, M, text, to, N)
+        solved = np.zeros(n, np.uint8); score = np.zeros(n, np.int32); sink = np.zeros((n, 2), np.uint32)
+        H.hh_gapless_job_shortcut(_p(sw), _p(gw), _p(po), _p(M), _p(to), _p(N), C.c_uint32(n), C.c_uint32(band), C.c_int32(scheme[0]), C.c_int32(scheme[1]),
+                                  C.c_int32(scheme[2]), _p(solved), _p(score), _p(sink))
+        ok = solved.astype(bool)
+        assert np.array_equal(score[ok], ws[ok]) and np.array_equal(sink[ok, 0], wx[ok]) and np.array_equal(sink[ok, 1], wy[ok]), (band, scheme)
+        assert not ok[N < M + band - 1].any()
+        exact = (np.arange(n) % 7 == 0) | (np.arange(n) % 7 == 6)
+        assert ok[exact & (N >= M + band - 1)].all()                     # a read without a difference is always resolved
+        total += int(ok.sum())
+        print("gapless_job_shortcut band %d scheme %s: %d of %d jobs claimed" % (band, scheme, int(ok.sum()), n))
+    assert total > 4 * n // 4
