@@ -21,7 +21,7 @@ def _p(a):
 
 @pytest.fixture(scope="module")
 def H():
-    deps = [SRC] + [os.path.join(HERE, "..", "nvbio_b200", "csrc", f) for f in ("fm_core.cuh", "gotoh_core.cuh", "gotoh_full_core.cuh", "common.cuh")]
+    deps = [SRC] + [os.path.join(HERE, "..", "nvbio_b200", "csrc", f) for f in ("fm_core.cuh", "gotoh_core.cuh", "gotoh_full_core.cuh", "pipeline_core.cuh", "common.cuh")]
     so, extra = SO, []
     if os.environ.get("NVB_HOST_HARNESS_ASAN"):
         # AddressSanitizer + UBSan build of the very same per-thread routines: run the file as
@@ -30,8 +30,9 @@ def H():
         extra = ["-g", "-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fsanitize=undefined", "-Xcompiler", "-fno-omit-frame-pointer",
                  "-Xcompiler", "-fno-sanitize-recover=undefined"]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        env = dict(os.environ); env.pop("LD_PRELOAD", None)            # (the sanitizer run preloads libasan: not into the compiler)
         subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
-                               "-Wno-deprecated-declarations", "-Xcompiler", "-fPIC", "-shared", "-o", so, SRC] + extra)
+                               "-Wno-deprecated-declarations", "-Xcompiler", "-fPIC", "-shared", "-o", so, SRC] + extra, env=env)
     return C.CDLL(so)
 
 
