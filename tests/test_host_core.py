@@ -800,7 +800,7 @@ def test_gotoh_window_quality_table(H, O):
 @pytest.mark.parametrize("band", [31, 15, 8])
 def test_gapless_job_shortcut(H, O, band):
     """gapless_job_shortcut (the exact shortcut of the LOCAL extension in nvb_seed_extend): whenever it claims a job, (score, sink) are
-    exactly what the oracle's banded DP (pinned to the reference's) returns -- reads with 0..4 substitutions at random and at chosen
+    exactly what the oracle's banded DP and the reference's own aln::banded_alignment_score<BAND> (oracle/_ref, bands 31 and 15) return -- reads with 0..4 substitutions at random and at chosen
     places (the ends, next to the ends, adjacent), reads with an indel (never provable), tandem repeats of period 1, 2, 3, 7 and 40 (other
     band diagonals as good as the seed's), short and ragged reads, windows longer than the band needs, four schemes"""
     rng = np.random.default_rng(900 + band)
@@ -838,6 +838,11 @@ def test_gapless_job_shortcut(H, O, band):
     total = 0
     for scheme in ((2, -2, -5, -3), (1, -4, -6, -1), (2, -6, -8, -3), (3, -1, -2, -2)):
         ws, wx, wy, _ = O.banded_gotoh(band, 1, scheme, reads.reshape(-1), po, M, text, to, N)
+        if band in (31, 15) and orc.Ref.available():
+            # ... and the reference's own aln::banded_alignment_score<BAND> (oracle/_ref) says the same as the restatement
+            rs, rx, ry, _ = orc.Ref().banded_gotoh(band, 1, scheme, reads.reshape(-1), po, M, text, to, N)
+            full = N >= M + band - 1                                    # (shorter windows: the reference reads past the text, undefined)
+            assert np.array_equal(rs[full], ws[full]) and np.array_equal(rx[full], wx[full]) and np.array_equal(ry[full], wy[full])
         solved = np.zeros(n, np.uint8); score = np.zeros(n, np.int32); sink = np.zeros((n, 2), np.uint32)
         H.hh_gapless_job_shortcut(_p(sw), _p(gw), _p(po), _p(M), _p(to), _p(N), C.c_uint32(n), C.c_uint32(band), C.c_int32(scheme[0]), C.c_int32(scheme[1]),
                                   C.c_int32(scheme[2]), _p(solved), _p(score), _p(sink))
